@@ -1,0 +1,105 @@
+/*
+ * isfusion_b200 — C ABI of the B200-native IS-Fusion fusion-neck hot path.
+ *
+ * Conventions: plain pointers + sizes, no torch types; every
+ * pointer is DEVICE memory unless marked "host"; `stream` is a cudaStream_t
+ * passed as void*; functions enqueue on that stream and never synchronise the
+ * device; no hidden allocation — scratch memory comes from the caller through
+ * (`workspace`, `ws_bytes`), sized by the matching *_workspace_size call;
+ * data-dependent output counts are written to a device int the caller reads
+ * when (and if) it needs them.  Return value: 0 = ISF_OK, otherwise an error
+ * code; isf_last_error() gives the message of the calling thread's last error.
+ * Each entry point cites the reference interface it replaces (file:line under
+ * the reference checkout yinjunbo/IS-Fusion @ 86c882a).
+ */
+#ifndef ISFUSION_B200_H_
+#define ISFUSION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISF_OK 0
+#define ISF_ERR_INVALID 1
+#define ISF_ERR_WORKSPACE 2
+#define ISF_ERR_CUDA 3
+#define ISF_ERR_UNSUPPORTED 4
+
+#define ISF_REDUCE_SUM 0
+#define ISF_REDUCE_MEAN 1
+#define ISF_REDUCE_MAX 2
+
+/* ---- library ---------------------------------------------------------------- */
+int isf_version(void);
+const char* isf_last_error(void);
+/* number of kernels this library has launched since the last reset (bench.py gpu_launches) */
+unsigned long long isf_launch_count(int reset);
+
+/* ---- a1: dynamic voxelization -------------------------------------------------
+ * replaces voxel_layer.dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3)
+ *   mmdet3d/ops/voxel/src/voxelization.cpp:8, voxelization.h:83-95,
+ *   kernel voxelization_cuda.cu:24-61 (launch :485-528), CPU voxelization_cpu.cpp:7-43.
+ * points [n,nfeat] fp32 (xyz first), coors [n,3] int32 (z,y,x).  voxel_size[3] and
+ * coors_range[6] are HOST arrays.  cpu_semantics=0 reproduces the CUDA kernel's partial
+ * -1 rows ((-1,0,0) / (-1,-1,0) / (-1,-1,-1)), 1 writes (-1,-1,-1) like the CPU path. */
+int isf_dynamic_voxelize(const float* points, int n, int nfeat, const float* voxel_size,
+                         const float* coors_range, int* coors, int cpu_semantics, void* stream);
+
+/* ---- a2: dynamic scatter (per-voxel mean / max / sum) -------------------------
+ * replaces voxel_layer.dynamic_point_to_voxel_forward(feats, coors, reduce_type)
+ *   mmdet3d/ops/voxel/src/voxelization.h:108-120, scatter_points_cuda.cu:183-239.
+ * feats [n,c] fp32, coors [n,ndim] int32 (ndim 3 or 4).  dims (HOST, may be NULL) = exclusive
+ * upper bound of every coordinate column; NULL assumes < 2^21 (ndim 3) / < 2^15 (ndim 4).
+ * Outputs are caller-allocated with capacity n rows: reduced [n,c], out_coors [n,ndim]
+ * (sorted-unique order, as at::unique_dim), coors_map [n] (-1 for rows with a negative
+ * coordinate), reduce_count [n]; *num_voxels_dev receives the number of valid rows. */
+int isf_dynamic_scatter_workspace_size(int n, size_t* bytes);
+int isf_dynamic_point_to_voxel_forward(const float* feats, const int* coors, int n, int c, int ndim,
+                                       const int* dims, int reduce_type, float* reduced, int* out_coors,
+                                       int* coors_map, int* reduce_count, int* num_voxels_dev,
+                                       void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- K7: rank inside a group --------------------------------------------------
+ * replaces ingroup_indices.forward(group_inds, out_inds)
+ *   mmdet3d/ops/TorchEx/torchex/src/ingroup_inds/ingroup_inds.cpp:28-54, kernel :17-30.
+ * group_inds [n] int64 in [0, 2^key_bits); out_inds[i] = stable rank of i inside its group
+ * (the reference hands ranks out in atomic arrival order; any bijection is valid). Uses the
+ * workspace size of isf_dynamic_scatter_workspace_size(n). */
+int isf_ingroup_indices(const long long* group_inds, int n, int key_bits, long long* out_inds,
+                        void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a5: deterministic hard voxelization (pillars) ----------------------------
+ * replaces voxel_layer.hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size,
+ *   coors_range, max_points, max_voxels, NDim, deterministic=True) -> voxel_num
+ *   mmdet3d/ops/voxel/src/voxelization.h:58-81, voxelization_cuda.cu:231-373,
+ *   voxelization_cpu.cpp:45-144.
+ * voxels [max_voxels,max_points,nfeat] fp32, coors [max_voxels,3], num_points_per_voxel
+ * [max_voxels]: rows < voxel_num are fully written (zero padded), other rows untouched. */
+int isf_hard_voxelize_workspace_size(int n, size_t* bytes);
+int isf_hard_voxelize(const float* points, int n, int nfeat, const float* voxel_size,
+                      const float* coors_range, int max_points, int max_voxels, float* voxels, int* coors,
+                      int* num_points_per_voxel, int* voxel_num_dev, void* workspace, size_t ws_bytes,
+                      void* stream);
+
+/* ---- a3: fused DynamicVFE ------------------------------------------------------
+ * replaces DynamicVFE.forward (mmdet3d/models/voxel_encoders/voxel_encoder.py:452-547) with
+ * its three DynamicScatter calls and two map_voxel_center_to_point canvases (:410-450), eval
+ * mode (BN folded into scale/shift by the caller).  points [n,nfeat>=5], coors [n,4] (b,z,y,x)
+ * all in range, dims[4] HOST = (B,Z,Y,X).  voxel_size[3], offsets[3] (= v/2 + range_min) HOST.
+ * w1 [64,11], w2 [64,128] fp32 row-major (nn.Linear layout).  Outputs (capacity n rows):
+ * voxel_feats_f32 and/or voxel_feats_f16 [n,64] (either may be NULL), voxel_coors [n,4]. */
+int isf_dynamic_vfe_workspace_size(int n, size_t* bytes);
+int isf_dynamic_vfe_forward(const float* points, const int* coors, int n, int nfeat, const int* dims,
+                            const float* voxel_size, const float* offsets, const float* w1,
+                            const float* scale1, const float* shift1, const float* w2, const float* scale2,
+                            const float* shift2, int in_ch, int feat_ch, float* voxel_feats_f32,
+                            void* voxel_feats_f16, int* voxel_coors, int* num_voxels_dev, void* workspace,
+                            size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISFUSION_B200_H_ */

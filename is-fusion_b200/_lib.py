@@ -1,0 +1,80 @@
+"""ctypes binding of libisfusion_b200.so (the C-ABI in include/isfusion_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails the
+caller gets an exception.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libisfusion_b200.so')
+_lib = None
+
+
+class IsfError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IsfError('%s not found: build it with `python is-fusion_b200/build.py` '
+                           '(there is no CPU fallback)' % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.isf_last_error.restype = ctypes.c_char_p
+        _lib.isf_launch_count.restype = ctypes.c_ulonglong
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise IsfError('isfusion_b200 error %d: %s' % (rc, lib().isf_last_error().decode()))
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_f32(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def host_i32(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise IsfError('expected a CUDA tensor (the product path has no CPU fallback)')
+        if not t.is_contiguous():
+            raise IsfError('expected a contiguous tensor')
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    """grow-only scratch buffer per device (owned by the torch caching allocator)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def launch_count(reset=False):
+    return int(lib().isf_launch_count(1 if reset else 0))

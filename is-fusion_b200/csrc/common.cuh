@@ -1,0 +1,64 @@
+// Shared helpers for the isfusion_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define ISF_OK 0
+#define ISF_ERR_INVALID 1      // bad argument (null pointer, bad size, unsupported shape)
+#define ISF_ERR_WORKSPACE 2    // workspace too small
+#define ISF_ERR_CUDA 3         // CUDA runtime error (see isf_last_error)
+#define ISF_ERR_UNSUPPORTED 4
+
+extern "C" void isf_set_error(const char* fmt, ...);
+
+#define ISF_CHECK_ARG(cond)                                                       \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      isf_set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond);    \
+      return ISF_ERR_INVALID;                                                     \
+    }                                                                             \
+  } while (0)
+
+#define ISF_CUDA(expr)                                                            \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      isf_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                    cudaGetErrorString(_e));                                      \
+      return ISF_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+#define ISF_LAUNCH_CHECK() ISF_CUDA(cudaGetLastError())
+
+static inline size_t isf_align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-owned workspace (no hidden allocation in the library).
+struct IsfArena {
+  char* base;
+  size_t cap;
+  size_t off;
+  bool ok;
+  IsfArena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), ok(true) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = isf_align_up(count * sizeof(T));
+    if (base == nullptr) {  // sizing pass
+      off += bytes;
+      return nullptr;
+    }
+    if (off + bytes > cap) {
+      ok = false;
+      return nullptr;
+    }
+    T* r = (T*)(base + off);
+    off += bytes;
+    return r;
+  }
+};
+
+__host__ __device__ inline int isf_cdiv(int a, int b) { return (a + b - 1) / b; }
+
+constexpr int ISF_NUM_SMS = 148;  // B200

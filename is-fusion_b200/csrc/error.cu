@@ -1,0 +1,25 @@
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+extern "C" void isf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* isf_last_error(void) { return g_err; }
+
+extern "C" int isf_version(void) { return 100; }
+
+// Counts kernels launched by this library since the last reset (bench.py "gpu_launches").
+static unsigned long long g_launches = 0;
+extern "C" void isf_count_launch(int n) { g_launches += (unsigned long long)n; }
+extern "C" unsigned long long isf_launch_count(int reset) {
+  unsigned long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}

@@ -1,0 +1,100 @@
+"""DynamicVFE (ref: mmdet3d/models/voxel_encoders/voxel_encoder.py:287-547, utils.py:107-144) as ONE fused
+CUDA op: point grouping by a radix sort of the (b,z,y,x) key, then a warp per voxel computes the cluster /
+voxel-centre offsets, both Linear+BN+ReLU layers and both voxel-max reductions on chip.  The three
+DynamicScatter passes and the two 663 MB `map_voxel_center_to_point` canvases of the reference disappear.
+Same constructor, state_dict keys (vfe_layers.{i}.linear.weight / .norm.*) and (voxel_feats, voxel_coors)
+return contract; voxel order = the reference's sorted-unique (b,z,y,x) order.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .registry import VOXEL_ENCODERS, build_norm_layer
+
+
+class DynamicVFELayer(nn.Module):
+    def __init__(self, in_channels, out_channels, norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01)):
+        super().__init__()
+        self.norm = build_norm_layer(norm_cfg, out_channels)[1]
+        self.linear = nn.Linear(in_channels, out_channels, bias=False)
+
+
+@VOXEL_ENCODERS.register_module()
+class DynamicVFE(nn.Module):
+
+    def __init__(self, in_channels=4, feat_channels=[], with_distance=False, with_cluster_center=False,
+                 with_voxel_center=False, voxel_size=(0.2, 0.2, 4), point_cloud_range=(0, -40, -3, 70.4, 40, 1),
+                 norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), mode='max', fusion_layer=None,
+                 pointaugmenting=False, fusion_channels=None, return_point_feats=False, out_dtype=torch.float16):
+        super().__init__()
+        if not (with_cluster_center and with_voxel_center and not with_distance and mode == 'max'
+                and fusion_layer is None and not return_point_feats and len(feat_channels) == 2):
+            raise L.IsfError('DynamicVFE: only the isfusion_0075voxel.py configuration is built '
+                             '(cluster+voxel centre, two layers, max pooling)')
+        in_channels += 6
+        self.in_channels = in_channels
+        self.feat_channels = list(feat_channels)
+        self.vx, self.vy, self.vz = voxel_size
+        self.x_offset = self.vx / 2 + point_cloud_range[0]
+        self.y_offset = self.vy / 2 + point_cloud_range[1]
+        self.z_offset = self.vz / 2 + point_cloud_range[2]
+        self.point_cloud_range = point_cloud_range
+        self.grid = [round((point_cloud_range[5] - point_cloud_range[2]) / self.vz),
+                     round((point_cloud_range[4] - point_cloud_range[1]) / self.vy),
+                     round((point_cloud_range[3] - point_cloud_range[0]) / self.vx)]  # (Z, Y, X)
+        chans = [in_channels] + self.feat_channels
+        self.vfe_layers = nn.ModuleList(
+            [DynamicVFELayer(chans[i] * (2 if i > 0 else 1), chans[i + 1], norm_cfg) for i in range(2)])
+        self.out_dtype = out_dtype
+        self._packed = None
+
+    def _pack(self, device):
+        """fold eval-mode BN into fp32 scale/shift (done once; invalidated by train())."""
+        if self._packed is None or self._packed[0].device != device:
+            out = []
+            for layer in self.vfe_layers:
+                bn = layer.norm
+                scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+                shift = (bn.bias - bn.running_mean * scale).float()
+                out += [layer.linear.weight.detach().float().contiguous(), scale.detach().contiguous(),
+                        shift.detach().contiguous()]
+            self._packed = [t.to(device) for t in out]
+        return self._packed
+
+    def train(self, mode=True):
+        self._packed = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    @torch.no_grad()
+    def forward(self, features, coors, points=None, img_feats=None, img_metas=None, batch_size=None, **kwargs):
+        """features [N,5] fp32 points, coors [N,4] int32 (b,z,y,x), all in range ->
+        (voxel_feats [V,64], voxel_coors [V,4] int32)."""
+        if self.training:
+            raise L.IsfError('DynamicVFE: the fused CUDA path implements eval-mode BN only')
+        L.require_cuda(features, coors)
+        n = features.size(0)
+        dev = features.device
+        if batch_size is None:
+            batch_size = int(coors[-1, 0].item()) + 1        # same host read as isfusion.py:110
+        w1, s1, b1, w2, s2, b2 = self._pack(dev)
+        ws_bytes = ctypes.c_size_t(0)
+        L.check(L.lib().isf_dynamic_vfe_workspace_size(n, ctypes.byref(ws_bytes)))
+        ws = L.workspace(ws_bytes.value, dev)
+        f16 = self.out_dtype == torch.float16
+        feats = torch.empty((n, self.feat_channels[-1]), dtype=self.out_dtype, device=dev)
+        vcoors = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        nv = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.check(L.lib().isf_dynamic_vfe_forward(
+            L.ptr(features), L.ptr(coors), n, features.size(1), L.host_i32([batch_size] + self.grid),
+            L.host_f32([self.vx, self.vy, self.vz]), L.host_f32([self.x_offset, self.y_offset, self.z_offset]),
+            L.ptr(w1), L.ptr(s1), L.ptr(b1), L.ptr(w2), L.ptr(s2), L.ptr(b2), self.in_channels,
+            self.feat_channels[-1], L.ptr(None if f16 else feats), L.ptr(feats if f16 else None), L.ptr(vcoors),
+            L.ptr(nv), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        v = int(nv.item())
+        return feats[:v], vcoors[:v]

@@ -1,0 +1,211 @@
+"""Voxelization / DynamicScatter / ingroup_indices operators.
+
+Mirrors the reference operator API (mmdet3d/ops/voxel/voxelize.py, scatter_points.py,
+voxel_layer.* pybind functions voxelization.cpp:6-11, and ingroup_indices.forward
+TorchEx/.../ingroup_inds.cpp:28-54) on top of the C-ABI library.
+"""
+import ctypes
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.nn.modules.utils import _pair
+
+from . import _lib as L
+
+_REDUCE = {'sum': 0, 'mean': 1, 'max': 2}
+
+
+def dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3):
+    """ref: voxel_layer.dynamic_voxelize (voxelization.h:83-95). Fills `coors` [N,3] int32 in place."""
+    assert NDim == 3
+    L.require_cuda(points, coors)
+    if points.dtype != torch.float32 or coors.dtype != torch.int32:
+        raise L.IsfError('dynamic_voxelize: points must be float32 and coors int32')
+    L.check(L.lib().isf_dynamic_voxelize(L.ptr(points), points.size(0), points.size(1), L.host_f32(voxel_size),
+                                         L.host_f32(coors_range), L.ptr(coors), 0, L.stream()))
+
+
+def hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors_range, max_points, max_voxels,
+                  NDim=3, deterministic=True):
+    """ref: voxel_layer.hard_voxelize (voxelization.h:58-81) -> voxel_num (host int, one D2H read as in
+    voxelization_cuda.cu:369-372).  Always deterministic."""
+    assert NDim == 3
+    L.require_cuda(points, voxels, coors, num_points_per_voxel)
+    n = points.size(0)
+    ws_bytes = ctypes.c_size_t(0)
+    L.check(L.lib().isf_hard_voxelize_workspace_size(n, ctypes.byref(ws_bytes)))
+    ws = L.workspace(ws_bytes.value, points.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=points.device)
+    L.check(L.lib().isf_hard_voxelize(L.ptr(points), n, points.size(1), L.host_f32(voxel_size),
+                                      L.host_f32(coors_range), int(max_points), int(max_voxels), L.ptr(voxels),
+                                      L.ptr(coors), L.ptr(num_points_per_voxel), L.ptr(cnt), L.ptr(ws),
+                                      ctypes.c_size_t(ws.numel()), L.stream()))
+    return int(cnt.item())
+
+
+def dynamic_point_to_voxel_forward(feats, coors, reduce_type='max', dims=None):
+    """ref: voxel_layer.dynamic_point_to_voxel_forward (voxelization.h:108-120) ->
+    [reduced_feats, out_coors, coors_map int32[N], reduce_count int32[V]] (sorted-unique order)."""
+    L.require_cuda(feats, coors)
+    n, c = feats.shape
+    ndim = coors.size(1)
+    if n == 0:  # scatter_points_cuda.cu:192-196
+        return [feats.clone().detach(), coors.clone().detach(),
+                coors.new_empty((0,), dtype=torch.int32), coors.new_empty((0,), dtype=torch.int32)]
+    if feats.dtype != torch.float32 or coors.dtype != torch.int32:
+        raise L.IsfError('dynamic_point_to_voxel_forward: feats must be float32 and coors int32')
+    dev = feats.device
+    ws_bytes = ctypes.c_size_t(0)
+    L.check(L.lib().isf_dynamic_scatter_workspace_size(n, ctypes.byref(ws_bytes)))
+    ws = L.workspace(ws_bytes.value, dev)
+    reduced = torch.empty((n, c), dtype=torch.float32, device=dev)
+    out_coors = torch.empty((n, ndim), dtype=torch.int32, device=dev)
+    cmap = torch.empty((n,), dtype=torch.int32, device=dev)
+    rcount = torch.empty((n,), dtype=torch.int32, device=dev)
+    nv = torch.zeros(1, dtype=torch.int32, device=dev)
+    if dims is None:
+        dims = [int(v) + 1 for v in coors.max(dim=0).values.clamp(min=0).tolist()]
+    L.check(L.lib().isf_dynamic_point_to_voxel_forward(
+        L.ptr(feats), L.ptr(coors), n, c, ndim, L.host_i32(dims), _REDUCE[reduce_type], L.ptr(reduced),
+        L.ptr(out_coors), L.ptr(cmap), L.ptr(rcount), L.ptr(nv), L.ptr(ws), ctypes.c_size_t(ws.numel()),
+        L.stream()))
+    v = int(nv.item())
+    return [reduced[:v], out_coors[:v], cmap, rcount[:v]]
+
+
+def ingroup_indices(group_inds):
+    """ref: IngroupIndicesFunction (mmdet3d/ops/sst/sst_ops.py:199-217): rank of each element in its group."""
+    L.require_cuda(group_inds)
+    assert group_inds.dtype == torch.int64
+    n = group_inds.numel()
+    out = torch.zeros_like(group_inds) - 1
+    if n == 0:
+        return out
+    ws_bytes = ctypes.c_size_t(0)
+    L.check(L.lib().isf_dynamic_scatter_workspace_size(n, ctypes.byref(ws_bytes)))
+    ws = L.workspace(ws_bytes.value, group_inds.device)
+    bits = max(1, int(group_inds.max().item()).bit_length())
+    L.check(L.lib().isf_ingroup_indices(L.ptr(group_inds), n, bits, L.ptr(out), L.ptr(ws),
+                                        ctypes.c_size_t(ws.numel()), L.stream()))
+    return out
+
+
+class _Voxelization(Function):
+    """ref: mmdet3d/ops/voxel/voxelize.py:10-70."""
+
+    @staticmethod
+    def forward(ctx, points, voxel_size, coors_range, max_points=35, max_voxels=20000, deterministic=True):
+        if max_points == -1 or max_voxels == -1:
+            coors = points.new_zeros(size=(points.size(0), 3), dtype=torch.int)
+            dynamic_voxelize(points, coors, voxel_size, coors_range, 3)
+            return coors
+        voxels = points.new_zeros(size=(max_voxels, max_points, points.size(1)))
+        coors = points.new_zeros(size=(max_voxels, 3), dtype=torch.int)
+        num_points_per_voxel = points.new_zeros(size=(max_voxels,), dtype=torch.int)
+        voxel_num = hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors_range,
+                                  max_points, max_voxels, 3, deterministic)
+        return voxels[:voxel_num], coors[:voxel_num], num_points_per_voxel[:voxel_num]
+
+
+voxelization = _Voxelization.apply
+
+
+class Voxelization(nn.Module):
+    """ref: mmdet3d/ops/voxel/voxelize.py:77-148 (same constructor / forward contract)."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000, deterministic=True):
+        super().__init__()
+        self.voxel_size = voxel_size
+        self.point_cloud_range = point_cloud_range
+        self.max_num_points = max_num_points
+        self.max_voxels = max_voxels if isinstance(max_voxels, tuple) else _pair(max_voxels)
+        self.deterministic = deterministic
+        pcr = torch.tensor(point_cloud_range, dtype=torch.float32)
+        vs = torch.tensor(voxel_size, dtype=torch.float32)
+        grid_size = torch.round((pcr[3:] - pcr[:3]) / vs).long()
+        self.grid_size = grid_size
+        self.pcd_shape = [*grid_size[:2], 1][::-1]
+
+    def forward(self, input):
+        max_voxels = self.max_voxels[0] if self.training else self.max_voxels[1]
+        return voxelization(input, self.voxel_size, self.point_cloud_range, self.max_num_points, max_voxels,
+                            self.deterministic)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(voxel_size={self.voxel_size}, point_cloud_range='
+                f'{self.point_cloud_range}, max_num_points={self.max_num_points}, max_voxels={self.max_voxels}, '
+                f'deterministic={self.deterministic})')
+
+
+class _dynamic_scatter(Function):
+    """ref: mmdet3d/ops/voxel/scatter_points.py:9-46.  Backward (K3b) follows
+    scatter_points_cuda.cu:105-179: mean/sum spread grad/count, max routes the gradient to the
+    lowest-index arg-max point of every (voxel, channel)."""
+
+    @staticmethod
+    def forward(ctx, feats, coors, reduce_type='max'):
+        voxel_feats, voxel_coors, point2voxel_map, voxel_points_count = dynamic_point_to_voxel_forward(
+            feats, coors, reduce_type)
+        ctx.reduce_type = reduce_type
+        ctx.save_for_backward(feats, voxel_feats, point2voxel_map, voxel_points_count)
+        ctx.mark_non_differentiable(voxel_coors)
+        return voxel_feats, voxel_coors
+
+    @staticmethod
+    def backward(ctx, grad_voxel_feats, grad_voxel_coors=None):
+        feats, voxel_feats, p2v, count = ctx.saved_tensors
+        grad_feats = torch.zeros_like(feats)
+        valid = p2v >= 0
+        idx = p2v.clamp(min=0).long()
+        g = grad_voxel_feats.contiguous()
+        if ctx.reduce_type in ('mean', 'sum'):
+            gp = g[idx]
+            if ctx.reduce_type == 'mean':
+                gp = gp / count[idx].unsqueeze(-1).to(gp.dtype)
+            grad_feats = torch.where(valid.unsqueeze(-1), gp, grad_feats)
+        else:
+            n, c = feats.shape
+            is_max = (feats == voxel_feats[idx]) & valid.unsqueeze(-1)
+            pidx = torch.arange(n, device=feats.device).unsqueeze(-1).expand(n, c)
+            cand = torch.where(is_max, pidx, torch.full_like(pidx, n))
+            first = torch.full((voxel_feats.size(0), c), n, dtype=torch.long, device=feats.device)
+            first.scatter_reduce_(0, idx.unsqueeze(-1).expand(n, c), cand, reduce='amin', include_self=True)
+            sel = first < n
+            rows = first[sel]
+            cols = torch.arange(c, device=feats.device).unsqueeze(0).expand_as(first)[sel]
+            grad_feats[rows, cols] = g[sel]
+        return grad_feats, None, None
+
+
+dynamic_scatter = _dynamic_scatter.apply
+
+
+class DynamicScatter(nn.Module):
+    """ref: mmdet3d/ops/voxel/scatter_points.py:49-103."""
+
+    def __init__(self, voxel_size, point_cloud_range, average_points: bool):
+        super().__init__()
+        self.voxel_size = voxel_size
+        self.point_cloud_range = point_cloud_range
+        self.average_points = average_points
+
+    def forward_single(self, points, coors):
+        reduce = 'mean' if self.average_points else 'max'
+        return dynamic_scatter(points.contiguous(), coors.contiguous(), reduce)
+
+    def forward(self, points, coors):
+        if coors.size(-1) == 3:
+            return self.forward_single(points, coors)
+        batch_size = coors[-1, 0] + 1
+        voxels, voxel_coors = [], []
+        for i in range(batch_size):
+            inds = torch.where(coors[:, 0] == i)
+            voxel, voxel_coor = self.forward_single(points[inds], coors[inds][:, 1:])
+            voxel_coors.append(nn.functional.pad(voxel_coor, (1, 0), mode='constant', value=i))
+            voxels.append(voxel)
+        return torch.cat(voxels, dim=0), torch.cat(voxel_coors, dim=0)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(voxel_size={self.voxel_size}, point_cloud_range='
+                f'{self.point_cloud_range}, average_points={self.average_points})')

@@ -1,0 +1,25 @@
+"""CPU oracle for the IS-Fusion fusion-neck hot path.
+
+TEST INFRASTRUCTURE ONLY.  This package is a line-by-line CPU restatement of the
+reference algorithm (yinjunbo/IS-Fusion @ 86c882a, files cited per function as
+``ref: path:lines`` relative to the reference checkout).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it, and there only as the checker / the CPU
+baseline — never as the product path.  The product (``is-fusion_b200``) must
+fail loudly when its CUDA library is missing; it never falls back to this code.
+
+Pinning status:
+  * dynamic / hard voxelization  : PINNED against the reference's own C++
+    (``oracle/_ref/libref_voxel.so`` compiled from
+    mmdet3d/ops/voxel/src/voxelization_cpu.cpp where it lies) and against the
+    reference's numpy ``VoxelGenerator`` known-answer test
+    (tests/test_models/test_voxel_encoder/test_voxel_generator.py:7-23).
+  * dynamic scatter              : pinned by the brute-force contract of
+    tests/test_models/test_voxel_encoder/test_dynamic_scatter.py:57-72.
+  * MSDA                         : pinned by ops/functions/ms_deform_attn_func.py
+    (imported from the reference to generate tests/golden/msda_*.npz).
+  * sparse conv, SST windows, camera->BEV, IGF, SECONDV2 staging:
+    PARITY UNPINNED by the reference (its tests assert shapes only / do not
+    exist); the restatement here, cross-checked against dense F.conv3d and
+    torch.nn primitives, is the only pin.
+"""

@@ -1,0 +1,108 @@
+"""Generate the golden fixtures under tests/golden/ FROM THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+  * voxel_generator_kat.npz : the reference's numpy VoxelGenerator (mmdet3d/core/voxel/
+    voxel_generator.py:212-280) on the known-answer input of
+    tests/test_models/test_voxel_encoder/test_voxel_generator.py:7-23.
+  * voxel_ref_cpp.npz       : the reference's C++ dynamic/hard voxelization
+    (mmdet3d/ops/voxel/src/voxelization_cpu.cpp, compiled by oracle/build_ref.py) on seeded
+    clouds incl. an adversarial set with coordinates within 1 ulp of cell faces.
+  * msda_ref.npz            : ops/functions/ms_deform_attn_func.py:41-61
+    (ms_deform_attn_core_pytorch) on the shapes of ops/test.py:20-36 and on the IGF shape.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def voxel_generator_kat():
+    vg = _load('vg', os.path.join(REF, 'mmdet3d/core/voxel/voxel_generator.py'))
+    np.random.seed(0)
+    g = vg.VoxelGenerator([0.5, 0.5, 0.5], [0, -40, -3, 70.4, 40, 1], 1000)
+    points = np.random.rand(1000, 4)
+    voxels, coors, npv = g.generate(points)
+    np.savez_compressed(os.path.join(HERE, 'voxel_generator_kat.npz'), points=points.astype(np.float32),
+                        voxels=voxels.astype(np.float32), coors=coors.astype(np.int32), npv=npv.astype(np.int32))
+
+
+def voxel_ref_cpp():
+    from oracle import build_ref, ref_voxel
+    build_ref.build()
+    g = torch.Generator().manual_seed(0)
+    n = 4000
+    pts = torch.rand(n, 5, generator=g) * torch.tensor([112., 112., 8.4, 1., 0.5]) + torch.tensor([-56., -56., -5.2, 0., 0.])
+    # adversarial: 10% of the points within 1 ulp of a voxel face
+    vs = np.float32(0.075)
+    k = torch.randint(0, 1440, (n // 10,), generator=g).numpy().astype(np.float32)
+    face = (k * vs + np.float32(-54.0)).astype(np.float32)
+    adv = np.stack([np.nextafter(face, np.float32(1e9)), face, np.nextafter(face, np.float32(-1e9))], 0)
+    sel = torch.randint(0, 3, (n // 10,), generator=g).numpy()
+    pts[: n // 10, 0] = torch.from_numpy(adv[sel, np.arange(n // 10)])
+    pts[n // 10: n // 5, 1] = torch.from_numpy(adv[(sel + 1) % 3, np.arange(n // 10)])
+    out = dict(points=pts.numpy())
+    cfgs = {'main': ([0.075, 0.075, 0.2], [-54, -54, -5, 54, 54, 3]),
+            'pillar': ([0.6, 0.6, 8.0], [-54, -54, -5, 54, 54, 3])}
+    for name, (v, r) in cfgs.items():
+        out['dyn_' + name] = ref_voxel.dynamic_voxelize(pts, v, r).numpy()
+    for tag, mp, mv in [('p12_v60000', 12, 60000), ('p12_v300', 12, 300), ('p3_v60000', 3, 60000)]:
+        vo, co, nu = ref_voxel.hard_voxelize(pts, *cfgs['pillar'], mp, mv)
+        out['hard_%s_voxels' % tag] = vo.numpy()
+        out['hard_%s_coors' % tag] = co.numpy()
+        out['hard_%s_npv' % tag] = nu.numpy()
+    np.savez_compressed(os.path.join(HERE, 'voxel_ref_cpp.npz'), **out)
+
+
+def msda_ref():
+    f = _load('msda', os.path.join(REF, 'ops/functions/ms_deform_attn_func.py')) if False else None
+    # ms_deform_attn_func.py imports the compiled MultiScaleDeformableAttention at module import;
+    # exec only the pure-PyTorch function (lines 41-61) from the reference file, unmodified.
+    src = open(os.path.join(REF, 'ops/functions/ms_deform_attn_func.py')).read().split('\n')
+    body = '\n'.join(src[40:61])
+    ns = {'torch': torch, 'F': torch.nn.functional}
+    exec(body, ns)
+    core = ns['ms_deform_attn_core_pytorch']
+    out = {}
+    torch.manual_seed(3)
+    # case A: ops/test.py:20-36 shapes
+    N, M, D, Lq, Lv, P = 1, 2, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    value = torch.rand(N, S, M, D) * 0.01
+    loc = torch.rand(N, Lq, M, Lv, P, 2)
+    aw = torch.rand(N, Lq, M, Lv, P) + 1e-5
+    aw /= aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    out.update(a_value=value.numpy(), a_shapes=shapes.numpy(), a_loc=loc.numpy(), a_aw=aw.numpy(),
+               a_out=core(value.double(), shapes, loc.double(), aw.double()).float().numpy())
+    # case B: the IGF head layout (fusion_encoder.py:773-780): 1 level, 8 heads x 16 ch, 16 points, 200 queries
+    N, M, D, Lq, Lv, P = 1, 8, 16, 200, 1, 16
+    shapes = torch.as_tensor([(40, 44)], dtype=torch.long)   # small non-square map, IGF head layout
+    value = torch.randn(N, 40 * 44, M, D).half().float()
+    loc = torch.rand(N, Lq, M, Lv, P, 2) * 1.2 - 0.1          # some samples fall outside [0,1]
+    aw = torch.softmax(torch.randn(N, Lq, M, Lv * P), -1).view(N, Lq, M, Lv, P)
+    ref = core(value.double(), shapes, loc.double(), aw.double()).float()
+    out.update(b_seed=np.int64(3), b_loc=loc.numpy().astype(np.float32), b_aw=aw.numpy().astype(np.float32),
+               b_value_f16=value.half().numpy(), b_out=ref.numpy())
+    np.savez_compressed(os.path.join(HERE, 'msda_ref.npz'), **out)
+
+
+if __name__ == '__main__':
+    voxel_generator_kat()
+    voxel_ref_cpp()
+    msda_ref()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,47 @@
+"""The C-ABI library loads and exports every symbol include/isfusion_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, 'include', 'isfusion_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    names = sorted(set(re.findall(r'\b(isf_\w+)\s*\(', hdr)))
+    assert len(names) >= 10
+    import isfusion_b200._lib as L
+    lib = L.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.isf_version() >= 100
+
+
+def test_errors_are_reported_without_gpu():
+    import isfusion_b200._lib as L
+    lib = L.lib()
+    n = ctypes.c_size_t(0)
+    assert lib.isf_dynamic_scatter_workspace_size(1000, ctypes.byref(n)) == 0 and n.value > 0
+    rc = lib.isf_dynamic_scatter_workspace_size(-1, ctypes.byref(n))
+    assert rc == 1 and b'invalid argument' in lib.isf_last_error()
+
+
+def test_product_has_no_cpu_fallback():
+    import pytest
+    import torch
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.voxel_layer import dynamic_voxelize
+    pts = torch.rand(10, 5)
+    coors = torch.zeros(10, 3, dtype=torch.int32)
+    with pytest.raises(L.IsfError):
+        dynamic_voxelize(pts, coors, [0.1, 0.1, 0.1], [0, 0, 0, 1, 1, 1])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'is-fusion_b200')
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py') or f.endswith('.cu') or f.endswith('.cuh'):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(d, f)
