@@ -99,6 +99,20 @@ int isf_dynamic_vfe_forward(const float* points, const int* coors, int n, int nf
                             void* voxel_feats_f16, int* voxel_coors, int* num_voxels_dev, void* workspace,
                             size_t ws_bytes, void* stream);
 
+/* ---- tensor-core GEMM with fused epilogue (tcgen05, fp16 in / fp32 accumulate) ----
+ * out[m, n] = act( LN( (A[m,k] . W[n,kpad]^T) * scale[n] + shift[n] + residual[m,n] ) )
+ * Replaces the cuBLAS calls behind nn.Linear / nn.MultiheadAttention projections / FFN on the path
+ * (mmdet3d/models/sst/sst_basic_block_v2.py:105-126, backbones/sst_v2.py:78-79,
+ *  middle_encoders/fusion_encoder.py:576,599,648-651).  A [m,k] fp16 row-major (k % 8 == 0);
+ * W [n,kpad] fp16 K-major, zero padded to kpad % 64 == 0; n % 32 == 0.  scale/shift/residual/
+ * ln_gamma/ln_beta may be NULL; act: 0 none, 1 ReLU, 2 GELU(erf).  LayerNorm needs n in
+ * {32,64,128,256}.  out_rows (optional) scatters output row i to row out_rows[i] (-1 = drop).
+ * m_dev (optional) overrides m with a device-side row count (m is then the upper bound). */
+int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad, int n, const float* scale,
+                 const float* shift, const void* residual, int ldr, int act, const float* ln_gamma,
+                 const float* ln_beta, float ln_eps, void* out_f16, float* out_f32, int ldo,
+                 const int* out_rows, const int* m_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

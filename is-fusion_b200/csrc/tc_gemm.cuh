@@ -1,0 +1,401 @@
+// tcgen05 implicit-GEMM building block (sm_100a).
+//
+//   D[m, n] = epilogue( sum_k A[row(m, k), k % Cin] * W[n, k] )        k in [0, taps*Cin)
+//
+// A is an fp16 feature matrix [rows, Cin]; `row(m,k)` is either m (plain GEMM, taps = 1) or
+// nbr[(k / Cin) * nbr_stride + m] (gathered rows of a sparse-convolution rulebook, -1 = no neighbour
+// -> zero).  W is pre-packed K-major [N, Kpad] fp16 (Kpad = taps*Cin rounded up to 64).
+//
+// One CTA = 128 output rows x BN output columns.  Warps 0-3 are the producers (one A row per thread,
+// 16-byte cp.async pieces written straight into the 128B-swizzled K-major layout the UMMA smem
+// descriptor expects) and, after the main loop, the epilogue (TMEM lane = output row = thread).
+// Warp 4 allocates TMEM and its elected lane issues tcgen05.mma (M=128, N=BN, K=16) and the
+// tcgen05.commit that recycles smem stages through mbarriers.  Accumulators live in TMEM (fp32).
+#pragma once
+#include "common.cuh"
+
+namespace tc {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::f16, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 columns of fp32: thread i of the warp receives lane (base_lane + i), columns col..col+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B smem matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format F16 (0) @7/@10, K-major A and B,
+// n_dim = N>>3 @17, m_dim = M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- kernel
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct GemmParams {
+  const __half* A;        // [rowsA, Cin]
+  const __half* W;        // [N_total, Kpad] K-major
+  const int* nbr;         // [taps, nbr_stride] or nullptr (identity rows)
+  long long nbr_stride;
+  const int* m_dev;       // optional device-side row count (overrides m when non-null)
+  int m;                  // output rows
+  int cin;                // channels per tap (multiple of 8)
+  int taps;
+  int kpad;               // padded K (multiple of 64)
+  int n_total;            // total output columns (B rows); the CTA covers [blockIdx.y*BN, +BN)
+  // epilogue
+  const float* scale;     // [N_total] or nullptr
+  const float* shift;     // [N_total] or nullptr
+  const __half* residual; // [m, ldr] or nullptr (added before the activation)
+  int ldr;
+  int act;
+  const float* ln_gamma;  // LayerNorm over the BN columns after residual (requires BN == n_total)
+  const float* ln_beta;
+  float ln_eps;
+  __half* out;            // [m, ldo] fp16 (may be nullptr)
+  float* out_f32;         // [m, ldo] fp32 (may be nullptr)
+  int ldo;
+  const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 fp16 = 128 B = one swizzle row
+constexpr int PRODUCERS = 128;  // 4 warps
+constexpr int THREADS = PRODUCERS + 32;
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + tmem slot, + alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
+  using SL = SmemLayout<BN, STAGES>;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + SL::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_total = p.m_dev ? *p.m_dev : p.m;
+  const int num_tiles = (m_total + BM - 1) / BM;
+  const int n0 = blockIdx.y * BN;
+  const int num_chunks = p.kpad / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PRODUCERS); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  uint32_t chunk_ctr = 0;   // running chunk counter across tiles (stage = ctr % STAGES, use = ctr / STAGES)
+  uint32_t tile_ctr = 0;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_ctr) {
+    const int row0 = tile * BM;
+    if (warp < 4) {
+      // ------------------------------------------------ producers
+      const int r = tid;                       // A row inside the tile
+      const int grow = row0 + r;
+      const bool row_ok = grow < m_total;
+      int cur_tap = -1;
+      long long src_row = -1;
+      uint32_t c0 = chunk_ctr;
+      for (int q = 0; q < num_chunks; ++q) {
+        const uint32_t cc = c0 + q;
+        const int s = cc % STAGES;
+        if (cc >= STAGES) mbar_wait(&empty_bar[s], ((cc / STAGES) - 1) & 1);
+        uint8_t* sa = smem + s * SL::STAGE_BYTES;
+        uint8_t* sb = sa + SL::A_BYTES;
+        // A: 8 pieces of 16 B for this thread's row
+        const uint32_t a_row = smem_u32(sa) + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int k = q * BK + c * 8;
+          const int tap = k / p.cin;
+          const int ch = k - tap * p.cin;
+          if (tap != cur_tap) {
+            cur_tap = tap;
+            src_row = -1;
+            if (row_ok && tap < p.taps) src_row = p.nbr ? (long long)p.nbr[(long long)tap * p.nbr_stride + grow] : grow;
+          }
+          const bool ok = src_row >= 0;
+          const __half* src = ok ? p.A + src_row * p.cin + ch : p.A;
+          cp_async16(a_row + ((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+        }
+        // B: BN rows x 8 pieces, spread over the 128 producer threads
+        const uint32_t b_base = smem_u32(sb);
+#pragma unroll
+        for (int i = 0; i < BN * 8 / PRODUCERS; ++i) {
+          const int piece = tid + i * PRODUCERS;
+          const int n = piece >> 3, c = piece & 7;
+          const __half* src = p.W + (long long)(n0 + n) * p.kpad + q * BK + c * 8;
+          cp_async16(b_base + n * 128 + ((c ^ (n & 7)) << 4), src, 16u);
+        }
+        cp_async_commit();
+        if (q >= STAGES - 1) {
+          cp_async_wait<STAGES - 1>();
+          fence_proxy_async();
+          mbar_arrive(&full_bar[(cc - (STAGES - 1)) % STAGES]);
+        }
+      }
+      // drain: the last (STAGES-1) chunks (or all of them when num_chunks < STAGES-1)
+      cp_async_wait<0>();
+      fence_proxy_async();
+      {
+        int first = num_chunks - (STAGES - 1);
+        if (first < 0) first = 0;
+        for (int q = first; q < num_chunks; ++q) mbar_arrive(&full_bar[(c0 + q) % STAGES]);
+      }
+      // ------------------------------------------------ epilogue
+      mbar_wait(accum_bar, tile_ctr & 1);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+      long long orow = grow;
+      if (p.out_rows && row_ok) orow = p.out_rows[grow];
+      const bool store_ok = row_ok && orow >= 0;
+      float mean = 0.f, rstd = 1.f;
+      if (p.ln_gamma) {
+        // pass 1 over TMEM: row statistics of (acc*scale+shift+residual)
+        float s1 = 0.f, s2 = 0.f;
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + cb, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            const int n = n0 + cb + j;
+            if (p.scale) x *= p.scale[n];
+            if (p.shift) x += p.shift[n];
+            if (p.residual && row_ok) x += __half2float(p.residual[(long long)grow * p.ldr + n]);
+            s1 += x; s2 += x * x;
+          }
+        }
+        mean = s1 / BN;
+        float var = s2 / BN - mean * mean;
+        rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+      }
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + cb, v);
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float y = __uint_as_float(v[j]);
+          const int n = n0 + cb + j;
+          if (p.scale) y *= p.scale[n];
+          if (p.shift) y += p.shift[n];
+          x[j] = y;
+        }
+        if (p.residual && row_ok) {
+          const uint4* rp = (const uint4*)(p.residual + (long long)grow * p.ldr + n0 + cb);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u = rp[j4];
+            const __half2* h = (const __half2*)&u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __half22float2(h[e]);
+              x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (p.ln_gamma) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * p.ln_gamma[n0 + cb + j] + p.ln_beta[n0 + cb + j];
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        } else if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+        }
+        if (store_ok) {
+          if (p.out) {
+            uint4* op = (uint4*)(p.out + orow * p.ldo + n0 + cb);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 u;
+              __half2* h = (__half2*)&u;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+              op[j4] = u;
+            }
+          }
+          if (p.out_f32) {
+            float4* op = (float4*)(p.out_f32 + orow * p.ldo + n0 + cb);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+          }
+        }
+      }
+      // all TMEM reads of this tile are ordered before the __syncthreads below, after which the MMA
+      // warp may overwrite the accumulator with the next tile
+      tc_fence_before();
+    } else {
+      // ------------------------------------------------ MMA issuer (warp 4)
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      uint32_t c0 = chunk_ctr;
+      for (int q = 0; q < num_chunks; ++q) {
+        const uint32_t cc = c0 + q;
+        const int s = cc % STAGES;
+        mbar_wait(&full_bar[s], (cc / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + SL::A_BYTES;
+          const uint64_t a_desc = make_desc_sw128(a_addr);
+          const uint64_t b_desc = make_desc_sw128(b_addr);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
+            umma_f16(tmem_base, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (q == num_chunks - 1) umma_commit(accum_bar);
+        }
+        __syncwarp();
+      }
+    }
+    chunk_ctr += num_chunks;
+    // The epilogue of tile t must finish reading TMEM before the MMA warp starts tile t+1.
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
+  using SL = SmemLayout<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+    if (e != cudaSuccess) { isf_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
+    configured = true;
+  }
+  int tiles = (m_upper + BM - 1) / BM;
+  if (tiles < 1) tiles = 1;
+  int ctas_per_sm = (227 * 1024) / (SL::TOTAL + 1024);
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  int n_tiles = p.n_total / BN;
+  int gx = ISF_NUM_SMS * ctas_per_sm / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > tiles) gx = tiles;
+  dim3 grid(gx, n_tiles);
+  gemm_kernel<BN, STAGES><<<grid, THREADS, SL::TOTAL, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { isf_set_error("gemm launch: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
+  return ISF_OK;
+}
+
+static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  switch (bn) {
+    case 32: return launch_gemm<32, 4>(p, m_upper, st);
+    case 64: return launch_gemm<64, 4>(p, m_upper, st);
+    case 128: return launch_gemm<128, 3>(p, m_upper, st);
+    case 256: return launch_gemm<256, 2>(p, m_upper, st);
+    default: isf_set_error("gemm: unsupported column tile %d", bn); return ISF_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace tc
