@@ -113,6 +113,48 @@ int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad, int n, co
                  const float* ln_beta, float ln_eps, void* out_f16, float* out_f32, int ldo,
                  const int* out_rows, const int* m_dev, void* stream);
 
+/* ---- a4: sparse 3-D convolution ------------------------------------------------
+ * Replaces the spconv / mmcv.ops sparse-conv stack the reference delegates to
+ * (call sites mmdet3d/models/middle_encoders/sparse_encoder.py:122-136, mmdet3d/ops/sparse_block.py:117-134;
+ *  semantic spec mmdet3d/ops/bevfusion-ops/spconv/{ops.py:45-125, conv.py:114-223,
+ *  include/spconv/spconv_ops.h:27-141,260-361, include/spconv/geometry.h:24-85,144-194}).
+ * Indices are [V,4] int32 (b,z,y,x); shapes / kernel geometry are HOST int[3] arrays (z,y,x order).
+ *
+ * isf_hash_build: coordinate -> row hash table over `indices`.  `table` = 2*capacity 32-bit words
+ *   (capacity = isf_hash_capacity(v), a power of two >= 2v).
+ * isf_spconv_out_indices: output sites of a strided SparseConv3d = sorted-unique linear index of every
+ *   (input, kernel offset) candidate (the GPU ordering of spconv_ops.h:129-137); writes up to out_cap
+ *   rows and the count to *num_out_dev.
+ * isf_spconv_neighbors: neighbour table nbr[k * nbr_stride + o] = input row reaching output row o via kernel
+ *   offset k (k = (kz*KH+ky)*KW+kx, geometry.h:62-73) or -1.  subm=1: outputs = inputs, centre aligned.
+ * isf_spconv_implicit_gemm: out[o, :] = act((sum_k in[nbr[k,o], :] . W[k]) * scale + shift + residual[o, :])
+ *   in ONE tcgen05 kernel.  w_packed [cout, kpad] fp16, column k*cin + c = W[k][c][cout] (kpad % 64 == 0,
+ *   zero padded).  cin in {32,64,128,256} (or a multiple of 64), cout in {32,64,128,256}.
+ * isf_sparse_to_dense: SparseConvTensor.dense() -> [B,C,D,H,W] fp16 (structure.py:49-59).
+ * isf_sparse_to_bev_nhwc: the [B, C*D, H, W] BEV view (sparse_encoder.py:133-136, channel c*D+z) written
+ *   channels-last with row pitch ldo at channel offset ch_offset (caller zero-fills). */
+int isf_hash_capacity(int n);
+int isf_hash_build(const int* indices, int v, const int* v_dev, const int* spatial_shape, int batch, void* table,
+                   int capacity, void* stream);
+int isf_spconv_out_shape(const int* in_shape, const int* ksize, const int* stride, const int* padding,
+                         const int* dilation, int* out_shape);
+int isf_spconv_out_indices_workspace_size(int v_in, int kvol, size_t* bytes);
+int isf_spconv_out_indices(const int* in_indices, int v_in, const int* in_shape, int batch, const int* ksize,
+                           const int* stride, const int* padding, const int* dilation, int* out_indices,
+                           int out_cap, int* num_out_dev, void* workspace, size_t ws_bytes, void* stream);
+int isf_spconv_neighbors(const int* out_indices, int v_out, const int* v_out_dev, const void* in_table,
+                         int in_capacity, const int* in_shape, const int* ksize, const int* stride,
+                         const int* padding, const int* dilation, int subm, int* nbr, long long nbr_stride,
+                         void* stream);
+int isf_spconv_implicit_gemm(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,
+                             const int* nbr, long long nbr_stride, int taps, int v_out, const int* v_out_dev,
+                             const float* scale, const float* shift, const void* residual, int ldr, int relu,
+                             void* out_f16, int ldo, void* stream);
+int isf_sparse_to_dense(const void* feats, const int* indices, int v, int c, int batch, int D, int H, int W,
+                        void* out, void* stream);
+int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, int c, int D, int H, int W, void* out,
+                           int ldo, int ch_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,338 @@
+// Sparse 3-D convolution: rulebook construction + tcgen05 implicit GEMM.
+//
+// Replaces spconv's getIndicePair (mmdet3d/ops/bevfusion-ops/spconv/include/spconv/spconv_ops.h:27-141,
+// indice.cu.h:22-203: dense B*D*H*W int32 grids, per-offset pair lists) and indiceConv (spconv_ops.h:260-361:
+// 27 x {gather kernel, cuBLAS mm, scatter-add kernel} per layer).  Here:
+//   * coordinates live in an open-addressing hash table (no dense grid);
+//   * the rulebook is an output-stationary neighbour table nbr[tap][out_row] -> in_row | -1;
+//   * strided-conv output sites = sorted unique of all candidate keys (one radix sort) = the reference's
+//     GPU ordering (unique of the linear index, spconv_ops.h:129-137);
+//   * the convolution is ONE kernel per layer (tc_gemm.cuh): gathered rows -> swizzled smem -> tcgen05.mma
+//     accumulating all taps in TMEM -> fused BN scale/shift (+residual) (+ReLU) epilogue -> one fp16 store.
+#include <cub/cub.cuh>
+#include "tc_gemm.cuh"
+
+extern "C" void isf_count_launch(int n);
+
+struct ConvGeom {
+  int in_shape[3];
+  int out_shape[3];
+  int ksize[3], stride[3], pad[3], dil[3];
+  int kvol;
+  int subm;
+};
+
+static const unsigned int HASH_EMPTY = 0xFFFFFFFFu;
+
+__device__ __forceinline__ unsigned int hash_u32(unsigned int k) {
+  k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
+  return k;
+}
+
+__device__ __forceinline__ unsigned int lin_key(int b, int z, int y, int x, const int* shape) {
+  return (unsigned int)(((b * shape[0] + z) * shape[1] + y) * shape[2] + x);
+}
+
+__global__ void __launch_bounds__(256) hash_insert_kernel(const int* __restrict__ indices, int v, const int* v_dev,
+                                                          ConvGeom g, unsigned int* __restrict__ keys,
+                                                          int* __restrict__ vals, unsigned int mask) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = v_dev ? *v_dev : v;
+  if (i >= n) return;
+  const int* c = indices + (size_t)i * 4;
+  unsigned int key = lin_key(c[0], c[1], c[2], c[3], g.in_shape);
+  unsigned int slot = hash_u32(key) & mask;
+  while (true) {
+    unsigned int prev = atomicCAS(&keys[slot], HASH_EMPTY, key);
+    if (prev == HASH_EMPTY || prev == key) { vals[slot] = i; return; }
+    slot = (slot + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ int hash_lookup(const unsigned int* __restrict__ keys, const int* __restrict__ vals,
+                                           unsigned int mask, unsigned int key) {
+  unsigned int slot = hash_u32(key) & mask;
+  while (true) {
+    unsigned int k = keys[slot];
+    if (k == key) return vals[slot];
+    if (k == HASH_EMPTY) return -1;
+    slot = (slot + 1) & mask;
+  }
+}
+
+extern "C" int isf_hash_capacity(int n) {
+  long long c = 1024;
+  while (c < 2ll * n) c <<= 1;
+  return (int)c;
+}
+
+static int fill_geom(ConvGeom* g, const int* in_shape, const int* ksize, const int* stride, const int* pad,
+                     const int* dil, int subm) {
+  g->kvol = 1;
+  for (int d = 0; d < 3; ++d) {
+    g->in_shape[d] = in_shape[d];
+    g->ksize[d] = ksize[d];
+    g->dil[d] = dil ? dil[d] : 1;
+    g->stride[d] = subm ? 1 : stride[d];
+    g->pad[d] = subm ? (ksize[d] / 2) * g->dil[d] : pad[d];
+    g->out_shape[d] = subm ? in_shape[d]
+                           : (in_shape[d] + 2 * g->pad[d] - g->dil[d] * (ksize[d] - 1) - 1) / g->stride[d] + 1;
+    g->kvol *= ksize[d];
+  }
+  g->subm = subm;
+  return 0;
+}
+
+// table: [capacity] uint32 keys followed by [capacity] int32 values
+extern "C" int isf_hash_build(const int* indices, int v, const int* v_dev, const int* spatial_shape, int batch,
+                              void* table, int capacity, void* stream) {
+  ISF_CHECK_ARG(v >= 0 && spatial_shape && table && capacity >= 1024 && (capacity & (capacity - 1)) == 0);
+  ISF_CHECK_ARG(capacity >= 2 * v || v_dev);
+  long long cells = (long long)batch * spatial_shape[0] * spatial_shape[1] * spatial_shape[2];
+  if (cells >= 0xFFFFFFFFll) { isf_set_error("spconv: B*D*H*W = %lld does not fit a 32-bit key", cells); return ISF_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned int* keys = (unsigned int*)table;
+  int* vals = (int*)(keys + capacity);
+  ISF_CUDA(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned int) * capacity, st));
+  if (v == 0) return ISF_OK;
+  ISF_CHECK_ARG(indices);
+  ConvGeom g{};
+  for (int d = 0; d < 3; ++d) g.in_shape[d] = spatial_shape[d];
+  hash_insert_kernel<<<isf_cdiv(v, 256), 256, 0, st>>>(indices, v, v_dev, g, keys, vals, (unsigned)capacity - 1);
+  isf_count_launch(2);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// strided conv: output sites
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) candidate_keys_kernel(const int* __restrict__ indices, int v, ConvGeom g,
+                                                             unsigned int* __restrict__ cand) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)v * g.kvol;
+  if (t >= total) return;
+  int i = (int)(t / g.kvol), k = (int)(t % g.kvol);
+  int kk[3];
+  kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
+  const int* c = indices + (size_t)i * 4;
+  int o[3];
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int num = c[1 + d] + g.pad[d] - kk[d] * g.dil[d];
+    int q = num / g.stride[d];
+    ok &= (num >= 0) && (q * g.stride[d] == num) && (q < g.out_shape[d]);
+    o[d] = q;
+  }
+  cand[t] = ok ? lin_key(c[0], o[0], o[1], o[2], g.out_shape) : HASH_EMPTY;
+}
+
+__global__ void __launch_bounds__(256) decode_out_kernel(const unsigned int* __restrict__ uniq,
+                                                         const int* __restrict__ num_sel, ConvGeom g, int cap,
+                                                         int* __restrict__ out_indices, int* __restrict__ num_out) {
+  int n = *num_sel;
+  // the invalid key (all ones) sorts last
+  if (n > 0 && uniq[n - 1] == HASH_EMPTY) n -= 1;
+  if (n > cap) n = cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *num_out = n;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    unsigned int k = uniq[j];
+    int x = k % g.out_shape[2]; k /= g.out_shape[2];
+    int y = k % g.out_shape[1]; k /= g.out_shape[1];
+    int z = k % g.out_shape[0]; k /= g.out_shape[0];
+    int* o = out_indices + (size_t)j * 4;
+    o[0] = (int)k; o[1] = z; o[2] = y; o[3] = x;
+  }
+}
+
+static size_t outidx_cub_bytes(long long n) {
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, a, (unsigned int*)nullptr, (unsigned int*)nullptr, n);
+  cub::DeviceSelect::Unique(nullptr, b, (unsigned int*)nullptr, (unsigned int*)nullptr, (int*)nullptr, n);
+  return a > b ? a : b;
+}
+
+extern "C" int isf_spconv_out_indices_workspace_size(int v_in, int kvol, size_t* bytes) {
+  ISF_CHECK_ARG(v_in >= 0 && kvol >= 1 && bytes);
+  long long n = (long long)(v_in > 0 ? v_in : 1) * kvol;
+  IsfArena A(nullptr, 0);
+  A.take<unsigned int>(n); A.take<unsigned int>(n); A.take<unsigned int>(n); A.take<int>(1);
+  A.take<char>(outidx_cub_bytes(n));
+  *bytes = A.off + 1024;
+  return ISF_OK;
+}
+
+extern "C" int isf_spconv_out_shape(const int* in_shape, const int* ksize, const int* stride, const int* padding,
+                                    const int* dilation, int* out_shape) {
+  ISF_CHECK_ARG(in_shape && ksize && stride && padding && out_shape);
+  ConvGeom g;
+  fill_geom(&g, in_shape, ksize, stride, padding, dilation, 0);
+  for (int d = 0; d < 3; ++d) out_shape[d] = g.out_shape[d];
+  return ISF_OK;
+}
+
+extern "C" int isf_spconv_out_indices(const int* in_indices, int v_in, const int* in_shape, int batch, const int* ksize,
+                                      const int* stride, const int* padding, const int* dilation, int* out_indices,
+                                      int out_cap, int* num_out_dev, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(v_in >= 0 && in_shape && ksize && stride && padding && num_out_dev && out_cap >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (v_in == 0) { ISF_CUDA(cudaMemsetAsync(num_out_dev, 0, sizeof(int), st)); return ISF_OK; }
+  ISF_CHECK_ARG(in_indices && out_indices && workspace);
+  ConvGeom g;
+  fill_geom(&g, in_shape, ksize, stride, padding, dilation, 0);
+  long long cells = (long long)batch * g.out_shape[0] * g.out_shape[1] * g.out_shape[2];
+  ISF_CHECK_ARG(cells > 0 && cells < 0xFFFFFFFFll);
+  long long n = (long long)v_in * g.kvol;
+  ISF_CHECK_ARG(n < 0x7fffffffll);
+  IsfArena A(workspace, ws_bytes);
+  unsigned int* cand = A.take<unsigned int>(n);
+  unsigned int* sorted = A.take<unsigned int>(n);
+  unsigned int* uniq = A.take<unsigned int>(n);
+  int* num_sel = A.take<int>(1);
+  size_t cub_bytes = outidx_cub_bytes(n);
+  void* cub_tmp = A.take<char>(cub_bytes);
+  if (!A.ok) { isf_set_error("spconv_out_indices: workspace too small"); return ISF_ERR_WORKSPACE; }
+  candidate_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, g, cand);
+  int bits = 1;
+  while ((1ll << bits) < cells) ++bits;
+  int end_bit = bits + 1 > 32 ? 32 : bits + 1;   // keeps the all-ones invalid key last
+  size_t tmp = cub_bytes;
+  ISF_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, tmp, cand, sorted, (int)n, 0, end_bit, st));
+  tmp = cub_bytes;
+  ISF_CUDA(cub::DeviceSelect::Unique(cub_tmp, tmp, sorted, uniq, num_sel, (int)n, st));
+  decode_out_kernel<<<ISF_NUM_SMS * 2, 256, 0, st>>>(uniq, num_sel, g, out_cap, out_indices, num_out_dev);
+  isf_count_launch(6);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbour table
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nbr_kernel(const int* __restrict__ out_indices, int v_out, const int* v_out_dev,
+                                                  ConvGeom g, const unsigned int* __restrict__ keys,
+                                                  const int* __restrict__ vals, unsigned int mask,
+                                                  int* __restrict__ nbr, long long nbr_stride) {
+  const int n = v_out_dev ? *v_out_dev : v_out;
+  const long long total = (long long)n * g.kvol;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    // consecutive threads -> consecutive rows of one tap: coalesced nbr writes, coalesced index reads
+    int k = (int)(t / n), j = (int)(t % n);
+    int kk[3];
+    kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
+    const int* o = out_indices + (size_t)j * 4;
+    int ip[3];
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ip[d] = o[1 + d] * g.stride[d] - g.pad[d] + kk[d] * g.dil[d];
+      ok &= ip[d] >= 0 && ip[d] < g.in_shape[d];
+    }
+    int r = -1;
+    if (ok) r = hash_lookup(keys, vals, mask, lin_key(o[0], ip[0], ip[1], ip[2], g.in_shape));
+    nbr[(long long)k * nbr_stride + j] = r;
+  }
+}
+
+extern "C" int isf_spconv_neighbors(const int* out_indices, int v_out, const int* v_out_dev, const void* in_table,
+                                    int in_capacity, const int* in_shape, const int* ksize, const int* stride,
+                                    const int* padding, const int* dilation, int subm, int* nbr, long long nbr_stride,
+                                    void* stream) {
+  ISF_CHECK_ARG(v_out >= 0 && in_shape && ksize && in_table && in_capacity >= 1024 && nbr_stride >= v_out);
+  ISF_CHECK_ARG(subm || (stride && padding));
+  if (v_out == 0) return ISF_OK;
+  ISF_CHECK_ARG(out_indices && nbr);
+  ConvGeom g;
+  fill_geom(&g, in_shape, ksize, stride, padding, dilation, subm);
+  const unsigned int* keys = (const unsigned int*)in_table;
+  const int* vals = (const int*)(keys + in_capacity);
+  long long total = (long long)v_out * g.kvol;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+  nbr_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_indices, v_out, v_out_dev, g, keys, vals,
+                                                       (unsigned)in_capacity - 1, nbr, nbr_stride);
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the convolution itself: implicit GEMM over the neighbour table
+// ------------------------------------------------------------------------------------------------
+extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,
+                                        const int* nbr, long long nbr_stride, int taps, int v_out,
+                                        const int* v_out_dev, const float* scale, const float* shift,
+                                        const void* residual, int ldr, int relu, void* out_f16, int ldo,
+                                        void* stream) {
+  ISF_CHECK_ARG(v_out >= 0 && cin % 8 == 0 && cin >= 8 && taps >= 1 && kpad % 64 == 0 && kpad >= taps * cin);
+  ISF_CHECK_ARG(cout == 32 || cout == 64 || cout == 128 || cout == 256);
+  ISF_CHECK_ARG(64 % cin == 0 || cin % 64 == 0);   // a 16-byte piece never straddles two taps / a chunk
+  if (v_out == 0) return ISF_OK;
+  ISF_CHECK_ARG(feats_in && w_packed && nbr && out_f16 && ldo % 8 == 0);
+  tc::GemmParams p{};
+  p.A = (const __half*)feats_in; p.W = (const __half*)w_packed; p.nbr = nbr; p.nbr_stride = nbr_stride;
+  p.m_dev = v_out_dev; p.m = v_out; p.cin = cin; p.taps = taps; p.kpad = kpad; p.n_total = cout;
+  p.scale = scale; p.shift = shift; p.residual = (const __half*)residual; p.ldr = ldr;
+  p.act = relu ? tc::ACT_RELU : tc::ACT_NONE;
+  p.out = (__half*)out_f16; p.ldo = ldo;
+  int rc = tc::dispatch_gemm(p, cout, v_out, (cudaStream_t)stream);
+  isf_count_launch(1);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SparseConvTensor.dense()  (structure.py:49-59)  -> [B, C, D, H, W] fp16, zero filled here
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) to_dense_kernel(const __half* __restrict__ feats, const int* __restrict__ idx,
+                                                       int v, int c, int D, int H, int W, __half* __restrict__ out) {
+  long long total = (long long)v * c;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(t / c), ch = (int)(t % c);
+    const int* o = idx + (size_t)j * 4;
+    out[((((long long)o[0] * c + ch) * D + o[1]) * H + o[2]) * W + o[3]] = feats[t];
+  }
+}
+
+extern "C" int isf_sparse_to_dense(const void* feats, const int* indices, int v, int c, int batch, int D, int H, int W,
+                                   void* out, void* stream) {
+  ISF_CHECK_ARG(v >= 0 && c >= 1 && batch >= 1 && out);
+  cudaStream_t st = (cudaStream_t)stream;
+  ISF_CUDA(cudaMemsetAsync(out, 0, sizeof(__half) * (size_t)batch * c * D * H * W, st));
+  if (v == 0) return ISF_OK;
+  long long total = (long long)v * c;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+  to_dense_kernel<<<blocks, 256, 0, st>>>((const __half*)feats, indices, v, c, D, H, W, (__half*)out);
+  isf_count_launch(2);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// BEV view of dense(): [B, C*D, H, W] with channel c' = c*D + z (sparse_encoder.py:133-136), written as NHWC
+// fp16 rows of pitch `ldo` starting at channel `ch_offset` (so it can land inside the fused 768-ch buffer).
+__global__ void __launch_bounds__(256) to_bev_nhwc_kernel(const __half* __restrict__ feats, const int* __restrict__ idx,
+                                                          int v, int c, int D, int H, int W, __half* __restrict__ out,
+                                                          int ldo, int ch_offset) {
+  long long total = (long long)v * c;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(t / c), ch = (int)(t % c);
+    const int* o = idx + (size_t)j * 4;
+    out[(((long long)o[0] * H + o[2]) * W + o[3]) * ldo + ch_offset + ch * D + o[1]] = feats[t];
+  }
+}
+
+extern "C" int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, int c, int D, int H, int W,
+                                      void* out, int ldo, int ch_offset, void* stream) {
+  ISF_CHECK_ARG(v >= 0 && c >= 1 && out);
+  if (v == 0) return ISF_OK;
+  long long total = (long long)v * c;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+  to_bev_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)feats, indices, v, c, D, H, W,
+                                                               (__half*)out, ldo, ch_offset);
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}

@@ -1,0 +1,135 @@
+"""SparseEncoder / SparseBasicBlock / make_sparse_convmodule on the B200 sparse-conv kernels.
+
+ref: mmdet3d/models/middle_encoders/sparse_encoder.py:18-216, mmdet3d/ops/sparse_block.py:82-199.
+Same constructor arguments, sub-module names and state_dict keys; in eval mode every conv + BN1d (+ residual)
+(+ ReLU) is one fused implicit-GEMM kernel, SubM rulebooks are shared by all convs of a stage, and dense()
++ view(N, C*D, H, W) is written directly.
+"""
+import torch
+from torch import nn
+
+from . import _lib as L
+from .registry import MIDDLE_ENCODERS, build_conv_layer, build_norm_layer
+from .spconv import SparseConvTensor, SparseModule, SparseSequential, SubMConv3d, fold_bn
+
+
+class SparseBasicBlock(SparseModule):
+    """ref: sparse_block.py:82-134 (mmdet BasicBlock over SubMConv3d; names conv1/bn1/conv2/bn2)."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, conv_cfg=None, norm_cfg=None):
+        super().__init__()
+        assert downsample is None and stride == 1
+        conv_cfg = conv_cfg or dict(type='SubMConv3d')
+        self.conv1 = build_conv_layer(conv_cfg, inplanes, planes, 3, stride=stride, padding=1, dilation=1, bias=False)
+        self.bn1 = build_norm_layer(norm_cfg, planes)[1]
+        self.conv2 = build_conv_layer(conv_cfg, planes, planes, 3, padding=1, bias=False)
+        self.bn2 = build_norm_layer(norm_cfg, planes)[1]
+        self.relu = nn.ReLU(inplace=True)
+
+    @property
+    def norm1(self):
+        return self.bn1
+
+    @property
+    def norm2(self):
+        return self.bn2
+
+    def forward(self, x):
+        if self.training:
+            raise L.IsfError('SparseBasicBlock: the fused CUDA path implements eval-mode BN only')
+        s1, b1 = fold_bn(self.bn1)
+        s2, b2 = fold_bn(self.bn2)
+        identity = x.features
+        out = self.conv1(x, scale=s1, shift=b1, relu=True)
+        out = self.conv2(out, scale=s2, shift=b2, residual=identity, relu=True)
+        return out
+
+
+def make_sparse_convmodule(in_channels, out_channels, kernel_size, indice_key, stride=1, padding=0,
+                           conv_type='SubMConv3d', norm_cfg=None, order=('conv', 'norm', 'act')):
+    """ref: sparse_block.py:137-199."""
+    assert isinstance(order, tuple) and len(order) <= 3
+    conv_cfg = dict(type=conv_type, indice_key=indice_key)
+    layers = []
+    for layer in order:
+        if layer == 'conv':
+            layers.append(build_conv_layer(conv_cfg, in_channels, out_channels, kernel_size, stride=stride,
+                                           padding=padding, bias=False))
+        elif layer == 'norm':
+            layers.append(build_norm_layer(norm_cfg, out_channels)[1])
+        elif layer == 'act':
+            layers.append(nn.ReLU(inplace=True))
+    return SparseSequential(*layers)
+
+
+@MIDDLE_ENCODERS.register_module()
+class SparseEncoder(nn.Module):
+
+    def __init__(self, in_channels, sparse_shape, order=('conv', 'norm', 'act'),
+                 norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), base_channels=16, output_channels=128,
+                 encoder_channels=((16,), (32, 32, 32), (64, 64, 64), (64, 64, 64)),
+                 encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1)), block_type='conv_module', **kwargs):
+        super().__init__()
+        assert block_type in ['conv_module', 'basicblock']
+        assert isinstance(order, tuple) and len(order) == 3 and set(order) == {'conv', 'norm', 'act'}
+        self.sparse_shape = sparse_shape
+        self.in_channels = in_channels
+        self.order = order
+        self.base_channels = base_channels
+        self.output_channels = output_channels
+        self.encoder_channels = encoder_channels
+        self.encoder_paddings = encoder_paddings
+        self.stage_num = len(self.encoder_channels)
+        if self.order[0] != 'conv':
+            self.conv_input = make_sparse_convmodule(in_channels, base_channels, 3, norm_cfg=norm_cfg, padding=1,
+                                                     indice_key='subm1', conv_type='SubMConv3d', order=('conv',))
+        else:
+            self.conv_input = make_sparse_convmodule(in_channels, base_channels, 3, norm_cfg=norm_cfg, padding=1,
+                                                     indice_key='subm1', conv_type='SubMConv3d')
+        enc_out = self.make_encoder_layers(make_sparse_convmodule, norm_cfg, base_channels, block_type=block_type)
+        self.conv_out = make_sparse_convmodule(enc_out, output_channels, kernel_size=(3, 1, 1), stride=(2, 1, 1),
+                                               norm_cfg=norm_cfg, padding=0, indice_key='spconv_down2',
+                                               conv_type='SparseConv3d')
+
+    def make_encoder_layers(self, make_block, norm_cfg, in_channels, block_type='conv_module',
+                            conv_cfg=dict(type='SubMConv3d')):
+        self.encoder_layers = SparseSequential()
+        for i, blocks in enumerate(self.encoder_channels):
+            blocks_list = []
+            for j, out_channels in enumerate(tuple(blocks)):
+                padding = tuple(self.encoder_paddings[i])[j]
+                if i != 0 and j == 0 and block_type == 'conv_module':
+                    blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg, stride=2,
+                                                  padding=padding, indice_key=f'spconv{i + 1}', conv_type='SparseConv3d'))
+                elif block_type == 'basicblock':
+                    if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
+                        blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg, stride=2,
+                                                      padding=padding, indice_key=f'spconv{i + 1}',
+                                                      conv_type='SparseConv3d'))
+                    else:
+                        blocks_list.append(SparseBasicBlock(out_channels, out_channels, norm_cfg=norm_cfg, conv_cfg=conv_cfg))
+                else:
+                    blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg, padding=padding,
+                                                  indice_key=f'subm{i + 1}', conv_type='SubMConv3d'))
+                in_channels = out_channels
+            self.encoder_layers.add_module(f'encoder_layer{i + 1}', SparseSequential(*blocks_list))
+        return out_channels
+
+    @torch.no_grad()
+    def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, **kwargs):
+        """voxel_features [V,C], coors [V,4] int32 (b,z,y,x) -> (spatial_features [B, C*D, H, W], encode_features, kwargs)"""
+        coors = coors.int()
+        feats = voxel_features if voxel_features.dtype == torch.float16 else voxel_features.half()
+        x = SparseConvTensor(feats.contiguous(), coors.contiguous(), self.sparse_shape, batch_size)
+        x = self.conv_input(x)
+        encode_features = [x]
+        for encoder_layer in self.encoder_layers:
+            x = encoder_layer(x)
+            encode_features.append(x)
+        out = self.conv_out(encode_features[-1])
+        spatial_features = out.dense()
+        n, c, d, h, w = spatial_features.shape
+        spatial_features = spatial_features.view(n, c * d, h, w)
+        self.last_out = out
+        return spatial_features, encode_features, kwargs

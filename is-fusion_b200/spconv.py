@@ -1,0 +1,251 @@
+"""Sparse 3-D convolution modules on the C-ABI CUDA library.
+
+Mirrors the spconv Python API the reference builds on (SparseConvTensor / SubMConv3d / SparseConv3d /
+SparseSequential / SparseModule, see mmdet3d/ops/bevfusion-ops/spconv/{structure.py:20-63, conv.py:55-223,
+modules.py} and the call sites mmdet3d/models/middle_encoders/sparse_encoder.py:11-15,122-136,
+mmdet3d/ops/sparse_block.py:8-20) with weights in the spconv1/mmcv layout (kD,kH,kW,Cin,Cout); spconv2
+checkpoints (Cout,kD,kH,kW,Cin) are accepted on load (write_spconv2.py:62-94).
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .registry import CONV_LAYERS
+
+
+def _triple(v):
+    return [int(x) for x in v] if isinstance(v, (list, tuple)) else [int(v)] * 3
+
+
+class SparseConvTensor:
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+        self.features = features
+        self.indices = indices
+        self.spatial_shape = [int(s) for s in spatial_shape]
+        self.batch_size = int(batch_size)
+        self.indice_dict = {}
+        self.grid = grid
+
+    @property
+    def spatial_size(self):
+        n = 1
+        for s in self.spatial_shape:
+            n *= s
+        return n
+
+    def replace_feature(self, feature):
+        t = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid)
+        t.indice_dict = self.indice_dict
+        return t
+
+    def find_indice_pair(self, key):
+        return self.indice_dict.get(key) if key is not None else None
+
+    def dense(self, channels_first=True):
+        f = self.features
+        if f.dtype != torch.float16:
+            f = f.half()
+        L.require_cuda(f, self.indices)
+        d, h, w = self.spatial_shape
+        c = f.shape[1]
+        out = torch.empty((self.batch_size, c, d, h, w), dtype=torch.float16, device=f.device)
+        L.check(L.lib().isf_sparse_to_dense(L.ptr(f.contiguous()), L.ptr(self.indices), f.shape[0], c, self.batch_size,
+                                            d, h, w, L.ptr(out), L.stream()))
+        out = out.to(self.features.dtype)
+        return out if channels_first else out.permute(0, 2, 3, 4, 1).contiguous()
+
+
+class Rulebook:
+    """output indices + neighbour table of one (coordinate set, kernel geometry)."""
+    __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'pairs')
+
+    def __init__(self, out_indices, out_shape, nbr, nbr_stride, taps, num_out):
+        self.out_indices, self.out_shape, self.nbr = out_indices, out_shape, nbr
+        self.nbr_stride, self.taps, self.num_out = nbr_stride, taps, num_out
+        self.pairs = None
+
+
+def _hash_table(x):
+    """coordinate hash of a tensor's indices (cached on the tensor: all convs reading it share it)."""
+    key = ('hash', x.indices.data_ptr(), x.indices.shape[0])
+    tab = x.indice_dict.get(key)
+    if tab is None:
+        v = x.indices.shape[0]
+        cap = L.lib().isf_hash_capacity(v)
+        table = torch.empty(2 * cap, dtype=torch.int32, device=x.indices.device)
+        L.check(L.lib().isf_hash_build(L.ptr(x.indices), v, L.ptr(None), L.host_i32(x.spatial_shape), x.batch_size,
+                                       L.ptr(table), cap, L.stream()))
+        tab = (table, cap)
+        x.indice_dict[key] = tab
+    return tab
+
+
+def build_rulebook(x, ksize, stride, padding, dilation, subm):
+    lib = L.lib()
+    dev = x.indices.device
+    v_in = x.indices.shape[0]
+    table, cap = _hash_table(x)
+    taps = ksize[0] * ksize[1] * ksize[2]
+    if subm:
+        out_indices, out_shape, v_out = x.indices, list(x.spatial_shape), v_in
+    else:
+        oshape = (ctypes.c_int * 3)()
+        L.check(lib.isf_spconv_out_shape(L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
+                                         L.host_i32(padding), L.host_i32(dilation), oshape))
+        out_shape = list(oshape)
+        cells = x.batch_size * out_shape[0] * out_shape[1] * out_shape[2]
+        cap_out = min(v_in * taps, cells)
+        ws_bytes = ctypes.c_size_t(0)
+        L.check(lib.isf_spconv_out_indices_workspace_size(v_in, taps, ctypes.byref(ws_bytes)))
+        ws = L.workspace(ws_bytes.value, dev)
+        out_buf = torch.empty((max(cap_out, 1), 4), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.check(lib.isf_spconv_out_indices(L.ptr(x.indices), v_in, L.host_i32(x.spatial_shape), x.batch_size,
+                                           L.host_i32(ksize), L.host_i32(stride), L.host_i32(padding),
+                                           L.host_i32(dilation), L.ptr(out_buf), cap_out, L.ptr(cnt), L.ptr(ws),
+                                           ctypes.c_size_t(ws.numel()), L.stream()))
+        v_out = int(cnt.item())      # one host read per strided layer (sizes the next stage's buffers)
+        out_indices = out_buf[:v_out]
+    stride_rows = max((v_out + 127) // 128 * 128, 128)
+    nbr = torch.empty((taps, stride_rows), dtype=torch.int32, device=dev)
+    L.check(lib.isf_spconv_neighbors(L.ptr(out_indices), v_out, L.ptr(None), L.ptr(table), cap,
+                                     L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
+                                     L.host_i32(padding), L.host_i32(dilation), 1 if subm else 0, L.ptr(nbr),
+                                     ctypes.c_longlong(stride_rows), L.stream()))
+    return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out)
+
+
+def implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, residual=None, relu=False, out=None):
+    if feats.dtype != torch.float16:
+        raise L.IsfError('sparse conv: fp16 features expected')
+    L.require_cuda(feats, w_packed, scale, shift, residual)
+    if out is None:
+        out = torch.empty((rb.num_out, cout), dtype=torch.float16, device=feats.device)
+    L.check(L.lib().isf_spconv_implicit_gemm(
+        L.ptr(feats), cin, L.ptr(w_packed), w_packed.shape[1], cout, L.ptr(rb.nbr), ctypes.c_longlong(rb.nbr_stride),
+        rb.taps, rb.num_out, L.ptr(None), L.ptr(scale), L.ptr(shift), L.ptr(residual),
+        residual.stride(0) if residual is not None else 0, 1 if relu else 0, L.ptr(out), out.stride(0), L.stream()))
+    return out
+
+
+def pack_conv_weight(weight):
+    """(kD,kH,kW,Cin,Cout) -> K-major fp16 [Cout, Kpad] with column k*Cin + c (zero padded to 64)."""
+    kd, kh, kw, cin, cout = weight.shape
+    taps = kd * kh * kw
+    w = weight.detach().reshape(taps * cin, cout).t()
+    kpad = (taps * cin + 63) // 64 * 64
+    out = torch.zeros((cout, kpad), dtype=torch.float16, device=weight.device)
+    out[:, :taps * cin] = w.half()
+    return out.contiguous()
+
+
+class SparseModule(nn.Module):
+    pass
+
+
+class SparseConvolution(SparseModule):
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None,
+                 fused_bn=False, **kwargs):
+        super().__init__()
+        if ndim != 3 or groups != 1 or transposed or inverse:
+            raise L.IsfError('sparse conv: only 3-D, groups=1, non-transposed convolutions are built')
+        self.ndim, self.in_channels, self.out_channels = ndim, in_channels, out_channels
+        self.kernel_size, self.stride = _triple(kernel_size), _triple(stride)
+        self.padding, self.dilation = _triple(padding), _triple(dilation)
+        self.subm, self.indice_key = subm, indice_key
+        self.weight = nn.Parameter(torch.empty(*self.kernel_size, in_channels, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        self._packed = None
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        self._packed = None
+        key = prefix + 'weight'
+        if key in state_dict:
+            w = state_dict[key]
+            exp = tuple(self.weight.shape)
+            if tuple(w.shape) != exp and tuple(w.shape) == (exp[4], exp[0], exp[1], exp[2], exp[3]):
+                state_dict[key] = w.permute(1, 2, 3, 4, 0).contiguous()      # spconv2 layout
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def train(self, mode=True):
+        self._packed = None
+        return super().train(mode)
+
+    def packed_weight(self):
+        if self._packed is None or self._packed.device != self.weight.device:
+            self._packed = pack_conv_weight(self.weight)
+        return self._packed
+
+    def rulebook(self, x):
+        key = self.indice_key
+        if key is None:   # the reference rebuilds here (sparse_block.py passes no indice_key); same coordinate
+            key = ('auto', self.subm, tuple(self.kernel_size), tuple(self.stride), tuple(self.padding),  # set ->
+                   tuple(self.dilation), x.indices.data_ptr(), x.indices.shape[0])                # same rulebook
+        rb = x.indice_dict.get(key)
+        if rb is None:
+            rb = build_rulebook(x, self.kernel_size, self.stride, self.padding, self.dilation, self.subm)
+            x.indice_dict[key] = rb
+        return rb
+
+    def forward(self, x, scale=None, shift=None, residual=None, relu=False):
+        """conv (+ optional fused scale/shift/residual/ReLU epilogue used by the encoder's executor)."""
+        rb = self.rulebook(x)
+        feats = x.features if x.features.dtype == torch.float16 else x.features.half()
+        if self.bias is not None:
+            shift = self.bias.float() if shift is None else shift + self.bias.float() * (scale if scale is not None else 1)
+        f = implicit_gemm(feats.contiguous(), rb, self.packed_weight(), self.in_channels, self.out_channels, scale,
+                          shift, residual, relu)
+        out = SparseConvTensor(f, rb.out_indices, rb.out_shape, x.batch_size)
+        out.indice_dict = x.indice_dict
+        return out
+
+
+@CONV_LAYERS.register_module('SubMConv3d')
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, **kw):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key=indice_key)
+
+
+@CONV_LAYERS.register_module('SparseConv3d')
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, **kw):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, False,
+                         indice_key=indice_key)
+
+
+def fold_bn(bn):
+    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float()
+    shift = (bn.bias - bn.running_mean * scale).detach().float()
+    return scale.contiguous(), shift.contiguous()
+
+
+class SparseSequential(SparseModule, nn.Sequential):
+    """ref: spconv modules.SparseSequential.  In eval mode the pattern conv -> BatchNorm1d -> ReLU is executed as
+    one fused kernel (BN folded into the conv epilogue)."""
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, SparseConvolution):
+                if (not self.training and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d)):
+                    scale, shift = fold_bn(mods[i + 1])
+                    relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                    x = m(x, scale=scale, shift=shift, relu=relu)
+                    i += 3 if relu else 2
+                    continue
+                x = m(x)
+            elif isinstance(m, SparseModule):
+                x = m(x)
+            else:
+                x = x.replace_feature(m(x.features))
+            i += 1
+        return x

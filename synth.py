@@ -1,0 +1,98 @@
+"""Seeded synthetic nuScenes-shaped inputs shared by tests/ and bench.py.
+
+points: 'U' = uniform box, 'S' = crude 32-beam LiDAR (ground plane + objects).  calibration: 6 pinhole cameras.
+Everything comes from torch.Generator().manual_seed(seed) on the CPU so that the oracle and the CUDA path see
+identical bits.
+"""
+import math
+
+import torch
+
+PC_RANGE = [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
+
+
+def make_points(n, kind='S', seed=0, pc_range=PC_RANGE):
+    g = torch.Generator().manual_seed(seed)
+    lo = torch.tensor(pc_range[:3])
+    hi = torch.tensor(pc_range[3:])
+    eps = 1e-3
+    if kind == 'U':
+        xyz = torch.rand(n, 3, generator=g) * (hi - lo - 2 * eps) + lo + eps
+    else:
+        beams = torch.linspace(math.radians(-30.0), math.radians(10.0), 32)
+        m = int(n * 1.25)
+        b = torch.randint(0, 32, (m,), generator=g)
+        elev = beams[b] + torch.randn(m, generator=g) * 0.002
+        az = torch.rand(m, generator=g) * 2 * math.pi
+        # ground return: z = -1.84 => range = -1.84 / sin(elev) for downward beams
+        ground_z = -1.84 + torch.randn(m, generator=g) * 0.02
+        rng = torch.where(elev < -0.01, ground_z / torch.sin(elev.clamp(max=-0.01)), torch.full((m,), 1e9))
+        obj = torch.rand(m, generator=g) < 0.35
+        obj_r = torch.rand(m, generator=g) * 57 + 3
+        rng = torch.where(obj, torch.minimum(rng, obj_r), rng)
+        far = rng > 75
+        rng = torch.where(far, torch.rand(m, generator=g) * 65 + 5, rng)
+        x = rng * torch.cos(elev) * torch.cos(az)
+        y = rng * torch.cos(elev) * torch.sin(az)
+        z = rng * torch.sin(elev)
+        xyz = torch.stack([x, y, z], 1)
+        ok = ((xyz > lo + eps) & (xyz < hi - eps)).all(1)
+        xyz = xyz[ok][:n]
+    inten = torch.rand(xyz.shape[0], 1, generator=g)
+    dt = torch.randint(0, 10, (xyz.shape[0], 1), generator=g).float() * 0.05
+    return torch.cat([xyz, inten, dt], 1).contiguous()
+
+
+def make_calib(batch, img_hw=(256, 704), seed=0):
+    """lidar2img [B,6,4,4], img_aug_matrix [B,6,4,4], lidar_aug_matrix [B,4,4] (eval: identity)."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    yaws = [0.0, 55.0, -55.0, 110.0, -110.0, 180.0]
+    f, cx, cy = 1260.0, 800.0, 450.0
+    K = torch.tensor([[f, 0, cx], [0, f, cy], [0, 0, 1.0]])
+    l2i = torch.zeros(batch, 6, 4, 4)
+    for b in range(batch):
+        for c, yaw in enumerate(yaws):
+            a = math.radians(yaw)
+            # camera looks along (cos a, sin a, 0); cam axes: x right, y down, z forward
+            fwd = torch.tensor([math.cos(a), math.sin(a), 0.0])
+            right = torch.tensor([math.sin(a), -math.cos(a), 0.0])
+            down = torch.tensor([0.0, 0.0, -1.0])
+            R = torch.stack([right, down, fwd], 0)
+            t_cam = torch.tensor([1.0 * math.cos(a), 0.5 * math.sin(a), 1.5]) + (torch.rand(3, generator=g) - 0.5) * 0.2
+            T = torch.eye(4)
+            T[:3, :3] = K @ R
+            T[:3, 3] = -(K @ R) @ t_cam
+            l2i[b, c] = T
+    s = img_hw[1] / 1600.0 * (0.48 / 0.44) if img_hw == (256, 704) else 0.72
+    s = 0.48 if img_hw == (256, 704) else 0.72
+    aug = torch.eye(4).repeat(batch, 6, 1, 1)
+    new_w, new_h = 1600 * s, 900 * s
+    crop_x = (new_w - img_hw[1]) / 2
+    crop_y = new_h - img_hw[0]
+    aug[:, :, 0, 0] = s
+    aug[:, :, 1, 1] = s
+    aug[:, :, 0, 3] = -crop_x
+    aug[:, :, 1, 3] = -crop_y
+    lidar_aug = torch.eye(4).repeat(batch, 1, 1)
+    return l2i, aug, lidar_aug
+
+
+def make_img_feats(batch, img_hw=(256, 704), channels=256, seed=0):
+    """the stride-16 FPN level the fusion encoder consumes (img_feats[1]) [B*6, 256, h, w]; the other levels are
+    present but unused by the path (fusion_encoder.py:1160)."""
+    g = torch.Generator().manual_seed(seed + 2000)
+    h, w = img_hw[0] // 16, img_hw[1] // 16
+    lvl1 = torch.randn(batch * 6, channels, h, w, generator=g) * 0.5
+    lvl0 = torch.zeros(batch * 6, channels, img_hw[0] // 8, img_hw[1] // 8)
+    lvl2 = torch.zeros(batch * 6, channels, max(h // 2, 1), max(w // 2, 1))
+    return [lvl0, lvl1, lvl2]
+
+
+def randomize_bn(module, seed=0):
+    """BN running stats randomised so that BN is not a no-op (SURVEY §8d 'weights')."""
+    g = torch.Generator().manual_seed(seed + 3000)
+    for m in module.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+    return module

@@ -1,0 +1,118 @@
+"""GPU parity: sparse conv rulebooks (bit-exact indices) and implicit GEMM vs the oracle."""
+import pytest
+import torch
+
+from oracle import spconv_ops as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_tensor(shape, nvox, c, batch, seed, clustered=False):
+    g = torch.Generator().manual_seed(seed)
+    cells = batch * shape[0] * shape[1] * shape[2]
+    if clustered:   # neighbours exist: random walk blobs
+        base = torch.randint(0, cells, (nvox // 8,), generator=g)
+        lin = (base[:, None] + torch.randint(-2, 3, (nvox // 8, 8), generator=g) * torch.tensor([1, shape[2], shape[1] * shape[2], 1, shape[2], 1, 1, shape[2]])).flatten() % cells
+        lin = torch.unique(lin)
+        lin = lin[torch.randperm(lin.numel(), generator=g)]
+    else:
+        lin = torch.randperm(cells, generator=g)[:nvox]
+    nvox = lin.numel()
+    idx = torch.stack([lin // (shape[0] * shape[1] * shape[2]), (lin // (shape[1] * shape[2])) % shape[0],
+                       (lin // shape[2]) % shape[1], lin % shape[2]], 1).int()
+    return so.SparseConvTensor(torch.randn(nvox, c, generator=g).half().float(), idx, shape, batch)
+
+
+def _to_gpu(x):
+    from isfusion_b200.spconv import SparseConvTensor
+    return SparseConvTensor(x.features.half().cuda(), x.indices.cuda(), x.spatial_shape, x.batch_size)
+
+
+CASES = [  # (subm, cin, cout, ksize, stride, padding)
+    (True, 64, 32, 3, 1, 1), (True, 32, 32, 3, 1, 1), (False, 32, 64, 3, 2, 1), (True, 128, 128, 3, 1, 1),
+    (False, 128, 256, 3, 2, (0, 1, 1)), (True, 256, 256, 3, 1, 1), (False, 256, 256, (3, 1, 1), (2, 1, 1), 0),
+]
+
+
+@pytest.mark.parametrize('subm,cin,cout,ksize,stride,padding', CASES)
+def test_conv_parity(subm, cin, cout, ksize, stride, padding):
+    import isfusion_b200.spconv as sp
+    x = _rand_tensor([11, 40, 36], 6000, cin, 2, cin + cout, clustered=True)
+    cls_o = so.SubMConv3d if subm else so.SparseConv3d
+    cls_g = sp.SubMConv3d if subm else sp.SparseConv3d
+    ref = cls_o(cin, cout, ksize, stride=stride, padding=padding, bias=False)
+    ref.weight.data = (torch.randn_like(ref.weight) / (27 * cin) ** 0.5 * 3).half().float()
+    mod = cls_g(cin, cout, ksize, stride=stride, padding=padding, bias=False)
+    mod.load_state_dict(ref.state_dict())
+    mod = mod.cuda().eval()
+    ro = ref(x)
+    go = mod(_to_gpu(x))
+    assert go.spatial_shape == ro.spatial_shape
+    assert torch.equal(go.indices.cpu(), ro.indices)                      # output sites + row order bit-exact
+    rb = list(go.indice_dict.values())[-1]
+    nbr_ref = so.get_indice_pairs(x.indices, x.batch_size, x.spatial_shape, ref.kernel_size, ref.stride, ref.padding,
+                                  ref.dilation, subm)[2]
+    assert torch.equal(rb.nbr[:, :rb.num_out].cpu().long(), nbr_ref)      # rulebook bit-exact
+    err = (go.features.float().cpu() - ro.features).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ro.features.abs().max().item()), err    # 1e-3 rel (fp16 storage, fp32 accumulate)
+    # spconv2 weight layout is accepted on load
+    sd = {'weight': ref.weight.data.permute(4, 0, 1, 2, 3).contiguous()}
+    mod2 = cls_g(cin, cout, ksize, stride=stride, padding=padding, bias=False)
+    mod2.load_state_dict(sd)
+    assert torch.equal(mod2.weight.data, ref.weight.data)
+
+
+def test_conv_fused_epilogue_and_dense():
+    import isfusion_b200.spconv as sp
+    x = _rand_tensor([9, 30, 30], 3000, 64, 2, 5, clustered=True)
+    ref = so.SubMConv3d(64, 64, 3, padding=1, bias=False)
+    mod = sp.SubMConv3d(64, 64, 3, padding=1, bias=False)
+    mod.load_state_dict(ref.state_dict())
+    mod = mod.cuda().eval()
+    scale, shift = torch.rand(64) + 0.5, torch.randn(64) * 0.1
+    res = torch.randn(x.features.shape[0], 64).half()
+    gx = _to_gpu(x)
+    go = mod(gx, scale=scale.cuda(), shift=shift.cuda(), residual=res.cuda(), relu=True)
+    want = torch.relu(ref(x).features * scale + shift + res.float())
+    assert (go.features.float().cpu() - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+    dense = go.dense().float().cpu()
+    want_d = so.SparseConvTensor(go.features.float().cpu(), x.indices, x.spatial_shape, x.batch_size).dense()
+    assert torch.equal(dense, want_d)
+
+
+def _randomize_bn(m):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.8, 1.2)
+            mod.bias.data.normal_(0, 0.1)
+
+
+def test_sparse_encoder_parity():
+    """whole SparseEncoder (isfusion_0075voxel.py:72-82 channel plan) on a reduced grid, LiDAR-like clustered input."""
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    torch.manual_seed(0)
+    cfg = dict(in_channels=64, sparse_shape=[41, 128, 128], base_channels=32, output_channels=256,
+               encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    ref = so.SparseEncoder(**cfg).eval()
+    _randomize_bn(ref)
+    for p in ref.parameters():
+        if p.dim() == 5:
+            p.data = p.data.half().float()
+    x = _rand_tensor([41, 128, 128], 20000, 64, 2, 11, clustered=True)
+    x.features = torch.relu(x.features)
+    rs, rfeats, _ = ref(x.features, x.indices, 2)
+    mod = SparseEncoder(**cfg)
+    missing = mod.load_state_dict(ref.state_dict(), strict=True)
+    mod = mod.cuda().eval()
+    gs, gfeats, _ = mod(x.features.half().cuda(), x.indices.cuda(), 2)
+    for a, b in zip(gfeats, rfeats):
+        assert a.spatial_shape == b.spatial_shape and torch.equal(a.indices.cpu(), b.indices)
+    assert gs.shape == rs.shape == (2, 512, 16, 16)
+    num = (gs.float().cpu() - rs).norm().item()
+    den = rs.norm().item()
+    mx = (gs.float().cpu() - rs).abs().max().item()
+    print('sparse encoder rel l2 err %.3e  max abs %.3e (max ref %.3f)' % (num / den, mx, rs.abs().max().item()))
+    assert num / den <= 3e-3, (num / den)
