@@ -155,6 +155,52 @@ int isf_sparse_to_dense(const void* feats, const int* indices, int v, int c, int
 int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, int c, int D, int H, int W, void* out,
                            int ldo, int ch_offset, void* stream);
 
+/* ---- a6: camera -> BEV (Point-to-Grid) -----------------------------------------
+ * replaces ISFusionEncoder.img_point_sampling + img_fv_to_bev (mmdet3d/models/middle_encoders/
+ * fusion_encoder.py:965-1070): 6*B F.grid_sample launches with [1,256,M*12,1] temporaries become one kernel
+ * (a warp per pillar).  pillars [M,P,nfeat] fp32 (zero-padded slots are projected too, Appendix C #1),
+ * pillar_coors [M,4] int32 (b,z,y,x), img_feat_nhwc [B,ncam,fh,fw,256] fp16, proj_dev [B*ncam,20] fp32 =
+ * {M(9) = lidar2img[:3,:3].inv(lidar_aug[:3,:3]), t(3), img_aug[:2,:3](6), img_aug[:2,3](2)}.
+ * Writes 256 channels at ch_off of the channels-last row (pitch ldo) of every non-empty pillar cell. */
+int isf_cam2bev(const float* pillars, int num_pillars, int points_per_pillar, int nfeat, const int* pillar_coors,
+                const void* img_feat_nhwc, const float* proj_dev, int batch, int ncam, int fh, int fw, int channels,
+                float img_w, float img_h, int bev_h, int bev_w, void* out_nhwc, int ldo, int ch_off, void* stream);
+
+/* ---- a8/a9: SST window attention core ------------------------------------------
+ * replaces get_window_coors / get_inner_win_inds / get_flat2win_inds_v2 / flat2window / nn.MultiheadAttention
+ * core / window2flat (mmdet3d/ops/sst/sst_ops.py:22-134,219-287; sst/sst_basic_block_v2.py:41-76) on a dense
+ * grid x grid BEV: qkv [B*grid*grid, 3C] fp16 (in_proj incl. bias), pos_q/pos_k [36,C] fp32 (Wq.pos, Wk.pos),
+ * shifted = 0 (aligned 6x6 windows) | 1 (shifted by 3).  out [B*grid*grid, C] fp16 (before out_proj). */
+int isf_window_attention(const void* qkv, const float* pos_q, const float* pos_k, int batch, int grid, int channels,
+                         int heads, int shifted, void* out, void* stream);
+
+/* ---- a10: heat-map NMS + top-K --------------------------------------------------
+ * replaces sigmoid / max_pool2d / argsort of fusion_encoder.py:1100-1131.  logits [B,classes,H,W] fp32;
+ * classes >= plain_from keep every cell (kernel-size-1 classes); top_idx [B,k] int32 = flat cell index. */
+int isf_heatmap_topk_workspace_size(int batch, int classes, int H, int W, size_t* bytes);
+int isf_heatmap_topk(const float* logits, int batch, int classes, int H, int W, int plain_from, int k, int* top_idx,
+                     float* top_score, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a11: multi-scale deformable attention forward ------------------------------
+ * replaces mmcv._ext.ms_deform_attn_forward (call site mmdet3d/models/middle_encoders/
+ * multi_scale_deformable_attn_function.py:118; kernel spec ops/src/cuda/ms_deform_im2col_cuda.cuh:34-83,238-298).
+ * value [B,S,H,D] fp32 or fp16, spatial_shapes int64 [L,2], level_start_index int64 [L] (device),
+ * sampling_loc [B,Q,H,L,P,2] fp32, attn_weight [B,Q,H,L,P] fp32 -> out [B,Q,H*D] fp32. */
+int isf_ms_deform_attn_forward(const void* value, int value_is_half, const long long* spatial_shapes,
+                               const long long* level_start_index, const float* sampling_loc,
+                               const float* attn_weight, int B, int S, int H, int D, int L, int Q, int P, float* out,
+                               void* stream);
+
+/* ---- a12: instance -> scene attention -------------------------------------------
+ * isf_i2s_attention: softmax(q k^T / sqrt(d)) v of fusion_encoder.py:441-462 for tokens x num_keys per frame:
+ *   q [B*tokens, C] fp16, kv [B, num_keys, 2C] fp16 (k | v), out [B*tokens, C] fp16.
+ * isf_channel_attention: out = S + softmax(S I^T, -1) I per (frame, channel) over the grid x grid plane
+ *   (fusion_encoder.py:495-500, no 1/sqrt(d)); scene / ins / out channels-last fp16 with pitches lds/ldi/ldo. */
+int isf_i2s_attention(const void* q, const void* kv, int batch, int tokens, int num_keys, int channels, int heads,
+                      void* out, void* stream);
+int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid, int channels,
+                          void* out, int ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,561 @@
+// Fusion-encoder kernels (SURVEY §8 rows a6, a9 core, a10, a11, a12):
+//   cam2bev            camera -> BEV: project 12 pillar points into 6 cameras, bilinear-gather the stride-16
+//                      feature map, sum cameras and points, write the BEV cell   (fusion_encoder.py:965-1070)
+//   window_attention   SST 6x6 window MHA core with analytic window partition     (sst_basic_block_v2.py:41-76,
+//                      sst_ops.py:219-268, sst_input_layer_v2.py:223-303)
+//   heatmap_topk       sigmoid + 3x3 local-max NMS + top-K                        (fusion_encoder.py:1100-1131)
+//   ms_deform_attn     deformable-attention bilinear gather                       (ops/src/cuda/ms_deform_im2col_cuda.cuh:238-298)
+//   i2s_attention      32 400 scene queries x 200 instance keys MHA core          (fusion_encoder.py:441-462)
+//   channel_attention  per-channel softmax(S.I^T).I + S over the 180x180 plane    (fusion_encoder.py:495-500)
+#include <cub/cub.cuh>
+#include "common.cuh"
+
+extern "C" void isf_count_launch(int n);
+
+// ================================================================================================
+// cam2bev
+// ================================================================================================
+struct CamProj {
+  float m[9];   // q = M p + t   (M = lidar2img[:3,:3] . inv(lidar_aug[:3,:3]))
+  float t[3];
+  float a[6];   // rows 0,1 of img_aug[:3,:3]
+  float at[2];
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) cam2bev_kernel(const float* __restrict__ pillars, int P, int nfeat,
+                                                      const int* __restrict__ pcoors, int M,
+                                                      const __half* __restrict__ feat,  // [B, ncam, h, w, C]
+                                                      const CamProj* __restrict__ proj,  // [B, ncam]
+                                                      int ncam, int fh, int fw, float img_w, float img_h, int bev_h,
+                                                      int bev_w, __half* __restrict__ out, int ldo, int ch_off) {
+  constexpr int CPL = C / 32;  // channels per lane (8 for C=256 -> one 16-byte load)
+  static_assert(CPL == 8, "cam2bev is built for 256 feature channels");
+  const int lane = threadIdx.x & 31;
+  const int pil = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pil >= M) return;
+  const int* pc = pcoors + (size_t)pil * 4;
+  const int b = pc[0], cy = pc[2], cx = pc[3];
+  float acc[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
+  const int total = P * ncam;
+  for (int base = 0; base < total; base += 32) {
+    const int idx = base + lane;
+    float ix = -10.f, iy = -10.f;
+    bool valid = false;
+    int cam = 0;
+    if (idx < total) {
+      const int pt = idx / ncam;
+      cam = idx - pt * ncam;
+      const float* p = pillars + ((size_t)pil * P + pt) * nfeat;
+      const CamProj& pr = proj[b * ncam + cam];
+      const float x = p[0], y = p[1], z = p[2];
+      float qx = pr.m[0] * x + pr.m[1] * y + pr.m[2] * z + pr.t[0];
+      float qy = pr.m[3] * x + pr.m[4] * y + pr.m[5] * z + pr.t[1];
+      float qz = pr.m[6] * x + pr.m[7] * y + pr.m[8] * z + pr.t[2];
+      qz = fminf(fmaxf(qz, 1e-5f), 1e5f);
+      const float u = qx / qz, v = qy / qz;
+      const float ua = pr.a[0] * u + pr.a[1] * v + pr.a[2] * qz + pr.at[0];
+      const float va = pr.a[3] * u + pr.a[4] * v + pr.a[5] * qz + pr.at[1];
+      const float gx = (ua / img_w - 0.5f) * 2.f, gy = (va / img_h - 0.5f) * 2.f;
+      // F.grid_sample, align_corners=False: pixel = ((g + 1) * size - 1) / 2
+      ix = ((gx + 1.f) * fw - 1.f) * 0.5f;
+      iy = ((gy + 1.f) * fh - 1.f) * 0.5f;
+      valid = ix > -1.f && ix < (float)fw && iy > -1.f && iy < (float)fh;   // at least one tap inside
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, valid);
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float fx = __shfl_sync(0xffffffffu, ix, j), fy = __shfl_sync(0xffffffffu, iy, j);
+      const int cj = __shfl_sync(0xffffffffu, cam, j);
+      const float x0f = floorf(fx), y0f = floorf(fy);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const float wx1 = fx - x0f, wy1 = fy - y0f, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+      const __half* fb = feat + ((size_t)(b * ncam + cj) * fh * fw) * C + lane * CPL;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+        if (xx < 0 || xx >= fw || yy < 0 || yy >= fh) continue;
+        const float w = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
+        const uint4 u4 = *(const uint4*)(fb + ((size_t)yy * fw + xx) * C);
+        const __half2* h2 = (const __half2*)&u4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          acc[e * 2] = fmaf(w, f.x, acc[e * 2]);
+          acc[e * 2 + 1] = fmaf(w, f.y, acc[e * 2 + 1]);
+        }
+      }
+    }
+  }
+  uint4 o;
+  __half2* oh = (__half2*)&o;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[e * 2], acc[e * 2 + 1]);
+  *(uint4*)(out + ((size_t)(b * bev_h + cy) * bev_w + cx) * ldo + ch_off + lane * CPL) = o;
+}
+
+// proj: HOST array of B*ncam CamProj-layout floats (20 floats each) copied by the caller to device memory
+extern "C" int isf_cam2bev(const float* pillars, int num_pillars, int points_per_pillar, int nfeat,
+                           const int* pillar_coors, const void* img_feat_nhwc, const float* proj_dev, int batch,
+                           int ncam, int fh, int fw, int channels, float img_w, float img_h, int bev_h, int bev_w,
+                           void* out_nhwc, int ldo, int ch_off, void* stream) {
+  ISF_CHECK_ARG(num_pillars >= 0 && points_per_pillar >= 1 && nfeat >= 3 && ncam >= 1 && batch >= 1);
+  if (channels != 256) { isf_set_error("cam2bev: built for 256 image-feature channels"); return ISF_ERR_UNSUPPORTED; }
+  ISF_CHECK_ARG(ldo % 8 == 0 && ch_off % 8 == 0);
+  if (num_pillars == 0) return ISF_OK;
+  ISF_CHECK_ARG(pillars && pillar_coors && img_feat_nhwc && proj_dev && out_nhwc);
+  int blocks = isf_cdiv(num_pillars, 8);
+  cam2bev_kernel<256><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      pillars, points_per_pillar, nfeat, pillar_coors, num_pillars, (const __half*)img_feat_nhwc,
+      (const CamProj*)proj_dev, ncam, fh, fw, img_w, img_h, bev_h, bev_w, (__half*)out_nhwc, ldo, ch_off);
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ================================================================================================
+// SST window attention core
+// ================================================================================================
+// qkv [B*S*S, 3C] fp16 (in_proj output incl. bias, no positional term), pos_q/pos_k [36, C] fp32
+// (= Wq.pos / Wk.pos of the in-window sinusoid, precomputed), out [B*S*S, C] fp16.
+// One CTA per window (b, wy, wx) of the partition with shift s (6 = aligned, 3 = shifted by half a window);
+// thread = (head, query slot).  Keys outside the grid are masked (key_padding_mask of the reference).
+template <int C, int HEADS>
+__global__ void __launch_bounds__(HEADS * 36) window_attention_kernel(const __half* __restrict__ qkv,
+                                                                      const float* __restrict__ pos_q,
+                                                                      const float* __restrict__ pos_k, int S, int shift,
+                                                                      int nwin, float scaling, __half* __restrict__ out) {
+  constexpr int D = C / HEADS;
+  constexpr int WIN = 6, TOK = 36;
+  __shared__ __half ks[TOK][C];
+  __shared__ __half vs[TOK][C];
+  __shared__ int tok_id[TOK];
+  const int w = blockIdx.x;
+  const int b = w / (nwin * nwin);
+  const int wy = (w / nwin) % nwin, wx = w % nwin;
+  // aligned partition: window origin = w*6; shifted: origin = w*6 - 3
+  const int oy = wy * WIN - (shift == 3 ? 3 : 0), ox = wx * WIN - (shift == 3 ? 3 : 0);
+  const int tid = threadIdx.x;
+  if (tid < TOK) {
+    const int iy = tid / WIN, ix = tid % WIN;
+    const int y = oy + iy, x = ox + ix;
+    tok_id[tid] = (y >= 0 && y < S && x >= 0 && x < S) ? (b * S + y) * S + x : -1;
+  }
+  __syncthreads();
+  // cooperative load of K (+pos) and V
+  for (int e = tid; e < TOK * (C / 8); e += blockDim.x) {
+    const int slot = e / (C / 8), c8 = (e % (C / 8)) * 8;
+    const int t = tok_id[slot];
+    uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (t >= 0) {
+      const __half* row = qkv + (size_t)t * 3 * C;
+      kk = *(const uint4*)(row + C + c8);
+      vv = *(const uint4*)(row + 2 * C + c8);
+      __half2* k2 = (__half2*)&kk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __half22float2(k2[i]);
+        f.x += pos_k[slot * C + c8 + 2 * i];
+        f.y += pos_k[slot * C + c8 + 2 * i + 1];
+        k2[i] = __floats2half2_rn(f.x, f.y);
+      }
+    }
+    *(uint4*)&ks[slot][c8] = kk;
+    *(uint4*)&vs[slot][c8] = vv;
+  }
+  __syncthreads();
+  const int h = tid / TOK, qs = tid % TOK;
+  const int tq = tok_id[qs];
+  if (tq < 0) return;
+  float q[D];
+  {
+    const __half* row = qkv + (size_t)tq * 3 * C + h * D;
+#pragma unroll
+    for (int i = 0; i < D; ++i) q[i] = (__half2float(row[i]) + pos_q[qs * C + h * D + i]) * scaling;
+  }
+  float sc[TOK];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < TOK; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; i += 2) {
+      const float2 kf = __half22float2(*(const __half2*)&ks[j][h * D + i]);
+      s = fmaf(q[i], kf.x, s);
+      s = fmaf(q[i + 1], kf.y, s);
+    }
+    s = tok_id[j] >= 0 ? s : -INFINITY;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < TOK; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.f / sum;
+  float o[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < TOK; ++j) {
+    const float pj = sc[j] * inv;
+#pragma unroll
+    for (int i = 0; i < D; i += 2) {
+      const float2 vf = __half22float2(*(const __half2*)&vs[j][h * D + i]);
+      o[i] = fmaf(pj, vf.x, o[i]);
+      o[i + 1] = fmaf(pj, vf.y, o[i + 1]);
+    }
+  }
+  __half* orow = out + (size_t)tq * C + h * D;
+#pragma unroll
+  for (int i = 0; i < D; i += 2) *(__half2*)(orow + i) = __floats2half2_rn(o[i], o[i + 1]);
+}
+
+extern "C" int isf_window_attention(const void* qkv, const float* pos_q, const float* pos_k, int batch, int grid,
+                                    int channels, int heads, int shifted, void* out, void* stream) {
+  ISF_CHECK_ARG(qkv && pos_q && pos_k && out && batch >= 1 && grid >= 1 && heads == 8);
+  const int nwin = shifted ? (grid + 3 + 5) / 6 : (grid + 5) / 6;
+  const int shift = shifted ? 3 : 6;
+  const int blocks = batch * nwin * nwin;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channels == 128) {
+    window_attention_kernel<128, 8><<<blocks, 288, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+                                                             1.0f / sqrtf(16.f), (__half*)out);
+  } else if (channels == 256) {
+    window_attention_kernel<256, 8><<<blocks, 288, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+                                                             1.0f / sqrtf(32.f), (__half*)out);
+  } else {
+    isf_set_error("window_attention: channels must be 128 or 256");
+    return ISF_ERR_UNSUPPORTED;
+  }
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ================================================================================================
+// heat-map NMS + top-K
+// ================================================================================================
+__global__ void __launch_bounds__(256) heatmap_nms_kernel(const float* __restrict__ logits, int C, int H, int W,
+                                                          int plain_from, unsigned int* __restrict__ keys,
+                                                          int* __restrict__ vals) {
+  const int n = C * H * W;
+  const int b = blockIdx.y;
+  const float* lg = logits + (size_t)b * n;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int c = t / (H * W), r = (t / W) % H, x = t % W;
+    const float v = lg[t];
+    bool keep;
+    if (c >= plain_from) {
+      keep = true;                               // kernel-size-1 classes (fusion_encoder.py:1107-1115)
+    } else if (r == 0 || r == H - 1 || x == 0 || x == W - 1) {
+      keep = false;                              // local_max is 0 on the border (:1102-1105)
+    } else {
+      float m = v;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) m = fmaxf(m, lg[(c * H + r + dy) * W + x + dx]);
+      keep = (v == m);                           // sigmoid is monotone: compare logits
+    }
+    const float s = keep ? 1.f / (1.f + __expf(-v)) : 0.f;
+    keys[(size_t)b * n + t] = __float_as_uint(s);  // s >= 0: uint order == float order
+    vals[(size_t)b * n + t] = t;
+  }
+}
+
+__global__ void take_topk_kernel(const unsigned int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted,
+                                 int n, int k, int hw, int* __restrict__ top_idx, float* __restrict__ top_score) {
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    top_idx[b * k + j] = vals_sorted[(size_t)b * n + j] % hw;
+    if (top_score) top_score[b * k + j] = __uint_as_float(keys_sorted[(size_t)b * n + j]);
+  }
+}
+
+static size_t topk_cub_bytes(int n) {
+  size_t a = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, a, (unsigned int*)nullptr, (unsigned int*)nullptr, (int*)nullptr,
+                                            (int*)nullptr, n);
+  return a;
+}
+
+extern "C" int isf_heatmap_topk_workspace_size(int batch, int classes, int H, int W, size_t* bytes) {
+  ISF_CHECK_ARG(bytes && batch >= 1);
+  const size_t n = (size_t)classes * H * W;
+  IsfArena A(nullptr, 0);
+  A.take<unsigned int>(batch * n); A.take<unsigned int>(batch * n); A.take<int>(batch * n); A.take<int>(batch * n);
+  A.take<char>(topk_cub_bytes((int)n));
+  *bytes = A.off + 1024;
+  return ISF_OK;
+}
+
+// logits [B, classes, H, W] fp32 (pre-sigmoid); classes >= plain_from use a 1x1 "NMS"; top_idx [B, k] int32 =
+// flat spatial index (index % (H*W)) of the k best (class, cell) scores, descending (stable on ties).
+extern "C" int isf_heatmap_topk(const float* logits, int batch, int classes, int H, int W, int plain_from, int k,
+                                int* top_idx, float* top_score, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(logits && top_idx && workspace && batch >= 1 && k >= 1 && k <= classes * H * W);
+  const int n = classes * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  IsfArena A(workspace, ws_bytes);
+  unsigned int* keys = A.take<unsigned int>((size_t)batch * n);
+  unsigned int* keys_s = A.take<unsigned int>((size_t)batch * n);
+  int* vals = A.take<int>((size_t)batch * n);
+  int* vals_s = A.take<int>((size_t)batch * n);
+  size_t cb = topk_cub_bytes(n);
+  void* tmp = A.take<char>(cb);
+  if (!A.ok) { isf_set_error("heatmap_topk: workspace too small"); return ISF_ERR_WORKSPACE; }
+  heatmap_nms_kernel<<<dim3(ISF_NUM_SMS * 2, batch), 256, 0, st>>>(logits, classes, H, W, plain_from, keys, vals);
+  for (int b = 0; b < batch; ++b) {
+    size_t t = cb;
+    ISF_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, t, keys + (size_t)b * n, keys_s + (size_t)b * n,
+                                                       vals + (size_t)b * n, vals_s + (size_t)b * n, n, 0, 32, st));
+  }
+  take_topk_kernel<<<batch, 256, 0, st>>>(keys_s, vals_s, n, k, H * W, top_idx, top_score);
+  isf_count_launch(2 + 4 * batch);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ================================================================================================
+// multi-scale deformable attention (forward)
+// ================================================================================================
+template <typename T>
+__device__ __forceinline__ float ldv(const T* p);
+template <>
+__device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldv<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) msda_kernel(const T* __restrict__ value, const long long* __restrict__ shapes,
+                                                   const long long* __restrict__ lvl_start,
+                                                   const float* __restrict__ loc, const float* __restrict__ attn,
+                                                   int B, int S, int H, int D, int L, int Q, int P,
+                                                   float* __restrict__ out) {
+  const long long n = (long long)B * Q * H * D;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(t % D);
+    long long r = t / D;
+    const int h = (int)(r % H); r /= H;
+    const int q = (int)(r % Q);
+    const int b = (int)(r / Q);
+    const long long samp = ((long long)b * Q + q) * H + h;
+    const float* lp = loc + samp * L * P * 2;
+    const float* ap = attn + samp * L * P;
+    float col = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const int sh = (int)shapes[2 * l], sw = (int)shapes[2 * l + 1];
+      const T* vb = value + ((long long)b * S + lvl_start[l]) * H * D + h * D + d;
+      for (int p = 0; p < P; ++p) {
+        const float lw = lp[(l * P + p) * 2], lh = lp[(l * P + p) * 2 + 1];
+        const float wgt = ap[l * P + p];
+        const float him = lh * sh - 0.5f, wim = lw * sw - 0.5f;
+        if (him > -1.f && wim > -1.f && him < (float)sh && wim < (float)sw) {
+          const int hl = (int)floorf(him), wl = (int)floorf(wim);
+          const float lhh = him - hl, lww = wim - wl, hh = 1.f - lhh, hw = 1.f - lww;
+          float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+          const int stride = H * D;
+          if (hl >= 0 && wl >= 0) v1 = ldv(vb + ((long long)hl * sw + wl) * stride);
+          if (hl >= 0 && wl + 1 <= sw - 1) v2 = ldv(vb + ((long long)hl * sw + wl + 1) * stride);
+          if (hl + 1 <= sh - 1 && wl >= 0) v3 = ldv(vb + ((long long)(hl + 1) * sw + wl) * stride);
+          if (hl + 1 <= sh - 1 && wl + 1 <= sw - 1) v4 = ldv(vb + ((long long)(hl + 1) * sw + wl + 1) * stride);
+          col += (hh * hw * v1 + hh * lww * v2 + lhh * hw * v3 + lhh * lww * v4) * wgt;
+        }
+      }
+    }
+    out[t] = col;
+  }
+}
+
+// value [B,S,H,D] (fp32 or fp16), spatial_shapes int64 [L,2] (h,w), level_start_index int64 [L] (both DEVICE),
+// sampling_loc [B,Q,H,L,P,2] fp32 in [0,1] (x = width first), attn_weight [B,Q,H,L,P] fp32 -> out [B,Q,H*D] fp32
+extern "C" int isf_ms_deform_attn_forward(const void* value, int value_is_half, const long long* spatial_shapes,
+                                          const long long* level_start_index, const float* sampling_loc,
+                                          const float* attn_weight, int B, int S, int H, int D, int L, int Q, int P,
+                                          float* out, void* stream) {
+  ISF_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out);
+  ISF_CHECK_ARG(B >= 1 && S >= 1 && H >= 1 && D >= 1 && L >= 1 && Q >= 1 && P >= 1);
+  long long n = (long long)B * Q * H * D;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (value_is_half)
+    msda_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)value, spatial_shapes, level_start_index, sampling_loc,
+                                                 attn_weight, B, S, H, D, L, Q, P, out);
+  else
+    msda_kernel<float><<<blocks, 256, 0, st>>>((const float*)value, spatial_shapes, level_start_index, sampling_loc,
+                                                attn_weight, B, S, H, D, L, Q, P, out);
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ================================================================================================
+// instance -> scene attention core: softmax(q k^T * scale) v, 32 400 queries x 200 keys per frame
+// ================================================================================================
+// q [B*T, C] fp16 (projected, bias added), kv [B, NK, 2C] fp16 (k | v projected), out [B*T, C] fp16.
+template <int C, int HEADS, int NK_MAX>
+__global__ void __launch_bounds__(256) i2s_attention_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
+                                                            int T, int NK, float scaling, __half* __restrict__ out) {
+  constexpr int D = C / HEADS;
+  extern __shared__ __half sm_kv[];   // [NK][2C]
+  const int b = blockIdx.y;
+  const __half* kvb = kv + (size_t)b * NK * 2 * C;
+  for (int e = threadIdx.x; e < NK * 2 * C / 8; e += blockDim.x) ((uint4*)sm_kv)[e] = ((const uint4*)kvb)[e];
+  __syncthreads();
+  const int QPB = 256 / HEADS;   // queries per block
+  const int h = threadIdx.x / QPB, ql = threadIdx.x % QPB;
+  for (int q0 = blockIdx.x * QPB; q0 < T; q0 += gridDim.x * QPB) {
+    const int qi = q0 + ql;
+    if (qi >= T) continue;
+    const __half* qrow = q + ((size_t)b * T + qi) * C + h * D;
+    float qv[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) qv[i] = __half2float(qrow[i]) * scaling;
+    float m = -INFINITY, l = 0.f;
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    for (int j = 0; j < NK; ++j) {
+      const __half* kr = sm_kv + (size_t)j * 2 * C + h * D;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < D; i += 2) {
+        const float2 kf = __half22float2(*(const __half2*)(kr + i));
+        s = fmaf(qv[i], kf.x, s);
+        s = fmaf(qv[i + 1], kf.y, s);
+      }
+      const float mn = fmaxf(m, s);
+      const float corr = __expf(m - mn), pj = __expf(s - mn);
+      l = l * corr + pj;
+      const __half* vr = kr + C;
+#pragma unroll
+      for (int i = 0; i < D; i += 2) {
+        const float2 vf = __half22float2(*(const __half2*)(vr + i));
+        o[i] = fmaf(pj, vf.x, o[i] * corr);
+        o[i + 1] = fmaf(pj, vf.y, o[i + 1] * corr);
+      }
+      m = mn;
+    }
+    const float inv = 1.f / l;
+    __half* orow = out + ((size_t)b * T + qi) * C + h * D;
+#pragma unroll
+    for (int i = 0; i < D; i += 2) *(__half2*)(orow + i) = __floats2half2_rn(o[i] * inv, o[i + 1] * inv);
+  }
+}
+
+extern "C" int isf_i2s_attention(const void* q, const void* kv, int batch, int tokens, int num_keys, int channels,
+                                 int heads, void* out, void* stream) {
+  ISF_CHECK_ARG(q && kv && out && batch >= 1 && tokens >= 1 && num_keys >= 1);
+  if (channels != 128 || heads != 8) { isf_set_error("i2s_attention: built for d_model 128, 8 heads"); return ISF_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)num_keys * 2 * channels * sizeof(__half);
+  ISF_CHECK_ARG(smem <= 200 * 1024 && (num_keys * 2 * channels) % 8 == 0);
+  static bool cfg = false;
+  if (!cfg) {
+    ISF_CUDA(cudaFuncSetAttribute(i2s_attention_kernel<128, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg = true;
+  }
+  int bx = isf_cdiv(tokens, 32);
+  if (bx > ISF_NUM_SMS * 2) bx = ISF_NUM_SMS * 2;
+  i2s_attention_kernel<128, 8, 256><<<dim3(bx, batch), 256, smem, (cudaStream_t)stream>>>(
+      (const __half*)q, (const __half*)kv, tokens, num_keys, 1.0f / sqrtf(16.f), (__half*)out);
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ================================================================================================
+// channel-wise scene attention: out[b,c] = S + softmax(S I^T, -1) I   with S, I the [G,G] planes of channel c
+// ================================================================================================
+// scene, ins: NHWC fp16 [B, G, G, ld*]; out NHWC fp16.  One CTA per (b, c); planes staged in smem (fp16, padded).
+__global__ void __launch_bounds__(256) channel_attention_kernel(const __half* __restrict__ scene, int lds,
+                                                                const __half* __restrict__ ins, int ldi, int G, int C,
+                                                                __half* __restrict__ out, int ldo) {
+  extern __shared__ __half sm[];
+  const int GP = G + 2 + ((G & 1) ? 1 : 0);      // padded row pitch (halfs), even, odd number of 32-bit words
+  __half* Sp = sm;
+  __half* Ip = sm + (size_t)G * GP;
+  float* prow = (float*)(Ip + (size_t)G * GP);    // [8 warps][G] softmax rows
+  const int b = blockIdx.x / C, c = blockIdx.x % C;
+  const size_t plane = (size_t)b * G * G;
+  for (int e = threadIdx.x; e < G * G; e += blockDim.x) {
+    const int y = e / G, x = e % G;
+    Sp[y * GP + x] = scene[(plane + e) * lds + c];
+    Ip[y * GP + x] = ins[(plane + e) * ldi + c];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = prow + warp * G;
+  const int NJ = (G + 31) / 32;
+  for (int y = warp; y < G; y += 8) {
+    // logits[x2] = sum_k S[y][k] * I[x2][k]
+    float lg[8];
+    float mx = -INFINITY;
+    for (int j = 0; j < NJ; ++j) {
+      const int x2 = lane + 32 * j;
+      float s = -INFINITY;
+      if (x2 < G) {
+        s = 0.f;
+        const __half* sr = Sp + y * GP;
+        const __half* ir = Ip + x2 * GP;
+        for (int k = 0; k < G; k += 2) {
+          const float2 a = __half22float2(*(const __half2*)(sr + k));
+          const float2 bb = __half22float2(*(const __half2*)(ir + k));
+          s = fmaf(a.x, bb.x, s);
+          if (k + 1 < G) s = fmaf(a.y, bb.y, s);
+        }
+      }
+      lg[j] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = 0; j < NJ; ++j) {
+      const int x2 = lane + 32 * j;
+      const float e = x2 < G ? __expf(lg[j] - mx) : 0.f;
+      lg[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    __syncwarp();
+    for (int j = 0; j < NJ; ++j) {
+      const int x2 = lane + 32 * j;
+      if (x2 < G) pr[x2] = lg[j] * inv;
+    }
+    __syncwarp();
+    // out[y][x] = S[y][x] + sum_x2 p[x2] * I[x2][x]
+    for (int j = 0; j < NJ; ++j) {
+      const int x = lane + 32 * j;
+      if (x < G) {
+        float acc = 0.f;
+        for (int x2 = 0; x2 < G; ++x2) acc = fmaf(pr[x2], __half2float(Ip[x2 * GP + x]), acc);
+        acc += __half2float(Sp[y * GP + x]);
+        out[(plane + (size_t)y * G + x) * ldo + c] = __float2half_rn(acc);
+      }
+    }
+  }
+}
+
+extern "C" int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid,
+                                     int channels, void* out, int ldo, void* stream) {
+  ISF_CHECK_ARG(scene && ins && out && batch >= 1 && grid >= 2 && grid <= 256 && channels >= 1);
+  const int GP = grid + 2 + ((grid & 1) ? 1 : 0);
+  const size_t smem = (size_t)2 * grid * GP * sizeof(__half) + 8 * grid * sizeof(float);
+  ISF_CHECK_ARG(smem <= 227 * 1024);
+  static bool cfg = false;
+  if (!cfg) {
+    ISF_CUDA(cudaFuncSetAttribute(channel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg = true;
+  }
+  channel_attention_kernel<<<batch * channels, 256, smem, (cudaStream_t)stream>>>(
+      (const __half*)scene, lds, (const __half*)ins, ldi, grid, channels, (__half*)out, ldo);
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}

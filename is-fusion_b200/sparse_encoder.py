@@ -117,7 +117,7 @@ class SparseEncoder(nn.Module):
         return out_channels
 
     @torch.no_grad()
-    def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, **kwargs):
+    def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True, **kwargs):
         """voxel_features [V,C], coors [V,4] int32 (b,z,y,x) -> (spatial_features [B, C*D, H, W], encode_features, kwargs)"""
         coors = coors.int()
         feats = voxel_features if voxel_features.dtype == torch.float16 else voxel_features.half()
@@ -128,8 +128,10 @@ class SparseEncoder(nn.Module):
             x = encoder_layer(x)
             encode_features.append(x)
         out = self.conv_out(encode_features[-1])
+        self.last_out = out
+        if not dense:      # fast path: the fusion encoder scatters `out` straight into its channels-last buffer
+            return None, encode_features, kwargs
         spatial_features = out.dense()
         n, c, d, h, w = spatial_features.shape
         spatial_features = spatial_features.view(n, c * d, h, w)
-        self.last_out = out
         return spatial_features, encode_features, kwargs

@@ -1,0 +1,210 @@
+"""GPU parity of the fusion-encoder kernels and of the whole neck against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import fusion_ops as fo
+from oracle import model as omodel
+from oracle import sst_ops as ss
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item(), (a - b).abs().max().item()
+
+
+def build_pair(seed=0, shuffle=False):
+    import isfusion_b200.detector as det
+    torch.manual_seed(seed)
+    cfg = omodel.neck_config()
+    ref = synth.randomize_bn(omodel.ISFusionNeck(cfg, shuffle_voxels=shuffle)).eval()
+    net = det.ISFusionDetector(
+        pts_voxel_layer=dict(point_cloud_range=cfg['pc_range'], max_num_points=-1, voxel_size=cfg['voxel_size'], max_voxels=(-1, -1)),
+        pts_voxel_encoder=dict(type='DynamicVFE', **cfg['pts_voxel_encoder']),
+        pts_middle_encoder=dict(type='SparseEncoder', **cfg['pts_middle_encoder']),
+        fusion_encoder=dict(type='ISFusionEncoder', **cfg['fusion_encoder']),
+        pts_backbone=dict(type='SECONDV2', **cfg['pts_backbone']),
+        detach=True, pc_range=cfg['pc_range'], voxel_size=cfg['voxel_size'], out_size_factor=8)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.cuda().eval()
+
+
+def test_msda_golden_and_oracle(golden_dir):
+    from isfusion_b200.fusion_encoder import ms_deform_attn
+    g = np.load(os.path.join(golden_dir, 'msda_ref.npz'))
+    # case A: ops/test.py shapes (2 levels), fp32
+    shapes = torch.from_numpy(g['a_shapes']).cuda()
+    lvl = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    out = ms_deform_attn(torch.from_numpy(g['a_value']).cuda(), shapes, lvl, torch.from_numpy(g['a_loc']).cuda(),
+                         torch.from_numpy(g['a_aw']).cuda())
+    assert torch.allclose(out.cpu(), torch.from_numpy(g['a_out']), rtol=1e-2, atol=1e-3)   # tolerance of ops/test.py:58
+    assert (out.cpu() - torch.from_numpy(g['a_out'])).abs().max() < 1e-6
+    # case B: IGF head layout, fp16 value
+    shapes = torch.tensor([[40, 44]]).cuda()
+    value = torch.from_numpy(g['b_value_f16']).cuda()
+    out = ms_deform_attn(value, shapes, torch.zeros(1, dtype=torch.long).cuda(), torch.from_numpy(g['b_loc']).cuda(),
+                         torch.from_numpy(g['b_aw']).cuda())
+    assert (out.cpu() - torch.from_numpy(g['b_out'])).abs().max() < 1e-4
+    # full IGF shape against the oracle restatement
+    torch.manual_seed(0)
+    value = torch.randn(2, 32400, 8, 16)
+    loc = torch.rand(2, 200, 8, 1, 16, 2) * 1.1 - 0.05
+    aw = torch.softmax(torch.randn(2, 200, 8, 16), -1).view(2, 200, 8, 1, 16)
+    shapes = torch.tensor([[180, 180]])
+    ref = fo.ms_deform_attn_core_pytorch(value, shapes, loc, aw)
+    out = ms_deform_attn(value.cuda(), shapes.cuda(), torch.zeros(1, dtype=torch.long).cuda(), loc.cuda(), aw.cuda())
+    assert (out.cpu() - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize('g,c,b', [(18, 128, 2), (21, 256, 1), (180, 128, 1), (90, 256, 2)])
+def test_sst_level_parity(g, c, b):
+    """SSTInputLayerV2 + SSTv2 (one shifted-window block) on a dense grid; partial windows when 6 does not divide g."""
+    from isfusion_b200.fusion_encoder import SSTInputLayerV2, SSTv2
+    torch.manual_seed(g + c)
+    di = {0: {'max_tokens': 36, 'drop_range': (0, 100000)}}
+    rl = ss.SSTInputLayerV2(di, (6, 6, 1), [g, g, 1], shuffle_voxels=True, pos_temperature=1000, pos_embed=c)
+    rn = ss.SSTv2([c] * 4, [8] * 4, 1, [c] * 4, output_shape=[g, g], in_channel=128 if c == 128 else None).eval()
+    for n_, p in rn.named_parameters():
+        if 'bias' in n_:
+            p.data.normal_(0, 0.05)
+    ys, xs = torch.meshgrid(torch.arange(g), torch.arange(g), indexing='ij')
+    coords = torch.cat([torch.stack([torch.full((g * g,), i), torch.zeros(g * g, dtype=torch.long), ys.flatten(), xs.flatten()], 1)
+                        for i in range(b)]).int()
+    feats = torch.randn(b * g * g, 128 if c == 128 else c).half().float()
+    ref = rn(rl(feats, coords, b))[0]
+    gl = SSTInputLayerV2(di, (6, 6, 1), [g, g, 1], pos_temperature=1000, pos_embed=c)
+    gn = SSTv2([c] * 4, [8] * 4, 1, [c] * 4, output_shape=[g, g], in_channel=128 if c == 128 else None)
+    gn.load_state_dict(rn.state_dict())
+    gn = gn.cuda().eval()
+    out = gn(gl(feats.half().cuda(), None, b))[0]
+    assert out.shape == ref.shape
+    r, m = rel(out, ref)
+    assert r < 3e-3, (r, m)       # two post-norm layers in fp16 storage / fp32 accumulate
+
+
+def test_cam2bev_parity():
+    from isfusion_b200.fusion_encoder import ISFusionEncoder
+    from isfusion_b200.voxel_layer import Voxelization
+    from oracle import voxel_ops as vo
+    cfg = omodel.neck_config()['fusion_encoder']
+    B = 2
+    pts = [synth.make_points(20000, 'S', s) for s in range(B)]
+    l2i, aug, laug = synth.make_calib(B)
+    laug[1, :3, :3] = torch.tensor([[0.98, -0.199, 0.], [0.199, 0.98, 0.], [0., 0., 1.]]) * 1.02    # exercise the inverse aug
+    laug[1, :3, 3] = torch.tensor([0.5, -0.3, 0.1])
+    feats = synth.make_img_feats(B)
+    feats[1] = feats[1].half().float()
+    ref_enc = fo.ISFusionEncoder(**cfg)
+    pv, pc, pn = [], [], []
+    for i, p in enumerate(pts):
+        v, c, n = vo.hard_voxelize(p, [0.6, 0.6, 8.0], synth.PC_RANGE, 12, 60000)
+        pv.append(v); pc.append(torch.nn.functional.pad(c, (1, 0), value=i)); pn.append(n)
+    pm = dict(pillars=torch.cat(pv), pillar_coors=torch.cat(pc), pillars_num_points=torch.cat(pn))
+    kw = dict(img_metas=[dict(input_shape=(256, 704))] * B, lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    ref = ref_enc.img_fv_to_bev([feats[1]], B, pts_metas=pm, **kw)
+    enc = ISFusionEncoder(**cfg).cuda()
+    pmg = {k: v.cuda() for k, v in pm.items()}
+    out = enc.img_fv_to_bev([feats[1].cuda()], B, pts_metas=pmg, **kw)
+    out = out.permute(0, 3, 1, 2)
+    r, m = rel(out, ref)
+    print('cam2bev rel %.2e max %.2e (ref max %.2f, nonzero cells %d)' % (r, m, ref.abs().max(), (ref.abs().sum(1) > 0).sum()))
+    assert (ref.abs().sum(1) > 0).sum() > 1000
+    assert r < 2e-3 and m < 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_heatmap_topk():
+    import ctypes
+    from isfusion_b200 import _lib as L
+    torch.manual_seed(0)
+    B, C, G, K = 2, 10, 180, 200
+    logits = torch.randn(B, C, G, G)
+    hm = logits.sigmoid()
+    lm = torch.zeros_like(hm)
+    lm[:, :, 1:-1, 1:-1] = torch.nn.functional.max_pool2d(hm, 3, stride=1, padding=0)
+    lm[:, 8] = hm[:, 8]; lm[:, 9] = hm[:, 9]
+    sc = (hm * (hm == lm)).view(B, -1)
+    ref_scores, ref_idx = sc.sort(dim=-1, descending=True, stable=True)
+    ws_bytes = ctypes.c_size_t(0)
+    L.check(L.lib().isf_heatmap_topk_workspace_size(B, C, G, G, ctypes.byref(ws_bytes)))
+    ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device='cuda')
+    top = torch.empty((B, K), dtype=torch.int32, device='cuda')
+    score = torch.empty((B, K), dtype=torch.float32, device='cuda')
+    lg = logits.cuda()
+    L.check(L.lib().isf_heatmap_topk(L.ptr(lg), B, C, G, G, 8, K, L.ptr(top), L.ptr(score), L.ptr(ws),
+                                     ctypes.c_size_t(ws.numel()), L.stream()))
+    assert torch.equal(top.cpu().long(), ref_idx[:, :K] % (G * G))
+    assert torch.allclose(score.cpu(), ref_scores[:, :K], atol=1e-6)
+
+
+def test_instance_to_scene_parity():
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.gemm import gemm, pack_weight
+    torch.manual_seed(0)
+    B, C, G, K = 2, 128, 180, 200
+    ref = fo.Instane2SceneAtt(C).eval()
+    ref.multihead_attn.in_proj_bias.data.normal_(0, 0.05)
+    q = (torch.randn(B, C, G * G) * 0.5).half().float()
+    key = torch.randn(B, C, K).half().float()
+    scene = (torch.randn(B, C, G, G) * 0.3).half().float()
+    want = ref(q, key, scene, B, G)
+    mha = ref.multihead_attn
+    qt = q.permute(0, 2, 1).reshape(B * G * G, C).half().cuda().contiguous()
+    qq = gemm(qt, pack_weight(mha.in_proj_weight.data[:C].cuda()), shift=mha.in_proj_bias.data[:C].cuda().contiguous())
+    kv = torch.nn.functional.linear(key.permute(0, 2, 1), mha.in_proj_weight.data[C:], mha.in_proj_bias.data[C:]).half().cuda().contiguous()
+    att = torch.empty_like(qq)
+    L.check(L.lib().isf_i2s_attention(L.ptr(qq), L.ptr(kv), B, G * G, K, C, 8, L.ptr(att), L.stream()))
+    qi = gemm(att, pack_weight(mha.out_proj.weight.data.cuda()), shift=mha.out_proj.bias.data.cuda().contiguous(), residual=qt,
+              ln=(ref.norm.weight.data.cuda().contiguous(), ref.norm.bias.data.cuda().contiguous(), ref.norm.eps))
+    sc = scene.permute(0, 2, 3, 1).half().cuda().contiguous()
+    out = torch.empty_like(sc)
+    L.check(L.lib().isf_channel_attention(L.ptr(sc), C, L.ptr(qi), C, B, G, C, L.ptr(out), C, L.stream()))
+    r, m = rel(out.permute(0, 3, 1, 2), want)
+    print('i2s rel %.2e max %.2e' % (r, m))
+    assert r < 3e-3, (r, m)
+
+
+def test_secondv2_parity():
+    from isfusion_b200.fusion_encoder import SECONDV2
+    torch.manual_seed(0)
+    cfg = omodel.neck_config()['pts_backbone']
+    ref = synth.randomize_bn(fo.SECONDV2(**cfg)).eval()
+    net = SECONDV2(**cfg)
+    net.load_state_dict(ref.state_dict())
+    net = net.cuda().eval()
+    x = torch.randn(1, 128, 60, 60).half().float()
+    rt, rc, rf = ref([x], 'stage1')
+    xt = x.half().cuda().contiguous(memory_format=torch.channels_last)
+    gt, _, gf = net([xt], 'stage1')
+    assert rel(gf, rf)[0] < 3e-3 and rel(gt, rt)[0] < 3e-3
+    r2 = ref([rt.view(1, 30, 30, 256).permute(0, 3, 1, 2)], 'stage2')[2]
+    g2 = net([gt.view(1, 30, 30, 256).permute(0, 3, 1, 2)], 'stage2')[2]
+    assert rel(g2, r2)[0] < 5e-3
+
+
+@pytest.mark.parametrize('npts,batch', [(20000, 1), (12000, 2)])
+def test_neck_end_to_end(npts, batch):
+    """BASELINE configs[0]: synthetic frame(s), 6x256x704 cameras, whole neck vs the CPU oracle."""
+    ref, net = build_pair(0)
+    pts = [synth.make_points(npts, 'S', s) for s in range(batch)]
+    l2i, aug, laug = synth.make_calib(batch)
+    feats = synth.make_img_feats(batch)
+    metas = [dict(input_shape=(256, 704))] * batch
+    rf, rhm = ref(pts, feats, metas, lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    gf, ghm = net([p.cuda() for p in pts], [f.cuda() for f in feats], metas, lidar2img=l2i, img_aug_matrix=aug,
+                  lidar_aug_matrix=laug)
+    dbg_r, dbg_g = ref.fusion_encoder._dbg, net.fusion_encoder._dbg
+    r_hm, m_hm = rel(ghm, rhm)
+    overlap = np.mean([len(set(dbg_r['top_idx'][b].tolist()) & set(dbg_g['top_idx'][b].cpu().tolist())) / 200.0
+                       for b in range(batch)])
+    r0, m0 = rel(gf[0], rf[0])
+    r1, m1 = rel(gf[1], rf[1])
+    print('neck e2e: heatmap rel %.2e | top-200 overlap %.3f | feat0 rel %.2e max %.2e | feat1 rel %.2e max %.2e'
+          % (r_hm, overlap, r0, m0, r1, m1))
+    assert gf[0].shape == rf[0].shape and gf[1].shape == rf[1].shape and ghm.shape == rhm.shape
+    assert r_hm < 5e-3 and overlap > 0.9
+    assert r0 < 1e-2 and r1 < 1e-2
