@@ -117,7 +117,29 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm):
     return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out)
 
 
+PROFILE = None      # bench.py: list collecting (start_event, end_event, issued_flops, rulebook) per launch
+
+
+def useful_flops(rb_cin_cout):
+    """2 * pairs * Cin * Cout of one launch (pairs counted once per rulebook, outside any timed region)."""
+    rb, cin, cout = rb_cin_cout
+    if rb.pairs is None:
+        rb.pairs = int((rb.nbr[:, :rb.num_out] >= 0).sum().item())
+    return 2.0 * rb.pairs * cin * cout
+
+
 def implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, residual=None, relu=False, out=None):
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = _implicit_gemm(feats, rb, w_packed, cin, cout, scale, shift, residual, relu, out)
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * rb.num_out * rb.taps * cin * cout, (rb, cin, cout)))
+        return r
+    return _implicit_gemm(feats, rb, w_packed, cin, cout, scale, shift, residual, relu, out)
+
+
+def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, residual=None, relu=False, out=None):
     if feats.dtype != torch.float16:
         raise L.IsfError('sparse conv: fp16 features expected')
     L.require_cuda(feats, w_packed, scale, shift, residual)
