@@ -73,12 +73,42 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons}
 
 
+def log(msg):
+    sys.stderr.write('[bench %.1fs] %s\n' % (time.time() - T0, msg))
+    sys.stderr.flush()
+    try:
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'bench_progress.log'), 'a') as f:
+            f.write('[%.1fs] %s\n' % (time.time() - T0, msg))
+    except Exception:
+        pass
+
+
+T0 = time.time()
+
+
+def host_threads():
+    """threads the CPU arm may use: the cores this process is allowed on (cgroup/affinity aware), capped at 64
+    (the oracle's ops are small; more threads only add OpenMP overhead)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:   # cgroup v2 cpu.max quota
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def oracle_fps(points, cloud, steps, warmup, threads=None):
     """CPU arm: the oracle neck forward on the host cores."""
     import torch
     import synth
     from oracle import model as omodel
-    threads = threads or os.cpu_count()
+    threads = threads or host_threads()
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     net = synth.randomize_bn(omodel.ISFusionNeck(shuffle_voxels=True)).eval()
@@ -92,11 +122,29 @@ def oracle_fps(points, cloud, steps, warmup, threads=None):
         t0 = time.perf_counter()
         net(pts, feats, metas, timings=tm, lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
         dt = time.perf_counter() - t0
+        log('cpu oracle frame %d (%d pts, %d threads): %.1f s' % (i, pts[0].shape[0], threads, dt))
         if i >= warmup:
             times.append(dt)
             for k, v in tm.items():
                 stages[k] = stages.get(k, 0.0) + v / steps
     return steps / sum(times), threads, {k: round(v, 3) for k, v in stages.items()}
+
+
+def cpu_baseline_subprocess(args, deadline=200):
+    """the CPU arm in a child process with a hard deadline (a mis-sized OpenMP pool must not stall the bench)."""
+    for pts_n in [args.cpu_points or args.points, 20000]:
+        cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+               '--points', str(args.points), '--cpu-points', str(pts_n), '--cloud', args.cloud]
+        try:
+            env = dict(os.environ)
+            for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+                env.pop(k, None)
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=deadline, env=env).stdout.strip().splitlines()
+            line = json.loads(out[-1])
+            return line['cpu_baseline']
+        except Exception as e:
+            log('cpu baseline with %d points failed or timed out (%s); falling back' % (pts_n, type(e).__name__))
+    return {'value': None, 'unit': 'frames/s', 'cores': host_threads(), 'kind': 'port', 'sample': 'timed out'}
 
 
 def run_reference(args):
@@ -108,7 +156,8 @@ def run_reference(args):
     cpu_points = args.cpu_points or args.points
     fps, threads, stages = oracle_fps(cpu_points, args.cloud, steps, warm)
     sample = ('%d frame(s) of %d %s-cloud points + 6x256x704 cameras through the CPU oracle (1 warm-up on a 5k-point frame); '
-              'same workload as the B200 arm (%d points)' % (steps, cpu_points, args.cloud, args.points))
+              '%s (B200 arm: %d points)' % (steps, cpu_points, args.cloud,
+                                            'same workload' if cpu_points == args.points else 'smaller bounded sample', args.points))
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': 1000.0 / fps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
@@ -204,7 +253,9 @@ def main():
     sampler.start()
     L.launch_count(reset=True)
     spmod.PROFILE = prof
+    log('model + %d frames resident; timing %d+%d steps' % (F_, args.warmup, args.steps))
     ms = timed(step_resident, args.steps, args.warmup)
+    log('resident: %.3f ms/step' % (ms / args.steps))
     spmod.PROFILE = None
     sampler.stop_flag = True
     launches = L.launch_count(reset=True)
@@ -213,6 +264,7 @@ def main():
     fps = world * B * args.steps / (ms / 1000.0)
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup), base=7)
     fps_e2e = world * B * args.steps / (ms_e2e / 1000.0)
+    log('e2e: %.3f ms/step' % (ms_e2e / args.steps))
     out_bytes = sum(h.numel() * h.element_size() for h in out_host)
 
     roof = None
@@ -239,12 +291,7 @@ def main():
                         'zero-filled (no-neighbour) slots the output-stationary tiles also multiply'}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_points = args.cpu_points or args.points
-        cfps, threads, stages = oracle_fps(cpu_points, args.cloud, 1, 1)
-        cpu = {'value': cfps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-               'sample': '1 frame of %d %s-cloud points through the CPU oracle after a 5k-point warm-up frame (~20-30 s of '
-                         'CPU work); same workload as the GPU arm' % (cpu_points, args.cloud),
-               'stage_seconds': stages}
+        cpu = cpu_baseline_subprocess(args)
     if rank == 0:
         line = {'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
