@@ -470,28 +470,34 @@ extern "C" int isf_i2s_attention(const void* q, const void* kv, int batch, int t
 // ================================================================================================
 // channel-wise scene attention: out[b,c] = S + softmax(S I^T, -1) I   with S, I the [G,G] planes of channel c
 // ================================================================================================
-// scene, ins: NHWC fp16 [B, G, G, ld*]; out NHWC fp16.  One CTA per (b, c); planes staged in smem (fp16, padded).
+// scene, ins: NHWC fp16 [B, G, G, ld*]; out NHWC fp16.  One CTA per (b, c, row slab): the whole I plane and a
+// slab of S rows are staged in smem (fp16, padded pitch), a warp owns one output row at a time.
+constexpr int CA_SPLIT = 3;
 __global__ void __launch_bounds__(256) channel_attention_kernel(const __half* __restrict__ scene, int lds,
                                                                 const __half* __restrict__ ins, int ldi, int G, int C,
                                                                 __half* __restrict__ out, int ldo) {
   extern __shared__ __half sm[];
-  const int GP = G + 2 + ((G & 1) ? 1 : 0);      // padded row pitch (halfs), even, odd number of 32-bit words
-  __half* Sp = sm;
-  __half* Ip = sm + (size_t)G * GP;
-  float* prow = (float*)(Ip + (size_t)G * GP);    // [8 warps][G] softmax rows
-  const int b = blockIdx.x / C, c = blockIdx.x % C;
+  const int GP = G + 2 + ((G & 1) ? 1 : 0);      // padded row pitch (halfs): odd number of 32-bit words
+  const int slab = (G + CA_SPLIT - 1) / CA_SPLIT;
+  __half* Ip = sm;
+  __half* Sp = sm + (size_t)G * GP;
+  float* prow = (float*)(Sp + (size_t)slab * GP);    // [8 warps][G] softmax rows
+  const int part = blockIdx.x % CA_SPLIT;
+  const int bc = blockIdx.x / CA_SPLIT;
+  const int b = bc / C, c = bc % C;
+  const int y0 = part * slab, y1 = min(G, y0 + slab);
   const size_t plane = (size_t)b * G * G;
   for (int e = threadIdx.x; e < G * G; e += blockDim.x) {
     const int y = e / G, x = e % G;
-    Sp[y * GP + x] = scene[(plane + e) * lds + c];
     Ip[y * GP + x] = ins[(plane + e) * ldi + c];
+    if (y >= y0 && y < y1) Sp[(y - y0) * GP + x] = scene[(plane + e) * lds + c];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* pr = prow + warp * G;
   const int NJ = (G + 31) / 32;
-  for (int y = warp; y < G; y += 8) {
-    // logits[x2] = sum_k S[y][k] * I[x2][k]
+  for (int y = y0 + warp; y < y1; y += 8) {
+    const __half* sr = Sp + (y - y0) * GP;
     float lg[8];
     float mx = -INFINITY;
     for (int j = 0; j < NJ; ++j) {
@@ -499,7 +505,6 @@ __global__ void __launch_bounds__(256) channel_attention_kernel(const __half* __
       float s = -INFINITY;
       if (x2 < G) {
         s = 0.f;
-        const __half* sr = Sp + y * GP;
         const __half* ir = Ip + x2 * GP;
         for (int k = 0; k < G; k += 2) {
           const float2 a = __half22float2(*(const __half2*)(sr + k));
@@ -535,7 +540,7 @@ __global__ void __launch_bounds__(256) channel_attention_kernel(const __half* __
       if (x < G) {
         float acc = 0.f;
         for (int x2 = 0; x2 < G; ++x2) acc = fmaf(pr[x2], __half2float(Ip[x2 * GP + x]), acc);
-        acc += __half2float(Sp[y * GP + x]);
+        acc += __half2float(sr[x]);
         out[(plane + (size_t)y * G + x) * ldo + c] = __float2half_rn(acc);
       }
     }
@@ -546,14 +551,15 @@ extern "C" int isf_channel_attention(const void* scene, int lds, const void* ins
                                      int channels, void* out, int ldo, void* stream) {
   ISF_CHECK_ARG(scene && ins && out && batch >= 1 && grid >= 2 && grid <= 256 && channels >= 1);
   const int GP = grid + 2 + ((grid & 1) ? 1 : 0);
-  const size_t smem = (size_t)2 * grid * GP * sizeof(__half) + 8 * grid * sizeof(float);
+  const int slab = (grid + CA_SPLIT - 1) / CA_SPLIT;
+  const size_t smem = (size_t)(grid + slab) * GP * sizeof(__half) + 8 * grid * sizeof(float);
   ISF_CHECK_ARG(smem <= 227 * 1024);
   static bool cfg = false;
   if (!cfg) {
     ISF_CUDA(cudaFuncSetAttribute(channel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cfg = true;
   }
-  channel_attention_kernel<<<batch * channels, 256, smem, (cudaStream_t)stream>>>(
+  channel_attention_kernel<<<batch * channels * CA_SPLIT, 256, smem, (cudaStream_t)stream>>>(
       (const __half*)scene, lds, (const __half*)ins, ldi, grid, channels, (__half*)out, ldo);
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();

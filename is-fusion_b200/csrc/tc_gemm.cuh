@@ -139,6 +139,8 @@ struct GemmParams {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 fp16 = 128 B = one swizzle row
 constexpr int PRODUCERS = 128;  // 4 warps
+constexpr int MAX_TAPS = 27;
+constexpr int MAX_CHUNKS = 512;
 constexpr int THREADS = PRODUCERS + 32;
 
 template <int BN, int STAGES>
@@ -146,7 +148,9 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int NBR_OFF = STAGES * STAGE_BYTES;            // [MAX_TAPS][128] int32 neighbour tile
+  static constexpr int LIST_OFF = NBR_OFF + MAX_TAPS * BM * 4;     // active chunk list (uint16) + flags
+  static constexpr int BAR_OFF = LIST_OFF + MAX_CHUNKS * 2 + 64 * 4;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + tmem slot, + alignment slack
 };
 
@@ -182,19 +186,59 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
 
   uint32_t chunk_ctr = 0;   // running chunk counter across tiles (stage = ctr % STAGES, use = ctr / STAGES)
   uint32_t tile_ctr = 0;
+  int* nbr_s = (int*)(smem + SL::NBR_OFF);
+  uint16_t* chunk_list = (uint16_t*)(smem + SL::LIST_OFF);
+  int* tap_flag = (int*)(smem + SL::LIST_OFF + MAX_CHUNKS * 2);   // [32] flags + [1] active count at index 32
+  const bool gather = p.nbr != nullptr;
 
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_ctr) {
     const int row0 = tile * BM;
+    // ---------------------------------------------------------------- tile prologue: neighbour tile -> smem,
+    // list of K-chunks that have at least one neighbour in this tile (empty kernel offsets are skipped)
+    if (warp < 4) {
+      const int r = tid;
+      const int grow = row0 + r;
+      const bool row_ok = grow < m_total;
+      if (gather) {
+        if (tid < 33) tap_flag[tid] = 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int t = 0; t < p.taps; ++t) {
+          const int v = row_ok ? p.nbr[(long long)t * p.nbr_stride + grow] : -1;
+          nbr_s[t * BM + r] = v;
+          if (v >= 0) tap_flag[t] = 1;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (warp == 0) {
+        int count = 0;
+        for (int base = 0; base < num_chunks; base += 32) {
+          const int q = base + lane;
+          bool act = q < num_chunks;
+          if (act && gather) {
+            const int t0 = (q * BK) / p.cin, t1 = (q * BK + BK - 1) / p.cin;
+            bool any = false;
+            for (int t = t0; t <= t1 && t < p.taps; ++t) any |= tap_flag[t] != 0;
+            act = any;
+          }
+          const unsigned mask = __ballot_sync(0xffffffffu, act);
+          if (act) chunk_list[count + __popc(mask & ((1u << lane) - 1))] = (uint16_t)q;
+          count += __popc(mask);
+        }
+        if (count == 0) { if (lane == 0) chunk_list[0] = 0; count = 1; }   // keeps the accumulator defined
+        if (lane == 0) tap_flag[32] = count;
+      }
+    }
+    __syncthreads();
+    const int n_act = tap_flag[32];
     if (warp < 4) {
       // ------------------------------------------------ producers
       const int r = tid;                       // A row inside the tile
       const int grow = row0 + r;
       const bool row_ok = grow < m_total;
-      int cur_tap = -1;
-      long long src_row = -1;
       uint32_t c0 = chunk_ctr;
-      for (int q = 0; q < num_chunks; ++q) {
-        const uint32_t cc = c0 + q;
+      for (int i = 0; i < n_act; ++i) {
+        const int q = chunk_list[i];
+        const uint32_t cc = c0 + i;
         const int s = cc % STAGES;
         if (cc >= STAGES) mbar_wait(&empty_bar[s], ((cc / STAGES) - 1) & 1);
         uint8_t* sa = smem + s * SL::STAGE_BYTES;
@@ -206,11 +250,8 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
           const int k = q * BK + c * 8;
           const int tap = k / p.cin;
           const int ch = k - tap * p.cin;
-          if (tap != cur_tap) {
-            cur_tap = tap;
-            src_row = -1;
-            if (row_ok && tap < p.taps) src_row = p.nbr ? (long long)p.nbr[(long long)tap * p.nbr_stride + grow] : grow;
-          }
+          long long src_row = -1;
+          if (tap < p.taps) src_row = gather ? (long long)nbr_s[tap * BM + r] : (row_ok ? (long long)grow : -1);
           const bool ok = src_row >= 0;
           const __half* src = ok ? p.A + src_row * p.cin + ch : p.A;
           cp_async16(a_row + ((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);
@@ -218,26 +259,26 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
         // B: BN rows x 8 pieces, spread over the 128 producer threads
         const uint32_t b_base = smem_u32(sb);
 #pragma unroll
-        for (int i = 0; i < BN * 8 / PRODUCERS; ++i) {
-          const int piece = tid + i * PRODUCERS;
+        for (int j = 0; j < BN * 8 / PRODUCERS; ++j) {
+          const int piece = tid + j * PRODUCERS;
           const int n = piece >> 3, c = piece & 7;
           const __half* src = p.W + (long long)(n0 + n) * p.kpad + q * BK + c * 8;
           cp_async16(b_base + n * 128 + ((c ^ (n & 7)) << 4), src, 16u);
         }
         cp_async_commit();
-        if (q >= STAGES - 1) {
+        if (i >= STAGES - 1) {
           cp_async_wait<STAGES - 1>();
           fence_proxy_async();
           mbar_arrive(&full_bar[(cc - (STAGES - 1)) % STAGES]);
         }
       }
-      // drain: the last (STAGES-1) chunks (or all of them when num_chunks < STAGES-1)
+      // drain: the last (STAGES-1) chunks (or all of them when n_act < STAGES-1)
       cp_async_wait<0>();
       fence_proxy_async();
       {
-        int first = num_chunks - (STAGES - 1);
+        int first = n_act - (STAGES - 1);
         if (first < 0) first = 0;
-        for (int q = first; q < num_chunks; ++q) mbar_arrive(&full_bar[(c0 + q) % STAGES]);
+        for (int i = first; i < n_act; ++i) mbar_arrive(&full_bar[(c0 + i) % STAGES]);
       }
       // ------------------------------------------------ epilogue
       mbar_wait(accum_bar, tile_ctr & 1);
@@ -331,7 +372,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
       // ------------------------------------------------ MMA issuer (warp 4)
       constexpr uint32_t idesc = make_idesc_f16(BM, BN);
       uint32_t c0 = chunk_ctr;
-      for (int q = 0; q < num_chunks; ++q) {
+      for (int q = 0; q < n_act; ++q) {
         const uint32_t cc = c0 + q;
         const int s = cc % STAGES;
         mbar_wait(&full_bar[s], (cc / STAGES) & 1);
@@ -347,12 +388,12 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
             umma_f16(tmem_base, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
-          if (q == num_chunks - 1) umma_commit(accum_bar);
+          if (q == n_act - 1) umma_commit(accum_bar);
         }
         __syncwarp();
       }
     }
-    chunk_ctr += num_chunks;
+    chunk_ctr += n_act;
     // The epilogue of tile t must finish reading TMEM before the MMA warp starts tile t+1.
     __syncthreads();
     tc_fence_after();
@@ -389,6 +430,10 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
 }
 
 static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  if (p.taps > MAX_TAPS || p.kpad / BK > MAX_CHUNKS) {
+    isf_set_error("gemm: taps=%d (max %d) / K chunks=%d (max %d) out of range", p.taps, MAX_TAPS, p.kpad / BK, MAX_CHUNKS);
+    return ISF_ERR_UNSUPPORTED;
+  }
   switch (bn) {
     case 32: return launch_gemm<32, 4>(p, m_upper, st);
     case 64: return launch_gemm<64, 4>(p, m_upper, st);

@@ -243,9 +243,16 @@ class SparseConv3d(SparseConvolution):
 
 
 def fold_bn(bn):
+    """eval-mode BN -> fp32 (scale, shift); cached on the module, invalidated when its buffers change version."""
+    key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, bn.weight.device)
+    cached = bn.__dict__.get('_isf_fold')
+    if cached is not None and cached[0] == key:
+        return cached[1]
     scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float()
     shift = (bn.bias - bn.running_mean * scale).detach().float()
-    return scale.contiguous(), shift.contiguous()
+    out = (scale.contiguous(), shift.contiguous())
+    bn.__dict__['_isf_fold'] = (key, out)
+    return out
 
 
 class SparseSequential(SparseModule, nn.Sequential):

@@ -52,11 +52,12 @@ def conv_time(conv, cur, name):
     global tot_flops
     rb = timed(lambda: sp_mod.build_rulebook(cur, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.subm), name + ' rulebook', 3)
     pairs = int((rb.nbr[:, :rb.num_out] >= 0).sum().item())
+    tile_occ = (rb.nbr >= 0).view(rb.taps, -1, 128).any(-1).float().mean().item()
     w = conv.packed_weight()
     f = timed(lambda: sp_mod.implicit_gemm(cur.features, rb, w, conv.in_channels, conv.out_channels, relu=True), name + ' gemm', 5)
     flops = 2.0 * pairs * conv.in_channels * conv.out_channels
     dense_flops = 2.0 * rb.num_out * rb.taps * conv.in_channels * conv.out_channels
-    print('    V_in %d V_out %d pairs %d (%.0f%% of slots)  useful %.1f GF  issued %.1f GF' % (cur.features.shape[0], rb.num_out, pairs, 100.0 * pairs / max(rb.num_out * rb.taps, 1), flops / 1e9, dense_flops / 1e9))
+    print('    V_in %d V_out %d pairs %d (%.0f%% of slots, %.0f%% of (tile,tap) non-empty)  useful %.1f GF  issued %.1f GF' % (cur.features.shape[0], rb.num_out, pairs, 100.0 * pairs / max(rb.num_out * rb.taps, 1), 100 * tile_occ, flops / 1e9, dense_flops / 1e9))
     out = sp_mod.SparseConvTensor(f, rb.out_indices, rb.out_shape, cur.batch_size)
     return out
 cur = conv_time(enc.conv_input[0], cur, 'conv_input 64->32')
