@@ -243,18 +243,24 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
         if (cc >= STAGES) mbar_wait(&empty_bar[s], ((cc / STAGES) - 1) & 1);
         uint8_t* sa = smem + s * SL::STAGE_BYTES;
         uint8_t* sb = sa + SL::A_BYTES;
-        // A: 8 pieces of 16 B for this thread's row
-        const uint32_t a_row = smem_u32(sa) + r * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        // A: the 128 x 128 B tile as 8 warp-coalesced sweeps: lane -> (row = t/8 + 16 j, 16-byte piece = t%8), so a
+        // warp instruction fetches 4 whole 128 B rows (full 32 B sectors) instead of 32 half-used sectors
+        {
+          const int c = tid & 7;
           const int k = q * BK + c * 8;
           const int tap = k / p.cin;
           const int ch = k - tap * p.cin;
-          long long src_row = -1;
-          if (tap < p.taps) src_row = gather ? (long long)nbr_s[tap * BM + r] : (row_ok ? (long long)grow : -1);
-          const bool ok = src_row >= 0;
-          const __half* src = ok ? p.A + src_row * p.cin + ch : p.A;
-          cp_async16(a_row + ((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+          const bool tap_ok = tap < p.taps;
+          const uint32_t a_base = smem_u32(sa);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = (tid >> 3) + 16 * j;
+            long long src_row = -1;
+            if (tap_ok) src_row = gather ? (long long)nbr_s[tap * BM + rr] : ((row0 + rr) < m_total ? (long long)(row0 + rr) : -1);
+            const bool ok = src_row >= 0;
+            const __half* src = ok ? p.A + src_row * p.cin + ch : p.A;
+            cp_async16(a_base + rr * 128 + ((c ^ (rr & 7)) << 4), src, ok ? 16u : 0u);
+          }
         }
         // B: BN rows x 8 pieces, spread over the 128 producer threads
         const uint32_t b_base = smem_u32(sb);
