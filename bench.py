@@ -36,6 +36,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=16, help='distinct resident frames rotated through (L2 defeat)')
     ap.add_argument('--cpu-points', type=int, default=0, help='points of the CPU-baseline sample frame (0 = same as --points)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--stages', action='store_true', help='extra pass with per-stage CUDA-event timers')
     return ap.parse_args()
 
 
@@ -267,6 +268,15 @@ def main():
     log('e2e: %.3f ms/step' % (ms_e2e / args.steps))
     out_bytes = sum(h.numel() * h.element_size() for h in out_host)
 
+    stage_ms = None
+    if args.stages:
+        from isfusion_b200 import profiling
+        profiling.ENABLED = True
+        profiling.reset()
+        for i in range(args.steps):
+            step_resident(100 + i)
+        stage_ms = {k: round(v / args.steps, 4) for k, v in profiling.summary().items()}
+        profiling.ENABLED = False
     roof = None
     if prof:
         torch.cuda.synchronize()
@@ -307,6 +317,8 @@ def main():
                 'gpu_launches_note': 'kernels of libisfusion_b200.so (incl. its CUB passes) in the timed region; the dense 3x3 '
                                      'convs additionally run on cuDNN through torch',
                 'roofline': roof, 'cpu_baseline': cpu}
+        if stage_ms:
+            line['stage_ms'] = stage_ms
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

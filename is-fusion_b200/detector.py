@@ -8,6 +8,7 @@ from torch import nn
 
 from . import fusion_encoder, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
 from .registry import DETECTORS, build_backbone, build_fusion_layer, build_middle_encoder, build_voxel_encoder
+from .profiling import stage
 from .voxel_layer import Voxelization
 
 
@@ -52,7 +53,8 @@ class ISFusionDetector(nn.Module):
 
     def isfusion(self, pts, pts_feats, img_feats, img_metas, batch_size, **kwargs):
         """ref: isfusion.py:84-101."""
-        pillars, pillars_num_points, pillar_coors = self.voxelize(pts, voxel_type='pillar')
+        with stage('a5 pillarize'):
+            pillars, pillars_num_points, pillar_coors = self.voxelize(pts, voxel_type='pillar')
         pts_metas = dict(pillars=pillars, pillars_num_points=pillars_num_points, pillar_coors=pillar_coors, pts=pts,
                          pillar_size=self.pillar_size)
         kwargs.update(dict(pts_metas=pts_metas, img_metas=img_metas, pts_backbone=self.pts_backbone))
@@ -61,11 +63,14 @@ class ISFusionDetector(nn.Module):
     @torch.no_grad()
     def extract_pts_feat(self, pts, img_feats, img_metas, **kwargs):
         """ref: isfusion.py:103-121 without pts_neck; returns ([feat_0, feat_1], ins_heatmap)."""
-        voxels, coors = self.dynamic_voxelize(pts)
+        with stage('a1 dynamic_voxelize'):
+            voxels, coors = self.dynamic_voxelize(pts)
         batch_size = len(pts)
-        voxel_features, feature_coors = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas,
-                                                               batch_size=batch_size)
-        x, _, kwargs = self.pts_middle_encoder(voxel_features, feature_coors, batch_size, dense=False, **kwargs)
+        with stage('a3 dynamic_vfe'):
+            voxel_features, feature_coors = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas,
+                                                                   batch_size=batch_size)
+        with stage('a4 sparse_encoder'):
+            x, _, kwargs = self.pts_middle_encoder(voxel_features, feature_coors, batch_size, dense=False, **kwargs)
         kwargs['lidar_sparse'] = self.pts_middle_encoder.last_out
         return self.isfusion(pts, x, img_feats, img_metas, batch_size, **kwargs)
 

@@ -19,6 +19,7 @@ from torch import nn
 
 from . import _lib as L
 from .gemm import gemm, pack_weight
+from .profiling import stage
 from .registry import (BACKBONES, FUSION_LAYERS, MIDDLE_ENCODERS, ConvModule, build_backbone, build_conv_layer,
                        build_middle_encoder, build_norm_layer)
 
@@ -566,8 +567,9 @@ class ISFusionEncoder(_Packable):
         dev = img_mlvl_feats[1].device
         pk = self._pack(dev)
         g = self.bev_size
-        cat = torch.zeros((bs, g, g, self.embed_dims * 3), dtype=torch.float16, device=dev)
-        self.img_fv_to_bev([img_mlvl_feats[1]], bs, out=cat, **kwargs)
+        with stage('a6 cam2bev'):
+            cat = torch.zeros((bs, g, g, self.embed_dims * 3), dtype=torch.float16, device=dev)
+            self.img_fv_to_bev([img_mlvl_feats[1]], bs, out=cat, **kwargs)
         sp = kwargs.get('lidar_sparse')
         if sp is not None:
             d = sp.spatial_shape[0]
@@ -576,17 +578,21 @@ class ISFusionEncoder(_Packable):
                                                    self.embed_dims, L.stream()))
         else:
             cat[..., self.embed_dims:] = lidar_feats.permute(0, 2, 3, 1)
-        bev = _conv(cat, pk['fusion'])                                     # [B,G,G,128]
+        with stage('a7 conv_fusion'):
+            bev = _conv(cat, pk['fusion'])                                 # [B,G,G,128]
         pts_backbone = kwargs.get('pts_backbone', None)
         grid_features = bev.reshape(bs * g * g, -1)
         ins_hm = None
         return_feats = []
         for i in range(len(self.get_regions)):
-            x = self.get_regions[i](grid_features, None, bs)
-            x = self.grid2region_att[i](x)
+            with stage('a8+a9 sst level %d' % i):
+                x = self.get_regions[i](grid_features, None, bs)
+                x = self.grid2region_att[i](x)
             if i == 0:
-                fused, ins_hm = self.instance_fusion(bev, x[0].permute(0, 2, 3, 1), bs, **kwargs)
+                with stage('a10-a13 instance fusion'):
+                    fused, ins_hm = self.instance_fusion(bev, x[0].permute(0, 2, 3, 1), bs, **kwargs)
                 x[0] = fused.permute(0, 3, 1, 2)
-            grid_features, _, this_feat = pts_backbone(x, 'stage{}'.format(i + 1))
+            with stage('a14 secondv2 stage%d' % (i + 1)):
+                grid_features, _, this_feat = pts_backbone(x, 'stage{}'.format(i + 1))
             return_feats.append(this_feat)
         return return_feats, ins_hm
