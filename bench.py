@@ -205,18 +205,29 @@ def main():
     dev_sets = [([p.to(dev) for p in pts], [t.to(dev) for t in feats]) for pts, feats in host_sets]
     in_bytes = sum(p.numel() * 4 for p in host_sets[0][0]) + host_sets[0][1][1].numel() * 4
 
-    def step_resident(i):
+    from isfusion_b200.detector import GraphedNeck
+    log('calibrating buffer capacities on 2 frames (exact mode)')
+    caps = GraphedNeck.calibrate(net, [dev_sets[0][0], dev_sets[1 % F_][0]], dev_sets[0][1], metas, margin=1.35, **kw)
+    npts_cap = max(p.shape[0] for pts, _ in host_sets for p in pts)
+    gn = GraphedNeck(net, B, npts_cap, img_hw=(256, 704), calib=kw, capacities=caps, device=dev)
+    gn.load(dev_sets[0][0], dev_sets[0][1][1])
+    gn.capture()
+    log('graph captured; strided-conv capacities %s' % caps)
+
+    def step_eager(i):
         pts, feats = dev_sets[i % F_]
         return net(pts, feats, metas, **kw)
+
+    def step_resident(i):
+        pts, feats = dev_sets[i % F_]
+        return gn(pts, feats[1])            # D2D copy into the graph's static inputs + one graph replay
 
     out_host = None
 
     def step_e2e(i):
         nonlocal out_host
         pts, feats = host_sets[i % F_]
-        dp = [p.to(dev, non_blocking=True) for p in pts]
-        df = [feats[0][:0].to(dev), feats[1].to(dev, non_blocking=True), feats[2][:0].to(dev)]   # only level 1 is read
-        o, _ = net(dp, df, metas, **kw)
+        o, _ = gn(pts, feats[1])            # pinned host -> static device buffers (H2D), replay
         if out_host is None:
             out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in o]
         for h, t in zip(out_host, o):
@@ -255,13 +266,20 @@ def main():
     L.launch_count(reset=True)
     spmod.PROFILE = prof
     log('model + %d frames resident; timing %d+%d steps' % (F_, args.warmup, args.steps))
-    ms = timed(step_resident, args.steps, args.warmup)
-    log('resident: %.3f ms/step' % (ms / args.steps))
+    ms_eager = timed(step_eager, args.steps, args.warmup)
+    log('eager (exact mode, host syncs): %.3f ms/step' % (ms_eager / args.steps))
     spmod.PROFILE = None
+    L.launch_count(reset=True)
+    ms = timed(step_resident, args.steps, args.warmup)
+    over = gn.check()
+    log('graph replay: %.3f ms/step  overflow=%s' % (ms / args.steps, over))
+    if over:
+        raise SystemExit('bench.py: strided-conv capacity overflow %s (raise the calibration margin)' % over)
     sampler.stop_flag = True
-    launches = L.launch_count(reset=True)
     steps_total = args.steps + args.warmup
-    own_per_step = launches / steps_total
+    L.launch_count(reset=True)
+    step_eager(0)
+    own_per_step = L.launch_count(reset=True)      # kernels of one frame (graph replays launch the same set)
     fps = world * B * args.steps / (ms / 1000.0)
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup), base=7)
     fps_e2e = world * B * args.steps / (ms_e2e / 1000.0)
@@ -274,7 +292,7 @@ def main():
         profiling.ENABLED = True
         profiling.reset()
         for i in range(args.steps):
-            step_resident(100 + i)
+            step_eager(100 + i)
         stage_ms = {k: round(v / args.steps, 4) for k, v in profiling.summary().items()}
         profiling.ENABLED = False
     roof = None
@@ -296,7 +314,7 @@ def main():
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF/s sustained',
                 'unit': 'TFLOP/s', 'frac': useful / (t_ms * 1e-3) / 1e12 / peak, 'traffic': None,
                 'launches': len(rec), 'kernel_ms_per_step': t_ms / args.steps,
-                'share_of_step': (t_ms / args.steps) / (ms / args.steps),
+                'share_of_step': (t_ms / args.steps) / (ms_eager / args.steps),
                 'note': 'achieved = 2*pairs*Cin*Cout summed over launches / summed CUDA-event time; achieved_issued counts the '
                         'zero-filled (no-neighbour) slots the output-stationary tiles also multiply'}
     cpu = None
@@ -313,7 +331,7 @@ def main():
                 'clocks': sampler.summary(),
                 'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
                         'ms_per_step': ms_e2e / args.steps},
-                'gpu_launches': int(round(own_per_step * args.steps)),
+                'gpu_launches': int(round(own_per_step * args.steps)), 'eager_ms_per_step': ms_eager / args.steps,
                 'gpu_launches_note': 'kernels of libisfusion_b200.so (incl. its CUB passes) in the timed region; the dense 3x3 '
                                      'convs additionally run on cuDNN through torch',
                 'roofline': roof, 'cpu_baseline': cpu}

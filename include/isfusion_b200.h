@@ -122,6 +122,8 @@ int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad, int n, co
  *
  * isf_hash_build: coordinate -> row hash table over `indices`.  `table` = 2*capacity 32-bit words
  *   (capacity = isf_hash_capacity(v), a power of two >= 2v).
+ * (every *_dev count argument is optional: when given it overrides the host count, which then is the capacity
+ *  of the buffer — this is what keeps the whole encoder free of host synchronisation / graph-capturable.)
  * isf_spconv_out_indices: output sites of a strided SparseConv3d = sorted-unique linear index of every
  *   (input, kernel offset) candidate (the GPU ordering of spconv_ops.h:129-137); writes up to out_cap
  *   rows and the count to *num_out_dev.
@@ -139,7 +141,7 @@ int isf_hash_build(const int* indices, int v, const int* v_dev, const int* spati
 int isf_spconv_out_shape(const int* in_shape, const int* ksize, const int* stride, const int* padding,
                          const int* dilation, int* out_shape);
 int isf_spconv_out_indices_workspace_size(int v_in, int kvol, size_t* bytes);
-int isf_spconv_out_indices(const int* in_indices, int v_in, const int* in_shape, int batch, const int* ksize,
+int isf_spconv_out_indices(const int* in_indices, int v_in, const int* v_in_dev, const int* in_shape, int batch, const int* ksize,
                            const int* stride, const int* padding, const int* dilation, int* out_indices,
                            int out_cap, int* num_out_dev, void* workspace, size_t ws_bytes, void* stream);
 int isf_spconv_neighbors(const int* out_indices, int v_out, const int* v_out_dev, const void* in_table,
@@ -152,8 +154,8 @@ int isf_spconv_implicit_gemm(const void* feats_in, int cin, const void* w_packed
                              void* out_f16, int ldo, void* stream);
 int isf_sparse_to_dense(const void* feats, const int* indices, int v, int c, int batch, int D, int H, int W,
                         void* out, void* stream);
-int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, int c, int D, int H, int W, void* out,
-                           int ldo, int ch_offset, void* stream);
+int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, const int* v_dev, int c, int D, int H, int W,
+                           void* out, int ldo, int ch_offset, void* stream);
 
 /* ---- a6: camera -> BEV (Point-to-Grid) -----------------------------------------
  * replaces ISFusionEncoder.img_point_sampling + img_fv_to_bev (mmdet3d/models/middle_encoders/
@@ -161,9 +163,12 @@ int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, int c, 
  * (a warp per pillar).  pillars [M,P,nfeat] fp32 (zero-padded slots are projected too, Appendix C #1),
  * pillar_coors [M,4] int32 (b,z,y,x), img_feat_nhwc [B,ncam,fh,fw,256] fp16, proj_dev [B*ncam,20] fp32 =
  * {M(9) = lidar2img[:3,:3].inv(lidar_aug[:3,:3]), t(3), img_aug[:2,:3](6), img_aug[:2,3](2)}.
- * Writes 256 channels at ch_off of the channels-last row (pitch ldo) of every non-empty pillar cell. */
-int isf_cam2bev(const float* pillars, int num_pillars, int points_per_pillar, int nfeat, const int* pillar_coors,
-                const void* img_feat_nhwc, const float* proj_dev, int batch, int ncam, int fh, int fw, int channels,
+ * Writes 256 channels at ch_off of the channels-last row (pitch ldo) of every non-empty pillar cell.
+ * pillar_coors is [M,4] (b,z,y,x) (coors_dim 4) or the per-sample [M,3] (z,y,x) with batch_index given;
+ * num_pillars_dev (optional) = device-side pillar count (num_pillars is then the buffer capacity). */
+int isf_cam2bev(const float* pillars, int num_pillars, const int* num_pillars_dev, int points_per_pillar, int nfeat,
+                const int* pillar_coors, int coors_dim, int batch_index, const void* img_feat_nhwc,
+                const float* proj_dev, int batch, int ncam, int fh, int fw, int channels,
                 float img_w, float img_h, int bev_h, int bev_w, void* out_nhwc, int ldo, int ch_off, void* stream);
 
 /* ---- a8/a9: SST window attention core ------------------------------------------

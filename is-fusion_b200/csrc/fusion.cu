@@ -24,7 +24,8 @@ struct CamProj {
 
 template <int C>
 __global__ void __launch_bounds__(256) cam2bev_kernel(const float* __restrict__ pillars, int P, int nfeat,
-                                                      const int* __restrict__ pcoors, int M,
+                                                      const int* __restrict__ pcoors, int cdim, int batch_override, int M,
+                                                      const int* __restrict__ m_dev,
                                                       const __half* __restrict__ feat,  // [B, ncam, h, w, C]
                                                       const CamProj* __restrict__ proj,  // [B, ncam]
                                                       int ncam, int fh, int fw, float img_w, float img_h, int bev_h,
@@ -33,9 +34,10 @@ __global__ void __launch_bounds__(256) cam2bev_kernel(const float* __restrict__ 
   static_assert(CPL == 8, "cam2bev is built for 256 feature channels");
   const int lane = threadIdx.x & 31;
   const int pil = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m_dev) M = *m_dev;
   if (pil >= M) return;
-  const int* pc = pcoors + (size_t)pil * 4;
-  const int b = pc[0], cy = pc[2], cx = pc[3];
+  const int* pc = pcoors + (size_t)pil * cdim;       // (b,z,y,x) or, per-sample, (z,y,x) with the batch index given
+  const int b = cdim == 4 ? pc[0] : batch_override, cy = pc[cdim - 2], cx = pc[cdim - 1];
   float acc[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
@@ -98,18 +100,21 @@ __global__ void __launch_bounds__(256) cam2bev_kernel(const float* __restrict__ 
 }
 
 // proj: HOST array of B*ncam CamProj-layout floats (20 floats each) copied by the caller to device memory
-extern "C" int isf_cam2bev(const float* pillars, int num_pillars, int points_per_pillar, int nfeat,
-                           const int* pillar_coors, const void* img_feat_nhwc, const float* proj_dev, int batch,
+extern "C" int isf_cam2bev(const float* pillars, int num_pillars, const int* num_pillars_dev, int points_per_pillar,
+                           int nfeat, const int* pillar_coors, int coors_dim, int batch_index,
+                           const void* img_feat_nhwc, const float* proj_dev, int batch,
                            int ncam, int fh, int fw, int channels, float img_w, float img_h, int bev_h, int bev_w,
                            void* out_nhwc, int ldo, int ch_off, void* stream) {
   ISF_CHECK_ARG(num_pillars >= 0 && points_per_pillar >= 1 && nfeat >= 3 && ncam >= 1 && batch >= 1);
+  ISF_CHECK_ARG(coors_dim == 4 || (coors_dim == 3 && batch_index >= 0 && batch_index < batch));
   if (channels != 256) { isf_set_error("cam2bev: built for 256 image-feature channels"); return ISF_ERR_UNSUPPORTED; }
   ISF_CHECK_ARG(ldo % 8 == 0 && ch_off % 8 == 0);
   if (num_pillars == 0) return ISF_OK;
   ISF_CHECK_ARG(pillars && pillar_coors && img_feat_nhwc && proj_dev && out_nhwc);
   int blocks = isf_cdiv(num_pillars, 8);
   cam2bev_kernel<256><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      pillars, points_per_pillar, nfeat, pillar_coors, num_pillars, (const __half*)img_feat_nhwc,
+      pillars, points_per_pillar, nfeat, pillar_coors, coors_dim, batch_index, num_pillars, num_pillars_dev,
+      (const __half*)img_feat_nhwc,
       (const CamProj*)proj_dev, ncam, fh, fw, img_w, img_h, bev_h, bev_w, (__half*)out_nhwc, ldo, ch_off);
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();

@@ -107,12 +107,13 @@ extern "C" int isf_hash_build(const int* indices, int v, const int* v_dev, const
 // ------------------------------------------------------------------------------------------------
 // strided conv: output sites
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) candidate_keys_kernel(const int* __restrict__ indices, int v, ConvGeom g,
-                                                             unsigned int* __restrict__ cand) {
+__global__ void __launch_bounds__(256) candidate_keys_kernel(const int* __restrict__ indices, int v, const int* v_dev,
+                                                             ConvGeom g, unsigned int* __restrict__ cand) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)v * g.kvol;
   if (t >= total) return;
   int i = (int)(t / g.kvol), k = (int)(t % g.kvol);
+  if (v_dev && i >= *v_dev) { cand[t] = HASH_EMPTY; return; }   // capacity rows beyond the device-side count
   int kk[3];
   kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
   const int* c = indices + (size_t)i * 4;
@@ -172,7 +173,7 @@ extern "C" int isf_spconv_out_shape(const int* in_shape, const int* ksize, const
   return ISF_OK;
 }
 
-extern "C" int isf_spconv_out_indices(const int* in_indices, int v_in, const int* in_shape, int batch, const int* ksize,
+extern "C" int isf_spconv_out_indices(const int* in_indices, int v_in, const int* v_in_dev, const int* in_shape, int batch, const int* ksize,
                                       const int* stride, const int* padding, const int* dilation, int* out_indices,
                                       int out_cap, int* num_out_dev, void* workspace, size_t ws_bytes, void* stream) {
   ISF_CHECK_ARG(v_in >= 0 && in_shape && ksize && stride && padding && num_out_dev && out_cap >= 0);
@@ -193,7 +194,7 @@ extern "C" int isf_spconv_out_indices(const int* in_indices, int v_in, const int
   size_t cub_bytes = outidx_cub_bytes(n);
   void* cub_tmp = A.take<char>(cub_bytes);
   if (!A.ok) { isf_set_error("spconv_out_indices: workspace too small"); return ISF_ERR_WORKSPACE; }
-  candidate_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, g, cand);
+  candidate_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, cand);
   int bits = 1;
   while ((1ll << bits) < cells) ++bits;
   int end_bit = bits + 1 > 32 ? 32 : bits + 1;   // keeps the all-ones invalid key last
@@ -313,8 +314,9 @@ extern "C" int isf_sparse_to_dense(const void* feats, const int* indices, int v,
 // BEV view of dense(): [B, C*D, H, W] with channel c' = c*D + z (sparse_encoder.py:133-136), written as NHWC
 // fp16 rows of pitch `ldo` starting at channel `ch_offset` (so it can land inside the fused 768-ch buffer).
 __global__ void __launch_bounds__(256) to_bev_nhwc_kernel(const __half* __restrict__ feats, const int* __restrict__ idx,
-                                                          int v, int c, int D, int H, int W, __half* __restrict__ out,
-                                                          int ldo, int ch_offset) {
+                                                          int v, const int* v_dev, int c, int D, int H, int W,
+                                                          __half* __restrict__ out, int ldo, int ch_offset) {
+  if (v_dev) v = *v_dev;
   long long total = (long long)v * c;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int j = (int)(t / c), ch = (int)(t % c);
@@ -323,14 +325,14 @@ __global__ void __launch_bounds__(256) to_bev_nhwc_kernel(const __half* __restri
   }
 }
 
-extern "C" int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, int c, int D, int H, int W,
-                                      void* out, int ldo, int ch_offset, void* stream) {
+extern "C" int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, const int* v_dev, int c, int D, int H,
+                                      int W, void* out, int ldo, int ch_offset, void* stream) {
   ISF_CHECK_ARG(v >= 0 && c >= 1 && out);
   if (v == 0) return ISF_OK;
   long long total = (long long)v * c;
   int blocks = (int)((total + 255) / 256);
   if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
-  to_bev_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)feats, indices, v, c, D, H, W,
+  to_bev_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)feats, indices, v, v_dev, c, D, H, W,
                                                                (__half*)out, ldo, ch_offset);
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();

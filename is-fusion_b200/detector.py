@@ -51,27 +51,132 @@ class ISFusionDetector(nn.Module):
             num_points.append(n)
         return torch.cat(voxels, dim=0), torch.cat(num_points, dim=0), torch.cat(coors, dim=0)
 
-    def isfusion(self, pts, pts_feats, img_feats, img_metas, batch_size, **kwargs):
+    def isfusion(self, pts, pts_feats, img_feats, img_metas, batch_size, nosync=False, **kwargs):
         """ref: isfusion.py:84-101."""
         with stage('a5 pillarize'):
-            pillars, pillars_num_points, pillar_coors = self.voxelize(pts, voxel_type='pillar')
-        pts_metas = dict(pillars=pillars, pillars_num_points=pillars_num_points, pillar_coors=pillar_coors, pts=pts,
-                         pillar_size=self.pillar_size)
+            if nosync:
+                pts_metas = dict(pillars_list=self.voxelize_nosync(pts), pts=pts, pillar_size=self.pillar_size)
+            else:
+                pillars, pillars_num_points, pillar_coors = self.voxelize(pts, voxel_type='pillar')
+                pts_metas = dict(pillars=pillars, pillars_num_points=pillars_num_points, pillar_coors=pillar_coors,
+                                 pts=pts, pillar_size=self.pillar_size)
         kwargs.update(dict(pts_metas=pts_metas, img_metas=img_metas, pts_backbone=self.pts_backbone))
         return self.fusion_encoder(img_feats, pts_feats, batch_size, **kwargs)
 
     @torch.no_grad()
-    def extract_pts_feat(self, pts, img_feats, img_metas, **kwargs):
-        """ref: isfusion.py:103-121 without pts_neck; returns ([feat_0, feat_1], ins_heatmap)."""
+    def voxelize_nosync(self, points):
+        """pillars per sample in capacity buffers with device-side counts (no host read)."""
+        from .voxel_layer import hard_voxelize
+        layer = self.pts_pillar_layer
+        cells = int(layer.grid_size[0] * layer.grid_size[1] * layer.grid_size[2])
+        max_voxels = layer.max_voxels[0] if self.training else layer.max_voxels[1]
+        cap = min(cells, max_voxels)
+        out = []
+        for res in points:
+            voxels = torch.empty((cap, layer.max_num_points, res.size(1)), dtype=res.dtype, device=res.device)
+            coors = torch.empty((cap, 3), dtype=torch.int32, device=res.device)
+            npv = torch.empty((cap,), dtype=torch.int32, device=res.device)
+            cnt = hard_voxelize(res, voxels, coors, npv, layer.voxel_size, layer.point_cloud_range, layer.max_num_points,
+                                cap, 3, True, nosync=True)
+            out.append((voxels, coors, cnt))
+        return out
+
+    @torch.no_grad()
+    def extract_pts_feat(self, pts, img_feats, img_metas, nosync=False, **kwargs):
+        """ref: isfusion.py:103-121 without pts_neck; returns ([feat_0, feat_1], ins_heatmap).
+        nosync=True keeps every data-dependent count on the device (capacity buffers): no host synchronisation
+        anywhere in the path, which makes it CUDA-graph capturable (see GraphedNeck)."""
         with stage('a1 dynamic_voxelize'):
             voxels, coors = self.dynamic_voxelize(pts)
         batch_size = len(pts)
         with stage('a3 dynamic_vfe'):
-            voxel_features, feature_coors = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas,
-                                                                   batch_size=batch_size)
+            r = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas, batch_size=batch_size, nosync=nosync)
+        nv = r[2] if nosync else None
         with stage('a4 sparse_encoder'):
-            x, _, kwargs = self.pts_middle_encoder(voxel_features, feature_coors, batch_size, dense=False, **kwargs)
+            x, _, kwargs = self.pts_middle_encoder(r[0], r[1], batch_size, dense=False, num_voxels_dev=nv, **kwargs)
         kwargs['lidar_sparse'] = self.pts_middle_encoder.last_out
-        return self.isfusion(pts, x, img_feats, img_metas, batch_size, **kwargs)
+        return self.isfusion(pts, x, img_feats, img_metas, batch_size, nosync=nosync, **kwargs)
 
     forward = extract_pts_feat
+
+
+class GraphedNeck:
+    """The whole fusion-neck forward as ONE CUDA graph replay.
+
+    Capacity buffers + device-side counts make every launch shape static, so the ~400 kernels of a frame are
+    captured once and replayed without any host work between them.  Frames with fewer points than `num_points`
+    are padded with out-of-range points (dropped by voxelization).  `capacities` = output-site buffer rows of
+    the five strided sparse convs (calibrate() measures them on sample frames); check() reports overflow.
+    """
+
+    def __init__(self, net, batch, num_points, img_hw=(256, 704), feat_hw=None, calib=None, capacities=None,
+                 device=None):
+        import isfusion_b200.spconv as spmod
+        self.net, self.batch, self.num_points = net, batch, num_points
+        dev = device or next(net.parameters()).device
+        self.dev = dev
+        fh, fw = feat_hw or (img_hw[0] // 16, img_hw[1] // 16)
+        self.points = [torch.full((num_points, 5), 1e6, dtype=torch.float32, device=dev) for _ in range(batch)]
+        self.img_feat = torch.zeros((batch * net.fusion_encoder.num_views, net.fusion_encoder.embed_dims, fh, fw),
+                                    dtype=torch.float32, device=dev)
+        self.metas = [dict(input_shape=img_hw)] * batch
+        self.cam_proj = net.fusion_encoder.camera_projection(calib['lidar2img'], calib['img_aug_matrix'],
+                                                              calib['lidar_aug_matrix'], batch, dev)
+        if capacities is not None:
+            net.pts_middle_encoder.set_capacities(capacities)
+        self._spmod = spmod
+        self.graph, self.outputs, self.watch = None, None, []
+
+    def _run(self):
+        feats = [self.img_feat[:0], self.img_feat, self.img_feat[:0]]
+        return self.net.extract_pts_feat(self.points, feats, self.metas, nosync=True, cam_proj=self.cam_proj)
+
+    def load(self, points, img_feat1):
+        for dst, src in zip(self.points, points):
+            n = src.shape[0]
+            if n > self.num_points:
+                raise ValueError('frame has %d points, graph capacity is %d' % (n, self.num_points))
+            dst[:n].copy_(src, non_blocking=True)
+            if n < self.num_points:
+                dst[n:].fill_(1e6)
+        self.img_feat.copy_(img_feat1, non_blocking=True)
+
+    def capture(self, warmup=3):
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._spmod.OVERFLOW_WATCH.clear()
+                self._run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._spmod.OVERFLOW_WATCH.clear()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = self._run()
+        self.watch = list(self._spmod.OVERFLOW_WATCH)
+        self._spmod.OVERFLOW_WATCH.clear()
+        return self
+
+    def __call__(self, points=None, img_feat1=None):
+        if points is not None:
+            self.load(points, img_feat1)
+        self.graph.replay()
+        return self.outputs
+
+    def check(self):
+        """[(count, capacity)] of strided convs whose output buffer overflowed in the last replay (host sync)."""
+        return [(int(c.item()), cap) for c, cap in self.watch if int(c.item()) >= cap]
+
+    @staticmethod
+    def calibrate(net, frames, img_feats, metas, margin=1.3, **kw):
+        """run sample frames in exact mode and size the strided-conv buffers to margin x the largest seen."""
+        best = None
+        for pts in frames:
+            net.extract_pts_feat(pts, img_feats, metas, **kw)
+            enc = net.pts_middle_encoder
+            rows = []
+            x = enc.last_encode_features
+            rows = [f.features.shape[0] for f in x[1:4]] + [enc.last_out.features.shape[0]]
+            best = rows if best is None else [max(a, b) for a, b in zip(best, rows)]
+        return [int(r * margin) // 128 * 128 + 128 for r in best]

@@ -482,32 +482,46 @@ class ISFusionEncoder(_Packable):
         return self.__dict__['_pk']
 
     # ------------------------------------------------------------------ a6: camera -> BEV
+    def camera_projection(self, lidar2img, img_aug_matrix, lidar_aug_matrix, bs, device):
+        """host-side 3x3 algebra of img_point_sampling (:976-1006) folded into 20 floats per (frame, camera):
+        q = M p + t with M = lidar2img[:3,:3].inv(lidar_aug[:3,:3]), then the image-aug affine rows."""
+        l2i = torch.as_tensor(lidar2img).float().cpu().reshape(bs, self.num_views, 4, 4)
+        aug = torch.as_tensor(img_aug_matrix).float().cpu().reshape(bs, self.num_views, 4, 4)
+        laug = torch.as_tensor(lidar_aug_matrix).float().cpu().reshape(bs, 4, 4)
+        rinv = torch.inverse(laug[:, :3, :3])
+        m = l2i[:, :, :3, :3] @ rinv[:, None]
+        t = l2i[:, :, :3, 3] - (m @ laug[:, None, :3, 3, None]).squeeze(-1)
+        proj = torch.cat([m.reshape(bs, self.num_views, 9), t, aug[:, :, :2, :3].reshape(bs, self.num_views, 6),
+                          aug[:, :, :2, 3]], -1).contiguous()
+        return proj.to(device)
+
     def img_fv_to_bev(self, mlvl_feats, bs, out=None, **kwargs):
         """ref: img_point_sampling + img_fv_to_bev (fusion_encoder.py:965-1070) as one fused kernel.
-        Returns the channels-last fp16 buffer [B, G, G, ldo] whose first 256 channels hold the image BEV."""
+        Returns the channels-last fp16 buffer [B, G, G, ldo] whose first 256 channels hold the image BEV.
+        pts_metas carries either the reference's concatenated pillars/pillar_coors or, on the sync-free path,
+        'pillars_list' = [(pillars [cap,P,nf], coors [cap,3], device count)] per sample."""
         pm = kwargs['pts_metas']
-        pillars, pcoors = pm['pillars'], pm['pillar_coors']
-        L.require_cuda(pillars, pcoors)
         feat = mlvl_feats[0]
         dev = feat.device
         c, fh, fw = feat.shape[1], feat.shape[2], feat.shape[3]
         feat_nhwc = feat.view(bs, self.num_views, c, fh, fw).permute(0, 1, 3, 4, 2).contiguous().half()
         image_size = kwargs['img_metas'][0]['input_shape']
-        l2i = torch.as_tensor(kwargs['lidar2img']).float().cpu().reshape(bs, self.num_views, 4, 4)
-        aug = torch.as_tensor(kwargs['img_aug_matrix']).float().cpu().reshape(bs, self.num_views, 4, 4)
-        laug = torch.as_tensor(kwargs['lidar_aug_matrix']).float().cpu().reshape(bs, 4, 4)
-        rinv = torch.inverse(laug[:, :3, :3])                                   # [B,3,3] (host, 3x3)
-        m = l2i[:, :, :3, :3] @ rinv[:, None]                                   # q = M p + t
-        t = l2i[:, :, :3, 3] - (m @ laug[:, None, :3, 3, None]).squeeze(-1)
-        proj = torch.cat([m.reshape(bs, self.num_views, 9), t, aug[:, :, :2, :3].reshape(bs, self.num_views, 6),
-                          aug[:, :, :2, 3]], -1).contiguous().to(dev)          # 20 floats per (b, cam)
+        proj = kwargs.get('cam_proj')
+        if proj is None:
+            proj = self.camera_projection(kwargs['lidar2img'], kwargs['img_aug_matrix'], kwargs['lidar_aug_matrix'], bs, dev)
         g = self.bev_size
         if out is None:
             out = torch.zeros((bs, g, g, self.embed_dims), dtype=torch.float16, device=dev)
-        L.check(L.lib().isf_cam2bev(L.ptr(pillars.contiguous()), pillars.shape[0], pillars.shape[1], pillars.shape[2],
-                                    L.ptr(pcoors.contiguous()), L.ptr(feat_nhwc), L.ptr(proj), bs, self.num_views, fh, fw,
-                                    c, ctypes.c_float(image_size[1]), ctypes.c_float(image_size[0]), g, g, L.ptr(out),
-                                    out.shape[-1], 0, L.stream()))
+        if 'pillars_list' in pm:
+            jobs = [(p, co, cnt, 3, b) for b, (p, co, cnt) in enumerate(pm['pillars_list'])]
+        else:
+            jobs = [(pm['pillars'].contiguous(), pm['pillar_coors'].contiguous(), None, 4, 0)]
+        for pillars, pcoors, cnt, cdim, b in jobs:
+            L.require_cuda(pillars, pcoors)
+            L.check(L.lib().isf_cam2bev(L.ptr(pillars), pillars.shape[0], L.ptr(cnt), pillars.shape[1], pillars.shape[2],
+                                        L.ptr(pcoors), cdim, b, L.ptr(feat_nhwc), L.ptr(proj), bs, self.num_views, fh, fw,
+                                        c, ctypes.c_float(image_size[1]), ctypes.c_float(image_size[0]), g, g, L.ptr(out),
+                                        out.shape[-1], 0, L.stream()))
         return out
 
     # ------------------------------------------------------------------ a10-a12: instance-guided fusion
@@ -574,7 +588,7 @@ class ISFusionEncoder(_Packable):
         if sp is not None:
             d = sp.spatial_shape[0]
             L.check(L.lib().isf_sparse_to_bev_nhwc(L.ptr(sp.features), L.ptr(sp.indices), sp.features.shape[0],
-                                                   sp.features.shape[1], d, g, g, L.ptr(cat), cat.shape[-1],
+                                                   L.ptr(sp.num_dev), sp.features.shape[1], d, g, g, L.ptr(cat), cat.shape[-1],
                                                    self.embed_dims, L.stream()))
         else:
             cat[..., self.embed_dims:] = lidar_feats.permute(0, 2, 3, 1)

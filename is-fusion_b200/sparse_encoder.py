@@ -116,12 +116,28 @@ class SparseEncoder(nn.Module):
             self.encoder_layers.add_module(f'encoder_layer{i + 1}', SparseSequential(*blocks_list))
         return out_channels
 
+    def strided_convs(self):
+        """the four stride-2 SparseConv3d + conv_out, in execution order (their output-site capacity is tunable)."""
+        out = []
+        for stage in self.encoder_layers:
+            for blk in stage:
+                if isinstance(blk, SparseSequential):
+                    out.append(blk[0])
+        out.append(self.conv_out[0])
+        return out
+
+    def set_capacities(self, rows):
+        """capacity mode: rows[i] = output-site buffer size of the i-th strided conv (None = analytic bound)."""
+        for conv, r in zip(self.strided_convs(), rows):
+            conv.out_capacity = r
+
     @torch.no_grad()
-    def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True, **kwargs):
+    def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True,
+                num_voxels_dev=None, **kwargs):
         """voxel_features [V,C], coors [V,4] int32 (b,z,y,x) -> (spatial_features [B, C*D, H, W], encode_features, kwargs)"""
         coors = coors.int()
         feats = voxel_features if voxel_features.dtype == torch.float16 else voxel_features.half()
-        x = SparseConvTensor(feats.contiguous(), coors.contiguous(), self.sparse_shape, batch_size)
+        x = SparseConvTensor(feats.contiguous(), coors.contiguous(), self.sparse_shape, batch_size, num_dev=num_voxels_dev)
         x = self.conv_input(x)
         encode_features = [x]
         for encoder_layer in self.encoder_layers:
@@ -129,6 +145,7 @@ class SparseEncoder(nn.Module):
             encode_features.append(x)
         out = self.conv_out(encode_features[-1])
         self.last_out = out
+        self.last_encode_features = encode_features
         if not dense:      # fast path: the fusion encoder scatters `out` straight into its channels-last buffer
             return None, encode_features, kwargs
         spatial_features = out.dense()

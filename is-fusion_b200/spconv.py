@@ -20,13 +20,16 @@ def _triple(v):
 
 
 class SparseConvTensor:
-    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None, num_dev=None):
         self.features = features
         self.indices = indices
         self.spatial_shape = [int(s) for s in spatial_shape]
         self.batch_size = int(batch_size)
         self.indice_dict = {}
         self.grid = grid
+        # capacity mode (sync-free / CUDA-graph path): rows [0, *num_dev) of features / indices are valid, the
+        # rest of the buffers is capacity.  None = exact mode (every row valid), the spconv API contract.
+        self.num_dev = num_dev
 
     @property
     def spatial_size(self):
@@ -36,14 +39,24 @@ class SparseConvTensor:
         return n
 
     def replace_feature(self, feature):
-        t = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid)
+        t = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.num_dev)
         t.indice_dict = self.indice_dict
         return t
 
     def find_indice_pair(self, key):
         return self.indice_dict.get(key) if key is not None else None
 
+    def exact(self):
+        """capacity mode -> exact mode (one host read of the row count)."""
+        if self.num_dev is None:
+            return self
+        n = int(self.num_dev.item())
+        t = SparseConvTensor(self.features[:n], self.indices[:n], self.spatial_shape, self.batch_size, self.grid)
+        return t
+
     def dense(self, channels_first=True):
+        if self.num_dev is not None:
+            return self.exact().dense(channels_first)
         f = self.features
         if f.dtype != torch.float16:
             f = f.half()
@@ -59,11 +72,12 @@ class SparseConvTensor:
 
 class Rulebook:
     """output indices + neighbour table of one (coordinate set, kernel geometry)."""
-    __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'pairs')
+    __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'num_dev', 'pairs')
 
-    def __init__(self, out_indices, out_shape, nbr, nbr_stride, taps, num_out):
+    def __init__(self, out_indices, out_shape, nbr, nbr_stride, taps, num_out, num_dev=None):
         self.out_indices, self.out_shape, self.nbr = out_indices, out_shape, nbr
-        self.nbr_stride, self.taps, self.num_out = nbr_stride, taps, num_out
+        self.nbr_stride, self.taps, self.num_out = nbr_stride, taps, num_out      # num_out = rows (capacity)
+        self.num_dev = num_dev                                                    # device-side valid-row count
         self.pairs = None
 
 
@@ -75,46 +89,68 @@ def _hash_table(x):
         v = x.indices.shape[0]
         cap = L.lib().isf_hash_capacity(v)
         table = torch.empty(2 * cap, dtype=torch.int32, device=x.indices.device)
-        L.check(L.lib().isf_hash_build(L.ptr(x.indices), v, L.ptr(None), L.host_i32(x.spatial_shape), x.batch_size,
+        L.check(L.lib().isf_hash_build(L.ptr(x.indices), v, L.ptr(x.num_dev), L.host_i32(x.spatial_shape), x.batch_size,
                                        L.ptr(table), cap, L.stream()))
         tab = (table, cap)
         x.indice_dict[key] = tab
     return tab
 
 
-def build_rulebook(x, ksize, stride, padding, dilation, subm):
+OVERFLOW_WATCH = []     # (count tensor, capacity) of every capacity-mode strided conv since the last check
+
+
+def check_overflow():
+    """capacity mode: did any strided conv produce more output sites than its buffer holds? (one host sync)"""
+    bad = [(int(c.item()), cap) for c, cap in OVERFLOW_WATCH if int(c.item()) >= cap]
+    OVERFLOW_WATCH.clear()
+    return bad
+
+
+def build_rulebook(x, ksize, stride, padding, dilation, subm, out_capacity=None):
     lib = L.lib()
     dev = x.indices.device
     v_in = x.indices.shape[0]
     table, cap = _hash_table(x)
     taps = ksize[0] * ksize[1] * ksize[2]
+    num_dev = None
     if subm:
-        out_indices, out_shape, v_out = x.indices, list(x.spatial_shape), v_in
+        out_indices, out_shape, v_out, num_dev = x.indices, list(x.spatial_shape), v_in, x.num_dev
     else:
         oshape = (ctypes.c_int * 3)()
         L.check(lib.isf_spconv_out_shape(L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
                                          L.host_i32(padding), L.host_i32(dilation), oshape))
         out_shape = list(oshape)
         cells = x.batch_size * out_shape[0] * out_shape[1] * out_shape[2]
-        cap_out = min(v_in * taps, cells)
+        # an input site reaches at most ceil(k/s) outputs per axis
+        reach = 1
+        for d in range(3):
+            reach *= -(-ksize[d] // stride[d])
+        cap_out = min(v_in * reach, cells)
+        capacity_mode = x.num_dev is not None
+        if capacity_mode and out_capacity is not None:
+            cap_out = min(cap_out, int(out_capacity))
         ws_bytes = ctypes.c_size_t(0)
         L.check(lib.isf_spconv_out_indices_workspace_size(v_in, taps, ctypes.byref(ws_bytes)))
         ws = L.workspace(ws_bytes.value, dev)
         out_buf = torch.empty((max(cap_out, 1), 4), dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.check(lib.isf_spconv_out_indices(L.ptr(x.indices), v_in, L.host_i32(x.spatial_shape), x.batch_size,
-                                           L.host_i32(ksize), L.host_i32(stride), L.host_i32(padding),
+        L.check(lib.isf_spconv_out_indices(L.ptr(x.indices), v_in, L.ptr(x.num_dev), L.host_i32(x.spatial_shape),
+                                           x.batch_size, L.host_i32(ksize), L.host_i32(stride), L.host_i32(padding),
                                            L.host_i32(dilation), L.ptr(out_buf), cap_out, L.ptr(cnt), L.ptr(ws),
                                            ctypes.c_size_t(ws.numel()), L.stream()))
-        v_out = int(cnt.item())      # one host read per strided layer (sizes the next stage's buffers)
-        out_indices = out_buf[:v_out]
+        if capacity_mode:
+            v_out, out_indices, num_dev = cap_out, out_buf, cnt
+            OVERFLOW_WATCH.append((cnt, cap_out))
+        else:
+            v_out = int(cnt.item())      # exact mode: one host read per strided layer
+            out_indices = out_buf[:v_out]
     stride_rows = max((v_out + 127) // 128 * 128, 128)
     nbr = torch.empty((taps, stride_rows), dtype=torch.int32, device=dev)
-    L.check(lib.isf_spconv_neighbors(L.ptr(out_indices), v_out, L.ptr(None), L.ptr(table), cap,
+    L.check(lib.isf_spconv_neighbors(L.ptr(out_indices), v_out, L.ptr(num_dev), L.ptr(table), cap,
                                      L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
                                      L.host_i32(padding), L.host_i32(dilation), 1 if subm else 0, L.ptr(nbr),
                                      ctypes.c_longlong(stride_rows), L.stream()))
-    return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out)
+    return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev)
 
 
 PROFILE = None      # bench.py: list collecting (start_event, end_event, issued_flops, rulebook) per launch
@@ -124,7 +160,8 @@ def useful_flops(rb_cin_cout):
     """2 * pairs * Cin * Cout of one launch (pairs counted once per rulebook, outside any timed region)."""
     rb, cin, cout = rb_cin_cout
     if rb.pairs is None:
-        rb.pairs = int((rb.nbr[:, :rb.num_out] >= 0).sum().item())
+        n = rb.num_out if rb.num_dev is None else int(rb.num_dev.item())
+        rb.pairs = int((rb.nbr[:, :n] >= 0).sum().item())
     return 2.0 * rb.pairs * cin * cout
 
 
@@ -147,7 +184,7 @@ def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, resid
         out = torch.empty((rb.num_out, cout), dtype=torch.float16, device=feats.device)
     L.check(L.lib().isf_spconv_implicit_gemm(
         L.ptr(feats), cin, L.ptr(w_packed), w_packed.shape[1], cout, L.ptr(rb.nbr), ctypes.c_longlong(rb.nbr_stride),
-        rb.taps, rb.num_out, L.ptr(None), L.ptr(scale), L.ptr(shift), L.ptr(residual),
+        rb.taps, rb.num_out, L.ptr(rb.num_dev), L.ptr(scale), L.ptr(shift), L.ptr(residual),
         residual.stride(0) if residual is not None else 0, 1 if relu else 0, L.ptr(out), out.stride(0), L.stream()))
     return out
 
@@ -209,7 +246,8 @@ class SparseConvolution(SparseModule):
                    tuple(self.dilation), x.indices.data_ptr(), x.indices.shape[0])                # same rulebook
         rb = x.indice_dict.get(key)
         if rb is None:
-            rb = build_rulebook(x, self.kernel_size, self.stride, self.padding, self.dilation, self.subm)
+            rb = build_rulebook(x, self.kernel_size, self.stride, self.padding, self.dilation, self.subm,
+                                out_capacity=getattr(self, 'out_capacity', None))
             x.indice_dict[key] = rb
         return rb
 
@@ -221,7 +259,7 @@ class SparseConvolution(SparseModule):
             shift = self.bias.float() if shift is None else shift + self.bias.float() * (scale if scale is not None else 1)
         f = implicit_gemm(feats.contiguous(), rb, self.packed_weight(), self.in_channels, self.out_channels, scale,
                           shift, residual, relu)
-        out = SparseConvTensor(f, rb.out_indices, rb.out_shape, x.batch_size)
+        out = SparseConvTensor(f, rb.out_indices, rb.out_shape, x.batch_size, num_dev=rb.num_dev)
         out.indice_dict = x.indice_dict
         return out
 

@@ -72,7 +72,8 @@ class DynamicVFE(nn.Module):
         return super()._load_from_state_dict(*a, **k)
 
     @torch.no_grad()
-    def forward(self, features, coors, points=None, img_feats=None, img_metas=None, batch_size=None, **kwargs):
+    def forward(self, features, coors, points=None, img_feats=None, img_metas=None, batch_size=None, nosync=False,
+                **kwargs):
         """features [N,5] fp32 points, coors [N,4] int32 (b,z,y,x), all in range ->
         (voxel_feats [V,64], voxel_coors [V,4] int32)."""
         if self.training:
@@ -96,5 +97,7 @@ class DynamicVFE(nn.Module):
             L.ptr(w1), L.ptr(s1), L.ptr(b1), L.ptr(w2), L.ptr(s2), L.ptr(b2), self.in_channels,
             self.feat_channels[-1], L.ptr(None if f16 else feats), L.ptr(feats if f16 else None), L.ptr(vcoors),
             L.ptr(nv), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        if nosync:       # capacity mode: (feats [N,64], coors [N,4], device-side voxel count)
+            return feats, vcoors, nv
         v = int(nv.item())
         return feats[:v], vcoors[:v]

@@ -27,7 +27,7 @@ def dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3):
 
 
 def hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors_range, max_points, max_voxels,
-                  NDim=3, deterministic=True):
+                  NDim=3, deterministic=True, nosync=False):
     """ref: voxel_layer.hard_voxelize (voxelization.h:58-81) -> voxel_num (host int, one D2H read as in
     voxelization_cuda.cu:369-372).  Always deterministic."""
     assert NDim == 3
@@ -41,7 +41,7 @@ def hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors
                                       L.host_f32(coors_range), int(max_points), int(max_voxels), L.ptr(voxels),
                                       L.ptr(coors), L.ptr(num_points_per_voxel), L.ptr(cnt), L.ptr(ws),
                                       ctypes.c_size_t(ws.numel()), L.stream()))
-    return int(cnt.item())
+    return cnt if nosync else int(cnt.item())
 
 
 def dynamic_point_to_voxel_forward(feats, coors, reduce_type='max', dims=None):

@@ -208,3 +208,37 @@ def test_neck_end_to_end(npts, batch):
     assert gf[0].shape == rf[0].shape and gf[1].shape == rf[1].shape and ghm.shape == rhm.shape
     assert r_hm < 5e-3 and overlap > 0.9
     assert r0 < 1e-2 and r1 < 1e-2
+
+
+def test_sync_free_and_graph_paths_match_exact_path():
+    """capacity buffers + device-side counts (nosync) and the one-graph replay give the same bits as the exact path."""
+    from isfusion_b200.detector import GraphedNeck
+    import isfusion_b200.spconv as spmod
+    _, net = build_pair(0)
+    B, N = 2, 15000
+    pts = [synth.make_points(N, 'S', 10 + s).cuda() for s in range(B)]
+    l2i, aug, laug = synth.make_calib(B)
+    feats = [f.cuda() for f in synth.make_img_feats(B)]
+    metas = [dict(input_shape=(256, 704))] * B
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    ef, ehm = net(pts, feats, metas, **kw)
+    sf, shm = net(pts, feats, metas, nosync=True, **kw)
+    assert not spmod.check_overflow()
+    for a, b in zip(ef, sf):
+        assert torch.equal(a, b)
+    assert torch.equal(ehm, shm)
+    caps = GraphedNeck.calibrate(net, [pts], feats, metas, **kw)
+    gn = GraphedNeck(net, B, max(p.shape[0] for p in pts) + 500, calib=kw, capacities=caps)   # padded points
+    gn.load(pts, feats[1])
+    gn.capture()
+    gf, ghm = gn(pts, feats[1])
+    torch.cuda.synchronize()
+    assert not gn.check()
+    for a, b in zip(ef, gf):
+        assert torch.equal(a, b)
+    # a different frame through the same graph
+    pts2 = [synth.make_points(N - 1000, 'S', 20 + s).cuda() for s in range(B)]
+    gf2, _ = gn(pts2, feats[1])
+    ef2, _ = net(pts2, feats, metas, **kw)
+    for a, b in zip(ef2, gf2):
+        assert torch.equal(a, b)
