@@ -153,7 +153,7 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm, out_capacity=None)
     return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev)
 
 
-PROFILE = None      # bench.py: list collecting (start_event, end_event, issued_flops, rulebook) per launch
+PROFILE = None      # bench.py: list collecting the arguments of every implicit-GEMM launch of a frame
 
 
 def useful_flops(rb_cin_cout):
@@ -167,13 +167,26 @@ def useful_flops(rb_cin_cout):
 
 def implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, residual=None, relu=False, out=None):
     if PROFILE is not None:
+        PROFILE.append((feats, rb, w_packed, cin, cout, scale, shift, residual, relu))
+    return _implicit_gemm(feats, rb, w_packed, cin, cout, scale, shift, residual, relu, out)
+
+
+def time_launches(records, reps=5):
+    """re-issue every recorded implicit-GEMM launch `reps` times back to back between CUDA events on the current
+    stream (queue kept full, so the event time is kernel time) -> [(ms per launch, issued flops, useful flops)]."""
+    out = []
+    for (feats, rb, w, cin, cout, scale, shift, residual, relu) in records:
+        buf = torch.empty((rb.num_out, cout), dtype=torch.float16, device=feats.device)
+        _implicit_gemm(feats, rb, w, cin, cout, scale, shift, residual, relu, buf)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = _implicit_gemm(feats, rb, w_packed, cin, cout, scale, shift, residual, relu, out)
+        for _ in range(reps):
+            _implicit_gemm(feats, rb, w, cin, cout, scale, shift, residual, relu, buf)
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * rb.num_out * rb.taps * cin * cout, (rb, cin, cout)))
-        return r
-    return _implicit_gemm(feats, rb, w_packed, cin, cout, scale, shift, residual, relu, out)
+        torch.cuda.synchronize()
+        n = rb.num_out if rb.num_dev is None else int(rb.num_dev.item())
+        out.append((e0.elapsed_time(e1) / reps, 2.0 * n * rb.taps * cin * cout, useful_flops((rb, cin, cout)), cin, cout, n))
+    return out
 
 
 def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, residual=None, relu=False, out=None):
