@@ -36,6 +36,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=16, help='distinct resident frames rotated through (L2 defeat)')
     ap.add_argument('--cpu-points', type=int, default=0, help='points of the CPU-baseline sample frame (0 = same as --points)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager-only', action='store_true', help='profiling aid: time the eager exact-mode path only (no graph)')
     ap.add_argument('--stages', action='store_true', help='extra pass with per-stage CUDA-event timers')
     return ap.parse_args()
 
@@ -233,6 +234,12 @@ def main():
         pts, feats = dev_sets[i % F_]
         return net(pts, feats, metas, **kw)
 
+    if args.eager_only:
+        ms = timed(step_eager_pre, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'mode': 'eager-only (profiling aid, not a bench value)',
+                              'ms_per_step': ms / args.steps}))
+        return
     from isfusion_b200.detector import GraphedNeck
     log('calibrating buffer capacities on 2 frames (exact mode)')
     caps = GraphedNeck.calibrate(net, [dev_sets[0][0], dev_sets[1 % F_][0]], dev_sets[0][1], metas, margin=1.35, **kw)
