@@ -24,6 +24,25 @@ sys.path.insert(0, ROOT)
 METRIC = 'frames/sec fusion-neck forward (0.075 voxel, 6-cam)'
 
 
+def frame_seed(rank, f):
+    """frames are the sharded unit: rank r owns seeds 1000 r + f, disjoint across ranks (weak scaling)."""
+    return 1000 * rank + f
+
+
+def max_over_ranks(ms, world, dist=None, device=None):
+    """whole-job time = slowest rank (device time of each rank, MAX all-reduce)."""
+    if world <= 1:
+        return ms
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def job_fps(world, batch, steps, ms):
+    return world * batch * steps / (ms / 1000.0)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -197,7 +216,7 @@ def main():
     # resident inputs: F distinct frames per rank, rotated so that consecutive steps never reuse L2-resident inputs
     host_sets = []
     for f in range(F_):
-        seed = 1000 * rank + f
+        seed = frame_seed(rank, f)
         pts = [synth.make_points(args.points, args.cloud, seed * 8 + b).pin_memory() for b in range(B)]
         feats = [t.pin_memory() for t in synth.make_img_feats(B, seed=seed)]
         host_sets.append((pts, feats))
@@ -223,12 +242,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms
+        return max_over_ranks(e0.elapsed_time(e1), world, dist, dev)
 
     def step_eager_pre(i):
         pts, feats = dev_sets[i % F_]
@@ -289,9 +303,9 @@ def main():
     step_eager(0)
     spmod.PROFILE = None
     own_per_step = L.launch_count(reset=True)      # kernels of one frame (a graph replay launches the same set)
-    fps = world * B * args.steps / (ms / 1000.0)
+    fps = job_fps(world, B, args.steps, ms)
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup), base=7)
-    fps_e2e = world * B * args.steps / (ms_e2e / 1000.0)
+    fps_e2e = job_fps(world, B, args.steps, ms_e2e)
     log('e2e: %.3f ms/step' % (ms_e2e / args.steps))
     out_bytes = sum(h.numel() * h.element_size() for h in out_host)
 
