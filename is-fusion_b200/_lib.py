@@ -78,3 +78,8 @@ def workspace(nbytes, device):
 
 def launch_count(reset=False):
     return int(lib().isf_launch_count(1 if reset else 0))
+
+
+def set_option(name, value):
+    """runtime options of the library (isf_set_option), e.g. set_option('gemm_cluster', 4)."""
+    check(lib().isf_set_option(name.encode(), int(value)))

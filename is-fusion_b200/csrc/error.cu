@@ -23,3 +23,14 @@ extern "C" unsigned long long isf_launch_count(int reset) {
   if (reset) g_launches = 0;
   return v;
 }
+
+// ---- runtime options
+int g_isf_gemm_cluster = 1;
+extern "C" int isf_set_option(const char* name, int value) {
+  if (name && strcmp(name, "gemm_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
+    g_isf_gemm_cluster = value;
+    return ISF_OK;
+  }
+  isf_set_error("isf_set_option: unknown option or bad value: %s=%d", name ? name : "(null)", value);
+  return ISF_ERR_INVALID;
+}

@@ -12,6 +12,8 @@
 // Warp 4 allocates TMEM and its elected lane issues tcgen05.mma (M=128, N=BN, K=16) and the
 // tcgen05.commit that recycles smem stages through mbarriers.  Accumulators live in TMEM (fp32).
 #pragma once
+#include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace tc {
@@ -70,6 +72,35 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- thread-block-cluster helpers (weight-chunk multicast)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D TMA tile load, multicast to every CTA of `mask`: data and complete_tx land at the same CTA-relative
+// offsets (dst, bar) in each destination CTA.
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
                : "memory");
 }
 
@@ -156,9 +187,14 @@ struct SmemLayout {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
+// CS = thread-block-cluster size.  CS > 1: the CTAs of a cluster walk the same K-chunk sequence on CS consecutive
+// row tiles; each CTA TMA-loads 1/CS of the weight chunk and multicasts it to the whole cluster, so weight
+// traffic from L2 drops by CS; smem stages are recycled cluster-wide (tcgen05.commit multicast on the empty barrier).
+template <int BN, int STAGES, int CS>
+__global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
   using SL = SmemLayout<BN, STAGES>;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1);
+  constexpr int SLICE_ROWS = BN / CS;
   constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -174,15 +210,22 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
   const int num_chunks = p.kpad / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PRODUCERS); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], PRODUCERS + (CS > 1 ? 1 : 0));   // + the expect_tx arrive of the TMA issuer
+      mbar_init(&empty_bar[s], CS);                             // one tcgen05.commit per CTA of the cluster
+    }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();       // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CS, num_clusters = gridDim.x / CS;
+  const int num_groups = (num_tiles + CS - 1) / CS;
 
   uint32_t chunk_ctr = 0;   // running chunk counter across tiles (stage = ctr % STAGES, use = ctr / STAGES)
   uint32_t tile_ctr = 0;
@@ -191,7 +234,8 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
   int* tap_flag = (int*)(smem + SL::LIST_OFF + MAX_CHUNKS * 2);   // [32] flags + [1] active count at index 32
   const bool gather = p.nbr != nullptr;
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_ctr) {
+  for (int grp = cluster_id; grp < num_groups; grp += num_clusters, ++tile_ctr) {
+    const int tile = grp * CS + crank;     // may lie beyond the last tile: the CTA then only feeds the multicast
     const int row0 = tile * BM;
     // ---------------------------------------------------------------- tile prologue: neighbour tile -> smem,
     // list of K-chunks that have at least one neighbour in this tile (empty kernel offsets are skipped)
@@ -202,10 +246,15 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
       if (gather) {
         if (tid < 33) tap_flag[tid] = 0;
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int t = 0; t < p.taps; ++t) {
-          const int v = row_ok ? p.nbr[(long long)t * p.nbr_stride + grow] : -1;
-          nbr_s[t * BM + r] = v;
-          if (v >= 0) tap_flag[t] = 1;
+#pragma unroll 1
+        for (int cs = 0; cs < CS; ++cs) {       // flags = union over the cluster's tiles (same chunk list everywhere)
+          const long long prow = (long long)(grp * CS + cs) * BM + r;
+          const bool pok = prow < m_total;
+          for (int t = 0; t < p.taps; ++t) {
+            const int v = pok ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
+            if (cs == crank) nbr_s[t * BM + r] = v;
+            if (v >= 0) tap_flag[t] = 1;
+          }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -262,14 +311,21 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
             cp_async16(a_base + rr * 128 + ((c ^ (rr & 7)) << 4), src, ok ? 16u : 0u);
           }
         }
-        // B: BN rows x 8 pieces, spread over the 128 producer threads
         const uint32_t b_base = smem_u32(sb);
+        if constexpr (CS == 1) {
+          // B: BN rows x 8 pieces, spread over the 128 producer threads
 #pragma unroll
-        for (int j = 0; j < BN * 8 / PRODUCERS; ++j) {
-          const int piece = tid + j * PRODUCERS;
-          const int n = piece >> 3, c = piece & 7;
-          const __half* src = p.W + (long long)(n0 + n) * p.kpad + q * BK + c * 8;
-          cp_async16(b_base + n * 128 + ((c ^ (n & 7)) << 4), src, 16u);
+          for (int j = 0; j < BN * 8 / PRODUCERS; ++j) {
+            const int piece = tid + j * PRODUCERS;
+            const int n = piece >> 3, c = piece & 7;
+            const __half* src = p.W + (long long)(n0 + n) * p.kpad + q * BK + c * 8;
+            cp_async16(b_base + n * 128 + ((c ^ (n & 7)) << 4), src, 16u);
+          }
+        } else if (tid == 0) {
+          // B: this CTA fetches rows [crank*SLICE_ROWS, +SLICE_ROWS) of the chunk by TMA (128B swizzle = the UMMA
+          // layout) and multicasts them into the same stage of every CTA of the cluster
+          mbar_expect_tx(&full_bar[s], BN * 128);
+          tma_load_2d_mcast(b_base + crank * SLICE_ROWS * 128, &tmap_w, q * BK, n0 + crank * SLICE_ROWS, &full_bar[s], CMASK);
         }
         cp_async_commit();
         if (i >= STAGES - 1) {
@@ -393,7 +449,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
             umma_f16(tmem_base, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if constexpr (CS == 1) umma_commit(&empty_bar[s]); else umma_commit_mcast(&empty_bar[s], CMASK);
           if (q == n_act - 1) umma_commit(accum_bar);
         }
         __syncwarp();
@@ -407,17 +463,57 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();       // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int BN, int STAGES>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// W [n_total, kpad] fp16 K-major; box = 64 K-elements (128 B, one swizzle row) x slice_rows
+static int make_weight_tmap(CUtensorMap* tm, const void* w, int n_total, int kpad, int slice_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { isf_set_error("cuTensorMapEncodeTiled not available"); return ISF_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)n_total};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)slice_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { isf_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return ISF_ERR_CUDA; }
+  return ISF_OK;
+}
+
+extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2|4), defined in error.cu
+
+template <int BN, int STAGES, int CS>
 static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
   using SL = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
     if (e != cudaSuccess) { isf_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
     configured = true;
+  }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (CS > 1) {
+    int rc = make_weight_tmap(&tm, p.W, p.n_total, p.kpad, BN / CS);
+    if (rc) return rc;
   }
   int tiles = (m_upper + BM - 1) / BM;
   if (tiles < 1) tiles = 1;
@@ -425,14 +521,37 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 4) ctas_per_sm = 4;
   int n_tiles = p.n_total / BN;
-  int gx = ISF_NUM_SMS * ctas_per_sm / n_tiles;
+  int groups = (tiles + CS - 1) / CS;
+  int gx = ISF_NUM_SMS * ctas_per_sm / n_tiles / CS;     // clusters
   if (gx < 1) gx = 1;
-  if (gx > tiles) gx = tiles;
-  dim3 grid(gx, n_tiles);
-  gemm_kernel<BN, STAGES><<<grid, THREADS, SL::TOTAL, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  if (gx > groups) gx = groups;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(gx * CS, n_tiles);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SL::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, CS>, p, tm);
   if (e != cudaSuccess) { isf_set_error("gemm launch: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
   return ISF_OK;
+}
+
+template <int CS>
+static inline int dispatch_gemm_cs(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  switch (bn) {
+    case 32: return launch_gemm<32, 4, CS>(p, m_upper, st);
+    case 64: return launch_gemm<64, 4, CS>(p, m_upper, st);
+    case 128: return launch_gemm<128, 3, CS>(p, m_upper, st);
+    case 256: return launch_gemm<256, 2, CS>(p, m_upper, st);
+    default: isf_set_error("gemm: unsupported column tile %d", bn); return ISF_ERR_UNSUPPORTED;
+  }
 }
 
 static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
@@ -440,12 +559,10 @@ static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaSt
     isf_set_error("gemm: taps=%d (max %d) / K chunks=%d (max %d) out of range", p.taps, MAX_TAPS, p.kpad / BK, MAX_CHUNKS);
     return ISF_ERR_UNSUPPORTED;
   }
-  switch (bn) {
-    case 32: return launch_gemm<32, 4>(p, m_upper, st);
-    case 64: return launch_gemm<64, 4>(p, m_upper, st);
-    case 128: return launch_gemm<128, 3>(p, m_upper, st);
-    case 256: return launch_gemm<256, 2>(p, m_upper, st);
-    default: isf_set_error("gemm: unsupported column tile %d", bn); return ISF_ERR_UNSUPPORTED;
+  switch (g_isf_gemm_cluster) {
+    case 4: return dispatch_gemm_cs<4>(p, bn, m_upper, st);
+    case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
+    default: return dispatch_gemm_cs<1>(p, bn, m_upper, st);
   }
 }
 

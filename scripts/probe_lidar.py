@@ -10,6 +10,8 @@ from isfusion_b200 import _lib as L
 
 VS, PR = [0.075, 0.075, 0.2], synth.PC_RANGE
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 300000
+if len(sys.argv) > 3:
+    L.set_option('gemm_cluster', int(sys.argv[3]))
 kind = sys.argv[2] if len(sys.argv) > 2 else 'S'
 torch.manual_seed(0)
 pts = synth.make_points(n, kind, 0).cuda()

@@ -73,3 +73,25 @@ def test_gemm_scatter_rows():
     exp = torch.zeros_like(ref)
     exp[perm[keep].long()] = ref[keep]
     assert (out.float() - exp).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize('cs', [2, 4])
+def test_gemm_cluster_multicast(cs):
+    """thread-block-cluster variant (TMA-multicast weights) gives the same bits as the single-CTA variant."""
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.gemm import gemm, pack_weight
+    torch.manual_seed(cs)
+    try:
+        for (m, k, n) in [(5000, 128, 128), (129, 256, 256), (32400, 128, 384), (700, 64, 64), (1000, 64, 32)]:
+            a = (torch.randn(m, k, device='cuda') * 0.5).half()
+            w = (torch.randn(n, k, device='cuda') / k ** 0.5).half()
+            res = torch.randn(m, n, device='cuda').half()
+            shift = torch.randn(n, device='cuda') * 0.1
+            L.set_option('gemm_cluster', 1)
+            ref = gemm(a, pack_weight(w), shift=shift, residual=res, act='relu')
+            L.set_option('gemm_cluster', cs)
+            out = gemm(a, pack_weight(w), shift=shift, residual=res, act='relu')
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref), (m, k, n)
+    finally:
+        L.set_option('gemm_cluster', 1)

@@ -116,3 +116,25 @@ def test_sparse_encoder_parity():
     mx = (gs.float().cpu() - rs).abs().max().item()
     print('sparse encoder rel l2 err %.3e  max abs %.3e (max ref %.3f)' % (num / den, mx, rs.abs().max().item()))
     assert num / den <= 3e-3, (num / den)
+
+
+@pytest.mark.parametrize('cs', [2, 4])
+def test_sparse_encoder_cluster_variant_bit_identical(cs):
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    torch.manual_seed(0)
+    cfg = dict(in_channels=64, sparse_shape=[41, 128, 128], base_channels=32, output_channels=256,
+               encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    mod = SparseEncoder(**cfg).cuda().eval()
+    x = _rand_tensor([41, 128, 128], 20000, 64, 2, 11, clustered=True)
+    f, c = torch.relu(x.features).half().cuda(), x.indices.cuda()
+    try:
+        L.set_option('gemm_cluster', 1)
+        ref, _, _ = mod(f, c, 2)
+        L.set_option('gemm_cluster', cs)
+        out, _, _ = mod(f, c, 2)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    finally:
+        L.set_option('gemm_cluster', 1)
