@@ -498,7 +498,6 @@ static int make_weight_tmap(CUtensorMap* tm, const void* w, int n_total, int kpa
   return ISF_OK;
 }
 
-extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2|4), defined in error.cu
 
 template <int BN, int STAGES, int CS>
 static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
@@ -559,7 +558,7 @@ static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaSt
     isf_set_error("gemm: taps=%d (max %d) / K chunks=%d (max %d) out of range", p.taps, MAX_TAPS, p.kpad / BK, MAX_CHUNKS);
     return ISF_ERR_UNSUPPORTED;
   }
-  switch (g_isf_gemm_cluster) {
+  switch (::g_isf_gemm_cluster) {
     case 4: return dispatch_gemm_cs<4>(p, bn, m_upper, st);
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
     default: return dispatch_gemm_cs<1>(p, bn, m_upper, st);
