@@ -107,38 +107,65 @@ extern "C" int isf_hash_build(const int* indices, int v, const int* v_dev, const
 // ------------------------------------------------------------------------------------------------
 // strided conv: output sites
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) candidate_keys_kernel(const int* __restrict__ indices, int v, const int* v_dev,
-                                                             ConvGeom g, unsigned int* __restrict__ cand) {
+// every (input site, kernel offset) proposes an output site; a hash SET keeps one copy of each and the winner
+// of the insert appends the key to a compact list (warp-aggregated counter) -> only the V_out unique keys are sorted
+__global__ void __launch_bounds__(256) candidate_insert_kernel(const int* __restrict__ indices, int v, const int* v_dev,
+                                                               ConvGeom g, unsigned int* __restrict__ set_keys,
+                                                               unsigned int mask, unsigned int* __restrict__ list,
+                                                               int list_cap, int* __restrict__ list_count) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)v * g.kvol;
-  if (t >= total) return;
-  int i = (int)(t / g.kvol), k = (int)(t % g.kvol);
-  if (v_dev && i >= *v_dev) { cand[t] = HASH_EMPTY; return; }   // capacity rows beyond the device-side count
-  int kk[3];
-  kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
-  const int* c = indices + (size_t)i * 4;
-  int o[3];
-  bool ok = true;
+  const long long total = (long long)v * g.kvol;
+  bool won = false;
+  unsigned int key = HASH_EMPTY;
+  if (t < total) {
+    int i = (int)(t / g.kvol), k = (int)(t % g.kvol);
+    if (!(v_dev && i >= *v_dev)) {
+      int kk[3];
+      kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
+      const int* c = indices + (size_t)i * 4;
+      int o[3];
+      bool ok = true;
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    int num = c[1 + d] + g.pad[d] - kk[d] * g.dil[d];
-    int q = num / g.stride[d];
-    ok &= (num >= 0) && (q * g.stride[d] == num) && (q < g.out_shape[d]);
-    o[d] = q;
+      for (int d = 0; d < 3; ++d) {
+        int num = c[1 + d] + g.pad[d] - kk[d] * g.dil[d];
+        int q = num / g.stride[d];
+        ok &= (num >= 0) && (q * g.stride[d] == num) && (q < g.out_shape[d]);
+        o[d] = q;
+      }
+      if (ok) {
+        key = lin_key(c[0], o[0], o[1], o[2], g.out_shape);
+        unsigned int slot = hash_u32(key) & mask;
+        // bounded probing: a full set (capacity overflow, reported through the count) must not spin forever
+        for (unsigned int probes = 0; probes <= mask; ++probes) {
+          unsigned int prev = atomicCAS(&set_keys[slot], HASH_EMPTY, key);
+          if (prev == HASH_EMPTY) { won = true; break; }
+          if (prev == key) break;
+          slot = (slot + 1) & mask;
+        }
+      }
+    }
   }
-  cand[t] = ok ? lin_key(c[0], o[0], o[1], o[2], g.out_shape) : HASH_EMPTY;
+  const unsigned ballot = __ballot_sync(0xffffffffu, won);
+  if (ballot) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == (__ffs(ballot) - 1)) base = atomicAdd(list_count, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+    if (won) {
+      const int pos = base + __popc(ballot & ((1u << lane) - 1));
+      if (pos < list_cap) list[pos] = key;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256) decode_out_kernel(const unsigned int* __restrict__ uniq,
-                                                         const int* __restrict__ num_sel, ConvGeom g, int cap,
+__global__ void __launch_bounds__(256) decode_out_kernel(const unsigned int* __restrict__ sorted,
+                                                         const int* __restrict__ list_count, ConvGeom g, int cap,
                                                          int* __restrict__ out_indices, int* __restrict__ num_out) {
-  int n = *num_sel;
-  // the invalid key (all ones) sorts last
-  if (n > 0 && uniq[n - 1] == HASH_EMPTY) n -= 1;
+  int n = *list_count;
   if (n > cap) n = cap;
   if (blockIdx.x == 0 && threadIdx.x == 0) *num_out = n;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    unsigned int k = uniq[j];
+    unsigned int k = sorted[j];
     int x = k % g.out_shape[2]; k /= g.out_shape[2];
     int y = k % g.out_shape[1]; k /= g.out_shape[1];
     int z = k % g.out_shape[0]; k /= g.out_shape[0];
@@ -148,18 +175,34 @@ __global__ void __launch_bounds__(256) decode_out_kernel(const unsigned int* __r
 }
 
 static size_t outidx_cub_bytes(long long n) {
-  size_t a = 0, b = 0;
+  size_t a = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, a, (unsigned int*)nullptr, (unsigned int*)nullptr, n);
-  cub::DeviceSelect::Unique(nullptr, b, (unsigned int*)nullptr, (unsigned int*)nullptr, (int*)nullptr, n);
-  return a > b ? a : b;
+  return a;
 }
 
-extern "C" int isf_spconv_out_indices_workspace_size(int v_in, int kvol, size_t* bytes) {
-  ISF_CHECK_ARG(v_in >= 0 && kvol >= 1 && bytes);
-  long long n = (long long)(v_in > 0 ? v_in : 1) * kvol;
+static long long pow2_at_least(long long x) {
+  long long c = 1024;
+  while (c < x) c <<= 1;
+  return c;
+}
+
+static void outidx_carve(IsfArena& A, long long out_cap, unsigned int** set_keys, long long* set_cap, unsigned int** list,
+                         unsigned int** sorted, int** count, void** cub_tmp, size_t* cub_bytes) {
+  *set_cap = pow2_at_least(2 * out_cap);
+  *set_keys = A.take<unsigned int>(*set_cap);
+  *list = A.take<unsigned int>(out_cap);
+  *sorted = A.take<unsigned int>(out_cap);
+  *count = A.take<int>(1);
+  *cub_bytes = outidx_cub_bytes(out_cap);
+  *cub_tmp = A.take<char>(*cub_bytes);
+}
+
+// workspace for isf_spconv_out_indices with an output buffer of out_cap rows (v_in, kvol kept for API stability)
+extern "C" int isf_spconv_out_indices_workspace_size(int v_in, int kvol, int out_cap, size_t* bytes) {
+  ISF_CHECK_ARG(v_in >= 0 && kvol >= 1 && out_cap >= 0 && bytes);
   IsfArena A(nullptr, 0);
-  A.take<unsigned int>(n); A.take<unsigned int>(n); A.take<unsigned int>(n); A.take<int>(1);
-  A.take<char>(outidx_cub_bytes(n));
+  unsigned int *a, *b, *c; int* d; void* e; size_t f; long long sc;
+  outidx_carve(A, out_cap > 0 ? out_cap : 1, &a, &sc, &b, &c, &d, &e, &f);
   *bytes = A.off + 1024;
   return ISF_OK;
 }
@@ -178,7 +221,7 @@ extern "C" int isf_spconv_out_indices(const int* in_indices, int v_in, const int
                                       int out_cap, int* num_out_dev, void* workspace, size_t ws_bytes, void* stream) {
   ISF_CHECK_ARG(v_in >= 0 && in_shape && ksize && stride && padding && num_out_dev && out_cap >= 0);
   cudaStream_t st = (cudaStream_t)stream;
-  if (v_in == 0) { ISF_CUDA(cudaMemsetAsync(num_out_dev, 0, sizeof(int), st)); return ISF_OK; }
+  if (v_in == 0 || out_cap == 0) { ISF_CUDA(cudaMemsetAsync(num_out_dev, 0, sizeof(int), st)); return ISF_OK; }
   ISF_CHECK_ARG(in_indices && out_indices && workspace);
   ConvGeom g;
   fill_geom(&g, in_shape, ksize, stride, padding, dilation, 0);
@@ -187,23 +230,21 @@ extern "C" int isf_spconv_out_indices(const int* in_indices, int v_in, const int
   long long n = (long long)v_in * g.kvol;
   ISF_CHECK_ARG(n < 0x7fffffffll);
   IsfArena A(workspace, ws_bytes);
-  unsigned int* cand = A.take<unsigned int>(n);
-  unsigned int* sorted = A.take<unsigned int>(n);
-  unsigned int* uniq = A.take<unsigned int>(n);
-  int* num_sel = A.take<int>(1);
-  size_t cub_bytes = outidx_cub_bytes(n);
-  void* cub_tmp = A.take<char>(cub_bytes);
+  unsigned int *set_keys, *list, *sorted; int* count; void* cub_tmp; size_t cub_bytes; long long set_cap;
+  outidx_carve(A, out_cap, &set_keys, &set_cap, &list, &sorted, &count, &cub_tmp, &cub_bytes);
   if (!A.ok) { isf_set_error("spconv_out_indices: workspace too small"); return ISF_ERR_WORKSPACE; }
-  candidate_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, cand);
+  ISF_CUDA(cudaMemsetAsync(set_keys, 0xFF, sizeof(unsigned int) * set_cap, st));
+  ISF_CUDA(cudaMemsetAsync(list, 0xFF, sizeof(unsigned int) * out_cap, st));   // unused slots sort last
+  ISF_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+  candidate_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, set_keys,
+                                                                        (unsigned)set_cap - 1, list, out_cap, count);
   int bits = 1;
   while ((1ll << bits) < cells) ++bits;
-  int end_bit = bits + 1 > 32 ? 32 : bits + 1;   // keeps the all-ones invalid key last
+  int end_bit = bits + 1 > 32 ? 32 : bits + 1;   // keeps the all-ones filler last
   size_t tmp = cub_bytes;
-  ISF_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, tmp, cand, sorted, (int)n, 0, end_bit, st));
-  tmp = cub_bytes;
-  ISF_CUDA(cub::DeviceSelect::Unique(cub_tmp, tmp, sorted, uniq, num_sel, (int)n, st));
-  decode_out_kernel<<<ISF_NUM_SMS * 2, 256, 0, st>>>(uniq, num_sel, g, out_cap, out_indices, num_out_dev);
-  isf_count_launch(6);
+  ISF_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, tmp, list, sorted, out_cap, 0, end_bit, st));
+  decode_out_kernel<<<ISF_NUM_SMS * 2, 256, 0, st>>>(sorted, count, g, out_cap, out_indices, num_out_dev);
+  isf_count_launch(8);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
 }

@@ -130,7 +130,7 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm, out_capacity=None)
         if capacity_mode and out_capacity is not None:
             cap_out = min(cap_out, int(out_capacity))
         ws_bytes = ctypes.c_size_t(0)
-        L.check(lib.isf_spconv_out_indices_workspace_size(v_in, taps, ctypes.byref(ws_bytes)))
+        L.check(lib.isf_spconv_out_indices_workspace_size(v_in, taps, cap_out, ctypes.byref(ws_bytes)))
         ws = L.workspace(ws_bytes.value, dev)
         out_buf = torch.empty((max(cap_out, 1), 4), dtype=torch.int32, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
