@@ -26,7 +26,7 @@ extern "C" int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad
   if (ln_gamma && bn != n) { isf_set_error("isf_gemm_f16: LayerNorm epilogue needs n in {32,64,128,256}"); return ISF_ERR_UNSUPPORTED; }
   tc::GemmParams p{};
   p.A = (const __half*)A; p.W = (const __half*)W; p.nbr = nullptr; p.nbr_stride = 0; p.m_dev = m_dev; p.m = m;
-  p.cin = k; p.taps = 1; p.kpad = kpad; p.n_total = n;
+  p.cin = k; p.cin_shift = 0; p.taps = 1; p.kpad = kpad; p.n_total = n;
   p.scale = scale; p.shift = shift; p.residual = (const __half*)residual; p.ldr = ldr; p.act = act;
   p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;
   p.out = (__half*)out_f16; p.out_f32 = out_f32; p.ldo = ldo; p.out_rows = out_rows;

@@ -310,12 +310,14 @@ extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const voi
                                         void* stream) {
   ISF_CHECK_ARG(v_out >= 0 && cin % 8 == 0 && cin >= 8 && taps >= 1 && kpad % 64 == 0 && kpad >= taps * cin);
   ISF_CHECK_ARG(cout == 32 || cout == 64 || cout == 128 || cout == 256);
-  ISF_CHECK_ARG(64 % cin == 0 || cin % 64 == 0);   // a 16-byte piece never straddles two taps / a chunk
+  ISF_CHECK_ARG((cin & (cin - 1)) == 0);            // power of two: tap = k >> log2(cin), a piece never straddles taps
   if (v_out == 0) return ISF_OK;
   ISF_CHECK_ARG(feats_in && w_packed && nbr && out_f16 && ldo % 8 == 0);
   tc::GemmParams p{};
   p.A = (const __half*)feats_in; p.W = (const __half*)w_packed; p.nbr = nbr; p.nbr_stride = nbr_stride;
-  p.m_dev = v_out_dev; p.m = v_out; p.cin = cin; p.taps = taps; p.kpad = kpad; p.n_total = cout;
+  p.m_dev = v_out_dev; p.m = v_out; p.cin = cin; p.taps = taps;
+  p.cin_shift = 0;
+  while ((1 << p.cin_shift) < cin) ++p.cin_shift; p.kpad = kpad; p.n_total = cout;
   p.scale = scale; p.shift = shift; p.residual = (const __half*)residual; p.ldr = ldr;
   p.act = relu ? tc::ACT_RELU : tc::ACT_NONE;
   p.out = (__half*)out_f16; p.ldo = ldo;

@@ -97,6 +97,12 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMa
       "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
@@ -149,6 +155,7 @@ struct GemmParams {
   const int* m_dev;       // optional device-side row count (overrides m when non-null)
   int m;                  // output rows
   int cin;                // channels per tap (multiple of 8)
+  int cin_shift;          // log2(cin) when taps > 1 (cin is then a power of two), else unused
   int taps;
   int kpad;               // padded K (multiple of 64)
   int n_total;            // total output columns (B rows); the CTA covers [blockIdx.y*BN, +BN)
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], PRODUCERS + (CS > 1 ? 1 : 0));   // + the expect_tx arrive of the TMA issuer
+      mbar_init(&full_bar[s], PRODUCERS + 1);                  // + the expect_tx arrive of the weight-TMA issuer
       mbar_init(&empty_bar[s], CS);                             // one tcgen05.commit per CTA of the cluster
     }
     mbar_init(accum_bar, 1);
@@ -252,7 +259,8 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
           const bool pok = prow < m_total;
           for (int t = 0; t < p.taps; ++t) {
             const int v = pok ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
-            if (cs == crank) nbr_s[t * BM + r] = v;
+            // staged as the BYTE offset of the neighbour's feature row (0xFFFFFFFF = none): one add per piece later
+            if (cs == crank) nbr_s[t * BM + r] = v >= 0 ? (int)((unsigned)v * (unsigned)(p.cin * 2)) : -1;
             if (v >= 0) tap_flag[t] = 1;
           }
         }
@@ -281,58 +289,54 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
     const int n_act = tap_flag[32];
     if (warp < 4) {
       // ------------------------------------------------ producers
-      const int r = tid;                       // A row inside the tile
+      const int r = tid;                       // epilogue row of this thread
       const int grow = row0 + r;
       const bool row_ok = grow < m_total;
+      // A tile = 8 warp-coalesced sweeps: thread -> 16-byte piece c = tid%8 of rows rr_j = tid/8 + 16 j, so one warp
+      // instruction fetches 4 whole 128 B rows; (rr_j & 7) is the same for every j -> the swizzled offset is a constant
+      const int pc = tid & 7;
+      const int rbase = tid >> 3;
+      const uint32_t a_thr_off = (uint32_t)(rbase * 128 + ((pc ^ (rbase & 7)) << 4));
+      const char* a_bytes = (const char*)p.A;
       uint32_t c0 = chunk_ctr;
+      int s = (int)(c0 % STAGES);
+      uint32_t use = c0 / STAGES;
       for (int i = 0; i < n_act; ++i) {
         const int q = chunk_list[i];
-        const uint32_t cc = c0 + i;
-        const int s = cc % STAGES;
-        if (cc >= STAGES) mbar_wait(&empty_bar[s], ((cc / STAGES) - 1) & 1);
-        uint8_t* sa = smem + s * SL::STAGE_BYTES;
-        uint8_t* sb = sa + SL::A_BYTES;
-        // A: the 128 x 128 B tile as 8 warp-coalesced sweeps: lane -> (row = t/8 + 16 j, 16-byte piece = t%8), so a
-        // warp instruction fetches 4 whole 128 B rows (full 32 B sectors) instead of 32 half-used sectors
+        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+        const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
+        const uint32_t b_base = sa + SL::A_BYTES;
+        // weights: one TMA box (128B swizzle = the UMMA layout); with clusters each CTA loads 1/CS and multicasts
+        if (tid == 0) {
+          mbar_expect_tx(&full_bar[s], BN * 128);
+          if constexpr (CS == 1) tma_load_2d(b_base, &tmap_w, q * BK, n0, &full_bar[s]);
+          else tma_load_2d_mcast(b_base + crank * SLICE_ROWS * 128, &tmap_w, q * BK, n0 + crank * SLICE_ROWS, &full_bar[s], CMASK);
+        }
         {
-          const int c = tid & 7;
-          const int k = q * BK + c * 8;
-          const int tap = k / p.cin;
-          const int ch = k - tap * p.cin;
+          const int k = q * BK + pc * 8;
+          int tap, ch;
+          if (p.taps == 1) { tap = k >= p.cin ? 1 : 0; ch = k; } else { tap = k >> p.cin_shift; ch = k & (p.cin - 1); }
           const bool tap_ok = tap < p.taps;
-          const uint32_t a_base = smem_u32(sa);
+          const int* nrow = nbr_s + tap * BM + rbase;
+          const char* src_ch = a_bytes + ch * 2;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int rr = (tid >> 3) + 16 * j;
-            long long src_row = -1;
-            if (tap_ok) src_row = gather ? (long long)nbr_s[tap * BM + rr] : ((row0 + rr) < m_total ? (long long)(row0 + rr) : -1);
-            const bool ok = src_row >= 0;
-            const __half* src = ok ? p.A + src_row * p.cin + ch : p.A;
-            cp_async16(a_base + rr * 128 + ((c ^ (rr & 7)) << 4), src, ok ? 16u : 0u);
+            unsigned off = 0xFFFFFFFFu;
+            if (tap_ok) {
+              if (gather) off = (unsigned)nrow[16 * j];
+              else { const int gr = row0 + rbase + 16 * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
+            }
+            const bool ok = off != 0xFFFFFFFFu;
+            cp_async16(sa + a_thr_off + j * 2048, ok ? src_ch + off : a_bytes, ok ? 16u : 0u);
           }
-        }
-        const uint32_t b_base = smem_u32(sb);
-        if constexpr (CS == 1) {
-          // B: BN rows x 8 pieces, spread over the 128 producer threads
-#pragma unroll
-          for (int j = 0; j < BN * 8 / PRODUCERS; ++j) {
-            const int piece = tid + j * PRODUCERS;
-            const int n = piece >> 3, c = piece & 7;
-            const __half* src = p.W + (long long)(n0 + n) * p.kpad + q * BK + c * 8;
-            cp_async16(b_base + n * 128 + ((c ^ (n & 7)) << 4), src, 16u);
-          }
-        } else if (tid == 0) {
-          // B: this CTA fetches rows [crank*SLICE_ROWS, +SLICE_ROWS) of the chunk by TMA (128B swizzle = the UMMA
-          // layout) and multicasts them into the same stage of every CTA of the cluster
-          mbar_expect_tx(&full_bar[s], BN * 128);
-          tma_load_2d_mcast(b_base + crank * SLICE_ROWS * 128, &tmap_w, q * BK, n0 + crank * SLICE_ROWS, &full_bar[s], CMASK);
         }
         cp_async_commit();
         if (i >= STAGES - 1) {
           cp_async_wait<STAGES - 1>();
           fence_proxy_async();
-          mbar_arrive(&full_bar[(cc - (STAGES - 1)) % STAGES]);
+          mbar_arrive(&full_bar[(c0 + i - (STAGES - 1)) % STAGES]);
         }
+        if (++s == STAGES) { s = 0; ++use; }
       }
       // drain: the last (STAGES-1) chunks (or all of them when n_act < STAGES-1)
       cp_async_wait<0>();
@@ -510,7 +514,7 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
   }
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  if (CS > 1) {
+  {
     int rc = make_weight_tmap(&tm, p.W, p.n_total, p.kpad, BN / CS);
     if (rc) return rc;
   }

@@ -193,6 +193,8 @@ def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, resid
     if feats.dtype != torch.float16:
         raise L.IsfError('sparse conv: fp16 features expected')
     L.require_cuda(feats, w_packed, scale, shift, residual)
+    if feats.shape[0] * cin * 2 >= 2 ** 32:
+        raise L.IsfError('sparse conv: feature matrix larger than 4 GiB (the kernel stages 32-bit row byte offsets)')
     if out is None:
         out = torch.empty((rb.num_out, cout), dtype=torch.float16, device=feats.device)
     L.check(L.lib().isf_spconv_implicit_gemm(
