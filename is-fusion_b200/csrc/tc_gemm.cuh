@@ -176,10 +176,11 @@ struct GemmParams {
 
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 fp16 = 128 B = one swizzle row
-constexpr int PRODUCERS = 128;  // 4 warps
+constexpr int PRODUCERS = 256;  // 8 warps gather A; all of them also run the epilogue (two column halves)
 constexpr int MAX_TAPS = 27;
 constexpr int MAX_CHUNKS = 512;
 constexpr int THREADS = PRODUCERS + 32;
+constexpr int PWARPS = PRODUCERS / 32;
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == PWARPS) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();       // peers' barriers are initialised before anyone signals them
@@ -246,25 +247,24 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
     const int row0 = tile * BM;
     // ---------------------------------------------------------------- tile prologue: neighbour tile -> smem,
     // list of K-chunks that have at least one neighbour in this tile (empty kernel offsets are skipped)
-    if (warp < 4) {
-      const int r = tid;
-      const int grow = row0 + r;
-      const bool row_ok = grow < m_total;
+    if (warp < PWARPS) {
       if (gather) {
+        const int r = tid & (BM - 1);          // row of the tile; the two thread halves split the kernel offsets
+        const int thalf = tid >> 7;
         if (tid < 33) tap_flag[tid] = 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
         for (int cs = 0; cs < CS; ++cs) {       // flags = union over the cluster's tiles (same chunk list everywhere)
           const long long prow = (long long)(grp * CS + cs) * BM + r;
           const bool pok = prow < m_total;
-          for (int t = 0; t < p.taps; ++t) {
+          for (int t = thalf; t < p.taps; t += PRODUCERS / BM) {
             const int v = pok ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
             // staged as the BYTE offset of the neighbour's feature row (0xFFFFFFFF = none): one add per piece later
             if (cs == crank) nbr_s[t * BM + r] = v >= 0 ? (int)((unsigned)v * (unsigned)(p.cin * 2)) : -1;
             if (v >= 0) tap_flag[t] = 1;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       if (warp == 0) {
         int count = 0;
@@ -287,12 +287,12 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
     }
     __syncthreads();
     const int n_act = tap_flag[32];
-    if (warp < 4) {
+    if (warp < PWARPS) {
       // ------------------------------------------------ producers
-      const int r = tid;                       // epilogue row of this thread
+      const int r = tid & (BM - 1);            // epilogue row of this thread (TMEM lane = 32*(warp%4) + lane)
       const int grow = row0 + r;
       const bool row_ok = grow < m_total;
-      // A tile = 8 warp-coalesced sweeps: thread -> 16-byte piece c = tid%8 of rows rr_j = tid/8 + 16 j, so one warp
+      // A tile = 4 warp-coalesced sweeps: thread -> 16-byte piece c = tid%8 of rows rr_j = tid/8 + 32 j, so one warp
       // instruction fetches 4 whole 128 B rows; (rr_j & 7) is the same for every j -> the swizzled offset is a constant
       const int pc = tid & 7;
       const int rbase = tid >> 3;
@@ -320,14 +320,14 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
           const int* nrow = nbr_s + tap * BM + rbase;
           const char* src_ch = a_bytes + ch * 2;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < BM * 8 / PRODUCERS; ++j) {
             unsigned off = 0xFFFFFFFFu;
             if (tap_ok) {
-              if (gather) off = (unsigned)nrow[16 * j];
-              else { const int gr = row0 + rbase + 16 * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
+              if (gather) off = (unsigned)nrow[(PRODUCERS / 8) * j];
+              else { const int gr = row0 + rbase + (PRODUCERS / 8) * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
             }
             const bool ok = off != 0xFFFFFFFFu;
-            cp_async16(sa + a_thr_off + j * 2048, ok ? src_ch + off : a_bytes, ok ? 16u : 0u);
+            cp_async16(sa + a_thr_off + j * (PRODUCERS / 8) * 128, ok ? src_ch + off : a_bytes, ok ? 16u : 0u);
           }
         }
         cp_async_commit();
@@ -349,12 +349,17 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       // ------------------------------------------------ epilogue
       mbar_wait(accum_bar, tile_ctr & 1);
       tc_fence_after();
-      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      // warps 0-3 own columns [0, BN/2), warps 4-7 [BN/2, BN) of the same rows; the row-local LayerNorm needs the
+      // whole row in one thread and stays on warps 0-3
+      const bool ln = p.ln_gamma != nullptr;
+      const int cb_lo = (ln || BN < 64) ? 0 : (warp >> 2) * (BN / 2);
+      const int cb_hi = (ln || BN < 64) ? ((warp >> 2) ? 0 : BN) : cb_lo + BN / 2;
       long long orow = grow;
       if (p.out_rows && row_ok) orow = p.out_rows[grow];
       const bool store_ok = row_ok && orow >= 0;
       float mean = 0.f, rstd = 1.f;
-      if (p.ln_gamma) {
+      if (ln && warp < 4) {
         // pass 1 over TMEM: row statistics of (acc*scale+shift+residual)
         float s1 = 0.f, s2 = 0.f;
         for (int cb = 0; cb < BN; cb += 32) {
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
         float var = s2 / BN - mean * mean;
         rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
       }
-      for (int cb = 0; cb < BN; cb += 32) {
+      for (int cb = cb_lo; cb < cb_hi; cb += 32) {
         uint32_t v[32];
         tmem_ld32(t_lane + cb, v);
         tmem_ld_wait();
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       // warp may overwrite the accumulator with the next tile
       tc_fence_before();
     } else {
-      // ------------------------------------------------ MMA issuer (warp 4)
+      // ------------------------------------------------ MMA issuer (warp PWARPS)
       constexpr uint32_t idesc = make_idesc_f16(BM, BN);
       uint32_t c0 = chunk_ctr;
       for (int q = 0; q < n_act; ++q) {
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();       // nobody leaves while a peer may still multicast into / signal this CTA
-  if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == PWARPS) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

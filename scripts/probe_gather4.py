@@ -8,7 +8,7 @@ a = torch.randn(rows, cols, device='cuda').half()
 idx = torch.randint(0, rows, (128,), dtype=torch.int32, device='cuda')
 idx[5] = rows + 7      # out of bounds -> expect zeros
 idx[9] = -1            # negative -> expect zeros?
-for box_rows in (1, 4):
+for box_rows in ([int(sys.argv[1])] if len(sys.argv) > 1 else (1, 4)):
     for col0 in (0, 64):
         out = torch.full((128, 64), 7.0, dtype=torch.float16, device='cuda')
         st = torch.zeros(1, dtype=torch.int32, device='cuda')
