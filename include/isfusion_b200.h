@@ -210,11 +210,6 @@ int isf_i2s_attention(const void* q, const void* kv, int batch, int tokens, int 
 int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid, int channels,
                           void* out, int ldo, void* stream);
 
-/* bring-up probe (not on the product path): TMA tile::gather4 of 128 rows x 64 fp16 columns into a 128B-swizzled
- * smem tile, raw smem (16 KiB) returned in out16k, *status_dev = 1 when the transaction completed. */
-int isf_debug_tma_gather4(const void* a, int rows, int cols, const int* idx_dev, int col0, int box_rows, void* out16k,
-                          int* status_dev, void* stream);
-
 #ifdef __cplusplus
 }
 #endif
