@@ -45,6 +45,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// the barrier receives one arrival when all cp.async issued so far by this thread have landed (no pending-count
+// increment: the arrival is part of the barrier's expected count)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -330,21 +335,10 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
             cp_async16(sa + a_thr_off + j * (PRODUCERS / 8) * 128, ok ? src_ch + off : a_bytes, ok ? 16u : 0u);
           }
         }
-        cp_async_commit();
-        if (i >= STAGES - 1) {
-          cp_async_wait<STAGES - 1>();
-          fence_proxy_async();
-          mbar_arrive(&full_bar[(c0 + i - (STAGES - 1)) % STAGES]);
-        }
+        // asynchronous arrival: the stage's full barrier is signalled by the hardware when this thread's pieces have
+        // landed, so the thread runs ahead to the next chunk instead of waiting for its own loads
+        cp_async_mbar_arrive(&full_bar[s]);
         if (++s == STAGES) { s = 0; ++use; }
-      }
-      // drain: the last (STAGES-1) chunks (or all of them when n_act < STAGES-1)
-      cp_async_wait<0>();
-      fence_proxy_async();
-      {
-        int first = n_act - (STAGES - 1);
-        if (first < 0) first = 0;
-        for (int i = first; i < n_act; ++i) mbar_arrive(&full_bar[(c0 + i) % STAGES]);
       }
       // ------------------------------------------------ epilogue
       mbar_wait(accum_bar, tile_ctr & 1);
@@ -447,6 +441,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
         const uint32_t cc = c0 + q;
         const int s = cc % STAGES;
         mbar_wait(&full_bar[s], (cc / STAGES) & 1);
+        fence_proxy_async();     // cp.async (generic proxy) writes of the producers -> visible to the tensor core
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
@@ -553,6 +548,15 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
 
 template <int CS>
 static inline int dispatch_gemm_cs(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  if (::g_isf_gemm_deep) {   // one CTA per SM with a deep smem ring instead of two CTAs with a shallow one
+    switch (bn) {
+      case 32: return launch_gemm<32, 8, CS>(p, m_upper, st);
+      case 64: return launch_gemm<64, 8, CS>(p, m_upper, st);
+      case 128: return launch_gemm<128, 6, CS>(p, m_upper, st);
+      case 256: return launch_gemm<256, 4, CS>(p, m_upper, st);
+      default: break;
+    }
+  }
   switch (bn) {
     case 32: return launch_gemm<32, 4, CS>(p, m_upper, st);
     case 64: return launch_gemm<64, 4, CS>(p, m_upper, st);
