@@ -37,7 +37,7 @@ int isf_version(void);
 const char* isf_last_error(void);
 /* number of kernels this library has launched since the last reset (bench.py gpu_launches) */
 unsigned long long isf_launch_count(int reset);
-/* runtime options: "gemm_cluster" = 1 | 2 | 4 : thread-block-cluster size of the tcgen05 GEMM (CTAs of a cluster
+/* runtime options: "gemm_cluster" = 1 | 2 : thread-block-cluster size of the tcgen05 GEMM (CTAs of a cluster
  * share every weight chunk through TMA multicast). */
 int isf_set_option(const char* name, int value);
 

@@ -63,5 +63,4 @@ __host__ __device__ inline int isf_cdiv(int a, int b) { return (a + b - 1) / b; 
 
 constexpr int ISF_NUM_SMS = 148;  // B200
 
-extern int g_isf_gemm_deep;       // isf_set_option("gemm_deep", 0|1)
-extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2|4), defined in error.cu
+extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2), defined in error.cu

@@ -548,18 +548,9 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
 
 template <int CS>
 static inline int dispatch_gemm_cs(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
-  if (::g_isf_gemm_deep) {   // one CTA per SM with a deep smem ring instead of two CTAs with a shallow one
-    switch (bn) {
-      case 32: return launch_gemm<32, 8, CS>(p, m_upper, st);
-      case 64: return launch_gemm<64, 8, CS>(p, m_upper, st);
-      case 128: return launch_gemm<128, 6, CS>(p, m_upper, st);
-      case 256: return launch_gemm<256, 4, CS>(p, m_upper, st);
-      default: break;
-    }
-  }
   switch (bn) {
     case 32: return launch_gemm<32, 4, CS>(p, m_upper, st);
-    case 64: return launch_gemm<64, 4, CS>(p, m_upper, st);
+    case 64: return launch_gemm<64, 2, CS>(p, m_upper, st);     // 3 CTAs/SM beat a deeper ring (measured)
     case 128: return launch_gemm<128, 3, CS>(p, m_upper, st);
     case 256: return launch_gemm<256, 2, CS>(p, m_upper, st);
     default: isf_set_error("gemm: unsupported column tile %d", bn); return ISF_ERR_UNSUPPORTED;
@@ -572,7 +563,6 @@ static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaSt
     return ISF_ERR_UNSUPPORTED;
   }
   switch (::g_isf_gemm_cluster) {
-    case 4: return dispatch_gemm_cs<4>(p, bn, m_upper, st);
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
     default: return dispatch_gemm_cs<1>(p, bn, m_upper, st);
   }

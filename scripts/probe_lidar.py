@@ -12,8 +12,6 @@ VS, PR = [0.075, 0.075, 0.2], synth.PC_RANGE
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 300000
 if len(sys.argv) > 3:
     L.set_option('gemm_cluster', int(sys.argv[3]))
-if len(sys.argv) > 4:
-    L.set_option('gemm_deep', int(sys.argv[4]))
 kind = sys.argv[2] if len(sys.argv) > 2 else 'S'
 torch.manual_seed(0)
 pts = synth.make_points(n, kind, 0).cuda()

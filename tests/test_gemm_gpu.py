@@ -75,7 +75,7 @@ def test_gemm_scatter_rows():
     assert (out.float() - exp).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize('cs', [2, 4])
+@pytest.mark.parametrize('cs', [2])
 def test_gemm_cluster_multicast(cs):
     """thread-block-cluster variant (TMA-multicast weights) gives the same bits as the single-CTA variant."""
     from isfusion_b200 import _lib as L

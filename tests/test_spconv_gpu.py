@@ -118,7 +118,7 @@ def test_sparse_encoder_parity():
     assert num / den <= 3e-3, (num / den)
 
 
-@pytest.mark.parametrize('cs', [2, 4])
+@pytest.mark.parametrize('cs', [2])
 def test_sparse_encoder_cluster_variant_bit_identical(cs):
     from isfusion_b200 import _lib as L
     from isfusion_b200.sparse_encoder import SparseEncoder
