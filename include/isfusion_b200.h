@@ -207,8 +207,9 @@ int isf_ms_deform_attn_forward(const void* value, int value_is_half, const long 
  *   (fusion_encoder.py:495-500, no 1/sqrt(d)); scene / ins / out channels-last fp16 with pitches lds/ldi/ldo. */
 int isf_i2s_attention(const void* q, const void* kv, int batch, int tokens, int num_keys, int channels, int heads,
                       void* out, void* stream);
+int isf_channel_attention_workspace_size(int batch, int grid, int channels, size_t* bytes);
 int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid, int channels,
-                          void* out, int ldo, void* stream);
+                          void* out, int ldo, void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

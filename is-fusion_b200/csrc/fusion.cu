@@ -399,73 +399,135 @@ extern "C" int isf_ms_deform_attn_forward(const void* value, int value_is_half, 
 }
 
 // ================================================================================================
+// tensor-core helpers for the two IGF attention cores (mma.sync m16n8k16: 36..200-key tiles are far below a
+// tcgen05 M=128 atom; SURVEY §7 "hard parts": documented choice)
+// ================================================================================================
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+  __half2 h = __floats2half2_rn(x, y);
+  return *(uint32_t*)&h;
+}
+__device__ __forceinline__ uint32_t pack_2h(__half lo, __half hi) {
+  return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+}
+
+// ================================================================================================
 // instance -> scene attention core: softmax(q k^T * scale) v, 32 400 queries x 200 keys per frame
 // ================================================================================================
 // q [B*T, C] fp16 (projected, bias added), kv [B, NK, 2C] fp16 (k | v projected), out [B*T, C] fp16.
-template <int C, int HEADS, int NK_MAX>
+// CTA = 8 warps = the 8 heads of a block of 16 queries; K/V of the frame stay in smem (padded pitch, conflict-free
+// fragment loads); QK^T and PV on mma.sync with the flash-attention register reuse (S accumulators -> P operand).
+template <int C, int HEADS, int NKP>
 __global__ void __launch_bounds__(256) i2s_attention_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
                                                             int T, int NK, float scaling, __half* __restrict__ out) {
-  constexpr int D = C / HEADS;
-  extern __shared__ __half sm_kv[];   // [NK][2C]
+  constexpr int D = C / HEADS;          // 16
+  constexpr int PITCH = 2 * C + 8;      // halfs: 132 words = 4 mod 32 -> the 8x4 fragment pattern hits 32 banks
+  static_assert(D == 16, "i2s attention is built for head_dim 16");
+  extern __shared__ __half sm_kv[];     // [NKP][PITCH]
   const int b = blockIdx.y;
   const __half* kvb = kv + (size_t)b * NK * 2 * C;
-  for (int e = threadIdx.x; e < NK * 2 * C / 8; e += blockDim.x) ((uint4*)sm_kv)[e] = ((const uint4*)kvb)[e];
+  for (int e = threadIdx.x; e < NKP * (2 * C / 8); e += blockDim.x) {
+    const int j = e / (2 * C / 8), c8 = (e % (2 * C / 8)) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (j < NK) v = *(const uint4*)(kvb + (size_t)j * 2 * C + c8);
+    *(uint4*)(sm_kv + (size_t)j * PITCH + c8) = v;
+  }
   __syncthreads();
-  const int QPB = 256 / HEADS;   // queries per block
-  const int h = threadIdx.x / QPB, ql = threadIdx.x % QPB;
-  for (int q0 = blockIdx.x * QPB; q0 < T; q0 += gridDim.x * QPB) {
-    const int qi = q0 + ql;
-    if (qi >= T) continue;
-    const __half* qrow = q + ((size_t)b * T + qi) * C + h * D;
-    float qv[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) qv[i] = __half2float(qrow[i]) * scaling;
-    float m = -INFINITY, l = 0.f;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    for (int j = 0; j < NK; ++j) {
-      const __half* kr = sm_kv + (size_t)j * 2 * C + h * D;
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < D; i += 2) {
-        const float2 kf = __half22float2(*(const __half2*)(kr + i));
-        s = fmaf(qv[i], kf.x, s);
-        s = fmaf(qv[i + 1], kf.y, s);
-      }
-      const float mn = fmaxf(m, s);
-      const float corr = __expf(m - mn), pj = __expf(s - mn);
-      l = l * corr + pj;
-      const __half* vr = kr + C;
-#pragma unroll
-      for (int i = 0; i < D; i += 2) {
-        const float2 vf = __half22float2(*(const __half2*)(vr + i));
-        o[i] = fmaf(pj, vf.x, o[i] * corr);
-        o[i + 1] = fmaf(pj, vf.y, o[i + 1] * corr);
-      }
-      m = mn;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gr = lane >> 2, gc = (lane & 3) * 2;
+  const float sl2 = scaling * 1.44269504088896f;
+  for (int q0 = blockIdx.x * 16; q0 < T; q0 += gridDim.x * 16) {
+    // Q fragment (16 queries x 16 dims of head h)
+    uint32_t qa[4];
+    {
+      const int r0 = q0 + gr, r1 = q0 + gr + 8;
+      const __half* p0 = q + ((size_t)b * T + (r0 < T ? r0 : T - 1)) * C + h * D;
+      const __half* p1 = q + ((size_t)b * T + (r1 < T ? r1 : T - 1)) * C + h * D;
+      qa[0] = *(const uint32_t*)(p0 + gc);
+      qa[1] = *(const uint32_t*)(p1 + gc);
+      qa[2] = *(const uint32_t*)(p0 + gc + 8);
+      qa[3] = *(const uint32_t*)(p1 + gc + 8);
     }
-    const float inv = 1.f / l;
-    __half* orow = out + ((size_t)b * T + qi) * C + h * D;
+    float s[NKP / 8][4];
 #pragma unroll
-    for (int i = 0; i < D; i += 2) *(__half2*)(orow + i) = __floats2half2_rn(o[i] * inv, o[i + 1] * inv);
+    for (int nt = 0; nt < NKP / 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const __half* kr = sm_kv + (size_t)(nt * 8 + gr) * PITCH + h * D;
+      mma16816(s[nt], qa, *(const uint32_t*)(kr + gc), *(const uint32_t*)(kr + gc + 8));
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NKP / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + gc + (e & 1);
+        s[nt][e] = key < NK ? s[nt][e] * sl2 : -INFINITY;
+      }
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NKP / 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
+      s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NKP / 16; ++kt) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(s[2 * kt][0], s[2 * kt][1]);
+      pa[1] = pack_h2(s[2 * kt][2], s[2 * kt][3]);
+      pa[2] = pack_h2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+      pa[3] = pack_h2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+      const __half* vr = sm_kv + (size_t)(kt * 16 + gc) * PITCH + C + h * D + gr;   // V[key][dv]
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const uint32_t b0 = pack_2h(vr[n * 8], vr[PITCH + n * 8]);
+        const uint32_t b1 = pack_2h(vr[8 * PITCH + n * 8], vr[9 * PITCH + n * 8]);
+        mma16816(o[n], pa, b0, b1);
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = q0 + gr, r1 = q0 + gr + 8;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      if (r0 < T) *(__half2*)(out + ((size_t)b * T + r0) * C + h * D + n * 8 + gc) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
+      if (r1 < T) *(__half2*)(out + ((size_t)b * T + r1) * C + h * D + n * 8 + gc) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+    }
   }
 }
 
 extern "C" int isf_i2s_attention(const void* q, const void* kv, int batch, int tokens, int num_keys, int channels,
                                  int heads, void* out, void* stream) {
   ISF_CHECK_ARG(q && kv && out && batch >= 1 && tokens >= 1 && num_keys >= 1);
-  if (channels != 128 || heads != 8) { isf_set_error("i2s_attention: built for d_model 128, 8 heads"); return ISF_ERR_UNSUPPORTED; }
-  const size_t smem = (size_t)num_keys * 2 * channels * sizeof(__half);
-  ISF_CHECK_ARG(smem <= 200 * 1024 && (num_keys * 2 * channels) % 8 == 0);
+  if (channels != 128 || heads != 8 || num_keys > 208) {
+    isf_set_error("i2s_attention: built for d_model 128, 8 heads, <= 208 keys");
+    return ISF_ERR_UNSUPPORTED;
+  }
+  constexpr int NKP = 208;
+  const size_t smem = (size_t)NKP * (2 * 128 + 8) * sizeof(__half);
   static bool cfg = false;
   if (!cfg) {
-    ISF_CUDA(cudaFuncSetAttribute(i2s_attention_kernel<128, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ISF_CUDA(cudaFuncSetAttribute(i2s_attention_kernel<128, 8, NKP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cfg = true;
   }
-  int bx = isf_cdiv(tokens, 32);
+  int bx = isf_cdiv(tokens, 16);
   if (bx > ISF_NUM_SMS * 2) bx = ISF_NUM_SMS * 2;
-  i2s_attention_kernel<128, 8, 256><<<dim3(bx, batch), 256, smem, (cudaStream_t)stream>>>(
+  i2s_attention_kernel<128, 8, NKP><<<dim3(bx, batch), 256, smem, (cudaStream_t)stream>>>(
       (const __half*)q, (const __half*)kv, tokens, num_keys, 1.0f / sqrtf(16.f), (__half*)out);
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();
@@ -475,98 +537,178 @@ extern "C" int isf_i2s_attention(const void* q, const void* kv, int batch, int t
 // ================================================================================================
 // channel-wise scene attention: out[b,c] = S + softmax(S I^T, -1) I   with S, I the [G,G] planes of channel c
 // ================================================================================================
-// scene, ins: NHWC fp16 [B, G, G, ld*]; out NHWC fp16.  One CTA per (b, c, row slab): the whole I plane and a
-// slab of S rows are staged in smem (fp16, padded pitch), a warp owns one output row at a time.
-constexpr int CA_SPLIT = 3;
-__global__ void __launch_bounds__(256) channel_attention_kernel(const __half* __restrict__ scene, int lds,
-                                                                const __half* __restrict__ ins, int ldi, int G, int C,
-                                                                __half* __restrict__ out, int ldo) {
+// channels-last <-> planar transposes (the attention reads contiguous planes)
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __half* __restrict__ in, int ld, int HW, int C,
+                                                           __half* __restrict__ out) {
+  __shared__ __half tile[32][34];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    tile[i][tx] = (p < HW && c < C) ? in[((size_t)b * HW + p) * ld + c] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    if (p < HW && c < C) out[((size_t)b * C + c) * HW + p] = tile[tx][i];
+  }
+}
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __half* __restrict__ in, int HW, int C,
+                                                           __half* __restrict__ out, int ld) {
+  __shared__ __half tile[32][34];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (p < HW && c < C) ? in[((size_t)b * C + c) * HW + p] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (p < HW && c < C) out[((size_t)b * HW + p) * ld + c] = tile[tx][i];
+  }
+}
+
+// planes: S, I, O are [B*C][G*G] fp16.  CTA = 4 warps = 64 rows of one plane; the whole I plane (as K and as V) and
+// the CTA's S rows sit in smem with pitch GP (conflict-free fragment loads); logits = S.I^T and P.I on mma.sync.
+template <int GPAD>   // G rounded up to 16
+__global__ void __launch_bounds__(128) channel_attention_kernel(const __half* __restrict__ Sg, const __half* __restrict__ Ig,
+                                                                int G, __half* __restrict__ Og) {
+  constexpr int GP = GPAD + 8;                 // pitch in halfs: (GPAD+8)/2 words, = 4 mod 32 for GPAD = 192
+  constexpr int NT = GPAD / 8, KT = GPAD / 16;
   extern __shared__ __half sm[];
-  const int GP = G + 2 + ((G & 1) ? 1 : 0);      // padded row pitch (halfs): odd number of 32-bit words
-  const int slab = (G + CA_SPLIT - 1) / CA_SPLIT;
-  __half* Ip = sm;
-  __half* Sp = sm + (size_t)G * GP;
-  float* prow = (float*)(Sp + (size_t)slab * GP);    // [8 warps][G] softmax rows
-  const int part = blockIdx.x % CA_SPLIT;
-  const int bc = blockIdx.x / CA_SPLIT;
-  const int b = bc / C, c = bc % C;
-  const int y0 = part * slab, y1 = min(G, y0 + slab);
-  const size_t plane = (size_t)b * G * G;
-  for (int e = threadIdx.x; e < G * G; e += blockDim.x) {
-    const int y = e / G, x = e % G;
-    Ip[y * GP + x] = ins[(plane + e) * ldi + c];
-    if (y >= y0 && y < y1) Sp[(y - y0) * GP + x] = scene[(plane + e) * lds + c];
+  __half* Ip = sm;                              // [GPAD][GP]
+  __half* Sp = sm + (size_t)GPAD * GP;          // [64][GP]
+  const int slabs = (G + 63) / 64;
+  const int plane = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+  const int y0 = slab * 64;
+  const __half* Sg_p = Sg + (size_t)plane * G * G;
+  const __half* Ig_p = Ig + (size_t)plane * G * G;
+  // zero-padded staging (pad columns / rows are multiplied, so they must be 0)
+  for (int e = threadIdx.x; e < GPAD * (GP / 2); e += blockDim.x) {
+    const int y = e / (GP / 2), x = (e % (GP / 2)) * 2;
+    __half2 v = __floats2half2_rn(0.f, 0.f);
+    if (y < G && x < G) v = *(const __half2*)(Ig_p + (size_t)y * G + x);     // G even
+    *(__half2*)(Ip + (size_t)y * GP + x) = v;
+  }
+  for (int e = threadIdx.x; e < 64 * (GP / 2); e += blockDim.x) {
+    const int y = e / (GP / 2), x = (e % (GP / 2)) * 2;
+    __half2 v = __floats2half2_rn(0.f, 0.f);
+    if (y0 + y < G && x < G) v = *(const __half2*)(Sg_p + (size_t)(y0 + y) * G + x);
+    *(__half2*)(Sp + (size_t)y * GP + x) = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* pr = prow + warp * G;
-  const int NJ = (G + 31) / 32;
-  for (int y = y0 + warp; y < y1; y += 8) {
-    const __half* sr = Sp + (y - y0) * GP;
-    float lg[8];
-    float mx = -INFINITY;
-    for (int j = 0; j < NJ; ++j) {
-      const int x2 = lane + 32 * j;
-      float s = -INFINITY;
-      if (x2 < G) {
-        s = 0.f;
-        const __half* ir = Ip + x2 * GP;
-        for (int k = 0; k < G; k += 2) {
-          const float2 a = __half22float2(*(const __half2*)(sr + k));
-          const float2 bb = __half22float2(*(const __half2*)(ir + k));
-          s = fmaf(a.x, bb.x, s);
-          if (k + 1 < G) s = fmaf(a.y, bb.y, s);
-        }
+  const int gr = lane >> 2, gc = (lane & 3) * 2;
+  const int wr = warp * 16;                    // first slab row of this warp
+  if (y0 + wr >= G) return;
+  float s[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll 2
+  for (int kt = 0; kt < KT; ++kt) {
+    uint32_t a[4];
+    const __half* ar = Sp + (size_t)(wr + gr) * GP + kt * 16 + gc;
+    a[0] = *(const uint32_t*)ar;
+    a[1] = *(const uint32_t*)(ar + 8 * GP);
+    a[2] = *(const uint32_t*)(ar + 8);
+    a[3] = *(const uint32_t*)(ar + 8 * GP + 8);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const __half* br = Ip + (size_t)(nt * 8 + gr) * GP + kt * 16 + gc;      // B[k][n] = I[n][k]
+      mma16816(s[nt], a, *(const uint32_t*)br, *(const uint32_t*)(br + 8));
+    }
+  }
+  // softmax over the G keys (fp32, un-scaled logits: fusion_encoder.py:496-497)
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (nt * 8 + gc + (e & 1) >= G) s[nt][e] = -INFINITY;
+    m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+    m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pa[KT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const float e0 = __expf(s[nt][0] - m0), e1 = __expf(s[nt][1] - m0), e2 = __expf(s[nt][2] - m1), e3 = __expf(s[nt][3] - m1);
+    l0 += e0 + e1;
+    l1 += e2 + e3;
+    pa[nt >> 1][(nt & 1) * 2] = pack_h2(e0, e1);
+    pa[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(e2, e3);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = y0 + wr + gr, r1 = r0 + 8;
+  __half* Og_p = Og + (size_t)plane * G * G;
+  // out = S + (P I) / l, two halves of the output columns to bound the live accumulators
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float o[NT / 2][4];
+#pragma unroll
+    for (int n = 0; n < NT / 2; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      const __half* vr = Ip + (size_t)(kt * 16 + gc) * GP + half * (GPAD / 2) + gr;    // B[k = x2][n = x] = I[x2][x]
+#pragma unroll
+      for (int n = 0; n < NT / 2; ++n) {
+        const uint32_t b0 = pack_2h(vr[n * 8], vr[GP + n * 8]);
+        const uint32_t b1 = pack_2h(vr[8 * GP + n * 8], vr[9 * GP + n * 8]);
+        mma16816(o[n], pa[kt], b0, b1);
       }
-      lg[j] = s;
-      mx = fmaxf(mx, s);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int j = 0; j < NJ; ++j) {
-      const int x2 = lane + 32 * j;
-      const float e = x2 < G ? __expf(lg[j] - mx) : 0.f;
-      lg[j] = e;
-      sum += e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.f / sum;
-    __syncwarp();
-    for (int j = 0; j < NJ; ++j) {
-      const int x2 = lane + 32 * j;
-      if (x2 < G) pr[x2] = lg[j] * inv;
-    }
-    __syncwarp();
-    // out[y][x] = S[y][x] + sum_x2 p[x2] * I[x2][x]
-    for (int j = 0; j < NJ; ++j) {
-      const int x = lane + 32 * j;
+    for (int n = 0; n < NT / 2; ++n) {
+      const int x = half * (GPAD / 2) + n * 8 + gc;
       if (x < G) {
-        float acc = 0.f;
-        for (int x2 = 0; x2 < G; ++x2) acc = fmaf(pr[x2], __half2float(Ip[x2 * GP + x]), acc);
-        acc += __half2float(sr[x]);
-        out[(plane + (size_t)y * G + x) * ldo + c] = __float2half_rn(acc);
+        if (r0 < G) {
+          const float2 sv = __half22float2(*(const __half2*)(Sp + (size_t)(wr + gr) * GP + x));
+          *(__half2*)(Og_p + (size_t)r0 * G + x) = __floats2half2_rn(sv.x + o[n][0] * i0, sv.y + o[n][1] * i0);
+        }
+        if (r1 < G) {
+          const float2 sv = __half22float2(*(const __half2*)(Sp + (size_t)(wr + gr + 8) * GP + x));
+          *(__half2*)(Og_p + (size_t)r1 * G + x) = __floats2half2_rn(sv.x + o[n][2] * i1, sv.y + o[n][3] * i1);
+        }
       }
     }
   }
 }
 
+extern "C" int isf_channel_attention_workspace_size(int batch, int grid, int channels, size_t* bytes) {
+  ISF_CHECK_ARG(bytes && batch >= 1 && grid >= 2 && channels >= 1);
+  *bytes = (size_t)3 * batch * channels * grid * grid * sizeof(__half) + 1024;
+  return ISF_OK;
+}
+
 extern "C" int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid,
-                                     int channels, void* out, int ldo, void* stream) {
-  ISF_CHECK_ARG(scene && ins && out && batch >= 1 && grid >= 2 && grid <= 256 && channels >= 1);
-  const int GP = grid + 2 + ((grid & 1) ? 1 : 0);
-  const int slab = (grid + CA_SPLIT - 1) / CA_SPLIT;
-  const size_t smem = (size_t)(grid + slab) * GP * sizeof(__half) + 8 * grid * sizeof(float);
-  ISF_CHECK_ARG(smem <= 227 * 1024);
+                                     int channels, void* out, int ldo, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(scene && ins && out && workspace && batch >= 1 && grid >= 2 && channels >= 1);
+  if (grid > 192 || (grid & 1)) { isf_set_error("channel_attention: built for even BEV sizes <= 192"); return ISF_ERR_UNSUPPORTED; }
+  constexpr int GPAD = 192, GP = GPAD + 8;
+  const size_t plane_elems = (size_t)batch * channels * grid * grid;
+  if (ws_bytes < 3 * plane_elems * sizeof(__half)) { isf_set_error("channel_attention: workspace too small"); return ISF_ERR_WORKSPACE; }
+  __half* Sp = (__half*)workspace;
+  __half* Ip = Sp + plane_elems;
+  __half* Op = Ip + plane_elems;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = grid * grid;
+  dim3 tg(isf_cdiv(HW, 32), isf_cdiv(channels, 32), batch);
+  nhwc_to_nchw_kernel<<<tg, 256, 0, st>>>((const __half*)scene, lds, HW, channels, Sp);
+  nhwc_to_nchw_kernel<<<tg, 256, 0, st>>>((const __half*)ins, ldi, HW, channels, Ip);
+  const size_t smem = (size_t)(GPAD + 64) * GP * sizeof(__half);
   static bool cfg = false;
   if (!cfg) {
-    ISF_CUDA(cudaFuncSetAttribute(channel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ISF_CUDA(cudaFuncSetAttribute(channel_attention_kernel<GPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cfg = true;
   }
-  channel_attention_kernel<<<batch * channels * CA_SPLIT, 256, smem, (cudaStream_t)stream>>>(
-      (const __half*)scene, lds, (const __half*)ins, ldi, grid, channels, (__half*)out, ldo);
-  isf_count_launch(1);
+  const int slabs = (grid + 63) / 64;
+  channel_attention_kernel<GPAD><<<batch * channels * slabs, 128, smem, st>>>(Sp, Ip, grid, Op);
+  nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(Op, HW, channels, (__half*)out, ldo);
+  isf_count_launch(4);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
 }

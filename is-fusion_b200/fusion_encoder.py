@@ -566,7 +566,11 @@ class ISFusionEncoder(_Packable):
         query_ins = gemm(att, pk['i2s_wo'], shift=pk['i2s_bo'], residual=ins_tok, ln=pk['i2s_ln'])
         fused = torch.empty((bs, g, g, c), dtype=torch.float16, device=dev)
         scene = scene.contiguous()
-        L.check(lib.isf_channel_attention(L.ptr(scene), c, L.ptr(query_ins), c, bs, g, c, L.ptr(fused), c, L.stream()))
+        cab = ctypes.c_size_t(0)
+        L.check(lib.isf_channel_attention_workspace_size(bs, g, c, ctypes.byref(cab)))
+        caws = torch.empty(cab.value, dtype=torch.uint8, device=dev)
+        L.check(lib.isf_channel_attention(L.ptr(scene), c, L.ptr(query_ins), c, bs, g, c, L.ptr(fused), c, L.ptr(caws),
+                                          ctypes.c_size_t(caws.numel()), L.stream()))
         ins_heatmap = logits.transpose(2, 3)                  # back to the reference's [X,Y] frame
         self._dbg = dict(top_idx=tx * g + ty, x_ins=out)
         return fused, ins_heatmap

@@ -162,7 +162,12 @@ def test_instance_to_scene_parity():
               ln=(ref.norm.weight.data.cuda().contiguous(), ref.norm.bias.data.cuda().contiguous(), ref.norm.eps))
     sc = scene.permute(0, 2, 3, 1).half().cuda().contiguous()
     out = torch.empty_like(sc)
-    L.check(L.lib().isf_channel_attention(L.ptr(sc), C, L.ptr(qi), C, B, G, C, L.ptr(out), C, L.stream()))
+    import ctypes
+    nb = ctypes.c_size_t(0)
+    L.check(L.lib().isf_channel_attention_workspace_size(B, G, C, ctypes.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device='cuda')
+    L.check(L.lib().isf_channel_attention(L.ptr(sc), C, L.ptr(qi), C, B, G, C, L.ptr(out), C, L.ptr(ws),
+                                          ctypes.c_size_t(ws.numel()), L.stream()))
     r, m = rel(out.permute(0, 3, 1, 2), want)
     print('i2s rel %.2e max %.2e' % (r, m))
     assert r < 3e-3, (r, m)
