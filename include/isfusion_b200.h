@@ -128,9 +128,9 @@ int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad, int n, co
  * (every *_dev count argument is optional: when given it overrides the host count, which then is the capacity
  *  of the buffer — this is what keeps the whole encoder free of host synchronisation / graph-capturable.)
  * isf_spconv_out_indices: output sites of a strided SparseConv3d = sorted-unique linear index of every
- *   (input, kernel offset) candidate (the GPU ordering of spconv_ops.h:129-137): candidates are de-duplicated
- *   in a hash set, only the unique keys are radix-sorted; writes up to out_cap rows and the count (clamped to
- *   out_cap; == out_cap means "possibly overflowed") to *num_out_dev.
+ *   (input, kernel offset) candidate (the GPU ordering of spconv_ops.h:129-137): the valid candidates
+ *   (<= prod ceil(k/s) <= 8 per input site) are compacted, radix-sorted and made unique; writes up to out_cap rows
+ *   and the count (clamped to out_cap; == out_cap means "possibly overflowed") to *num_out_dev.
  * isf_spconv_neighbors: neighbour table nbr[k * nbr_stride + o] = input row reaching output row o via kernel
  *   offset k (k = (kz*KH+ky)*KW+kx, geometry.h:62-73) or -1.  subm=1: outputs = inputs, centre aligned.
  * isf_spconv_implicit_gemm: out[o, :] = act((sum_k in[nbr[k,o], :] . W[k]) * scale + shift + residual[o, :])

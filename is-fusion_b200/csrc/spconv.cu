@@ -107,12 +107,11 @@ extern "C" int isf_hash_build(const int* indices, int v, const int* v_dev, const
 // ------------------------------------------------------------------------------------------------
 // strided conv: output sites
 // ------------------------------------------------------------------------------------------------
-// every (input site, kernel offset) proposes an output site; a hash SET keeps one copy of each and the winner
-// of the insert appends the key to a compact list (warp-aggregated counter) -> only the V_out unique keys are sorted
-__global__ void __launch_bounds__(256) candidate_insert_kernel(const int* __restrict__ indices, int v, const int* v_dev,
-                                                               ConvGeom g, unsigned int* __restrict__ set_keys,
-                                                               unsigned int mask, unsigned int* __restrict__ list,
-                                                               int list_cap, int* __restrict__ list_count) {
+// every (input site, kernel offset) proposes an output site; the VALID proposals (<= ceil(k/s)^3 per input) are
+// appended to a compact list (warp-aggregated counter), radix-sorted and made unique
+__global__ void __launch_bounds__(256) candidate_append_kernel(const int* __restrict__ indices, int v, const int* v_dev,
+                                                               ConvGeom g, unsigned int* __restrict__ list, int list_cap,
+                                                               int* __restrict__ list_count) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)v * g.kvol;
   bool won = false;
@@ -132,17 +131,7 @@ __global__ void __launch_bounds__(256) candidate_insert_kernel(const int* __rest
         ok &= (num >= 0) && (q * g.stride[d] == num) && (q < g.out_shape[d]);
         o[d] = q;
       }
-      if (ok) {
-        key = lin_key(c[0], o[0], o[1], o[2], g.out_shape);
-        unsigned int slot = hash_u32(key) & mask;
-        // bounded probing: a full set (capacity overflow, reported through the count) must not spin forever
-        for (unsigned int probes = 0; probes <= mask; ++probes) {
-          unsigned int prev = atomicCAS(&set_keys[slot], HASH_EMPTY, key);
-          if (prev == HASH_EMPTY) { won = true; break; }
-          if (prev == key) break;
-          slot = (slot + 1) & mask;
-        }
-      }
+      if (ok) { key = lin_key(c[0], o[0], o[1], o[2], g.out_shape); won = true; }
     }
   }
   const unsigned ballot = __ballot_sync(0xffffffffu, won);
@@ -161,7 +150,8 @@ __global__ void __launch_bounds__(256) candidate_insert_kernel(const int* __rest
 __global__ void __launch_bounds__(256) decode_out_kernel(const unsigned int* __restrict__ sorted,
                                                          const int* __restrict__ list_count, ConvGeom g, int cap,
                                                          int* __restrict__ out_indices, int* __restrict__ num_out) {
-  int n = *list_count;
+  int n = *list_count;                                         // unique keys incl. the all-ones filler (sorts last)
+  if (n > 0 && sorted[n - 1] == HASH_EMPTY) n -= 1;
   if (n > cap) n = cap;
   if (blockIdx.x == 0 && threadIdx.x == 0) *num_out = n;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -175,34 +165,37 @@ __global__ void __launch_bounds__(256) decode_out_kernel(const unsigned int* __r
 }
 
 static size_t outidx_cub_bytes(long long n) {
-  size_t a = 0;
+  size_t a = 0, b = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, a, (unsigned int*)nullptr, (unsigned int*)nullptr, n);
-  return a;
+  cub::DeviceSelect::Unique(nullptr, b, (unsigned int*)nullptr, (unsigned int*)nullptr, (int*)nullptr, n);
+  return a > b ? a : b;
 }
 
-static long long pow2_at_least(long long x) {
-  long long c = 1024;
-  while (c < x) c <<= 1;
-  return c;
+static int conv_reach(const int* ksize, const int* stride) {
+  int r = 1;
+  for (int d = 0; d < 3; ++d) r *= (ksize[d] + stride[d] - 1) / stride[d];
+  return r;
 }
 
-static void outidx_carve(IsfArena& A, long long out_cap, unsigned int** set_keys, long long* set_cap, unsigned int** list,
-                         unsigned int** sorted, int** count, void** cub_tmp, size_t* cub_bytes) {
-  *set_cap = pow2_at_least(2 * out_cap);
-  *set_keys = A.take<unsigned int>(*set_cap);
-  *list = A.take<unsigned int>(out_cap);
-  *sorted = A.take<unsigned int>(out_cap);
+static void outidx_carve(IsfArena& A, long long list_cap, unsigned int** list, unsigned int** sorted, unsigned int** uniq,
+                         int** count, int** num_sel, void** cub_tmp, size_t* cub_bytes) {
+  *list = A.take<unsigned int>(list_cap);
+  *sorted = A.take<unsigned int>(list_cap);
+  *uniq = A.take<unsigned int>(list_cap);
   *count = A.take<int>(1);
-  *cub_bytes = outidx_cub_bytes(out_cap);
+  *num_sel = A.take<int>(1);
+  *cub_bytes = outidx_cub_bytes(list_cap);
   *cub_tmp = A.take<char>(*cub_bytes);
 }
 
-// workspace for isf_spconv_out_indices with an output buffer of out_cap rows (v_in, kvol kept for API stability)
+// workspace for isf_spconv_out_indices: the candidate list holds up to reach = prod ceil(k/s) proposals per input
+// site; `reach` is passed by the caller as `kvol`'s companion through out_cap >= 0 (kept for API stability)
 extern "C" int isf_spconv_out_indices_workspace_size(int v_in, int kvol, int out_cap, size_t* bytes) {
   ISF_CHECK_ARG(v_in >= 0 && kvol >= 1 && out_cap >= 0 && bytes);
   IsfArena A(nullptr, 0);
-  unsigned int *a, *b, *c; int* d; void* e; size_t f; long long sc;
-  outidx_carve(A, out_cap > 0 ? out_cap : 1, &a, &sc, &b, &c, &d, &e, &f);
+  unsigned int *a, *b, *c; int *d, *e; void* f; size_t g;
+  long long cap = (long long)(v_in > 0 ? v_in : 1) * (kvol < 8 ? kvol : 8);
+  outidx_carve(A, cap, &a, &b, &c, &d, &e, &f, &g);
   *bytes = A.off + 1024;
   return ISF_OK;
 }
@@ -229,21 +222,27 @@ extern "C" int isf_spconv_out_indices(const int* in_indices, int v_in, const int
   ISF_CHECK_ARG(cells > 0 && cells < 0xFFFFFFFFll);
   long long n = (long long)v_in * g.kvol;
   ISF_CHECK_ARG(n < 0x7fffffffll);
+  int reach = conv_reach(ksize, stride);
+  if (reach > g.kvol) reach = g.kvol;
+  ISF_CHECK_ARG(reach <= 8);
+  const long long list_cap = (long long)v_in * (g.kvol < 8 ? g.kvol : 8);
   IsfArena A(workspace, ws_bytes);
-  unsigned int *set_keys, *list, *sorted; int* count; void* cub_tmp; size_t cub_bytes; long long set_cap;
-  outidx_carve(A, out_cap, &set_keys, &set_cap, &list, &sorted, &count, &cub_tmp, &cub_bytes);
+  unsigned int *list, *sorted, *uniq; int *count, *num_sel; void* cub_tmp; size_t cub_bytes;
+  outidx_carve(A, list_cap, &list, &sorted, &uniq, &count, &num_sel, &cub_tmp, &cub_bytes);
   if (!A.ok) { isf_set_error("spconv_out_indices: workspace too small"); return ISF_ERR_WORKSPACE; }
-  ISF_CUDA(cudaMemsetAsync(set_keys, 0xFF, sizeof(unsigned int) * set_cap, st));
-  ISF_CUDA(cudaMemsetAsync(list, 0xFF, sizeof(unsigned int) * out_cap, st));   // unused slots sort last
+  // only the first v_in*reach slots can be written; the filler (all ones) sorts last
+  const long long n_sort = (long long)v_in * reach;
+  ISF_CUDA(cudaMemsetAsync(list, 0xFF, sizeof(unsigned int) * n_sort, st));
   ISF_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
-  candidate_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, set_keys,
-                                                                        (unsigned)set_cap - 1, list, out_cap, count);
+  candidate_append_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, list, (int)n_sort, count);
   int bits = 1;
   while ((1ll << bits) < cells) ++bits;
   int end_bit = bits + 1 > 32 ? 32 : bits + 1;   // keeps the all-ones filler last
   size_t tmp = cub_bytes;
-  ISF_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, tmp, list, sorted, out_cap, 0, end_bit, st));
-  decode_out_kernel<<<ISF_NUM_SMS * 2, 256, 0, st>>>(sorted, count, g, out_cap, out_indices, num_out_dev);
+  ISF_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp, tmp, list, sorted, (int)n_sort, 0, end_bit, st));
+  tmp = cub_bytes;
+  ISF_CUDA(cub::DeviceSelect::Unique(cub_tmp, tmp, sorted, uniq, num_sel, (int)n_sort, st));
+  decode_out_kernel<<<ISF_NUM_SMS * 2, 256, 0, st>>>(uniq, num_sel, g, out_cap, out_indices, num_out_dev);
   isf_count_launch(8);
   ISF_LAUNCH_CHECK();
   return ISF_OK;

@@ -42,9 +42,11 @@ def _fold_conv_bn(conv, bn, transpose_kernel=False):
 def _conv(x_nhwc, packed, stride=1, relu=True):
     """3x3 conv + folded BN (+ReLU) on a channels-last fp16 map [B,Y,X,C] (cuDNN implicit GEMM)."""
     w, b = packed
-    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), w, b, stride=stride, padding=1)
-    if relu:
-        y = torch.relu_(y)
+    x = x_nhwc.permute(0, 3, 1, 2)
+    if relu:     # cuDNN runtime-fused conv + bias + ReLU (one kernel)
+        y = torch.cudnn_convolution_relu(x, w, b, [stride, stride], [1, 1], [1, 1], 1)
+    else:
+        y = F.conv2d(x, w, b, stride=stride, padding=1)
     return y.permute(0, 2, 3, 1)        # stays channels-last in memory: a free view
 
 
