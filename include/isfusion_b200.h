@@ -152,6 +152,24 @@ int isf_spconv_neighbors(const int* out_indices, int v_out, const int* v_out_dev
                          int in_capacity, const int* in_shape, const int* ksize, const int* stride,
                          const int* padding, const int* dilation, int subm, int* nbr, long long nbr_stride,
                          void* stream);
+/* bitmap-rank rulebook for tensors whose rows are in ascending linear-key order (every tensor this library
+ * produces): one bit per cell (`bits`, isf_bitmap_words(shape,batch) words) + exclusive prefix of the word popcounts
+ * (`prefix`, same length) give row(coordinate) in O(1) and the sorted-unique output sites of a strided conv with no
+ * sort.  isf_bitmap_build: map of an existing tensor.  isf_bitmap_out_sites: output sites of a strided conv (also
+ * the map of the output tensor).  isf_spconv_neighbors_bitmap: isf_spconv_neighbors on such a map.  Workspace:
+ * isf_bitmap_workspace_size(words). */
+long long isf_bitmap_words(const int* spatial_shape, int batch);
+int isf_bitmap_workspace_size(long long words, size_t* bytes);
+int isf_bitmap_build(const int* indices, int v, const int* v_dev, const int* spatial_shape, int batch,
+                     unsigned int* bits, int* prefix, void* workspace, size_t ws_bytes, void* stream);
+int isf_bitmap_out_sites(const int* in_indices, int v_in, const int* v_in_dev, const int* in_shape, int batch,
+                         const int* ksize, const int* stride, const int* padding, const int* dilation,
+                         unsigned int* out_bits, int* out_prefix, int* out_indices, int out_cap, int* num_out_dev,
+                         void* workspace, size_t ws_bytes, void* stream);
+int isf_spconv_neighbors_bitmap(const int* out_indices, int v_out, const int* v_out_dev, const unsigned int* in_bits,
+                                const int* in_prefix, const int* in_shape, const int* ksize, const int* stride,
+                                const int* padding, const int* dilation, int subm, int* nbr, long long nbr_stride,
+                                void* stream);
 int isf_spconv_implicit_gemm(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,
                              const int* nbr, long long nbr_stride, int taps, int v_out, const int* v_out_dev,
                              const float* scale, const float* shift, const void* residual, int ldr, int relu,

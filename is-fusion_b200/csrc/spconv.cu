@@ -300,6 +300,208 @@ extern "C" int isf_spconv_neighbors(const int* out_indices, int v_out, const int
 }
 
 // ------------------------------------------------------------------------------------------------
+// bitmap-rank rulebook (rows in ascending linear-key order, which is how this library produces every tensor):
+// a coordinate set is one bit per cell + an exclusive prefix of the word popcounts, so
+//   row(coordinate) = prefix[key >> 5] + popc(bits[key >> 5] & ((1 << (key & 31)) - 1))          (O(1), no probing)
+// and the sorted-unique output sites of a strided conv are simply the set bits in order (no sort at all).
+// ------------------------------------------------------------------------------------------------
+struct PopcOp {
+  __host__ __device__ int operator()(const unsigned int& w) const {
+#ifdef __CUDA_ARCH__
+    return __popc(w);
+#else
+    return __builtin_popcount(w);
+#endif
+  }
+};
+
+__global__ void __launch_bounds__(256) bitmap_set_kernel(const int* __restrict__ indices, int v, const int* v_dev, ConvGeom g,
+                                                         unsigned int* __restrict__ bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = v_dev ? *v_dev : v;
+  if (i >= n) return;
+  const int* c = indices + (size_t)i * 4;
+  unsigned int key = lin_key(c[0], c[1], c[2], c[3], g.in_shape);
+  atomicOr(&bits[key >> 5], 1u << (key & 31));
+}
+
+__global__ void __launch_bounds__(256) bitmap_candidates_kernel(const int* __restrict__ indices, int v, const int* v_dev,
+                                                                ConvGeom g, unsigned int* __restrict__ bits) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)v * g.kvol;
+  if (t >= total) return;
+  int i = (int)(t / g.kvol), k = (int)(t % g.kvol);
+  if (v_dev && i >= *v_dev) return;
+  int kk[3];
+  kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
+  const int* c = indices + (size_t)i * 4;
+  int o[3];
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int num = c[1 + d] + g.pad[d] - kk[d] * g.dil[d];
+    int q = num / g.stride[d];
+    ok &= (num >= 0) && (q * g.stride[d] == num) && (q < g.out_shape[d]);
+    o[d] = q;
+  }
+  if (!ok) return;
+  unsigned int key = lin_key(c[0], o[0], o[1], o[2], g.out_shape);
+  atomicOr(&bits[key >> 5], 1u << (key & 31));
+}
+
+__global__ void __launch_bounds__(256) bitmap_enumerate_kernel(const unsigned int* __restrict__ bits,
+                                                               const int* __restrict__ prefix, long long words, ConvGeom g,
+                                                               int cap, int* __restrict__ out_indices, int* __restrict__ num_out) {
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
+    unsigned int word = bits[w];
+    int row = prefix[w];
+    if (w == words - 1) { int tot = row + __popc(word); *num_out = tot < cap ? tot : cap; }
+    while (word) {
+      const int b = __ffs(word) - 1;
+      word &= word - 1;
+      if (row < cap) {
+        unsigned int k = (unsigned int)(w * 32 + b);
+        int x = k % g.out_shape[2]; k /= g.out_shape[2];
+        int y = k % g.out_shape[1]; k /= g.out_shape[1];
+        int z = k % g.out_shape[0]; k /= g.out_shape[0];
+        int* o = out_indices + (size_t)row * 4;
+        o[0] = (int)k; o[1] = z; o[2] = y; o[3] = x;
+      }
+      ++row;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nbr_bitmap_kernel(const int* __restrict__ out_indices, int v_out, const int* v_out_dev,
+                                                         ConvGeom g, const unsigned int* __restrict__ bits,
+                                                         const int* __restrict__ prefix, int* __restrict__ nbr,
+                                                         long long nbr_stride) {
+  const int n = v_out_dev ? *v_out_dev : v_out;
+  const long long total = (long long)n * g.kvol;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(t / n), j = (int)(t % n);
+    int kk[3];
+    kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
+    const int* o = out_indices + (size_t)j * 4;
+    int ip[3];
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ip[d] = o[1 + d] * g.stride[d] - g.pad[d] + kk[d] * g.dil[d];
+      ok &= ip[d] >= 0 && ip[d] < g.in_shape[d];
+    }
+    int r = -1;
+    if (ok) {
+      const unsigned int key = lin_key(o[0], ip[0], ip[1], ip[2], g.in_shape);
+      const unsigned int word = bits[key >> 5], b = key & 31;
+      if ((word >> b) & 1u) r = prefix[key >> 5] + __popc(word & ((1u << b) - 1u));
+    }
+    nbr[(long long)k * nbr_stride + j] = r;
+  }
+}
+
+static long long bitmap_words(const int* shape, int batch) {
+  long long cells = (long long)batch * shape[0] * shape[1] * shape[2];
+  return (cells + 31) / 32;
+}
+
+static size_t bitmap_scan_bytes(long long words) {
+  size_t a = 0;
+  cub::TransformInputIterator<int, PopcOp, const unsigned int*> it((const unsigned int*)nullptr, PopcOp());
+  cub::DeviceScan::ExclusiveSum(nullptr, a, it, (int*)nullptr, (int)words);
+  return a;
+}
+
+static int bitmap_scan(const unsigned int* bits, int* prefix, long long words, void* ws, size_t ws_bytes, cudaStream_t st) {
+  cub::TransformInputIterator<int, PopcOp, const unsigned int*> it(bits, PopcOp());
+  size_t need = bitmap_scan_bytes(words);
+  if (need > ws_bytes) { isf_set_error("bitmap scan: workspace too small"); return ISF_ERR_WORKSPACE; }
+  ISF_CUDA(cub::DeviceScan::ExclusiveSum(ws, need, it, prefix, (int)words, st));
+  return ISF_OK;
+}
+
+// number of 32-bit words of the bitmap (and of the prefix array) of a coordinate space
+extern "C" long long isf_bitmap_words(const int* spatial_shape, int batch) {
+  if (!spatial_shape) return 0;
+  return bitmap_words(spatial_shape, batch);
+}
+
+extern "C" int isf_bitmap_workspace_size(long long words, size_t* bytes) {
+  ISF_CHECK_ARG(words >= 1 && words < 0x7fffffffll && bytes);
+  *bytes = bitmap_scan_bytes(words) + 1024;
+  return ISF_OK;
+}
+
+// bitmap + prefix of a tensor whose rows are in ascending linear-key order (row == rank)
+extern "C" int isf_bitmap_build(const int* indices, int v, const int* v_dev, const int* spatial_shape, int batch,
+                                unsigned int* bits, int* prefix, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(v >= 0 && spatial_shape && bits && prefix && workspace);
+  long long words = bitmap_words(spatial_shape, batch);
+  ISF_CHECK_ARG(words >= 1 && words < 0x7fffffffll / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  ISF_CUDA(cudaMemsetAsync(bits, 0, sizeof(unsigned int) * words, st));
+  if (v > 0) {
+    ISF_CHECK_ARG(indices);
+    ConvGeom g{};
+    for (int d = 0; d < 3; ++d) g.in_shape[d] = spatial_shape[d];
+    bitmap_set_kernel<<<isf_cdiv(v, 256), 256, 0, st>>>(indices, v, v_dev, g, bits);
+  }
+  int rc = bitmap_scan(bits, prefix, words, workspace, ws_bytes, st);
+  if (rc) return rc;
+  isf_count_launch(4);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// output sites of a strided conv as a bitmap: sets out_bits / out_prefix (the coordinate->row map of the OUTPUT
+// tensor, reusable as the input map of the next layer) and writes the sorted-unique out_indices + count
+extern "C" int isf_bitmap_out_sites(const int* in_indices, int v_in, const int* v_in_dev, const int* in_shape, int batch,
+                                    const int* ksize, const int* stride, const int* padding, const int* dilation,
+                                    unsigned int* out_bits, int* out_prefix, int* out_indices, int out_cap,
+                                    int* num_out_dev, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(v_in >= 0 && in_shape && ksize && stride && padding && out_bits && out_prefix && num_out_dev && workspace);
+  ConvGeom g;
+  fill_geom(&g, in_shape, ksize, stride, padding, dilation, 0);
+  long long words = bitmap_words(g.out_shape, batch);
+  ISF_CHECK_ARG(words >= 1 && words < 0x7fffffffll / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  ISF_CUDA(cudaMemsetAsync(out_bits, 0, sizeof(unsigned int) * words, st));
+  if (v_in > 0) {
+    ISF_CHECK_ARG(in_indices && out_indices);
+    long long n = (long long)v_in * g.kvol;
+    bitmap_candidates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, out_bits);
+  }
+  int rc = bitmap_scan(out_bits, out_prefix, words, workspace, ws_bytes, st);
+  if (rc) return rc;
+  int blocks = (int)((words + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 8) blocks = ISF_NUM_SMS * 8;
+  bitmap_enumerate_kernel<<<blocks, 256, 0, st>>>(out_bits, out_prefix, words, g, out_cap, out_indices, num_out_dev);
+  isf_count_launch(5);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+extern "C" int isf_spconv_neighbors_bitmap(const int* out_indices, int v_out, const int* v_out_dev,
+                                           const unsigned int* in_bits, const int* in_prefix, const int* in_shape,
+                                           const int* ksize, const int* stride, const int* padding, const int* dilation,
+                                           int subm, int* nbr, long long nbr_stride, void* stream) {
+  ISF_CHECK_ARG(v_out >= 0 && in_shape && ksize && in_bits && in_prefix && nbr_stride >= v_out);
+  ISF_CHECK_ARG(subm || (stride && padding));
+  if (v_out == 0) return ISF_OK;
+  ISF_CHECK_ARG(out_indices && nbr);
+  ConvGeom g;
+  fill_geom(&g, in_shape, ksize, stride, padding, dilation, subm);
+  long long total = (long long)v_out * g.kvol;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+  nbr_bitmap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_indices, v_out, v_out_dev, g, in_bits, in_prefix, nbr,
+                                                              nbr_stride);
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // the convolution itself: implicit GEMM over the neighbour table
 // ------------------------------------------------------------------------------------------------
 extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,

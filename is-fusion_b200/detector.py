@@ -93,7 +93,8 @@ class ISFusionDetector(nn.Module):
             r = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas, batch_size=batch_size, nosync=nosync)
         nv = r[2] if nosync else None
         with stage('a4 sparse_encoder'):
-            x, _, kwargs = self.pts_middle_encoder(r[0], r[1], batch_size, dense=False, num_voxels_dev=nv, **kwargs)
+            x, _, kwargs = self.pts_middle_encoder(r[0], r[1], batch_size, dense=False, num_voxels_dev=nv,
+                                                   sorted_coors=True, **kwargs)
         kwargs['lidar_sparse'] = self.pts_middle_encoder.last_out
         return self.isfusion(pts, x, img_feats, img_metas, batch_size, nosync=nosync, **kwargs)
 

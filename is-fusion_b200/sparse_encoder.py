@@ -133,11 +133,12 @@ class SparseEncoder(nn.Module):
 
     @torch.no_grad()
     def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True,
-                num_voxels_dev=None, **kwargs):
+                num_voxels_dev=None, sorted_coors=False, **kwargs):
         """voxel_features [V,C], coors [V,4] int32 (b,z,y,x) -> (spatial_features [B, C*D, H, W], encode_features, kwargs)"""
         coors = coors.int()
         feats = voxel_features if voxel_features.dtype == torch.float16 else voxel_features.half()
         x = SparseConvTensor(feats.contiguous(), coors.contiguous(), self.sparse_shape, batch_size, num_dev=num_voxels_dev)
+        x.sorted = bool(sorted_coors)      # DynamicVFE output is in sorted-unique (b,z,y,x) order -> bitmap rulebooks
         x = self.conv_input(x)
         encode_features = [x]
         for encoder_layer in self.encoder_layers:

@@ -30,6 +30,9 @@ class SparseConvTensor:
         # capacity mode (sync-free / CUDA-graph path): rows [0, *num_dev) of features / indices are valid, the
         # rest of the buffers is capacity.  None = exact mode (every row valid), the spconv API contract.
         self.num_dev = num_dev
+        # rows are in ascending linear (b,z,y,x) key order (true for everything this library produces): enables the
+        # bitmap-rank rulebook; False = unknown order -> hash-table rulebook
+        self.sorted = False
 
     @property
     def spatial_size(self):
@@ -41,6 +44,7 @@ class SparseConvTensor:
     def replace_feature(self, feature):
         t = SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.num_dev)
         t.indice_dict = self.indice_dict
+        t.sorted = self.sorted
         return t
 
     def find_indice_pair(self, key):
@@ -106,7 +110,82 @@ def check_overflow():
     return bad
 
 
+def _bitmap(x):
+    """bitmap + prefix coordinate->row map of a tensor in sorted row order (cached on the tensor)."""
+    key = ('bitmap', x.indices.data_ptr(), x.indices.shape[0])
+    bm = x.indice_dict.get(key)
+    if bm is None:
+        lib = L.lib()
+        dev = x.indices.device
+        words = int(lib.isf_bitmap_words(L.host_i32(x.spatial_shape), x.batch_size))
+        bits = torch.empty(words, dtype=torch.int32, device=dev)
+        prefix = torch.empty(words, dtype=torch.int32, device=dev)
+        wsb = ctypes.c_size_t(0)
+        L.check(lib.isf_bitmap_workspace_size(ctypes.c_longlong(words), ctypes.byref(wsb)))
+        ws = L.workspace(wsb.value, dev)
+        L.check(lib.isf_bitmap_build(L.ptr(x.indices), x.indices.shape[0], L.ptr(x.num_dev), L.host_i32(x.spatial_shape),
+                                     x.batch_size, L.ptr(bits), L.ptr(prefix), L.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                     L.stream()))
+        bm = (bits, prefix)
+        x.indice_dict[key] = bm
+    return bm
+
+
+def build_rulebook_bitmap(x, ksize, stride, padding, dilation, subm, out_capacity=None):
+    """rulebook of a tensor in sorted row order: no hash table, no sort (see csrc/spconv.cu, bitmap-rank rulebook)."""
+    lib = L.lib()
+    dev = x.indices.device
+    v_in = x.indices.shape[0]
+    bits, prefix = _bitmap(x)
+    taps = ksize[0] * ksize[1] * ksize[2]
+    num_dev = None
+    if subm:
+        out_indices, out_shape, v_out, num_dev = x.indices, list(x.spatial_shape), v_in, x.num_dev
+    else:
+        oshape = (ctypes.c_int * 3)()
+        L.check(lib.isf_spconv_out_shape(L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
+                                         L.host_i32(padding), L.host_i32(dilation), oshape))
+        out_shape = list(oshape)
+        cells = x.batch_size * out_shape[0] * out_shape[1] * out_shape[2]
+        reach = 1
+        for d in range(3):
+            reach *= -(-ksize[d] // stride[d])
+        cap_out = min(v_in * reach, cells)
+        capacity_mode = x.num_dev is not None
+        if capacity_mode and out_capacity is not None:
+            cap_out = min(cap_out, int(out_capacity))
+        words = int(lib.isf_bitmap_words(L.host_i32(out_shape), x.batch_size))
+        obits = torch.empty(words, dtype=torch.int32, device=dev)
+        oprefix = torch.empty(words, dtype=torch.int32, device=dev)
+        wsb = ctypes.c_size_t(0)
+        L.check(lib.isf_bitmap_workspace_size(ctypes.c_longlong(words), ctypes.byref(wsb)))
+        ws = L.workspace(wsb.value, dev)
+        out_buf = torch.empty((max(cap_out, 1), 4), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.check(lib.isf_bitmap_out_sites(L.ptr(x.indices), v_in, L.ptr(x.num_dev), L.host_i32(x.spatial_shape), x.batch_size,
+                                         L.host_i32(ksize), L.host_i32(stride), L.host_i32(padding), L.host_i32(dilation),
+                                         L.ptr(obits), L.ptr(oprefix), L.ptr(out_buf), cap_out, L.ptr(cnt), L.ptr(ws),
+                                         ctypes.c_size_t(ws.numel()), L.stream()))
+        if capacity_mode:
+            v_out, out_indices, num_dev = cap_out, out_buf, cnt
+            OVERFLOW_WATCH.append((cnt, cap_out))
+        else:
+            v_out = int(cnt.item())
+            out_indices = out_buf[:v_out]
+        # the output-site bitmap IS the coordinate map of the output tensor: the next layer reuses it
+        x.indice_dict[('bitmap', out_indices.data_ptr(), out_indices.shape[0])] = (obits, oprefix)
+    stride_rows = max((v_out + 127) // 128 * 128, 128)
+    nbr = torch.empty((taps, stride_rows), dtype=torch.int32, device=dev)
+    L.check(lib.isf_spconv_neighbors_bitmap(L.ptr(out_indices), v_out, L.ptr(num_dev), L.ptr(bits), L.ptr(prefix),
+                                            L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
+                                            L.host_i32(padding), L.host_i32(dilation), 1 if subm else 0, L.ptr(nbr),
+                                            ctypes.c_longlong(stride_rows), L.stream()))
+    return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev)
+
+
 def build_rulebook(x, ksize, stride, padding, dilation, subm, out_capacity=None):
+    if x.sorted:
+        return build_rulebook_bitmap(x, ksize, stride, padding, dilation, subm, out_capacity)
     lib = L.lib()
     dev = x.indices.device
     v_in = x.indices.shape[0]
@@ -276,6 +355,7 @@ class SparseConvolution(SparseModule):
                           shift, residual, relu)
         out = SparseConvTensor(f, rb.out_indices, rb.out_shape, x.batch_size, num_dev=rb.num_dev)
         out.indice_dict = x.indice_dict
+        out.sorted = x.sorted if self.subm else True      # strided outputs are sorted-unique by construction
         return out
 
 

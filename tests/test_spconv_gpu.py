@@ -138,3 +138,30 @@ def test_sparse_encoder_cluster_variant_bit_identical(cs):
         assert torch.equal(out, ref)
     finally:
         L.set_option('gemm_cluster', 1)
+
+
+def test_bitmap_rulebook_matches_hash_rulebook():
+    """sorted-row tensors take the bitmap-rank rulebook; it must give the hash rulebook's bits (indices, nbr, features)."""
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    import isfusion_b200.spconv as sp
+    torch.manual_seed(0)
+    cfg = dict(in_channels=64, sparse_shape=[41, 128, 128], base_channels=32, output_channels=256,
+               encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    mod = SparseEncoder(**cfg).cuda().eval()
+    x = _rand_tensor([41, 128, 128], 20000, 64, 2, 3, clustered=True)
+    key = so._lin(x.indices, x.spatial_shape)
+    order = torch.argsort(key)
+    f, c = torch.relu(x.features[order]).half().cuda(), x.indices[order].contiguous().cuda()
+    ref, rfe, _ = mod(f, c, 2, sorted_coors=False)
+    out, ofe, _ = mod(f, c, 2, sorted_coors=True)
+    torch.cuda.synchronize()
+    for a, b in zip(ofe, rfe):
+        assert torch.equal(a.indices, b.indices)
+    assert torch.equal(out, ref)
+    # oracle cross-check of one strided rulebook built by the bitmap path
+    xs = sp.SparseConvTensor(f, c, [41, 128, 128], 2)
+    xs.sorted = True
+    rb = sp.build_rulebook(xs, [3, 3, 3], [2, 2, 2], [1, 1, 1], [1, 1, 1], False)
+    oi, osz, nbr = so.get_indice_pairs(c.cpu(), 2, [41, 128, 128], 3, 2, 1, 1, False)
+    assert torch.equal(rb.out_indices.cpu(), oi) and torch.equal(rb.nbr[:, :rb.num_out].cpu().long(), nbr)
