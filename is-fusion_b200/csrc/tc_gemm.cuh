@@ -564,8 +564,11 @@ static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaSt
   }
   switch (::g_isf_gemm_cluster) {
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
-    default: return dispatch_gemm_cs<1>(p, bn, m_upper, st);
+    default: break;
   }
+  // measured: sharing the weight chunk in a CTA pair pays only for the 32-column tiles
+  if (bn == 32 && m_upper > 4 * BM) return dispatch_gemm_cs<2>(p, bn, m_upper, st);
+  return dispatch_gemm_cs<1>(p, bn, m_upper, st);
 }
 
 }  // namespace tc

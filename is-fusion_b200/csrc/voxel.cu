@@ -494,18 +494,20 @@ __global__ void __launch_bounds__(VFE_WARPS * 32) vfe_fused_kernel(
     const float* __restrict__ w2,  // [64][128]
     const float* __restrict__ s2, const float* __restrict__ b2,
     float* __restrict__ out_f32, __half* __restrict__ out_f16, int* __restrict__ out_coors) {
-  __shared__ float w1t[VFE_IN][VFE_C];
   __shared__ float w2t[2 * VFE_C][VFE_C];
-  __shared__ float hbuf[VFE_WARPS][VFE_C];
-  for (int t = threadIdx.x; t < VFE_IN * VFE_C; t += blockDim.x) w1t[t % VFE_IN][t / VFE_IN] = w1[t];
+  __shared__ __align__(16) float hbuf[VFE_WARPS][VFE_C][4];   // layer-1 activations of up to 4 points, [k][point]
   for (int t = threadIdx.x; t < 2 * VFE_C * VFE_C; t += blockDim.x)
     w2t[t % (2 * VFE_C)][t / (2 * VFE_C)] = w2[t];
-  __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // layer-1 weights of this lane's two output channels live in registers
+  float w1a[VFE_IN], w1b[VFE_IN];
+#pragma unroll
+  for (int k = 0; k < VFE_IN; ++k) { w1a[k] = w1[lane * VFE_IN + k]; w1b[k] = w1[(lane + 32) * VFE_IN + k]; }
+  __syncthreads();
   const int nv = *num_valid;
   const float s1a = s1[lane], s1b = s1[lane + 32], b1a = b1[lane], b1b = b1[lane + 32];
   const float s2a = s2[lane], s2b = s2[lane + 32], b2a = b2[lane], b2b = b2[lane + 32];
-  float* hb = hbuf[wid];
+  float (*hb)[4] = hbuf[wid];
   for (int v = blockIdx.x * VFE_WARPS + wid; v < nv; v += gridDim.x * VFE_WARPS) {
     const int s = start[v], m = cnt[v];
     int cc[4];
@@ -522,52 +524,60 @@ __global__ void __launch_bounds__(VFE_WARPS * 32) vfe_fused_kernel(
     const float ccx = __fadd_rn(__fmul_rn((float)cc[3], P.vx), P.xoff);
     const float ccy = __fadd_rn(__fmul_rn((float)cc[2], P.vy), P.yoff);
     const float ccz = __fadd_rn(__fmul_rn((float)cc[1], P.vz), P.zoff);
-    float vmaxa = 0.f, vmaxb = 0.f;  // post-ReLU values are >= 0 and every voxel has >= 1 point
-    for (int pass = 0; pass < 2; ++pass) {
-      float ga = 0.f, gb = 0.f;
-      if (pass == 1) {
-        // per-voxel half of layer 2: W2[:, 64:128] . vmax1
-        __syncwarp();
-        hb[lane] = vmaxa; hb[lane + 32] = vmaxb;
-        __syncwarp();
-#pragma unroll 8
-        for (int k = 0; k < VFE_C; ++k) {
-          float h = hb[k];
-          ga = fmaf(w2t[VFE_C + k][lane], h, ga);
-          gb = fmaf(w2t[VFE_C + k][lane + 32], h, gb);
-        }
-        vmaxa = 0.f; vmaxb = 0.f;
-      }
-      for (int j = 0; j < m; ++j) {
-        const float* p = points + (size_t)idx_sorted[s + j] * nfeat;
-        float f[VFE_IN];
-        f[0] = p[0]; f[1] = p[1]; f[2] = p[2]; f[3] = p[3]; f[4] = p[4];
-        f[5] = __fsub_rn(f[0], mx); f[6] = __fsub_rn(f[1], my); f[7] = __fsub_rn(f[2], mz);
-        f[8] = __fsub_rn(f[0], ccx); f[9] = __fsub_rn(f[1], ccy); f[10] = __fsub_rn(f[2], ccz);
-        float ha = 0.f, hc = 0.f;
+    auto layer1 = [&](int j, float& ha, float& hc) {
+      const float* p = points + (size_t)idx_sorted[s + j] * nfeat;
+      float f[VFE_IN];
+      f[0] = p[0]; f[1] = p[1]; f[2] = p[2]; f[3] = p[3]; f[4] = p[4];
+      f[5] = __fsub_rn(f[0], mx); f[6] = __fsub_rn(f[1], my); f[7] = __fsub_rn(f[2], mz);
+      f[8] = __fsub_rn(f[0], ccx); f[9] = __fsub_rn(f[1], ccy); f[10] = __fsub_rn(f[2], ccz);
+      ha = 0.f; hc = 0.f;
 #pragma unroll
-        for (int k = 0; k < VFE_IN; ++k) {
-          ha = fmaf(w1t[k][lane], f[k], ha);
-          hc = fmaf(w1t[k][lane + 32], f[k], hc);
-        }
-        ha = fmaxf(fmaf(ha, s1a, b1a), 0.f);
-        hc = fmaxf(fmaf(hc, s1b, b1b), 0.f);
-        if (pass == 0) {
-          vmaxa = fmaxf(vmaxa, ha); vmaxb = fmaxf(vmaxb, hc);
-        } else {
-          __syncwarp();
-          hb[lane] = ha; hb[lane + 32] = hc;
-          __syncwarp();
-          float oa = ga, ob = gb;
+      for (int k = 0; k < VFE_IN; ++k) { ha = fmaf(w1a[k], f[k], ha); hc = fmaf(w1b[k], f[k], hc); }
+      ha = fmaxf(fmaf(ha, s1a, b1a), 0.f);
+      hc = fmaxf(fmaf(hc, s1b, b1b), 0.f);
+    };
+    // pass 1: voxel max of the layer-1 activations (post-ReLU values are >= 0 and every voxel has >= 1 point)
+    float vmaxa = 0.f, vmaxb = 0.f;
+    for (int j = 0; j < m; ++j) {
+      float ha, hc;
+      layer1(j, ha, hc);
+      vmaxa = fmaxf(vmaxa, ha); vmaxb = fmaxf(vmaxb, hc);
+    }
+    // per-voxel half of layer 2: W2[:, 64:128] . vmax1
+    __syncwarp();
+    hb[lane][0] = vmaxa; hb[lane + 32][0] = vmaxb;
+    __syncwarp();
+    float ga = 0.f, gb = 0.f;
 #pragma unroll 8
-          for (int k = 0; k < VFE_C; ++k) {
-            float h = hb[k];
-            oa = fmaf(w2t[k][lane], h, oa);
-            ob = fmaf(w2t[k][lane + 32], h, ob);
-          }
-          oa = fmaxf(fmaf(oa, s2a, b2a), 0.f);
-          ob = fmaxf(fmaf(ob, s2b, b2b), 0.f);
-          vmaxa = fmaxf(vmaxa, oa); vmaxb = fmaxf(vmaxb, ob);
+    for (int k = 0; k < VFE_C; ++k) {
+      const float h = hb[k][0];
+      ga = fmaf(w2t[VFE_C + k][lane], h, ga);
+      gb = fmaf(w2t[VFE_C + k][lane + 32], h, gb);
+    }
+    // pass 2: per-point half of layer 2, four points per sweep over the weights
+    vmaxa = 0.f; vmaxb = 0.f;
+    for (int j0 = 0; j0 < m; j0 += 4) {
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float ha = 0.f, hc = 0.f;
+        if (j0 + q < m) layer1(j0 + q, ha, hc);
+        hb[lane][q] = ha; hb[lane + 32][q] = hc;
+      }
+      __syncwarp();
+      float oa[4] = {ga, ga, ga, ga}, ob[4] = {gb, gb, gb, gb};
+#pragma unroll 8
+      for (int k = 0; k < VFE_C; ++k) {
+        const float4 h = *(const float4*)hb[k];
+        const float wa = w2t[k][lane], wb = w2t[k][lane + 32];
+        oa[0] = fmaf(wa, h.x, oa[0]); oa[1] = fmaf(wa, h.y, oa[1]); oa[2] = fmaf(wa, h.z, oa[2]); oa[3] = fmaf(wa, h.w, oa[3]);
+        ob[0] = fmaf(wb, h.x, ob[0]); ob[1] = fmaf(wb, h.y, ob[1]); ob[2] = fmaf(wb, h.z, ob[2]); ob[3] = fmaf(wb, h.w, ob[3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (j0 + q < m) {
+          vmaxa = fmaxf(vmaxa, fmaxf(fmaf(oa[q], s2a, b2a), 0.f));
+          vmaxb = fmaxf(vmaxb, fmaxf(fmaf(ob[q], s2b, b2b), 0.f));
         }
       }
     }
