@@ -210,7 +210,9 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
   constexpr int SLICE_ROWS = BN / CS;
   constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space visible to the
+  // compiler: LDS/STS instead of generic LD/ST on every smem access)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = (uint64_t*)(smem + SL::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
@@ -262,11 +264,21 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
         for (int cs = 0; cs < CS; ++cs) {       // flags = union over the cluster's tiles (same chunk list everywhere)
           const long long prow = (long long)(grp * CS + cs) * BM + r;
           const bool pok = prow < m_total;
-          for (int t = thalf; t < p.taps; t += PRODUCERS / BM) {
-            const int v = pok ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
-            // staged as the BYTE offset of the neighbour's feature row (0xFFFFFFFF = none): one add per piece later
-            if (cs == crank) nbr_s[t * BM + r] = v >= 0 ? (int)((unsigned)v * (unsigned)(p.cin * 2)) : -1;
-            if (v >= 0) tap_flag[t] = 1;
+          // all neighbour loads of this row are issued before any is consumed (one exposed latency, not 14)
+          int nv[(MAX_TAPS + 1) / 2];
+#pragma unroll
+          for (int u = 0; u < (MAX_TAPS + 1) / 2; ++u) {
+            const int t = thalf + 2 * u;
+            nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < (MAX_TAPS + 1) / 2; ++u) {
+            const int t = thalf + 2 * u;
+            if (t < p.taps) {
+              // staged as the BYTE offset of the neighbour's feature row (0xFFFFFFFF = none): one add per piece later
+              if (cs == crank) nbr_s[t * BM + r] = nv[u] >= 0 ? (int)((unsigned)nv[u] * (unsigned)(p.cin * 2)) : -1;
+              if (nv[u] >= 0) tap_flag[t] = 1;
+            }
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
