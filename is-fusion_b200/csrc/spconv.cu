@@ -325,28 +325,29 @@ __global__ void __launch_bounds__(256) bitmap_set_kernel(const int* __restrict__
   atomicOr(&bits[key >> 5], 1u << (key & 31));
 }
 
+// one thread per input site: per axis the (at most ceil(k/s)) output coordinates it reaches, then their product
 __global__ void __launch_bounds__(256) bitmap_candidates_kernel(const int* __restrict__ indices, int v, const int* v_dev,
                                                                 ConvGeom g, unsigned int* __restrict__ bits) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)v * g.kvol;
-  if (t >= total) return;
-  int i = (int)(t / g.kvol), k = (int)(t % g.kvol);
-  if (v_dev && i >= *v_dev) return;
-  int kk[3];
-  kk[2] = k % g.ksize[2]; kk[1] = (k / g.ksize[2]) % g.ksize[1]; kk[0] = k / (g.ksize[2] * g.ksize[1]);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = v_dev ? *v_dev : v;
+  if (i >= n) return;
   const int* c = indices + (size_t)i * 4;
-  int o[3];
-  bool ok = true;
+  int cand[3][4], cnt[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    int num = c[1 + d] + g.pad[d] - kk[d] * g.dil[d];
-    int q = num / g.stride[d];
-    ok &= (num >= 0) && (q * g.stride[d] == num) && (q < g.out_shape[d]);
-    o[d] = q;
+    cnt[d] = 0;
+    for (int k = 0; k < g.ksize[d]; ++k) {
+      const int num = c[1 + d] + g.pad[d] - k * g.dil[d];
+      const int q = num / g.stride[d];
+      if (num >= 0 && q * g.stride[d] == num && q < g.out_shape[d] && cnt[d] < 4) cand[d][cnt[d]++] = q;
+    }
   }
-  if (!ok) return;
-  unsigned int key = lin_key(c[0], o[0], o[1], o[2], g.out_shape);
-  atomicOr(&bits[key >> 5], 1u << (key & 31));
+  for (int a = 0; a < cnt[0]; ++a)
+    for (int b = 0; b < cnt[1]; ++b)
+      for (int e = 0; e < cnt[2]; ++e) {
+        const unsigned int key = lin_key(c[0], cand[0][a], cand[1][b], cand[2][e], g.out_shape);
+        atomicOr(&bits[key >> 5], 1u << (key & 31));
+      }
 }
 
 __global__ void __launch_bounds__(256) bitmap_enumerate_kernel(const unsigned int* __restrict__ bits,
@@ -468,8 +469,8 @@ extern "C" int isf_bitmap_out_sites(const int* in_indices, int v_in, const int* 
   ISF_CUDA(cudaMemsetAsync(out_bits, 0, sizeof(unsigned int) * words, st));
   if (v_in > 0) {
     ISF_CHECK_ARG(in_indices && out_indices);
-    long long n = (long long)v_in * g.kvol;
-    bitmap_candidates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, out_bits);
+    for (int d = 0; d < 3; ++d) ISF_CHECK_ARG((ksize[d] + g.stride[d] - 1) / g.stride[d] <= 4);
+    bitmap_candidates_kernel<<<isf_cdiv(v_in, 256), 256, 0, st>>>(in_indices, v_in, v_in_dev, g, out_bits);
   }
   int rc = bitmap_scan(out_bits, out_prefix, words, workspace, ws_bytes, st);
   if (rc) return rc;

@@ -622,8 +622,14 @@ extern "C" int isf_dynamic_vfe_forward(const float* points, const int* coors, in
   int rc = group_by_key(G, n, L.total_bits, num_voxels_dev, st);
   if (rc) return rc;
   VfeParams P{voxel_size[0], voxel_size[1], voxel_size[2], offsets[0], offsets[1], offsets[2]};
+  // persistent warps: exactly one resident wave (a partial second wave would double the kernel time)
+  static int occ = 0;
+  if (!occ) {
+    ISF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfe_fused_kernel, VFE_WARPS * 32, 0));
+    if (occ < 1) occ = 1;
+  }
   int blocks = isf_cdiv(n, VFE_WARPS);
-  if (blocks > ISF_NUM_SMS * 4) blocks = ISF_NUM_SMS * 4;
+  if (blocks > ISF_NUM_SMS * occ) blocks = ISF_NUM_SMS * occ;
   vfe_fused_kernel<<<blocks, VFE_WARPS * 32, 0, st>>>(points, nfeat, G.idx_sorted, G.uniq, G.cnt, G.start,
                                                       G.num_valid, L, P, w1, scale1, shift1, w2, scale2, shift2,
                                                       voxel_feats_f32, (__half*)voxel_feats_f16, voxel_coors);
