@@ -46,8 +46,8 @@ def job_fps(world, batch, steps, ms):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--points', type=int, default=300000)
     ap.add_argument('--cloud', default='S', choices=['S', 'U'])
@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
@@ -291,12 +291,22 @@ def main():
     ms_eager /= max(3, args.steps // 4)
     log('eager (exact mode, host syncs, after capture): %.3f ms/step' % ms_eager)
     L.launch_count(reset=True)
-    ms = timed(step_resident, args.steps, args.warmup)
+    for attempt in range(3):
+        ms = timed(step_resident, args.steps, args.warmup)
+        over = gn.check()
+        log('graph replay: %.3f ms/step  overflow=%s' % (ms / args.steps, over))
+        # the decision is collective: every rank re-captures if any rank overflowed (keeps the barriers paired)
+        if max_over_ranks(1.0 if over else 0.0, world, dist, dev) == 0.0:
+            break
+        # a frame produced more strided-conv output sites than calibrated: grow the buffers and re-capture
+        caps = [int(c * 1.5) // 128 * 128 + 128 for c in caps]
+        gn = GraphedNeck(net, B, npts_cap, img_hw=(256, 704), calib=kw, capacities=caps, device=dev)
+        gn.load(dev_sets[0][0], dev_sets[0][1][1])
+        gn.capture()
+        log('re-captured with capacities %s' % caps)
+    else:
+        raise SystemExit('bench.py: strided-conv capacity overflow persists: %s' % over)
     sampler.stop_flag = True
-    over = gn.check()
-    log('graph replay: %.3f ms/step  overflow=%s' % (ms / args.steps, over))
-    if over:
-        raise SystemExit('bench.py: strided-conv capacity overflow %s (raise the calibration margin)' % over)
     L.launch_count(reset=True)
     prof = []
     spmod.PROFILE = prof

@@ -94,7 +94,15 @@ class SSTInputLayerV2(nn.Module):
             raise L.IsfError('SSTInputLayerV2: built for 6x6 windows, max_tokens >= 36 (isfusion_0075voxel.py:17-21)')
 
     def pos_table(self, device):
-        """[36, C] in-window sinusoid, slot = iy*6 + ix (sst_input_layer_v2.py:245-276)."""
+        """[36, C] in-window sinusoid, slot = iy*6 + ix (sst_input_layer_v2.py:245-276); input independent -> cached."""
+        cached = self.__dict__.get('_pos_cache')
+        if cached is not None and cached.device == device:
+            return cached
+        t = self._pos_table(device)
+        self.__dict__['_pos_cache'] = t
+        return t
+
+    def _pos_table(self, device):
         c = self.pos_embed_channels
         pos_length = c // 2
         inv = torch.arange(pos_length, dtype=torch.float32, device=device)
