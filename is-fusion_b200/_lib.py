@@ -67,8 +67,9 @@ _ws_cache = {}
 
 
 def workspace(nbytes, device):
-    """grow-only scratch buffer per device (owned by the torch caching allocator)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """grow-only scratch buffer per (device, stream): kernels on concurrent streams never share scratch memory."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)

@@ -54,7 +54,9 @@ class ISFusionDetector(nn.Module):
     def isfusion(self, pts, pts_feats, img_feats, img_metas, batch_size, nosync=False, **kwargs):
         """ref: isfusion.py:84-101."""
         with stage('a5 pillarize'):
-            if nosync:
+            if 'pts_metas' in kwargs:          # pillar branch already run on a side stream
+                pts_metas = kwargs.pop('pts_metas')
+            elif nosync:
                 pts_metas = dict(pillars_list=self.voxelize_nosync(pts), pts=pts, pillar_size=self.pillar_size)
             else:
                 pillars, pillars_num_points, pillar_coors = self.voxelize(pts, voxel_type='pillar')
@@ -81,20 +83,43 @@ class ISFusionDetector(nn.Module):
             out.append((voxels, coors, cnt))
         return out
 
+    def _streams(self, device):
+        st = self.__dict__.get('_side_streams')
+        if st is None:
+            st = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+            self.__dict__['_side_streams'] = st
+        return st
+
     @torch.no_grad()
-    def extract_pts_feat(self, pts, img_feats, img_metas, nosync=False, **kwargs):
+    def extract_pts_feat(self, pts, img_feats, img_metas, nosync=False, overlap=False, **kwargs):
         """ref: isfusion.py:103-121 without pts_neck; returns ([feat_0, feat_1], ins_heatmap).
         nosync=True keeps every data-dependent count on the device (capacity buffers): no host synchronisation
         anywhere in the path, which makes it CUDA-graph capturable (see GraphedNeck)."""
+        batch_size = len(pts)
+        rb_stream = None
+        if overlap and nosync:
+            # independent branches on side streams (captured as parallel branches of the CUDA graph):
+            #   pillar stream : pillarize -> camera->BEV      rulebook stream : all sparse-conv index work
+            main = torch.cuda.current_stream()
+            pillar_stream, rb_stream = self._streams(pts[0].device)
+            pillar_stream.wait_stream(main)
+            with torch.cuda.stream(pillar_stream):
+                pm = dict(pillars_list=self.voxelize_nosync(pts), pts=pts, pillar_size=self.pillar_size)
+                enc = self.fusion_encoder
+                cat = enc.new_fusion_buffer(batch_size, pts[0].device)
+                enc.img_fv_to_bev([img_feats[1]], batch_size, out=cat, pts_metas=pm, img_metas=img_metas, **kwargs)
+            kwargs['pts_metas'] = pm
+            kwargs['img_bev_buffer'] = cat
         with stage('a1 dynamic_voxelize'):
             voxels, coors = self.dynamic_voxelize(pts)
-        batch_size = len(pts)
         with stage('a3 dynamic_vfe'):
             r = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas, batch_size=batch_size, nosync=nosync)
         nv = r[2] if nosync else None
         with stage('a4 sparse_encoder'):
             x, _, kwargs = self.pts_middle_encoder(r[0], r[1], batch_size, dense=False, num_voxels_dev=nv,
-                                                   sorted_coors=True, **kwargs)
+                                                   sorted_coors=True, rulebook_stream=rb_stream, **kwargs)
+        if overlap and nosync:
+            torch.cuda.current_stream().wait_stream(self._streams(pts[0].device)[0])
         kwargs['lidar_sparse'] = self.pts_middle_encoder.last_out
         return self.isfusion(pts, x, img_feats, img_metas, batch_size, nosync=nosync, **kwargs)
 
@@ -111,9 +136,10 @@ class GraphedNeck:
     """
 
     def __init__(self, net, batch, num_points, img_hw=(256, 704), feat_hw=None, calib=None, capacities=None,
-                 device=None):
+                 device=None, overlap=True):
         import isfusion_b200.spconv as spmod
         self.net, self.batch, self.num_points = net, batch, num_points
+        self.overlap = overlap
         dev = device or next(net.parameters()).device
         self.dev = dev
         fh, fw = feat_hw or (img_hw[0] // 16, img_hw[1] // 16)
@@ -130,7 +156,8 @@ class GraphedNeck:
 
     def _run(self):
         feats = [self.img_feat[:0], self.img_feat, self.img_feat[:0]]
-        return self.net.extract_pts_feat(self.points, feats, self.metas, nosync=True, cam_proj=self.cam_proj)
+        return self.net.extract_pts_feat(self.points, feats, self.metas, nosync=True, overlap=self.overlap,
+                                         cam_proj=self.cam_proj)
 
     def load(self, points, img_feat1):
         for dst, src in zip(self.points, points):

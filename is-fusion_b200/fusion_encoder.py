@@ -491,6 +491,11 @@ class ISFusionEncoder(_Packable):
             self.__dict__['_pk'] = pk
         return self.__dict__['_pk']
 
+    def new_fusion_buffer(self, bs, device):
+        """zeroed channels-last [B,G,G,768] buffer: image BEV in channels 0..255, LiDAR BEV in 256..767."""
+        g = self.bev_size
+        return torch.zeros((bs, g, g, self.embed_dims * 3), dtype=torch.float16, device=device)
+
     # ------------------------------------------------------------------ a6: camera -> BEV
     def camera_projection(self, lidar2img, img_aug_matrix, lidar_aug_matrix, bs, device):
         """host-side 3x3 algebra of img_point_sampling (:976-1006) folded into 20 floats per (frame, camera):
@@ -595,9 +600,11 @@ class ISFusionEncoder(_Packable):
         dev = img_mlvl_feats[1].device
         pk = self._pack(dev)
         g = self.bev_size
-        with stage('a6 cam2bev'):
-            cat = torch.zeros((bs, g, g, self.embed_dims * 3), dtype=torch.float16, device=dev)
-            self.img_fv_to_bev([img_mlvl_feats[1]], bs, out=cat, **kwargs)
+        cat = kwargs.get('img_bev_buffer')      # camera->BEV already done on a side stream (detector fast path)
+        if cat is None:
+            with stage('a6 cam2bev'):
+                cat = self.new_fusion_buffer(bs, dev)
+                self.img_fv_to_bev([img_mlvl_feats[1]], bs, out=cat, **kwargs)
         sp = kwargs.get('lidar_sparse')
         if sp is not None:
             d = sp.spatial_shape[0]

@@ -132,13 +132,55 @@ class SparseEncoder(nn.Module):
             conv.out_capacity = r
 
     @torch.no_grad()
+    def prebuild_rulebooks(self, x):
+        """Build every rulebook of the encoder from the coordinates alone (they do not depend on features) and
+        return [(event, ...)] in execution order.  Called on a side stream so that the index work of all stages
+        overlaps the feature GEMMs; each rulebook is stored in the shared indice_dict under the key its conv will
+        look up, with a CUDA event the consumer waits on."""
+        events = []
+
+        def index_only(indices, shape, num_dev):
+            t = SparseConvTensor(None, indices, shape, x.batch_size, num_dev=num_dev)
+            t.indice_dict = x.indice_dict
+            t.sorted = x.sorted
+            return t
+
+        def build(conv, t):
+            rb = conv.rulebook(t)
+            ev = torch.cuda.Event()
+            ev.record()
+            x.indice_dict[('event', id(rb))] = ev
+            events.append(ev)
+            return rb
+
+        cur = index_only(x.indices, x.spatial_shape, x.num_dev)
+        build(self.conv_input[0], cur)
+        for stage in self.encoder_layers:
+            for blk in stage:
+                if isinstance(blk, SparseBasicBlock):
+                    build(blk.conv1, cur)
+                    build(blk.conv2, cur)
+                else:
+                    rb = build(blk[0], cur)
+                    cur = index_only(rb.out_indices, rb.out_shape, rb.num_dev)
+                    cur.sorted = True
+        build(self.conv_out[0], cur)
+        return events
+
+    @torch.no_grad()
     def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True,
-                num_voxels_dev=None, sorted_coors=False, **kwargs):
+                num_voxels_dev=None, sorted_coors=False, rulebook_stream=None, **kwargs):
         """voxel_features [V,C], coors [V,4] int32 (b,z,y,x) -> (spatial_features [B, C*D, H, W], encode_features, kwargs)"""
         coors = coors.int()
         feats = voxel_features if voxel_features.dtype == torch.float16 else voxel_features.half()
         x = SparseConvTensor(feats.contiguous(), coors.contiguous(), self.sparse_shape, batch_size, num_dev=num_voxels_dev)
         x.sorted = bool(sorted_coors)      # DynamicVFE output is in sorted-unique (b,z,y,x) order -> bitmap rulebooks
+        if rulebook_stream is not None:
+            # all index work on a side stream, overlapping the feature GEMMs of the main stream
+            main = torch.cuda.current_stream()
+            rulebook_stream.wait_stream(main)
+            with torch.cuda.stream(rulebook_stream):
+                self.prebuild_rulebooks(x)
         x = self.conv_input(x)
         encode_features = [x]
         for encoder_layer in self.encoder_layers:
@@ -147,6 +189,8 @@ class SparseEncoder(nn.Module):
         out = self.conv_out(encode_features[-1])
         self.last_out = out
         self.last_encode_features = encode_features
+        if rulebook_stream is not None:
+            torch.cuda.current_stream().wait_stream(rulebook_stream)
         if not dense:      # fast path: the fusion encoder scatters `out` straight into its channels-last buffer
             return None, encode_features, kwargs
         spatial_features = out.dense()

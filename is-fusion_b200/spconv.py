@@ -340,14 +340,23 @@ class SparseConvolution(SparseModule):
                    tuple(self.dilation), x.indices.data_ptr(), x.indices.shape[0])                # same rulebook
         rb = x.indice_dict.get(key)
         if rb is None:
-            rb = build_rulebook(x, self.kernel_size, self.stride, self.padding, self.dilation, self.subm,
-                                out_capacity=getattr(self, 'out_capacity', None))
+            # the same (coordinate set, geometry) under any indice_key is the same rulebook
+            geo = ('geo', self.subm, tuple(self.kernel_size), tuple(self.stride), tuple(self.padding),
+                   tuple(self.dilation), x.indices.data_ptr(), x.indices.shape[0])
+            rb = x.indice_dict.get(geo)
+            if rb is None:
+                rb = build_rulebook(x, self.kernel_size, self.stride, self.padding, self.dilation, self.subm,
+                                    out_capacity=getattr(self, 'out_capacity', None))
+                x.indice_dict[geo] = rb
             x.indice_dict[key] = rb
         return rb
 
     def forward(self, x, scale=None, shift=None, residual=None, relu=False):
         """conv (+ optional fused scale/shift/residual/ReLU epilogue used by the encoder's executor)."""
         rb = self.rulebook(x)
+        ev = x.indice_dict.get(('event', id(rb)))
+        if ev is not None:      # rulebook built on a side stream (SparseEncoder.prebuild_rulebooks)
+            torch.cuda.current_stream().wait_event(ev)
         feats = x.features if x.features.dtype == torch.float16 else x.features.half()
         if self.bias is not None:
             shift = self.bias.float() if shift is None else shift + self.bias.float() * (scale if scale is not None else 1)
