@@ -274,16 +274,23 @@ def main():
         return gn(pts, feats[1])            # D2D copy into the graph's static inputs + one graph replay
 
     out_host = None
+    e2e_state = {'ticket': None}
 
     def step_e2e(i):
+        """public pipelined API: pinned host frame i -> H2D -> graph replay -> D2H of both output maps.  The H2D of
+        frame i+1 and the D2H of frame i run on a copy stream and overlap the replays; every byte still moves
+        inside the timed region (it ends with a device synchronise)."""
         nonlocal out_host
-        pts, feats = host_sets[i % F_]
-        o, _ = gn(pts, feats[1])            # pinned host -> static device buffers (H2D), replay
         if out_host is None:
+            o, _ = gn.outputs
             out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in o]
-        for h, t in zip(out_host, o):
-            h.copy_(t, non_blocking=True)
-        return o
+        if e2e_state['ticket'] is None:
+            pts, feats = host_sets[i % F_]
+            e2e_state['ticket'] = gn.prefetch(pts, feats[1])
+        ticket = e2e_state['ticket']
+        pts, feats = host_sets[(i + 1) % F_]
+        e2e_state['ticket'] = gn.prefetch(pts, feats[1])      # next frame's H2D overlaps this replay
+        return gn.run_prefetched(ticket, out_host)
 
     sampler = ClockSampler(local)
     sampler.start()

@@ -192,6 +192,70 @@ class GraphedNeck:
         self.graph.replay()
         return self.outputs
 
+    # ---- pipelined host interface: H2D of frame i+1 and D2H of frame i overlap the replay of frame i / i+1 --------
+    def _pipe(self):
+        p = self.__dict__.get('_pipe_state')
+        if p is None:
+            dev = self.dev
+            p = dict(copy=torch.cuda.Stream(device=dev),
+                     pts=[[torch.empty_like(t) for t in self.points] for _ in range(2)],
+                     img=[torch.empty_like(self.img_feat) for _ in range(2)],
+                     n=[[0] * self.batch for _ in range(2)], ev_in=[torch.cuda.Event(), torch.cuda.Event()],
+                     ev_used=[None, None],
+                     out=None, out_host=None, ev_out=torch.cuda.Event(), ev_d2h=torch.cuda.Event(), slot=0, pending=None)
+            self.__dict__['_pipe_state'] = p
+        return p
+
+    def prefetch(self, points_host, img_feat1_host):
+        """start the H2D copy of the NEXT frame (pinned host tensors) on the copy stream; returns a ticket."""
+        p = self._pipe()
+        k = p['slot']
+        p['slot'] ^= 1
+        with torch.cuda.stream(p['copy']):
+            if p['ev_used'][k] is not None:
+                p['copy'].wait_event(p['ev_used'][k])     # the replay that read this staging set has consumed it
+            for b, src in enumerate(points_host):
+                n = src.shape[0]
+                if n > self.num_points:
+                    raise ValueError('frame has %d points, graph capacity is %d' % (n, self.num_points))
+                p['pts'][k][b][:n].copy_(src, non_blocking=True)
+                p['n'][k][b] = n
+            p['img'][k].copy_(img_feat1_host, non_blocking=True)
+            p['ev_in'][k].record()
+        return k
+
+    def run_prefetched(self, ticket, out_host=None):
+        """replay on the prefetched frame; the two output maps are copied to `out_host` (pinned) on the copy stream,
+        overlapping the next replay.  Returns the device outputs (valid until the next replay)."""
+        p = self._pipe()
+        main = torch.cuda.current_stream()
+        main.wait_event(p['ev_in'][ticket])
+        for b, dst in enumerate(self.points):           # staging -> the graph's static inputs (device-to-device)
+            n = p['n'][ticket][b]
+            dst[:n].copy_(p['pts'][ticket][b][:n], non_blocking=True)
+            if n < self.num_points:
+                dst[n:].fill_(1e6)
+        self.img_feat.copy_(p['img'][ticket], non_blocking=True)
+        if p['ev_used'][ticket] is None:
+            p['ev_used'][ticket] = torch.cuda.Event()
+        p['ev_used'][ticket].record()
+        self.graph.replay()
+        feats, _ = self.outputs
+        if out_host is not None:
+            if p['out'] is None:
+                p['out'] = [torch.empty_like(t) for t in feats]
+            else:
+                main.wait_event(p['ev_d2h'])            # the previous D2H has left the staging outputs
+            for d, t in zip(p['out'], feats):
+                d.copy_(t, non_blocking=True)
+            p['ev_out'].record()
+            with torch.cuda.stream(p['copy']):
+                p['copy'].wait_event(p['ev_out'])
+                for h, d in zip(out_host, p['out']):
+                    h.copy_(d, non_blocking=True)
+                p['ev_d2h'].record()
+        return self.outputs
+
     def check(self):
         """[(count, capacity)] of strided convs whose output buffer overflowed in the last replay (host sync)."""
         return [(int(c.item()), cap) for c, cap in self.watch if int(c.item()) >= cap]

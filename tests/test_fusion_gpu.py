@@ -247,3 +247,17 @@ def test_sync_free_and_graph_paths_match_exact_path():
     ef2, _ = net(pts2, feats, metas, **kw)
     for a, b in zip(ef2, gf2):
         assert torch.equal(a, b)
+
+    # pipelined host interface (H2D / D2H on a copy stream) returns the same bits
+    hp = [[p.cpu().pin_memory() for p in pts], [p.cpu().pin_memory() for p in pts2]]
+    hf = feats[1].cpu().pin_memory()
+    oh = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in ef] for _ in range(2)]
+    t0 = gn.prefetch(hp[0], hf)
+    t1 = gn.prefetch(hp[1], hf)
+    gn.run_prefetched(t0, oh[0])
+    gn.run_prefetched(t1, oh[1])
+    torch.cuda.synchronize()
+    for a, b in zip(ef, oh[0]):
+        assert torch.equal(a.cpu(), b)
+    for a, b in zip(ef2, oh[1]):
+        assert torch.equal(a.cpu(), b)
