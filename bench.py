@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--points', type=int, default=300000)
     ap.add_argument('--cloud', default='S', choices=['S', 'U'])
+    ap.add_argument('--img', default='384x1056', help='network input size of the 6 cameras (config img_scale; 256x704 = BASELINE configs[0])')
     ap.add_argument('--batch', type=int, default=1, help='frames per step per GPU')
     ap.add_argument('--frames', type=int, default=16, help='distinct resident frames rotated through (L2 defeat)')
     ap.add_argument('--cpu-points', type=int, default=0, help='points of the CPU-baseline sample frame (0 = same as --points)')
@@ -124,7 +125,12 @@ def host_threads():
     return max(1, min(n, 64))
 
 
-def oracle_fps(points, cloud, steps, warmup, threads=None):
+def img_hw_of(args):
+    h, w = args.img.lower().split('x')
+    return (int(h), int(w))
+
+
+def oracle_fps(points, cloud, steps, warmup, threads=None, img_hw=(384, 1056)):
     """CPU arm: the oracle neck forward on the host cores."""
     import torch
     import synth
@@ -133,9 +139,9 @@ def oracle_fps(points, cloud, steps, warmup, threads=None):
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     net = synth.randomize_bn(omodel.ISFusionNeck(shuffle_voxels=True)).eval()
-    l2i, aug, laug = synth.make_calib(1)
-    feats = synth.make_img_feats(1)
-    metas = [dict(input_shape=(256, 704))]
+    l2i, aug, laug = synth.make_calib(1, img_hw)
+    feats = synth.make_img_feats(1, img_hw)
+    metas = [dict(input_shape=img_hw)]
     times, stages = [], {}
     for i in range(warmup + steps):
         pts = [synth.make_points(points if i >= warmup else 5000, cloud, i)]      # warm-up on a small frame
@@ -155,7 +161,7 @@ def cpu_baseline_subprocess(args, deadline=200):
     """the CPU arm in a child process with a hard deadline (a mis-sized OpenMP pool must not stall the bench)."""
     for pts_n in [args.cpu_points or args.points, 20000]:
         cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '1', '--warmup', '1',
-               '--points', str(args.points), '--cpu-points', str(pts_n), '--cloud', args.cloud]
+               '--points', str(args.points), '--cpu-points', str(pts_n), '--cloud', args.cloud, '--img', args.img]
         try:
             env = dict(os.environ)
             for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
@@ -175,15 +181,15 @@ def run_reference(args):
     steps = max(1, min(args.steps, 2))
     warm = 1 if args.warmup > 0 else 0
     cpu_points = args.cpu_points or args.points
-    fps, threads, stages = oracle_fps(cpu_points, args.cloud, steps, warm)
-    sample = ('%d frame(s) of %d %s-cloud points + 6x256x704 cameras through the CPU oracle (1 warm-up on a 5k-point frame); '
+    fps, threads, stages = oracle_fps(cpu_points, args.cloud, steps, warm, img_hw=img_hw_of(args))
+    sample = ('%d frame(s) of %d %s-cloud points + 6 cameras through the CPU oracle (1 warm-up on a 5k-point frame); '
               '%s (B200 arm: %d points)' % (steps, cpu_points, args.cloud,
                                             'same workload' if cpu_points == args.points else 'smaller bounded sample', args.points))
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': 1000.0 / fps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'isfusion_0075voxel fusion-neck forward, CPU oracle (restated reference)', 'points': cpu_points,
-                       'cloud': args.cloud, 'cams': 6, 'img': [256, 704], 'batch': 1},
+                       'cloud': args.cloud, 'cams': 6, 'img': list(img_hw_of(args)), 'batch': 1},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                              'stage_seconds': stages},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -212,15 +218,16 @@ def main():
     _, net = make_pair(0)
     net = net.to(dev).eval()
     B, F_ = args.batch, args.frames
-    metas = [dict(input_shape=(256, 704))] * B
+    IMG = img_hw_of(args)
+    metas = [dict(input_shape=IMG)] * B
     # resident inputs: F distinct frames per rank, rotated so that consecutive steps never reuse L2-resident inputs
     host_sets = []
     for f in range(F_):
         seed = frame_seed(rank, f)
         pts = [synth.make_points(args.points, args.cloud, seed * 8 + b).pin_memory() for b in range(B)]
-        feats = [t.pin_memory() for t in synth.make_img_feats(B, seed=seed)]
+        feats = [t.pin_memory() for t in synth.make_img_feats(B, IMG, seed=seed)]
         host_sets.append((pts, feats))
-    l2i, aug, laug = synth.make_calib(B)
+    l2i, aug, laug = synth.make_calib(B, IMG)
     kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
     dev_sets = [([p.to(dev) for p in pts], [t.to(dev) for t in feats]) for pts, feats in host_sets]
     in_bytes = sum(p.numel() * 4 for p in host_sets[0][0]) + host_sets[0][1][1].numel() * 4
@@ -258,7 +265,7 @@ def main():
     log('calibrating buffer capacities on 2 frames (exact mode)')
     caps = GraphedNeck.calibrate(net, [dev_sets[0][0], dev_sets[1 % F_][0]], dev_sets[0][1], metas, margin=1.35, **kw)
     npts_cap = max(p.shape[0] for pts, _ in host_sets for p in pts)
-    gn = GraphedNeck(net, B, npts_cap, img_hw=(256, 704), calib=kw, capacities=caps, device=dev)
+    gn = GraphedNeck(net, B, npts_cap, img_hw=IMG, calib=kw, capacities=caps, device=dev)
     t_pre = timed(step_eager_pre, 5, 2) / 5
     log('eager before capture: %.3f ms/step' % t_pre)
     gn.load(dev_sets[0][0], dev_sets[0][1][1])
@@ -307,7 +314,7 @@ def main():
             break
         # a frame produced more strided-conv output sites than calibrated: grow the buffers and re-capture
         caps = [int(c * 1.5) // 128 * 128 + 128 for c in caps]
-        gn = GraphedNeck(net, B, npts_cap, img_hw=(256, 704), calib=kw, capacities=caps, device=dev)
+        gn = GraphedNeck(net, B, npts_cap, img_hw=IMG, calib=kw, capacities=caps, device=dev)
         gn.load(dev_sets[0][0], dev_sets[0][1][1])
         gn.capture()
         log('re-captured with capacities %s' % caps)
@@ -368,7 +375,7 @@ def main():
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
                 'data': 'synthetic',
                 'config': {'workload': 'BASELINE configs[1]: isfusion_0075voxel.py fusion-neck forward, synthetic nuScenes-shaped frame',
-                           'points_per_frame': args.points, 'cloud': args.cloud, 'cams': 6, 'img': [256, 704], 'bev': 180,
+                           'points_per_frame': args.points, 'cloud': args.cloud, 'cams': 6, 'img': list(IMG), 'bev': 180,
                            'batch_per_gpu': B, 'parallelism': 'dp%d (independent replicas, no data-path collective)' % world,
                            'l2': 'rotating %d distinct resident frames (%.0f MB of inputs) > 126 MB L2' % (F_, F_ * in_bytes / 1e6)},
                 'clocks': sampler.summary(),
