@@ -122,36 +122,60 @@ extern "C" int isf_cam2bev(const float* pillars, int num_pillars, const int* num
 }
 
 // ================================================================================================
+// tensor-core helpers for the two IGF attention cores (mma.sync m16n8k16: 36..200-key tiles are far below a
+// tcgen05 M=128 atom; SURVEY §7 "hard parts": documented choice)
+// ================================================================================================
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+  __half2 h = __floats2half2_rn(x, y);
+  return *(uint32_t*)&h;
+}
+__device__ __forceinline__ uint32_t pack_2h(__half lo, __half hi) {
+  return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
+}
+
+// ================================================================================================
 // SST window attention core
 // ================================================================================================
 // qkv [B*S*S, 3C] fp16 (in_proj output incl. bias, no positional term), pos_q/pos_k [36, C] fp32
 // (= Wq.pos / Wk.pos of the in-window sinusoid, precomputed), out [B*S*S, C] fp16.
-// One CTA per window (b, wy, wx) of the partition with shift s (6 = aligned, 3 = shifted by half a window);
-// thread = (head, query slot).  Keys outside the grid are masked (key_padding_mask of the reference).
+// One CTA per window (b, wy, wx) of the partition with shift s (6 = aligned, 3 = shifted by half a window), one warp
+// per head: S = QK^T (48x40 padded) and PV on mma.sync.m16n8k16, fp32 softmax in the accumulator registers
+// (quad shuffles), K(+pos) and V of the window in smem with a conflict-free pitch.  Keys outside the grid are masked
+// (the key_padding_mask of the reference); query rows outside the grid are never stored.
 template <int C, int HEADS>
-__global__ void __launch_bounds__(HEADS * 36) window_attention_kernel(const __half* __restrict__ qkv,
+__global__ void __launch_bounds__(HEADS * 32) window_attention_kernel(const __half* __restrict__ qkv,
                                                                       const float* __restrict__ pos_q,
                                                                       const float* __restrict__ pos_k, int S, int shift,
                                                                       int nwin, float scaling, __half* __restrict__ out) {
-  constexpr int D = C / HEADS;
-  constexpr int WIN = 6, TOK = 36;
-  __shared__ __half ks[TOK][C];
-  __shared__ __half vs[TOK][C];
-  __shared__ int tok_id[TOK];
+  constexpr int D = C / HEADS;              // 16 or 32
+  constexpr int WIN = 6, TOK = 36, TOKP = 48;
+  constexpr int PITCH = C + 8;              // halfs; (C+8)/2 words = 4 mod 32
+  constexpr int KS = D / 16, NV = D / 8;
+  __shared__ __align__(16) __half ks[40][PITCH];       // keys: 5 n-tiles of 8
+  __shared__ __align__(16) __half vs[TOKP][PITCH];     // values: 3 k-steps of 16 (rows >= 36 are zero)
+  __shared__ int tok_id[TOKP];
   const int w = blockIdx.x;
   const int b = w / (nwin * nwin);
   const int wy = (w / nwin) % nwin, wx = w % nwin;
-  // aligned partition: window origin = w*6; shifted: origin = w*6 - 3
   const int oy = wy * WIN - (shift == 3 ? 3 : 0), ox = wx * WIN - (shift == 3 ? 3 : 0);
   const int tid = threadIdx.x;
-  if (tid < TOK) {
-    const int iy = tid / WIN, ix = tid % WIN;
-    const int y = oy + iy, x = ox + ix;
-    tok_id[tid] = (y >= 0 && y < S && x >= 0 && x < S) ? (b * S + y) * S + x : -1;
+  if (tid < TOKP) {
+    int t = -1;
+    if (tid < TOK) {
+      const int iy = tid / WIN, ix = tid % WIN;
+      const int y = oy + iy, x = ox + ix;
+      if (y >= 0 && y < S && x >= 0 && x < S) t = (b * S + y) * S + x;
+    }
+    tok_id[tid] = t;
   }
   __syncthreads();
-  // cooperative load of K (+pos) and V
-  for (int e = tid; e < TOK * (C / 8); e += blockDim.x) {
+  for (int e = tid; e < TOKP * (C / 8); e += blockDim.x) {
     const int slot = e / (C / 8), c8 = (e % (C / 8)) * 8;
     const int t = tok_id[slot];
     uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
@@ -168,54 +192,98 @@ __global__ void __launch_bounds__(HEADS * 36) window_attention_kernel(const __ha
         k2[i] = __floats2half2_rn(f.x, f.y);
       }
     }
-    *(uint4*)&ks[slot][c8] = kk;
+    if (slot < 40) *(uint4*)&ks[slot][c8] = kk;
     *(uint4*)&vs[slot][c8] = vv;
   }
   __syncthreads();
-  const int h = tid / TOK, qs = tid % TOK;
-  const int tq = tok_id[qs];
-  if (tq < 0) return;
-  float q[D];
-  {
-    const __half* row = qkv + (size_t)tq * 3 * C + h * D;
+  const int h = tid >> 5, lane = tid & 31;
+  const int gr = lane >> 2, gc = (lane & 3) * 2;
+  const float sl2 = scaling * 1.44269504088896f;
+#pragma unroll 1
+  for (int mt = 0; mt < 3; ++mt) {
+    const int s0 = mt * 16 + gr, s1 = s0 + 8;          // query slots of this thread's two rows
+    const int t0 = tok_id[s0], t1 = tok_id[s1];
+    if (__all_sync(0xffffffffu, t0 < 0 && t1 < 0)) continue;
+    uint32_t qa[KS][4];
 #pragma unroll
-    for (int i = 0; i < D; ++i) q[i] = (__half2float(row[i]) + pos_q[qs * C + h * D + i]) * scaling;
-  }
-  float sc[TOK];
-  float mx = -INFINITY;
+    for (int kt = 0; kt < KS; ++kt) {
 #pragma unroll
-  for (int j = 0; j < TOK; ++j) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < D; i += 2) {
-      const float2 kf = __half22float2(*(const __half2*)&ks[j][h * D + i]);
-      s = fmaf(q[i], kf.x, s);
-      s = fmaf(q[i + 1], kf.y, s);
+      for (int part = 0; part < 4; ++part) {
+        const int slot = (part & 1) ? s1 : s0, tk = (part & 1) ? t1 : t0;
+        const int col = h * D + kt * 16 + gc + (part >> 1) * 8;
+        float2 f = make_float2(0.f, 0.f);
+        if (tk >= 0) {
+          f = __half22float2(*(const __half2*)(qkv + (size_t)tk * 3 * C + col));
+          f.x += pos_q[slot * C + col];
+          f.y += pos_q[slot * C + col + 1];
+        }
+        qa[kt][part] = pack_h2(f.x, f.y);
+      }
     }
-    s = tok_id[j] >= 0 ? s : -INFINITY;
-    sc[j] = s;
-    mx = fmaxf(mx, s);
-  }
-  float sum = 0.f;
+    float sc[5][4];
 #pragma unroll
-  for (int j = 0; j < TOK; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
-  const float inv = 1.f / sum;
-  float o[D];
+    for (int nt = 0; nt < 5; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
 #pragma unroll
-  for (int i = 0; i < D; ++i) o[i] = 0.f;
+      for (int kt = 0; kt < KS; ++kt) {
+        const __half* kr = &ks[nt * 8 + gr][h * D + kt * 16 + gc];
+        mma16816(sc[nt], qa[kt], *(const uint32_t*)kr, *(const uint32_t*)(kr + 8));
+      }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < TOK; ++j) {
-    const float pj = sc[j] * inv;
+    for (int nt = 0; nt < 5; ++nt) {
 #pragma unroll
-    for (int i = 0; i < D; i += 2) {
-      const float2 vf = __half22float2(*(const __half2*)&vs[j][h * D + i]);
-      o[i] = fmaf(pj, vf.x, o[i]);
-      o[i + 1] = fmaf(pj, vf.y, o[i + 1]);
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + gc + (e & 1);
+        const bool ok = key < TOK && tok_id[key] >= 0;
+        sc[nt][e] = ok ? sc[nt][e] * sl2 : -INFINITY;
+      }
+      m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    float pe[6][4];                                        // probabilities, keys padded to 48 (3 k-steps of 16)
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      if (nt < 5) {
+        pe[nt][0] = exp2f(sc[nt][0] - m0); pe[nt][1] = exp2f(sc[nt][1] - m0);
+        pe[nt][2] = exp2f(sc[nt][2] - m1); pe[nt][3] = exp2f(sc[nt][3] - m1);
+        l0 += pe[nt][0] + pe[nt][1];
+        l1 += pe[nt][2] + pe[nt][3];
+      } else {
+        pe[nt][0] = pe[nt][1] = pe[nt][2] = pe[nt][3] = 0.f;
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[NV][4];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(pe[2 * kt][0], pe[2 * kt][1]);
+      pa[1] = pack_h2(pe[2 * kt][2], pe[2 * kt][3]);
+      pa[2] = pack_h2(pe[2 * kt + 1][0], pe[2 * kt + 1][1]);
+      pa[3] = pack_h2(pe[2 * kt + 1][2], pe[2 * kt + 1][3]);
+      const __half* vr = &vs[kt * 16 + gc][h * D + gr];       // B[k = key][n = dv] = V[key][dv]
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const uint32_t b0 = pack_2h(vr[n * 8], vr[PITCH + n * 8]);
+        const uint32_t b1 = pack_2h(vr[8 * PITCH + n * 8], vr[9 * PITCH + n * 8]);
+        mma16816(o[n], pa, b0, b1);
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+      if (t0 >= 0) *(__half2*)(out + (size_t)t0 * C + h * D + n * 8 + gc) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
+      if (t1 >= 0) *(__half2*)(out + (size_t)t1 * C + h * D + n * 8 + gc) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
     }
   }
-  __half* orow = out + (size_t)tq * C + h * D;
-#pragma unroll
-  for (int i = 0; i < D; i += 2) *(__half2*)(orow + i) = __floats2half2_rn(o[i], o[i + 1]);
 }
 
 extern "C" int isf_window_attention(const void* qkv, const float* pos_q, const float* pos_k, int batch, int grid,
@@ -226,10 +294,10 @@ extern "C" int isf_window_attention(const void* qkv, const float* pos_q, const f
   const int blocks = batch * nwin * nwin;
   cudaStream_t st = (cudaStream_t)stream;
   if (channels == 128) {
-    window_attention_kernel<128, 8><<<blocks, 288, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+    window_attention_kernel<128, 8><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
                                                              1.0f / sqrtf(16.f), (__half*)out);
   } else if (channels == 256) {
-    window_attention_kernel<256, 8><<<blocks, 288, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+    window_attention_kernel<256, 8><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
                                                              1.0f / sqrtf(32.f), (__half*)out);
   } else {
     isf_set_error("window_attention: channels must be 128 or 256");
@@ -396,24 +464,6 @@ extern "C" int isf_ms_deform_attn_forward(const void* value, int value_is_half, 
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
-}
-
-// ================================================================================================
-// tensor-core helpers for the two IGF attention cores (mma.sync m16n8k16: 36..200-key tiles are far below a
-// tcgen05 M=128 atom; SURVEY §7 "hard parts": documented choice)
-// ================================================================================================
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
-  __half2 h = __floats2half2_rn(x, y);
-  return *(uint32_t*)&h;
-}
-__device__ __forceinline__ uint32_t pack_2h(__half lo, __half hi) {
-  return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
 }
 
 // ================================================================================================
