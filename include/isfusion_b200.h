@@ -51,6 +51,17 @@ int isf_set_option(const char* name, int value);
 int isf_dynamic_voxelize(const float* points, int n, int nfeat, const float* voxel_size,
                          const float* coors_range, int* coors, int cpu_semantics, void* stream);
 
+/* the same op in two calls: `group` (sort + run-length encode + voxel coordinates + count) then `compute` (the
+ * fused feature kernel on the grouping left in the same workspace, same stream, same n/dims).  The coordinates
+ * - all the sparse-conv rulebooks need - are thus available before the feature kernel has run. */
+int isf_dynamic_vfe_group(const int* coors, int n, const int* dims, int* voxel_coors, int* num_voxels_dev,
+                          void* workspace, size_t ws_bytes, void* stream);
+int isf_dynamic_vfe_compute(const float* points, int n, int nfeat, const int* dims, const float* voxel_size,
+                            const float* offsets, const float* w1, const float* scale1, const float* shift1,
+                            const float* w2, const float* scale2, const float* shift2, int in_ch, int feat_ch,
+                            float* voxel_feats_f32, void* voxel_feats_f16, void* workspace, size_t ws_bytes,
+                            void* stream);
+
 /* ---- a2: dynamic scatter (per-voxel mean / max / sum) -------------------------
  * replaces voxel_layer.dynamic_point_to_voxel_forward(feats, coors, reduce_type)
  *   mmdet3d/ops/voxel/src/voxelization.h:108-120, scatter_points_cuda.cu:183-239.

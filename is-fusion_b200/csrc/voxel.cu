@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(VFE_WARPS * 32) vfe_fused_kernel(
       out_f16[(size_t)v * VFE_C + lane] = __float2half_rn(vmaxa);
       out_f16[(size_t)v * VFE_C + lane + 32] = __float2half_rn(vmaxb);
     }
-    if (lane < 4) out_coors[(size_t)v * 4 + lane] = cc[lane];
+    if (out_coors && lane < 4) out_coors[(size_t)v * 4 + lane] = cc[lane];
   }
 }
 
@@ -634,6 +634,75 @@ extern "C" int isf_dynamic_vfe_forward(const float* points, const int* coors, in
                                                       G.num_valid, L, P, w1, scale1, shift1, w2, scale2, shift2,
                                                       voxel_feats_f32, (__half*)voxel_feats_f16, voxel_coors);
   isf_count_launch(2);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a3 split in two calls so that the voxel COORDINATES (all the sparse-conv rulebooks need) are available before
+// the feature kernel has run: group (sort + run-length encode + coordinates + count), then compute (fused VFE on
+// the grouping left in the same workspace).  isf_dynamic_vfe_forward == group + compute.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxel_coors_kernel(const unsigned long long* __restrict__ uniq,
+                                                          const int* __restrict__ num_valid, KeyLayout L, int n,
+                                                          int* __restrict__ out_coors) {
+  const int nv = *num_valid;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    int cc[4];
+    unpack_key(uniq[v], L, cc);
+    *(int4*)(out_coors + (size_t)v * 4) = make_int4(cc[0], cc[1], cc[2], cc[3]);
+  }
+}
+
+extern "C" int isf_dynamic_vfe_group(const int* coors, int n, const int* dims, int* voxel_coors, int* num_voxels_dev,
+                                     void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(n >= 0 && dims && num_voxels_dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { ISF_CUDA(cudaMemsetAsync(num_voxels_dev, 0, sizeof(int), st)); return ISF_OK; }
+  ISF_CHECK_ARG(coors && voxel_coors && workspace);
+  IsfArena A(workspace, ws_bytes);
+  GroupBuffers G;
+  group_carve(A, n, &G);
+  if (!A.ok) { isf_set_error("dynamic_vfe_group: workspace too small"); return ISF_ERR_WORKSPACE; }
+  KeyLayout L = make_layout(4, dims);
+  make_keys_kernel<<<isf_cdiv(n, 256), 256, 0, st>>>(coors, n, L, G.keys, G.idx);
+  int rc = group_by_key(G, n, L.total_bits, num_voxels_dev, st);
+  if (rc) return rc;
+  int blocks = isf_cdiv(n, 256);
+  if (blocks > ISF_NUM_SMS * 8) blocks = ISF_NUM_SMS * 8;
+  voxel_coors_kernel<<<blocks, 256, 0, st>>>(G.uniq, G.num_valid, L, n, voxel_coors);
+  isf_count_launch(2);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// must follow isf_dynamic_vfe_group on the same stream with the same (n, dims, workspace)
+extern "C" int isf_dynamic_vfe_compute(const float* points, int n, int nfeat, const int* dims, const float* voxel_size,
+                                       const float* offsets, const float* w1, const float* scale1, const float* shift1,
+                                       const float* w2, const float* scale2, const float* shift2, int in_ch, int feat_ch,
+                                       float* voxel_feats_f32, void* voxel_feats_f16, void* workspace, size_t ws_bytes,
+                                       void* stream) {
+  ISF_CHECK_ARG(n >= 0 && nfeat >= 5 && dims && voxel_size && offsets);
+  if (in_ch != VFE_IN || feat_ch != VFE_C) { isf_set_error("dynamic_vfe: only in=11, feat=(64,64) is built"); return ISF_ERR_UNSUPPORTED; }
+  if (n == 0) return ISF_OK;
+  ISF_CHECK_ARG(points && w1 && scale1 && shift1 && w2 && scale2 && shift2 && workspace && (voxel_feats_f32 || voxel_feats_f16));
+  IsfArena A(workspace, ws_bytes);
+  GroupBuffers G;
+  group_carve(A, n, &G);
+  if (!A.ok) { isf_set_error("dynamic_vfe_compute: workspace too small"); return ISF_ERR_WORKSPACE; }
+  KeyLayout L = make_layout(4, dims);
+  VfeParams P{voxel_size[0], voxel_size[1], voxel_size[2], offsets[0], offsets[1], offsets[2]};
+  static int occ = 0;
+  if (!occ) {
+    ISF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfe_fused_kernel, VFE_WARPS * 32, 0));
+    if (occ < 1) occ = 1;
+  }
+  int blocks = isf_cdiv(n, VFE_WARPS);
+  if (blocks > ISF_NUM_SMS * occ) blocks = ISF_NUM_SMS * occ;
+  vfe_fused_kernel<<<blocks, VFE_WARPS * 32, 0, (cudaStream_t)stream>>>(points, nfeat, G.idx_sorted, G.uniq, G.cnt, G.start,
+                                                                      G.num_valid, L, P, w1, scale1, shift1, w2, scale2, shift2,
+                                                                      voxel_feats_f32, (__half*)voxel_feats_f16, nullptr);
+  isf_count_launch(1);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
 }

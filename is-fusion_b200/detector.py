@@ -112,12 +112,22 @@ class ISFusionDetector(nn.Module):
             kwargs['img_bev_buffer'] = cat
         with stage('a1 dynamic_voxelize'):
             voxels, coors = self.dynamic_voxelize(pts)
-        with stage('a3 dynamic_vfe'):
-            r = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas, batch_size=batch_size, nosync=nosync)
-        nv = r[2] if nosync else None
-        with stage('a4 sparse_encoder'):
-            x, _, kwargs = self.pts_middle_encoder(r[0], r[1], batch_size, dense=False, num_voxels_dev=nv,
-                                                   sorted_coors=True, rulebook_stream=rb_stream, **kwargs)
+        if overlap and nosync:
+            # coordinates first: the rulebook stream starts on them while the VFE feature kernel runs
+            vfe, enc3d = self.pts_voxel_encoder, self.pts_middle_encoder
+            with stage('a3 dynamic_vfe'):
+                vcoors, nv, ws = vfe.group(voxels, coors, batch_size)
+                pre = enc3d.start_rulebooks(vcoors, batch_size, nv, rb_stream)
+                vfeats = vfe.compute(voxels, batch_size, ws)
+            with stage('a4 sparse_encoder'):
+                x, _, kwargs = enc3d(vfeats, vcoors, batch_size, dense=False, prebuilt=pre, **kwargs)
+        else:
+            with stage('a3 dynamic_vfe'):
+                r = self.pts_voxel_encoder(voxels, coors, pts, img_feats, img_metas, batch_size=batch_size, nosync=nosync)
+            nv = r[2] if nosync else None
+            with stage('a4 sparse_encoder'):
+                x, _, kwargs = self.pts_middle_encoder(r[0], r[1], batch_size, dense=False, num_voxels_dev=nv,
+                                                       sorted_coors=True, **kwargs)
         if overlap and nosync:
             torch.cuda.current_stream().wait_stream(self._streams(pts[0].device)[0])
         kwargs['lidar_sparse'] = self.pts_middle_encoder.last_out

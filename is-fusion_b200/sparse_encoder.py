@@ -132,6 +132,18 @@ class SparseEncoder(nn.Module):
             conv.out_capacity = r
 
     @torch.no_grad()
+    def start_rulebooks(self, coors, batch_size, num_voxels_dev, stream, sorted_coors=True):
+        """kick off every rulebook on `stream` as soon as the voxel coordinates exist (before the features do);
+        returns the feature-less tensor to pass to forward(prebuilt=...)."""
+        x = SparseConvTensor(None, coors.contiguous(), self.sparse_shape, batch_size, num_dev=num_voxels_dev)
+        x.sorted = bool(sorted_coors)
+        x.__dict__['_rb_stream'] = stream
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            self.prebuild_rulebooks(x)
+        return x
+
+    @torch.no_grad()
     def prebuild_rulebooks(self, x):
         """Build every rulebook of the encoder from the coordinates alone (they do not depend on features) and
         return [(event, ...)] in execution order.  Called on a side stream so that the index work of all stages
@@ -169,13 +181,19 @@ class SparseEncoder(nn.Module):
 
     @torch.no_grad()
     def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True,
-                num_voxels_dev=None, sorted_coors=False, rulebook_stream=None, **kwargs):
+                num_voxels_dev=None, sorted_coors=False, rulebook_stream=None, prebuilt=None, **kwargs):
         """voxel_features [V,C], coors [V,4] int32 (b,z,y,x) -> (spatial_features [B, C*D, H, W], encode_features, kwargs)"""
         coors = coors.int()
         feats = voxel_features if voxel_features.dtype == torch.float16 else voxel_features.half()
-        x = SparseConvTensor(feats.contiguous(), coors.contiguous(), self.sparse_shape, batch_size, num_dev=num_voxels_dev)
-        x.sorted = bool(sorted_coors)      # DynamicVFE output is in sorted-unique (b,z,y,x) order -> bitmap rulebooks
-        if rulebook_stream is not None:
+        if prebuilt is not None:           # tensor whose rulebooks were started early (start_rulebooks); add the features
+            x = prebuilt
+            x.features = feats.contiguous()
+            rulebook_stream_join = x.__dict__.get('_rb_stream')
+        else:
+            rulebook_stream_join = None
+            x = SparseConvTensor(feats.contiguous(), coors.contiguous(), self.sparse_shape, batch_size, num_dev=num_voxels_dev)
+            x.sorted = bool(sorted_coors)  # DynamicVFE output is in sorted-unique (b,z,y,x) order -> bitmap rulebooks
+        if prebuilt is None and rulebook_stream is not None:
             # all index work on a side stream, overlapping the feature GEMMs of the main stream
             main = torch.cuda.current_stream()
             rulebook_stream.wait_stream(main)
@@ -189,7 +207,9 @@ class SparseEncoder(nn.Module):
         out = self.conv_out(encode_features[-1])
         self.last_out = out
         self.last_encode_features = encode_features
-        if rulebook_stream is not None:
+        if rulebook_stream_join is not None:
+            torch.cuda.current_stream().wait_stream(rulebook_stream_join)
+        elif rulebook_stream is not None:
             torch.cuda.current_stream().wait_stream(rulebook_stream)
         if not dense:      # fast path: the fusion encoder scatters `out` straight into its channels-last buffer
             return None, encode_features, kwargs

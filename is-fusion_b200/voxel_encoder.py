@@ -72,6 +72,37 @@ class DynamicVFE(nn.Module):
         return super()._load_from_state_dict(*a, **k)
 
     @torch.no_grad()
+    def group(self, features, coors, batch_size):
+        """first half of the fused op (capacity mode): voxel coordinates [N,4] + device-side count, available before
+        the feature kernel runs (the sparse-conv rulebooks only need these)."""
+        L.require_cuda(features, coors)
+        n, dev = features.size(0), features.device
+        ws_bytes = ctypes.c_size_t(0)
+        L.check(L.lib().isf_dynamic_vfe_workspace_size(n, ctypes.byref(ws_bytes)))
+        ws = L.workspace(ws_bytes.value, dev)
+        vcoors = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        nv = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.check(L.lib().isf_dynamic_vfe_group(L.ptr(coors), n, L.host_i32([batch_size] + self.grid), L.ptr(vcoors), L.ptr(nv),
+                                              L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        return vcoors, nv, ws
+
+    @torch.no_grad()
+    def compute(self, features, batch_size, ws):
+        """second half: the fused feature kernel on the grouping `group` left in `ws` (same stream)."""
+        if self.training:
+            raise L.IsfError('DynamicVFE: the fused CUDA path implements eval-mode BN only')
+        n, dev = features.size(0), features.device
+        w1, s1, b1, w2, s2, b2 = self._pack(dev)
+        f16 = self.out_dtype == torch.float16
+        feats = torch.empty((n, self.feat_channels[-1]), dtype=self.out_dtype, device=dev)
+        L.check(L.lib().isf_dynamic_vfe_compute(
+            L.ptr(features), n, features.size(1), L.host_i32([batch_size] + self.grid),
+            L.host_f32([self.vx, self.vy, self.vz]), L.host_f32([self.x_offset, self.y_offset, self.z_offset]),
+            L.ptr(w1), L.ptr(s1), L.ptr(b1), L.ptr(w2), L.ptr(s2), L.ptr(b2), self.in_channels, self.feat_channels[-1],
+            L.ptr(None if f16 else feats), L.ptr(feats if f16 else None), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        return feats
+
+    @torch.no_grad()
     def forward(self, features, coors, points=None, img_feats=None, img_metas=None, batch_size=None, nosync=False,
                 **kwargs):
         """features [N,5] fp32 points, coors [N,4] int32 (b,z,y,x), all in range ->
