@@ -357,10 +357,21 @@ def main():
             pass
         peak = peaks.get('bf16_tflops_sustained', 1400.0)
         top = max(recs, key=lambda r: r[0])
+        # DRAM traffic of the largest launch from the committed `ncu --set full` capture (profiles/), if present
+        traffic = None
+        try:
+            txt = open(os.path.join(ROOT, 'profiles', 'prof_gemm_r01_final.txt')).read().split('== tc::gemm_kernel<256')[0]
+            rd = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_read.sum')][0]
+            wr = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_write.sum')][0]
+            traffic = (rd + wr) * 1e6      # ncu prints MB
+        except Exception:
+            pass
         roof = {'kernel': 'tc::gemm_kernel (tcgen05 sparse-conv implicit GEMM; %d launches per frame)' % len(recs),
                 'bound': 'tensor', 'achieved': useful / (t_ms * 1e-3) / 1e12, 'achieved_issued': issued / (t_ms * 1e-3) / 1e12,
                 'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF/s sustained',
-                'unit': 'TFLOP/s', 'frac': useful / (t_ms * 1e-3) / 1e12 / peak, 'traffic': None, 'launches_per_frame': len(recs),
+                'unit': 'TFLOP/s', 'frac': useful / (t_ms * 1e-3) / 1e12 / peak, 'traffic': traffic,
+                'traffic_note': 'dram read+write bytes of the largest launch (stage-3 SubM 128->128; algorithmic 170 MB incl. the '
+                                'neighbour table) from profiles/prof_gemm_r01_final.txt', 'launches_per_frame': len(recs),
                 'kernel_ms_per_step': t_ms, 'share_of_step': t_ms / (ms / args.steps),
                 'largest_launch': {'cin': top[3], 'cout': top[4], 'rows': top[5], 'ms': top[0],
                                    'useful_tflops': top[2] / (top[0] * 1e-3) / 1e12, 'issued_tflops': top[1] / (top[0] * 1e-3) / 1e12},
