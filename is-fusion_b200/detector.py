@@ -7,7 +7,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import fusion_encoder, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
-from .registry import DETECTORS, build_backbone, build_fusion_layer, build_middle_encoder, build_voxel_encoder
+from .registry import (DETECTORS, NECKS, build_backbone, build_fusion_layer, build_middle_encoder,
+                       build_voxel_encoder)
 from .profiling import stage
 from .voxel_layer import Voxelization
 
@@ -24,6 +25,8 @@ class ISFusionDetector(nn.Module):
         self.pts_middle_encoder = build_middle_encoder(dict(pts_middle_encoder))
         self.fusion_encoder = build_fusion_layer(dict(fusion_encoder))
         self.pts_backbone = build_backbone(dict(pts_backbone))
+        # pts_neck (SECONDFPN) is the next row after the hot path; built when the config carries it
+        self.pts_neck = NECKS.build(dict(pts_neck)) if pts_neck is not None else None
         self.detach = kwargs.get('detach', False)
         out_size_factor = kwargs.get('out_size_factor', None)
         voxel_size = kwargs.get('voxel_size', None)
@@ -131,7 +134,10 @@ class ISFusionDetector(nn.Module):
         if overlap and nosync:
             torch.cuda.current_stream().wait_stream(self._streams(pts[0].device)[0])
         kwargs['lidar_sparse'] = self.pts_middle_encoder.last_out
-        return self.isfusion(pts, x, img_feats, img_metas, batch_size, nosync=nosync, **kwargs)
+        feats, ins_hm = self.isfusion(pts, x, img_feats, img_metas, batch_size, nosync=nosync, **kwargs)
+        if self.pts_neck is not None:        # isfusion.py:115-116
+            feats = self.pts_neck(feats)
+        return feats, ins_hm
 
     forward = extract_pts_feat
 

@@ -281,6 +281,85 @@ class SECONDV2(_Packable):
 
 
 # =====================================================================================================
+# SECONDFPN (pts_neck)
+# =====================================================================================================
+from .registry import NECKS  # noqa: E402
+
+
+@NECKS.register_module()
+class SECONDFPN(_Packable):
+    """ref: mmdet3d/models/necks/second_fpn.py:11-98 for the isfusion_0075voxel.py:105-112 configuration: a 1x1 conv
+    (level 0) and a 2x2 stride-2 deconv (level 1), each + BN + ReLU, concatenated and transposed to [X,Y].
+    Both are GEMMs over the BEV token matrix, so the whole neck is five launches of the tcgen05 GEMM with the BN
+    fold + ReLU in the epilogue and the concat / pixel-shuffle / transpose done by the epilogue's row scatter
+    straight into the channels-last [B, X, Y, 512] output."""
+
+    def __init__(self, in_channels=[128, 128, 256], out_channels=[256, 256, 256], upsample_strides=[1, 2, 4],
+                 norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), upsample_cfg=dict(type='deconv', bias=False),
+                 conv_cfg=dict(type='Conv2d', bias=False), use_conv_for_no_stride=False, init_cfg=None):
+        super().__init__()
+        if list(upsample_strides) != [1, 2] or not use_conv_for_no_stride:
+            raise L.IsfError('SECONDFPN: built for upsample_strides=[1,2], use_conv_for_no_stride=True')
+        self.in_channels, self.out_channels = in_channels, out_channels
+        blocks = []
+        for i, oc in enumerate(out_channels):
+            st = upsample_strides[i]
+            up = (nn.ConvTranspose2d(in_channels[i], oc, st, stride=st, bias=False) if st > 1 else
+                  nn.Conv2d(in_channels[i], oc, 1, stride=1, bias=False))
+            blocks.append(nn.Sequential(up, build_norm_layer(norm_cfg, oc)[1], nn.ReLU(inplace=True)))
+        self.deblocks = nn.ModuleList(blocks)
+        self._pk = None
+
+    def _pack(self):
+        if self.__dict__.get('_pk') is None:
+            from .spconv import fold_bn
+            c0, b0 = self.deblocks[0][0], self.deblocks[0][1]
+            c1, b1 = self.deblocks[1][0], self.deblocks[1][1]
+            pk = dict(w0=pack_weight(c0.weight.detach()[:, :, 0, 0]), sb0=fold_bn(b0), sb1=fold_bn(b1),
+                      w1=[pack_weight(c1.weight.detach()[:, :, dy, dx].t().contiguous()) for dy in range(2) for dx in range(2)])
+            self.__dict__['_pk'] = pk
+            self.__dict__['_rows'] = {}
+        return self.__dict__['_pk']
+
+    def _row_maps(self, bs, g, device):
+        """output row (in the transposed [B, X, Y] frame) of every input token."""
+        key = (bs, g, device)
+        rows = self.__dict__['_rows'].get(key)
+        if rows is None:
+            b = torch.arange(bs, device=device).view(bs, 1, 1)
+            y = torch.arange(g, device=device).view(1, g, 1)
+            x = torch.arange(g, device=device).view(1, 1, g)
+            r0 = ((b * g + x) * g + y).reshape(-1).int().contiguous()                 # level 0: (b,y,x) -> (b,x,y)
+            h = g // 2
+            yh = torch.arange(h, device=device).view(1, h, 1)
+            xh = torch.arange(h, device=device).view(1, 1, h)
+            r1 = [((b * g + 2 * xh + dx) * g + 2 * yh + dy).reshape(-1).int().contiguous()
+                  for dy in range(2) for dx in range(2)]
+            rows = (r0, r1)
+            self.__dict__['_rows'][key] = rows
+        return rows
+
+    @torch.no_grad()
+    def forward(self, x, swin_format=False, **kwargs):
+        """x = [feat_0 [B,128,G,G], feat_1 [B,256,G/2,G/2]] (channels-last memory) -> [out [B,512,G,G]] in the [X,Y] frame."""
+        if self.training:
+            raise L.IsfError('SECONDFPN: eval-mode CUDA path only')
+        pk = self._pack()
+        f0, f1 = x[0].permute(0, 2, 3, 1), x[1].permute(0, 2, 3, 1)
+        bs, g = f0.shape[0], f0.shape[1]
+        t0 = f0.reshape(bs * g * g, f0.shape[-1]).half().contiguous()
+        t1 = f1.reshape(bs * (g // 2) ** 2, f1.shape[-1]).half().contiguous()
+        oc0, oc1 = self.out_channels[0], self.out_channels[1]
+        out = torch.empty((bs * g * g, oc0 + oc1), dtype=torch.float16, device=t0.device)
+        r0, r1 = self._row_maps(bs, g, t0.device)
+        gemm(t0, pk['w0'], scale=pk['sb0'][0], shift=pk['sb0'][1], act='relu', out=out, out_rows=r0, ldo=oc0 + oc1)
+        up = out[:, oc0:]                                   # column offset: same rows, pitch oc0+oc1
+        for w, r in zip(pk['w1'], r1):
+            gemm(t1, w, scale=pk['sb1'][0], shift=pk['sb1'][1], act='relu', out=up, out_rows=r, ldo=oc0 + oc1)
+        return [out.view(bs, g, g, oc0 + oc1).permute(0, 3, 1, 2)]
+
+
+# =====================================================================================================
 # IGF parameter containers (names of fusion_encoder.py:44-171, 173-189, 472-502, 505-674, 768-830)
 # =====================================================================================================
 class MultiheadAttention(nn.Module):

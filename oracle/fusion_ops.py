@@ -252,6 +252,33 @@ class SECONDV2(nn.Module):
         return (x1, self.blocks[1](self.ds_layer(x1)))
 
 
+class SECONDFPN(nn.Module):
+    """ref: mmdet3d/models/necks/second_fpn.py:11-98 (config isfusion_0075voxel.py:105-112):
+    level 0: 1x1 conv (use_conv_for_no_stride) + BN + ReLU, level 1: 2x2 stride-2 deconv + BN + ReLU, concat,
+    then the [Y,X] -> [X,Y] transpose of :96."""
+
+    def __init__(self, in_channels=[128, 128, 256], out_channels=[256, 256, 256], upsample_strides=[1, 2, 4],
+                 norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), upsample_cfg=dict(type='deconv', bias=False),
+                 conv_cfg=dict(type='Conv2d', bias=False), use_conv_for_no_stride=False, **kw):
+        super().__init__()
+        eps, mom = norm_cfg.get('eps', 1e-5), norm_cfg.get('momentum', 0.1)
+        blocks = []
+        for i, oc in enumerate(out_channels):
+            st = upsample_strides[i]
+            if st > 1 or (st == 1 and not use_conv_for_no_stride):
+                up = nn.ConvTranspose2d(in_channels[i], oc, st, stride=st, bias=False)
+            else:
+                up = nn.Conv2d(in_channels[i], oc, 1, stride=1, bias=False)
+            blocks.append(nn.Sequential(up, nn.BatchNorm2d(oc, eps=eps, momentum=mom), nn.ReLU(inplace=True)))
+        self.deblocks = nn.ModuleList(blocks)
+
+    @torch.no_grad()
+    def forward(self, x):
+        ups = [d(x[i]) for i, d in enumerate(self.deblocks)]
+        out = torch.cat(ups, dim=1) if len(ups) > 1 else ups[0]
+        return [out.permute(0, 1, 3, 2).contiguous()]
+
+
 class ISFusionEncoder(nn.Module):
     """ref: fusion_encoder.py:833-1189."""
 

@@ -261,3 +261,24 @@ def test_sync_free_and_graph_paths_match_exact_path():
         assert torch.equal(a.cpu(), b)
     for a, b in zip(ef2, oh[1]):
         assert torch.equal(a.cpu(), b)
+
+
+def test_secondfpn_parity():
+    """pts_neck: 1x1 conv + 2x2 deconv + BN + ReLU + concat + [X,Y] transpose on the tcgen05 GEMM."""
+    from isfusion_b200.fusion_encoder import SECONDFPN
+    torch.manual_seed(0)
+    cfg = dict(in_channels=[128, 256], out_channels=[256, 256], upsample_strides=[1, 2],
+               norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), upsample_cfg=dict(type='deconv', bias=False),
+               use_conv_for_no_stride=True)
+    ref = synth.randomize_bn(fo.SECONDFPN(**cfg)).eval()
+    net = SECONDFPN(**cfg)
+    net.load_state_dict(ref.state_dict())
+    net = net.cuda().eval()
+    x0 = torch.randn(2, 128, 180, 180).half().float()
+    x1 = torch.randn(2, 256, 90, 90).half().float()
+    want = ref([x0, x1])[0]
+    got = net([x0.half().cuda().contiguous(memory_format=torch.channels_last),
+               x1.half().cuda().contiguous(memory_format=torch.channels_last)])[0]
+    assert got.shape == want.shape == (2, 512, 180, 180)
+    r, m = rel(got, want)
+    assert r < 2e-3, (r, m)
