@@ -1,0 +1,43 @@
+"""Drop-in check of the module/registry boundary: the reference's own config file instantiates the B200 modules by
+name (no mmcv), and the parameter names of the hot-path sub-modules are the reference's.
+Needs the reference checkout (build container only); skipped elsewhere."""
+import os
+
+import pytest
+
+CFG = '/root/reference/configs/isfusion/isfusion_0075voxel.py'
+
+
+@pytest.mark.skipif(not os.path.exists(CFG), reason='reference checkout not present')
+def test_reference_config_builds_b200_modules():
+    import isfusion_b200.detector  # noqa: F401  (registers the modules)
+    from isfusion_b200.registry import build_detector
+    ns = {}
+    exec(compile(open(CFG).read(), CFG, 'exec'), ns)       # the config is self-contained (no _base_)
+    model = dict(ns['model'])
+    assert model['type'] == 'ISFusionDetector'
+    det = build_detector(model)                            # img_backbone / img_neck / pts_bbox_head are outside the path
+    sd = det.state_dict()
+    expected = [
+        'pts_voxel_encoder.vfe_layers.0.linear.weight', 'pts_voxel_encoder.vfe_layers.1.norm.running_var',
+        'pts_middle_encoder.conv_input.0.weight', 'pts_middle_encoder.encoder_layers.encoder_layer1.0.conv1.weight',
+        'pts_middle_encoder.encoder_layers.encoder_layer3.2.0.weight', 'pts_middle_encoder.conv_out.1.running_mean',
+        'fusion_encoder.conv_fusion.conv.weight', 'fusion_encoder.conv_fusion.bn.running_mean',
+        'fusion_encoder.grid2region_att.0.linear0.weight',
+        'fusion_encoder.grid2region_att.1.block_list.0.encoder_list.1.win_attn.self_attn.in_proj_weight',
+        'fusion_encoder.grid2region_att.0.block_list.0.encoder_list.0.norm2.bias',
+        'fusion_encoder.heatmap_head_3.bias', 'fusion_encoder.instance_att.layers.1.cross_attn.sampling_offsets.bias',
+        'fusion_encoder.instance_att.query_pos_embed.position_embedding_head.3.weight',
+        'fusion_encoder.instance_to_scene_att.multihead_attn.in_proj_weight', 'fusion_encoder.instance_to_scene_att.norm.weight',
+        'pts_backbone.blocks.0.15.weight', 'pts_backbone.ds_layer.1.running_var', 'pts_backbone.blocks.1.12.weight',
+        'pts_neck.deblocks.0.0.weight', 'pts_neck.deblocks.1.1.running_mean',
+    ]
+    missing = [k for k in expected if k not in sd]
+    assert not missing, missing
+    # shapes fixed by the config
+    assert tuple(sd['pts_middle_encoder.conv_input.0.weight'].shape) == (3, 3, 3, 64, 32)       # spconv1/mmcv layout
+    assert tuple(sd['fusion_encoder.conv_fusion.conv.weight'].shape) == (128, 768, 3, 3)
+    assert tuple(sd['pts_neck.deblocks.1.0.weight'].shape) == (256, 256, 2, 2)
+    assert det.fusion_encoder.bev_size == 180 and det.fusion_encoder.instance_num == 200
+    assert det.pts_pillar_layer.max_num_points == 12 and det.pillar_size[:2] == [0.6, 0.6]
+    assert det.pts_middle_encoder.sparse_shape == [41, 1440, 1440]
