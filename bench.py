@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
@@ -300,7 +300,8 @@ def main():
         return gn.run_prefetched(ticket, out_host)
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:           # one sampler per job (rank 0's GPU): N concurrent nvidia-smi loops would perturb the run
+        sampler.start()
     ms_eager = timed(step_eager, max(3, args.steps // 4), 2)
     ms_eager /= max(3, args.steps // 4)
     log('eager (exact mode, host syncs, after capture): %.3f ms/step' % ms_eager)
