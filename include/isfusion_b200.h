@@ -62,6 +62,15 @@ int isf_dynamic_vfe_compute(const float* points, int n, int nfeat, const int* di
                             float* voxel_feats_f32, void* voxel_feats_f16, void* workspace, size_t ws_bytes,
                             void* stream);
 
+/* tensor-core variant of `compute` (the default of the module): the two 64x64 halves of layer 2 run on the tcgen05
+ * GEMM (w2a = W2[:, :64], w2b = W2[:, 64:], fp16 K-major [64][64]); fp16 output only.  Needs
+ * isf_dynamic_vfe_tc_workspace_size(n) bytes for both the preceding `group` call and this call. */
+int isf_dynamic_vfe_tc_workspace_size(int n, size_t* bytes);
+int isf_dynamic_vfe_compute_tc(const float* points, int n, int nfeat, const int* dims, const float* voxel_size,
+                               const float* offsets, const float* w1, const float* scale1, const float* shift1,
+                               const void* w2a, const void* w2b, const float* scale2, const float* shift2,
+                               void* voxel_feats_f16, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- a2: dynamic scatter (per-voxel mean / max / sum) -------------------------
  * replaces voxel_layer.dynamic_point_to_voxel_forward(feats, coors, reduce_type)
  *   mmdet3d/ops/voxel/src/voxelization.h:108-120, scatter_points_cuda.cu:183-239.

@@ -169,6 +169,7 @@ struct GemmParams {
   const float* shift;     // [N_total] or nullptr
   const __half* residual; // [m, ldr] or nullptr (added before the activation)
   int ldr;
+  const int* res_rows;    // optional gather of the residual row: residual[res_rows[m]] (-1 = none)
   int act;
   const float* ln_gamma;  // LayerNorm over the BN columns after residual (requires BN == n_total)
   const float* ln_beta;
@@ -364,6 +365,8 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       long long orow = grow;
       if (p.out_rows && row_ok) orow = p.out_rows[grow];
       const bool store_ok = row_ok && orow >= 0;
+      long long rrow = row_ok ? (long long)grow : -1;
+      if (p.res_rows && row_ok) rrow = p.res_rows[grow];
       float mean = 0.f, rstd = 1.f;
       if (ln && warp < 4) {
         // pass 1 over TMEM: row statistics of (acc*scale+shift+residual)
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
             const int n = n0 + cb + j;
             if (p.scale) x *= p.scale[n];
             if (p.shift) x += p.shift[n];
-            if (p.residual && row_ok) x += __half2float(p.residual[(long long)grow * p.ldr + n]);
+            if (p.residual && rrow >= 0) x += __half2float(p.residual[rrow * p.ldr + n]);
             s1 += x; s2 += x * x;
           }
         }
@@ -399,8 +402,8 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
           if (p.shift) y += p.shift[n];
           x[j] = y;
         }
-        if (p.residual && row_ok) {
-          const uint4* rp = (const uint4*)(p.residual + (long long)grow * p.ldr + n0 + cb);
+        if (p.residual && rrow >= 0) {
+          const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n0 + cb);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             uint4 u = rp[j4];

@@ -9,7 +9,7 @@
 // and then works on contiguous segments: no atomics, no dense canvases, no host syncs, results
 // deterministic and in the reference's sorted-unique (b,z,y,x) order.
 #include <cub/cub.cuh>
-#include "common.cuh"
+#include "tc_gemm.cuh"
 
 extern "C" void isf_count_launch(int n);
 
@@ -703,6 +703,178 @@ extern "C" int isf_dynamic_vfe_compute(const float* points, int n, int nfeat, co
                                                                       G.num_valid, L, P, w1, scale1, shift1, w2, scale2, shift2,
                                                                       voxel_feats_f32, (__half*)voxel_feats_f16, nullptr);
   isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a3, tensor-core formulation (default): the 64x64 halves of layer 2 are GEMMs on tcgen05, everything else is
+// a light streaming kernel.  With h1 = relu(bn1(W1 f)) per point and m1 = per-voxel max of h1:
+//   layer 2 = relu(bn2(W2[:, :64] h1 + W2[:, 64:] m1))  ->  g' = (W2[:, 64:] m1) * scale2           (GEMM over voxels)
+//                                                           y  = relu((W2[:, :64] h1) * scale2 + shift2 + g'[voxel(p)])
+//                                                                                                   (GEMM over points)
+// and the output is the per-voxel max of y.  Layer 1 (11 inputs, raw coordinates) stays fp32; h1 / g' / y are stored
+// fp16 (fp32 accumulate).  The ncu capture of the SIMT kernel showed it shared-memory bound (L1TEX 80 %, 265 M warp
+// instructions, 0.41 ms); this path moves ~190 MB through HBM instead.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vfe_voxel_prep_kernel(const float* __restrict__ points, int nfeat,
+                                                             const int* __restrict__ idx_sorted,
+                                                             const int* __restrict__ cnt, const int* __restrict__ start,
+                                                             const int* __restrict__ num_valid, int n,
+                                                             float4* __restrict__ mean, int* __restrict__ seg_of) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nv = *num_valid;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nv; v += warps) {
+    const int s = start[v], m = cnt[v];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int j = lane; j < m; j += 32) {
+      const float* p = points + (size_t)idx_sorted[s + j] * nfeat;
+      sx += p[0]; sy += p[1]; sz += p[2];
+      seg_of[s + j] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    if (lane == 0) mean[v] = make_float4(sx / (float)m, sy / (float)m, sz / (float)m, (float)m);
+  }
+  // sorted positions beyond the valid points (out-of-range padding) belong to no voxel
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nv > 0) seg_of[n] = start[nv - 1] + cnt[nv - 1];   // = number of valid points
+}
+
+// layer 1 per point (8 lanes per point, 8 channels per lane), fp32 math, fp16 row of h1 in sorted order
+__global__ void __launch_bounds__(256) vfe_point_layer1_kernel(const float* __restrict__ points, int nfeat,
+                                                               const int* __restrict__ idx_sorted,
+                                                               const unsigned long long* __restrict__ uniq,
+                                                               const float4* __restrict__ mean,
+                                                               const int* __restrict__ seg_of, int n, KeyLayout L, VfeParams P,
+                                                               const float* __restrict__ w1, const float* __restrict__ s1,
+                                                               const float* __restrict__ b1, __half* __restrict__ h1,
+                                                               int* __restrict__ res_rows) {
+  __shared__ __align__(16) float w1t[VFE_IN][VFE_C];
+  for (int t = threadIdx.x; t < VFE_IN * VFE_C; t += blockDim.x) w1t[t % VFE_IN][t / VFE_IN] = w1[t];
+  __syncthreads();
+  const int nvalid_pts = seg_of[n];
+  const int sub = threadIdx.x & 7;                    // channel group: channels sub*8 .. sub*8+7
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; j < n; j += (gridDim.x * blockDim.x) >> 3) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+    int v = -1;
+    if (j < nvalid_pts) {
+      v = seg_of[j];
+      const float* p = points + (size_t)idx_sorted[j] * nfeat;
+      const float4 mu = mean[v];
+      int cc[4];
+      unpack_key(uniq[v], L, cc);
+      float f[VFE_IN];
+      f[0] = p[0]; f[1] = p[1]; f[2] = p[2]; f[3] = p[3]; f[4] = p[4];
+      f[5] = __fsub_rn(f[0], mu.x); f[6] = __fsub_rn(f[1], mu.y); f[7] = __fsub_rn(f[2], mu.z);
+      f[8] = __fsub_rn(f[0], __fadd_rn(__fmul_rn((float)cc[3], P.vx), P.xoff));
+      f[9] = __fsub_rn(f[1], __fadd_rn(__fmul_rn((float)cc[2], P.vy), P.yoff));
+      f[10] = __fsub_rn(f[2], __fadd_rn(__fmul_rn((float)cc[1], P.vz), P.zoff));
+      float h[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) h[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < VFE_IN; ++k) {
+        const float4 wa = *(const float4*)&w1t[k][sub * 8], wb = *(const float4*)&w1t[k][sub * 8 + 4];
+        h[0] = fmaf(wa.x, f[k], h[0]); h[1] = fmaf(wa.y, f[k], h[1]); h[2] = fmaf(wa.z, f[k], h[2]); h[3] = fmaf(wa.w, f[k], h[3]);
+        h[4] = fmaf(wb.x, f[k], h[4]); h[5] = fmaf(wb.y, f[k], h[5]); h[6] = fmaf(wb.z, f[k], h[6]); h[7] = fmaf(wb.w, f[k], h[7]);
+      }
+      __half2* oh = (__half2*)&o;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ch = sub * 8 + 2 * c;
+        const float a = fmaxf(fmaf(h[2 * c], s1[ch], b1[ch]), 0.f), b = fmaxf(fmaf(h[2 * c + 1], s1[ch + 1], b1[ch + 1]), 0.f);
+        oh[c] = __floats2half2_rn(a, b);
+      }
+    }
+    *(uint4*)(h1 + (size_t)j * VFE_C + sub * 8) = o;
+    if (sub == 0) res_rows[j] = v;
+  }
+}
+
+// per-voxel max over its (contiguous) rows: thread = (voxel, 8-channel group); values are >= 0 (post-ReLU)
+__global__ void __launch_bounds__(256) vfe_voxel_max_kernel(const __half* __restrict__ rows, const int* __restrict__ cnt,
+                                                            const int* __restrict__ start, const int* __restrict__ num_valid,
+                                                            __half* __restrict__ out) {
+  const int nv = *num_valid;
+  const int sub = threadIdx.x & 7;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; v < nv; v += (gridDim.x * blockDim.x) >> 3) {
+    const int s = start[v], m = cnt[v];
+    __half2 mx[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mx[c] = __floats2half2_rn(0.f, 0.f);
+    for (int j = 0; j < m; ++j) {
+      const uint4 u = *(const uint4*)(rows + (size_t)(s + j) * VFE_C + sub * 8);
+      const __half2* h = (const __half2*)&u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mx[c] = __hmax2(mx[c], h[c]);
+    }
+    uint4 o;
+    o.x = *(const uint32_t*)&mx[0]; o.y = *(const uint32_t*)&mx[1]; o.z = *(const uint32_t*)&mx[2]; o.w = *(const uint32_t*)&mx[3];
+    *(uint4*)(out + (size_t)v * VFE_C + sub * 8) = o;
+  }
+}
+
+extern "C" int isf_dynamic_vfe_tc_workspace_size(int n, size_t* bytes) {
+  ISF_CHECK_ARG(n >= 0 && bytes);
+  size_t base = 0;
+  int rc = isf_dynamic_scatter_workspace_size(n, &base);
+  if (rc) return rc;
+  const size_t nn = n > 0 ? n : 1;
+  *bytes = base + isf_align_up((nn + 1) * sizeof(int)) * 2 + isf_align_up(nn * sizeof(float4)) +
+           4 * isf_align_up(nn * VFE_C * sizeof(__half)) + 4096;
+  return ISF_OK;
+}
+
+// tensor-core second half of the fused op; must follow isf_dynamic_vfe_group on the same stream with the same
+// (n, dims) and a workspace of isf_dynamic_vfe_tc_workspace_size(n) bytes.  w2a / w2b: fp16 K-major [64][64]
+// (= W2[:, :64] and W2[:, 64:]).  Output: voxel_feats_f16 [n,64] (rows < num_voxels valid).
+extern "C" int isf_dynamic_vfe_compute_tc(const float* points, int n, int nfeat, const int* dims, const float* voxel_size,
+                                          const float* offsets, const float* w1, const float* scale1, const float* shift1,
+                                          const void* w2a, const void* w2b, const float* scale2, const float* shift2,
+                                          void* voxel_feats_f16, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(n >= 0 && nfeat >= 5 && dims && voxel_size && offsets);
+  if (n == 0) return ISF_OK;
+  ISF_CHECK_ARG(points && w1 && scale1 && shift1 && w2a && w2b && scale2 && shift2 && voxel_feats_f16 && workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  IsfArena A(workspace, ws_bytes);
+  GroupBuffers G;
+  group_carve(A, n, &G);                       // same carve as isf_dynamic_vfe_group: finds its buffers
+  int* seg_of = A.take<int>(n + 1);
+  int* res_rows = A.take<int>(n + 1);
+  float4* mean = A.take<float4>(n);
+  __half* h1 = A.take<__half>((size_t)n * VFE_C);
+  __half* m1 = A.take<__half>((size_t)n * VFE_C);
+  __half* g = A.take<__half>((size_t)n * VFE_C);
+  __half* y = A.take<__half>((size_t)n * VFE_C);
+  if (!A.ok) { isf_set_error("dynamic_vfe_compute_tc: workspace too small"); return ISF_ERR_WORKSPACE; }
+  KeyLayout L = make_layout(4, dims);
+  VfeParams P{voxel_size[0], voxel_size[1], voxel_size[2], offsets[0], offsets[1], offsets[2]};
+  const int blocks = ISF_NUM_SMS * 8;
+  ISF_CUDA(cudaMemsetAsync(seg_of + n, 0, sizeof(int), st));
+  vfe_voxel_prep_kernel<<<blocks, 256, 0, st>>>(points, nfeat, G.idx_sorted, G.cnt, G.start, G.num_valid, n, mean, seg_of);
+  vfe_point_layer1_kernel<<<blocks, 256, 0, st>>>(points, nfeat, G.idx_sorted, G.uniq, mean, seg_of, n, L, P, w1, scale1,
+                                                  shift1, h1, res_rows);
+  vfe_voxel_max_kernel<<<blocks, 256, 0, st>>>(h1, G.cnt, G.start, G.num_valid, m1);
+  // g' = (m1 . W2b^T) * scale2          [voxels, 64]
+  tc::GemmParams q{};
+  q.A = m1; q.W = (const __half*)w2b; q.m_dev = G.num_valid; q.m = n; q.cin = VFE_C; q.taps = 1; q.kpad = VFE_C;
+  q.n_total = VFE_C; q.scale = scale2; q.act = tc::ACT_NONE; q.out = g; q.ldo = VFE_C;
+  int rc = tc::dispatch_gemm(q, VFE_C, n, st);
+  if (rc) return rc;
+  // y = relu((h1 . W2a^T) * scale2 + shift2 + g'[voxel(p)])     [points, 64]
+  tc::GemmParams r{};
+  r.A = h1; r.W = (const __half*)w2a; r.m = n; r.cin = VFE_C; r.taps = 1; r.kpad = VFE_C; r.n_total = VFE_C;
+  r.scale = scale2; r.shift = shift2; r.residual = g; r.ldr = VFE_C; r.res_rows = res_rows; r.act = tc::ACT_RELU;
+  r.out = y; r.ldo = VFE_C;
+  rc = tc::dispatch_gemm(r, VFE_C, n, st);
+  if (rc) return rc;
+  vfe_voxel_max_kernel<<<blocks, 256, 0, st>>>(y, G.cnt, G.start, G.num_valid, (__half*)voxel_feats_f16);
+  isf_count_launch(7);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
 }

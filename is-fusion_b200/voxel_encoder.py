@@ -48,6 +48,8 @@ class DynamicVFE(nn.Module):
         self.vfe_layers = nn.ModuleList(
             [DynamicVFELayer(chans[i] * (2 if i > 0 else 1), chans[i + 1], norm_cfg) for i in range(2)])
         self.out_dtype = out_dtype
+        # layer 2 on the tcgen05 GEMM (fp16 activations, fp32 accumulate); False = the all-fp32 SIMT kernel
+        self.tensor_core = True
         self._packed = None
 
     def _pack(self, device):
@@ -60,7 +62,12 @@ class DynamicVFE(nn.Module):
                 shift = (bn.bias - bn.running_mean * scale).float()
                 out += [layer.linear.weight.detach().float().contiguous(), scale.detach().contiguous(),
                         shift.detach().contiguous()]
-            self._packed = [t.to(device) for t in out]
+            out = [t.to(device) for t in out]
+            from .gemm import pack_weight
+            c = self.feat_channels[0]
+            w2 = out[3]
+            out += [pack_weight(w2[:, :c]), pack_weight(w2[:, c:])]        # W2[:, :64], W2[:, 64:] fp16 K-major
+            self._packed = out
         return self._packed
 
     def train(self, mode=True):
@@ -71,6 +78,9 @@ class DynamicVFE(nn.Module):
         self._packed = None
         return super()._load_from_state_dict(*a, **k)
 
+    def _use_tc(self):
+        return self.tensor_core and self.out_dtype == torch.float16
+
     @torch.no_grad()
     def group(self, features, coors, batch_size):
         """first half of the fused op (capacity mode): voxel coordinates [N,4] + device-side count, available before
@@ -78,7 +88,10 @@ class DynamicVFE(nn.Module):
         L.require_cuda(features, coors)
         n, dev = features.size(0), features.device
         ws_bytes = ctypes.c_size_t(0)
-        L.check(L.lib().isf_dynamic_vfe_workspace_size(n, ctypes.byref(ws_bytes)))
+        if self._use_tc():
+            L.check(L.lib().isf_dynamic_vfe_tc_workspace_size(n, ctypes.byref(ws_bytes)))
+        else:
+            L.check(L.lib().isf_dynamic_vfe_workspace_size(n, ctypes.byref(ws_bytes)))
         ws = L.workspace(ws_bytes.value, dev)
         vcoors = torch.empty((n, 4), dtype=torch.int32, device=dev)
         nv = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -92,9 +105,16 @@ class DynamicVFE(nn.Module):
         if self.training:
             raise L.IsfError('DynamicVFE: the fused CUDA path implements eval-mode BN only')
         n, dev = features.size(0), features.device
-        w1, s1, b1, w2, s2, b2 = self._pack(dev)
+        w1, s1, b1, w2, s2, b2, w2a, w2b = self._pack(dev)
         f16 = self.out_dtype == torch.float16
         feats = torch.empty((n, self.feat_channels[-1]), dtype=self.out_dtype, device=dev)
+        if self._use_tc():
+            L.check(L.lib().isf_dynamic_vfe_compute_tc(
+                L.ptr(features), n, features.size(1), L.host_i32([batch_size] + self.grid),
+                L.host_f32([self.vx, self.vy, self.vz]), L.host_f32([self.x_offset, self.y_offset, self.z_offset]),
+                L.ptr(w1), L.ptr(s1), L.ptr(b1), L.ptr(w2a), L.ptr(w2b), L.ptr(s2), L.ptr(b2), L.ptr(feats), L.ptr(ws),
+                ctypes.c_size_t(ws.numel()), L.stream()))
+            return feats
         L.check(L.lib().isf_dynamic_vfe_compute(
             L.ptr(features), n, features.size(1), L.host_i32([batch_size] + self.grid),
             L.host_f32([self.vx, self.vy, self.vz]), L.host_f32([self.x_offset, self.y_offset, self.z_offset]),
@@ -114,20 +134,8 @@ class DynamicVFE(nn.Module):
         dev = features.device
         if batch_size is None:
             batch_size = int(coors[-1, 0].item()) + 1        # same host read as isfusion.py:110
-        w1, s1, b1, w2, s2, b2 = self._pack(dev)
-        ws_bytes = ctypes.c_size_t(0)
-        L.check(L.lib().isf_dynamic_vfe_workspace_size(n, ctypes.byref(ws_bytes)))
-        ws = L.workspace(ws_bytes.value, dev)
-        f16 = self.out_dtype == torch.float16
-        feats = torch.empty((n, self.feat_channels[-1]), dtype=self.out_dtype, device=dev)
-        vcoors = torch.empty((n, 4), dtype=torch.int32, device=dev)
-        nv = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.check(L.lib().isf_dynamic_vfe_forward(
-            L.ptr(features), L.ptr(coors), n, features.size(1), L.host_i32([batch_size] + self.grid),
-            L.host_f32([self.vx, self.vy, self.vz]), L.host_f32([self.x_offset, self.y_offset, self.z_offset]),
-            L.ptr(w1), L.ptr(s1), L.ptr(b1), L.ptr(w2), L.ptr(s2), L.ptr(b2), self.in_channels,
-            self.feat_channels[-1], L.ptr(None if f16 else feats), L.ptr(feats if f16 else None), L.ptr(vcoors),
-            L.ptr(nv), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        vcoors, nv, ws = self.group(features, coors, batch_size)
+        feats = self.compute(features, batch_size, ws)
         if nosync:       # capacity mode: (feats [N,64], coors [N,4], device-side voxel count)
             return feats, vcoors, nv
         v = int(nv.item())
