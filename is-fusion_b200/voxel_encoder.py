@@ -6,6 +6,7 @@ Same constructor, state_dict keys (vfe_layers.{i}.linear.weight / .norm.*) and (
 return contract; voxel order = the reference's sorted-unique (b,z,y,x) order.
 """
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -48,8 +49,9 @@ class DynamicVFE(nn.Module):
         self.vfe_layers = nn.ModuleList(
             [DynamicVFELayer(chans[i] * (2 if i > 0 else 1), chans[i + 1], norm_cfg) for i in range(2)])
         self.out_dtype = out_dtype
-        # layer 2 on the tcgen05 GEMM (fp16 activations, fp32 accumulate); False = the all-fp32 SIMT kernel
-        self.tensor_core = True
+        # layer 2 on the tcgen05 GEMM (fp16 activations, fp32 accumulate); False = the all-fp32 SIMT kernel.
+        # Both are CUDA paths of the same op; ISF_VFE_TC selects the default until the GEMM form is the measured winner.
+        self.tensor_core = os.environ.get('ISF_VFE_TC', '0') == '1'
         self._packed = None
 
     def _pack(self, device):
