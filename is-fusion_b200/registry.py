@@ -7,6 +7,8 @@ import inspect
 
 from torch import nn
 
+from .norm import NaiveSyncBatchNorm1d, NaiveSyncBatchNorm2d
+
 
 class Registry:
     def __init__(self, name):
@@ -42,9 +44,9 @@ CONV_LAYERS = Registry('conv')
 NORM_LAYERS.register_module('BN', module=nn.BatchNorm2d)
 NORM_LAYERS.register_module('BN1d', module=nn.BatchNorm1d)
 NORM_LAYERS.register_module('BN2d', module=nn.BatchNorm2d)
-# eval / single-process behaviour of the reference's naiveSyncBN* is plain BatchNorm (ops/norm.py:173-175)
-NORM_LAYERS.register_module('naiveSyncBN1d', module=nn.BatchNorm1d)
-NORM_LAYERS.register_module('naiveSyncBN2d', module=nn.BatchNorm2d)
+# plain BatchNorm in eval / single process, cross-rank moments when training on >1 rank (ops/norm.py:136-271)
+NORM_LAYERS.register_module('naiveSyncBN1d', module=NaiveSyncBatchNorm1d)
+NORM_LAYERS.register_module('naiveSyncBN2d', module=NaiveSyncBatchNorm2d)
 CONV_LAYERS.register_module('Conv2d', module=nn.Conv2d)
 
 

@@ -47,3 +47,63 @@ def test_frame_generators_are_rank_disjoint_and_seeded():
     b = synth.make_points(2000, 'S', bench.frame_seed(1, 1) * 8)
     a2 = synth.make_points(2000, 'S', bench.frame_seed(0, 1) * 8)
     assert torch.equal(a, a2) and not torch.equal(a, b)
+
+
+def _bn_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from isfusion_b200.norm import NaiveSyncBatchNorm1d, NaiveSyncBatchNorm2d
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    out = {}
+    for name, cls, shape in (('1d', NaiveSyncBatchNorm1d, (50 + 30 * rank, 8)), ('2d', NaiveSyncBatchNorm2d, (2, 8, 5, 3 + rank))):
+        torch.manual_seed(0)
+        bn = cls(8, eps=1e-3, momentum=0.01)
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.5, 0.5)
+        x = (torch.randn(shape, generator=g) * (1 + rank) + rank).requires_grad_(True)
+        bn.train()
+        y = bn(x)
+        y.square().sum().backward()
+        bn.eval()
+        y_eval = bn(x.detach())
+        out[name] = {k: v.detach().clone().numpy() for k, v in dict(
+            x=x, y=y, gx=x.grad, rm=bn.running_mean, rv=bn.running_var, w=bn.weight, b=bn.bias, y_eval=y_eval).items()}
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_naive_sync_bn_two_ranks():
+    """a15 (ref ops/norm.py:160-202): ranks are averaged with equal weight; checked against the closed form computed
+    in one process from both ranks' inputs, gradients against autograd through that closed form."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bn_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    res = {r: {n: {k: torch.from_numpy(v) for k, v in d.items()} for n, d in o.items()} for r, o in res.items()}
+    for name in ('1d', '2d'):
+        xs = [res[r][name]['x'].clone().requires_grad_(True) for r in range(2)]
+        w = res[0][name]['w'].clone().requires_grad_(True)
+        b = res[0][name]['b']
+        red = [d for d in range(xs[0].dim()) if d != 1]
+        mean = sum(x.mean(dim=red) for x in xs) / 2
+        meansqr = sum((x * x).mean(dim=red) for x in xs) / 2
+        var = meansqr - mean * mean
+        bshape = [1, -1] + [1] * (xs[0].dim() - 2)
+        scale = w * torch.rsqrt(var + 1e-3)
+        ys = [x * scale.view(bshape) + (b - mean * scale).view(bshape) for x in xs]
+        # every rank back-propagates its own loss; DDP-style total = sum of the per-rank losses
+        sum(y.square().sum() for y in ys).backward()
+        for r in range(2):
+            o = res[r][name]
+            assert torch.allclose(o['y'], ys[r].detach(), atol=1e-5)
+            assert torch.allclose(o['gx'], xs[r].grad, atol=1e-4, rtol=1e-4)
+            assert torch.allclose(o['rm'], 0.01 * mean.detach(), atol=1e-6)
+            assert torch.allclose(o['rv'], 1 + 0.01 * (var.detach() - 1), atol=1e-6)
+            # eval = plain BatchNorm on the running statistics
+            ref = torch.nn.functional.batch_norm(o['x'], o['rm'], o['rv'], o['w'], o['b'], False, 0.0, 1e-3)
+            assert torch.allclose(o['y_eval'], ref, atol=1e-5)
