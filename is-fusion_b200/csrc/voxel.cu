@@ -760,9 +760,10 @@ __global__ void __launch_bounds__(256) vfe_point_layer1_kernel(const float* __re
   const int nvalid_pts = seg_of[n];
   const int sub = threadIdx.x & 7;                    // channel group: channels sub*8 .. sub*8+7
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; j < n; j += (gridDim.x * blockDim.x) >> 3) {
-    uint4 o = make_uint4(0, 0, 0, 0);
-    int v = -1;
-    if (j < nvalid_pts) {
+    if (j >= nvalid_pts) break;                         // out-of-range padding: rows never read (GEMM stops at nvalid)
+    uint4 o;
+    int v;
+    {
       v = seg_of[j];
       const float* p = points + (size_t)idx_sorted[j] * nfeat;
       const float4 mu = mean[v];
@@ -868,7 +869,8 @@ extern "C" int isf_dynamic_vfe_compute_tc(const float* points, int n, int nfeat,
   if (rc) return rc;
   // y = relu((h1 . W2a^T) * scale2 + shift2 + g'[voxel(p)])     [points, 64]
   tc::GemmParams r{};
-  r.A = h1; r.W = (const __half*)w2a; r.m = n; r.cin = VFE_C; r.taps = 1; r.kpad = VFE_C; r.n_total = VFE_C;
+  r.A = h1; r.W = (const __half*)w2a; r.m = n; r.m_dev = seg_of + n;   // only the in-range points (device-side count)
+  r.cin = VFE_C; r.taps = 1; r.kpad = VFE_C; r.n_total = VFE_C;
   r.scale = scale2; r.shift = shift2; r.residual = g; r.ldr = VFE_C; r.res_rows = res_rows; r.act = tc::ACT_RELU;
   r.out = y; r.ldo = VFE_C;
   rc = tc::dispatch_gemm(r, VFE_C, n, st);
