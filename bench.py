@@ -56,6 +56,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=16, help='distinct resident frames rotated through (L2 defeat)')
     ap.add_argument('--cpu-points', type=int, default=0, help='points of the CPU-baseline sample frame (0 = same as --points)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--inflight', type=int, default=3, help='frames in flight (graph lanes replayed round-robin on their own streams)')
     ap.add_argument('--eager-only', action='store_true', help='profiling aid: time the eager exact-mode path only (no graph)')
     ap.add_argument('--stages', action='store_true', help='extra pass with per-stage CUDA-event timers')
     return ap.parse_args()
@@ -236,7 +237,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def timed(fn, steps, warmup, base=0):
+    def timed(fn, steps, warmup, base=0, join=None):
         for i in range(warmup):
             fn(base + i)
         torch.cuda.synchronize()
@@ -246,6 +247,8 @@ def main():
         e0.record()
         for i in range(steps):
             fn(base + warmup + i)
+        if join is not None:
+            join()                  # the timing stream waits for every frame still in flight on the lane streams
         e1.record()
         torch.cuda.synchronize()
         barrier()
@@ -261,16 +264,20 @@ def main():
             print(json.dumps({'metric': METRIC, 'mode': 'eager-only (profiling aid, not a bench value)',
                               'ms_per_step': ms / args.steps}))
         return
-    from isfusion_b200.detector import GraphedNeck
+    from isfusion_b200.detector import FramePipeline, GraphedNeck
+    LANES = max(1, args.inflight)
     log('calibrating buffer capacities on 2 frames (exact mode)')
     caps = GraphedNeck.calibrate(net, [dev_sets[0][0], dev_sets[1 % F_][0]], dev_sets[0][1], metas, margin=1.35, **kw)
     npts_cap = max(p.shape[0] for pts, _ in host_sets for p in pts)
-    gn = GraphedNeck(net, B, npts_cap, img_hw=IMG, calib=kw, capacities=caps, device=dev)
     t_pre = timed(step_eager_pre, 5, 2) / 5
     log('eager before capture: %.3f ms/step' % t_pre)
-    gn.load(dev_sets[0][0], dev_sets[0][1][1])
-    gn.capture()
-    log('graph captured; strided-conv capacities %s' % caps)
+
+    def build_pipeline(caps):
+        return FramePipeline(net, LANES, B, npts_cap, img_hw=IMG, calib=kw, capacities=caps,
+                             device=dev).capture(dev_sets[0][0], dev_sets[0][1][1])
+
+    pipe = build_pipeline(caps)
+    log('graph captured (%d lane(s)); strided-conv capacities %s' % (LANES, caps))
 
     def step_eager(i):
         pts, feats = dev_sets[i % F_]
@@ -278,26 +285,26 @@ def main():
 
     def step_resident(i):
         pts, feats = dev_sets[i % F_]
-        return gn(pts, feats[1])            # D2D copy into the graph's static inputs + one graph replay
+        return pipe.submit(pts, feats[1])   # D2D copy into the lane's static inputs + one graph replay
 
-    out_host = None
-    e2e_state = {'ticket': None}
+    out_host = [None] * LANES
+    tickets = [None] * LANES
 
     def step_e2e(i):
         """public pipelined API: pinned host frame i -> H2D -> graph replay -> D2H of both output maps.  The H2D of
-        frame i+1 and the D2H of frame i run on a copy stream and overlap the replays; every byte still moves
-        inside the timed region (it ends with a device synchronise)."""
-        nonlocal out_host
-        if out_host is None:
-            o, _ = gn.outputs
-            out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in o]
-        if e2e_state['ticket'] is None:
+        the lane's next frame and the D2H of its previous frame run on a copy stream and overlap the replays; every
+        byte still moves inside the timed region (it ends with a join + device synchronise)."""
+        k = i % LANES
+        if out_host[k] is None:
+            o, _ = pipe.lanes[k].outputs
+            out_host[k] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in o]
+        if tickets[k] is None:
             pts, feats = host_sets[i % F_]
-            e2e_state['ticket'] = gn.prefetch(pts, feats[1])
-        ticket = e2e_state['ticket']
-        pts, feats = host_sets[(i + 1) % F_]
-        e2e_state['ticket'] = gn.prefetch(pts, feats[1])      # next frame's H2D overlaps this replay
-        return gn.run_prefetched(ticket, out_host)
+            tickets[k] = pipe.prefetch(k, pts, feats[1])
+        ticket = tickets[k]
+        pts, feats = host_sets[(i + LANES) % F_]
+        tickets[k] = pipe.prefetch(k, pts, feats[1])          # the lane's next frame: its H2D overlaps this replay
+        return pipe.submit_prefetched(k, ticket, out_host[k])
 
     sampler = ClockSampler(local)
     if rank == 0:           # one sampler per job (rank 0's GPU): N concurrent nvidia-smi loops would perturb the run
@@ -307,21 +314,24 @@ def main():
     log('eager (exact mode, host syncs, after capture): %.3f ms/step' % ms_eager)
     L.launch_count(reset=True)
     for attempt in range(3):
-        ms = timed(step_resident, args.steps, args.warmup)
-        over = gn.check()
+        ms = timed(step_resident, args.steps, args.warmup, join=pipe.join)
+        over = pipe.check()
         log('graph replay: %.3f ms/step  overflow=%s' % (ms / args.steps, over))
         # the decision is collective: every rank re-captures if any rank overflowed (keeps the barriers paired)
         if max_over_ranks(1.0 if over else 0.0, world, dist, dev) == 0.0:
             break
         # a frame produced more strided-conv output sites than calibrated: grow the buffers and re-capture
         caps = [int(c * 1.5) // 128 * 128 + 128 for c in caps]
-        gn = GraphedNeck(net, B, npts_cap, img_hw=IMG, calib=kw, capacities=caps, device=dev)
-        gn.load(dev_sets[0][0], dev_sets[0][1][1])
-        gn.capture()
+        pipe = build_pipeline(caps)
         log('re-captured with capacities %s' % caps)
     else:
         raise SystemExit('bench.py: strided-conv capacity overflow persists: %s' % over)
     sampler.stop_flag = True
+    # one frame alone (a single lane, nothing else in flight): the latency of a frame and the denominator of the
+    # dominant kernel's share
+    n_lat = max(5, args.steps // 4)
+    ms_frame = timed(lambda i: pipe.lanes[0](dev_sets[i % F_][0], dev_sets[i % F_][1][1]), n_lat, 2) / n_lat
+    log('single frame in flight: %.3f ms/frame' % ms_frame)
     L.launch_count(reset=True)
     prof = []
     spmod.PROFILE = prof
@@ -329,10 +339,10 @@ def main():
     spmod.PROFILE = None
     own_per_step = L.launch_count(reset=True)      # kernels of one frame (a graph replay launches the same set)
     fps = job_fps(world, B, args.steps, ms)
-    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup), base=7)
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup) // LANES * LANES + LANES, base=7 * LANES, join=pipe.join)
     fps_e2e = job_fps(world, B, args.steps, ms_e2e)
     log('e2e: %.3f ms/step' % (ms_e2e / args.steps))
-    out_bytes = sum(h.numel() * h.element_size() for h in out_host)
+    out_bytes = sum(h.numel() * h.element_size() for h in out_host[0])
 
     stage_ms = None
     if args.stages:
@@ -373,7 +383,9 @@ def main():
                 'unit': 'TFLOP/s', 'frac': useful / (t_ms * 1e-3) / 1e12 / peak, 'traffic': traffic,
                 'traffic_note': 'dram read+write bytes of the largest launch (stage-3 SubM 128->128; algorithmic 170 MB incl. the '
                                 'neighbour table) from profiles/prof_gemm_r01_final.txt', 'launches_per_frame': len(recs),
-                'kernel_ms_per_step': t_ms, 'share_of_step': t_ms / (ms / args.steps),
+                'kernel_ms_per_step': t_ms, 'share_of_step': t_ms / ms_frame,
+                'share_note': 'kernel time of one frame / latency of one frame alone (%.3f ms); with %d frames in flight the '
+                              'steps overlap, so ms_per_step is below that latency' % (ms_frame, LANES),
                 'largest_launch': {'cin': top[3], 'cout': top[4], 'rows': top[5], 'ms': top[0],
                                    'useful_tflops': top[2] / (top[0] * 1e-3) / 1e12, 'issued_tflops': top[1] / (top[0] * 1e-3) / 1e12},
                 'note': 'achieved = sum(2*pairs*Cin*Cout) / sum(CUDA-event time per launch) over the 21 sparse-conv launches of '
@@ -384,11 +396,11 @@ def main():
         cpu = cpu_baseline_subprocess(args)
     if rank == 0:
         line = {'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
+                'ms_per_step': ms / args.steps, 'frame_latency_ms': ms_frame, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
                 'data': 'synthetic',
                 'config': {'workload': 'BASELINE configs[1]: isfusion_0075voxel.py fusion-neck forward, synthetic nuScenes-shaped frame',
                            'points_per_frame': args.points, 'cloud': args.cloud, 'cams': 6, 'img': list(IMG), 'bev': 180,
-                           'batch_per_gpu': B, 'parallelism': 'dp%d (independent replicas, no data-path collective)' % world,
+                           'batch_per_gpu': B, 'frames_in_flight': LANES, 'parallelism': 'dp%d (independent replicas, no data-path collective)' % world,
                            'l2': 'rotating %d distinct resident frames (%.0f MB of inputs) > 126 MB L2' % (F_, F_ * in_bytes / 1e6)},
                 'clocks': sampler.summary(),
                 'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,

@@ -186,18 +186,29 @@ class GraphedNeck:
         self.img_feat.copy_(img_feat1, non_blocking=True)
 
     def capture(self, warmup=3):
-        s = torch.cuda.Stream(device=self.dev)
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._spmod.OVERFLOW_WATCH.clear()
-                self._run()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        self._spmod.OVERFLOW_WATCH.clear()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.outputs = self._run()
+        """warm up and capture on streams owned by THIS graph (main + the two branch streams), so that several
+        GraphedNeck lanes over one set of weights never share a scratch workspace (`_lib.workspace` is keyed by
+        stream) and can be replayed concurrently (FramePipeline)."""
+        if self.__dict__.get('_lane') is None:
+            self._lane = (torch.cuda.Stream(device=self.dev), (torch.cuda.Stream(device=self.dev),
+                                                                torch.cuda.Stream(device=self.dev)))
+        s, sides = self._lane
+        saved = self.net.__dict__.get('_side_streams')
+        self.net.__dict__['_side_streams'] = sides
+        try:
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self._spmod.OVERFLOW_WATCH.clear()
+                    self._run()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._spmod.OVERFLOW_WATCH.clear()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=s):
+                self.outputs = self._run()
+        finally:
+            self.net.__dict__['_side_streams'] = saved
         self.watch = list(self._spmod.OVERFLOW_WATCH)
         self._spmod.OVERFLOW_WATCH.clear()
         return self
@@ -288,3 +299,57 @@ class GraphedNeck:
             rows = [f.features.shape[0] for f in x[1:4]] + [enc.last_out.features.shape[0]]
             best = rows if best is None else [max(a, b) for a, b in zip(best, rows)]
         return [int(r * margin) // 128 * 128 + 128 for r in best]
+
+
+class FramePipeline:
+    """`lanes` GraphedNeck graphs over ONE set of weights, replayed round-robin on their own streams: consecutive
+    frames are in flight together, so the launch-bound tail of frame i (the 200-query decoder, small transformer
+    GEMMs, index kernels that fill a fraction of the 148 SMs) overlaps the sparse encoder of frame i+1.  Each lane
+    owns its static inputs, activations (graph-private pool), scratch workspaces and copy stream; the outputs of a
+    frame stay valid until the same lane is submitted again (`lanes` - 1 frames later)."""
+
+    def __init__(self, net, lanes, *args, **kwargs):
+        self.lanes = [GraphedNeck(net, *args, **kwargs) for _ in range(lanes)]
+        self.streams = [torch.cuda.Stream(device=self.lanes[0].dev) for _ in range(lanes)]
+        self.turn = 0
+
+    def capture(self, points, img_feat1, warmup=3):
+        for g in self.lanes:
+            g.load(points, img_feat1)
+            g.capture(warmup)
+        return self
+
+    def _next(self):
+        k = self.turn
+        self.turn = (k + 1) % len(self.lanes)
+        return k
+
+    def submit(self, points, img_feat1):
+        """resident (device) frame -> (lane, outputs); asynchronous, ordered after the caller's current stream."""
+        k = self._next()
+        st = self.streams[k]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            out = self.lanes[k](points, img_feat1)
+        return k, out
+
+    def prefetch(self, lane, points_host, img_feat1_host):
+        return self.lanes[lane].prefetch(points_host, img_feat1_host)
+
+    def submit_prefetched(self, lane, ticket, out_host=None):
+        st = self.streams[lane]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            return self.lanes[lane].run_prefetched(ticket, out_host)
+
+    def join(self):
+        """the caller's current stream waits for every frame in flight (replays and their D2H copies)."""
+        cur = torch.cuda.current_stream()
+        for g, st in zip(self.lanes, self.streams):
+            cur.wait_stream(st)
+            p = g.__dict__.get('_pipe_state')
+            if p is not None:
+                cur.wait_stream(p['copy'])
+
+    def check(self):
+        return [o for g in self.lanes for o in g.check()]

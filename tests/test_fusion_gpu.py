@@ -263,6 +263,49 @@ def test_sync_free_and_graph_paths_match_exact_path():
         assert torch.equal(a.cpu(), b)
 
 
+def test_two_frames_in_flight_match_exact_path():
+    """FramePipeline: two graph lanes over one set of weights replayed concurrently on their own streams give the same
+    bits as the exact path, for resident frames and through the pipelined host interface."""
+    from isfusion_b200.detector import FramePipeline, GraphedNeck
+    _, net = build_pair(0)
+    B, N = 1, 15000
+    l2i, aug, laug = synth.make_calib(B)
+    feats = [f.cuda() for f in synth.make_img_feats(B)]
+    metas = [dict(input_shape=(256, 704))] * B
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    frames = [[synth.make_points(N - 700 * f, 'S', 30 + f).cuda()] for f in range(3)]
+    want = [net(pts, feats, metas, **kw)[0] for pts in frames]
+    caps = GraphedNeck.calibrate(net, frames, feats, metas, **kw)
+    pipe = FramePipeline(net, 2, B, N + 100, calib=kw, capacities=caps).capture(frames[0], feats[1])
+    got = []
+    for i in range(9):                                   # no host sync between submissions: lanes overlap
+        k, (out, _) = pipe.submit(frames[i % 3], feats[1])
+        with torch.cuda.stream(pipe.streams[k]):
+            got.append([t.clone() for t in out])
+    pipe.join()
+    torch.cuda.synchronize()
+    assert not pipe.check()
+    for i, g in enumerate(got):
+        for a, b in zip(want[i % 3], g):
+            assert torch.equal(a, b), i
+    # host interface: each lane prefetches its own next frame
+    hp = [[p.cpu().pin_memory() for p in pts] for pts in frames]
+    hf = feats[1].cpu().pin_memory()
+    oh = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in want[0]] for _ in range(4)]
+    t = [pipe.prefetch(i % 2, hp[i % 3], hf) for i in range(2)]
+    for i in range(4):
+        k = i % 2
+        ticket = t[k]
+        if i + 2 < 4:
+            t[k] = pipe.prefetch(k, hp[(i + 2) % 3], hf)
+        pipe.submit_prefetched(k, ticket, oh[i])
+    pipe.join()
+    torch.cuda.synchronize()
+    for i in range(4):
+        for a, b in zip(want[i % 3], oh[i]):
+            assert torch.equal(a.cpu(), b), i
+
+
 def test_secondfpn_parity():
     """pts_neck: 1x1 conv + 2x2 deconv + BN + ReLU + concat + [X,Y] transpose on the tcgen05 GEMM."""
     from isfusion_b200.fusion_encoder import SECONDFPN
