@@ -319,6 +319,10 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       uint32_t c0 = chunk_ctr;
       int s = (int)(c0 % STAGES);
       uint32_t use = c0 / STAGES;
+      // byte offsets of this thread's 4 rows for the kernel offset it is currently gathering: re-read from the smem
+      // neighbour tile only when the offset changes (Cin = 128 / 256 spend 2 / 4 chunks on one offset)
+      unsigned offs[BM * 8 / PRODUCERS];
+      int offs_tap = -1;
       for (int i = 0; i < n_act; ++i) {
         const int q = chunk_list[i];
         if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
@@ -335,17 +339,24 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
           int tap, ch;
           if (p.taps == 1) { tap = k >= p.cin ? 1 : 0; ch = k; } else { tap = k >> p.cin_shift; ch = k & (p.cin - 1); }
           const bool tap_ok = tap < p.taps;
-          const int* nrow = nbr_s + tap * BM + rbase;
           const char* src_ch = a_bytes + ch * 2;
+          if (tap != offs_tap) {
+            offs_tap = tap;
+            const int* nrow = nbr_s + tap * BM + rbase;
+#pragma unroll
+            for (int j = 0; j < BM * 8 / PRODUCERS; ++j) {
+              unsigned off = 0xFFFFFFFFu;
+              if (tap_ok) {
+                if (gather) off = (unsigned)nrow[(PRODUCERS / 8) * j];
+                else { const int gr = row0 + rbase + (PRODUCERS / 8) * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
+              }
+              offs[j] = off;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < BM * 8 / PRODUCERS; ++j) {
-            unsigned off = 0xFFFFFFFFu;
-            if (tap_ok) {
-              if (gather) off = (unsigned)nrow[(PRODUCERS / 8) * j];
-              else { const int gr = row0 + rbase + (PRODUCERS / 8) * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
-            }
-            const bool ok = off != 0xFFFFFFFFu;
-            cp_async16(sa + a_thr_off + j * (PRODUCERS / 8) * 128, ok ? src_ch + off : a_bytes, ok ? 16u : 0u);
+            const bool ok = offs[j] != 0xFFFFFFFFu;
+            cp_async16(sa + a_thr_off + j * (PRODUCERS / 8) * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
           }
         }
         // asynchronous arrival: the stage's full barrier is signalled by the hardware when this thread's pieces have
