@@ -201,6 +201,35 @@ struct SmemLayout {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
+// one 32-column block of the accumulator row owned by this thread: TMEM -> registers, BN fold (scale / shift) and the
+// residual row (four 16-byte loads).  Shared by the LayerNorm statistics pass and the output pass, so both see
+// bit-identical values.
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t taddr, int n_base, long long rrow, float (&x)[32]) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float y = __uint_as_float(v[j]);
+    if (p.scale) y *= p.scale[n_base + j];
+    if (p.shift) y += p.shift[n_base + j];
+    x[j] = y;
+  }
+  if (p.residual && rrow >= 0) {
+    const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n_base);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const uint4 u = rp[j4];
+      const __half2* h = (const __half2*)&u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
+      }
+    }
+  }
+}
+
 // CS = thread-block-cluster size.  CS > 1: the CTAs of a cluster walk the same K-chunk sequence on CS consecutive
 // row tiles; each CTA TMA-loads 1/CS of the weight chunk and multicasts it to the whole cluster, so weight
 // traffic from L2 drops by CS; smem stages are recycled cluster-wide (tcgen05.commit multicast on the empty barrier).
@@ -383,49 +412,18 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
         // pass 1 over TMEM: row statistics of (acc*scale+shift+residual)
         float s1 = 0.f, s2 = 0.f;
         for (int cb = 0; cb < BN; cb += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + cb, v);
-          tmem_ld_wait();
+          float x[32];
+          epilogue_block(p, t_lane + cb, n0 + cb, rrow, x);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]);
-            const int n = n0 + cb + j;
-            if (p.scale) x *= p.scale[n];
-            if (p.shift) x += p.shift[n];
-            if (p.residual && rrow >= 0) x += __half2float(p.residual[rrow * p.ldr + n]);
-            s1 += x; s2 += x * x;
-          }
+          for (int j = 0; j < 32; ++j) { s1 += x[j]; s2 += x[j] * x[j]; }
         }
         mean = s1 / BN;
         float var = s2 / BN - mean * mean;
         rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
       }
       for (int cb = cb_lo; cb < cb_hi; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_lane + cb, v);
-        tmem_ld_wait();
         float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float y = __uint_as_float(v[j]);
-          const int n = n0 + cb + j;
-          if (p.scale) y *= p.scale[n];
-          if (p.shift) y += p.shift[n];
-          x[j] = y;
-        }
-        if (p.residual && rrow >= 0) {
-          const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n0 + cb);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 u = rp[j4];
-            const __half2* h = (const __half2*)&u;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __half22float2(h[e]);
-              x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
-            }
-          }
-        }
+        epilogue_block(p, t_lane + cb, n0 + cb, rrow, x);
         if (p.ln_gamma) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * p.ln_gamma[n0 + cb + j] + p.ln_beta[n0 + cb + j];

@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(256) vfe_voxel_prep_kernel(const float* __rest
 }
 
 // layer 1 per point (8 lanes per point, 8 channels per lane), fp32 math, fp16 row of h1 in sorted order
-__global__ void __launch_bounds__(256) vfe_point_layer1_kernel(const float* __restrict__ points, int nfeat,
+__global__ void __launch_bounds__(256, 2) vfe_point_layer1_kernel(const float* __restrict__ points, int nfeat,
                                                                const int* __restrict__ idx_sorted,
                                                                const unsigned long long* __restrict__ uniq,
                                                                const float4* __restrict__ mean,
