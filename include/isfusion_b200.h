@@ -38,7 +38,8 @@ const char* isf_last_error(void);
 /* number of kernels this library has launched since the last reset (bench.py gpu_launches) */
 unsigned long long isf_launch_count(int reset);
 /* runtime options: "gemm_cluster" = 1 | 2 : thread-block-cluster size of the tcgen05 GEMM (CTAs of a cluster
- * share every weight chunk through TMA multicast). */
+ * share every weight chunk through TMA multicast).  "gemm_v2" = 0 | 1 | 2 : opt-in warp-specialised GEMM schedule
+ * (csrc/tc_gemm2.cuh; 1 = sparse-conv launches, 2 = every GEMM); 0 (default) = the validated kernel. */
 int isf_set_option(const char* name, int value);
 
 /* ---- a1: dynamic voxelization -------------------------------------------------

@@ -581,11 +581,15 @@ static inline int dispatch_gemm_cs(const GemmParams& p, int bn, int m_upper, cud
   }
 }
 
+static inline int dispatch_gemm2(const GemmParams& p, int bn, int m_upper, cudaStream_t st);   // tc_gemm2.cuh
+
 static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
   if (p.taps > MAX_TAPS || p.kpad / BK > MAX_CHUNKS) {
     isf_set_error("gemm: taps=%d (max %d) / K chunks=%d (max %d) out of range", p.taps, MAX_TAPS, p.kpad / BK, MAX_CHUNKS);
     return ISF_ERR_UNSUPPORTED;
   }
+  // opt-in warp-specialised variant (isf_set_option("gemm_v2", 1 = sparse-conv launches, 2 = every GEMM))
+  if (::g_isf_gemm_v2 == 2 || (::g_isf_gemm_v2 == 1 && p.nbr != nullptr)) return dispatch_gemm2(p, bn, m_upper, st);
   switch (::g_isf_gemm_cluster) {
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
     default: break;
@@ -596,3 +600,5 @@ static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaSt
 }
 
 }  // namespace tc
+
+#include "tc_gemm2.cuh"
