@@ -178,6 +178,7 @@ struct GemmParams {
   float* out_f32;         // [m, ldo] fp32 (may be nullptr)
   int ldo;
   const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
+  int v2_flags;           // tc_gemm2.cuh only (set by dispatch_gemm2): bit 0 = skip zero-fill copies of rows already zero
 };
 
 constexpr int BM = 128;

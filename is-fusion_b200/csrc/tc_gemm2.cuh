@@ -14,7 +14,10 @@
 //     with a short latency and need fewer stages, so the A ring — the bytes in flight that cover the gather latency —
 //     gets the smem (e.g. BN=256: 6 x 16 KB of A in flight per SM instead of 4 x 16 KB);
 //   * the neighbour ids of tile t+1 are loaded into registers before the gather loop of tile t (their global latency is
-//     hidden), the neighbour tile / chunk list in smem are double-buffered.
+//     hidden), the neighbour tile / chunk list in smem are double-buffered;
+//   * zero-skip (v2_flags bit 0): one warp-level LDGSTS covers 4 rows x 128 B of a stage; when none of the 4 rows has
+//     a neighbour AND the previous use of that stage left zeros in those rows, the copy is skipped (the sparse 32/64-
+//     channel stages fill 15-35 % of the slots, and the LSU issue rate of these copies is what bounds them).
 //
 // Every mbarrier wait is bounded (~2 s) and traps instead of hanging the GPU while the kernel is being brought up.
 #pragma once
@@ -129,6 +132,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm2_kernel(const GemmParams p
       }
     }
     uint32_t ca = 0;                                  // running chunk counter (A stage = ca % SA, B stage = ca % SB)
+    unsigned long long zstate = 0;                    // zero-skip state, 4 bits per A stage (SA <= 16)
+    const bool zskip = (p.v2_flags & 1) != 0;
+    static_assert(SA <= 16, "zero-skip state holds 16 stages");
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm2_kernel(const GemmParams p
       }
       unsigned offs[BM * 8 / V2_PRODUCERS];
       int offs_tap = -1;
+      unsigned miss = 0;      // bit j: none of the 4 rows of this warp's j-th copy has a neighbour at the current offset
       for (int i = 0; i < n_act; ++i, ++ca) {
         const int q = gather ? (int)chunk_list[i] : i;
         const int sa = (int)(ca % SA), sb = (int)(ca % SB);
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm2_kernel(const GemmParams p
         int tap, ch;
         if (p.taps == 1) { tap = k >= p.cin ? 1 : 0; ch = k; } else { tap = k >> p.cin_shift; ch = k & (p.cin - 1); }
         const char* src_ch = a_bytes + ch * 2;
-        if (tap != offs_tap) {
+        if (__any_sync(0xffffffffu, tap != offs_tap)) {        // warp-uniform: the votes below need every lane
           offs_tap = tap;
           const bool tap_ok = tap < p.taps;
           const int* nrow = nbr_s + tap * BM + rbase;
@@ -214,12 +221,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm2_kernel(const GemmParams p
             }
             offs[j] = off;
           }
+          miss = 0;
+#pragma unroll
+          for (int j = 0; j < BM * 8 / V2_PRODUCERS; ++j)
+            if (__all_sync(0xffffffffu, offs[j] == 0xFFFFFFFFu)) miss |= 1u << j;
         }
+        // zstate bit (4*sa + j): the 4 rows of copy j in stage sa currently hold zeros (left there by an all-missing copy)
+        const unsigned zbits = (unsigned)((zstate >> (4 * sa)) & 0xFull);
+        const unsigned skip = zskip ? (miss & zbits) : 0u;
 #pragma unroll
         for (int j = 0; j < BM * 8 / V2_PRODUCERS; ++j) {
+          if (skip & (1u << j)) continue;
           const bool ok = offs[j] != 0xFFFFFFFFu;
           cp_async16(a_dst + a_thr_off + j * (V2_PRODUCERS / 8) * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
         }
+        zstate = (zstate & ~(0xFull << (4 * sa))) | ((unsigned long long)miss << (4 * sa));
         cp_async_mbar_arrive(&a_full[sa]);
       }
     }
@@ -362,7 +378,9 @@ static int launch_gemm2(const GemmParams& p, int m_upper, cudaStream_t st) {
 }
 
 // ring depths: the A ring takes the shared memory the weight ring does not need
-static inline int dispatch_gemm2(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+static inline int dispatch_gemm2(const GemmParams& p0, int bn, int m_upper, cudaStream_t st) {
+  GemmParams p = p0;
+  p.v2_flags = ::g_isf_gemm_v2_zskip ? 1 : 0;
   switch (bn) {
     case 32: return launch_gemm2<32, 10, 3>(p, m_upper, st);      // 160 + 12 KB
     case 64: return launch_gemm2<64, 9, 3>(p, m_upper, st);       // 144 + 24 KB

@@ -37,7 +37,8 @@ def test_v2_dense_gemm_bit_identical(m, k, n):
         L.set_option('gemm_v2', 0)
 
 
-def test_v2_sparse_encoder_bit_identical():
+@pytest.mark.parametrize('zskip', [0, 1])
+def test_v2_sparse_encoder_bit_identical(zskip):
     from isfusion_b200 import _lib as L
     from isfusion_b200.sparse_encoder import SparseEncoder
     from test_spconv_gpu import _rand_tensor
@@ -52,8 +53,10 @@ def test_v2_sparse_encoder_bit_identical():
         L.set_option('gemm_v2', 0)
         ref, _, _ = mod(f, c, 2)
         L.set_option('gemm_v2', 1)
+        L.set_option('gemm_v2_zskip', zskip)
         out, _, _ = mod(f, c, 2)
         torch.cuda.synchronize()
         assert torch.equal(out, ref)
     finally:
         L.set_option('gemm_v2', 0)
+        L.set_option('gemm_v2_zskip', 1)
