@@ -1,8 +1,9 @@
 """Oracle: ISFusionEncoder (HSF + IGF) and SECONDV2 (rows a6, a7, a10-a14 of SURVEY §8).
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED by the reference except the deformable-attention core, which is the
-reference's own pure-PyTorch ``ms_deform_attn_core_pytorch`` (ops/functions/ms_deform_attn_func.py:41-61, pinned
-by ops/test.py:32-60 and tests/golden/msda_ref.npz).  Literal restatement of
+TEST INFRASTRUCTURE ONLY.  PINNED by outputs of the reference's own fusion_encoder.py / second.py / second_fpn.py run
+in the build container (tests/golden/ref_fusion.npz, tests/test_oracle_vs_reference.py); the deformable-attention
+core is the reference's own pure-PyTorch ``ms_deform_attn_core_pytorch`` (ops/functions/ms_deform_attn_func.py:41-61,
+pinned by ops/test.py:32-60 and tests/golden/msda_ref.npz).  Literal restatement of
 mmdet3d/models/middle_encoders/fusion_encoder.py (line numbers cited per function) and
 mmdet3d/models/backbones/second.py:98-239, eval mode, including the quirks of SURVEY Appendix C.
 """

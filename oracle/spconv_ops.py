@@ -1,10 +1,13 @@
 """Oracle: sparse 3-D convolution + SparseEncoder (row a4 of SURVEY §8).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED by the reference: the arithmetic lives
-in un-vendored spconv>=2.0 / mmcv-full 1.3.8-1.4.0 (mmdet3d/ops/spconv/__init__.py:4-12) and the reference's
-tests assert shapes only (tests/test_models/test_common_modules/test_sparse_unet.py:53-137).  The restatement
-follows the vendored spconv-1.x sources as the semantic spec and is cross-checked against a dense F.conv3d on
-the scattered grid (tests/test_oracle_spconv.py).
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The layer the config runs lives in un-vendored spconv>=2.0 /
+mmcv-full 1.3.8-1.4.0 (mmdet3d/ops/spconv/__init__.py:4-12) and the reference's tests assert shapes only
+(tests/test_models/test_common_modules/test_sparse_unet.py:53-137).  PINNED against the vendored spconv-1.x CPU
+generator compiled from the reference header where it lies (oracle/_ref/libref_spconv.so, fixture
+tests/golden/spconv_ref_cpp.npz: output sites and (offset, input, output) pairs identical, gather-mm-scatter over the
+reference's pairs equal) and cross-checked against a dense F.conv3d on the scattered grid (tests/test_oracle_spconv.py);
+the SparseEncoder assembly is pinned by the reference's own sparse_encoder.py / sparse_block.py driving a dense-grid
+conv (tests/golden/ref_sparse.npz).
 """
 import numpy as np
 import torch

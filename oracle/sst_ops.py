@@ -1,6 +1,8 @@
 """Oracle: SST region partition + window attention (rows a8, a9 of SURVEY §8).
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED by the reference (no test touches these files); literal restatement
+TEST INFRASTRUCTURE ONLY.  PINNED by outputs of the reference's own files run in the build container
+(tests/golden/ref_sst.npz: window / slot indices, masks, positional table exact; SSTv2 level output to 2e-4;
+tests/test_oracle_vs_reference.py).  Literal restatement
 of mmdet3d/ops/sst/sst_ops.py:22-287, mmdet3d/models/sst/sst_input_layer_v2.py, sst_basic_block_v2.py and
 mmdet3d/models/backbones/sst_v2.py, with the reference's nondeterministic pieces made canonical:
 inner-window index = stable rank (the CUDA op hands ranks out in atomic order, ingroup_inds_kernel.cu:17-30) and

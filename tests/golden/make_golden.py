@@ -9,6 +9,10 @@ Run in the build container only (needs /root/reference):  python tests/golden/ma
     clouds incl. an adversarial set with coordinates within 1 ulp of cell faces.
   * msda_ref.npz            : ops/functions/ms_deform_attn_func.py:41-61
     (ms_deform_attn_core_pytorch) on the shapes of ops/test.py:20-36 and on the IGF shape.
+  * spconv_ref_cpp.npz      : rulebooks (output sites + (offset, input row, output site) pairs) of the vendored
+    spconv-1.x CPU generator (bevfusion-ops/spconv/include/spconv/geometry.h:144-297) for the four conv shapes
+    of the SparseEncoder.
+(The fixtures made by running the reference's Python modules are in make_golden_ref.py.)
 """
 import importlib.util
 import os
@@ -100,9 +104,51 @@ def msda_ref():
     np.savez_compressed(os.path.join(HERE, 'msda_ref.npz'), **out)
 
 
+SPCONV_CASES = {   # the four rulebook shapes of the SparseEncoder (config:72-82; sparse_encoder.py:76-105)
+    'subm3': dict(ksize=(3, 3, 3), stride=(1, 1, 1), padding=(1, 1, 1), subm=True),
+    'down_p1': dict(ksize=(3, 3, 3), stride=(2, 2, 2), padding=(1, 1, 1), subm=False),
+    'down_p011': dict(ksize=(3, 3, 3), stride=(2, 2, 2), padding=(0, 1, 1), subm=False),
+    'conv_out': dict(ksize=(3, 1, 1), stride=(2, 1, 1), padding=(0, 0, 0), subm=False),
+}
+SPCONV_SHAPE, SPCONV_BATCH = [11, 20, 18], 2
+
+
+def canonical_rulebook(out_indices, pairs_k_in_out, out_shape):
+    """(sorted output coordinates, (k, in_row, rank of the output site) triples sorted) — independent of row order."""
+    oi = np.asarray(out_indices, dtype=np.int64)
+    key = ((oi[:, 0] * out_shape[0] + oi[:, 1]) * out_shape[1] + oi[:, 2]) * out_shape[2] + oi[:, 3]
+    order = np.argsort(key, kind='stable')
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    t = np.asarray(pairs_k_in_out, dtype=np.int64).reshape(-1, 3)
+    t = np.stack([t[:, 0], t[:, 1], rank[t[:, 2]]], 1) if len(t) else t
+    t = t[np.lexsort((t[:, 2], t[:, 1], t[:, 0]))] if len(t) else t
+    return oi[order].astype(np.int32), t.astype(np.int32)
+
+
+def spconv_ref_cpp():
+    """spconv_ref_cpp.npz: rulebooks of the reference's vendored spconv-1.x CPU generator (geometry.h:144-297, compiled by
+    oracle/build_ref.py::build_spconv) on a seeded clustered voxel set, in canonical (order-free) form."""
+    from oracle import build_ref, ref_spconv
+    build_ref.build_spconv()
+    rs = np.random.RandomState(5)
+    cells = SPCONV_BATCH * SPCONV_SHAPE[0] * SPCONV_SHAPE[1] * SPCONV_SHAPE[2]
+    lin = rs.permutation(cells)[:700]
+    s0, s1, s2 = SPCONV_SHAPE
+    idx = np.stack([lin // (s0 * s1 * s2), (lin // (s1 * s2)) % s0, (lin // s2) % s1, lin % s2], 1).astype(np.int32)
+    out = dict(indices=idx)
+    for name, c in SPCONV_CASES.items():
+        oi, oshape, pairs, num = ref_spconv.indice_pairs(idx, SPCONV_BATCH, SPCONV_SHAPE, c['ksize'], c['stride'], c['padding'],
+                                                         (1, 1, 1), c['subm'])
+        trip = [(k, pairs[k, 0, j], pairs[k, 1, j]) for k in range(pairs.shape[0]) for j in range(num[k])]
+        co, ct = canonical_rulebook(oi, trip, oshape)
+        out[name + '_out'], out[name + '_pairs'], out[name + '_shape'] = co, ct, np.asarray(oshape, np.int32)
+        print(name, 'sites', len(co), 'pairs', len(ct), 'out shape', oshape)
+    np.savez_compressed(os.path.join(HERE, 'spconv_ref_cpp.npz'), **out)
+
+
 if __name__ == '__main__':
-    voxel_generator_kat()
-    voxel_ref_cpp()
-    msda_ref()
+    for name in (sys.argv[1:] or ['voxel_generator_kat', 'voxel_ref_cpp', 'msda_ref', 'spconv_ref_cpp']):
+        globals()[name]()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

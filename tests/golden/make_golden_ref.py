@@ -1,0 +1,122 @@
+"""Golden fixtures produced BY THE REFERENCE'S OWN PYTHON FILES, executed unmodified from /root/reference.
+
+Build container only:  python tests/golden/make_golden_ref.py      (writes tests/golden/ref_*.npz)
+
+tests/golden/ref_shim.py explains what is the reference's code (every module on the path) and what is a stand-in
+(absent third-party pieces: mmcv builders, a dense-formulation sparse conv, the PyTorch statement of the MSDA
+kernel from the reference's ops/functions/ms_deform_attn_func.py, the TorchEx in-group rank).  Weights and the
+large inputs are regenerated on both sides by tests/golden/golden_common.py, so the fixtures hold outputs only.
+
+Fixtures (checked by tests/test_oracle_vs_reference.py against oracle/):
+  ref_fusion.npz  : ISFusionEncoder.forward + SECONDV2 stages (fusion_encoder.py:1152-1189, second.py:200-230) on
+                    a 24x24 BEV, B = 2: both output maps, the instance heat-map, img_fv_to_bev (every 8th channel),
+                    conv_fusion output (every 8th channel); SECONDFPN on the two maps (every 8th channel).
+  ref_sst.npz     : SSTInputLayerV2 (shuffle off) window/slot indices, positional embedding, key mask for both
+                    shifts, and SSTv2 level-0 output on those tokens.
+  ref_vfe.npz     : DynamicVFE.forward (voxel_encoder.py:452-547) features + coordinates; DynamicScatter mean.
+  ref_sparse.npz  : SparseEncoder.forward (sparse_encoder.py:107-138) dense output [B,512,H/8,W/8] and the
+                    active-site count after every stage.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+warnings.filterwarnings('ignore')
+
+import golden_common as gc  # noqa: E402
+import ref_shim  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@torch.no_grad()
+def fusion(R):
+    enc = gc.fill_state(R.ISFusionEncoder(**gc.fusion_cfg()), 1).eval()
+    bb = gc.fill_state(R.SECONDV2(**gc.backbone_cfg()), 2).eval()
+    fpn = gc.fill_state(R.SECONDFPN(in_channels=[128, 256], out_channels=[256, 256], upsample_strides=[1, 2],
+                                    norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01),
+                                    upsample_cfg=dict(type='deconv', bias=False), use_conv_for_no_stride=True), 3).eval()
+    inp = gc.fusion_inputs()
+    bs = 2
+    pts_metas = dict(pillars=inp['pillars'], pillars_num_points=None, pillar_coors=inp['pillar_coors'], pts=None, pillar_size=None)
+    kw = dict(pts_metas=pts_metas, img_metas=inp['img_metas'], lidar2img=inp['lidar2img'],
+              img_aug_matrix=inp['img_aug_matrix'], lidar_aug_matrix=inp['lidar_aug_matrix'])
+    img_bev = enc.img_fv_to_bev([inp['img_feats'][1]], bs, **kw)
+    bev = enc.conv_fusion(torch.cat([img_bev, inp['lidar_feats']], 1))
+    torch.manual_seed(0)                                       # the reference shuffles tokens (randperm) in eval too
+    feats, hm = enc(inp['img_feats'], inp['lidar_feats'], bs, pts_backbone=bb, **kw)
+    neck = fpn(feats)[0]
+    np.savez_compressed(os.path.join(HERE, 'ref_fusion.npz'), feat0=_np(feats[0]), feat1=_np(feats[1]), heatmap=_np(hm),
+                        img_bev_c8=_np(img_bev[:, ::8]), bev_c8=_np(bev[:, ::8]), neck_c8=_np(neck[:, ::8]),
+                        keys_enc=np.array(sorted(enc.state_dict().keys())), keys_bb=np.array(sorted(bb.state_dict().keys())),
+                        keys_fpn=np.array(sorted(fpn.state_dict().keys())))
+    print('fusion:', [tuple(f.shape) for f in feats], tuple(hm.shape), 'neck', tuple(neck.shape),
+          'nonzero img_bev cells', int((img_bev.abs().sum(1) > 0).sum()))
+
+
+@torch.no_grad()
+def sst(R):
+    cfg = gc.fusion_cfg()
+    d = 128
+    layer = R.SSTInputLayerV2(window_shape=cfg['region_shape'][0], sparse_shape=cfg['grid_size'][0], shuffle_voxels=False,
+                              drop_info=cfg['region_drop_info'][0], pos_temperature=1000, normalize_pos=False, pos_embed=d).eval()
+    net = gc.fill_state(R.SSTv2(d_model=[d] * 4, nhead=[8] * 4, num_blocks=1, dim_feedforward=[d] * 4,
+                                output_shape=cfg['grid_size'][0][:2], in_channel=d), 4).eval()
+    bs, g = 2, gc.BEV
+    feats = gc.rand('sst_tokens', (bs * g * g, d), 0)
+    b, y, x = torch.meshgrid(torch.arange(bs), torch.arange(g), torch.arange(g), indexing='ij')
+    # the encoder's grid coordinates are (b, 0, x-index, y-index) of a meshgrid: any (b,z,y,x) rows do
+    coors = torch.stack([b, torch.zeros_like(b), y, x], -1).reshape(-1, 4).int()
+    info = layer(feats, coors, bs)
+    out = {}
+    for i in range(2):
+        out['flat2win_%d' % i] = _np(info['flat2win_inds_shift%d' % i][0][0])
+        out['pos_%d_c4' % i] = _np(info['pos_dict_shift%d' % i][0][..., ::4])
+        out['mask_%d' % i] = _np(info['key_mask_shift%d' % i][0])
+        out['batch_win_inds_%d' % i] = _np(info['batch_win_inds_shift%d' % i])
+        out['coors_in_win_%d' % i] = _np(info['coors_in_win_shift%d' % i])
+    y0 = net(info)[0]
+    out['sst_out'] = _np(y0)
+    out['keys'] = np.array(sorted(net.state_dict().keys()))
+    np.savez_compressed(os.path.join(HERE, 'ref_sst.npz'), **out)
+    print('sst:', {k: v.shape for k, v in out.items() if k != 'keys'})
+
+
+@torch.no_grad()
+def vfe(R):
+    net = gc.fill_state(R.DynamicVFE(**gc.vfe_cfg()), 5).eval()
+    pts, coors = gc.vfe_inputs()
+    f, c = net(pts, coors)
+    sc = R.DynamicScatter(gc.VFE_VOXEL, gc.VFE_RANGE, True)
+    fm, cm = sc(pts, coors)
+    np.savez_compressed(os.path.join(HERE, 'ref_vfe.npz'), feats=_np(f), coors=_np(c), mean_feats=_np(fm), mean_coors=_np(cm),
+                        keys=np.array(sorted(net.state_dict().keys())))
+    print('vfe:', tuple(f.shape), tuple(c.shape), 'in-range points', int((coors[:, 1] >= 0).sum()))
+
+
+@torch.no_grad()
+def sparse(R):
+    net = gc.fill_state(R.SparseEncoder(**gc.sparse_cfg()), 6).eval()
+    feats, coors = gc.sparse_inputs()
+    out, enc_feats, _ = net(feats, coors, 2)
+    counts = np.array([e.indices.shape[0] for e in enc_feats])
+    np.savez_compressed(os.path.join(HERE, 'ref_sparse.npz'), out=_np(out), stage_voxels=counts,
+                        stage1_coors=_np(enc_feats[1].indices), keys=np.array(sorted(net.state_dict().keys())))
+    print('sparse:', tuple(out.shape), 'active sites per stage', counts.tolist(), 'nonzero', int((out != 0).sum()))
+
+
+if __name__ == '__main__':
+    R = ref_shim.install()
+    which = sys.argv[1:] or ['fusion', 'sst', 'vfe', 'sparse']
+    for w in which:
+        globals()[w](R)
+    for f in sorted(os.listdir(HERE)):
+        if f.startswith('ref_') and f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')

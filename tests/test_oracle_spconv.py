@@ -60,3 +60,72 @@ def test_sparse_encoder_shapes():
     assert [f.spatial_shape for f in feats] == [[41, 64, 64], [21, 32, 32], [11, 16, 16], [5, 8, 8], [5, 8, 8]]
     assert set(k for k in enc.state_dict()) >= {'conv_input.0.weight', 'encoder_layers.encoder_layer1.0.conv1.weight',
                                                 'encoder_layers.encoder_layer1.2.0.weight', 'conv_out.1.running_mean'}
+
+
+# ---------------------------------------------------------------- pinned by the reference's vendored spconv-1.x C++
+def _oracle_canonical(idx, shape, batch, case):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden as mg
+    oi, oshape, nbr = so.get_indice_pairs(torch.from_numpy(idx), batch, shape, case['ksize'], case['stride'], case['padding'],
+                                          (1, 1, 1), case['subm'])
+    k, o = torch.nonzero(nbr >= 0, as_tuple=True)
+    trip = torch.stack([k, nbr[k, o], o], 1).numpy()
+    return mg.canonical_rulebook(oi.numpy(), trip, oshape) + (list(oshape),)
+
+
+def test_rulebook_matches_reference_spconv_cpp_golden():
+    """Output sites and (kernel offset, input row, output site) pairs of oracle.get_indice_pairs == the reference's
+    getIndicePairsConv / getIndicePairsSubM (geometry.h:144-297), for the four conv shapes of the encoder.  Row ORDER
+    is implementation-defined in the reference (first-touch on CPU, sorted-unique on GPU), so both are canonicalised."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden as mg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'spconv_ref_cpp.npz'))
+    for name, case in mg.SPCONV_CASES.items():
+        co, ct, oshape = _oracle_canonical(g['indices'], mg.SPCONV_SHAPE, mg.SPCONV_BATCH, case)
+        assert oshape == g[name + '_shape'].tolist(), name
+        assert np.array_equal(co, g[name + '_out']), name
+        assert np.array_equal(ct, g[name + '_pairs']), name
+
+
+def test_rulebook_and_conv_match_reference_spconv_cpp_live():
+    """Same check on fresh seeds against oracle/_ref/libref_spconv.so (built from the reference header where it lies),
+    plus the arithmetic: gather -> mm -> scatter-add over the REFERENCE's pairs == oracle.indice_conv."""
+    import numpy as np
+    from oracle import ref_spconv
+    if not ref_spconv.available():
+        pytest.skip('oracle/_ref/libref_spconv.so not built (needs /root/reference)')
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import make_golden as mg
+    shape, batch = [13, 16, 22], 3
+    for seed in (1, 2):
+        x = _rand_tensor(shape, 900, 6, batch, seed)
+        idx = x.indices.numpy()
+        for name, case in mg.SPCONV_CASES.items():
+            oi, oshape, pairs, num = ref_spconv.indice_pairs(idx, batch, shape, case['ksize'], case['stride'], case['padding'],
+                                                             (1, 1, 1), case['subm'])
+            trip = [(k, pairs[k, 0, j], pairs[k, 1, j]) for k in range(pairs.shape[0]) for j in range(num[k])]
+            rco, rct = mg.canonical_rulebook(oi, trip, oshape)
+            co, ct, osh = _oracle_canonical(idx, shape, batch, case)
+            assert osh == oshape and np.array_equal(co, rco) and np.array_equal(ct, rct), (seed, name)
+            # arithmetic over the reference's own pairs (spconv_ops.h:260-361), rows then sorted like the oracle's
+            conv = (so.SubMConv3d if case['subm'] else so.SparseConv3d)(6, 10, case['ksize'], stride=case['stride'],
+                                                                          padding=case['padding'], bias=False)
+            w = conv.weight.detach().reshape(-1, 6, 10)
+            ref = torch.zeros(len(oi), 10)
+            for k in range(pairs.shape[0]):
+                n = int(num[k])
+                if n:
+                    ref.index_add_(0, torch.from_numpy(pairs[k, 1, :n].astype(np.int64)),
+                                   x.features[torch.from_numpy(pairs[k, 0, :n].astype(np.int64))] @ w[k])
+            out = conv(x)
+            key = so._lin(torch.from_numpy(np.asarray(oi)), oshape)
+            okey = so._lin(out.indices, out.spatial_shape)
+            assert torch.equal(torch.sort(key).values, torch.sort(okey).values)
+            assert torch.allclose(ref[torch.argsort(key)], out.features.detach()[torch.argsort(okey)], atol=1e-5), (seed, name)

@@ -1,0 +1,137 @@
+"""The oracle pinned by OUTPUTS OF THE REFERENCE ITSELF (CPU, no GPU needed).
+
+tests/golden/ref_*.npz were produced by tests/golden/make_golden_ref.py, which executes the reference's own Python
+files for the path (fusion_encoder.py, sst_input_layer_v2.py, sst_ops.py, sst_v2.py, sst_basic_block_v2.py,
+second.py, second_fpn.py, voxel_encoder.py, sparse_encoder.py, sparse_block.py, scatter_points.py, norm.py)
+unmodified from /root/reference (tests/golden/ref_shim.py lists the third-party stand-ins).  Here the oracle gets the
+same name-keyed weights and inputs (tests/golden/golden_common.py) and must reproduce those outputs; the tests also
+prove that the oracle's state_dict keys equal the reference modules' keys.
+
+Tolerances: both sides are fp32 CPU; differences come from summation order only (the reference shuffles the SST
+tokens with randperm, conv/matmul blocking) -> 2e-4 of the tensor's max magnitude; index outputs exact.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+import golden_common as gc  # noqa: E402
+
+from oracle import fusion_ops, spconv_ops, sst_ops, voxel_ops  # noqa: E402
+
+TOL = 2e-4
+
+
+def _load(name):
+    return np.load(os.path.join(HERE, 'golden', name))
+
+
+def _close(a, b, what, tol=TOL):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-6)
+    assert err < tol, '%s: max err %.3g of max |ref|' % (what, err)
+    return err
+
+
+def _keys(module, g, field):
+    assert sorted(module.state_dict().keys()) == list(g[field]), field
+
+
+@pytest.fixture(scope='module')
+def fusion_run():
+    g = _load('ref_fusion.npz')
+    enc = gc.fill_state(fusion_ops.ISFusionEncoder(**gc.fusion_cfg()), 1).eval()
+    bb = gc.fill_state(fusion_ops.SECONDV2(**gc.backbone_cfg()), 2).eval()
+    fpn = gc.fill_state(fusion_ops.SECONDFPN(in_channels=[128, 256], out_channels=[256, 256], upsample_strides=[1, 2],
+                                             norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01),
+                                             upsample_cfg=dict(type='deconv', bias=False), use_conv_for_no_stride=True), 3).eval()
+    inp = gc.fusion_inputs()
+    pts_metas = dict(pillars=inp['pillars'], pillars_num_points=None, pillar_coors=inp['pillar_coors'], pts=None, pillar_size=None)
+    torch.manual_seed(1)      # a DIFFERENT token shuffle than the generator's: the result must not depend on it
+    feats, hm = enc(inp['img_feats'], inp['lidar_feats'], 2, pts_metas=pts_metas, img_metas=inp['img_metas'],
+                    pts_backbone=bb, lidar2img=inp['lidar2img'], img_aug_matrix=inp['img_aug_matrix'],
+                    lidar_aug_matrix=inp['lidar_aug_matrix'])
+    return g, enc, bb, fpn, feats, hm
+
+
+def test_state_dict_keys_equal_the_reference_modules(fusion_run):
+    g, enc, bb, fpn, _, _ = fusion_run
+    _keys(enc, g, 'keys_enc')
+    _keys(bb, g, 'keys_bb')
+    _keys(fpn, g, 'keys_fpn')
+
+
+def test_camera_to_bev_and_conv_fusion_match_reference(fusion_run):
+    g, enc, _, _, _, _ = fusion_run
+    _close(enc._dbg_fwd['img_bev'][:, ::8], g['img_bev_c8'], 'img_fv_to_bev (a6)')
+    _close(enc._dbg_fwd['bev'][:, ::8], g['bev_c8'], 'conv_fusion (a7)')
+
+
+def test_instance_heatmap_matches_reference(fusion_run):
+    g, _, _, _, _, hm = fusion_run
+    _close(hm, g['heatmap'], 'ins_heatmap (a10)')
+
+
+def test_fusion_encoder_outputs_match_reference(fusion_run):
+    """a7-a14 end to end: SST level 0 -> instance-guided fusion -> SECONDV2 stage1 -> SST level 1 -> stage2."""
+    g, _, _, _, feats, _ = fusion_run
+    _close(feats[0], g['feat0'], 'feat_0 [B,128,G,G]')
+    _close(feats[1], g['feat1'], 'feat_1 [B,256,G/2,G/2]')
+
+
+def test_second_fpn_matches_reference(fusion_run):
+    g, _, _, fpn, feats, _ = fusion_run
+    _close(fpn(feats)[0][:, ::8], g['neck_c8'], 'SECONDFPN')
+
+
+def test_sst_input_layer_and_level_match_reference():
+    g = _load('ref_sst.npz')
+    cfg = gc.fusion_cfg()
+    d, bs, n = 128, 2, gc.BEV
+    layer = sst_ops.SSTInputLayerV2(window_shape=cfg['region_shape'][0], sparse_shape=cfg['grid_size'][0], shuffle_voxels=False,
+                                    drop_info=cfg['region_drop_info'][0], pos_temperature=1000, normalize_pos=False, pos_embed=d)
+    net = gc.fill_state(sst_ops.SSTv2(d_model=[d] * 4, nhead=[8] * 4, num_blocks=1, dim_feedforward=[d] * 4,
+                                      output_shape=cfg['grid_size'][0][:2], in_channel=d), 4).eval()
+    _keys(net, g, 'keys')
+    feats = gc.rand('sst_tokens', (bs * n * n, d), 0)
+    b, y, x = torch.meshgrid(torch.arange(bs), torch.arange(n), torch.arange(n), indexing='ij')
+    coors = torch.stack([b, torch.zeros_like(b), y, x], -1).reshape(-1, 4).int()
+    info = layer(feats, coors, bs)
+    for i in range(2):
+        assert np.array_equal(info['batch_win_inds_shift%d' % i].numpy(), g['batch_win_inds_%d' % i]), i
+        assert np.array_equal(info['coors_in_win_shift%d' % i].numpy(), g['coors_in_win_%d' % i]), i
+        assert np.array_equal(info['flat2win_inds_shift%d' % i][0][0].numpy(), g['flat2win_%d' % i]), i
+        assert np.array_equal(info['key_mask_shift%d' % i][0].numpy(), g['mask_%d' % i]), i
+        _close(info['pos_dict_shift%d' % i][0][..., ::4], g['pos_%d_c4' % i], 'pos embed shift %d' % i, 1e-6)
+    _close(net(info)[0], g['sst_out'], 'SSTv2 level 0 (a9)')
+
+
+def test_dynamic_vfe_and_scatter_match_reference():
+    g = _load('ref_vfe.npz')
+    net = gc.fill_state(voxel_ops.DynamicVFE(**gc.vfe_cfg()), 5).eval()
+    _keys(net, g, 'keys')
+    pts, coors = gc.vfe_inputs()
+    f, c = net(pts, coors)
+    assert np.array_equal(c.numpy(), g['coors'])
+    _close(f, g['feats'], 'DynamicVFE (a3)', 1e-5)
+    fm, cm = voxel_ops.DynamicScatter(gc.VFE_VOXEL, gc.VFE_RANGE, True)(pts, coors)
+    assert np.array_equal(cm.numpy(), g['mean_coors'])
+    _close(fm, g['mean_feats'], 'DynamicScatter mean (a2)', 1e-6)
+
+
+def test_sparse_encoder_matches_reference_driving_a_dense_conv():
+    """The reference's SparseEncoder / SparseBasicBlock / make_sparse_convmodule code driving a dense-grid conv3d
+    formulation of the sparse layers against the oracle's rulebook formulation (a4)."""
+    g = _load('ref_sparse.npz')
+    net = gc.fill_state(spconv_ops.SparseEncoder(**gc.sparse_cfg()), 6).eval()
+    _keys(net, g, 'keys')
+    feats, coors = gc.sparse_inputs()
+    out, enc, _ = net(feats, coors, 2)
+    assert [e.indices.shape[0] for e in enc] == g['stage_voxels'].tolist()
+    assert np.array_equal(enc[1].indices.numpy(), g['stage1_coors'])
+    _close(out, g['out'], 'SparseEncoder dense output')
