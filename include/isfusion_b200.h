@@ -195,6 +195,22 @@ int isf_spconv_implicit_gemm(const void* feats_in, int cin, const void* w_packed
                              const int* nbr, long long nbr_stride, int taps, int v_out, const int* v_out_dev,
                              const float* scale, const float* shift, const void* residual, int ldr, int relu,
                              void* out_f16, int ldo, void* stream);
+/* Tile order (opt-in, no reference counterpart: spconv's per-offset pair lists — spconv_ops.h:260-361 — never
+ * multiply a missing neighbour; the output-stationary tiles here do, unless rows with the same neighbour pattern
+ * share a tile).  isf_spconv_tile_order: stable sort of the rows of a neighbour table by their kernel-offset
+ * occupancy mask (inside chunks of 2^chunk_log2 consecutive rows; >= 31 = one global sort) -> permuted table
+ * `nbr_out` [taps, nbr_stride] + `row_perm` [nbr_stride] (tile slot -> storage row, -1 beyond the valid rows).
+ * isf_spconv_implicit_gemm_ordered: isf_spconv_implicit_gemm over such a table; slot i reads residual row
+ * row_perm[i] and writes output row row_perm[i], so `out` is bit-identical to the unordered call.
+ * ksize = host int[3] (kD,kH,kW) with kD*kH*kW == taps <= 27.  Workspace: isf_spconv_tile_order_workspace_size(v). */
+int isf_spconv_tile_order_workspace_size(int v, size_t* bytes);
+int isf_spconv_tile_order_bits(const int* ksize, int taps, unsigned char* pos);   /* host-only: key bit of every tap */
+int isf_spconv_tile_order(const int* nbr, long long nbr_stride, int taps, const int* ksize, int v, const int* v_dev,
+                          int chunk_log2, int* nbr_out, int* row_perm, void* workspace, size_t ws_bytes, void* stream);
+int isf_spconv_implicit_gemm_ordered(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,
+                                     const int* nbr_ordered, long long nbr_stride, int taps, int v_out,
+                                     const int* v_out_dev, const int* row_perm, const float* scale, const float* shift,
+                                     const void* residual, int ldr, int relu, void* out_f16, int ldo, void* stream);
 int isf_sparse_to_dense(const void* feats, const int* indices, int v, int c, int batch, int D, int H, int W,
                         void* out, void* stream);
 int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, const int* v_dev, int c, int D, int H, int W,

@@ -529,6 +529,156 @@ extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const voi
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tile order (opt-in): which rows share a 128-row tile of the implicit GEMM.
+//
+// The kernel skips a kernel offset for a whole tile when none of the tile's rows has a neighbour there, and
+// zero-fills the slot of every row that lacks one otherwise.  With the rows taken in storage order (ascending
+// (b,z,y,x)) a tile of a LiDAR frame touches ~25 of the 27 offsets while a row has 4-20 neighbours: 40-75 % of the
+// gathered slots and of the issued MMAs are zeros (scripts/tile_occupancy.py).  Spatial re-blocking does not
+// change that; grouping rows by their NEIGHBOUR PATTERN does: rows are stably sorted by their 27-bit occupancy
+// mask (rarest kernel offsets = most significant bits), optionally inside chunks of 2^chunk_log2 consecutive rows
+// (keeps the gathers of a tile inside a bounded window of the feature matrix).  Storage order is untouched: the
+// kernel reads the permuted neighbour table and scatters / gathers its epilogue rows through row_perm
+// (GemmParams::out_rows / res_rows), so results are bit-identical to the unordered launch.
+// ------------------------------------------------------------------------------------------------
+struct TapBits { unsigned char pos[32]; };
+
+__global__ void __launch_bounds__(256) tile_order_keys_kernel(const int* __restrict__ nbr, long long nbr_stride, int taps,
+                                                              int v, const int* __restrict__ v_dev, int chunk_shift,
+                                                              int invalid_bit, TapBits tb,
+                                                              unsigned long long* __restrict__ keys, int* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v) return;
+  const int n = v_dev ? min(*v_dev, v) : v;
+  unsigned long long key;
+  if (i < n) {
+    unsigned int mask = 0;
+    for (int k = 0; k < taps; ++k)
+      if (nbr[(long long)k * nbr_stride + i] >= 0) mask |= 1u << tb.pos[k];
+    key = ((unsigned long long)(chunk_shift < 31 ? (i >> chunk_shift) : 0) << taps) | mask;
+  } else {
+    key = 1ull << invalid_bit;          // capacity rows beyond the device-side count sort last
+  }
+  keys[i] = key;
+  rows[i] = i;
+}
+
+__global__ void __launch_bounds__(256) tile_order_apply_kernel(const int* __restrict__ nbr, long long nbr_stride, int taps,
+                                                               int v, const int* __restrict__ v_dev,
+                                                               const int* __restrict__ rows_sorted, int* __restrict__ nbr_out,
+                                                               int* __restrict__ row_perm) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbr_stride) return;
+  const int n = v_dev ? min(*v_dev, v) : v;
+  const int r = i < n ? rows_sorted[i] : -1;
+  row_perm[i] = r;
+  for (int k = 0; k < taps; ++k)
+    nbr_out[(long long)k * nbr_stride + i] = r >= 0 ? nbr[(long long)k * nbr_stride + r] : -1;
+}
+
+// significance of the taps in the sort key: rank by (moves in z, in-plane L1 distance, moves in y), ties by tap index;
+// pos[k] = bit of tap k (taps-1 = most significant = sorts first)
+static void tile_order_bits(const int* ksize, int taps, unsigned char* pos) {
+  int order[27], score[27];
+  for (int k = 0; k < taps; ++k) {
+    const int kx = k % ksize[2], ky = (k / ksize[2]) % ksize[1], kz = k / (ksize[2] * ksize[1]);
+    const int dz = abs(kz - ksize[0] / 2), dy = abs(ky - ksize[1] / 2), dx = abs(kx - ksize[2] / 2);
+    score[k] = (dz * 16 + (dy + dx)) * 4 + dy;
+    order[k] = k;
+  }
+  for (int a = 1; a < taps; ++a)                       // insertion sort, descending score, stable
+    for (int b = a; b > 0 && score[order[b]] > score[order[b - 1]]; --b) { int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
+  for (int rank = 0; rank < taps; ++rank) pos[order[rank]] = (unsigned char)(taps - 1 - rank);
+}
+
+// host-only: the bit position of every tap in the sort key (for tests and for CPU models of the order)
+extern "C" int isf_spconv_tile_order_bits(const int* ksize, int taps, unsigned char* pos) {
+  ISF_CHECK_ARG(ksize && pos && taps >= 1 && taps <= 27 && ksize[0] * ksize[1] * ksize[2] == taps);
+  tile_order_bits(ksize, taps, pos);
+  return ISF_OK;
+}
+
+static void tile_order_carve(IsfArena& A, int v, unsigned long long** k0, unsigned long long** k1, int** r0, int** r1,
+                             char** cub_tmp, size_t* cub_bytes) {
+  *k0 = A.take<unsigned long long>(v);
+  *k1 = A.take<unsigned long long>(v);
+  *r0 = A.take<int>(v);
+  *r1 = A.take<int>(v);
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
+                                  (int*)nullptr, v);
+  *cub_bytes = b;
+  *cub_tmp = A.take<char>(b);
+}
+
+extern "C" int isf_spconv_tile_order_workspace_size(int v, size_t* bytes) {
+  ISF_CHECK_ARG(v >= 0 && bytes);
+  IsfArena A(nullptr, 0);
+  unsigned long long *k0, *k1; int *r0, *r1; char* tmp; size_t cb;
+  tile_order_carve(A, v > 0 ? v : 1, &k0, &k1, &r0, &r1, &tmp, &cb);
+  *bytes = A.off;
+  return ISF_OK;
+}
+
+// nbr [taps, nbr_stride] -> nbr_out [taps, nbr_stride] (rows regrouped) + row_perm [nbr_stride] (tile slot -> storage
+// row, -1 beyond the valid rows).  ksize = the kernel's (kD,kH,kW) (taps = kD*kH*kW): it fixes the significance of
+// the mask bits (offsets that move in z, then the far in-plane ones, sort first).  chunk_log2 >= 31 = one global sort.
+extern "C" int isf_spconv_tile_order(const int* nbr, long long nbr_stride, int taps, const int* ksize, int v,
+                                     const int* v_dev, int chunk_log2, int* nbr_out, int* row_perm, void* workspace,
+                                     size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(nbr && nbr_out && row_perm && ksize && nbr != nbr_out);
+  ISF_CHECK_ARG(taps >= 1 && taps <= 27 && ksize[0] * ksize[1] * ksize[2] == taps && v >= 0 && nbr_stride >= v);
+  ISF_CHECK_ARG(chunk_log2 >= 7);                      // a chunk holds at least one 128-row tile
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vv = v > 0 ? v : 1;
+  IsfArena A(workspace, ws_bytes);
+  unsigned long long *k0, *k1; int *r0, *r1; char* tmp; size_t cb;
+  tile_order_carve(A, vv, &k0, &k1, &r0, &r1, &tmp, &cb);
+  if (!A.ok || !workspace) { isf_set_error("isf_spconv_tile_order: workspace too small"); return ISF_ERR_WORKSPACE; }
+  TapBits tb{};
+  tile_order_bits(ksize, taps, tb.pos);
+  int chunk_bits = 0;
+  if (chunk_log2 < 31) while (((long long)(vv - 1) >> chunk_log2) >> chunk_bits) ++chunk_bits;
+  const int invalid_bit = taps + chunk_bits;
+  if (v > 0) {
+    tile_order_keys_kernel<<<isf_cdiv(v, 256), 256, 0, st>>>(nbr, nbr_stride, taps, v, v_dev, chunk_log2, invalid_bit, tb, k0, r0);
+    ISF_LAUNCH_CHECK();
+    ISF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, cb, k0, k1, r0, r1, v, 0, invalid_bit + 1, st));
+  }
+  tile_order_apply_kernel<<<(int)((nbr_stride + 255) / 256), 256, 0, st>>>(nbr, nbr_stride, taps, v, v_dev, r1, nbr_out, row_perm);
+  ISF_LAUNCH_CHECK();
+  isf_count_launch(v > 0 ? 4 + (invalid_bit + 1 + 7) / 8 : 1);   // keys + CUB (histogram, scan, one onesweep per 8 key bits) + apply
+  return ISF_OK;
+}
+
+// implicit GEMM over a tile-ordered neighbour table: tile slot i computes storage row row_perm[i]
+extern "C" int isf_spconv_implicit_gemm_ordered(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,
+                                                const int* nbr_ordered, long long nbr_stride, int taps, int v_out,
+                                                const int* v_out_dev, const int* row_perm, const float* scale,
+                                                const float* shift, const void* residual, int ldr, int relu,
+                                                void* out_f16, int ldo, void* stream) {
+  ISF_CHECK_ARG(v_out >= 0 && cin % 8 == 0 && cin >= 8 && taps >= 1 && kpad % 64 == 0 && kpad >= taps * cin);
+  ISF_CHECK_ARG(cout == 32 || cout == 64 || cout == 128 || cout == 256);
+  ISF_CHECK_ARG((cin & (cin - 1)) == 0);
+  if (v_out == 0) return ISF_OK;
+  ISF_CHECK_ARG(feats_in && w_packed && nbr_ordered && row_perm && out_f16 && ldo % 8 == 0);
+  tc::GemmParams p{};
+  p.A = (const __half*)feats_in; p.W = (const __half*)w_packed; p.nbr = nbr_ordered; p.nbr_stride = nbr_stride;
+  p.m_dev = v_out_dev; p.m = v_out; p.cin = cin; p.taps = taps;
+  p.cin_shift = 0;
+  while ((1 << p.cin_shift) < cin) ++p.cin_shift;
+  p.kpad = kpad; p.n_total = cout;
+  p.scale = scale; p.shift = shift; p.residual = (const __half*)residual; p.ldr = ldr;
+  p.res_rows = residual ? row_perm : nullptr;
+  p.out_rows = row_perm;
+  p.act = relu ? tc::ACT_RELU : tc::ACT_NONE;
+  p.out = (__half*)out_f16; p.ldo = ldo;
+  int rc = tc::dispatch_gemm(p, cout, v_out, (cudaStream_t)stream);
+  isf_count_launch(1);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // SparseConvTensor.dense()  (structure.py:49-59)  -> [B, C, D, H, W] fp16, zero filled here
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) to_dense_kernel(const __half* __restrict__ feats, const int* __restrict__ idx,

@@ -7,6 +7,7 @@ mmdet3d/ops/sparse_block.py:8-20) with weights in the spconv1/mmcv layout (kD,kH
 checkpoints (Cout,kD,kH,kW,Cin) are accepted on load (write_spconv2.py:62-94).
 """
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -76,13 +77,38 @@ class SparseConvTensor:
 
 class Rulebook:
     """output indices + neighbour table of one (coordinate set, kernel geometry)."""
-    __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'num_dev', 'pairs')
+    __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'num_dev', 'pairs', 'nbr_ordered',
+                 'row_perm')
 
     def __init__(self, out_indices, out_shape, nbr, nbr_stride, taps, num_out, num_dev=None):
         self.out_indices, self.out_shape, self.nbr = out_indices, out_shape, nbr
         self.nbr_stride, self.taps, self.num_out = nbr_stride, taps, num_out      # num_out = rows (capacity)
         self.num_dev = num_dev                                                    # device-side valid-row count
         self.pairs = None
+        self.nbr_ordered = self.row_perm = None     # tile order (TILE_ORDER): regrouped table + tile slot -> storage row
+
+
+# Opt-in tile order of the implicit GEMM (csrc/spconv.cu "Tile order", scripts/tile_occupancy.py): None = rows in
+# storage order (default); an int = rows regrouped by neighbour pattern inside chunks of 2**TILE_ORDER consecutive rows
+# (31 = one global sort).  Results are bit-identical either way.  Environment: ISF_TILE_ORDER=<int>.
+TILE_ORDER = int(os.environ['ISF_TILE_ORDER']) if os.environ.get('ISF_TILE_ORDER') else None
+
+
+def _tile_order(rb, ksize):
+    """attach the regrouped neighbour table to a freshly built rulebook (same stream as the rulebook build)."""
+    if TILE_ORDER is None or rb.taps < 2:
+        return rb
+    lib = L.lib()
+    dev = rb.nbr.device
+    wsb = ctypes.c_size_t(0)
+    L.check(lib.isf_spconv_tile_order_workspace_size(rb.num_out, ctypes.byref(wsb)))
+    ws = L.workspace(wsb.value, dev)
+    rb.nbr_ordered = torch.empty_like(rb.nbr)
+    rb.row_perm = torch.empty(rb.nbr_stride, dtype=torch.int32, device=dev)
+    L.check(lib.isf_spconv_tile_order(L.ptr(rb.nbr), ctypes.c_longlong(rb.nbr_stride), rb.taps, L.host_i32(ksize), rb.num_out,
+                                      L.ptr(rb.num_dev), int(TILE_ORDER), L.ptr(rb.nbr_ordered), L.ptr(rb.row_perm), L.ptr(ws),
+                                      ctypes.c_size_t(ws.numel()), L.stream()))
+    return rb
 
 
 def _hash_table(x):
@@ -180,7 +206,7 @@ def build_rulebook_bitmap(x, ksize, stride, padding, dilation, subm, out_capacit
                                             L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
                                             L.host_i32(padding), L.host_i32(dilation), 1 if subm else 0, L.ptr(nbr),
                                             ctypes.c_longlong(stride_rows), L.stream()))
-    return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev)
+    return _tile_order(Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev), ksize)
 
 
 def build_rulebook(x, ksize, stride, padding, dilation, subm, out_capacity=None):
@@ -229,7 +255,7 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm, out_capacity=None)
                                      L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
                                      L.host_i32(padding), L.host_i32(dilation), 1 if subm else 0, L.ptr(nbr),
                                      ctypes.c_longlong(stride_rows), L.stream()))
-    return Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev)
+    return _tile_order(Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev), ksize)
 
 
 PROFILE = None      # bench.py: list collecting the arguments of every implicit-GEMM launch of a frame
@@ -276,10 +302,17 @@ def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, resid
         raise L.IsfError('sparse conv: feature matrix larger than 4 GiB (the kernel stages 32-bit row byte offsets)')
     if out is None:
         out = torch.empty((rb.num_out, cout), dtype=torch.float16, device=feats.device)
+    ldr = residual.stride(0) if residual is not None else 0
+    if rb.row_perm is not None:
+        L.check(L.lib().isf_spconv_implicit_gemm_ordered(
+            L.ptr(feats), cin, L.ptr(w_packed), w_packed.shape[1], cout, L.ptr(rb.nbr_ordered),
+            ctypes.c_longlong(rb.nbr_stride), rb.taps, rb.num_out, L.ptr(rb.num_dev), L.ptr(rb.row_perm), L.ptr(scale),
+            L.ptr(shift), L.ptr(residual), ldr, 1 if relu else 0, L.ptr(out), out.stride(0), L.stream()))
+        return out
     L.check(L.lib().isf_spconv_implicit_gemm(
         L.ptr(feats), cin, L.ptr(w_packed), w_packed.shape[1], cout, L.ptr(rb.nbr), ctypes.c_longlong(rb.nbr_stride),
-        rb.taps, rb.num_out, L.ptr(rb.num_dev), L.ptr(scale), L.ptr(shift), L.ptr(residual),
-        residual.stride(0) if residual is not None else 0, 1 if relu else 0, L.ptr(out), out.stride(0), L.stream()))
+        rb.taps, rb.num_out, L.ptr(rb.num_dev), L.ptr(scale), L.ptr(shift), L.ptr(residual), ldr, 1 if relu else 0,
+        L.ptr(out), out.stride(0), L.stream()))
     return out
 
 

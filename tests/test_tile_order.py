@@ -1,0 +1,161 @@
+"""Tile order of the sparse-conv implicit GEMM (csrc/spconv.cu, isf_spconv_tile_order; opt-in via
+isfusion_b200.spconv.TILE_ORDER / ISF_TILE_ORDER).
+
+CPU part: the host-side key layout and a numpy model of the order (scripts/tile_occupancy.py) on an oracle rulebook.
+GPU part (bring-up, ISF_EXPERIMENTAL=1: written at the end of round 1 without GPU time left to run it): the device
+order equals the model and every convolution over the regrouped table is BIT-IDENTICAL to the default launch."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+experimental = pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='opt-in path: set ISF_EXPERIMENTAL=1')
+
+
+def test_key_bits_rank_z_moving_and_far_offsets_first():
+    import tile_occupancy as to
+    pos = to.library_tap_bits((3, 3, 3))
+    assert sorted(pos) == list(range(27))
+    offs = [(kz - 1, ky - 1, kx - 1) for kz in range(3) for ky in range(3) for kx in range(3)]
+    assert pos[13] == 0                                              # the centre tap (always present) is the LSB
+    z_moving = [pos[k] for k, o in enumerate(offs) if o[0] != 0]
+    in_plane = [pos[k] for k, o in enumerate(offs) if o[0] == 0]
+    assert min(z_moving) > max(in_plane)                             # 18 z-moving taps own the 18 top bits
+    corner = [pos[k] for k, o in enumerate(offs) if all(o)]
+    assert min(corner) >= 27 - 8                                     # the 8 corners sort first of all
+    assert to.library_tap_bits((3, 1, 1)) == [2, 0, 1] or sorted(to.library_tap_bits((3, 1, 1))) == [0, 1, 2]
+    from isfusion_b200 import _lib as L
+    bad = (ctypes.c_ubyte * 32)()
+    assert L.lib().isf_spconv_tile_order_bits(L.host_i32((3, 3, 3)), 9, bad) == 1      # taps != kD*kH*kW
+
+
+def test_model_order_is_a_stable_permutation_and_cuts_zero_slots():
+    import synth
+    import tile_occupancy as to
+    from oracle import spconv_ops as so, voxel_ops
+    pts = synth.make_points(30000, 'S', 4)
+    c = voxel_ops.dynamic_voxelize(pts, [0.075, 0.075, 0.2], synth.PC_RANGE)
+    c = c[(c >= 0).all(1)]
+    idx = torch.unique(torch.cat([torch.zeros(len(c), 1, dtype=c.dtype), c], 1), dim=0).int()
+    idx, shape, _ = so.get_indice_pairs(idx, 1, [41, 1440, 1440], 3, 2, [1, 1, 1], 1, False)
+    _, _, nbr = so.get_indice_pairs(idx, 1, shape, 3, 1, 1, 1, True)
+    valid = (nbr >= 0).numpy()
+    v = valid.shape[1]
+    base, _ = to.issued_slots(valid, np.arange(v))
+    for chunk in (12, 31):
+        perm = to.tile_order_model(valid, chunk)
+        assert np.array_equal(np.sort(perm), np.arange(v))
+        if chunk < 31:                                               # rows never leave their chunk
+            assert np.array_equal(perm >> chunk, np.arange(v) >> chunk)
+        got, _ = to.issued_slots(valid, perm)
+        assert got < 0.85 * base, (chunk, got, base)
+    # stable: rows with identical masks keep their storage order
+    perm = to.tile_order_model(valid, 31)
+    pos = to.library_tap_bits()
+    key = sum(valid[k].astype(np.int64) << pos[k] for k in range(27))
+    same = key[perm][1:] == key[perm][:-1]
+    assert (perm[1:][same] > perm[:-1][same]).all()
+
+
+# ------------------------------------------------------------------------------------------------ GPU bring-up
+def _device_order(nbr, v, chunk, num_dev=None, ksize=(3, 3, 3)):
+    from isfusion_b200 import _lib as L
+    lib = L.lib()
+    taps, stride = nbr.shape
+    wsb = ctypes.c_size_t(0)
+    L.check(lib.isf_spconv_tile_order_workspace_size(v, ctypes.byref(wsb)))
+    ws = torch.empty(wsb.value, dtype=torch.uint8, device='cuda')
+    out = torch.full_like(nbr, -7)
+    perm = torch.full((stride,), -7, dtype=torch.int32, device='cuda')
+    L.check(lib.isf_spconv_tile_order(L.ptr(nbr), ctypes.c_longlong(stride), taps, L.host_i32(ksize), v, L.ptr(num_dev), chunk,
+                                      L.ptr(out), L.ptr(perm), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+    torch.cuda.synchronize()
+    return out, perm
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.parametrize('chunk', [7, 12, 31])
+def test_device_order_equals_model(chunk):
+    import tile_occupancy as to
+    from isfusion_b200.spconv import SparseConvTensor, build_rulebook
+    from test_spconv_gpu import _rand_tensor
+    x = _rand_tensor([41, 96, 96], 30000, 16, 2, 3, clustered=True)
+    xt = SparseConvTensor(x.features.half().cuda(), x.indices.cuda(), x.spatial_shape, x.batch_size)
+    rb = build_rulebook(xt, [3, 3, 3], [1, 1, 1], [1, 1, 1], [1, 1, 1], True)
+    v = rb.num_out
+    out, perm = _device_order(rb.nbr, v, chunk)
+    valid = (rb.nbr[:, :v] >= 0).cpu().numpy()
+    model = to.tile_order_model(valid, chunk)
+    assert np.array_equal(perm[:v].cpu().numpy(), model)
+    assert (perm[v:] == -1).all() and (out[:, v:] == -1).all()
+    assert torch.equal(out[:, :v], rb.nbr[:, perm[:v].long()])
+    # capacity mode: only the first n rows are valid, the tail of the capacity sorts last and is dropped
+    n = v - 1000
+    num_dev = torch.tensor([n], dtype=torch.int32, device='cuda')
+    out2, perm2 = _device_order(rb.nbr, v, chunk, num_dev)
+    assert np.array_equal(perm2[:n].cpu().numpy(), to.tile_order_model(valid[:, :n], chunk))
+    assert (perm2[n:] == -1).all() and (out2[:, n:] == -1).all()
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.parametrize('chunk', [12, 31])
+def test_sparse_encoder_bit_identical_with_tile_order(chunk):
+    import isfusion_b200.spconv as sp
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    from test_spconv_gpu import _rand_tensor
+    torch.manual_seed(0)
+    cfg = dict(in_channels=64, sparse_shape=[41, 128, 128], base_channels=32, output_channels=256,
+               encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    mod = SparseEncoder(**cfg).cuda().eval()
+    x = _rand_tensor([41, 128, 128], 20000, 64, 2, 11, clustered=True)
+    f, c = torch.relu(x.features).half().cuda(), x.indices.cuda()
+    try:
+        sp.TILE_ORDER = None
+        ref, _, _ = mod(f, c, 2)
+        sp.TILE_ORDER = chunk
+        out, _, _ = mod(f, c, 2)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    finally:
+        sp.TILE_ORDER = None
+
+
+@pytest.mark.gpu
+@experimental
+def test_graphed_neck_bit_identical_with_tile_order():
+    """capacity mode + CUDA graph: device-side row counts, rulebooks (and their orders) built on the side stream."""
+    import isfusion_b200.spconv as sp
+    import synth
+    from __graft_entry__ import make_pair
+    from isfusion_b200.detector import GraphedNeck
+    _, net = make_pair(0)
+    net = net.cuda().eval()
+    pts = [synth.make_points(20000, 'S', 5).cuda()]
+    l2i, aug, laug = synth.make_calib(1)
+    feats = [t.cuda() for t in synth.make_img_feats(1)]
+    metas = [dict(input_shape=(256, 704))]
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    outs = {}
+    try:
+        for mode in (None, 31):
+            sp.TILE_ORDER = mode
+            caps = GraphedNeck.calibrate(net, [pts], feats, metas, **kw)
+            g = GraphedNeck(net, 1, pts[0].shape[0] + 500, calib=kw, capacities=caps)
+            g.load(pts, feats[1])
+            g.capture()
+            o, hm = g(pts, feats[1])
+            torch.cuda.synchronize()
+            assert not g.check()
+            outs[mode] = [t.clone() for t in o] + [hm.clone()]
+        for a, b in zip(outs[None], outs[31]):
+            assert torch.equal(a, b)
+    finally:
+        sp.TILE_ORDER = None
