@@ -1,7 +1,9 @@
 """Per-layer timing of the sparse-conv implicit GEMMs of one frame (round-2 iteration aid, GPU only):
-   python scripts/bench_gemm_layers.py [--points 300000] [--v2]
-prints, for each of the 21 launches, rows / Cin / Cout / ms and useful + issued TFLOP/s, for the default kernel and
-(with --v2) the opt-in warp-specialised schedule side by side."""
+   python scripts/bench_gemm_layers.py [--points 300000] [--v2] [--tile-order 12,16,31]
+prints, for each of the 21 launches, rows / Cin / Cout / ms and useful TFLOP/s for the default kernel and, side by
+side, the opt-in variants: the warp-specialised schedule (--v2, csrc/tc_gemm2.cuh) and the neighbour-pattern tile
+order (--tile-order, csrc/spconv.cu isf_spconv_tile_order; chunk log2 per variant, 31 = one global sort), alone and
+combined.  Also checks that every variant's encoder output is bit-identical to the default one."""
 import argparse
 import os
 import sys
@@ -20,6 +22,7 @@ def main():
     ap.add_argument('--points', type=int, default=300000)
     ap.add_argument('--cloud', default='S')
     ap.add_argument('--v2', action='store_true')
+    ap.add_argument('--tile-order', default='', help='comma-separated chunk log2 values, e.g. 12,16,31')
     ap.add_argument('--reps', type=int, default=10)
     args = ap.parse_args()
     _, net = make_pair(0)
@@ -29,26 +32,42 @@ def main():
     feats = [f.cuda() for f in synth.make_img_feats(1)]
     metas = [dict(input_shape=(256, 704))]
     kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
-    net(pts, feats, metas, **kw)
-    prof = []
-    spmod.PROFILE = prof
-    net(pts, feats, metas, **kw)
-    spmod.PROFILE = None
-    cols = {}
-    for name, opt in (('v1', 0),) + ((('v2', 1),) if args.v2 else ()):
-        L.set_option('gemm_v2', opt)
-        cols[name] = spmod.time_launches(prof, reps=args.reps)
-    L.set_option('gemm_v2', 0)
-    print('%3s %8s %4s %4s | %s' % ('#', 'rows', 'cin', 'cout', ' | '.join('%s ms  useful/issued TF/s' % n for n in cols)))
-    tot = {n: 0.0 for n in cols}
-    for i in range(len(prof)):
-        r0 = cols['v1'][i]
+    orders = [None] + [int(t) for t in args.tile_order.split(',') if t]
+    variants = [('v1' + ('' if o is None else '+ord%d' % o), 0, o) for o in orders]
+    if args.v2:
+        variants += [('v2' + ('' if o is None else '+ord%d' % o), 1, o) for o in orders]
+    cols, ref_out = {}, None
+    for name, v2, order in variants:
+        L.set_option('gemm_v2', v2)
+        spmod.TILE_ORDER = order
+        try:
+            net(pts, feats, metas, **kw)
+            prof = []
+            spmod.PROFILE = prof
+            out, _ = net(pts, feats, metas, **kw)
+            spmod.PROFILE = None
+            torch.cuda.synchronize()
+            if ref_out is None:
+                ref_out = [o.clone() for o in out]
+            else:
+                same = all(torch.equal(a, b) for a, b in zip(ref_out, out))
+                print('%s: neck output %s the default path' % (name, 'bit-identical to' if same else 'DIFFERS from'))
+            cols[name] = spmod.time_launches(prof, reps=args.reps)
+        finally:
+            spmod.PROFILE = None
+            spmod.TILE_ORDER = None
+            L.set_option('gemm_v2', 0)
+    names = list(cols)
+    print('%3s %8s %4s %4s | %s' % ('#', 'rows', 'cin', 'cout', ' | '.join('%-16s' % (n + ' ms/TF') for n in names)))
+    tot = {n: 0.0 for n in names}
+    base = cols[names[0]]
+    for i in range(len(base)):
         cells = []
-        for n, recs in cols.items():
-            ms, issued, useful = recs[i][0], recs[i][1], recs[i][2]
+        for n in names:
+            ms, useful = cols[n][i][0], cols[n][i][2]
             tot[n] += ms
-            cells.append('%7.3f  %6.0f /%6.0f' % (ms, useful / ms / 1e9, issued / ms / 1e9))
-        print('%3d %8d %4d %4d | %s' % (i, r0[5], r0[3], r0[4], ' | '.join(cells)))
+            cells.append('%7.3f %7.0f ' % (ms, useful / ms / 1e9))
+        print('%3d %8d %4d %4d | %s' % (i, base[i][5], base[i][3], base[i][4], ' | '.join(cells)))
     print('total ms: ' + '  '.join('%s %.3f' % (n, t) for n, t in tot.items()))
 
 
