@@ -119,6 +119,26 @@ def fusion_inputs(bs=2, seed=0):
                 img_metas=[dict(input_shape=IMG_SHAPE) for _ in range(bs)])
 
 
+# ----------------------------------------------------------------------------- head
+def head_cfg():
+    """configs/isfusion/isfusion_0075voxel.py:115-171 on the 24x24 grid (grid_size 192 / out_size_factor 8)."""
+    return dict(num_proposals=200, auxiliary=True, in_channels=512, hidden_channel=128, num_classes=10, num_decoder_layers=1,
+                num_heads=8, nms_kernel_size=3, ffn_channel=256, dropout=0.1, bn_momentum=0.1, activation='relu',
+                common_heads=dict(center=(2, 2), height=(1, 2), dim=(3, 2), rot=(2, 2), vel=(2, 2)),
+                bbox_coder=dict(type='TransFusionBBoxCoder', pc_range=PC_RANGE[:2], voxel_size=[0.5625, 0.5625], out_size_factor=8,
+                                post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0], score_threshold=0.0, code_size=10),
+                loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2, alpha=0.25, reduction='mean', loss_weight=1.0),
+                loss_bbox=dict(type='L1Loss', reduction='mean', loss_weight=0.25),
+                loss_heatmap=dict(type='GaussianFocalLoss', reduction='mean', loss_weight=1.0),
+                train_cfg=None,
+                test_cfg=dict(dataset='nuScenes', grid_size=[BEV * 8, BEV * 8, 40], out_size_factor=8, pc_range=PC_RANGE[:2],
+                              voxel_size=[0.5625, 0.5625], nms_type=None, use_rotate_nms=True, nms_thr=0.2, max_num=200))
+
+
+def head_input(bs=2, seed=0):
+    return torch.relu(rand('head_input', (bs, 512, BEV, BEV), seed, 0.7))
+
+
 # ----------------------------------------------------------------------------- small VFE / sparse-encoder cases
 VFE_VOXEL = [0.5, 0.5, 1.0]
 VFE_RANGE = [-8.0, -8.0, -2.0, 8.0, 8.0, 2.0]

@@ -16,6 +16,8 @@ Fixtures (checked by tests/test_oracle_vs_reference.py against oracle/):
   ref_vfe.npz     : DynamicVFE.forward (voxel_encoder.py:452-547) features + coordinates; DynamicScatter mean.
   ref_sparse.npz  : SparseEncoder.forward (sparse_encoder.py:107-138) dense output [B,512,H/8,W/8] and the
                     active-site count after every stage.
+  ref_head.npz    : TransFusionHeadV2.forward (transfusion_head_v2.py:771-908) prediction dict on a [2,512,24,24] map,
+                    query labels, and TransFusionBBoxCoder.decode (transfusion_bbox_coder.py:41-125) of it.
 """
 import os
 import sys
@@ -112,9 +114,33 @@ def sparse(R):
     print('sparse:', tuple(out.shape), 'active sites per stage', counts.tolist(), 'nonzero', int((out != 0).sum()))
 
 
+@torch.no_grad()
+def head(R):
+    R = ref_shim.install_head()
+    net = gc.fill_state(R.TransFusionHeadV2(**gc.head_cfg()), 7).eval()
+    x = gc.head_input()
+    res = net([x], None, None)                                  # tuple(list[dict]) as the detector receives it
+    p = res[0][0]
+    out = {k: _np(v) for k, v in p.items()}
+    out['query_labels'] = _np(net.query_labels)
+    # get_bboxes (:1278-1409) wraps the result in metas[0]['box_type_3d'] (a box class of mmdet3d.core, absent here) and
+    # asserts batch 1; its arithmetic up to that point is the coder's decode over the last-layer predictions:
+    n = net.num_proposals
+    score = p['heatmap'][..., -n:].sigmoid()
+    one_hot = torch.nn.functional.one_hot(net.query_labels, num_classes=net.num_classes).permute(0, 2, 1)
+    score = score * p['query_heatmap_score'] * one_hot
+    dec = net.bbox_coder.decode(score, p['rot'][..., -n:].clone(), p['dim'][..., -n:].clone(), p['center'][..., -n:].clone(),
+                                p['height'][..., -n:].clone(), p['vel'][..., -n:].clone(), filter=True)
+    for i, d in enumerate(dec):
+        out['box%d_bboxes' % i], out['box%d_scores' % i], out['box%d_labels' % i] = _np(d['bboxes']), _np(d['scores']), _np(d['labels'])
+    out['keys'] = np.array(sorted(net.state_dict().keys()))
+    np.savez_compressed(os.path.join(HERE, 'ref_head.npz'), **out)
+    print('head:', {k: v.shape for k, v in out.items() if k != 'keys'})
+
+
 if __name__ == '__main__':
     R = ref_shim.install()
-    which = sys.argv[1:] or ['fusion', 'sst', 'vfe', 'sparse']
+    which = sys.argv[1:] or ['fusion', 'sst', 'vfe', 'sparse', 'head']
     for w in which:
         globals()[w](R)
     for f in sorted(os.listdir(HERE)):

@@ -491,7 +491,7 @@ def install():
         _mod('cv2') if 'cv2' not in sys.modules and importlib.util.find_spec('cv2') is None else None
 
         _pkg('mmdet3d')
-        _mod('mmdet3d.core', draw_heatmap_gaussian=None, gaussian_radius=None)
+        _pkg('mmdet3d.core', draw_heatmap_gaussian=None, gaussian_radius=None)
         ops = _pkg('mmdet3d.ops')
         _mod('mmdet3d.ops.spconv', IS_SPCONV2_AVAILABLE=False)
         _load_ref('mmdet3d.ops.norm', 'mmdet3d/ops/norm.py')
@@ -543,7 +543,60 @@ def install():
         SparseConvTensor=SparseConvTensor)
 
 
-if __name__ == '__main__':
+_head_installed = False
+
+
+def install_head():
+    """additionally load the reference's TransFusionHeadV2 (dense_heads/transfusion_head_v2.py) and
+    TransFusionBBoxCoder (core/bbox/coders/transfusion_bbox_coder.py).  Only the inference forward / decode run; the
+    training-side imports (losses, assigners, samplers, box structures, NMS ops) are inert placeholders."""
+    global _head_installed
     ns = install()
+    m = sys.modules
+    if not _head_installed:
+        class _Inert:
+            def __init__(self, *a, **k):
+                pass
+        losses = m['mmdet.models.builder'].LOSSES
+        for n in ('FocalLoss', 'L1Loss', 'GaussianFocalLoss', 'VarifocalLoss', 'CrossEntropyLoss'):
+            losses.register_module(n, module=type(n, (_Inert,), {}))
+        m['mmcv.cnn'].kaiming_init = lambda *a, **k: None
+        core = m['mmdet3d.core']
+        for n in ('circle_nms', 'xywhr2xyxyr', 'limit_period'):
+            setattr(core, n, None)
+        for n in ('PseudoSampler', 'Box3DMode', 'LiDARInstance3DBoxes'):
+            setattr(core, n, type(n, (_Inert,), {}))
+        _pkg('mmdet3d.core.bbox')
+        _mod('mmdet3d.core.bbox.structures', rotation_3d_in_axis=None)
+        _pkg('mmdet3d.core.bbox.coders')
+        coders = Registry('bbox_coder')
+
+        class BaseBBoxCoder:
+            def __init__(self, **kwargs):
+                pass
+
+        def multi_apply(func, *args, **kwargs):                       # mmdet/core/utils/misc.py
+            from functools import partial
+            pfunc = partial(func, **kwargs) if kwargs else func
+            return tuple(map(list, zip(*map(pfunc, *args))))
+        _pkg('mmdet.core', build_bbox_coder=lambda cfg, **k: coders.build(cfg), multi_apply=multi_apply,
+             build_assigner=lambda *a, **k: None, build_sampler=lambda *a, **k: None, AssignResult=_Inert)
+        _pkg('mmdet.core.bbox', BaseBBoxCoder=BaseBBoxCoder)
+        _mod('mmdet.core.bbox.builder', BBOX_CODERS=coders)
+        _load_ref('mmdet3d.core.bbox.coders.transfusion_bbox_coder', 'mmdet3d/core/bbox/coders/transfusion_bbox_coder.py')
+        _mod('mmdet3d.models.utils', clip_sigmoid=None)
+        _mod('mmdet3d.models.fusion_layers', apply_3d_transformation=None)
+        _pkg('mmdet3d.ops.iou3d')
+        _mod('mmdet3d.ops.iou3d.iou3d_utils', nms_gpu=None)
+        _pkg('mmdet3d.models.dense_heads')
+        _load_ref('mmdet3d.models.dense_heads.transfusion_head_v2', 'mmdet3d/models/dense_heads/transfusion_head_v2.py')
+        _head_installed = True
+    ns.TransFusionHeadV2 = m['mmdet3d.models.dense_heads.transfusion_head_v2'].TransFusionHeadV2
+    ns.TransFusionBBoxCoder = m['mmdet3d.core.bbox.coders.transfusion_bbox_coder'].TransFusionBBoxCoder
+    return ns
+
+
+if __name__ == '__main__':
+    ns = install_head()
     print('reference classes loaded:', [k for k in vars(ns)])
     print(inspect.getsourcefile(ns.ISFusionEncoder))

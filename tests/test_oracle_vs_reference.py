@@ -135,3 +135,22 @@ def test_sparse_encoder_matches_reference_driving_a_dense_conv():
     assert [e.indices.shape[0] for e in enc] == g['stage_voxels'].tolist()
     assert np.array_equal(enc[1].indices.numpy(), g['stage1_coors'])
     _close(out, g['out'], 'SparseEncoder dense output')
+
+
+def test_transfusion_head_forward_and_decode_match_reference():
+    """TransFusionHeadV2.forward + TransFusionBBoxCoder.decode of the reference run."""
+    from oracle import head_ops
+    g = _load('ref_head.npz')
+    cfg = gc.head_cfg()
+    net = gc.fill_state(head_ops.TransFusionHeadV2(**cfg), 7).eval()
+    _keys(net, g, 'keys')
+    res = net([gc.head_input()])
+    p = res[0][0]
+    assert np.array_equal(net.query_labels.numpy(), g['query_labels'])          # same top-200 proposals, same order
+    for k in ('center', 'height', 'dim', 'rot', 'vel', 'heatmap', 'query_heatmap_score', 'dense_heatmap'):
+        _close(p[k], g[k], 'head ' + k, 1e-4)
+    boxes = net.get_bboxes(res)
+    for i, b in enumerate(boxes):
+        assert np.array_equal(b['labels'].numpy(), g['box%d_labels' % i])
+        _close(b['scores'], g['box%d_scores' % i], 'scores', 1e-4)
+        _close(b['bboxes'], g['box%d_bboxes' % i], 'bboxes', 1e-4)
