@@ -244,6 +244,10 @@ int isf_window_attention(const void* qkv, const float* pos_q, const float* pos_k
 int isf_heatmap_topk_workspace_size(int batch, int classes, int H, int W, size_t* bytes);
 int isf_heatmap_topk(const float* logits, int batch, int classes, int H, int W, int plain_from, int k, int* top_idx,
                      float* top_score, void* workspace, size_t ws_bytes, void* stream);
+/* same, top_idx = class * H*W + cell: the proposals of TransFusionHeadV2.forward_single
+ * (mmdet3d/models/dense_heads/transfusion_head_v2.py:789-826), which also needs each proposal's class. */
+int isf_heatmap_topk_class(const float* logits, int batch, int classes, int H, int W, int plain_from, int k, int* top_idx,
+                           float* top_score, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- a11: multi-scale deformable attention forward ------------------------------
  * replaces mmcv._ext.ms_deform_attn_forward (call site mmdet3d/models/middle_encoders/

@@ -365,10 +365,10 @@ extern "C" int isf_heatmap_topk_workspace_size(int batch, int classes, int H, in
   return ISF_OK;
 }
 
-// logits [B, classes, H, W] fp32 (pre-sigmoid); classes >= plain_from use a 1x1 "NMS"; top_idx [B, k] int32 =
-// flat spatial index (index % (H*W)) of the k best (class, cell) scores, descending (stable on ties).
-extern "C" int isf_heatmap_topk(const float* logits, int batch, int classes, int H, int W, int plain_from, int k,
-                                int* top_idx, float* top_score, void* workspace, size_t ws_bytes, void* stream) {
+// logits [B, classes, H, W] fp32 (pre-sigmoid); classes >= plain_from use a 1x1 "NMS"; the k best (class, cell)
+// scores, descending (stable on ties), reported modulo `mod`: H*W = flat spatial index, classes*H*W = class*H*W + cell.
+static int heatmap_topk_impl(const float* logits, int batch, int classes, int H, int W, int plain_from, int k, int mod,
+                             int* top_idx, float* top_score, void* workspace, size_t ws_bytes, void* stream) {
   ISF_CHECK_ARG(logits && top_idx && workspace && batch >= 1 && k >= 1 && k <= classes * H * W);
   const int n = classes * H * W;
   cudaStream_t st = (cudaStream_t)stream;
@@ -386,10 +386,23 @@ extern "C" int isf_heatmap_topk(const float* logits, int batch, int classes, int
     ISF_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, t, keys + (size_t)b * n, keys_s + (size_t)b * n,
                                                        vals + (size_t)b * n, vals_s + (size_t)b * n, n, 0, 32, st));
   }
-  take_topk_kernel<<<batch, 256, 0, st>>>(keys_s, vals_s, n, k, H * W, top_idx, top_score);
+  take_topk_kernel<<<batch, 256, 0, st>>>(keys_s, vals_s, n, k, mod, top_idx, top_score);
   isf_count_launch(2 + 4 * batch);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
+}
+
+// top_idx = flat spatial index of each proposal (instance-guided fusion, fusion_encoder.py:1126-1128)
+extern "C" int isf_heatmap_topk(const float* logits, int batch, int classes, int H, int W, int plain_from, int k,
+                                int* top_idx, float* top_score, void* workspace, size_t ws_bytes, void* stream) {
+  return heatmap_topk_impl(logits, batch, classes, H, W, plain_from, k, H * W, top_idx, top_score, workspace, ws_bytes, stream);
+}
+
+// top_idx = class * H*W + cell (TransFusionHeadV2 needs the proposal's class too, transfusion_head_v2.py:825-826)
+extern "C" int isf_heatmap_topk_class(const float* logits, int batch, int classes, int H, int W, int plain_from, int k,
+                                      int* top_idx, float* top_score, void* workspace, size_t ws_bytes, void* stream) {
+  return heatmap_topk_impl(logits, batch, classes, H, W, plain_from, k, classes * H * W, top_idx, top_score, workspace,
+                           ws_bytes, stream);
 }
 
 // ================================================================================================

@@ -1,13 +1,14 @@
 """ISFusionDetector point branch (ref: mmdet3d/models/detectors/isfusion.py:13-176): the fusion-neck hot path
 `extract_pts_feat` = dynamic voxelize -> DynamicVFE -> SparseEncoder -> pillarize -> ISFusionEncoder (+SECONDV2
-stages) wired from the reference's config keys.  Image backbone / pts_neck / bbox head are outside the path
- and are taken as inputs / left to the caller."""
+stages) wired from the reference's config keys.  The image backbone is outside the path: its feature
+maps are taken as inputs.  `pts_neck` (SECONDFPN) and `pts_bbox_head` (TransFusionHeadV2, inference forward + box
+decoding: `simple_test_pts`) are the rows after the path and are built when the config carries them."""
 import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import fusion_encoder, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
-from .registry import (DETECTORS, NECKS, build_backbone, build_fusion_layer, build_middle_encoder,
+from . import fusion_encoder, head, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
+from .registry import (DETECTORS, MODELS, NECKS, build_backbone, build_fusion_layer, build_middle_encoder,
                        build_voxel_encoder)
 from .profiling import stage
 from .voxel_layer import Voxelization
@@ -27,6 +28,13 @@ class ISFusionDetector(nn.Module):
         self.pts_backbone = build_backbone(dict(pts_backbone))
         # pts_neck (SECONDFPN) is the next row after the hot path; built when the config carries it
         self.pts_neck = NECKS.build(dict(pts_neck)) if pts_neck is not None else None
+        # pts_bbox_head (TransFusionHeadV2): like MVXTwoStageDetector, train_cfg.pts / test_cfg.pts are handed to the head
+        self.pts_bbox_head = None
+        if pts_bbox_head is not None:
+            hc = dict(pts_bbox_head)
+            hc.setdefault('train_cfg', train_cfg.get('pts') if train_cfg else None)
+            hc.setdefault('test_cfg', test_cfg.get('pts') if test_cfg else None)
+            self.pts_bbox_head = MODELS.build(hc)
         self.detach = kwargs.get('detach', False)
         out_size_factor = kwargs.get('out_size_factor', None)
         voxel_size = kwargs.get('voxel_size', None)
@@ -140,6 +148,24 @@ class ISFusionDetector(nn.Module):
         return feats, ins_hm
 
     forward = extract_pts_feat
+
+    @torch.no_grad()
+    def simple_test_pts(self, x, x_img=None, img_metas=None, rescale=False):
+        """ref: isfusion.py:272-281: head forward + box decoding on the pts_neck output.  Returns per sample
+        dict(boxes_3d [K,9] tensor, scores_3d, labels_3d) — `bbox3d2result` without the mmdet3d box class."""
+        if self.pts_bbox_head is None:
+            raise RuntimeError('ISFusionDetector: the config carries no pts_bbox_head')
+        outs = self.pts_bbox_head(x, x_img, img_metas)
+        return [dict(boxes_3d=b['bboxes'], scores_3d=b['scores'], labels_3d=b['labels'])
+                for b in self.pts_bbox_head.get_bboxes(outs, img_metas, rescale=rescale)]
+
+    @torch.no_grad()
+    def simple_test(self, points, img_metas, img_feats=None, rescale=False, **kwargs):
+        """ref: isfusion.py:283-302 with the image branch's feature maps given (`img_feats` = extract_img_feat output)."""
+        if self.pts_neck is None:
+            raise RuntimeError('ISFusionDetector.simple_test: the head consumes the pts_neck output (config:105-112)')
+        feats, _ = self.extract_pts_feat(points, img_feats, img_metas, **kwargs)
+        return [dict(pts_bbox=r) for r in self.simple_test_pts(feats, img_feats, img_metas, rescale=rescale)]
 
 
 class GraphedNeck:

@@ -1,0 +1,284 @@
+"""TransFusionHeadV2 inference forward + box decoding on the B200 kernels (the consumer of the neck).
+
+ref: mmdet3d/models/dense_heads/transfusion_head_v2.py:593-892 (forward_single), :1278-1310 (get_bboxes) and
+mmdet3d/core/bbox/coders/transfusion_bbox_coder.py:41-125 (decode).  Same registry name, constructor kwargs, output
+dictionary and state_dict keys as the reference (checked against the reference module's keys through the oracle).
+
+What runs where:
+  * shared 3x3 conv 512->128 (38 GFLOP at 180^2) and the two heat-map convs: cuDNN, channels-last fp16, BN folded
+    (like the neck's dense convs);
+  * sigmoid + 3x3 local-max NMS (classes 8, 9 exempt) + top-200 over class x cell: `isf_heatmap_topk_class`
+    (heatmap_nms_kernel + one radix sort + take_topk, csrc/fusion.cu) — no argsort of 324 000 scores;
+  * K/V projection of the 32 400 BEV tokens of the cross attention: ONE tcgen05 GEMM (N = 256) over
+    `tokens + key positional embedding`; the embedding of the constant (x+.5, y+.5) grid is input independent and
+    cached at pack time;
+  * the 200-query x 32 400-key attention core: `F.scaled_dot_product_attention` (library flash kernel, 3.3 GFLOP) —
+    the hand-written split-K kernel is the next step for this row;
+  * the 200-query pieces (self attention, FFN, LayerNorms, Conv1d prediction heads, decode): fp32 torch ops (tiny).
+Eval mode only; training (targets, Hungarian assignment, losses) is out of scope."""
+import copy
+import ctypes
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib as L
+from .fusion_encoder import MultiheadAttention, PositionEmbeddingLearned, _conv, _fold_conv_bn, _Packable
+from .gemm import gemm, pack_weight
+from .registry import MODELS, ConvModule
+
+HEADS = MODELS
+
+
+class TransformerDecoderLayer(nn.Module):
+    """parameter container with the reference's names (transfusion_head_v2.py:42-75)."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation='relu', self_posembed=None,
+                 cross_posembed=None, cross_only=False):
+        super().__init__()
+        if activation != 'relu' or cross_only:
+            raise L.IsfError('TransformerDecoderLayer: built for activation="relu", cross_only=False (config:126-127)')
+        self.self_attn = MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.multihead_attn = MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.self_posembed = self_posembed
+        self.cross_posembed = cross_posembed
+
+
+class _Conv1dModule(nn.Sequential):
+    """mmcv ConvModule with conv_cfg Conv1d / norm_cfg BN1d: conv(bias=False) -> BN1d -> ReLU (names conv/bn/activate)."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.add_module('conv', nn.Conv1d(cin, cout, k, padding=k // 2, bias=False))
+        self.add_module('bn', nn.BatchNorm1d(cout))
+        self.add_module('activate', nn.ReLU(inplace=True))
+
+
+class FFN(nn.Module):
+    """ref: transfusion_head_v2.py:505-590 (per-attribute Conv1d stacks over the 200 queries)."""
+
+    def __init__(self, in_channels, heads, head_conv=64, final_kernel=1, init_bias=-2.19, **kwargs):
+        super().__init__()
+        self.heads = heads
+        self.init_bias = init_bias
+        for head, (classes, num_conv) in heads.items():
+            layers, c_in = [], in_channels
+            for _ in range(num_conv - 1):
+                layers.append(_Conv1dModule(c_in, head_conv, final_kernel))
+                c_in = head_conv
+            layers.append(nn.Conv1d(head_conv, classes, final_kernel, padding=final_kernel // 2, bias=True))
+            setattr(self, head, nn.Sequential(*layers))
+        getattr(self, 'heatmap')[-1].bias.data.fill_(init_bias) if 'heatmap' in heads else None
+
+    def forward(self, x):
+        return {head: getattr(self, head)(x) for head in self.heads}
+
+
+def _mha_small(m, q_in, k_in, v_in):
+    """the reference's custom MHA (transfusion_head_v2.py:253-503) for a few hundred tokens: [B,L,E] fp32 in / out."""
+    e, h = m.embed_dim, m.num_heads
+    w, b = m.in_proj_weight, m.in_proj_bias
+    q = F.linear(q_in, w[:e], b[:e])
+    k = F.linear(k_in, w[e:2 * e], b[e:2 * e])
+    v = F.linear(v_in, w[2 * e:], b[2 * e:])
+    bs, lq, _ = q.shape
+    split = lambda t: t.view(bs, t.shape[1], h, e // h).transpose(1, 2)
+    o = F.scaled_dot_product_attention(split(q), split(k), split(v))          # scale = head_dim ** -0.5 (:388)
+    return m.out_proj(o.transpose(1, 2).reshape(bs, lq, e))
+
+
+@HEADS.register_module()
+class TransFusionHeadV2(_Packable):
+
+    def __init__(self, num_proposals=128, auxiliary=True, in_channels=128 * 3, hidden_channel=128, num_classes=4,
+                 num_decoder_layers=3, num_heads=8, nms_kernel_size=1, ffn_channel=256, dropout=0.1, bn_momentum=0.1,
+                 activation='relu', common_heads=dict(), num_heatmap_convs=2, conv_cfg=dict(type='Conv1d'),
+                 norm_cfg=dict(type='BN1d'), bias='auto', loss_cls=None, loss_iou=None, loss_bbox=None, loss_heatmap=None,
+                 train_cfg=None, test_cfg=None, bbox_coder=None):
+        super().__init__()
+        if nms_kernel_size != 3:
+            raise L.IsfError('TransFusionHeadV2: the fused NMS + top-K kernel is built for nms_kernel_size=3 (config:125)')
+        if hidden_channel % 64 or hidden_channel // num_heads % 8:
+            raise L.IsfError('TransFusionHeadV2: hidden_channel must be a multiple of 64 and head_dim a multiple of 8')
+        self.num_classes, self.num_proposals, self.auxiliary = num_classes, num_proposals, auxiliary
+        if loss_cls is not None and not loss_cls.get('use_sigmoid', False):
+            self.num_classes += 1                                  # transfusion_head_v2.py:640-642
+        self.in_channels, self.num_heads, self.num_decoder_layers = in_channels, num_heads, num_decoder_layers
+        self.bn_momentum, self.nms_kernel_size = bn_momentum, nms_kernel_size
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.bbox_coder_cfg = dict(bbox_coder) if bbox_coder is not None else None
+        self.shared_conv = nn.Conv2d(in_channels, hidden_channel, 3, padding=1, bias=bool(bias))    # 'auto' is truthy (:655)
+        self.heatmap_head = nn.Sequential(
+            ConvModule(hidden_channel, hidden_channel, kernel_size=3, padding=1, norm_cfg=dict(type='BN2d'), bias=bias),
+            nn.Conv2d(hidden_channel, num_classes, 3, padding=1, bias=bool(bias)))
+        self.class_encoding = nn.Conv1d(num_classes, hidden_channel, 1)
+        self.decoder = nn.ModuleList([
+            TransformerDecoderLayer(hidden_channel, num_heads, ffn_channel, dropout, activation,
+                                    self_posembed=PositionEmbeddingLearned(2, hidden_channel),
+                                    cross_posembed=PositionEmbeddingLearned(2, hidden_channel))
+            for _ in range(num_decoder_layers)])
+        self.prediction_heads = nn.ModuleList()
+        for _ in range(num_decoder_layers):
+            heads = copy.deepcopy(common_heads)
+            heads.update(dict(heatmap=(self.num_classes, num_heatmap_convs)))
+            self.prediction_heads.append(FFN(hidden_channel, heads))
+        for m in self.decoder.parameters():
+            if m.dim() > 1:
+                nn.init.xavier_uniform_(m)
+        for m in self.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.momentum = bn_momentum
+        self.x_size = test_cfg['grid_size'][0] // test_cfg['out_size_factor']
+        self.y_size = test_cfg['grid_size'][1] // test_cfg['out_size_factor']
+        bx, by = torch.meshgrid(torch.linspace(0, self.x_size - 1, self.x_size), torch.linspace(0, self.y_size - 1, self.y_size),
+                                indexing='ij')
+        self.bev_pos = torch.cat([(bx + 0.5)[None], (by + 0.5)[None]], dim=0)[None].view(1, 2, -1).permute(0, 2, 1)
+        self.query_labels = None
+        self._pk = None
+
+    # ------------------------------------------------------------------ packing (eval-mode constants)
+    def _pack(self, device):
+        if self.__dict__.get('_pk') is None:
+            pk = {}
+            pk['shared'] = _fold_conv_bn(self.shared_conv, None)
+            pk['hm0'] = _fold_conv_bn(self.heatmap_head[0].conv, self.heatmap_head[0].bn)
+            pk['hm1'] = _fold_conv_bn(self.heatmap_head[1], None)
+            bev_pos = self.bev_pos.to(device)                                          # [1, HW, 2]
+            pk['bev_pos'] = bev_pos
+            pk['cls_w'] = self.class_encoding.weight.detach()[:, :, 0].t().float().contiguous()     # [classes, C]
+            pk['cls_b'] = self.class_encoding.bias.detach().float()
+            layers = []
+            for layer in self.decoder:
+                d = {}
+                mha = layer.multihead_attn
+                e = mha.embed_dim
+                # key positional embedding of the constant grid: input independent in eval mode
+                d['kpe'] = layer.cross_posembed(bev_pos).permute(0, 2, 1)[0].half().contiguous()      # [HW, C]
+                d['wkv'] = pack_weight(mha.in_proj_weight.detach()[e:])                                # [2C, C]
+                d['bkv'] = mha.in_proj_bias.detach()[e:].float().contiguous()
+                layers.append(d)
+            pk['layers'] = layers
+            self.__dict__['_pk'] = pk
+        return self.__dict__['_pk']
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward_single(self, inputs, img_inputs=None, metas=None):
+        """inputs [B, in_channels, X, Y] (any memory format; channels-last fp16 is consumed without a copy)."""
+        if self.training:
+            raise L.IsfError('TransFusionHeadV2: eval-mode CUDA path only')
+        if not inputs.is_cuda:
+            raise L.IsfError('expected a CUDA tensor (the product path has no CPU fallback)')
+        dev = inputs.device
+        pk = self._pack(dev)
+        lib = L.lib()
+        bs, _, gh, gw = inputs.shape
+        if (gh, gw) != (self.x_size, self.y_size):
+            raise L.IsfError('TransFusionHeadV2: feature map %dx%d does not match test_cfg grid %dx%d' % (gh, gw, self.x_size, self.y_size))
+        hw, k, c = gh * gw, self.num_proposals, self.shared_conv.out_channels
+        x = inputs.permute(0, 2, 3, 1)
+        x = (x if x.dtype == torch.float16 else x.half()).contiguous()
+        lidar = _conv(x, pk['shared'], relu=False)                                             # [B,H,W,C] fp16
+        logits = _conv(_conv(lidar, pk['hm0']), pk['hm1'], relu=False).permute(0, 3, 1, 2).float().contiguous()   # [B,cls,H,W]
+        # proposals: sigmoid + 3x3 local-max NMS + top-k over class x cell (:789-826)
+        wsb = ctypes.c_size_t(0)
+        L.check(lib.isf_heatmap_topk_workspace_size(bs, self.num_classes, gh, gw, ctypes.byref(wsb)))
+        ws = L.workspace(wsb.value, dev)
+        top = torch.empty((bs, k), dtype=torch.int32, device=dev)
+        plain_from = 8 if self.test_cfg['dataset'] == 'nuScenes' else self.num_classes
+        if self.test_cfg['dataset'] not in ('nuScenes',):
+            raise L.IsfError('TransFusionHeadV2: built for the nuScenes class exemptions (classes 8, 9)')
+        L.check(lib.isf_heatmap_topk_class(L.ptr(logits), bs, self.num_classes, gh, gw, plain_from, k, L.ptr(top), L.ptr(None),
+                                           L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        top = top.long()
+        top_class, top_index = top // hw, top % hw
+        self.query_labels = top_class
+        toks = lidar.reshape(bs, hw, c)
+        query = torch.gather(toks, 1, top_index[..., None].expand(-1, -1, c)).float()          # [B,K,C]
+        query = query + pk['cls_w'][top_class] + pk['cls_b']                                   # class encoding (:840-845)
+        bev_pos = pk['bev_pos']
+        query_pos = bev_pos[0][top_index]                                                      # [B,K,2]
+        # the NMS'ed score map is also an output (query_heatmap_score, :873-876)
+        heat = logits.sigmoid()
+        local_max = torch.zeros_like(heat)
+        local_max[:, :, 1:-1, 1:-1] = F.max_pool2d(heat, kernel_size=3, stride=1, padding=0)
+        local_max[:, plain_from:] = heat[:, plain_from:]
+        heat = (heat * (heat == local_max)).view(bs, self.num_classes, hw)
+        rets = []
+        for i, layer in enumerate(self.decoder):
+            d = pk['layers'][i]
+            qpe = layer.self_posembed(query_pos).permute(0, 2, 1)                              # [B,K,C]
+            q = query + qpe
+            query = layer.norm1(query + _mha_small(layer.self_attn, q, q, q))
+            # cross attention to the BEV tokens: K,V = (tokens + pos) W_kv^T + b on the tcgen05 GEMM
+            mha = layer.multihead_attn
+            e, h = mha.embed_dim, mha.num_heads
+            src = (toks + d['kpe'][None]).reshape(bs * hw, c)
+            kv = gemm(src, d['wkv'], shift=d['bkv']).view(bs, hw, 2, h, e // h)                # fp16
+            qc = F.linear(query + qpe, mha.in_proj_weight[:e], mha.in_proj_bias[:e]).half()
+            o = F.scaled_dot_product_attention(qc.view(bs, k, h, e // h).transpose(1, 2), kv[:, :, 0].transpose(1, 2),
+                                               kv[:, :, 1].transpose(1, 2))                  # [B,h,K,d]
+            query = layer.norm2(query + mha.out_proj(o.transpose(1, 2).reshape(bs, k, e).float()))
+            query = layer.norm3(query + layer.linear2(F.relu(layer.linear1(query))))
+            res = self.prediction_heads[i](query.transpose(1, 2).contiguous())                # dict of [B,*,K]
+            res['center'] = res['center'] + query_pos.permute(0, 2, 1)
+            rets.append(res)
+            query_pos = res['center'].clone().permute(0, 2, 1)
+        rets[0]['query_heatmap_score'] = heat.gather(index=top_index[:, None, :].expand(-1, self.num_classes, -1), dim=-1)
+        rets[0]['dense_heatmap'] = logits
+        if not self.auxiliary:
+            return [rets[-1]]
+        out = {}
+        for key in rets[0]:
+            out[key] = rets[0][key] if key in ('dense_heatmap', 'dense_heatmap_old', 'query_heatmap_score') else \
+                torch.cat([r[key] for r in rets], dim=-1)
+        return [out]
+
+    def forward(self, feats, img_feats=None, metas=None):
+        """-> tuple(list[dict]) exactly as multi_apply(forward_single, ...) returns it (:894-908)."""
+        if isinstance(feats, torch.Tensor):
+            feats = [feats]
+        if len(feats) != 1:
+            raise L.IsfError('only support one level features.')
+        return ([self.forward_single(feats[0], None, metas)[0]],)
+
+    # ------------------------------------------------------------------ decoding
+    @torch.no_grad()
+    def get_bboxes(self, preds_dicts, metas=None, img=None, rescale=False, for_roi=False):
+        """ref :1278-1409 with test_cfg nms_type=None (config:170) + TransFusionBBoxCoder.decode(filter=True).
+        Returns per sample dict(bboxes [K', 7|9] (x, y, z_bottom, w, l, h, yaw[, vx, vy]) metres, scores, labels);
+        wrapping into mmdet3d's LiDARInstance3DBoxes is the caller's (metas[i]['box_type_3d'], :1401-1407)."""
+        if self.test_cfg.get('nms_type') is not None:
+            raise L.IsfError('TransFusionHeadV2.get_bboxes: built for test_cfg nms_type=None')
+        cd = self.bbox_coder_cfg
+        p = preds_dicts[0][0]
+        n = self.num_proposals
+        score = p['heatmap'][..., -n:].sigmoid()
+        one_hot = F.one_hot(self.query_labels, num_classes=self.num_classes).permute(0, 2, 1)
+        score = score * p['query_heatmap_score'] * one_hot
+        labels = score.max(1).indices
+        scores = score.max(1).values
+        osf, vs, pr = cd['out_size_factor'], cd['voxel_size'], cd['pc_range']
+        center = p['center'][..., -n:]
+        center = torch.stack([center[:, 0] * osf * vs[0] + pr[0], center[:, 1] * osf * vs[1] + pr[1]], 1)
+        dim = p['dim'][..., -n:].exp()
+        height = p['height'][..., -n:] - dim[:, 2:3] * 0.5
+        rot = p['rot'][..., -n:]
+        rot = torch.atan2(rot[:, 0:1], rot[:, 1:2])
+        parts = [center, height, dim, rot] + ([p['vel'][..., -n:]] if 'vel' in p else [])
+        boxes = torch.cat(parts, dim=1).permute(0, 2, 1)
+        rng = torch.tensor(cd['post_center_range'], dtype=boxes.dtype, device=boxes.device)
+        mask = (boxes[..., :3] >= rng[:3]).all(2) & (boxes[..., :3] <= rng[3:]).all(2)
+        if cd.get('score_threshold'):
+            mask &= scores > cd['score_threshold']
+        return [dict(bboxes=boxes[i, mask[i]], scores=scores[i, mask[i]], labels=labels[i, mask[i]]) for i in range(boxes.shape[0])]
