@@ -28,6 +28,7 @@ extern "C" unsigned long long isf_launch_count(int reset) {
 int g_isf_gemm_cluster = 1;
 int g_isf_gemm_v2 = 0;
 int g_isf_gemm_v2_zskip = 1;
+int g_isf_gemm_v2_io256 = 1;
 extern "C" int isf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_cluster") == 0 && (value == 1 || value == 2)) {
     g_isf_gemm_cluster = value;
@@ -39,6 +40,10 @@ extern "C" int isf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_v2_zskip") == 0 && (value == 0 || value == 1)) {
     g_isf_gemm_v2_zskip = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "gemm_v2_io256") == 0 && (value == 0 || value == 1)) {
+    g_isf_gemm_v2_io256 = value;
     return ISF_OK;
   }
   isf_set_error("isf_set_option: unknown option or bad value: %s=%d", name ? name : "(null)", value);

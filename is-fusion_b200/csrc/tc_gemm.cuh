@@ -178,7 +178,8 @@ struct GemmParams {
   float* out_f32;         // [m, ldo] fp32 (may be nullptr)
   int ldo;
   const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
-  int v2_flags;           // tc_gemm2.cuh only (set by dispatch_gemm2): bit 0 = skip zero-fill copies of rows already zero
+  int v2_flags;           // tc_gemm2.cuh only (set by dispatch_gemm2): bit 0 = skip zero-fill copies of rows already zero,
+                          // bit 1 = 32-byte residual loads, bit 2 = 32-byte fp16 output stores (alignment checked by the host)
 };
 
 constexpr int BM = 128;
@@ -205,6 +206,22 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // one 32-column block of the accumulator row owned by this thread: TMEM -> registers, BN fold (scale / shift) and the
 // residual row (four 16-byte loads).  Shared by the LayerNorm statistics pass and the output pass, so both see
 // bit-identical values.
+// 256-bit global accesses (LDG/STG.E.ENL2.256 on sm_100): one whole 32-byte sector per lane and instruction.  The
+// address must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&w)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// IO256 (v2 kernel only, when the residual rows are 32-byte aligned): the residual row comes in two 32-byte loads
+// instead of four 16-byte ones.  Same values, same order of the additions.
+template <bool IO256 = false>
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t taddr, int n_base, long long rrow, float (&x)[32]) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
@@ -217,15 +234,28 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
     x[j] = y;
   }
   if (p.residual && rrow >= 0) {
-    const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n_base);
+    if constexpr (IO256) {
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const uint4 u = rp[j4];
-      const __half2* h = (const __half2*)&u;
+      for (int j8 = 0; j8 < 2; ++j8) {
+        uint32_t w[8];
+        ld_global_256(p.residual + rrow * p.ldr + n_base + j8 * 16, w);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
+        for (int e = 0; e < 8; ++e) {
+          const float2 f = __half22float2(*(const __half2*)&w[e]);
+          x[j8 * 16 + e * 2] += f.x; x[j8 * 16 + e * 2 + 1] += f.y;
+        }
+      }
+    } else {
+      const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n_base);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const uint4 u = rp[j4];
+        const __half2* h = (const __half2*)&u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
+        }
       }
     }
   }

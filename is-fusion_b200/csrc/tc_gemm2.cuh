@@ -15,6 +15,8 @@
 //     gets the smem (e.g. BN=256: 6 x 16 KB of A in flight per SM instead of 4 x 16 KB);
 //   * the neighbour ids of tile t+1 are loaded into registers before the gather loop of tile t (their global latency is
 //     hidden), the neighbour tile / chunk list in smem are double-buffered;
+//   * 32-byte epilogue accesses (v2_flags bits 1, 2; isf_set_option("gemm_v2_io256", 0|1)): residual rows and fp16 output
+//     rows move as LDG/STG.E.ENL2.256 — a full sector per lane — instead of 16-byte halves;
 //   * zero-skip (v2_flags bit 0): one warp-level LDGSTS covers 4 rows x 128 B of a stage; when none of the 4 rows has
 //     a neighbour AND the previous use of that stage left zeros in those rows, the copy is skipped (the sparse 32/64-
 //     channel stages fill 15-35 % of the slots, and the LSU issue rate of these copies is what bounds them).
@@ -66,6 +68,74 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
     for (int i = 0; i < 256; ++i)
       if (mbar_try(bar, parity)) return;
     if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+// one output row (TMEM lane) of a finished tile: scale/shift (+residual) (+LayerNorm) (+activation) -> global.
+// LD256: 32-byte residual loads; (p.v2_flags & 4): 32-byte fp16 stores — one full sector per lane and instruction
+// instead of half a sector (the un-coalesced row-per-thread epilogue is 15-25 % of the L1TEX load).
+template <int BN, bool LD256>
+__device__ __forceinline__ void epilogue_tile2(const GemmParams& p, uint32_t t_lane, int n0, long long rrow, long long orow,
+                                               bool store_ok) {
+  float mean = 0.f, rstd = 1.f;
+  if (p.ln_gamma) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int cb = 0; cb < BN; cb += 32) {
+      float x[32];
+      epilogue_block<LD256>(p, t_lane + cb, n0 + cb, rrow, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s1 += x[j]; s2 += x[j] * x[j]; }
+    }
+    mean = s1 / BN;
+    const float var = s2 / BN - mean * mean;
+    rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+  }
+  const bool st256 = (p.v2_flags & 4) != 0;
+  for (int cb = 0; cb < BN; cb += 32) {
+    float x[32];
+    epilogue_block<LD256>(p, t_lane + cb, n0 + cb, rrow, x);
+    if (p.ln_gamma) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * p.ln_gamma[n0 + cb + j] + p.ln_beta[n0 + cb + j];
+    }
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+    } else if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (store_ok) {
+      if (p.out) {
+        __half* op = p.out + orow * p.ldo + n0 + cb;
+        if (st256) {
+#pragma unroll
+          for (int j8 = 0; j8 < 2; ++j8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const __half2 h = __floats2half2_rn(x[j8 * 16 + e * 2], x[j8 * 16 + e * 2 + 1]);
+              w[e] = *(const uint32_t*)&h;
+            }
+            st_global_256(op + j8 * 16, w);
+          }
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u;
+            __half2* h = (__half2*)&u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+            ((uint4*)op)[j4] = u;
+          }
+        }
+      }
+      if (p.out_f32) {
+        float4* op = (float4*)(p.out_f32 + orow * p.ldo + n0 + cb);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+      }
+    }
   }
 }
 
@@ -294,52 +364,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm2_kernel(const GemmParams p
       mbar_wait_b(&acc_full[buf], ubuf & 1);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
-      float mean = 0.f, rstd = 1.f;
-      if (p.ln_gamma) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int cb = 0; cb < BN; cb += 32) {
-          float x[32];
-          epilogue_block(p, t_lane + cb, n0 + cb, rrow, x);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { s1 += x[j]; s2 += x[j] * x[j]; }
-        }
-        mean = s1 / BN;
-        const float var = s2 / BN - mean * mean;
-        rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
-      }
-      for (int cb = 0; cb < BN; cb += 32) {
-        float x[32];
-        epilogue_block(p, t_lane + cb, n0 + cb, rrow, x);
-        if (p.ln_gamma) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * p.ln_gamma[n0 + cb + j] + p.ln_beta[n0 + cb + j];
-        }
-        if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-        } else if (p.act == ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-        }
-        if (store_ok) {
-          if (p.out) {
-            uint4* op = (uint4*)(p.out + orow * p.ldo + n0 + cb);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint4 u;
-              __half2* h = (__half2*)&u;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
-              op[j4] = u;
-            }
-          }
-          if (p.out_f32) {
-            float4* op = (float4*)(p.out_f32 + orow * p.ldo + n0 + cb);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
-          }
-        }
-      }
+      if (p.v2_flags & 2) epilogue_tile2<BN, true>(p, t_lane, n0, rrow, orow, store_ok);
+      else epilogue_tile2<BN, false>(p, t_lane, n0, rrow, orow, store_ok);
       // this thread's TMEM reads of the buffer are complete (tcgen05.wait::ld inside epilogue_block) and ordered
       // before the arrival that lets the MMA warp overwrite it
       tc_fence_before();
@@ -381,6 +407,10 @@ static int launch_gemm2(const GemmParams& p, int m_upper, cudaStream_t st) {
 static inline int dispatch_gemm2(const GemmParams& p0, int bn, int m_upper, cudaStream_t st) {
   GemmParams p = p0;
   p.v2_flags = ::g_isf_gemm_v2_zskip ? 1 : 0;
+  if (::g_isf_gemm_v2_io256) {       // 32-byte epilogue accesses where every row start is 32-byte aligned
+    if (p.residual && ((uintptr_t)p.residual & 31) == 0 && p.ldr % 16 == 0) p.v2_flags |= 2;
+    if (p.out && ((uintptr_t)p.out & 31) == 0 && p.ldo % 16 == 0) p.v2_flags |= 4;
+  }
   switch (bn) {
     case 32: return launch_gemm2<32, 10, 3>(p, m_upper, st);      // 160 + 12 KB
     case 64: return launch_gemm2<64, 9, 3>(p, m_upper, st);       // 144 + 24 KB

@@ -30,11 +30,19 @@ def test_v2_dense_gemm_bit_identical(m, k, n):
             L.set_option('gemm_v2', 0)
             ref = gemm(a, wp, shift=shift, residual=res, act='relu', ln=ln)
             L.set_option('gemm_v2', 2)
-            out = gemm(a, wp, shift=shift, residual=res, act='relu', ln=ln)
+            for io in (0, 1):           # 16-byte / 32-byte (LDG/STG.E.ENL2.256) epilogue accesses
+                L.set_option('gemm_v2_io256', io)
+                out = gemm(a, wp, shift=shift, residual=res, act='relu', ln=ln)
+                torch.cuda.synchronize()
+                assert torch.equal(out, ref), (m, k, n, ln is not None, io)
+            # a column-offset view whose rows are NOT 32-byte aligned must fall back to 16-byte stores by itself
+            wide = torch.zeros(m, n + 8, device='cuda', dtype=torch.float16)
+            gemm(a, wp, shift=shift, residual=res, act='relu', ln=ln, out=wide[:, 8:])
             torch.cuda.synchronize()
-            assert torch.equal(out, ref), (m, k, n, ln is not None)
+            assert torch.equal(wide[:, 8:], ref) and not wide[:, :8].any()
     finally:
         L.set_option('gemm_v2', 0)
+        L.set_option('gemm_v2_io256', 1)
 
 
 @pytest.mark.parametrize('zskip', [0, 1])
