@@ -357,40 +357,45 @@ def main():
     if prof:
         # dominant kernel: the tcgen05 implicit GEMM of the sparse encoder; every launch of one frame is re-issued
         # back to back between CUDA events on its launching stream (same tensors, same shapes)
-        recs = spmod.time_launches(prof, reps=5)
-        t_ms = sum(r[0] for r in recs)
-        issued = sum(r[1] for r in recs)
-        useful = sum(r[2] for r in recs)
-        peaks = {}
         try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
-        peak = peaks.get('bf16_tflops_sustained', 1400.0)
-        top = max(recs, key=lambda r: r[0])
-        # DRAM traffic of the largest launch from the committed `ncu --set full` capture (profiles/), if present
-        traffic = None
-        try:
-            txt = open(os.path.join(ROOT, 'profiles', 'prof_gemm_r01_final.txt')).read().split('== tc::gemm_kernel<256')[0]
-            rd = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_read.sum')][0]
-            wr = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_write.sum')][0]
-            traffic = (rd + wr) * 1e6      # ncu prints MB
-        except Exception:
-            pass
-        roof = {'kernel': 'tc::gemm_kernel (tcgen05 sparse-conv implicit GEMM; %d launches per frame)' % len(recs),
-                'bound': 'tensor', 'achieved': useful / (t_ms * 1e-3) / 1e12, 'achieved_issued': issued / (t_ms * 1e-3) / 1e12,
-                'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF/s sustained',
-                'unit': 'TFLOP/s', 'frac': useful / (t_ms * 1e-3) / 1e12 / peak, 'traffic': traffic,
-                'traffic_note': 'dram read+write bytes of the largest launch (stage-3 SubM 128->128; algorithmic 170 MB incl. the '
-                                'neighbour table) from profiles/prof_gemm_r01_final.txt', 'launches_per_frame': len(recs),
-                'kernel_ms_per_step': t_ms, 'share_of_step': t_ms / ms_frame,
-                'share_note': 'kernel time of one frame / latency of one frame alone (%.3f ms); with %d frames in flight the '
-                              'steps overlap, so ms_per_step is below that latency' % (ms_frame, LANES),
-                'largest_launch': {'cin': top[3], 'cout': top[4], 'rows': top[5], 'ms': top[0],
-                                   'useful_tflops': top[2] / (top[0] * 1e-3) / 1e12, 'issued_tflops': top[1] / (top[0] * 1e-3) / 1e12},
-                'note': 'achieved = sum(2*pairs*Cin*Cout) / sum(CUDA-event time per launch) over the 21 sparse-conv launches of '
-                        'one frame, each re-issued 5x back to back; achieved_issued also counts the zero-filled (no-neighbour) '
-                        'slots the output-stationary tiles multiply'}
+            recs = spmod.time_launches(prof, reps=5)
+        except Exception as e:       # the headline numbers are already measured: never lose the line to the roofline pass
+            log('roofline pass failed: %r' % (e,))
+            recs = None
+        if recs:
+            t_ms = sum(r[0] for r in recs)
+            issued = sum(r[1] for r in recs)
+            useful = sum(r[2] for r in recs)
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+            except Exception:
+                pass
+            peak = peaks.get('bf16_tflops_sustained', 1400.0)
+            top = max(recs, key=lambda r: r[0])
+            # DRAM traffic of the largest launch from the committed `ncu --set full` capture (profiles/), if present
+            traffic = None
+            try:
+                txt = open(os.path.join(ROOT, 'profiles', 'prof_gemm_r01_final.txt')).read().split('== tc::gemm_kernel<256')[0]
+                rd = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_read.sum')][0]
+                wr = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_write.sum')][0]
+                traffic = (rd + wr) * 1e6      # ncu prints MB
+            except Exception:
+                pass
+            roof = {'kernel': 'tc::gemm_kernel (tcgen05 sparse-conv implicit GEMM; %d launches per frame)' % len(recs),
+                    'bound': 'tensor', 'achieved': useful / (t_ms * 1e-3) / 1e12, 'achieved_issued': issued / (t_ms * 1e-3) / 1e12,
+                    'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF/s sustained',
+                    'unit': 'TFLOP/s', 'frac': useful / (t_ms * 1e-3) / 1e12 / peak, 'traffic': traffic,
+                    'traffic_note': 'dram read+write bytes of the largest launch (stage-3 SubM 128->128; algorithmic 170 MB incl. the '
+                                    'neighbour table) from profiles/prof_gemm_r01_final.txt', 'launches_per_frame': len(recs),
+                    'kernel_ms_per_step': t_ms, 'share_of_step': t_ms / ms_frame,
+                    'share_note': 'kernel time of one frame / latency of one frame alone (%.3f ms); with %d frames in flight the '
+                                  'steps overlap, so ms_per_step is below that latency' % (ms_frame, LANES),
+                    'largest_launch': {'cin': top[3], 'cout': top[4], 'rows': top[5], 'ms': top[0],
+                                       'useful_tflops': top[2] / (top[0] * 1e-3) / 1e12, 'issued_tflops': top[1] / (top[0] * 1e-3) / 1e12},
+                    'note': 'achieved = sum(2*pairs*Cin*Cout) / sum(CUDA-event time per launch) over the 21 sparse-conv launches of '
+                            'one frame, each re-issued 5x back to back; achieved_issued = the 128x64xCout MMA blocks the kernel '
+                            'really walks (chunks skipped per tile excluded, zero-filled no-neighbour slots included)'}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_subprocess(args)

@@ -276,6 +276,32 @@ def implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, residu
     return _implicit_gemm(feats, rb, w_packed, cin, cout, scale, shift, residual, relu, out)
 
 
+def issued_flops(rb, cin, cout, kpad=None):
+    """FLOPs the kernel actually issues for one launch: it walks K in 64-wide chunks and skips a chunk for a whole
+    128-row tile when none of the taps the chunk covers has a neighbour in that tile; every other chunk is a
+    128 x 64 x Cout MMA block, zero-filled slots included.  Uses the tile-ordered table when the rulebook has one."""
+    n = rb.num_out if rb.num_dev is None else int(rb.num_dev.item())
+    nbr = rb.nbr_ordered if rb.nbr_ordered is not None else rb.nbr
+    taps = rb.taps
+    kpad = kpad if kpad is not None else (taps * cin + 63) // 64 * 64
+    valid = nbr[:, :n] >= 0
+    pad = (-n) % 128
+    if pad:
+        valid = torch.cat([valid, torch.zeros((taps, pad), dtype=torch.bool, device=valid.device)], 1)
+    tap_active = valid.view(taps, -1, 128).any(2)                       # [taps, tiles]
+    chunks = kpad // 64
+    q = torch.arange(chunks, device=valid.device)
+    t0 = (q * 64) // cin
+    t1 = torch.clamp((q * 64 + 63) // cin, max=taps - 1)
+    csum = torch.cat([torch.zeros((1, tap_active.shape[1]), dtype=torch.int32, device=valid.device),
+                      torch.cumsum(tap_active.int(), 0)], 0)            # prefix over taps
+    inside = t0 < taps
+    chunk_active = ((csum[t1 + 1] - csum[torch.clamp(t0, max=taps - 1)]) > 0) & inside[:, None]
+    tiles_without_any = (~chunk_active.any(0)).sum()                    # the kernel still issues one chunk there
+    blocks = int(chunk_active.sum().item()) + int(tiles_without_any.item())
+    return 2.0 * blocks * 128 * 64 * cout
+
+
 def time_launches(records, reps=5):
     """re-issue every recorded implicit-GEMM launch `reps` times back to back between CUDA events on the current
     stream (queue kept full, so the event time is kernel time) -> [(ms per launch, issued flops, useful flops)]."""
@@ -290,7 +316,7 @@ def time_launches(records, reps=5):
         e1.record()
         torch.cuda.synchronize()
         n = rb.num_out if rb.num_dev is None else int(rb.num_dev.item())
-        out.append((e0.elapsed_time(e1) / reps, 2.0 * n * rb.taps * cin * cout, useful_flops((rb, cin, cout)), cin, cout, n))
+        out.append((e0.elapsed_time(e1) / reps, issued_flops(rb, cin, cout, w.shape[1]), useful_flops((rb, cin, cout)), cin, cout, n))
     return out
 
 

@@ -159,3 +159,25 @@ def test_graphed_neck_bit_identical_with_tile_order():
             assert torch.equal(a, b)
     finally:
         sp.TILE_ORDER = None
+
+
+def test_issued_flops_counts_exactly_the_chunks_the_kernel_walks():
+    """bench.py's `achieved_issued` denominator: 64-wide K chunks skipped per 128-row tile when none of their taps has a
+    neighbour there (CPU tensors; the helper is pure index arithmetic)."""
+    from isfusion_b200.spconv import Rulebook, issued_flops
+    taps, n = 27, 300                                   # 3 tiles (128, 128, 44 rows)
+    nbr = torch.full((taps, 384), -1, dtype=torch.int32)
+    nbr[13, :n] = torch.arange(n, dtype=torch.int32)    # centre tap everywhere
+    nbr[0, 5] = 7                                       # tap 0 only in tile 0
+    nbr[26, 290] = 1                                    # tap 26 only in tile 2
+    rb = Rulebook(None, None, nbr, 384, taps, n)
+    # cin = 64: one chunk per tap -> tiles have 2, 1, 2 active chunks
+    assert issued_flops(rb, 64, 32) == 2.0 * 5 * 128 * 64 * 32
+    # cin = 128: two chunks per tap
+    assert issued_flops(rb, 128, 128) == 2.0 * 10 * 128 * 64 * 128
+    # cin = 32: chunk q covers taps 2q, 2q+1 -> taps 0 | 12,13 | 26 sit in chunks 0, 6, 13
+    assert issued_flops(rb, 32, 64) == 2.0 * 5 * 128 * 64 * 64
+    # a tile without any neighbour still costs one chunk (the accumulator must be defined)
+    nbr2 = torch.full((taps, 256), -1, dtype=torch.int32)
+    nbr2[13, :128] = 0
+    assert issued_flops(Rulebook(None, None, nbr2, 256, taps, 256), 64, 32) == 2.0 * 2 * 128 * 64 * 32
