@@ -189,8 +189,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': 1000.0 / fps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'isfusion_0075voxel fusion-neck forward, CPU oracle (restated reference)', 'points': cpu_points,
-                       'cloud': args.cloud, 'cams': 6, 'img': list(img_hw_of(args)), 'batch': 1},
+            'config': {'workload': 'BASELINE configs[1]: isfusion_0075voxel.py fusion-neck forward, synthetic nuScenes-shaped frame',
+                       'points_per_frame': cpu_points, 'cloud': args.cloud, 'cams': 6, 'img': list(img_hw_of(args)), 'bev': 180,
+                       'batch_per_gpu': 1, 'parallelism': 'host cores of the box (CPU oracle = restated reference, fp32)'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                              'stage_seconds': stages},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
