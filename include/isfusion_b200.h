@@ -39,7 +39,10 @@ const char* isf_last_error(void);
 unsigned long long isf_launch_count(int reset);
 /* runtime options: "gemm_cluster" = 1 | 2 : thread-block-cluster size of the tcgen05 GEMM (CTAs of a cluster
  * share every weight chunk through TMA multicast).  "gemm_v2" = 0 | 1 | 2 : opt-in warp-specialised GEMM schedule
- * (csrc/tc_gemm2.cuh; 1 = sparse-conv launches, 2 = every GEMM); 0 (default) = the validated kernel. */
+ * (csrc/tc_gemm2.cuh; 1 = sparse-conv launches, 2 = every GEMM); 0 (default) = the validated kernel.
+ * "gemm_v2_zskip" / "gemm_v2_io256" = 0 | 1 : zero-skip of all-missing 4-row copies / 32-byte epilogue accesses of
+ * that schedule (default 1).  "tile_order_drop_bits" = 0..26 : low occupancy-mask bits left out of the sort of
+ * isf_spconv_tile_order (fewer radix passes). */
 int isf_set_option(const char* name, int value);
 
 /* ---- a1: dynamic voxelization -------------------------------------------------

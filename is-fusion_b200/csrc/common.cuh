@@ -66,4 +66,5 @@ constexpr int ISF_NUM_SMS = 148;  // B200
 extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2), defined in error.cu
 extern int g_isf_gemm_v2_zskip;   // isf_set_option("gemm_v2_zskip", 0|1): zero-skip of the v2 producers (default 1)
 extern int g_isf_gemm_v2_io256;   // isf_set_option("gemm_v2_io256", 0|1): 32-byte epilogue loads / stores of the v2 kernel (default 1)
+extern int g_isf_tile_order_drop_bits;   // isf_set_option("tile_order_drop_bits", 0..26): low mask bits left out of the tile-order sort
 extern int g_isf_gemm_v2;         // isf_set_option("gemm_v2", 0|1|2): opt-in warp-specialised GEMM (tc_gemm2.cuh)

@@ -643,11 +643,15 @@ extern "C" int isf_spconv_tile_order(const int* nbr, long long nbr_stride, int t
   if (v > 0) {
     tile_order_keys_kernel<<<isf_cdiv(v, 256), 256, 0, st>>>(nbr, nbr_stride, taps, v, v_dev, chunk_log2, invalid_bit, tb, k0, r0);
     ISF_LAUNCH_CHECK();
-    ISF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, cb, k0, k1, r0, r1, v, 0, invalid_bit + 1, st));
+    // isf_set_option("tile_order_drop_bits", d): the d least significant mask bits (near in-plane offsets) are left
+    // out of the sort -> fewer radix passes; rows that differ only there keep their storage order (stable sort)
+    int begin_bit = ::g_isf_tile_order_drop_bits;
+    if (begin_bit > taps - 1) begin_bit = taps - 1;
+    ISF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, cb, k0, k1, r0, r1, v, begin_bit, invalid_bit + 1, st));
   }
   tile_order_apply_kernel<<<(int)((nbr_stride + 255) / 256), 256, 0, st>>>(nbr, nbr_stride, taps, v, v_dev, r1, nbr_out, row_perm);
   ISF_LAUNCH_CHECK();
-  isf_count_launch(v > 0 ? 4 + (invalid_bit + 1 + 7) / 8 : 1);   // keys + CUB (histogram, scan, one onesweep per 8 key bits) + apply
+  isf_count_launch(v > 0 ? 4 + (invalid_bit + 1 - (::g_isf_tile_order_drop_bits > taps - 1 ? taps - 1 : ::g_isf_tile_order_drop_bits) + 7) / 8 : 1);   // keys + CUB (histogram, scan, one onesweep per 8 key bits) + apply
   return ISF_OK;
 }
 

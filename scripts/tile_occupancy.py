@@ -54,15 +54,16 @@ def library_tap_bits(ksize=(3, 3, 3)):
     return [int(pos[k]) for k in range(taps)]
 
 
-def tile_order_model(valid, chunk_log2=31, ksize=(3, 3, 3)):
-    """CPU model of isf_spconv_tile_order: stable sort of the rows by (row >> chunk_log2, occupancy mask)."""
+def tile_order_model(valid, chunk_log2=31, ksize=(3, 3, 3), drop_bits=0):
+    """CPU model of isf_spconv_tile_order: stable sort of the rows by (row >> chunk_log2, occupancy mask), the
+    `drop_bits` least significant key bits left out (isf_set_option("tile_order_drop_bits"))."""
     pos = library_tap_bits(ksize)
     key = np.zeros(valid.shape[1], np.uint64)
     for k in range(valid.shape[0]):
         key |= valid[k].astype(np.uint64) << np.uint64(pos[k])
     if chunk_log2 < 31:
         key |= (np.arange(valid.shape[1], dtype=np.uint64) >> np.uint64(chunk_log2)) << np.uint64(valid.shape[0])
-    return np.argsort(key, kind='stable')
+    return np.argsort(key >> np.uint64(drop_bits), kind='stable')
 
 
 def orders(idx):

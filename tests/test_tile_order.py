@@ -94,6 +94,13 @@ def test_device_order_equals_model(chunk):
     model = to.tile_order_model(valid, chunk)
     assert np.array_equal(perm[:v].cpu().numpy(), model)
     assert (perm[v:] == -1).all() and (out[:, v:] == -1).all()
+    from isfusion_b200 import _lib as L
+    try:        # fewer sorted bits: same model with the low key bits dropped
+        L.set_option('tile_order_drop_bits', 11)
+        _, perm11 = _device_order(rb.nbr, v, chunk)
+        assert np.array_equal(perm11[:v].cpu().numpy(), to.tile_order_model(valid, chunk, drop_bits=11))
+    finally:
+        L.set_option('tile_order_drop_bits', 0)
     assert torch.equal(out[:, :v], rb.nbr[:, perm[:v].long()])
     # capacity mode: only the first n rows are valid, the tail of the capacity sorts last and is dropped
     n = v - 1000
