@@ -42,7 +42,8 @@ unsigned long long isf_launch_count(int reset);
  * (csrc/tc_gemm2.cuh; 1 = sparse-conv launches, 2 = every GEMM); 0 (default) = the validated kernel.
  * "gemm_v2_zskip" / "gemm_v2_io256" = 0 | 1 : zero-skip of all-missing 4-row copies / 32-byte epilogue accesses of
  * that schedule (default 1).  "tile_order_drop_bits" = 0..26 : low occupancy-mask bits left out of the sort of
- * isf_spconv_tile_order (fewer radix passes). */
+ * isf_spconv_tile_order (fewer radix passes).  "nbr_rows" = 0 | 1 : row-per-thread kernel behind
+ * isf_spconv_neighbors_bitmap (one bitmap word load per (kz, ky) instead of per tap; same results). */
 int isf_set_option(const char* name, int value);
 
 /* ---- a1: dynamic voxelization -------------------------------------------------

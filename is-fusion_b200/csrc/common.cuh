@@ -67,4 +67,5 @@ extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2), define
 extern int g_isf_gemm_v2_zskip;   // isf_set_option("gemm_v2_zskip", 0|1): zero-skip of the v2 producers (default 1)
 extern int g_isf_gemm_v2_io256;   // isf_set_option("gemm_v2_io256", 0|1): 32-byte epilogue loads / stores of the v2 kernel (default 1)
 extern int g_isf_tile_order_drop_bits;   // isf_set_option("tile_order_drop_bits", 0..26): low mask bits left out of the tile-order sort
+extern int g_isf_nbr_rows;        // isf_set_option("nbr_rows", 0|1): row-per-thread neighbour-table kernel (opt-in)
 extern int g_isf_gemm_v2;         // isf_set_option("gemm_v2", 0|1|2): opt-in warp-specialised GEMM (tc_gemm2.cuh)

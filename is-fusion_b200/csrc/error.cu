@@ -30,6 +30,7 @@ int g_isf_gemm_v2 = 0;
 int g_isf_gemm_v2_zskip = 1;
 int g_isf_gemm_v2_io256 = 1;
 int g_isf_tile_order_drop_bits = 0;
+int g_isf_nbr_rows = 0;
 extern "C" int isf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_cluster") == 0 && (value == 1 || value == 2)) {
     g_isf_gemm_cluster = value;
@@ -45,6 +46,10 @@ extern "C" int isf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "tile_order_drop_bits") == 0 && value >= 0 && value <= 26) {
     g_isf_tile_order_drop_bits = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "nbr_rows") == 0 && (value == 0 || value == 1)) {
+    g_isf_nbr_rows = value;
     return ISF_OK;
   }
   if (name && strcmp(name, "gemm_v2_io256") == 0 && (value == 0 || value == 1)) {

@@ -92,6 +92,8 @@ class Rulebook:
 # storage order (default); an int = rows regrouped by neighbour pattern inside chunks of 2**TILE_ORDER consecutive rows
 # (31 = one global sort).  Results are bit-identical either way.  Environment: ISF_TILE_ORDER=<int>.
 TILE_ORDER = int(os.environ['ISF_TILE_ORDER']) if os.environ.get('ISF_TILE_ORDER') else None
+if os.environ.get('ISF_NBR_ROWS'):      # opt-in row-per-thread neighbour-table kernel (csrc/spconv.cu nbr_bitmap_rows_kernel)
+    L.set_option('nbr_rows', int(os.environ['ISF_NBR_ROWS']))
 
 
 def _tile_order(rb, ksize):

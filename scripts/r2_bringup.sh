@@ -14,6 +14,11 @@ timeout 300 python -m pytest tests/test_reference_fixtures_gpu.py -x -q -m gpu >
 echo "== per-layer A/B"            | tee -a gpurun_out/r2_bringup.log
 timeout 400 python scripts/bench_gemm_layers.py --v2 --tile-order 12,16,31    >> gpurun_out/r2_bringup.log 2>&1
 unset ISF_EXPERIMENTAL
+echo "== neighbour-table kernel A/B (launch list, second frame = warm)" | tee -a gpurun_out/r2_bringup.log
+for opt in 0 1; do
+  ISF_NBR_ROWS=$opt timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:nbr_bitmap --csv \
+    --log-file gpurun_out/r2_nbr_rows_$opt.csv python bench.py --eager-only --steps 1 --warmup 1 --frames 2 >> gpurun_out/r2_bringup.log 2>&1
+done
 echo "== bench: default, then tile order 31 / 16" | tee -a gpurun_out/r2_bringup.log
 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline           > gpurun_out/r2_bench_default.json 2>> gpurun_out/r2_bringup.log
 ISF_TILE_ORDER=31 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_ord31.json 2>> gpurun_out/r2_bringup.log

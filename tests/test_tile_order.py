@@ -188,3 +188,32 @@ def test_issued_flops_counts_exactly_the_chunks_the_kernel_walks():
     nbr2 = torch.full((taps, 256), -1, dtype=torch.int32)
     nbr2[13, :128] = 0
     assert issued_flops(Rulebook(None, None, nbr2, 256, taps, 256), 64, 32) == 2.0 * 2 * 128 * 64 * 32
+
+
+@pytest.mark.gpu
+@experimental
+def test_row_per_thread_neighbour_kernel_bit_identical():
+    """isf_set_option("nbr_rows", 1): same neighbour tables as the tap-per-thread kernel for every conv geometry of the
+    encoder, exact and capacity mode."""
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.spconv import SparseConvTensor, build_rulebook
+    from test_spconv_gpu import _rand_tensor
+    x = _rand_tensor([41, 96, 96], 30000, 16, 2, 3, clustered=True)
+    order = torch.argsort(((x.indices[:, 0].long() * 41 + x.indices[:, 1]) * 96 + x.indices[:, 2]) * 96 + x.indices[:, 3])
+    idx = x.indices[order].contiguous().cuda()
+    geos = [([3, 3, 3], [1, 1, 1], [1, 1, 1], True), ([3, 3, 3], [2, 2, 2], [1, 1, 1], False),
+            ([3, 3, 3], [2, 2, 2], [0, 1, 1], False), ([3, 1, 1], [2, 1, 1], [0, 0, 0], False)]
+    try:
+        for ks, st, pd, subm in geos:
+            tabs = []
+            for opt in (0, 1):
+                L.set_option('nbr_rows', opt)
+                xt = SparseConvTensor(None, idx, x.spatial_shape, x.batch_size)
+                xt.sorted = True                                   # bitmap-rank rulebook
+                rb = build_rulebook(xt, ks, st, pd, [1, 1, 1], subm)
+                torch.cuda.synchronize()
+                tabs.append((rb.nbr[:, :rb.num_out].clone(), rb.out_indices.clone()))
+            assert torch.equal(tabs[0][1], tabs[1][1])
+            assert torch.equal(tabs[0][0], tabs[1][0]), (ks, st, pd, subm)
+    finally:
+        L.set_option('nbr_rows', 0)
