@@ -211,6 +211,12 @@ int isf_spconv_tile_order_workspace_size(int v, size_t* bytes);
 int isf_spconv_tile_order_bits(const int* ksize, int taps, unsigned char* pos);   /* host-only: key bit of every tap */
 int isf_spconv_tile_order(const int* nbr, long long nbr_stride, int taps, const int* ksize, int v, const int* v_dev,
                           int chunk_log2, int* nbr_out, int* row_perm, void* workspace, size_t ws_bytes, void* stream);
+/* isf_spconv_neighbors_bitmap followed by isf_spconv_tile_order, fused: the occupancy masks come straight from the
+ * bitmap, and the table is written in tile order (the plain table is never materialised).  Same outputs. */
+int isf_spconv_neighbors_bitmap_ordered(const int* out_indices, int v_out, const int* v_out_dev, const unsigned int* in_bits,
+                                        const int* in_prefix, const int* in_shape, const int* ksize, const int* stride,
+                                        const int* padding, const int* dilation, int subm, int chunk_log2, int* nbr_out,
+                                        long long nbr_stride, int* row_perm, void* workspace, size_t ws_bytes, void* stream);
 int isf_spconv_implicit_gemm_ordered(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,
                                      const int* nbr_ordered, long long nbr_stride, int taps, int v_out,
                                      const int* v_out_dev, const int* row_perm, const float* scale, const float* shift,

@@ -405,15 +405,40 @@ __global__ void __launch_bounds__(256) nbr_bitmap_kernel(const int* __restrict__
 // kernel offsets itself.  The kW taps of one (kz, ky) are adjacent cells of the input map, i.e. adjacent bits of (almost
 // always) one bitmap word, so the thread loads a word + its prefix once per (kz, ky) instead of once per tap: 9-18
 // dependent loads per row instead of 54; the 27 stores of a warp stay coalesced (consecutive rows).  Same results.
+struct TapBits { unsigned char pos[32]; };
+
+// MODE 0: nbr[k][j] for row j.  MODE 1: only the tile-order sort key of row j (occupancy mask of its kernel offsets, no
+// prefix loads, no table writes) -> keys[j], rows[j] = j.  MODE 2: slot i computes storage row perm[i] and writes
+// nbr[k][i] + row_perm[i] (-1 beyond the valid rows): the tile-ordered table without a detour through the plain one.
+template <int MODE>
 __global__ void __launch_bounds__(256) nbr_bitmap_rows_kernel(const int* __restrict__ out_indices, int v_out,
                                                               const int* v_out_dev, ConvGeom g,
                                                               const unsigned int* __restrict__ bits,
                                                               const int* __restrict__ prefix, int* __restrict__ nbr,
-                                                              long long nbr_stride) {
-  const int n = v_out_dev ? *v_out_dev : v_out;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+                                                              long long nbr_stride, const int* __restrict__ perm,
+                                                              int* __restrict__ row_perm, TapBits tb, int chunk_shift,
+                                                              int invalid_bit, unsigned long long* __restrict__ keys,
+                                                              int* __restrict__ rows) {
+  const int n = v_out_dev ? min(*v_out_dev, v_out) : v_out;
+  const int limit = MODE == 0 ? n : (MODE == 1 ? v_out : (int)nbr_stride);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < limit; i += gridDim.x * blockDim.x) {
+    int j = i;
+    if (MODE == 1 && i >= n) {                  // capacity rows beyond the device-side count sort last
+      keys[i] = 1ull << invalid_bit;
+      rows[i] = i;
+      continue;
+    }
+    if (MODE == 2) {
+      j = i < n ? perm[i] : -1;
+      row_perm[i] = j;
+      if (j < 0) {
+        for (int k = 0; k < g.kvol; ++k) nbr[(long long)k * nbr_stride + i] = -1;
+        continue;
+      }
+    }
     const int4 o = *(const int4*)(out_indices + (size_t)j * 4);      // (b, z, y, x)
     const int x0 = o.w * g.stride[2] - g.pad[2];
+    unsigned int mask = 0;
     int k = 0;
     for (int kz = 0; kz < g.ksize[0]; ++kz) {
       const int iz = o.y * g.stride[0] - g.pad[0] + kz * g.dil[0];
@@ -429,12 +454,23 @@ __global__ void __launch_bounds__(256) nbr_bitmap_rows_kernel(const int* __restr
           if (row_ok && ix >= 0 && ix < g.in_shape[2]) {
             const unsigned int key = key_row + (unsigned int)ix;
             const unsigned int w = key >> 5, b = key & 31;
-            if (w != cached_w) { cached_w = w; word = bits[w]; pre = (word != 0u) ? prefix[w] : 0; }
-            if ((word >> b) & 1u) r = pre + __popc(word & ((1u << b) - 1u));
+            if (w != cached_w) {
+              cached_w = w;
+              word = bits[w];
+              if (MODE != 1) pre = (word != 0u) ? prefix[w] : 0;
+            }
+            if ((word >> b) & 1u) {
+              if (MODE == 1) mask |= 1u << tb.pos[k];
+              else r = pre + __popc(word & ((1u << b) - 1u));
+            }
           }
-          nbr[(long long)k * nbr_stride + j] = r;
+          if (MODE != 1) nbr[(long long)k * nbr_stride + i] = r;
         }
       }
+    }
+    if (MODE == 1) {
+      keys[i] = ((unsigned long long)(chunk_shift < 31 ? (i >> chunk_shift) : 0) << g.kvol) | mask;
+      rows[i] = i;
     }
   }
 }
@@ -536,8 +572,8 @@ extern "C" int isf_spconv_neighbors_bitmap(const int* out_indices, int v_out, co
   if (::g_isf_nbr_rows && ((uintptr_t)out_indices & 15) == 0) {      // the row kernel reads a coordinate as one int4
     int rb = isf_cdiv(v_out, 256);
     if (rb > ISF_NUM_SMS * 16) rb = ISF_NUM_SMS * 16;
-    nbr_bitmap_rows_kernel<<<rb, 256, 0, (cudaStream_t)stream>>>(out_indices, v_out, v_out_dev, g, in_bits, in_prefix, nbr,
-                                                                 nbr_stride);
+    nbr_bitmap_rows_kernel<0><<<rb, 256, 0, (cudaStream_t)stream>>>(out_indices, v_out, v_out_dev, g, in_bits, in_prefix, nbr,
+                                                                    nbr_stride, nullptr, nullptr, TapBits{}, 0, 0, nullptr, nullptr);
   } else {
     nbr_bitmap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_indices, v_out, v_out_dev, g, in_bits, in_prefix, nbr,
                                                                 nbr_stride);
@@ -586,8 +622,6 @@ extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const voi
 // kernel reads the permuted neighbour table and scatters / gathers its epilogue rows through row_perm
 // (GemmParams::out_rows / res_rows), so results are bit-identical to the unordered launch.
 // ------------------------------------------------------------------------------------------------
-struct TapBits { unsigned char pos[32]; };
-
 __global__ void __launch_bounds__(256) tile_order_keys_kernel(const int* __restrict__ nbr, long long nbr_stride, int taps,
                                                               int v, const int* __restrict__ v_dev, int chunk_shift,
                                                               int invalid_bit, TapBits tb,
@@ -697,6 +731,53 @@ extern "C" int isf_spconv_tile_order(const int* nbr, long long nbr_stride, int t
   tile_order_apply_kernel<<<(int)((nbr_stride + 255) / 256), 256, 0, st>>>(nbr, nbr_stride, taps, v, v_dev, r1, nbr_out, row_perm);
   ISF_LAUNCH_CHECK();
   isf_count_launch(v > 0 ? 4 + (invalid_bit + 1 - (::g_isf_tile_order_drop_bits > taps - 1 ? taps - 1 : ::g_isf_tile_order_drop_bits) + 7) / 8 : 1);   // keys + CUB (histogram, scan, one onesweep per 8 key bits) + apply
+  return ISF_OK;
+}
+
+// isf_spconv_neighbors_bitmap + isf_spconv_tile_order in one: occupancy masks straight from the bitmap (mode-1 row
+// kernel) -> sort -> the table is WRITTEN in tile order (mode-2 row kernel).  The plain table is never materialised
+// and nothing is gathered back: two row-kernel passes + one radix sort.  Same nbr_out / row_perm as the two-call path.
+extern "C" int isf_spconv_neighbors_bitmap_ordered(const int* out_indices, int v_out, const int* v_out_dev,
+                                                   const unsigned int* in_bits, const int* in_prefix, const int* in_shape,
+                                                   const int* ksize, const int* stride, const int* padding,
+                                                   const int* dilation, int subm, int chunk_log2, int* nbr_out,
+                                                   long long nbr_stride, int* row_perm, void* workspace, size_t ws_bytes,
+                                                   void* stream) {
+  ISF_CHECK_ARG(v_out >= 0 && in_shape && ksize && in_bits && in_prefix && nbr_stride >= v_out && nbr_out && row_perm);
+  ISF_CHECK_ARG(subm || (stride && padding));
+  ISF_CHECK_ARG(chunk_log2 >= 7 && (v_out == 0 || (out_indices && ((uintptr_t)out_indices & 15) == 0)));
+  ConvGeom g;
+  fill_geom(&g, in_shape, ksize, stride, padding, dilation, subm);
+  ISF_CHECK_ARG(g.kvol >= 1 && g.kvol <= 27);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vv = v_out > 0 ? v_out : 1;
+  IsfArena A(workspace, ws_bytes);
+  unsigned long long *k0, *k1; int *r0, *r1; char* tmp; size_t cb;
+  tile_order_carve(A, vv, &k0, &k1, &r0, &r1, &tmp, &cb);
+  if (!A.ok || !workspace) { isf_set_error("isf_spconv_neighbors_bitmap_ordered: workspace too small"); return ISF_ERR_WORKSPACE; }
+  TapBits tb{};
+  tile_order_bits(g.ksize, g.kvol, tb.pos);
+  int chunk_bits = 0;
+  if (chunk_log2 < 31) while (((long long)(vv - 1) >> chunk_log2) >> chunk_bits) ++chunk_bits;
+  const int invalid_bit = g.kvol + chunk_bits;
+  int begin_bit = ::g_isf_tile_order_drop_bits;
+  if (begin_bit > g.kvol - 1) begin_bit = g.kvol - 1;
+  int launches = 1;
+  if (v_out > 0) {
+    int rb = isf_cdiv(v_out, 256);
+    if (rb > ISF_NUM_SMS * 16) rb = ISF_NUM_SMS * 16;
+    nbr_bitmap_rows_kernel<1><<<rb, 256, 0, st>>>(out_indices, v_out, v_out_dev, g, in_bits, in_prefix, nullptr, nbr_stride,
+                                                  nullptr, nullptr, tb, chunk_log2, invalid_bit, k0, r0);
+    ISF_LAUNCH_CHECK();
+    ISF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, cb, k0, k1, r0, r1, v_out, begin_bit, invalid_bit + 1, st));
+    launches += 3 + (invalid_bit + 1 - begin_bit + 7) / 8;
+  }
+  int rb2 = (int)((nbr_stride + 255) / 256);
+  if (rb2 > ISF_NUM_SMS * 16) rb2 = ISF_NUM_SMS * 16;
+  nbr_bitmap_rows_kernel<2><<<rb2, 256, 0, st>>>(out_indices, v_out, v_out_dev, g, in_bits, in_prefix, nbr_out, nbr_stride, r1,
+                                                 row_perm, tb, 0, 0, nullptr, nullptr);
+  ISF_LAUNCH_CHECK();
+  isf_count_launch(launches);
   return ISF_OK;
 }
 

@@ -96,6 +96,9 @@ if os.environ.get('ISF_NBR_ROWS'):      # opt-in row-per-thread neighbour-table 
     L.set_option('nbr_rows', int(os.environ['ISF_NBR_ROWS']))
 
 
+TILE_ORDER_FUSED = os.environ.get('ISF_TILE_ORDER_FUSED', '1') != '0'   # sorted tensors: build the table in tile order directly
+
+
 def _tile_order(rb, ksize):
     """attach the regrouped neighbour table to a freshly built rulebook (same stream as the rulebook build)."""
     if TILE_ORDER is None or rb.taps < 2:
@@ -204,6 +207,18 @@ def build_rulebook_bitmap(x, ksize, stride, padding, dilation, subm, out_capacit
         x.indice_dict[('bitmap', out_indices.data_ptr(), out_indices.shape[0])] = (obits, oprefix)
     stride_rows = max((v_out + 127) // 128 * 128, 128)
     nbr = torch.empty((taps, stride_rows), dtype=torch.int32, device=dev)
+    if TILE_ORDER is not None and TILE_ORDER_FUSED and taps >= 2 and out_indices.data_ptr() % 16 == 0:
+        wsb = ctypes.c_size_t(0)
+        L.check(lib.isf_spconv_tile_order_workspace_size(v_out, ctypes.byref(wsb)))
+        ws = L.workspace(wsb.value, dev)
+        perm = torch.empty(stride_rows, dtype=torch.int32, device=dev)
+        L.check(lib.isf_spconv_neighbors_bitmap_ordered(
+            L.ptr(out_indices), v_out, L.ptr(num_dev), L.ptr(bits), L.ptr(prefix), L.host_i32(x.spatial_shape), L.host_i32(ksize),
+            L.host_i32(stride), L.host_i32(padding), L.host_i32(dilation), 1 if subm else 0, int(TILE_ORDER), L.ptr(nbr),
+            ctypes.c_longlong(stride_rows), L.ptr(perm), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        rb = Rulebook(out_indices, out_shape, nbr, stride_rows, taps, v_out, num_dev)
+        rb.nbr_ordered, rb.row_perm = nbr, perm          # rb.nbr (same tensor) only serves the pair count
+        return rb
     L.check(lib.isf_spconv_neighbors_bitmap(L.ptr(out_indices), v_out, L.ptr(num_dev), L.ptr(bits), L.ptr(prefix),
                                             L.host_i32(x.spatial_shape), L.host_i32(ksize), L.host_i32(stride),
                                             L.host_i32(padding), L.host_i32(dilation), 1 if subm else 0, L.ptr(nbr),

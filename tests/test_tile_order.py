@@ -113,6 +113,35 @@ def test_device_order_equals_model(chunk):
 @pytest.mark.gpu
 @experimental
 @pytest.mark.parametrize('chunk', [12, 31])
+def test_fused_ordered_rulebook_equals_two_call_path(chunk):
+    """isf_spconv_neighbors_bitmap_ordered == isf_spconv_neighbors_bitmap + isf_spconv_tile_order, every geometry."""
+    import isfusion_b200.spconv as sp
+    from test_spconv_gpu import _rand_tensor
+    x = _rand_tensor([41, 96, 96], 30000, 16, 2, 3, clustered=True)
+    order = torch.argsort(((x.indices[:, 0].long() * 41 + x.indices[:, 1]) * 96 + x.indices[:, 2]) * 96 + x.indices[:, 3])
+    idx = x.indices[order].contiguous().cuda()
+    geos = [([3, 3, 3], [1, 1, 1], [1, 1, 1], True), ([3, 3, 3], [2, 2, 2], [1, 1, 1], False),
+            ([3, 3, 3], [2, 2, 2], [0, 1, 1], False), ([3, 1, 1], [2, 1, 1], [0, 0, 0], False)]
+    try:
+        sp.TILE_ORDER = chunk
+        for ks, st, pd, subm in geos:
+            res = []
+            for fused in (False, True):
+                sp.TILE_ORDER_FUSED = fused
+                xt = sp.SparseConvTensor(None, idx, x.spatial_shape, x.batch_size)
+                xt.sorted = True
+                rb = sp.build_rulebook(xt, ks, st, pd, [1, 1, 1], subm)
+                torch.cuda.synchronize()
+                res.append((rb.nbr_ordered.clone(), rb.row_perm.clone()))
+            assert torch.equal(res[0][1], res[1][1]), (ks, st, pd, subm)
+            assert torch.equal(res[0][0], res[1][0]), (ks, st, pd, subm)
+    finally:
+        sp.TILE_ORDER, sp.TILE_ORDER_FUSED = None, True
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.parametrize('chunk', [12, 31])
 def test_sparse_encoder_bit_identical_with_tile_order(chunk):
     import isfusion_b200.spconv as sp
     from isfusion_b200.sparse_encoder import SparseEncoder
