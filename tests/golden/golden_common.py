@@ -62,13 +62,33 @@ def backbone_cfg():
                 norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), conv_cfg=dict(type='Conv2d', bias=False))
 
 
-def fusion_inputs(bs=2, seed=0):
+def fusion_cfg_full():
+    """the config's own sizes (isfusion_0075voxel.py:84-97): 180x180 BEV, 30x30 windows, 90x90 second level."""
+    c = fusion_cfg()
+    c.update(bev_size=180, grid_size=[[180, 180, 1], [90, 90, 1]])
+    return c
+
+
+def sample_positions(shape, n=4096, seed=0):
+    """n flat positions of a tensor of `shape` (fixtures of full-size maps hold samples + moments, not the maps)."""
+    total = int(np.prod(shape))
+    return _rs('samples%s' % (tuple(shape),), seed).randint(0, total, n)
+
+
+def fusion_inputs(bs=2, seed=0, bev=None, pillars_per_frame=300):
     """Pillars (zero-padded to 12 points like the hard voxelizer), camera features, LiDAR BEV, calibration."""
+    global BEV
+    if bev is not None and bev != BEV:          # full-size case: same generator on the bigger grid
+        saved, BEV = BEV, bev
+        try:
+            return fusion_inputs(bs, seed + 100, None, pillars_per_frame)
+        finally:
+            BEV = saved
     r = _rs('fusion_inputs', seed)
     cell = (PC_RANGE[3] - PC_RANGE[0]) / BEV
     pillars, coors = [], []
     for b in range(bs):
-        m = 300 + 40 * b
+        m = pillars_per_frame + 40 * b
         lin = r.permutation(BEV * BEV)[:m]                    # first-come order is arbitrary: keep it unsorted
         y, x = lin // BEV, lin % BEV
         n = r.randint(1, NPTS + 1, size=m)

@@ -11,6 +11,7 @@ Fixtures (checked by tests/test_oracle_vs_reference.py against oracle/):
   ref_fusion.npz  : ISFusionEncoder.forward + SECONDV2 stages (fusion_encoder.py:1152-1189, second.py:200-230) on
                     a 24x24 BEV, B = 2: both output maps, the instance heat-map, img_fv_to_bev (every 8th channel),
                     conv_fusion output (every 8th channel); SECONDFPN on the two maps (every 8th channel).
+  ref_fusion_full.npz : the same at the config's own sizes (180x180 / 90x90, B = 1): sampled values + moments.
   ref_sst.npz     : SSTInputLayerV2 (shuffle off) window/slot indices, positional embedding, key mask for both
                     shifts, and SSTv2 level-0 output on those tokens.
   ref_vfe.npz     : DynamicVFE.forward (voxel_encoder.py:452-547) features + coordinates; DynamicScatter mean.
@@ -61,6 +62,28 @@ def fusion(R):
                         keys_fpn=np.array(sorted(fpn.state_dict().keys())))
     print('fusion:', [tuple(f.shape) for f in feats], tuple(hm.shape), 'neck', tuple(neck.shape),
           'nonzero img_bev cells', int((img_bev.abs().sum(1) > 0).sum()))
+
+
+@torch.no_grad()
+def fusion_full(R):
+    """ref_fusion_full.npz: the same reference run at the CONFIG's sizes (180x180 BEV, B = 1, 6000 pillars): 4096 sampled
+    values + first / second moments of every output (the maps themselves are 20 MB)."""
+    enc = gc.fill_state(R.ISFusionEncoder(**gc.fusion_cfg_full()), 1).eval()
+    bb = gc.fill_state(R.SECONDV2(**gc.backbone_cfg()), 2).eval()
+    inp = gc.fusion_inputs(bs=1, bev=180, pillars_per_frame=6000)
+    pts_metas = dict(pillars=inp['pillars'], pillars_num_points=None, pillar_coors=inp['pillar_coors'], pts=None, pillar_size=None)
+    torch.manual_seed(0)
+    feats, hm = enc(inp['img_feats'], inp['lidar_feats'], 1, pts_backbone=bb, pts_metas=pts_metas, img_metas=inp['img_metas'],
+                    lidar2img=inp['lidar2img'], img_aug_matrix=inp['img_aug_matrix'], lidar_aug_matrix=inp['lidar_aug_matrix'])
+    out = {}
+    for name, t in (('feat0', feats[0]), ('feat1', feats[1]), ('heatmap', hm)):
+        flat = _np(t).reshape(-1)
+        out[name + '_samples'] = flat[gc.sample_positions(t.shape)]
+        out[name + '_moments'] = np.array([flat.mean(), np.abs(flat).mean(), (flat.astype(np.float64) ** 2).mean(), np.abs(flat).max()])
+        out[name + '_shape'] = np.array(t.shape)
+    np.savez_compressed(os.path.join(HERE, 'ref_fusion_full.npz'), **out)
+    print('fusion_full:', {k: v.tolist() for k, v in out.items() if k.endswith('_shape')},
+          {k: np.round(v, 4).tolist() for k, v in out.items() if k.endswith('_moments')})
 
 
 @torch.no_grad()
@@ -140,7 +163,7 @@ def head(R):
 
 if __name__ == '__main__':
     R = ref_shim.install()
-    which = sys.argv[1:] or ['fusion', 'sst', 'vfe', 'sparse', 'head']
+    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head']
     for w in which:
         globals()[w](R)
     for f in sorted(os.listdir(HERE)):

@@ -154,3 +154,24 @@ def test_transfusion_head_forward_and_decode_match_reference():
         assert np.array_equal(b['labels'].numpy(), g['box%d_labels' % i])
         _close(b['scores'], g['box%d_scores' % i], 'scores', 1e-4)
         _close(b['bboxes'], g['box%d_bboxes' % i], 'bboxes', 1e-4)
+
+
+def test_fusion_encoder_at_config_size_matches_reference_samples():
+    """The same reference run at the config's own sizes (180x180 BEV with 30x30 (+31x31 shifted) windows, 90x90 second
+    level, 200 instances of 324 000 scores): 4096 sampled values and the moments of every output map."""
+    g = _load('ref_fusion_full.npz')
+    enc = gc.fill_state(fusion_ops.ISFusionEncoder(**gc.fusion_cfg_full()), 1).eval()
+    bb = gc.fill_state(fusion_ops.SECONDV2(**gc.backbone_cfg()), 2).eval()
+    inp = gc.fusion_inputs(bs=1, bev=180, pillars_per_frame=6000)
+    pts_metas = dict(pillars=inp['pillars'], pillars_num_points=None, pillar_coors=inp['pillar_coors'], pts=None, pillar_size=None)
+    torch.manual_seed(3)
+    feats, hm = enc(inp['img_feats'], inp['lidar_feats'], 1, pts_backbone=bb, pts_metas=pts_metas, img_metas=inp['img_metas'],
+                    lidar2img=inp['lidar2img'], img_aug_matrix=inp['img_aug_matrix'], lidar_aug_matrix=inp['lidar_aug_matrix'])
+    for name, t in (('feat0', feats[0]), ('feat1', feats[1]), ('heatmap', hm)):
+        assert list(t.shape) == g[name + '_shape'].tolist()
+        flat = t.numpy().reshape(-1)
+        ref = g[name + '_samples']
+        scale = float(g[name + '_moments'][3])
+        assert np.abs(flat[gc.sample_positions(t.shape)] - ref).max() < TOL * scale, name
+        mom = np.array([flat.mean(), np.abs(flat).mean(), (flat.astype(np.float64) ** 2).mean(), np.abs(flat).max()])
+        assert np.allclose(mom, g[name + '_moments'], rtol=1e-4), (name, mom, g[name + '_moments'])

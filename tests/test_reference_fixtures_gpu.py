@@ -105,3 +105,22 @@ def test_transfusion_head_against_reference_run():
         assert np.abs(a - r)[m].max() < 5e-2 * max(1.0, np.abs(r).max()), k
     boxes = net.get_bboxes(res)
     assert len(boxes) == 2 and boxes[0]['bboxes'].shape[1] == 9
+
+
+def test_fusion_encoder_at_config_size_against_reference_samples():
+    """The CUDA fusion encoder at the config's sizes (180x180 BEV, B = 1) against 4096 sampled values of the reference's
+    own run (tests/golden/ref_fusion_full.npz)."""
+    from isfusion_b200.fusion_encoder import ISFusionEncoder, SECONDV2
+    g = _g('ref_fusion_full.npz')
+    enc = gc.fill_state(ISFusionEncoder(**gc.fusion_cfg_full()), 1).cuda().eval()
+    bb = gc.fill_state(SECONDV2(**gc.backbone_cfg()), 2).cuda().eval()
+    inp = gc.fusion_inputs(bs=1, bev=180, pillars_per_frame=6000)
+    pm = dict(pillars=inp['pillars'].cuda(), pillars_num_points=None, pillar_coors=inp['pillar_coors'].cuda(), pts=None,
+              pillar_size=None)
+    feats, hm = enc([t.cuda() for t in inp['img_feats']], inp['lidar_feats'].cuda(), 1, pts_metas=pm, img_metas=inp['img_metas'],
+                    pts_backbone=bb, lidar2img=inp['lidar2img'], img_aug_matrix=inp['img_aug_matrix'],
+                    lidar_aug_matrix=inp['lidar_aug_matrix'])
+    for name, t, bar in (('heatmap', hm, 5e-3), ('feat0', feats[0], 1e-2), ('feat1', feats[1], 1e-2)):
+        assert list(t.shape) == g[name + '_shape'].tolist()
+        got = t.float().cpu().numpy().reshape(-1)[gc.sample_positions(t.shape)]
+        assert _rel(got, g[name + '_samples']) < bar, name
