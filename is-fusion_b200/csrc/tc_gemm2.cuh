@@ -17,6 +17,8 @@
 //     hidden), the neighbour tile / chunk list in smem are double-buffered;
 //   * 32-byte epilogue accesses (v2_flags bits 1, 2; isf_set_option("gemm_v2_io256", 0|1)): residual rows and fp16 output
 //     rows move as LDG/STG.E.ENL2.256 — a full sector per lane — instead of 16-byte halves;
+//   * the per-column epilogue vectors (BN scale / shift, LayerNorm gamma / beta) are staged in shared memory once per CTA
+//     instead of being fetched by uniform global loads per column and tile;
 //   * zero-skip (v2_flags bit 0): one warp-level LDGSTS covers 4 rows x 128 B of a stage; when none of the 4 rows has
 //     a neighbour AND the previous use of that stage left zeros in those rows, the copy is skipped (the sparse 32/64-
 //     channel stages fill 15-35 % of the slots, and the LSU issue rate of these copies is what bounds them).
@@ -42,7 +44,8 @@ struct Smem2 {
   static constexpr int NBR_OFF = B_OFF + SB * B_BYTES;                  // 2 x [MAX_TAPS][128] byte offsets
   static constexpr int LIST_OFF = NBR_OFF + 2 * MAX_TAPS * BM * 4;      // 2 x chunk list (uint16)
   static constexpr int FLAG_OFF = LIST_OFF + 2 * MAX_CHUNKS * 2;        // 2 x (32 tap flags + count + pad)
-  static constexpr int BAR_OFF = FLAG_OFF + 2 * 64 * 4;
+  static constexpr int VEC_OFF = FLAG_OFF + 2 * 64 * 4;                 // [4][BN] fp32: scale, shift, ln_gamma, ln_beta of the CTA's columns
+  static constexpr int BAR_OFF = VEC_OFF + 4 * BN * 4;
   static constexpr int NUM_BARS = 2 * SA + 2 * SB + 8;
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;      // + tmem slot + alignment slack
   static_assert(TOTAL <= 227 * 1024, "v2 GEMM: shared memory budget exceeded");
@@ -71,18 +74,69 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// 32 accumulator columns of one row with the per-column vectors read from SHARED memory (staged once per CTA): the
+// v1 epilogue fetches scale / shift / gamma / beta with one uniform LDG per column and tile (~100-260 global loads per
+// thread and tile, ncu: 50-56 us for the LayerNorm GEMMs against 12-20 us without).  Arithmetic and order as epilogue_block.
+template <bool LD256>
+__device__ __forceinline__ void epilogue_block2(const GemmParams& p, uint32_t taddr, const float* __restrict__ vs,
+                                                const float* __restrict__ vh, int n_base, long long rrow, float (&x)[32]) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  tmem_ld_wait();
+  const bool has_s = p.scale != nullptr, has_h = p.shift != nullptr;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 s4 = *(const float4*)(vs + j4 * 4), h4 = *(const float4*)(vh + j4 * 4);
+    const float sc[4] = {s4.x, s4.y, s4.z, s4.w}, sh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float y = __uint_as_float(v[j4 * 4 + e]);
+      if (has_s) y *= sc[e];
+      if (has_h) y += sh[e];
+      x[j4 * 4 + e] = y;
+    }
+  }
+  if (p.residual && rrow >= 0) {
+    if constexpr (LD256) {
+#pragma unroll
+      for (int j8 = 0; j8 < 2; ++j8) {
+        uint32_t w[8];
+        ld_global_256(p.residual + rrow * p.ldr + n_base + j8 * 16, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 f = __half22float2(*(const __half2*)&w[e]);
+          x[j8 * 16 + e * 2] += f.x; x[j8 * 16 + e * 2 + 1] += f.y;
+        }
+      }
+    } else {
+      const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n_base);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const uint4 u = rp[j4];
+        const __half2* h = (const __half2*)&u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
+        }
+      }
+    }
+  }
+}
+
 // one output row (TMEM lane) of a finished tile: scale/shift (+residual) (+LayerNorm) (+activation) -> global.
 // LD256: 32-byte residual loads; (p.v2_flags & 4): 32-byte fp16 stores — one full sector per lane and instruction
 // instead of half a sector (the un-coalesced row-per-thread epilogue is 15-25 % of the L1TEX load).
+// vec = the CTA's [4][BN] per-column vectors in shared memory.
 template <int BN, bool LD256>
 __device__ __forceinline__ void epilogue_tile2(const GemmParams& p, uint32_t t_lane, int n0, long long rrow, long long orow,
-                                               bool store_ok) {
+                                               bool store_ok, const float* __restrict__ vec) {
   float mean = 0.f, rstd = 1.f;
   if (p.ln_gamma) {
     float s1 = 0.f, s2 = 0.f;
     for (int cb = 0; cb < BN; cb += 32) {
       float x[32];
-      epilogue_block<LD256>(p, t_lane + cb, n0 + cb, rrow, x);
+      epilogue_block2<LD256>(p, t_lane + cb, vec + cb, vec + BN + cb, n0 + cb, rrow, x);
 #pragma unroll
       for (int j = 0; j < 32; ++j) { s1 += x[j]; s2 += x[j] * x[j]; }
     }
@@ -93,10 +147,12 @@ __device__ __forceinline__ void epilogue_tile2(const GemmParams& p, uint32_t t_l
   const bool st256 = (p.v2_flags & 4) != 0;
   for (int cb = 0; cb < BN; cb += 32) {
     float x[32];
-    epilogue_block<LD256>(p, t_lane + cb, n0 + cb, rrow, x);
+    epilogue_block2<LD256>(p, t_lane + cb, vec + cb, vec + BN + cb, n0 + cb, rrow, x);
     if (p.ln_gamma) {
+      const float* ga = vec + 2 * BN + cb;
+      const float* be = vec + 3 * BN + cb;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * p.ln_gamma[n0 + cb + j] + p.ln_beta[n0 + cb + j];
+      for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * ga[j] + be[j];
     }
     if (p.act == ACT_RELU) {
 #pragma unroll
@@ -176,6 +232,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm2_kernel(const GemmParams p
     fence_barrier_init();
   }
   if (warp == V2_MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_slot);
+  {   // per-column epilogue vectors of this CTA's columns -> shared memory (read there by every tile's epilogue)
+    float* vec = (float*)(smem + SL::VEC_OFF);
+    for (int c = tid; c < BN; c += V2_THREADS) {
+      vec[c] = p.scale ? p.scale[n0 + c] : 1.f;
+      vec[BN + c] = p.shift ? p.shift[n0 + c] : 0.f;
+      vec[2 * BN + c] = p.ln_gamma ? p.ln_gamma[n0 + c] : 1.f;
+      vec[3 * BN + c] = p.ln_beta ? p.ln_beta[n0 + c] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -364,8 +429,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm2_kernel(const GemmParams p
       mbar_wait_b(&acc_full[buf], ubuf & 1);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
-      if (p.v2_flags & 2) epilogue_tile2<BN, true>(p, t_lane, n0, rrow, orow, store_ok);
-      else epilogue_tile2<BN, false>(p, t_lane, n0, rrow, orow, store_ok);
+      const float* vec = (const float*)(smem + SL::VEC_OFF);
+      if (p.v2_flags & 2) epilogue_tile2<BN, true>(p, t_lane, n0, rrow, orow, store_ok, vec);
+      else epilogue_tile2<BN, false>(p, t_lane, n0, rrow, orow, store_ok, vec);
       // this thread's TMEM reads of the buffer are complete (tcgen05.wait::ld inside epilogue_block) and ordered
       // before the arrival that lets the MMA warp overwrite it
       tc_fence_before();
