@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
+from . import conv2d
 from .gemm import gemm, pack_weight
 from .profiling import stage
 from .registry import (BACKBONES, FUSION_LAYERS, MIDDLE_ENCODERS, ConvModule, build_backbone, build_conv_layer,
@@ -41,6 +42,10 @@ def _fold_conv_bn(conv, bn, transpose_kernel=False):
 
 def _conv(x_nhwc, packed, stride=1, relu=True):
     """3x3 conv + folded BN (+ReLU) on a channels-last fp16 map [B,Y,X,C] (cuDNN implicit GEMM)."""
+    if conv2d.ENABLED:       # opt-in: the library's own tcgen05 implicit GEMM instead of cuDNN (conv2d.py)
+        y = conv2d.conv3x3(x_nhwc, packed, stride, relu)
+        if y is not None:
+            return y
     w, b = packed
     x = x_nhwc.permute(0, 3, 1, 2)
     if relu:     # cuDNN runtime-fused conv + bias + ReLU (one kernel)

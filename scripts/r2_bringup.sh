@@ -11,6 +11,8 @@ echo "== v2 GEMM bring-up"         | tee -a gpurun_out/r2_bringup.log
 timeout 300 python -m pytest tests/test_gemm_v2_gpu.py -x -q -m gpu           >> gpurun_out/r2_bringup.log 2>&1
 echo "== direct parity against the reference fixtures" | tee -a gpurun_out/r2_bringup.log
 timeout 300 python -m pytest tests/test_reference_fixtures_gpu.py -x -q -m gpu >> gpurun_out/r2_bringup.log 2>&1
+echo "== own dense 3x3 convs on the implicit-GEMM kernel" | tee -a gpurun_out/r2_bringup.log
+timeout 300 python -m pytest tests/test_conv2d_own.py -x -q -m gpu             >> gpurun_out/r2_bringup.log 2>&1
 echo "== per-layer A/B"            | tee -a gpurun_out/r2_bringup.log
 timeout 400 python scripts/bench_gemm_layers.py --v2 --tile-order 12,16,31    >> gpurun_out/r2_bringup.log 2>&1
 unset ISF_EXPERIMENTAL
@@ -23,5 +25,6 @@ echo "== bench: default, then tile order 31 / 16" | tee -a gpurun_out/r2_bringup
 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline           > gpurun_out/r2_bench_default.json 2>> gpurun_out/r2_bringup.log
 ISF_TILE_ORDER=31 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_ord31.json 2>> gpurun_out/r2_bringup.log
 ISF_TILE_ORDER=16 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_ord16.json 2>> gpurun_out/r2_bringup.log
+ISF_OWN_CONV=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_ownconv.json 2>> gpurun_out/r2_bringup.log
 tail -n 60 gpurun_out/r2_bringup.log
 for f in gpurun_out/r2_bench_*.json; do echo $f; python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['frame_latency_ms'], d['roofline']['frac'], d['roofline']['kernel_ms_per_step'])" 2>/dev/null; done
