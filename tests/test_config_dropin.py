@@ -65,7 +65,6 @@ def test_head_module_has_the_reference_state_dict_keys():
     net = MODELS.build(dict(type='TransFusionHeadV2', **cfg))
     keys = list(np.load(os.path.join(here, 'golden', 'ref_head.npz'))['keys'])
     assert sorted(net.state_dict().keys()) == keys
-    ref_shapes = None
     from oracle import head_ops
     ref = head_ops.TransFusionHeadV2(**cfg)
     assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
