@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import fusion_encoder, head, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
+from . import fusion_encoder, head, img_neck, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
 from .registry import (DETECTORS, MODELS, NECKS, build_backbone, build_fusion_layer, build_middle_encoder,
                        build_voxel_encoder)
 from .profiling import stage
@@ -28,6 +28,9 @@ class ISFusionDetector(nn.Module):
         self.pts_backbone = build_backbone(dict(pts_backbone))
         # pts_neck (SECONDFPN) is the next row after the hot path; built when the config carries it
         self.pts_neck = NECKS.build(dict(pts_neck)) if pts_neck is not None else None
+        # img_neck (GeneralizedLSSFPN) turns the image backbone's stage outputs into img_feats; the
+        # Swin backbone itself stays the reference's module
+        self.img_neck = NECKS.build(dict(img_neck)) if img_neck is not None else None
         # pts_bbox_head (TransFusionHeadV2): like MVXTwoStageDetector, train_cfg.pts / test_cfg.pts are handed to the head
         self.pts_bbox_head = None
         if pts_bbox_head is not None:

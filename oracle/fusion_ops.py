@@ -280,6 +280,32 @@ class SECONDFPN(nn.Module):
         return [out.permute(0, 1, 3, 2).contiguous()]
 
 
+class GeneralizedLSSFPN(nn.Module):
+    """ref: mmdet3d/models/necks/generalized_lss.py:12-103 (the producer of img_feats; config
+    isfusion_0075voxel.py:50-55): top-down, per level: bilinear upsample (align_corners=True) of the level above ->
+    concat -> 1x1 ConvModule -> 3x3 ConvModule (conv bias-free + BN2d + ReLU each)."""
+
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, **kw):
+        super().__init__()
+        assert start_level == 0 and end_level == -1
+        self.in_channels = in_channels
+        last = len(in_channels) - 1
+        self.lateral_convs = nn.ModuleList()
+        self.fpn_convs = nn.ModuleList()
+        for i in range(last):
+            cin = in_channels[i] + (in_channels[i + 1] if i == last - 1 else out_channels)
+            self.lateral_convs.append(ConvModule(cin, out_channels, 1, padding=0))
+            self.fpn_convs.append(ConvModule(out_channels, out_channels, 3, padding=1))
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        lat = list(inputs)
+        for i in range(len(lat) - 2, -1, -1):
+            x = F.interpolate(lat[i + 1], size=lat[i].shape[2:], mode='bilinear', align_corners=True)
+            lat[i] = self.fpn_convs[i](self.lateral_convs[i](torch.cat([lat[i], x], dim=1)))
+        return tuple(lat[:-1])
+
+
 class ISFusionEncoder(nn.Module):
     """ref: fusion_encoder.py:833-1189."""
 

@@ -139,6 +139,16 @@ def fusion_inputs(bs=2, seed=0, bev=None, pillars_per_frame=300):
                 img_metas=[dict(input_shape=IMG_SHAPE) for _ in range(bs)])
 
 
+# ----------------------------------------------------------------------------- image neck
+def lss_cfg():
+    return dict(in_channels=[192, 384, 768], out_channels=256, start_level=0, num_outs=3)
+
+
+def lss_inputs(n_img=3, seed=0):
+    """Swin-T stage outputs of a 128x352 image (strides 8 / 16 / 32)."""
+    return [rand('lss_in%d' % i, (n_img, c, 128 // s, 352 // s), seed, 0.5) for i, (c, s) in enumerate(((192, 8), (384, 16), (768, 32)))]
+
+
 # ----------------------------------------------------------------------------- head (SURVEY 8f rank 2)
 def head_cfg():
     """configs/isfusion/isfusion_0075voxel.py:115-171 on the 24x24 grid (grid_size 192 / out_size_factor 8)."""

@@ -17,6 +17,7 @@ Fixtures (checked by tests/test_oracle_vs_reference.py against oracle/):
   ref_vfe.npz     : DynamicVFE.forward (voxel_encoder.py:452-547) features + coordinates; DynamicScatter mean.
   ref_sparse.npz  : SparseEncoder.forward (sparse_encoder.py:107-138) dense output [B,512,H/8,W/8] and the
                     active-site count after every stage.
+  ref_lss.npz     : GeneralizedLSSFPN.forward (necks/generalized_lss.py:79-103) on Swin-T-shaped stage outputs of 3 images.
   ref_head.npz    : TransFusionHeadV2.forward (transfusion_head_v2.py:771-908) prediction dict on a [2,512,24,24] map,
                     query labels, and TransFusionBBoxCoder.decode (transfusion_bbox_coder.py:41-125) of it.
 """
@@ -138,6 +139,15 @@ def sparse(R):
 
 
 @torch.no_grad()
+def lss(R):
+    net = gc.fill_state(R.GeneralizedLSSFPN(**gc.lss_cfg()), 8).eval()
+    outs = net(gc.lss_inputs())
+    np.savez_compressed(os.path.join(HERE, 'ref_lss.npz'), out0_c8=_np(outs[0][:, ::8]), out1_c4=_np(outs[1][:, ::4]),
+                        keys=np.array(sorted(net.state_dict().keys())))
+    print('lss:', [tuple(o.shape) for o in outs])
+
+
+@torch.no_grad()
 def head(R):
     R = ref_shim.install_head()
     net = gc.fill_state(R.TransFusionHeadV2(**gc.head_cfg()), 7).eval()
@@ -163,7 +173,7 @@ def head(R):
 
 if __name__ == '__main__':
     R = ref_shim.install()
-    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head']
+    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head', 'lss']
     for w in which:
         globals()[w](R)
     for f in sorted(os.listdir(HERE)):

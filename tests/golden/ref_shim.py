@@ -519,6 +519,7 @@ def install():
         _load_ref('mmdet3d.models.backbones.second', 'mmdet3d/models/backbones/second.py')
         _pkg('mmdet3d.models.necks')
         _load_ref('mmdet3d.models.necks.second_fpn', 'mmdet3d/models/necks/second_fpn.py')
+        _load_ref('mmdet3d.models.necks.generalized_lss', 'mmdet3d/models/necks/generalized_lss.py')
         _pkg('mmdet3d.models.middle_encoders')
         _load_ref('mmdet3d.models.middle_encoders.multi_scale_deformable_attn_function',
                   'mmdet3d/models/middle_encoders/multi_scale_deformable_attn_function.py')
@@ -536,6 +537,7 @@ def install():
         SSTv2=m['mmdet3d.models.backbones.sst_v2'].SSTv2,
         SECONDV2=m['mmdet3d.models.backbones.second'].SECONDV2,
         SECONDFPN=m['mmdet3d.models.necks.second_fpn'].SECONDFPN,
+        GeneralizedLSSFPN=m['mmdet3d.models.necks.generalized_lss'].GeneralizedLSSFPN,
         SparseEncoder=m['mmdet3d.models.middle_encoders.sparse_encoder'].SparseEncoder,
         DynamicVFE=m['mmdet3d.models.voxel_encoders.voxel_encoder'].DynamicVFE,
         DynamicScatter=m['mmdet3d.ops'].DynamicScatter,

@@ -31,6 +31,7 @@ def test_reference_config_builds_b200_modules():
         'fusion_encoder.instance_to_scene_att.multihead_attn.in_proj_weight', 'fusion_encoder.instance_to_scene_att.norm.weight',
         'pts_backbone.blocks.0.15.weight', 'pts_backbone.ds_layer.1.running_var', 'pts_backbone.blocks.1.12.weight',
         'pts_neck.deblocks.0.0.weight', 'pts_neck.deblocks.1.1.running_mean',
+        'img_neck.lateral_convs.1.conv.weight', 'img_neck.fpn_convs.0.bn.running_mean',
         'pts_bbox_head.shared_conv.bias', 'pts_bbox_head.heatmap_head.0.bn.running_var', 'pts_bbox_head.class_encoding.weight',
         'pts_bbox_head.decoder.0.multihead_attn.in_proj_weight', 'pts_bbox_head.decoder.0.cross_posembed.position_embedding_head.0.weight',
         'pts_bbox_head.prediction_heads.0.vel.0.conv.weight', 'pts_bbox_head.prediction_heads.0.heatmap.1.bias',
@@ -44,6 +45,7 @@ def test_reference_config_builds_b200_modules():
     assert det.fusion_encoder.bev_size == 180 and det.fusion_encoder.instance_num == 200
     assert det.pts_pillar_layer.max_num_points == 12 and det.pillar_size[:2] == [0.6, 0.6]
     assert det.pts_middle_encoder.sparse_shape == [41, 1440, 1440]
+    assert tuple(sd['img_neck.lateral_convs.1.conv.weight'].shape) == (256, 1152, 1, 1)
     assert tuple(sd['pts_bbox_head.shared_conv.weight'].shape) == (128, 512, 3, 3)
     assert det.pts_bbox_head.x_size == 180 and det.pts_bbox_head.num_proposals == 200 and det.pts_bbox_head.num_classes == 10
     assert det.pts_bbox_head.bbox_coder_cfg['post_center_range'] == [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]
@@ -68,3 +70,15 @@ def test_head_module_has_the_reference_state_dict_keys():
     from oracle import head_ops
     ref = head_ops.TransFusionHeadV2(**cfg)
     assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+
+
+def test_img_neck_module_has_the_reference_state_dict_keys():
+    import os
+    import sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, 'golden'))
+    import golden_common as gc
+    from isfusion_b200.img_neck import GeneralizedLSSFPN
+    net = GeneralizedLSSFPN(**gc.lss_cfg())
+    assert sorted(net.state_dict().keys()) == list(np.load(os.path.join(here, 'golden', 'ref_lss.npz'))['keys'])

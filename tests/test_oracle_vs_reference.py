@@ -175,3 +175,14 @@ def test_fusion_encoder_at_config_size_matches_reference_samples():
         assert np.abs(flat[gc.sample_positions(t.shape)] - ref).max() < TOL * scale, name
         mom = np.array([flat.mean(), np.abs(flat).mean(), (flat.astype(np.float64) ** 2).mean(), np.abs(flat).max()])
         assert np.allclose(mom, g[name + '_moments'], rtol=1e-4), (name, mom, g[name + '_moments'])
+
+
+def test_generalized_lss_fpn_matches_reference():
+    """SURVEY §8f rank 1 (image neck, the producer of img_feats[1])."""
+    g = _load('ref_lss.npz')
+    net = gc.fill_state(fusion_ops.GeneralizedLSSFPN(**gc.lss_cfg()), 8).eval()
+    _keys(net, g, 'keys')
+    outs = net(gc.lss_inputs())
+    assert len(outs) == 2
+    _close(outs[0][:, ::8], g['out0_c8'], 'img_feats[0]')
+    _close(outs[1][:, ::4], g['out1_c4'], 'img_feats[1]')

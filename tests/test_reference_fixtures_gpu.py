@@ -124,3 +124,12 @@ def test_fusion_encoder_at_config_size_against_reference_samples():
         assert list(t.shape) == g[name + '_shape'].tolist()
         got = t.float().cpu().numpy().reshape(-1)[gc.sample_positions(t.shape)]
         assert _rel(got, g[name + '_samples']) < bar, name
+
+
+def test_generalized_lss_fpn_against_reference_run():
+    from isfusion_b200.img_neck import GeneralizedLSSFPN
+    g = _g('ref_lss.npz')
+    net = gc.fill_state(GeneralizedLSSFPN(**gc.lss_cfg()), 8).cuda().eval()
+    outs = net([t.cuda() for t in gc.lss_inputs()])
+    assert len(outs) == 2
+    assert _rel(outs[0][:, ::8], g['out0_c8']) < 3e-3 and _rel(outs[1][:, ::4], g['out1_c4']) < 3e-3
