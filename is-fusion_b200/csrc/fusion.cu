@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __half* __restr
 template <int GPAD>   // G rounded up to 16
 __global__ void __launch_bounds__(128) channel_attention_kernel(const __half* __restrict__ Sg, const __half* __restrict__ Ig,
                                                                 int G, __half* __restrict__ Og) {
-  constexpr int GP = GPAD + 8;                 // pitch in halfs: (GPAD+8)/2 words, = 4 mod 32 for GPAD = 192
+  constexpr int GP = GPAD + 8;                 // pitch in halfs: (GPAD+8)/2 words, = 4 mod 32 for GPAD = 192 and 256
   constexpr int NT = GPAD / 8, KT = GPAD / 16;
   extern __shared__ __half sm[];
   __half* Ip = sm;                              // [GPAD][GP]
@@ -750,8 +750,7 @@ extern "C" int isf_channel_attention_workspace_size(int batch, int grid, int cha
 extern "C" int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid,
                                      int channels, void* out, int ldo, void* workspace, size_t ws_bytes, void* stream) {
   ISF_CHECK_ARG(scene && ins && out && workspace && batch >= 1 && grid >= 2 && channels >= 1);
-  if (grid > 192 || (grid & 1)) { isf_set_error("channel_attention: built for even BEV sizes <= 192"); return ISF_ERR_UNSUPPORTED; }
-  constexpr int GPAD = 192, GP = GPAD + 8;
+  if (grid > 256 || (grid & 1)) { isf_set_error("channel_attention: built for even BEV sizes <= 256"); return ISF_ERR_UNSUPPORTED; }
   const size_t plane_elems = (size_t)batch * channels * grid * grid;
   if (ws_bytes < 3 * plane_elems * sizeof(__half)) { isf_set_error("channel_attention: workspace too small"); return ISF_ERR_WORKSPACE; }
   __half* Sp = (__half*)workspace;
@@ -762,14 +761,26 @@ extern "C" int isf_channel_attention(const void* scene, int lds, const void* ins
   dim3 tg(isf_cdiv(HW, 32), isf_cdiv(channels, 32), batch);
   nhwc_to_nchw_kernel<<<tg, 256, 0, st>>>((const __half*)scene, lds, HW, channels, Sp);
   nhwc_to_nchw_kernel<<<tg, 256, 0, st>>>((const __half*)ins, ldi, HW, channels, Ip);
-  const size_t smem = (size_t)(GPAD + 64) * GP * sizeof(__half);
-  static bool cfg = false;
-  if (!cfg) {
-    ISF_CUDA(cudaFuncSetAttribute(channel_attention_kernel<GPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cfg = true;
-  }
   const int slabs = (grid + 63) / 64;
-  channel_attention_kernel<GPAD><<<batch * channels * slabs, 128, smem, st>>>(Sp, Ip, grid, Op);
+  if (grid <= 192) {       // the config's 180x180 BEV (isfusion_0075voxel.py)
+    constexpr int GPAD = 192, GP = GPAD + 8;
+    const size_t smem = (size_t)(GPAD + 64) * GP * sizeof(__half);
+    static bool cfg = false;
+    if (!cfg) {
+      ISF_CUDA(cudaFuncSetAttribute(channel_attention_kernel<GPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg = true;
+    }
+    channel_attention_kernel<GPAD><<<batch * channels * slabs, 128, smem, st>>>(Sp, Ip, grid, Op);
+  } else {                 // up to 256x256 (BASELINE configs[4]: 0.05 m voxels, 2048^2 grid / 8)
+    constexpr int GPAD = 256, GP = GPAD + 8;
+    const size_t smem = (size_t)(GPAD + 64) * GP * sizeof(__half);
+    static bool cfg = false;
+    if (!cfg) {
+      ISF_CUDA(cudaFuncSetAttribute(channel_attention_kernel<GPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cfg = true;
+    }
+    channel_attention_kernel<GPAD><<<batch * channels * slabs, 128, smem, st>>>(Sp, Ip, grid, Op);
+  }
   nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(Op, HW, channels, (__half*)out, ldo);
   isf_count_launch(4);
   ISF_LAUNCH_CHECK();

@@ -133,3 +133,25 @@ def test_generalized_lss_fpn_against_reference_run():
     outs = net([t.cuda() for t in gc.lss_inputs()])
     assert len(outs) == 2
     assert _rel(outs[0][:, ::8], g['out0_c8']) < 3e-3 and _rel(outs[1][:, ::4], g['out1_c4']) < 3e-3
+
+
+@pytest.mark.parametrize('g', [200, 256])
+def test_channel_attention_on_grids_up_to_256(g):
+    """BASELINE configs[4] (0.05 m voxels -> 256x256 BEV): the second template instance of channel_attention_kernel
+    against the closed form S + softmax(S I^T) I (fusion_encoder.py:495-500)."""
+    import ctypes
+    from isfusion_b200 import _lib as L
+    torch.manual_seed(0)
+    b, c = 1, 16
+    s = (torch.randn(b, g, g, c, device='cuda') * 0.3).half()
+    i = (torch.randn(b, g, g, c, device='cuda') * 0.3).half()
+    out = torch.empty_like(s)
+    nb = ctypes.c_size_t(0)
+    L.check(L.lib().isf_channel_attention_workspace_size(b, g, c, ctypes.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device='cuda')
+    L.check(L.lib().isf_channel_attention(L.ptr(s), c, L.ptr(i), c, b, g, c, L.ptr(out), c, L.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                          L.stream()))
+    sp, ip = s.float().permute(0, 3, 1, 2), i.float().permute(0, 3, 1, 2)
+    want = sp + torch.softmax(sp @ ip.transpose(2, 3), dim=-1) @ ip
+    got = out.float().permute(0, 3, 1, 2)
+    assert ((got - want).norm() / want.norm()).item() < 3e-3
