@@ -11,6 +11,8 @@ echo "== v2 GEMM bring-up"         | tee -a gpurun_out/r2_bringup.log
 timeout 300 python -m pytest tests/test_gemm_v2_gpu.py -x -q -m gpu           >> gpurun_out/r2_bringup.log 2>&1
 echo "== direct parity against the reference fixtures" | tee -a gpurun_out/r2_bringup.log
 timeout 300 python -m pytest tests/test_reference_fixtures_gpu.py -x -q -m gpu >> gpurun_out/r2_bringup.log 2>&1
+echo "== configs[4] geometry (0.05 m voxels, 256x256 BEV)" | tee -a gpurun_out/r2_bringup.log
+timeout 300 python -m pytest tests/test_config5_gpu.py -x -q -m gpu            >> gpurun_out/r2_bringup.log 2>&1
 echo "== own dense 3x3 convs on the implicit-GEMM kernel" | tee -a gpurun_out/r2_bringup.log
 timeout 300 python -m pytest tests/test_conv2d_own.py -x -q -m gpu             >> gpurun_out/r2_bringup.log 2>&1
 echo "== per-layer A/B"            | tee -a gpurun_out/r2_bringup.log

@@ -1,0 +1,46 @@
+"""BASELINE configs[4] geometry (dense-scene stress: 0.05 m voxels, +-51.2 m range -> 2048 x 2048 x 40 voxel grid,
+256 x 256 BEV) through the whole neck against the CPU oracle, at a point count the oracle finishes in seconds.
+
+Bring-up (ISF_EXPERIMENTAL=1): the kernels were validated on the 0.075 m / 180 x 180 configuration; this geometry
+exercises the 256-grid instance of the channel attention, partial 6x6 windows on a grid that is not a multiple of 6 and
+a 2048^2 x 41 coordinate bitmap."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='bring-up test: set ISF_EXPERIMENTAL=1')]
+
+
+def test_neck_on_the_005_voxel_256_bev_geometry():
+    import synth
+    import isfusion_b200.detector as det
+    from oracle import model as omodel
+    torch.manual_seed(0)
+    pc_range = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    cfg = omodel.neck_config(voxel_size=[0.05, 0.05, 0.2], pc_range=pc_range, out_size_factor=8)
+    assert cfg['bev_size'] == 256 and cfg['pts_middle_encoder']['sparse_shape'] == [41, 2048, 2048]
+    ref = synth.randomize_bn(omodel.ISFusionNeck(cfg, shuffle_voxels=False)).eval()
+    net = det.ISFusionDetector(
+        pts_voxel_layer=dict(point_cloud_range=pc_range, max_num_points=-1, voxel_size=cfg['voxel_size'], max_voxels=(-1, -1)),
+        pts_voxel_encoder=dict(type='DynamicVFE', **cfg['pts_voxel_encoder']),
+        pts_middle_encoder=dict(type='SparseEncoder', **cfg['pts_middle_encoder']),
+        fusion_encoder=dict(type='ISFusionEncoder', **cfg['fusion_encoder']),
+        pts_backbone=dict(type='SECONDV2', **cfg['pts_backbone']),
+        detach=True, pc_range=pc_range, voxel_size=cfg['voxel_size'], out_size_factor=8)
+    net.load_state_dict(ref.state_dict())
+    net = net.cuda().eval()
+    pts = [synth.make_points(40000, 'S', 3, pc_range)]
+    l2i, aug, laug = synth.make_calib(1)
+    feats = synth.make_img_feats(1)
+    metas = [dict(input_shape=(256, 704))]
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    rf, rhm = ref(pts, feats, metas, **kw)
+    gf, ghm = net([p.cuda() for p in pts], [f.cuda() for f in feats], metas, **kw)
+    rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
+    assert gf[0].shape == rf[0].shape == (1, 128, 256, 256) and gf[1].shape == rf[1].shape == (1, 256, 128, 128)
+    overlap = len(set(ref.fusion_encoder._dbg['top_idx'][0].tolist()) & set(net.fusion_encoder._dbg['top_idx'][0].cpu().tolist())) / 200.0
+    assert rel(ghm, rhm) < 5e-3 and overlap > 0.9
+    assert rel(gf[0], rf[0]) < 1e-2 and rel(gf[1], rf[1]) < 1e-2
