@@ -160,7 +160,7 @@ int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad, int n, co
  *   offset k (k = (kz*KH+ky)*KW+kx, geometry.h:62-73) or -1.  subm=1: outputs = inputs, centre aligned.
  * isf_spconv_implicit_gemm: out[o, :] = act((sum_k in[nbr[k,o], :] . W[k]) * scale + shift + residual[o, :])
  *   in ONE tcgen05 kernel.  w_packed [cout, kpad] fp16, column k*cin + c = W[k][c][cout] (kpad % 64 == 0,
- *   zero padded).  cin in {32,64,128,256} (or a multiple of 64), cout in {32,64,128,256}.
+ *   zero padded).  cin a power of two >= 8, cout in {32,64,128,256}, taps <= 27.
  * isf_sparse_to_dense: SparseConvTensor.dense() -> [B,C,D,H,W] fp16 (structure.py:49-59).
  * isf_sparse_to_bev_nhwc: the [B, C*D, H, W] BEV view (sparse_encoder.py:133-136, channel c*D+z) written
  *   channels-last with row pitch ldo at channel offset ch_offset (caller zero-fills). */
