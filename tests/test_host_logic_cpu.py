@@ -1,0 +1,63 @@
+"""CPU tests of the product's HOST-side logic (no kernel calls): the algebra that is folded on the host before a kernel
+runs must reproduce the reference's arithmetic."""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+import golden_common as gc  # noqa: E402
+
+from oracle import fusion_ops  # noqa: E402
+
+
+def test_camera_projection_folding_reproduces_the_reference_sampling():
+    """ISFusionEncoder.camera_projection folds inverse lidar-aug, lidar2img and the image-aug affine rows into 20
+    floats per (frame, camera) (fusion_encoder.py:976-1016 of the reference).  A torch statement of what cam2bev_kernel
+    does with them (csrc/fusion.cu) must give the reference's img_fv_to_bev."""
+    from isfusion_b200.fusion_encoder import ISFusionEncoder
+    cfg = gc.fusion_cfg()
+    inp = gc.fusion_inputs()                      # non-identity lidar_aug_matrix (rotation, scale, translation)
+    bs, g, ncam = 2, gc.BEV, 6
+    ref = fusion_ops.ISFusionEncoder(**cfg)
+    pm = dict(pillars=inp['pillars'], pillars_num_points=None, pillar_coors=inp['pillar_coors'], pts=None, pillar_size=None)
+    feat = inp['img_feats'][1]
+    want = ref.img_fv_to_bev([feat], bs, pts_metas=pm, img_metas=inp['img_metas'], lidar2img=inp['lidar2img'],
+                             img_aug_matrix=inp['img_aug_matrix'], lidar_aug_matrix=inp['lidar_aug_matrix'])
+    enc = ISFusionEncoder(**cfg)
+    proj = enc.camera_projection(inp['lidar2img'], inp['img_aug_matrix'], inp['lidar_aug_matrix'], bs, torch.device('cpu'))
+    assert proj.shape == (bs, ncam, 20)
+    img_h, img_w = inp['img_metas'][0]['input_shape']
+    c, fh, fw = feat.shape[1:]
+    fmap = feat.view(bs, ncam, c, fh, fw)
+    got = torch.zeros(bs, c, g, g)
+    coors, pillars = inp['pillar_coors'].long(), inp['pillars'][..., :3]
+    for b in range(bs):
+        sel = coors[:, 0] == b
+        p = pillars[sel].reshape(-1, 3)                                    # [M*12, 3]
+        acc = torch.zeros(c, p.shape[0])
+        for cam in range(ncam):
+            pr = proj[b, cam]
+            m, t, a, at = pr[:9].view(3, 3), pr[9:12], pr[12:18].view(2, 3), pr[18:20]
+            q = p @ m.t() + t
+            qz = q[:, 2].clamp(1e-5, 1e5)
+            uvz = torch.stack([q[:, 0] / qz, q[:, 1] / qz, qz], 1)
+            ua = uvz @ a.t() + at
+            grid = torch.stack([(ua[:, 0] / img_w - 0.5) * 2, (ua[:, 1] / img_h - 0.5) * 2], -1)
+            acc += F.grid_sample(fmap[b, cam][None], grid.view(1, -1, 1, 2), align_corners=False)[0, :, :, 0]
+        cell = acc.view(c, -1, gc.NPTS).sum(2)
+        got[b][:, coors[sel, 2], coors[sel, 3]] = cell
+    err = (got - want).abs().max() / want.abs().max()
+    assert err < 1e-4, err
+
+
+def test_dense_conv_plan_cache_keys_do_not_alias():
+    """conv2d caches rulebooks per (device, B, H, W, stride, groups) and packed weights per (pointer, version)."""
+    from isfusion_b200 import conv2d
+    a, _, _ = conv2d.dense_rulebook(1, 6, 6, 1, 1, torch.device('cpu'))
+    b, oh, ow = conv2d.dense_rulebook(1, 6, 6, 2, 1, torch.device('cpu'))
+    assert a.shape[0] == b.shape[0] == 9 and (oh, ow) == (3, 3)
+    assert int((a[4, :36] == torch.arange(36)).all())                      # centre tap of a stride-1 conv = identity
+    assert int((b[4, :9] == torch.tensor([0, 2, 4, 12, 14, 16, 24, 26, 28])).all())
