@@ -217,6 +217,12 @@ int isf_spconv_neighbors_bitmap_ordered(const int* out_indices, int v_out, const
                                         const int* in_prefix, const int* in_shape, const int* ksize, const int* stride,
                                         const int* padding, const int* dilation, int subm, int chunk_log2, int* nbr_out,
                                         long long nbr_stride, int* row_perm, void* workspace, size_t ws_bytes, void* stream);
+/* host-only test hook: the row walk of the row-per-thread kernels (same source, compiled for the host) on HOST memory;
+ * nbr [kvol, nbr_stride] and masks [v_out] (occupancy mask, offset k at bit isf_spconv_tile_order_bits()[k]) are host
+ * arrays.  Lets the CPU suite check the device logic against the oracle rulebook. */
+int isf_debug_nbr_rows_host(const int* out_indices, int v_out, const unsigned int* in_bits, const int* in_prefix,
+                            const int* in_shape, const int* ksize, const int* stride, const int* padding,
+                            const int* dilation, int subm, int* nbr, long long nbr_stride, unsigned int* masks);
 int isf_spconv_implicit_gemm_ordered(const void* feats_in, int cin, const void* w_packed, int kpad, int cout,
                                      const int* nbr_ordered, long long nbr_stride, int taps, int v_out,
                                      const int* v_out_dev, const int* row_perm, const float* scale, const float* shift,

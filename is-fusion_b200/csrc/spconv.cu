@@ -29,7 +29,7 @@ __device__ __forceinline__ unsigned int hash_u32(unsigned int k) {
   return k;
 }
 
-__device__ __forceinline__ unsigned int lin_key(int b, int z, int y, int x, const int* shape) {
+__host__ __device__ __forceinline__ unsigned int lin_key(int b, int z, int y, int x, const int* shape) {
   return (unsigned int)(((b * shape[0] + z) * shape[1] + y) * shape[2] + x);
 }
 
@@ -407,6 +407,59 @@ __global__ void __launch_bounds__(256) nbr_bitmap_kernel(const int* __restrict__
 // dependent loads per row instead of 54; the 27 stores of a warp stay coalesced (consecutive rows).  Same results.
 struct TapBits { unsigned char pos[32]; };
 
+__host__ __device__ __forceinline__ int isf_popc(unsigned int x) {
+#ifdef __CUDA_ARCH__
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+static void tile_order_bits_fwd(const int* ksize, int taps, unsigned char* pos);   // = tile_order_bits (defined below)
+
+// every kernel offset of the output site (b, z, y, x): MASK_ONLY = false writes the input row (or -1) of offset k to
+// dst[k * dst_stride]; MASK_ONLY = true only tests the bitmap (no prefix loads, no stores) and returns the occupancy mask
+// with offset k at bit pos[k].  The kW offsets of one (kz, ky) are adjacent cells = adjacent bits: one word (+ prefix)
+// load serves them unless they straddle a 32-cell boundary.
+template <bool MASK_ONLY>
+__host__ __device__ __forceinline__ unsigned int nbr_row_walk(int ob, int oz, int oy, int ox, const ConvGeom& g,
+                                                              const unsigned int* __restrict__ bits,
+                                                              const int* __restrict__ prefix, const unsigned char* pos,
+                                                              int* __restrict__ dst, long long dst_stride) {
+  const int x0 = ox * g.stride[2] - g.pad[2];
+  unsigned int mask = 0;
+  int k = 0;
+  for (int kz = 0; kz < g.ksize[0]; ++kz) {
+    const int iz = oz * g.stride[0] - g.pad[0] + kz * g.dil[0];
+    for (int ky = 0; ky < g.ksize[1]; ++ky) {
+      const int iy = oy * g.stride[1] - g.pad[1] + ky * g.dil[1];
+      const bool row_ok = iz >= 0 && iz < g.in_shape[0] && iy >= 0 && iy < g.in_shape[1];
+      const unsigned int key_row = row_ok ? lin_key(ob, iz, iy, 0, g.in_shape) : 0u;
+      unsigned int cached_w = 0xFFFFFFFFu, word = 0;
+      int pre = 0;
+      for (int kx = 0; kx < g.ksize[2]; ++kx, ++k) {
+        const int ix = x0 + kx * g.dil[2];
+        int r = -1;
+        if (row_ok && ix >= 0 && ix < g.in_shape[2]) {
+          const unsigned int key = key_row + (unsigned int)ix;
+          const unsigned int w = key >> 5, b = key & 31;
+          if (w != cached_w) {
+            cached_w = w;
+            word = bits[w];
+            if (!MASK_ONLY) pre = (word != 0u) ? prefix[w] : 0;
+          }
+          if ((word >> b) & 1u) {
+            if (MASK_ONLY) mask |= 1u << pos[k];
+            else r = pre + isf_popc(word & ((1u << b) - 1u));
+          }
+        }
+        if (!MASK_ONLY) dst[(long long)k * dst_stride] = r;
+      }
+    }
+  }
+  return mask;
+}
+
 // MODE 0: nbr[k][j] for row j.  MODE 1: only the tile-order sort key of row j (occupancy mask of its kernel offsets, no
 // prefix loads, no table writes) -> keys[j], rows[j] = j.  MODE 2: slot i computes storage row perm[i] and writes
 // nbr[k][i] + row_perm[i] (-1 beyond the valid rows): the tile-ordered table without a detour through the plain one.
@@ -437,42 +490,33 @@ __global__ void __launch_bounds__(256) nbr_bitmap_rows_kernel(const int* __restr
       }
     }
     const int4 o = *(const int4*)(out_indices + (size_t)j * 4);      // (b, z, y, x)
-    const int x0 = o.w * g.stride[2] - g.pad[2];
-    unsigned int mask = 0;
-    int k = 0;
-    for (int kz = 0; kz < g.ksize[0]; ++kz) {
-      const int iz = o.y * g.stride[0] - g.pad[0] + kz * g.dil[0];
-      for (int ky = 0; ky < g.ksize[1]; ++ky) {
-        const int iy = o.z * g.stride[1] - g.pad[1] + ky * g.dil[1];
-        const bool row_ok = iz >= 0 && iz < g.in_shape[0] && iy >= 0 && iy < g.in_shape[1];
-        const unsigned int key_row = row_ok ? lin_key(o.x, iz, iy, 0, g.in_shape) : 0u;
-        unsigned int cached_w = 0xFFFFFFFFu, word = 0;
-        int pre = 0;
-        for (int kx = 0; kx < g.ksize[2]; ++kx, ++k) {
-          const int ix = x0 + kx * g.dil[2];
-          int r = -1;
-          if (row_ok && ix >= 0 && ix < g.in_shape[2]) {
-            const unsigned int key = key_row + (unsigned int)ix;
-            const unsigned int w = key >> 5, b = key & 31;
-            if (w != cached_w) {
-              cached_w = w;
-              word = bits[w];
-              if (MODE != 1) pre = (word != 0u) ? prefix[w] : 0;
-            }
-            if ((word >> b) & 1u) {
-              if (MODE == 1) mask |= 1u << tb.pos[k];
-              else r = pre + __popc(word & ((1u << b) - 1u));
-            }
-          }
-          if (MODE != 1) nbr[(long long)k * nbr_stride + i] = r;
-        }
-      }
-    }
+    const unsigned int mask = nbr_row_walk<MODE == 1>(o.x, o.y, o.z, o.w, g, bits, prefix, tb.pos, MODE == 1 ? nullptr : nbr + i,
+                                                      nbr_stride);
     if (MODE == 1) {
       keys[i] = ((unsigned long long)(chunk_shift < 31 ? (i >> chunk_shift) : 0) << g.kvol) | mask;
       rows[i] = i;
     }
   }
+}
+
+// host-only: nbr_row_walk on HOST memory (the same source the kernels compile) — lets the CPU test suite check the
+// device logic of the row-per-thread kernels against the oracle rulebook without a GPU.  nbr [kvol, nbr_stride] and
+// masks [v_out] are host arrays; bits / prefix = the coordinate bitmap of the INPUT tensor in host memory.
+extern "C" int isf_debug_nbr_rows_host(const int* out_indices, int v_out, const unsigned int* in_bits, const int* in_prefix,
+                                       const int* in_shape, const int* ksize, const int* stride, const int* padding,
+                                       const int* dilation, int subm, int* nbr, long long nbr_stride, unsigned int* masks) {
+  ISF_CHECK_ARG(out_indices && in_bits && in_prefix && in_shape && ksize && nbr && masks && nbr_stride >= v_out && v_out >= 0);
+  ConvGeom g;
+  fill_geom(&g, in_shape, ksize, stride, padding, dilation, subm);
+  ISF_CHECK_ARG(g.kvol >= 1 && g.kvol <= 27);
+  TapBits tb{};
+  tile_order_bits_fwd(g.ksize, g.kvol, tb.pos);
+  for (int j = 0; j < v_out; ++j) {
+    const int* o = out_indices + (size_t)j * 4;
+    nbr_row_walk<false>(o[0], o[1], o[2], o[3], g, in_bits, in_prefix, tb.pos, nbr + j, nbr_stride);
+    masks[j] = nbr_row_walk<true>(o[0], o[1], o[2], o[3], g, in_bits, in_prefix, tb.pos, nullptr, nbr_stride);
+  }
+  return ISF_OK;
 }
 
 static long long bitmap_words(const int* shape, int batch) {
@@ -669,6 +713,8 @@ static void tile_order_bits(const int* ksize, int taps, unsigned char* pos) {
     for (int b = a; b > 0 && score[order[b]] > score[order[b - 1]]; --b) { int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
   for (int rank = 0; rank < taps; ++rank) pos[order[rank]] = (unsigned char)(taps - 1 - rank);
 }
+
+static void tile_order_bits_fwd(const int* ksize, int taps, unsigned char* pos) { tile_order_bits(ksize, taps, pos); }
 
 // host-only: the bit position of every tap in the sort key (for tests and for CPU models of the order)
 extern "C" int isf_spconv_tile_order_bits(const int* ksize, int taps, unsigned char* pos) {

@@ -246,3 +246,52 @@ def test_row_per_thread_neighbour_kernel_bit_identical():
             assert torch.equal(tabs[0][0], tabs[1][0]), (ks, st, pd, subm)
     finally:
         L.set_option('nbr_rows', 0)
+
+
+def _host_row_walk(in_idx, out_idx, in_shape, batch, ks, st, pd, subm):
+    """run the row-per-thread kernels' walk (csrc/spconv.cu nbr_row_walk, compiled for the host) on numpy arrays."""
+    from isfusion_b200 import _lib as L
+    lib = L.lib()
+    cells = batch * in_shape[0] * in_shape[1] * in_shape[2]
+    words = (cells + 31) // 32
+    key = ((in_idx[:, 0].astype(np.int64) * in_shape[0] + in_idx[:, 1]) * in_shape[1] + in_idx[:, 2]) * in_shape[2] + in_idx[:, 3]
+    assert (np.diff(key) > 0).all(), 'bitmap-rank rulebooks need rows in ascending key order'
+    bits = np.zeros(words, np.uint32)
+    np.bitwise_or.at(bits, key >> 5, (np.uint32(1) << (key & 31).astype(np.uint32)))
+    pop = np.array([bin(int(w)).count('1') for w in bits], np.int64)
+    prefix = np.concatenate([[0], np.cumsum(pop)[:-1]]).astype(np.int32)
+    v_out = out_idx.shape[0]
+    kvol = ks[0] * ks[1] * ks[2]
+    stride_rows = max((v_out + 127) // 128 * 128, 128)
+    nbr = np.full((kvol, stride_rows), -7, np.int32)
+    masks = np.zeros(v_out, np.uint32)
+    out_c = np.ascontiguousarray(out_idx, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.check(lib.isf_debug_nbr_rows_host(p(out_c), v_out, p(bits), p(prefix), L.host_i32(in_shape), L.host_i32(ks), L.host_i32(st),
+                                        L.host_i32(pd), L.host_i32([1, 1, 1]), 1 if subm else 0, p(nbr), ctypes.c_longlong(stride_rows),
+                                        p(masks)))
+    return nbr[:, :v_out], masks
+
+
+@pytest.mark.parametrize('ks,st,pd,subm', [([3, 3, 3], [1, 1, 1], [1, 1, 1], True), ([3, 3, 3], [2, 2, 2], [1, 1, 1], False),
+                                           ([3, 3, 3], [2, 2, 2], [0, 1, 1], False), ([3, 1, 1], [2, 1, 1], [0, 0, 0], False)])
+def test_row_walk_device_logic_matches_oracle_rulebook_on_host(ks, st, pd, subm):
+    """The source of nbr_bitmap_rows_kernel's inner walk, compiled for the HOST (isf_debug_nbr_rows_host), against the
+    oracle's rulebook (itself pinned by the reference's spconv C++): neighbour rows and occupancy masks, incl. offsets
+    that straddle a 32-cell bitmap word and cells on the grid border."""
+    import tile_occupancy as to
+    from oracle import spconv_ops as so
+    rs = np.random.RandomState(3)
+    shape, batch = [11, 37, 45], 2                      # x extent not a multiple of 32: words straddle rows
+    cells = batch * shape[0] * shape[1] * shape[2]
+    lin = np.sort(rs.permutation(cells)[:6000])
+    idx = np.stack([lin // (shape[0] * shape[1] * shape[2]), (lin // (shape[1] * shape[2])) % shape[0],
+                    (lin // shape[2]) % shape[1], lin % shape[2]], 1).astype(np.int32)
+    oi, oshape, want = so.get_indice_pairs(torch.from_numpy(idx), batch, shape, ks, st, pd, [1, 1, 1], subm)
+    got, masks = _host_row_walk(idx, oi.numpy(), shape, batch, ks, st, pd, subm)
+    assert np.array_equal(got, want.numpy().astype(np.int32))
+    pos = to.library_tap_bits(tuple(ks))
+    want_mask = np.zeros(got.shape[1], np.uint32)
+    for k in range(got.shape[0]):
+        want_mask |= (want.numpy()[k] >= 0).astype(np.uint32) << np.uint32(pos[k])
+    assert np.array_equal(masks, want_mask)
