@@ -214,10 +214,10 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    from __graft_entry__ import make_pair
+    from __graft_entry__ import make_net
     from isfusion_b200 import _lib as L
     import isfusion_b200.spconv as spmod
-    _, net = make_pair(0)
+    net = make_net(0)              # product modules only: the oracle is not touched by the B200 arm
     net = net.to(dev).eval()
     B, F_ = args.batch, args.frames
     IMG = img_hw_of(args)

@@ -659,7 +659,7 @@ extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const voi
 // The kernel skips a kernel offset for a whole tile when none of the tile's rows has a neighbour there, and
 // zero-fills the slot of every row that lacks one otherwise.  With the rows taken in storage order (ascending
 // (b,z,y,x)) a tile of a LiDAR frame touches ~25 of the 27 offsets while a row has 4-20 neighbours: 40-75 % of the
-// gathered slots and of the issued MMAs are zeros (scripts/tile_occupancy.py).  Spatial re-blocking does not
+// gathered slots and of the issued MMAs are zeros (tests/analysis/tile_occupancy.py).  Spatial re-blocking does not
 // change that; grouping rows by their NEIGHBOUR PATTERN does: rows are stably sorted by their 27-bit occupancy
 // mask (rarest kernel offsets = most significant bits), optionally inside chunks of 2^chunk_log2 consecutive rows
 // (keeps the gathers of a tile inside a bounded window of the feature matrix).  Storage order is untouched: the

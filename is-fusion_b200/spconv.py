@@ -88,7 +88,7 @@ class Rulebook:
         self.nbr_ordered = self.row_perm = None     # tile order (TILE_ORDER): regrouped table + tile slot -> storage row
 
 
-# Opt-in tile order of the implicit GEMM (csrc/spconv.cu "Tile order", scripts/tile_occupancy.py): None = rows in
+# Opt-in tile order of the implicit GEMM (csrc/spconv.cu "Tile order", tests/analysis/tile_occupancy.py): None = rows in
 # storage order (default); an int = rows regrouped by neighbour pattern inside chunks of 2**TILE_ORDER consecutive rows
 # (31 = one global sort).  Results are bit-identical either way.  Environment: ISF_TILE_ORDER=<int>.
 TILE_ORDER = int(os.environ['ISF_TILE_ORDER']) if os.environ.get('ISF_TILE_ORDER') else None

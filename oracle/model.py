@@ -11,28 +11,7 @@ import torch.nn.functional as F
 
 from . import fusion_ops, spconv_ops, voxel_ops
 
-VOXEL_SIZE = [0.075, 0.075, 0.2]
-PC_RANGE = [-54, -54, -5, 54, 54, 3]
-
-
-def neck_config(voxel_size=VOXEL_SIZE, pc_range=PC_RANGE, out_size_factor=8):
-    voxel_shape = int((pc_range[3] - pc_range[0]) // voxel_size[0])
-    bev = voxel_shape // out_size_factor
-    return dict(
-        voxel_size=voxel_size, pc_range=pc_range, out_size_factor=out_size_factor, bev_size=bev,
-        pts_voxel_encoder=dict(in_channels=5, feat_channels=[64, 64], with_distance=False, voxel_size=voxel_size,
-                               with_cluster_center=True, with_voxel_center=True, point_cloud_range=pc_range,
-                               norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01)),
-        pts_middle_encoder=dict(in_channels=64, sparse_shape=[41, voxel_shape, voxel_shape], base_channels=32,
-                                output_channels=256, order=('conv', 'norm', 'act'),
-                                encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
-                                encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock'),
-        fusion_encoder=dict(num_points_in_pillar=12, embed_dims=256, bev_size=bev, num_views=6,
-                            region_shape=[(6, 6, 1), (6, 6, 1)], grid_size=[[bev, bev, 1], [bev // 2, bev // 2, 1]],
-                            region_drop_info=[{0: {'max_tokens': 36, 'drop_range': (0, 100000)}},
-                                              {0: {'max_tokens': 36, 'drop_range': (0, 100000)}}], instance_num=200),
-        pts_backbone=dict(in_channels=128, out_channels=[128, 256], layer_nums=[5, 5], layer_strides=[1, 2],
-                          norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), conv_cfg=dict(type='Conv2d', bias=False)))
+from synth import PC_RANGE, VOXEL_SIZE, neck_config  # noqa: E402,F401  (the workload definition is shared with the product's bench)
 
 
 class ISFusionNeck(nn.Module):

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import synth  # noqa: E402
-from __graft_entry__ import make_pair  # noqa: E402
+from __graft_entry__ import make_net  # noqa: E402
 from isfusion_b200 import _lib as L  # noqa: E402
 import isfusion_b200.spconv as spmod  # noqa: E402
 
@@ -25,7 +25,7 @@ def main():
     ap.add_argument('--tile-order', default='', help='comma-separated chunk log2 values, e.g. 12,16,31')
     ap.add_argument('--reps', type=int, default=10)
     args = ap.parse_args()
-    _, net = make_pair(0)
+    net = make_net(0)
     net = net.cuda().eval()
     pts = [synth.make_points(args.points, args.cloud, 8).cuda()]
     l2i, aug, laug = synth.make_calib(1)

@@ -1,14 +1,14 @@
 """CPU analysis (no GPU): how many zero-filled slots does the output-stationary implicit GEMM multiply, per stage,
 and how does that change with the assignment of rows to 128-row tiles?
 
-  python scripts/tile_occupancy.py [--points 300000] [--cloud S]
+  python tests/analysis/tile_occupancy.py [--points 300000] [--cloud S]
 
 For every SubM stage of the SparseEncoder on the synthetic frame it builds the neighbour table with the oracle and
 reports, for each candidate tile assignment (a permutation of the rows; storage order is untouched, the kernel
 would read nbr[k][perm[i]] and scatter row perm[i] in its epilogue):
   useful = pairs, issued = 128 * sum_tiles #(kernel offsets with >= 1 neighbour in the tile)   (what the kernel gathers
   and multiplies: chunks whose offset has no neighbour in the whole tile are skipped), fill = useful / issued.
-TEST/ANALYSIS INFRASTRUCTURE: imports oracle/ (allowed for scripts that are not the product path)."""
+TEST / ANALYSIS INFRASTRUCTURE (lives under tests/: it imports oracle/ for the rulebooks)."""
 import argparse
 import os
 import sys
@@ -16,7 +16,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import synth  # noqa: E402
 from oracle import spconv_ops as so, voxel_ops  # noqa: E402
 

@@ -45,3 +45,25 @@ def test_product_does_not_import_oracle():
             if f.endswith('.py') or f.endswith('.cu') or f.endswith('.cuh'):
                 src = open(os.path.join(d, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(d, f)
+
+
+def test_only_the_checkers_import_the_oracle():
+    """tier rule: oracle/ is test infrastructure — outside tests/ only __graft_entry__ (build of the checker, smoke(),
+    make_pair for the parity tests) and bench.py's CPU legs (oracle_fps, reached by --impl reference / cpu_baseline) use it."""
+    import ast
+    allowed = {'__graft_entry__.py': {'build', 'make_pair', 'smoke'}, 'bench.py': {'oracle_fps'}}
+    for d, dirs, files in os.walk(ROOT):
+        dirs[:] = [x for x in dirs if x not in ('.git', 'tests', 'oracle', 'gpurun_out', '__pycache__', 'baseline')]
+        for f in files:
+            if not f.endswith('.py'):
+                continue
+            path = os.path.join(d, f)
+            tree = ast.parse(open(path).read())
+            for fn in ast.walk(tree):
+                if isinstance(fn, (ast.FunctionDef, ast.Module)):
+                    for node in (fn.body if isinstance(fn, ast.Module) else ast.walk(fn)):
+                        hit = (isinstance(node, ast.ImportFrom) and (node.module or '').split('.')[0] == 'oracle') or \
+                              (isinstance(node, ast.Import) and any(a.name.split('.')[0] == 'oracle' for a in node.names))
+                        if hit:
+                            name = fn.name if isinstance(fn, ast.FunctionDef) else '<module>'
+                            assert name in allowed.get(os.path.relpath(path, ROOT), set()), (path, name)

@@ -1,7 +1,7 @@
 """Tile order of the sparse-conv implicit GEMM (csrc/spconv.cu, isf_spconv_tile_order; opt-in via
 isfusion_b200.spconv.TILE_ORDER / ISF_TILE_ORDER).
 
-CPU part: the host-side key layout and a numpy model of the order (scripts/tile_occupancy.py) on an oracle rulebook.
+CPU part: the host-side key layout and a numpy model of the order (tests/analysis/tile_occupancy.py) on an oracle rulebook.
 GPU part (bring-up, ISF_EXPERIMENTAL=1: written at the end of round 1 without GPU time left to run it): the device
 order equals the model and every convolution over the regrouped table is BIT-IDENTICAL to the default launch."""
 import ctypes
@@ -13,7 +13,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'analysis'))
 experimental = pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='opt-in path: set ISF_EXPERIMENTAL=1')
 
 
