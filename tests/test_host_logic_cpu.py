@@ -61,3 +61,21 @@ def test_dense_conv_plan_cache_keys_do_not_alias():
     assert a.shape[0] == b.shape[0] == 9 and (oh, ow) == (3, 3)
     assert int((a[4, :36] == torch.arange(36)).all())                      # centre tap of a stride-1 conv = identity
     assert int((b[4, :9] == torch.tensor([0, 2, 4, 12, 14, 16, 24, 26, 28])).all())
+
+
+def test_head_small_mha_equals_the_reference_mha():
+    """head._mha_small (self-attention of the 200 queries via SDPA) == the reference's custom multi_head_attention_forward
+    as restated by the oracle ([L,B,E] layout, q scaled by head_dim**-0.5)."""
+    from isfusion_b200.head import _mha_small
+    from isfusion_b200.fusion_encoder import MultiheadAttention
+    torch.manual_seed(0)
+    e, h, b, lq, lk = 128, 8, 2, 50, 70
+    ref = fusion_ops.MultiheadAttention(e, h)
+    ref.in_proj_bias.data.normal_(0, 0.1)
+    ref.out_proj.bias.data.normal_(0, 0.1)
+    mod = MultiheadAttention(e, h)
+    mod.load_state_dict(ref.state_dict())
+    q, k = torch.randn(b, lq, e), torch.randn(b, lk, e)
+    want = ref(q.transpose(0, 1), k.transpose(0, 1), k.transpose(0, 1))[0].transpose(0, 1)
+    got = _mha_small(mod, q, k, k)
+    assert torch.allclose(got, want, atol=1e-5)
