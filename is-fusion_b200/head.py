@@ -171,6 +171,19 @@ class TransFusionHeadV2(_Packable):
             self.__dict__['_pk'] = pk
         return self.__dict__['_pk']
 
+    @staticmethod
+    def _topk(logits, k, plain_from):
+        """[B, classes, H, W] fp32 logits -> [B, k] int32 flat indices class*H*W + cell of the k best NMS'ed scores."""
+        lib = L.lib()
+        bs, classes, gh, gw = logits.shape
+        wsb = ctypes.c_size_t(0)
+        L.check(lib.isf_heatmap_topk_workspace_size(bs, classes, gh, gw, ctypes.byref(wsb)))
+        ws = L.workspace(wsb.value, logits.device)
+        top = torch.empty((bs, k), dtype=torch.int32, device=logits.device)
+        L.check(lib.isf_heatmap_topk_class(L.ptr(logits), bs, classes, gh, gw, plain_from, k, L.ptr(top), L.ptr(None), L.ptr(ws),
+                                           ctypes.c_size_t(ws.numel()), L.stream()))
+        return top
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward_single(self, inputs, img_inputs=None, metas=None):
@@ -181,7 +194,6 @@ class TransFusionHeadV2(_Packable):
             raise L.IsfError('expected a CUDA tensor (the product path has no CPU fallback)')
         dev = inputs.device
         pk = self._pack(dev)
-        lib = L.lib()
         bs, _, gh, gw = inputs.shape
         if (gh, gw) != (self.x_size, self.y_size):
             raise L.IsfError('TransFusionHeadV2: feature map %dx%d does not match test_cfg grid %dx%d' % (gh, gw, self.x_size, self.y_size))
@@ -191,15 +203,10 @@ class TransFusionHeadV2(_Packable):
         lidar = _conv(x, pk['shared'], relu=False)                                             # [B,H,W,C] fp16
         logits = _conv(_conv(lidar, pk['hm0']), pk['hm1'], relu=False).permute(0, 3, 1, 2).float().contiguous()   # [B,cls,H,W]
         # proposals: sigmoid + 3x3 local-max NMS + top-k over class x cell (:789-826)
-        wsb = ctypes.c_size_t(0)
-        L.check(lib.isf_heatmap_topk_workspace_size(bs, self.num_classes, gh, gw, ctypes.byref(wsb)))
-        ws = L.workspace(wsb.value, dev)
-        top = torch.empty((bs, k), dtype=torch.int32, device=dev)
-        plain_from = 8 if self.test_cfg['dataset'] == 'nuScenes' else self.num_classes
         if self.test_cfg['dataset'] not in ('nuScenes',):
             raise L.IsfError('TransFusionHeadV2: built for the nuScenes class exemptions (classes 8, 9)')
-        L.check(lib.isf_heatmap_topk_class(L.ptr(logits), bs, self.num_classes, gh, gw, plain_from, k, L.ptr(top), L.ptr(None),
-                                           L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+        plain_from = 8
+        top = self._topk(logits, k, plain_from)
         top = top.long()
         top_class, top_index = top // hw, top % hw
         self.query_labels = top_class
@@ -225,7 +232,7 @@ class TransFusionHeadV2(_Packable):
             e, h = mha.embed_dim, mha.num_heads
             src = (toks + d['kpe'][None]).reshape(bs * hw, c)
             kv = gemm(src, d['wkv'], shift=d['bkv']).view(bs, hw, 2, h, e // h)                # fp16
-            qc = F.linear(query + qpe, mha.in_proj_weight[:e], mha.in_proj_bias[:e]).half()
+            qc = F.linear(query + qpe, mha.in_proj_weight[:e], mha.in_proj_bias[:e]).to(kv.dtype)
             o = F.scaled_dot_product_attention(qc.view(bs, k, h, e // h).transpose(1, 2), kv[:, :, 0].transpose(1, 2),
                                                kv[:, :, 1].transpose(1, 2))                  # [B,h,K,d]
             query = layer.norm2(query + mha.out_proj(o.transpose(1, 2).reshape(bs, k, e).float()))
