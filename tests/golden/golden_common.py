@@ -146,7 +146,8 @@ def lss_cfg():
 
 def lss_inputs(n_img=3, seed=0):
     """Swin-T stage outputs of a 128x352 image (strides 8 / 16 / 32)."""
-    return [rand('lss_in%d' % i, (n_img, c, 128 // s, 352 // s), seed, 0.5) for i, (c, s) in enumerate(((192, 8), (384, 16), (768, 32)))]
+    return [rand('lss_in%d' % i, (n_img, c, 128 // s, 352 // s), seed, 0.5).half().float()       # fp16-representable
+            for i, (c, s) in enumerate(((192, 8), (384, 16), (768, 32)))]
 
 
 # ----------------------------------------------------------------------------- head (SURVEY 8f rank 2)

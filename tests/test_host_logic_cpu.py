@@ -148,3 +148,36 @@ def _fold_fp32(conv, bn):
     else:
         b = conv.bias if conv.bias is not None else torch.zeros(w.shape[0])
     return w.detach(), b.detach()
+
+
+def test_img_neck_module_logic_against_the_reference_run(monkeypatch):
+    """GeneralizedLSSFPN (img_neck.py): upsample -> concat -> 1x1 conv as a GEMM over pixel rows with folded BN -> 3x3
+    conv, with the GEMM / conv seams replaced by torch statements, against the reference module's run (ref_lss.npz)."""
+    import numpy as np
+    import isfusion_b200.img_neck as N
+
+    def conv_cpu(x_nhwc, packed, stride=1, relu=True):
+        w, b = packed
+        y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).float(), w.float(), b.float(), stride=stride, padding=1)
+        return (torch.relu(y) if relu else y).permute(0, 2, 3, 1)
+
+    def gemm_cpu(a, w, k=None, scale=None, shift=None, act=None, **kw):
+        y = (a.float() @ w.float()[:, :k].t()) * scale + shift
+        return torch.relu(y) if act == 'relu' else y
+
+    class FakeCuda(torch.Tensor):
+        @property
+        def is_cuda(self):
+            return True
+    monkeypatch.setattr(N, '_conv', conv_cpu)
+    monkeypatch.setattr(N, 'gemm', gemm_cpu)
+    monkeypatch.setattr(N, '_fold_conv_bn', lambda conv, bn, t=False: _fold_fp32(conv, bn))
+    monkeypatch.setattr(N, 'pack_weight', lambda w: w.float())
+    g = np.load(os.path.join(HERE, 'golden', 'ref_lss.npz'))
+    net = gc.fill_state(N.GeneralizedLSSFPN(**gc.lss_cfg()), 8).eval()
+    outs = net([t.as_subclass(FakeCuda) for t in gc.lss_inputs()])
+    assert len(outs) == 2
+    for o, key, step in ((outs[0], 'out0_c8', 8), (outs[1], 'out1_c4', 4)):
+        a = torch.Tensor(o).float().detach().numpy()[:, ::step]
+        err = np.abs(a - g[key]).max() / np.abs(g[key]).max()
+        assert a.shape == g[key].shape and err < 3e-3, (key, err)         # the upsample runs on the fp16 map
