@@ -157,3 +157,51 @@ def test_channel_attention_on_grids_up_to_256(g):
     want = sp + torch.softmax(sp @ ip.transpose(2, 3), dim=-1) @ ip
     got = out.float().permute(0, 3, 1, 2)
     assert ((got - want).norm() / want.norm()).item() < 3e-3
+
+
+def test_detector_simple_test_end_to_end_against_the_oracle_pipeline():
+    """points + camera features -> neck -> SECONDFPN -> TransFusionHeadV2 -> boxes (ISFusionDetector.simple_test) against
+    the oracle pipeline with the same weights: proposal classes / scores of the best boxes agree."""
+    import synth
+    import isfusion_b200.detector as det
+    from oracle import fusion_ops as fo, head_ops, model as omodel
+    torch.manual_seed(0)
+    cfg = synth.neck_config()
+    fpn_cfg = dict(in_channels=[128, 256], out_channels=[256, 256], upsample_strides=[1, 2], norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01),
+                   upsample_cfg=dict(type='deconv', bias=False), use_conv_for_no_stride=True)
+    hcfg = gc.head_cfg()
+    hcfg['test_cfg'] = dict(hcfg['test_cfg'], grid_size=[1440, 1440, 40])
+    hcfg['bbox_coder'] = dict(hcfg['bbox_coder'], voxel_size=[0.075, 0.075])
+    neck = synth.randomize_bn(omodel.ISFusionNeck(cfg, shuffle_voxels=False)).eval()
+    fpn = synth.randomize_bn(fo.SECONDFPN(**fpn_cfg)).eval()
+    head = synth.randomize_bn(head_ops.TransFusionHeadV2(**hcfg)).eval()
+    net = det.ISFusionDetector(
+        pts_voxel_layer=dict(point_cloud_range=cfg['pc_range'], max_num_points=-1, voxel_size=cfg['voxel_size'], max_voxels=(-1, -1)),
+        pts_voxel_encoder=dict(type='DynamicVFE', **cfg['pts_voxel_encoder']),
+        pts_middle_encoder=dict(type='SparseEncoder', **cfg['pts_middle_encoder']),
+        fusion_encoder=dict(type='ISFusionEncoder', **cfg['fusion_encoder']),
+        pts_backbone=dict(type='SECONDV2', **cfg['pts_backbone']), pts_neck=dict(type='SECONDFPN', **fpn_cfg),
+        pts_bbox_head=dict(type='TransFusionHeadV2', **{k: v for k, v in hcfg.items() if k not in ('train_cfg', 'test_cfg')}),
+        test_cfg=dict(pts=hcfg['test_cfg']), detach=True, pc_range=cfg['pc_range'], voxel_size=cfg['voxel_size'], out_size_factor=8)
+    sd = dict(neck.state_dict())
+    sd.update({'pts_neck.' + k: v for k, v in fpn.state_dict().items()})
+    sd.update({'pts_bbox_head.' + k: v for k, v in head.state_dict().items()})
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    pts = [synth.make_points(20000, 'S', 2)]
+    l2i, aug, laug = synth.make_calib(1)
+    feats = synth.make_img_feats(1)
+    metas = [dict(input_shape=(256, 704))]
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    rf, _ = neck(pts, feats, metas, **kw)
+    want = head.get_bboxes(head(fpn(rf)))[0]
+    got = net.simple_test([p.cuda() for p in pts], metas, img_feats=[f.cuda() for f in feats], **kw)[0]['pts_bbox']
+    assert got['boxes_3d'].shape[1] == 9 and got['boxes_3d'].shape[0] == got['scores_3d'].shape[0] == got['labels_3d'].shape[0]
+    # the 20 most confident boxes of the oracle are found by the CUDA path (same class, centre within one BEV cell)
+    order = torch.argsort(want['scores'], descending=True)[:20]
+    gb, gl = got['boxes_3d'].float().cpu(), got['labels_3d'].cpu()
+    hits = 0
+    for i in order:
+        d = (gb[:, :2] - want['bboxes'][i, :2]).norm(dim=1)
+        hits += int(((d < 0.6) & (gl == want['labels'][i])).any())
+    assert hits >= 16, hits
