@@ -1,11 +1,15 @@
 """Host wrapper of the tcgen05 GEMM (csrc/tc_gemm.cuh, isf_gemm_f16)."""
 import ctypes
+import os
 
 import torch
 
 from . import _lib as L
 
 ACT = {None: 0, 'none': 0, 'relu': 1, 'gelu': 2}
+
+if os.environ.get('ISF_GEMM_V2'):       # opt-in warp-specialised schedule (csrc/tc_gemm2.cuh): 1 = sparse convs, 2 = every GEMM
+    L.set_option('gemm_v2', int(os.environ['ISF_GEMM_V2']))
 
 
 def pack_weight(w, dtype=torch.float16):

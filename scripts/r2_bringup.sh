@@ -37,6 +37,11 @@ step "v2 warp-specialised GEMM schedule: bring-up tests (bounded waits trap inst
 timeout 300 python -m pytest tests/test_gemm_v2_gpu.py -x -q -m gpu            >> $LOG 2>&1 && {
   step "per-layer A/B: v2 alone and with tile orders"
   timeout 400 python scripts/bench_gemm_layers.py --v2 --tile-order 16,31     >> $LOG 2>&1
+  unset ISF_EXPERIMENTAL
+  step "bench: v2 on the sparse convs / on every GEMM, with tile order 31"
+  ISF_GEMM_V2=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline                   > gpurun_out/r2_bench_v2.json 2>> $LOG
+  ISF_GEMM_V2=2 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline                   > gpurun_out/r2_bench_v2all.json 2>> $LOG
+  ISF_GEMM_V2=2 ISF_TILE_ORDER=31 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_v2all_ord31.json 2>> $LOG
 }
 tail -n 80 $LOG
 for f in gpurun_out/r2_bench_*.json; do echo $f; python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['frame_latency_ms'], d['roofline']['frac'], d['roofline']['kernel_ms_per_step'])" 2>/dev/null; done
