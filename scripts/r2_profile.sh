@@ -12,14 +12,14 @@ TAG=${1:-r02}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --eager-only --steps 1 --warmup 1 --frames 2 > gpurun_out/profile_$TAG.log 2>&1
-# profile_spconv.py runs the sparse encoder twice: skip the first (cold) pass = 21 launches; launches 12 and 17 of the
-# second pass are the first SubM 128->128 and the first SubM 256->256 of a basic block with residual
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 33 -c 1 -o gpurun_out/gemm128_$TAG -f \
+# profile_spconv.py launches 2 DynamicVFE GEMMs, then the sparse encoder twice (21 launches each: conv_input, 4+1 per
+# stage 1-3, 4 of stage 4, conv_out).  Second (warm) pass: index 2 + 21 + 12 = 35 is a stage-3 SubM 128->128 with residual,
+# 2 + 21 + 17 = 40 a stage-4 SubM 256->256 with residual (check the kernel's grid / rows in the report).
+ncu --set full --clock-control none --import-source on -k regex:gemm -s 35 -c 1 -o gpurun_out/gemm128_$TAG -f \
     python scripts/profile_spconv.py >> gpurun_out/profile_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 38 -c 1 -o gpurun_out/gemm256_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:gemm -s 40 -c 1 -o gpurun_out/gemm256_$TAG -f \
     python scripts/profile_spconv.py >> gpurun_out/profile_$TAG.log 2>&1
 for k in gemm128 gemm256; do
-  ncu -i gpurun_out/${k}_$TAG.ncu-rep --page raw --csv 2>/dev/null | tr ',' '\n' | grep -n "" > /dev/null
   ncu -i gpurun_out/${k}_$TAG.ncu-rep --page raw --csv > gpurun_out/${k}_${TAG}_raw.csv 2>> gpurun_out/profile_$TAG.log
 done
 METRICS=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread
