@@ -139,6 +139,19 @@ def fusion_inputs(bs=2, seed=0, bev=None, pillars_per_frame=300):
                 img_metas=[dict(input_shape=IMG_SHAPE) for _ in range(bs)])
 
 
+# ----------------------------------------------------------------------------- image backbone
+def swin_cfg():
+    """configs/isfusion/isfusion_0075voxel.py:33-49 (Swin-T)."""
+    return dict(embed_dims=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7, mlp_ratio=4, qkv_bias=True, qk_scale=None,
+                drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, patch_norm=True, out_indices=[1, 2, 3], with_cp=False,
+                convert_weights=False)
+
+
+def swin_input(seed=0):
+    """two 62 x 94 images: not a multiple of the 4-pixel patch nor (after embedding) of the 7-token window."""
+    return rand('swin_input', (2, 3, 62, 94), seed).half().float()
+
+
 # ----------------------------------------------------------------------------- image neck (SURVEY 8f rank 1)
 def lss_cfg():
     return dict(in_channels=[192, 384, 768], out_channels=256, start_level=0, num_outs=3)

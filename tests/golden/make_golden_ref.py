@@ -17,6 +17,7 @@ Fixtures (checked by tests/test_oracle_vs_reference.py against oracle/):
   ref_vfe.npz     : DynamicVFE.forward (voxel_encoder.py:452-547) features + coordinates; DynamicScatter mean.
   ref_sparse.npz  : SparseEncoder.forward (sparse_encoder.py:107-138) dense output [B,512,H/8,W/8] and the
                     active-site count after every stage.
+  ref_swin.npz    : SwinTransformer.forward (backbones/swin.py:744-763, Swin-T of the config) on two 62x94 images.
   ref_lss.npz     : GeneralizedLSSFPN.forward (necks/generalized_lss.py:79-103) on Swin-T-shaped stage outputs of 3 images.
   ref_head.npz    : TransFusionHeadV2.forward (transfusion_head_v2.py:771-908) prediction dict on a [2,512,24,24] map,
                     query labels, and TransFusionBBoxCoder.decode (transfusion_bbox_coder.py:41-125) of it.
@@ -139,6 +140,18 @@ def sparse(R):
 
 
 @torch.no_grad()
+def swin(R):
+    R = ref_shim.install_swin()
+    net = gc.fill_state(R.SwinTransformer(**gc.swin_cfg()), 9)
+    net.eval()                                       # the reference's train() returns None
+    outs = net(gc.swin_input())
+    np.savez_compressed(os.path.join(HERE, 'ref_swin.npz'), out0=_np(outs[0]), out1=_np(outs[1]), out2=_np(outs[2]),
+                        rel_index=_np(net.stages[0].blocks[0].attn.w_msa.relative_position_index),
+                        keys=np.array(sorted(net.state_dict().keys())))
+    print('swin:', [tuple(o.shape) for o in outs])
+
+
+@torch.no_grad()
 def lss(R):
     net = gc.fill_state(R.GeneralizedLSSFPN(**gc.lss_cfg()), 8).eval()
     outs = net(gc.lss_inputs())
@@ -173,7 +186,7 @@ def head(R):
 
 if __name__ == '__main__':
     R = ref_shim.install()
-    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head', 'lss']
+    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head', 'lss', 'swin']
     for w in which:
         globals()[w](R)
     for f in sorted(os.listdir(HERE)):

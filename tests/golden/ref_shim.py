@@ -27,6 +27,7 @@ What is a stand-in (third-party code that is absent, restated from its published
     (mmdet3d/ops/voxel/scatter_points.py:53-104) is the reference's file.
 """
 import collections
+import collections.abc
 import importlib.util
 import inspect
 import os
@@ -218,7 +219,8 @@ def deprecated_api_warning(name_dict, cls_name=None):
 
 
 def to_2tuple(x):
-    return tuple(x) if isinstance(x, (list, tuple)) else (x, x)
+    """mmcv.utils.to_2tuple = _ntuple(2): any iterable (strings included, e.g. padding='corner') passes through."""
+    return x if isinstance(x, collections.abc.Iterable) else (x, x)
 
 
 # ----------------------------------------------------------------------------- mmdet BasicBlock (2.14)
@@ -543,6 +545,71 @@ def install():
         DynamicScatter=m['mmdet3d.ops'].DynamicScatter,
         sst_ops=m['mmdet3d.ops.sst.sst_ops'],
         SparseConvTensor=SparseConvTensor)
+
+
+_swin_installed = False
+
+
+class _MmcvFFN(BaseModule):
+    """mmcv/cnn/bricks/transformer.py FFN (mmcv 1.4): [Linear -> act -> Dropout] x (num_fcs-1) -> Linear -> Dropout,
+    + identity; parameter names layers.{i}.0.* and layers.{num_fcs-1}.*."""
+
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2, act_cfg=dict(type='ReLU', inplace=True),
+                 ffn_drop=0., dropout_layer=None, add_identity=True, init_cfg=None, **kwargs):
+        super().__init__(init_cfg)
+        act = {'GELU': nn.GELU, 'ReLU': nn.ReLU}[act_cfg['type']]
+        layers, cin = [], embed_dims
+        for _ in range(num_fcs - 1):
+            layers.append(nn.Sequential(nn.Linear(cin, feedforward_channels), act(), nn.Dropout(ffn_drop)))
+            cin = feedforward_channels
+        layers.append(nn.Linear(feedforward_channels, embed_dims))
+        layers.append(nn.Dropout(ffn_drop))
+        self.layers = nn.Sequential(*layers)
+        self.dropout_layer = nn.Identity()            # DropPath is the identity in eval mode
+        self.add_identity = add_identity
+
+    def forward(self, x, identity=None):
+        out = self.layers(x)
+        if not self.add_identity:
+            return self.dropout_layer(out)
+        return (x if identity is None else identity) + self.dropout_layer(out)
+
+
+def install_swin():
+    """additionally load the reference's SwinTransformer (backbones/swin.py) with its PatchEmbed /
+    PatchMerging (models/utils/transformer.py).  Stand-ins: mmcv FFN (above), DropPath = identity (eval), initialisers."""
+    global _swin_installed
+    ns = install()
+    m = sys.modules
+    if not _swin_installed:
+        class _Inert(nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+        cnn = m['mmcv.cnn']
+        cnn.constant_init = lambda *a, **k: None
+        cnn.trunc_normal_init = lambda *a, **k: None
+        cnn.xavier_init = lambda *a, **k: None
+        cnn.build_activation_layer = lambda cfg: {'GELU': nn.GELU, 'ReLU': nn.ReLU}[cfg['type']]()
+        _mod('mmcv.cnn.bricks.transformer', FFN=_MmcvFFN, build_dropout=lambda cfg: nn.Identity(),
+             BaseTransformerLayer=_Inert, TransformerLayerSequence=_Inert, build_transformer_layer_sequence=lambda *a, **k: None,
+             MultiScaleDeformableAttention=_Inert)
+        m['mmcv.ops.multi_scale_deform_attn'].MultiScaleDeformableAttention = _Inert
+        m['mmcv.runner']._load_checkpoint = lambda *a, **k: None
+        _pkg('mmdet.models.utils')
+        _mod('mmdet.models.utils.builder', TRANSFORMER=Registry('Transformer'))
+        _mod('mmdet3d.utils', get_root_logger=lambda *a, **k: None)
+        utils = sys.modules.get('mmdet3d.models.utils')
+        if utils is None or not hasattr(utils, '__path__'):
+            old = utils
+            utils = _pkg('mmdet3d.models.utils')
+            if old is not None:
+                utils.__dict__.update({k: v for k, v in old.__dict__.items() if not k.startswith('__')})
+        _load_ref('mmdet3d.models.utils.ckpt_convert', 'mmdet3d/models/utils/ckpt_convert.py')
+        _load_ref('mmdet3d.models.utils.transformer', 'mmdet3d/models/utils/transformer.py')
+        _load_ref('mmdet3d.models.backbones.swin', 'mmdet3d/models/backbones/swin.py')
+        _swin_installed = True
+    ns.SwinTransformer = m['mmdet3d.models.backbones.swin'].SwinTransformer
+    return ns
 
 
 _head_installed = False

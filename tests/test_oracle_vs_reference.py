@@ -186,3 +186,16 @@ def test_generalized_lss_fpn_matches_reference():
     assert len(outs) == 2
     _close(outs[0][:, ::8], g['out0_c8'], 'img_feats[0]')
     _close(outs[1][:, ::4], g['out1_c4'], 'img_feats[1]')
+
+
+def test_swin_backbone_matches_reference():
+    """SURVEY §8f rank 1 (image backbone): the reference's SwinTransformer run (padding to the patch / window size,
+    shifted-window masks, relative position bias, patch merging)."""
+    from oracle import image_ops
+    g = _load('ref_swin.npz')
+    net = gc.fill_state(image_ops.SwinTransformer(**gc.swin_cfg()), 9).eval()
+    _keys(net, g, 'keys')
+    assert np.array_equal(net.stages[0].blocks[0].attn.w_msa.relative_position_index.numpy(), g['rel_index'])
+    outs = net(gc.swin_input())
+    for i, o in enumerate(outs):
+        _close(o, g['out%d' % i], 'swin stage output %d' % (i + 1), 5e-4)
