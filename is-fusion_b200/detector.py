@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import fusion_encoder, head, img_neck, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
+from . import fusion_encoder, head, img_backbone, img_neck, sparse_encoder, voxel_encoder  # noqa: F401  (register the modules)
 from .registry import (DETECTORS, MODELS, NECKS, build_backbone, build_fusion_layer, build_middle_encoder,
                        build_voxel_encoder)
 from .profiling import stage
@@ -31,6 +31,7 @@ class ISFusionDetector(nn.Module):
         # img_neck (GeneralizedLSSFPN) turns the image backbone's stage outputs into img_feats; the
         # Swin backbone itself stays the reference's module
         self.img_neck = NECKS.build(dict(img_neck)) if img_neck is not None else None
+        self.img_backbone = MODELS.build(dict(img_backbone)) if img_backbone is not None else None
         # pts_bbox_head (TransFusionHeadV2): like MVXTwoStageDetector, train_cfg.pts / test_cfg.pts are handed to the head
         self.pts_bbox_head = None
         if pts_bbox_head is not None:
@@ -153,6 +154,18 @@ class ISFusionDetector(nn.Module):
     forward = extract_pts_feat
 
     @torch.no_grad()
+    def extract_img_feat(self, img, img_metas):
+        """ref: isfusion.py:54-82: img [B, N, 3, H, W] -> img_feats (tuple of [B*N, 256, h, w]); records input_shape."""
+        if self.img_backbone is None or img is None:
+            return None
+        input_shape = tuple(img.shape[-2:])
+        for meta in img_metas:
+            meta.update(input_shape=input_shape)
+        b, n, c, h, w = img.shape
+        feats = self.img_backbone(img.view(b * n, c, h, w))
+        return self.img_neck(feats) if self.img_neck is not None else feats
+
+    @torch.no_grad()
     def simple_test_pts(self, x, x_img=None, img_metas=None, rescale=False):
         """ref: isfusion.py:272-281: head forward + box decoding on the pts_neck output.  Returns per sample
         dict(boxes_3d [K,9] tensor, scores_3d, labels_3d) — `bbox3d2result` without the mmdet3d box class."""
@@ -163,8 +176,10 @@ class ISFusionDetector(nn.Module):
                 for b in self.pts_bbox_head.get_bboxes(outs, img_metas, rescale=rescale)]
 
     @torch.no_grad()
-    def simple_test(self, points, img_metas, img_feats=None, rescale=False, **kwargs):
-        """ref: isfusion.py:283-302 with the image branch's feature maps given (`img_feats` = extract_img_feat output)."""
+    def simple_test(self, points, img_metas, img=None, img_feats=None, rescale=False, **kwargs):
+        """ref: isfusion.py:283-302; `img` [B, N, 3, H, W] runs the image branch, or pass its output as `img_feats`."""
+        if img_feats is None:
+            img_feats = self.extract_img_feat(img, img_metas)
         if self.pts_neck is None:
             raise RuntimeError('ISFusionDetector.simple_test: the head consumes the pts_neck output (config:105-112)')
         feats, _ = self.extract_pts_feat(points, img_feats, img_metas, **kwargs)

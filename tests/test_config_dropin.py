@@ -16,7 +16,7 @@ def test_reference_config_builds_b200_modules():
     exec(compile(open(CFG).read(), CFG, 'exec'), ns)       # the config is self-contained (no _base_)
     model = dict(ns['model'])
     assert model['type'] == 'ISFusionDetector'
-    det = build_detector(model)                            # img_backbone / img_neck are outside the path
+    det = build_detector(model)                            # every sub-module of the config is built by name
     sd = det.state_dict()
     expected = [
         'pts_voxel_encoder.vfe_layers.0.linear.weight', 'pts_voxel_encoder.vfe_layers.1.norm.running_var',
@@ -31,6 +31,8 @@ def test_reference_config_builds_b200_modules():
         'fusion_encoder.instance_to_scene_att.multihead_attn.in_proj_weight', 'fusion_encoder.instance_to_scene_att.norm.weight',
         'pts_backbone.blocks.0.15.weight', 'pts_backbone.ds_layer.1.running_var', 'pts_backbone.blocks.1.12.weight',
         'pts_neck.deblocks.0.0.weight', 'pts_neck.deblocks.1.1.running_mean',
+        'img_backbone.patch_embed.projection.weight', 'img_backbone.stages.2.blocks.5.attn.w_msa.relative_position_bias_table',
+        'img_backbone.stages.1.downsample.reduction.weight', 'img_backbone.stages.3.blocks.1.ffn.layers.1.bias', 'img_backbone.norm3.weight',
         'img_neck.lateral_convs.1.conv.weight', 'img_neck.fpn_convs.0.bn.running_mean',
         'pts_bbox_head.shared_conv.bias', 'pts_bbox_head.heatmap_head.0.bn.running_var', 'pts_bbox_head.class_encoding.weight',
         'pts_bbox_head.decoder.0.multihead_attn.in_proj_weight', 'pts_bbox_head.decoder.0.cross_posembed.position_embedding_head.0.weight',

@@ -181,3 +181,39 @@ def test_img_neck_module_logic_against_the_reference_run(monkeypatch):
         a = torch.Tensor(o).float().detach().numpy()[:, ::step]
         err = np.abs(a - g[key]).max() / np.abs(g[key]).max()
         assert a.shape == g[key].shape and err < 3e-3, (key, err)         # the upsample runs on the fp16 map
+
+
+def test_swin_module_logic_against_the_reference_run(monkeypatch):
+    """The product SwinTransformer's own forward (patch embedding as a GEMM over unfolded patches, window partition /
+    cyclic shift / padding glue, bias + shift mask as one additive SDPA mask, patch merging) in fp32 on the CPU, GEMM seam
+    replaced by a torch statement, against the reference module's run (ref_swin.npz)."""
+    import numpy as np
+    import isfusion_b200.img_backbone as B
+
+    def gemm_cpu(a, w, k=None, shift=None, act=None, residual=None, **kw):
+        y = a.float() @ w.float()[:, :k].t()
+        if shift is not None:
+            y = y + shift
+        if residual is not None:
+            y = y + residual.float()
+        if act == 'gelu':
+            y = F.gelu(y)
+        return y
+
+    class FakeCuda(torch.Tensor):
+        @property
+        def is_cuda(self):
+            return True
+    monkeypatch.setattr(B, 'gemm', gemm_cpu)
+    monkeypatch.setattr(B, 'pack_weight', lambda w: w.float())
+    monkeypatch.setattr(B.SwinTransformer, 'act_dtype', torch.float32)
+    g = np.load(os.path.join(HERE, 'golden', 'ref_swin.npz'))
+    net = gc.fill_state(B.SwinTransformer(**gc.swin_cfg()), 9).eval()
+    assert sorted(net.state_dict().keys()) == list(g['keys'])
+    assert np.array_equal(net.stages[0].blocks[0].attn.w_msa.relative_position_index.numpy(), g['rel_index'])
+    outs = net(gc.swin_input().as_subclass(FakeCuda))
+    assert len(outs) == 3
+    for i, o in enumerate(outs):
+        a = torch.Tensor(o).float().detach().numpy()
+        err = np.abs(a - g['out%d' % i]).max() / np.abs(g['out%d' % i]).max()
+        assert a.shape == g['out%d' % i].shape and err < 5e-4, (i, err)

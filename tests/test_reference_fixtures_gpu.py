@@ -205,3 +205,15 @@ def test_detector_simple_test_end_to_end_against_the_oracle_pipeline():
         d = (gb[:, :2] - want['bboxes'][i, :2]).norm(dim=1)
         hits += int(((d < 0.6) & (gl == want['labels'][i])).any())
     assert hits >= 16, hits
+
+
+def test_swin_backbone_against_reference_run():
+    """linears on the tcgen05 GEMM, fp16 activations through 12 blocks, against the reference's fp32 run."""
+    from isfusion_b200.img_backbone import SwinTransformer
+    g = _g('ref_swin.npz')
+    net = gc.fill_state(SwinTransformer(**gc.swin_cfg()), 9).cuda().eval()
+    outs = net(gc.swin_input().cuda())
+    assert len(outs) == 3
+    for i, o in enumerate(outs):
+        assert tuple(o.shape) == g['out%d' % i].shape
+        assert _rel(o, g['out%d' % i]) < 2e-2, i
