@@ -417,6 +417,15 @@ __host__ __device__ __forceinline__ int isf_popc(unsigned int x) {
 
 static void tile_order_bits_fwd(const int* ksize, int taps, unsigned char* pos);   // = tile_order_bits (defined below)
 
+// sort key of an occupancy mask: the mask read as a binary-reflected Gray code, i.e. its rank along the Gray sequence.
+// Neighbouring keys then differ in ONE kernel offset, so the small mask groups that end up sharing a 128-row tile have
+// a smaller union than under the plain numeric order (-1.5 ... -4 % issued slots on the bench frame, tile_occupancy.py).
+__host__ __device__ __forceinline__ unsigned int tile_order_rank(unsigned int mask) {
+  unsigned int b = mask;
+  b ^= b >> 1; b ^= b >> 2; b ^= b >> 4; b ^= b >> 8; b ^= b >> 16;
+  return b;
+}
+
 // every kernel offset of the output site (b, z, y, x): MASK_ONLY = false writes the input row (or -1) of offset k to
 // dst[k * dst_stride]; MASK_ONLY = true only tests the bitmap (no prefix loads, no stores) and returns the occupancy mask
 // with offset k at bit pos[k].  The kW offsets of one (kz, ky) are adjacent cells = adjacent bits: one word (+ prefix)
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(256) nbr_bitmap_rows_kernel(const int* __restr
     const unsigned int mask = nbr_row_walk<MODE == 1>(o.x, o.y, o.z, o.w, g, bits, prefix, tb.pos, MODE == 1 ? nullptr : nbr + i,
                                                       nbr_stride);
     if (MODE == 1) {
-      keys[i] = ((unsigned long long)(chunk_shift < 31 ? (i >> chunk_shift) : 0) << g.kvol) | mask;
+      keys[i] = ((unsigned long long)(chunk_shift < 31 ? (i >> chunk_shift) : 0) << g.kvol) | tile_order_rank(mask);
       rows[i] = i;
     }
   }
@@ -678,7 +687,7 @@ __global__ void __launch_bounds__(256) tile_order_keys_kernel(const int* __restr
     unsigned int mask = 0;
     for (int k = 0; k < taps; ++k)
       if (nbr[(long long)k * nbr_stride + i] >= 0) mask |= 1u << tb.pos[k];
-    key = ((unsigned long long)(chunk_shift < 31 ? (i >> chunk_shift) : 0) << taps) | mask;
+    key = ((unsigned long long)(chunk_shift < 31 ? (i >> chunk_shift) : 0) << taps) | tile_order_rank(mask);
   } else {
     key = 1ull << invalid_bit;          // capacity rows beyond the device-side count sort last
   }

@@ -54,13 +54,27 @@ def library_tap_bits(ksize=(3, 3, 3)):
     return [int(pos[k]) for k in range(taps)]
 
 
+def occupancy_masks(valid, ksize=(3, 3, 3)):
+    """occupancy mask of every row with kernel offset k at bit library_tap_bits()[k]."""
+    pos = library_tap_bits(ksize)
+    mask = np.zeros(valid.shape[1], np.uint64)
+    for k in range(valid.shape[0]):
+        mask |= valid[k].astype(np.uint64) << np.uint64(pos[k])
+    return mask
+
+
+def mask_rank(mask):
+    """tile_order_rank of csrc/spconv.cu: the mask read as a binary-reflected Gray code (neighbouring keys differ in one offset)."""
+    b = mask.copy()
+    for s in (1, 2, 4, 8, 16):
+        b ^= b >> np.uint64(s)
+    return b
+
+
 def tile_order_model(valid, chunk_log2=31, ksize=(3, 3, 3), drop_bits=0):
     """CPU model of isf_spconv_tile_order: stable sort of the rows by (row >> chunk_log2, occupancy mask), the
     `drop_bits` least significant key bits left out (isf_set_option("tile_order_drop_bits"))."""
-    pos = library_tap_bits(ksize)
-    key = np.zeros(valid.shape[1], np.uint64)
-    for k in range(valid.shape[0]):
-        key |= valid[k].astype(np.uint64) << np.uint64(pos[k])
+    key = mask_rank(occupancy_masks(valid, ksize))
     if chunk_log2 < 31:
         key |= (np.arange(valid.shape[1], dtype=np.uint64) >> np.uint64(chunk_log2)) << np.uint64(valid.shape[0])
     return np.argsort(key >> np.uint64(drop_bits), kind='stable')
@@ -82,11 +96,42 @@ def orders(idx):
     return out
 
 
+def gathered_slots_4row(valid, perm):
+    """slots actually copied when a 4-row warp copy is skipped if none of its rows has a neighbour (v2 zero-skip)."""
+    k, v = valid.shape
+    pad = (-v) % TILE
+    m = valid[:, perm]
+    if pad:
+        m = np.concatenate([m, np.zeros((k, pad), bool)], 1)
+    return int(m.reshape(k, -1, TILE // 4, 4).any(3).sum()) * 4
+
+
+SUMMARY = []      # (name, useful slots, issued slots now, issued slots with the global tile order)
+
+
+def report(name, idx_np, valid, ksize=(3, 3, 3), spatial=True):
+    useful = int(valid.sum())
+    SUMMARY.append((name, useful, issued_slots(valid, np.arange(valid.shape[1]))[0],
+                    issued_slots(valid, tile_order_model(valid, 31, ksize))[0]))
+    v = valid.shape[1]
+    print('\n%s: rows = %d, pairs = %d (%.1f per row)' % (name, v, useful, useful / max(v, 1)))
+    cand = orders(idx_np) if spatial else {'sorted (b,z,y,x) [current]': np.arange(v)}
+    for cl in (12, 14, 16, 31):
+        cand['neighbour-pattern sort (isf_spconv_tile_order), chunk 2^%d' % cl] = tile_order_model(valid, cl, ksize)
+    base = None
+    for oname, perm in cand.items():
+        iss, tiles = issued_slots(valid, perm)
+        base = base or iss
+        print('   %-62s issued %9d  fill %.3f  offsets/tile %5.2f  issued vs current %.3f  | 4-row zero-skip copies vs current issued %.3f'
+              % (oname, iss, useful / iss, iss / TILE / tiles, iss / base, gathered_slots_4row(valid, perm) / base))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--points', type=int, default=300000)
     ap.add_argument('--cloud', default='S')
     ap.add_argument('--seed', type=int, default=8)
+    ap.add_argument('--all-orders', action='store_true', help='also list the spatial re-blockings (they do not help)')
     args = ap.parse_args()
     pts = synth.make_points(args.points, args.cloud, args.seed)
     vs, pr = [0.075, 0.075, 0.2], synth.PC_RANGE
@@ -94,25 +139,22 @@ def main():
     c = c[(c >= 0).all(1)]
     idx = torch.unique(torch.cat([torch.zeros(len(c), 1, dtype=c.dtype), c], 1), dim=0).int()
     shape = [41, 1440, 1440]
-    stages = [('stage1 SubM 32', None), ('stage2 SubM 64', (1, 1, 1)), ('stage3 SubM 128', (1, 1, 1)),
-              ('stage4 SubM 256', (0, 1, 1))]
-    chans = [32, 64, 128, 256]
-    for (name, pad), ch in zip(stages, chans):
+    stages = [('stage1 SubM 32', None), ('stage2 SubM 64', (1, 1, 1)), ('stage3 SubM 128', (1, 1, 1)), ('stage4 SubM 256', (0, 1, 1))]
+    for name, pad in stages:
         if pad is not None:
-            idx, shape, _ = so.get_indice_pairs(idx, 1, shape, 3, 2, list(pad), 1, False)
+            idx, shape, nbr_s = so.get_indice_pairs(idx, 1, shape, 3, 2, list(pad), 1, False)
+            report('strided SparseConv3d into ' + name.split()[0] + ' (padding %s)' % (pad,), idx.numpy(), (nbr_s >= 0).numpy(), spatial=False)
         _, _, nbr = so.get_indice_pairs(idx, 1, shape, 3, 1, 1, 1, True)
-        valid = (nbr >= 0).numpy()
-        useful = int(valid.sum())
-        print('\n%s: V = %d, pairs = %d (%.1f per row), grid %s' % (name, len(idx), useful, useful / len(idx), shape))
-        base = None
-        cand = orders(idx.numpy())
-        for cl in (12, 14, 16, 31):
-            cand['neighbour-pattern sort (isf_spconv_tile_order), chunk 2^%d' % cl] = tile_order_model(valid, cl)
-        for oname, perm in cand.items():
-            iss, tiles = issued_slots(valid, perm)
-            base = base or iss
-            print('   %-62s issued %9d  fill %.3f  offsets/tile %5.2f  issued vs current %.3f'
-                  % (oname, iss, useful / iss, iss / TILE / tiles, iss / base))
+        report(name + ' (grid %s)' % shape, idx.numpy(), (nbr >= 0).numpy(), spatial=args.all_orders)
+    oidx, oshape, nbr_o = so.get_indice_pairs(idx, 1, shape, (3, 1, 1), (2, 1, 1), [0, 0, 0], 1, False)
+    report('conv_out SparseConv3d (3,1,1)/(2,1,1)', oidx.numpy(), (nbr_o >= 0).numpy(), ksize=(3, 1, 1), spatial=False)
+    # whole encoder: every launch weighted by its Cin x Cout (config:72-82): conv_input 64->32 and 4 x 32->32 on the stage-1
+    # rulebook, strided 32->64, 4 x 64->64, strided 64->128, 4 x 128->128, strided 128->256, 4 x 256->256, conv_out 256->256
+    weights = [64 * 32 + 4 * 32 * 32, 32 * 64, 4 * 64 * 64, 64 * 128, 4 * 128 * 128, 128 * 256, 4 * 256 * 256, 256 * 256]
+    tot = np.array([[u * w, a * w, b * w] for (_, u, a, b), w in zip(SUMMARY, weights)], dtype=np.float64).sum(0) * 2
+    print('\nwhole sparse encoder (21 launches): useful %.0f GFLOP, issued now %.0f GFLOP (fill %.3f), issued with the global '
+          'tile order %.0f GFLOP (fill %.3f, x%.3f)' % (tot[0] / 1e9, tot[1] / 1e9, tot[0] / tot[1], tot[2] / 1e9, tot[0] / tot[2],
+                                                         tot[2] / tot[1]))
 
 
 if __name__ == '__main__':
