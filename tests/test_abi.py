@@ -67,3 +67,20 @@ def test_only_the_checkers_import_the_oracle():
                         if hit:
                             name = fn.name if isinstance(fn, ast.FunctionDef) else '<module>'
                             assert name in allowed.get(os.path.relpath(path, ROOT), set()), (path, name)
+
+
+def test_new_host_side_entry_points_validate_arguments():
+    import isfusion_b200._lib as L
+    lib = L.lib()
+    n = ctypes.c_size_t(0)
+    assert lib.isf_spconv_tile_order_workspace_size(300000, ctypes.byref(n)) == 0 and n.value > 300000 * 24
+    assert lib.isf_spconv_tile_order_workspace_size(-1, ctypes.byref(n)) == 1
+    for name, good, bad in (('tile_order_drop_bits', 11, 27), ('nbr_rows', 1, 2), ('gemm_v2', 2, 3), ('gemm_v2_io256', 0, 2),
+                            ('gemm_v2_zskip', 1, -1)):
+        assert lib.isf_set_option(name.encode(), good) == 0, name
+        assert lib.isf_set_option(name.encode(), bad) == 1 and b'unknown option or bad value' in lib.isf_last_error(), name
+    for name, default in (('tile_order_drop_bits', 0), ('nbr_rows', 0), ('gemm_v2', 0), ('gemm_v2_io256', 1), ('gemm_v2_zskip', 1)):
+        assert lib.isf_set_option(name.encode(), default) == 0
+    assert lib.isf_set_option(b'no_such_option', 1) == 1
+    # the tile-order entry points refuse bad geometry before touching the device
+    assert lib.isf_spconv_tile_order(None, ctypes.c_longlong(128), 27, None, 10, None, 31, None, None, None, ctypes.c_size_t(0), None) == 1
