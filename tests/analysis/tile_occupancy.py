@@ -107,10 +107,55 @@ def gathered_slots_4row(valid, perm):
 
 
 SUMMARY = []      # (name, useful slots, issued slots now, issued slots with the global tile order)
+VALID = []        # (name, valid [K, V], ksize) of every rulebook, in launch order
+
+# measured per-launch durations (us) of the 21 sparse-conv launches of this very frame (seed 8), from the ncu table
+# profiles/own_kernels_r01.txt (ids 15-19, 23, 25-28, 32, 34-37, 41, 43-46, 50): (rulebook index, Cin, Cout, us)
+MEASURED_R01 = [(0, 64, 32, 100.5), (0, 32, 32, 80.1), (0, 32, 32, 84.8), (0, 32, 32, 79.5), (0, 32, 32, 84.7), (1, 32, 64, 103.0),
+                (2, 64, 64, 160.6), (2, 64, 64, 167.0), (2, 64, 64, 161.5), (2, 64, 64, 170.6), (3, 64, 128, 178.5),
+                (4, 128, 128, 285.2), (4, 128, 128, 303.1), (4, 128, 128, 283.4), (4, 128, 128, 302.6), (5, 128, 256, 177.9),
+                (6, 256, 256, 257.6), (6, 256, 256, 274.0), (6, 256, 256, 259.2), (6, 256, 256, 274.9), (7, 256, 256, 44.7)]
+
+
+def chunk_blocks(valid, perm, cin):
+    """128-row x 64-K MMA blocks the kernel walks: a 64-wide K chunk covers 64/cin kernel offsets (cin < 64) or a
+    cin/64-th of one (cin >= 64) and is skipped for a tile when none of its offsets has a neighbour there."""
+    k, v = valid.shape
+    m = valid[:, perm]
+    pad = (-v) % TILE
+    if pad:
+        m = np.concatenate([m, np.zeros((k, pad), bool)], 1)
+    t = m.reshape(k, -1, TILE).any(2)
+    if cin < 64:
+        g = 64 // cin
+        kp = (-k) % g
+        if kp:
+            t = np.concatenate([t, np.zeros((kp, t.shape[1]), bool)], 0)
+        return int(t.reshape(-1, g, t.shape[1]).any(1).sum())
+    return int(t.sum()) * (cin // 64)
+
+
+def predict():
+    """ties the round-1 measurement to the pacing model of DESIGN.md 3.1: cycles per walked block per SM of every launch
+    (1965 MHz, 148 SMs), and the launch times the same cost per block predicts under the global tile order."""
+    print('\nper-launch cost model from the round-1 ncu durations (cold-cache, serialised: upper bounds):')
+    print('   %-4s %-10s %9s %8s %14s | %9s %8s' % ('#', 'Cin->Cout', 'blocks', 'us', 'cyc/block/SM', 'blocks*', 'us*'))
+    tot = tot_new = 0.0
+    for i, (rb, cin, cout, us) in enumerate(MEASURED_R01):
+        name, valid, ksize = VALID[rb]
+        b0 = chunk_blocks(valid, np.arange(valid.shape[1]), cin)
+        b1 = chunk_blocks(valid, tile_order_model(valid, 31, ksize), cin)
+        cyc = us * 1965.0 * 148 / b0
+        tot += us
+        tot_new += us * b1 / b0
+        print('   %-4d %-10s %9d %8.1f %14.0f | %9d %8.1f' % (i, '%d->%d' % (cin, cout), b0, us, cyc, b1, us * b1 / b0))
+    print('   sum of the 21 launches: %.0f us measured -> %.0f us predicted with the global tile order (x%.3f) if the cost per '
+          'walked block stays what it is' % (tot, tot_new, tot_new / tot))
 
 
 def report(name, idx_np, valid, ksize=(3, 3, 3), spatial=True):
     useful = int(valid.sum())
+    VALID.append((name, valid, ksize))
     SUMMARY.append((name, useful, issued_slots(valid, np.arange(valid.shape[1]))[0],
                     issued_slots(valid, tile_order_model(valid, 31, ksize))[0]))
     v = valid.shape[1]
@@ -155,6 +200,8 @@ def main():
     print('\nwhole sparse encoder (21 launches): useful %.0f GFLOP, issued now %.0f GFLOP (fill %.3f), issued with the global '
           'tile order %.0f GFLOP (fill %.3f, x%.3f)' % (tot[0] / 1e9, tot[1] / 1e9, tot[0] / tot[1], tot[2] / 1e9, tot[0] / tot[2],
                                                          tot[2] / tot[1]))
+    if args.points == 300000 and args.cloud == 'S' and args.seed == 8:
+        predict()
 
 
 if __name__ == '__main__':
