@@ -282,6 +282,13 @@ int isf_ms_deform_attn_forward(const void* value, int value_is_half, const long 
  *   (fusion_encoder.py:495-500, no 1/sqrt(d)); scene / ins / out channels-last fp16 with pitches lds/ldi/ldo. */
 int isf_i2s_attention(const void* q, const void* kv, int batch, int tokens, int num_keys, int channels, int heads,
                       void* out, void* stream);
+/* query -> scene attention (TransFusionHeadV2 cross attention, transfusion_head_v2.py:107-110 through
+ * multi_head_attention_forward :388-470): few queries x many keys, split over key blocks (flash-decoding), the tile code of
+ * isf_i2s_attention with the roles swapped.  q [B, queries, C] fp16 (projected, un-scaled), kv [B, num_keys, 2C] fp16 (k | v)
+ * -> out [B, queries, C] fp16.  C = 128, 8 heads. */
+int isf_query_scene_attention_workspace_size(int batch, int queries, int num_keys, int channels, int heads, size_t* bytes);
+int isf_query_scene_attention(const void* q, const void* kv, int batch, int queries, int num_keys, int channels, int heads,
+                              void* out, void* workspace, size_t ws_bytes, void* stream);
 int isf_channel_attention_workspace_size(int batch, int grid, int channels, size_t* bytes);
 int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid, int channels,
                           void* out, int ldo, void* workspace, size_t ws_bytes, void* stream);

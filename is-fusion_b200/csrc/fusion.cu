@@ -598,6 +598,169 @@ extern "C" int isf_i2s_attention(const void* q, const void* kv, int batch, int t
 }
 
 // ================================================================================================
+// query -> scene attention (TransFusionHeadV2 cross attention: 200 queries x 32 400 BEV keys, 8 heads, d = 16)
+// ================================================================================================
+// i2s_attention_kernel with the roles swapped: the few hundred queries are the rows, the scene tokens the keys.  The
+// keys are split into blocks of NKP; a CTA (8 warps = 8 heads) stages ONE key block of one frame in smem and runs every
+// 16-query tile against it with the same mma.sync tiles and register reuse as i2s_attention_kernel, but leaves the
+// softmax un-normalised: per (frame, key block, head, query) it writes the block's running maximum m (log2 domain), the
+// sum l of exp2(s - m) and the 16 un-normalised output values.  qs_combine_kernel merges the blocks:
+//   M = max_b m_b,  out = sum_b O_b 2^(m_b - M) / sum_b l_b 2^(m_b - M)        (flash-decoding split-K).
+// part layout: [B][blocks][HEADS][QP][D + 2] fp32 (QP = queries rounded up to 16).
+template <int C, int HEADS, int NKP>
+__global__ void __launch_bounds__(256) qs_attention_partial_kernel(const __half* __restrict__ q, const __half* __restrict__ kv,
+                                                                   int Q, int QP, int NK, float scaling,
+                                                                   float* __restrict__ part) {
+  constexpr int D = C / HEADS;          // 16
+  constexpr int PITCH = 2 * C + 8;
+  static_assert(D == 16, "query-scene attention is built for head_dim 16");
+  extern __shared__ __half sm_kv[];     // [NKP][PITCH]
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int k0 = blk * NKP;
+  const int nk = min(NKP, NK - k0);     // keys of this block (>= 1 by construction of the grid)
+  const __half* kvb = kv + ((size_t)b * NK + k0) * 2 * C;
+  for (int e = threadIdx.x; e < NKP * (2 * C / 8); e += blockDim.x) {
+    const int j = e / (2 * C / 8), c8 = (e % (2 * C / 8)) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (j < nk) v = *(const uint4*)(kvb + (size_t)j * 2 * C + c8);
+    *(uint4*)(sm_kv + (size_t)j * PITCH + c8) = v;
+  }
+  __syncthreads();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gr = lane >> 2, gc = (lane & 3) * 2;
+  const float sl2 = scaling * 1.44269504088896f;
+  float* pb = part + (((size_t)b * nblk + blk) * HEADS + h) * QP * (D + 2);
+  for (int q0 = 0; q0 < QP; q0 += 16) {
+    uint32_t qa[4];
+    {
+      const int r0 = q0 + gr, r1 = q0 + gr + 8;
+      const __half* p0 = q + ((size_t)b * Q + (r0 < Q ? r0 : Q - 1)) * C + h * D;
+      const __half* p1 = q + ((size_t)b * Q + (r1 < Q ? r1 : Q - 1)) * C + h * D;
+      qa[0] = *(const uint32_t*)(p0 + gc);
+      qa[1] = *(const uint32_t*)(p1 + gc);
+      qa[2] = *(const uint32_t*)(p0 + gc + 8);
+      qa[3] = *(const uint32_t*)(p1 + gc + 8);
+    }
+    float s[NKP / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < NKP / 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const __half* kr = sm_kv + (size_t)(nt * 8 + gr) * PITCH + h * D;
+      mma16816(s[nt], qa, *(const uint32_t*)(kr + gc), *(const uint32_t*)(kr + gc + 8));
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NKP / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + gc + (e & 1);
+        s[nt][e] = key < nk ? s[nt][e] * sl2 : -INFINITY;
+      }
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NKP / 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - m0); s[nt][1] = exp2f(s[nt][1] - m0);
+      s[nt][2] = exp2f(s[nt][2] - m1); s[nt][3] = exp2f(s[nt][3] - m1);
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NKP / 16; ++kt) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(s[2 * kt][0], s[2 * kt][1]);
+      pa[1] = pack_h2(s[2 * kt][2], s[2 * kt][3]);
+      pa[2] = pack_h2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+      pa[3] = pack_h2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+      const __half* vr = sm_kv + (size_t)(kt * 16 + gc) * PITCH + C + h * D + gr;   // V[key][dv]
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const uint32_t b0 = pack_2h(vr[n * 8], vr[PITCH + n * 8]);
+        const uint32_t b1 = pack_2h(vr[8 * PITCH + n * 8], vr[9 * PITCH + n * 8]);
+        mma16816(o[n], pa, b0, b1);
+      }
+    }
+    // un-normalised partials of rows r0 = q0 + gr and r1 = r0 + 8: columns n*8 + gc, +1 ; then m, l (written by gc == 0)
+    float* row0 = pb + (size_t)(q0 + gr) * (D + 2);
+    float* row1 = pb + (size_t)(q0 + gr + 8) * (D + 2);
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      row0[n * 8 + gc] = o[n][0]; row0[n * 8 + gc + 1] = o[n][1];
+      row1[n * 8 + gc] = o[n][2]; row1[n * 8 + gc + 1] = o[n][3];
+    }
+    if (gc == 0) { row0[D] = m0; row0[D + 1] = l0; row1[D] = m1; row1[D + 1] = l1; }
+  }
+}
+
+template <int C, int HEADS>
+__global__ void __launch_bounds__(256) qs_combine_kernel(const float* __restrict__ part, int Q, int QP, int nblk,
+                                                         __half* __restrict__ out) {
+  constexpr int D = C / HEADS;
+  // one thread per (frame, query, head, dim)
+  const long long total = (long long)gridDim.y * Q * C;
+  const int b = blockIdx.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Q * C; t += gridDim.x * blockDim.x) {
+    const int qi = t / C, c = t % C, h = c / D, d = c % D;
+    float M = -INFINITY;
+    for (int k = 0; k < nblk; ++k)
+      M = fmaxf(M, part[((((size_t)b * nblk + k) * HEADS + h) * QP + qi) * (D + 2) + D]);
+    float num = 0.f, den = 0.f;
+    for (int k = 0; k < nblk; ++k) {
+      const float* r = part + ((((size_t)b * nblk + k) * HEADS + h) * QP + qi) * (D + 2);
+      const float w = exp2f(r[D] - M);
+      num += r[d] * w;
+      den += r[D + 1] * w;
+    }
+    out[((size_t)b * Q + qi) * C + c] = __float2half(num / den);
+  }
+  (void)total;
+}
+
+extern "C" int isf_query_scene_attention_workspace_size(int batch, int queries, int num_keys, int channels, int heads,
+                                                        size_t* bytes) {
+  ISF_CHECK_ARG(bytes && batch >= 1 && queries >= 1 && num_keys >= 1 && channels == 128 && heads == 8);
+  const int qp = (queries + 15) / 16 * 16, nblk = (num_keys + 207) / 208;
+  *bytes = (size_t)batch * nblk * heads * qp * (channels / heads + 2) * sizeof(float) + 256;
+  return ISF_OK;
+}
+
+// q [B, queries, C] fp16 (already projected; the 1/sqrt(d) scale is applied here), kv [B, num_keys, 2C] fp16 (k | v)
+// -> out [B, queries, C] fp16 = softmax(q k^T / sqrt(d)) v per head
+extern "C" int isf_query_scene_attention(const void* q, const void* kv, int batch, int queries, int num_keys, int channels,
+                                         int heads, void* out, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(q && kv && out && workspace && batch >= 1 && queries >= 1 && num_keys >= 1);
+  if (channels != 128 || heads != 8) { isf_set_error("query_scene_attention: built for d_model 128, 8 heads"); return ISF_ERR_UNSUPPORTED; }
+  constexpr int NKP = 208, C = 128, H = 8;
+  const int qp = (queries + 15) / 16 * 16, nblk = (num_keys + NKP - 1) / NKP;
+  const size_t need = (size_t)batch * nblk * H * qp * (C / H + 2) * sizeof(float);
+  if (ws_bytes < need) { isf_set_error("query_scene_attention: workspace too small"); return ISF_ERR_WORKSPACE; }
+  const size_t smem = (size_t)NKP * (2 * C + 8) * sizeof(__half);
+  static bool cfg = false;
+  if (!cfg) {
+    ISF_CUDA(cudaFuncSetAttribute(qs_attention_partial_kernel<C, H, NKP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  qs_attention_partial_kernel<C, H, NKP><<<dim3(nblk, batch), 256, smem, st>>>((const __half*)q, (const __half*)kv, queries, qp,
+                                                                               num_keys, 1.0f / sqrtf(16.f), (float*)workspace);
+  ISF_LAUNCH_CHECK();
+  qs_combine_kernel<C, H><<<dim3(isf_cdiv(queries * C, 256), batch), 256, 0, st>>>((const float*)workspace, queries, qp, nblk,
+                                                                                  (__half*)out);
+  ISF_LAUNCH_CHECK();
+  isf_count_launch(2);
+  return ISF_OK;
+}
+
+// ================================================================================================
 // channel-wise scene attention: out[b,c] = S + softmax(S I^T, -1) I   with S, I the [G,G] planes of channel c
 // ================================================================================================
 // channels-last <-> planar transposes (the attention reads contiguous planes)

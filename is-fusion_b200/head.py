@@ -12,12 +12,14 @@ What runs where:
   * K/V projection of the 32 400 BEV tokens of the cross attention: ONE tcgen05 GEMM (N = 256) over
     `tokens + key positional embedding`; the embedding of the constant (x+.5, y+.5) grid is input independent and
     cached at pack time;
-  * the 200-query x 32 400-key attention core: `F.scaled_dot_product_attention` (library flash kernel, 3.3 GFLOP) —
-    the hand-written split-K kernel is the next step for this row;
+  * the 200-query x 32 400-key attention core: `F.scaled_dot_product_attention` (library flash kernel, 3.3 GFLOP) by
+    default; `ISF_HEAD_ATTN=own` runs `isf_query_scene_attention`, the tile code of the validated `i2s_attention_kernel`
+    with the roles swapped and the keys split over 208-key blocks (flash-decoding partials + a combine kernel);
   * the 200-query pieces (self attention, FFN, LayerNorms, Conv1d prediction heads, decode): fp32 torch ops (tiny).
 Eval mode only; training (targets, Hungarian assignment, losses) is out of scope."""
 import copy
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -82,6 +84,30 @@ class FFN(nn.Module):
 
     def forward(self, x):
         return {head: getattr(self, head)(x) for head in self.heads}
+
+
+OWN_ATTENTION = os.environ.get('ISF_HEAD_ATTN') == 'own'    # opt-in: the library's split-K kernel instead of SDPA
+
+
+def query_scene_attention(qc, kv, heads):
+    """softmax(q k^T / sqrt(d)) v of the cross attention: qc [B, K, C] (projected queries), kv [B, HW, 2, heads, d] (k | v of
+    the BEV tokens, one GEMM output) -> [B, K, C].  Default: torch SDPA (library flash kernel); ISF_HEAD_ATTN=own:
+    `isf_query_scene_attention` (csrc/fusion.cu: the i2s tile code with the roles swapped, split over 208-key blocks)."""
+    bs, k, e = qc.shape
+    hw = kv.shape[1]
+    if OWN_ATTENTION and e == 128 and heads == 8 and qc.dtype == torch.float16:
+        lib = L.lib()
+        wsb = ctypes.c_size_t(0)
+        L.check(lib.isf_query_scene_attention_workspace_size(bs, k, hw, e, heads, ctypes.byref(wsb)))
+        ws = L.workspace(wsb.value, qc.device)
+        out = torch.empty((bs, k, e), dtype=torch.float16, device=qc.device)
+        qcc, kvc = qc.contiguous(), kv.reshape(bs, hw, 2 * e).contiguous()
+        L.check(lib.isf_query_scene_attention(L.ptr(qcc), L.ptr(kvc), bs, k, hw, e, heads, L.ptr(out), L.ptr(ws),
+                                              ctypes.c_size_t(ws.numel()), L.stream()))
+        return out
+    o = F.scaled_dot_product_attention(qc.view(bs, k, heads, e // heads).transpose(1, 2), kv[:, :, 0].transpose(1, 2),
+                                       kv[:, :, 1].transpose(1, 2))                          # [B, heads, K, d]
+    return o.transpose(1, 2).reshape(bs, k, e)
 
 
 def _mha_small(m, q_in, k_in, v_in):
@@ -233,9 +259,8 @@ class TransFusionHeadV2(_Packable):
             src = (toks + d['kpe'][None]).reshape(bs * hw, c)
             kv = gemm(src, d['wkv'], shift=d['bkv']).view(bs, hw, 2, h, e // h)                # fp16
             qc = F.linear(query + qpe, mha.in_proj_weight[:e], mha.in_proj_bias[:e]).to(kv.dtype)
-            o = F.scaled_dot_product_attention(qc.view(bs, k, h, e // h).transpose(1, 2), kv[:, :, 0].transpose(1, 2),
-                                               kv[:, :, 1].transpose(1, 2))                  # [B,h,K,d]
-            query = layer.norm2(query + mha.out_proj(o.transpose(1, 2).reshape(bs, k, e).float()))
+            o = query_scene_attention(qc, kv, h)                                              # [B,K,C]
+            query = layer.norm2(query + mha.out_proj(o.float()))
             query = layer.norm3(query + layer.linear2(F.relu(layer.linear1(query))))
             res = self.prediction_heads[i](query.transpose(1, 2).contiguous())                # dict of [B,*,K]
             res['center'] = res['center'] + query_pos.permute(0, 2, 1)

@@ -217,3 +217,23 @@ def test_swin_backbone_against_reference_run():
     for i, o in enumerate(outs):
         assert tuple(o.shape) == g['out%d' % i].shape
         assert _rel(o, g['out%d' % i]) < 2e-2, i
+
+
+@pytest.mark.parametrize('nq,nk', [(200, 32400), (37, 576), (16, 208), (1, 209)])
+def test_query_scene_attention_kernel_against_sdpa(nq, nk):
+    """isf_query_scene_attention (split-K over 208-key blocks + combine) == softmax(q k^T / sqrt(d)) v."""
+    import isfusion_b200.head as H
+    torch.manual_seed(nq)
+    b, c, h = 2, 128, 8
+    q = (torch.randn(b, nq, c, device='cuda') * 0.7).half()
+    kv = (torch.randn(b, nk, 2, h, c // h, device='cuda') * 0.7).half()
+    try:
+        H.OWN_ATTENTION = False
+        want = H.query_scene_attention(q, kv, h).float()
+        H.OWN_ATTENTION = True
+        got = H.query_scene_attention(q, kv, h).float()
+        torch.cuda.synchronize()
+    finally:
+        H.OWN_ATTENTION = False
+    assert got.shape == want.shape == (b, nq, c)
+    assert ((got - want).norm() / want.norm()).item() < 3e-3
