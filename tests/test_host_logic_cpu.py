@@ -217,3 +217,26 @@ def test_swin_module_logic_against_the_reference_run(monkeypatch):
         a = torch.Tensor(o).float().detach().numpy()
         err = np.abs(a - g['out%d' % i]).max() / np.abs(g['out%d' % i]).max()
         assert a.shape == g['out%d' % i].shape and err < 5e-4, (i, err)
+
+
+def test_split_k_attention_algebra():
+    """the algorithm of qs_attention_partial_kernel + qs_combine_kernel (csrc/fusion.cu) stated in torch: per 208-key block
+    m = max of the log2-domain logits, l = sum 2^(s - m), O = sum 2^(s - m) v; merged with M = max m:
+    out = sum O_b 2^(m_b - M) / sum l_b 2^(m_b - M) == softmax(q k^T / sqrt(d)) v."""
+    torch.manual_seed(0)
+    nq, nk, d, blk = 37, 1000, 16, 208
+    q, k, v = torch.randn(nq, d), torch.randn(nk, d), torch.randn(nk, d)
+    sl2 = d ** -0.5 * 1.44269504088896
+    ms, ls, os_ = [], [], []
+    for k0 in range(0, nk, blk):
+        s = (q @ k[k0:k0 + blk].t()) * sl2
+        m = s.max(1, keepdim=True).values
+        p = torch.exp2(s - m)
+        ms.append(m); ls.append(p.sum(1, keepdim=True)); os_.append(p @ v[k0:k0 + blk])
+    m_all = torch.cat(ms, 1)
+    big = m_all.max(1, keepdim=True).values
+    w = torch.exp2(m_all - big)                                   # [nq, blocks]
+    num = sum(o * w[:, i:i + 1] for i, o in enumerate(os_))
+    den = sum(l * w[:, i:i + 1] for i, l in enumerate(ls))
+    want = torch.softmax((q @ k.t()) * d ** -0.5, -1) @ v
+    assert torch.allclose(num / den, want, atol=1e-5)
