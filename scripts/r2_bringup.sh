@@ -14,6 +14,8 @@ step "tile order (index kernels + the validated GEMM through out_rows / res_rows
 timeout 300 python -m pytest tests/test_tile_order.py -x -q -m gpu             >> $LOG 2>&1
 step "CUDA path directly against the reference-run fixtures (small grids, head, image neck, detector e2e)"
 timeout 400 python -m pytest tests/test_reference_fixtures_gpu.py -q -m gpu    >> $LOG 2>&1
+step "head with the own split-K attention kernel"
+ISF_HEAD_ATTN=own timeout 300 python -m pytest tests/test_reference_fixtures_gpu.py -q -m gpu -k "head or detector" >> $LOG 2>&1
 step "configs[4] geometry (0.05 m voxels, 256x256 BEV)"
 timeout 300 python -m pytest tests/test_config5_gpu.py -x -q -m gpu            >> $LOG 2>&1
 step "own dense 3x3 convs on the implicit-GEMM kernel"
