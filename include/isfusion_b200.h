@@ -254,6 +254,15 @@ int isf_cam2bev(const float* pillars, int num_pillars, const int* num_pillars_de
 int isf_window_attention(const void* qkv, const float* pos_q, const float* pos_k, int batch, int grid, int channels,
                          int heads, int shifted, void* out, void* stream);
 
+/* ---- image backbone: Swin shifted-window attention ----------------------------
+ * replaces the pad / roll / window_partition / WindowMSA core / window_reverse / roll / crop sequence of
+ * mmdet3d/models/backbones/swin.py:85-123,177-283.  qkv [B*H*W, 3C] fp16 token-major (bias included), qkv_bias [3C] fp32
+ * (value of a padding position), rel_bias [heads, 49, 49] fp32 -> out [B*H*W, C] fp16 (input of `proj`).  7x7 windows,
+ * head_dim 32, shift 0 | 3.  isf_debug_swin_window_map: host-only, the kernel's (window, slot) -> token / region closed form. */
+int isf_swin_window_attention(const void* qkv, const float* qkv_bias, const float* rel_bias, int batch, int H, int W, int channels,
+                              int heads, int shift, void* out, void* stream);
+int isf_debug_swin_window_map(int H, int W, int shift, int* tok, int* region);
+
 /* ---- a10: heat-map NMS + top-K --------------------------------------------------
  * replaces sigmoid / max_pool2d / argsort of fusion_encoder.py:1100-1131.  logits [B,classes,H,W] fp32;
  * classes >= plain_from keep every cell (kernel-size-1 classes); top_idx [B,k] int32 = flat cell index. */

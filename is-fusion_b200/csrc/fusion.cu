@@ -309,6 +309,222 @@ extern "C" int isf_window_attention(const void* qkv, const float* pos_q, const f
 }
 
 // ================================================================================================
+// Swin shifted-window attention (image backbone; opt-in ISF_SWIN_ATTN=own)
+// ================================================================================================
+// ref: mmdet3d/models/backbones/swin.py:85-123 (WindowMSA.forward) + :177-283 (ShiftWindowMSA.forward: pad to a multiple
+// of the window, cyclic shift, window partition, -100 mask between the regions the shift brings together, reverse).
+// Like window_attention_kernel above, every index the reference materialises (padding, roll, partition, mask, reverse,
+// roll back, crop) is a closed form of (window, slot): the kernel reads the TOKEN-MAJOR qkv matrix of the un-padded map
+// and writes token-major output rows, so the block needs no copies around the attention.
+struct SwinGeom { int H, W, Hp, Wp, shift, nwh, nww; };
+constexpr int SWIN_WS = 7, SWIN_TOK = 49;
+
+// token (row of the un-padded H x W map) held by slot `slot` of window (wy, wx) of the shifted, padded frame, or -1 for a
+// padding position; *region = the 3 x 3 region id of the reference's img_mask (0 when there is no shift).
+__host__ __device__ __forceinline__ int swin_token(const SwinGeom& g, int wy, int wx, int slot, int* region) {
+  const int ys = wy * SWIN_WS + slot / SWIN_WS, xs = wx * SWIN_WS + slot % SWIN_WS;      // shifted-frame coordinates
+  int rh = 0, rw = 0;
+  if (g.shift > 0) {
+    rh = ys < g.Hp - SWIN_WS ? 0 : (ys < g.Hp - g.shift ? 1 : 2);
+    rw = xs < g.Wp - SWIN_WS ? 0 : (xs < g.Wp - g.shift ? 1 : 2);
+  }
+  *region = rh * 3 + rw;
+  int yo = ys + g.shift, xo = xs + g.shift;                // shifted[y] = padded[(y + shift) mod Hp]  (torch.roll by -shift)
+  if (yo >= g.Hp) yo -= g.Hp;
+  if (xo >= g.Wp) xo -= g.Wp;
+  return (yo < g.H && xo < g.W) ? yo * g.W + xo : -1;
+}
+
+static SwinGeom swin_geom(int H, int W, int shift) {
+  SwinGeom g;
+  g.H = H; g.W = W;
+  g.Hp = (H + SWIN_WS - 1) / SWIN_WS * SWIN_WS; g.Wp = (W + SWIN_WS - 1) / SWIN_WS * SWIN_WS;
+  g.shift = shift; g.nwh = g.Hp / SWIN_WS; g.nww = g.Wp / SWIN_WS;
+  return g;
+}
+
+// host-only test hook: the window -> token map and region ids of swin_token for every (window, slot)
+extern "C" int isf_debug_swin_window_map(int H, int W, int shift, int* tok, int* region) {
+  ISF_CHECK_ARG(H >= 1 && W >= 1 && shift >= 0 && shift < SWIN_WS && tok && region);
+  const SwinGeom g = swin_geom(H, W, shift);
+  for (int w = 0; w < g.nwh * g.nww; ++w)
+    for (int s = 0; s < SWIN_TOK; ++s) tok[w * SWIN_TOK + s] = swin_token(g, w / g.nww, w % g.nww, s, &region[w * SWIN_TOK + s]);
+  return ISF_OK;
+}
+
+// CTA = one window x HPC heads (a warp per head, head_dim 32).  qkv [B*H*W, 3C] fp16 token-major (bias included);
+// padding positions carry qkv = the layer's bias (the reference pads AFTER norm1 with zeros, so qkv(0) = bias);
+// rel_bias [heads][49][49] fp32 = relative_position_bias_table[relative_position_index]; out [B*H*W, C] fp16.
+template <int HPC>
+__global__ void __launch_bounds__(HPC * 32) swin_window_attention_kernel(const __half* __restrict__ qkv,
+                                                                         const float* __restrict__ qkv_bias,
+                                                                         const float* __restrict__ rel_bias, SwinGeom g, int C,
+                                                                         float scaling, __half* __restrict__ out) {
+  constexpr int D = 32, CH = HPC * D, PITCH = CH + 8, KS = D / 16, NV = D / 8;
+  constexpr int TOKK = 56, TOKP = 64;                    // keys padded to 7 n-tiles / 4 k-steps, queries to 4 m-tiles
+  __shared__ __align__(16) __half ks[TOKK][PITCH];
+  __shared__ __align__(16) __half vs[TOKP][PITCH];
+  __shared__ int tok_id[TOKP];
+  __shared__ int reg_id[TOKP];
+  const int nw = g.nwh * g.nww;
+  const int b = blockIdx.x / nw, w = blockIdx.x % nw;
+  const int wy = w / g.nww, wx = w % g.nww;
+  const int cb = blockIdx.y * CH;                        // first channel of this CTA's heads
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)b * g.H * g.W;
+  for (int sidx = tid; sidx < TOKP; sidx += blockDim.x) {
+    int r = -1, t = -2;                                  // -2 = slot beyond the 49 tokens of a window
+    if (sidx < SWIN_TOK) t = swin_token(g, wy, wx, sidx, &r);
+    tok_id[sidx] = t;
+    reg_id[sidx] = r;
+  }
+  __syncthreads();
+  for (int e = tid; e < TOKP * (CH / 8); e += blockDim.x) {
+    const int slot = e / (CH / 8), c8 = (e % (CH / 8)) * 8;
+    const int t = tok_id[slot];
+    uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (t >= 0) {
+      const __half* row = qkv + (row0 + t) * 3 * C;
+      kk = *(const uint4*)(row + C + cb + c8);
+      vv = *(const uint4*)(row + 2 * C + cb + c8);
+    } else if (t == -1) {                                // padding position: k, v = bias
+      __half2* k2 = (__half2*)&kk;
+      __half2* v2 = (__half2*)&vv;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        k2[i] = __floats2half2_rn(qkv_bias[C + cb + c8 + 2 * i], qkv_bias[C + cb + c8 + 2 * i + 1]);
+        v2[i] = __floats2half2_rn(qkv_bias[2 * C + cb + c8 + 2 * i], qkv_bias[2 * C + cb + c8 + 2 * i + 1]);
+      }
+    }
+    if (slot < TOKK) *(uint4*)&ks[slot][c8] = kk;
+    *(uint4*)&vs[slot][c8] = vv;
+  }
+  __syncthreads();
+  const int hl = tid >> 5, lane = tid & 31;              // local head
+  const int head = blockIdx.y * HPC + hl;
+  const int gr = lane >> 2, gc = (lane & 3) * 2;
+  const float l2e = 1.44269504088896f;
+  const float* rb = rel_bias + (size_t)head * SWIN_TOK * SWIN_TOK;
+#pragma unroll 1
+  for (int mt = 0; mt < 4; ++mt) {
+    const int s0 = mt * 16 + gr, s1 = s0 + 8;            // query slots of this thread's two rows
+    const int t0 = tok_id[s0], t1 = tok_id[s1];
+    if (__all_sync(0xffffffffu, t0 < 0 && t1 < 0)) continue;        // nothing to store (padding / beyond the window)
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int kt = 0; kt < KS; ++kt) {
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {
+        const int tk = (part & 1) ? t1 : t0;
+        const int col = cb + hl * D + kt * 16 + gc + (part >> 1) * 8;
+        uint32_t v = 0;
+        if (tk >= 0) v = *(const uint32_t*)(qkv + (row0 + tk) * 3 * C + col);
+        qa[kt][part] = v;                                // rows that are not stored may hold anything finite
+      }
+    }
+    float sc[7][4];
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < KS; ++kt) {
+        const __half* kr = &ks[nt * 8 + gr][hl * D + kt * 16 + gc];
+        mma16816(sc[nt], qa[kt], *(const uint32_t*)kr, *(const uint32_t*)(kr + 8));
+      }
+    }
+    const int r0 = s0 < SWIN_TOK ? reg_id[s0] : 0, r1 = s1 < SWIN_TOK ? reg_id[s1] : 0;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + gc + (e & 1);
+        const int qs = (e & 2) ? s1 : s0;
+        float v = -INFINITY;
+        if (key < SWIN_TOK && qs < SWIN_TOK) {
+          v = sc[nt][e] * scaling + rb[qs * SWIN_TOK + key];
+          if (g.shift > 0 && reg_id[key] != ((e & 2) ? r1 : r0)) v += -100.f;
+          v *= l2e;
+        } else if (key < SWIN_TOK) {
+          v = 0.f;                                       // rows beyond the window: keep the softmax finite, never stored
+        }
+        sc[nt][e] = v;
+      }
+      m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    float pe[8][4];                                      // probabilities, keys padded to 64 (4 k-steps of 16)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      if (nt < 7) {
+        pe[nt][0] = exp2f(sc[nt][0] - m0); pe[nt][1] = exp2f(sc[nt][1] - m0);
+        pe[nt][2] = exp2f(sc[nt][2] - m1); pe[nt][3] = exp2f(sc[nt][3] - m1);
+        l0 += pe[nt][0] + pe[nt][1];
+        l1 += pe[nt][2] + pe[nt][3];
+      } else {
+        pe[nt][0] = pe[nt][1] = pe[nt][2] = pe[nt][3] = 0.f;
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[NV][4];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(pe[2 * kt][0], pe[2 * kt][1]);
+      pa[1] = pack_h2(pe[2 * kt][2], pe[2 * kt][3]);
+      pa[2] = pack_h2(pe[2 * kt + 1][0], pe[2 * kt + 1][1]);
+      pa[3] = pack_h2(pe[2 * kt + 1][2], pe[2 * kt + 1][3]);
+      const __half* vr = &vs[kt * 16 + gc][hl * D + gr];       // B[k = key][n = dv] = V[key][dv]
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const uint32_t b0 = pack_2h(vr[n * 8], vr[PITCH + n * 8]);
+        const uint32_t b1 = pack_2h(vr[8 * PITCH + n * 8], vr[9 * PITCH + n * 8]);
+        mma16816(o[n], pa, b0, b1);
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+      const int col = cb + hl * D + n * 8 + gc;
+      if (t0 >= 0) *(__half2*)(out + (row0 + t0) * C + col) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
+      if (t1 >= 0) *(__half2*)(out + (row0 + t1) * C + col) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+    }
+  }
+}
+
+// qkv [B*H*W, 3C] fp16 token-major, qkv_bias [3C] fp32, rel_bias [heads, 49, 49] fp32 -> out [B*H*W, C] fp16 (before proj).
+// head_dim = C / heads must be 32 (Swin-T/S/B); shift = 0 or window/2 = 3.
+extern "C" int isf_swin_window_attention(const void* qkv, const float* qkv_bias, const float* rel_bias, int batch, int H, int W,
+                                         int channels, int heads, int shift, void* out, void* stream) {
+  ISF_CHECK_ARG(qkv && qkv_bias && rel_bias && out && batch >= 1 && H >= 1 && W >= 1 && heads >= 1);
+  ISF_CHECK_ARG(shift >= 0 && shift < SWIN_WS);
+  if (channels != heads * 32 || (heads % 3 != 0)) {
+    isf_set_error("swin_window_attention: built for head_dim 32 and 3k heads (Swin-T/S: 3, 6, 12, 24)");
+    return ISF_ERR_UNSUPPORTED;
+  }
+  const SwinGeom g = swin_geom(H, W, shift);
+  const float scaling = 1.0f / sqrtf(32.f);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = batch * g.nwh * g.nww;
+  if (heads % 6 == 0) {
+    swin_window_attention_kernel<6><<<dim3(blocks, heads / 6), 6 * 32, 0, st>>>((const __half*)qkv, qkv_bias, rel_bias, g, channels,
+                                                                                scaling, (__half*)out);
+  } else {
+    swin_window_attention_kernel<3><<<dim3(blocks, heads / 3), 3 * 32, 0, st>>>((const __half*)qkv, qkv_bias, rel_bias, g, channels,
+                                                                                scaling, (__half*)out);
+  }
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ================================================================================================
 // heat-map NMS + top-K
 // ================================================================================================
 __global__ void __launch_bounds__(256) heatmap_nms_kernel(const float* __restrict__ logits, int C, int H, int W,

@@ -8,8 +8,14 @@ Where the ~218 GFLOP of a 6-camera frame go: qkv / proj / FFN / patch-merging li
 `isf_gemm_f16` (bias, GELU and the FFN's residual fused in the epilogue; the 4x4 patch embedding is a GEMM over the
 unfolded 48-value patches).  LayerNorm, the window partition / cyclic shift glue and the 49-token attention core
 (`F.scaled_dot_product_attention` with relative-position bias + shift mask as an additive mask, cached per resolution)
-are torch ops for now — a 7x7-window kernel in the style of `window_attention_kernel` is the next step for this row.
+are torch ops by default; `ISF_SWIN_ATTN=own` replaces the whole pad / roll / partition / attention / reverse sequence by
+`isf_swin_window_attention` (csrc/fusion.cu: the mma.sync tile code of the validated SST `window_attention_kernel`, with the
+reference's padding, cyclic shift, region mask and crop as closed forms of (window, slot) — checked on the host against the
+reference's index sequence), which also lets the `proj` GEMM add the residual in its epilogue.
 Eval mode only (DropPath / dropout are the identity); activations are fp16 token matrices [B, L, C]."""
+import ctypes
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -18,6 +24,11 @@ from . import _lib as L
 from .fusion_encoder import _Packable
 from .gemm import gemm, pack_weight
 from .registry import BACKBONES
+
+
+# opt-in: the library's shifted-window attention kernel (csrc/fusion.cu swin_window_attention_kernel) instead of the torch
+# pad / roll / partition / SDPA / reverse sequence; with it a block is LN -> GEMM -> kernel -> GEMM(+residual) -> LN -> 2 GEMMs
+OWN_WINDOW_ATTENTION = os.environ.get('ISF_SWIN_ATTN') == 'own'
 
 
 class _Lin:
@@ -176,6 +187,16 @@ class SwinTransformer(_Packable):
         b, l, c = x.shape
         h, w = hw
         ws, shift, heads = self.window_size, blk.attn.shift, blk.attn.w_msa.num_heads
+        if OWN_WINDOW_ATTENTION and ws == 7 and c == heads * 32 and heads % 3 == 0 and x.dtype == torch.float16:
+            y = F.layer_norm(x, (c,), blk.norm1.weight.to(x.dtype), blk.norm1.bias.to(x.dtype), blk.norm1.eps).view(b * l, c)
+            qkv = pk['qkv'](y.contiguous())                                            # token-major [B*L, 3C]
+            att = torch.empty((b * l, c), dtype=torch.float16, device=x.device)
+            L.check(L.lib().isf_swin_window_attention(L.ptr(qkv), L.ptr(pk['qkv'].b), L.ptr(pk['bias']), b, h, w, c, heads, shift,
+                                                      L.ptr(att), L.stream()))
+            x = pk['proj'](att, residual=x.reshape(b * l, c).contiguous()).view(b, l, c)   # + identity in the epilogue
+            y = F.layer_norm(x, (c,), blk.norm2.weight.to(x.dtype), blk.norm2.bias.to(x.dtype), blk.norm2.eps).view(b * l, c)
+            hid = pk['fc1'](y, act='gelu')
+            return pk['fc2'](hid, residual=x.view(b * l, c).contiguous()).view(b, l, c)
         y = F.layer_norm(x, (c,), blk.norm1.weight.to(x.dtype), blk.norm1.bias.to(x.dtype), blk.norm1.eps).view(b, h, w, c)
         y = F.pad(y, (0, 0, 0, (-w) % ws, 0, (-h) % ws))
         hp, wp = y.shape[1], y.shape[2]

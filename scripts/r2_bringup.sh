@@ -16,6 +16,8 @@ step "CUDA path directly against the reference-run fixtures (small grids, head, 
 timeout 400 python -m pytest tests/test_reference_fixtures_gpu.py -q -m gpu    >> $LOG 2>&1
 step "head with the own split-K attention kernel"
 ISF_HEAD_ATTN=own timeout 300 python -m pytest tests/test_reference_fixtures_gpu.py -q -m gpu -k "head or detector" >> $LOG 2>&1
+step "Swin with the own shifted-window attention kernel"
+timeout 300 python -m pytest tests/test_reference_fixtures_gpu.py -q -m gpu -k "swin" >> $LOG 2>&1
 step "configs[4] geometry (0.05 m voxels, 256x256 BEV)"
 timeout 300 python -m pytest tests/test_config5_gpu.py -x -q -m gpu            >> $LOG 2>&1
 step "own dense 3x3 convs on the implicit-GEMM kernel"

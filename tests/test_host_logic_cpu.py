@@ -240,3 +240,36 @@ def test_split_k_attention_algebra():
     den = sum(l * w[:, i:i + 1] for i, l in enumerate(ls))
     want = torch.softmax((q @ k.t()) * d ** -0.5, -1) @ v
     assert torch.allclose(num / den, want, atol=1e-5)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize('h,w,shift', [(16, 24, 0), (16, 24, 3), (7, 7, 3), (24, 66, 3), (5, 9, 3), (14, 14, 0), (96, 264, 3)])
+def test_swin_window_closed_form_equals_pad_roll_partition(h, w, shift):
+    """swin_token (csrc/fusion.cu, compiled for the host through isf_debug_swin_window_map): the (window, slot) -> token map
+    and the region ids of the shift mask == the reference's F.pad / torch.roll / window_partition / img_mask sequence
+    (swin.py:206-247)."""
+    import ctypes
+    import numpy as np
+    from isfusion_b200 import _lib as L
+    ws = 7
+    hp, wp = (h + ws - 1) // ws * ws, (w + ws - 1) // ws * ws
+    nw = (hp // ws) * (wp // ws)
+    tok = np.full(nw * 49, -9, np.int32)
+    reg = np.full(nw * 49, -9, np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.check(L.lib().isf_debug_swin_window_map(h, w, shift, p(tok), p(reg)))
+    idx = torch.arange(h * w).view(1, h, w, 1)
+    idx = F.pad(idx, (0, 0, 0, wp - w, 0, hp - h), value=-1)
+    region = torch.zeros(1, hp, wp, 1)
+    if shift > 0:
+        idx = torch.roll(idx, shifts=(-shift, -shift), dims=(1, 2))
+        cnt = 0
+        for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+                region[:, hs, wsl, :] = cnt
+                cnt += 1
+    part = lambda t: t.view(1, hp // ws, ws, wp // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1)
+    assert np.array_equal(tok, part(idx).numpy().astype(np.int32))
+    assert np.array_equal(reg, part(region).numpy().astype(np.int32))

@@ -237,3 +237,23 @@ def test_query_scene_attention_kernel_against_sdpa(nq, nk):
         H.OWN_ATTENTION = False
     assert got.shape == want.shape == (b, nq, c)
     assert ((got - want).norm() / want.norm()).item() < 3e-3
+
+
+def test_swin_own_window_attention_against_torch_path_and_reference():
+    """ISF_SWIN_ATTN=own: the shifted-window attention kernel (closed-form padding / roll / mask / crop) against the torch
+    glue + SDPA path of the same module, and both against the reference run."""
+    import isfusion_b200.img_backbone as B
+    g = _g('ref_swin.npz')
+    net = gc.fill_state(B.SwinTransformer(**gc.swin_cfg()), 9).cuda().eval()
+    x = gc.swin_input().cuda()
+    try:
+        B.OWN_WINDOW_ATTENTION = False
+        ref = [o.float() for o in net(x)]
+        B.OWN_WINDOW_ATTENTION = True
+        out = [o.float() for o in net(x)]
+        torch.cuda.synchronize()
+    finally:
+        B.OWN_WINDOW_ATTENTION = False
+    for i, (a, r) in enumerate(zip(out, ref)):
+        assert ((a - r).norm() / r.norm()).item() < 5e-3, i
+        assert _rel(a, g['out%d' % i]) < 2e-2, i
