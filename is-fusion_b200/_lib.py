@@ -53,11 +53,16 @@ def host_i32(vals):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
 
 
+def is_device(t):
+    """True for a CUDA tensor (the only kind the library takes)."""
+    return t.is_cuda
+
+
 def require_cuda(*tensors):
     for t in tensors:
         if t is None:
             continue
-        if not t.is_cuda:
+        if not is_device(t):
             raise IsfError('expected a CUDA tensor (the product path has no CPU fallback)')
         if not t.is_contiguous():
             raise IsfError('expected a contiguous tensor')

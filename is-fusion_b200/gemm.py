@@ -25,7 +25,7 @@ def gemm(a, w_packed, k=None, scale=None, shift=None, residual=None, act=None, l
          out_rows=None, ldo=None):
     """out = epi(a[M,K] @ w[N,K]^T): y = acc*scale + shift (+ residual) -> LayerNorm(gamma,beta,eps) -> act."""
     L.require_cuda(a, w_packed, scale, shift, residual)
-    if out is not None and (not out.is_cuda or out.stride(-1) != 1):
+    if out is not None and (not L.is_device(out) or out.stride(-1) != 1):
         raise L.IsfError('gemm: out must be a CUDA tensor with unit column stride')
     if a.dtype != torch.float16 or w_packed.dtype != torch.float16:
         raise L.IsfError('gemm: fp16 operands expected')

@@ -8,6 +8,7 @@ import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, 'golden'))
+sys.path.insert(0, HERE)
 import golden_common as gc  # noqa: E402
 
 from oracle import fusion_ops  # noqa: E402
@@ -273,3 +274,32 @@ def test_swin_window_closed_form_equals_pad_roll_partition(h, w, shift):
     part = lambda t: t.view(1, hp // ws, ws, wp // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1)
     assert np.array_equal(tok, part(idx).numpy().astype(np.int32))
     assert np.array_equal(reg, part(region).numpy().astype(np.int32))
+
+
+def test_fusion_encoder_host_logic_against_the_reference_run(monkeypatch):
+    """The product ISFusionEncoder / SSTInputLayerV2 / SSTv2 / SECONDV2 / SECONDFPN Python code, unmodified, on the CPU
+    against a software stand-in of the C-ABI library (tests/abi_emulator.py: every entry point restated in torch from
+    include/isfusion_b200.h) — weight packing, BN folding, channels-last layouts, token order, positional tables, the
+    transposed-kernel trick for the [X,Y]-frame branches, epilogue arguments, the FPN's row scatter — against the
+    reference module's run (ref_fusion.npz).  fp16 storage like the product: tolerances of the GPU parity tests."""
+    import numpy as np
+    import abi_emulator
+    from isfusion_b200.fusion_encoder import ISFusionEncoder, SECONDFPN, SECONDV2
+    abi_emulator.install(monkeypatch)
+    g = np.load(os.path.join(HERE, 'golden', 'ref_fusion.npz'))
+    enc = gc.fill_state(ISFusionEncoder(**gc.fusion_cfg()), 1).eval()
+    bb = gc.fill_state(SECONDV2(**gc.backbone_cfg()), 2).eval()
+    fpn = gc.fill_state(SECONDFPN(in_channels=[128, 256], out_channels=[256, 256], upsample_strides=[1, 2],
+                                  norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), upsample_cfg=dict(type='deconv', bias=False),
+                                  use_conv_for_no_stride=True), 3).eval()
+    inp = gc.fusion_inputs()
+    pm = dict(pillars=inp['pillars'], pillars_num_points=None, pillar_coors=inp['pillar_coors'], pts=None, pillar_size=None)
+    feats, hm = enc(inp['img_feats'], inp['lidar_feats'], 2, pts_metas=pm, img_metas=inp['img_metas'], pts_backbone=bb,
+                    lidar2img=inp['lidar2img'], img_aug_matrix=inp['img_aug_matrix'], lidar_aug_matrix=inp['lidar_aug_matrix'])
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    assert tuple(feats[0].shape) == g['feat0'].shape and tuple(feats[1].shape) == g['feat1'].shape
+    assert rel(hm.float().numpy(), g['heatmap']) < 5e-3
+    # fp16 storage through ~40 layers with these gain-1.5 synthetic weights: 1.0e-2 / 1.5e-2 (a logic error would be O(1))
+    assert rel(feats[0].float().numpy(), g['feat0']) < 3e-2 and rel(feats[1].float().numpy(), g['feat1']) < 3e-2
+    neck = fpn(feats)[0]
+    assert rel(neck.float().numpy()[:, ::8], g['neck_c8']) < 3e-2

@@ -72,9 +72,10 @@ def test_fusion_encoder_against_reference_run():
                     lidar_aug_matrix=inp['lidar_aug_matrix'])
     assert tuple(feats[0].shape) == g['feat0'].shape and tuple(feats[1].shape) == g['feat1'].shape
     assert _rel(hm, g['heatmap']) < 5e-3
-    assert _rel(feats[0], g['feat0']) < 1e-2 and _rel(feats[1], g['feat1']) < 1e-2
+    # the CPU emulation of the product's fp16 storage alone gives 1.0e-2 / 1.5e-2 on this fixture (test_host_logic_cpu.py)
+    assert _rel(feats[0], g['feat0']) < 3e-2 and _rel(feats[1], g['feat1']) < 3e-2
     neck = fpn(feats)[0]
-    assert _rel(neck[:, ::8], g['neck_c8']) < 1e-2
+    assert _rel(neck[:, ::8], g['neck_c8']) < 3e-2
 
 
 def test_transfusion_head_against_reference_run():
