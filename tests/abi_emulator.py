@@ -5,7 +5,8 @@ are torch statements of what each entry point computes according to include/isfu
 tensor itself over (instead of its device address) and neutralises the CUDA-only plumbing (streams, workspaces, the
 `is_cuda` checks, cuDNN's fused conv).  The product's Python modules then run UNMODIFIED on the CPU: packing, layouts,
 token orders, the transposed-kernel trick, epilogue arguments, row scatters ... everything except the kernels themselves,
-which the GPU suite covers.  Only the entry points of the fusion encoder / SECONDV2 / SECONDFPN path are emulated.
+which the GPU suite covers.  Emulated: the entry points of the fusion encoder / SECONDV2 / SECONDFPN path and of the sparse
+encoder with bitmap-rank rulebooks (incl. the opt-in tile order).
 """
 import ctypes
 
@@ -21,7 +22,7 @@ def _set_size(byref_obj, n):
     byref_obj._obj.value = n
 
 
-class FakeLib:
+class _FusionLib:
     # ------------------------------------------------------------------ plumbing
     def isf_last_error(self):
         return b'(emulator)'
@@ -154,6 +155,163 @@ class FakeLib:
         return 0
 
 
+# ---------------------------------------------------------------------- sparse convolution entry points
+def _ints(a, n=3):
+    return [int(a[i]) for i in range(n)]
+
+
+def _lin(idx, shape):
+    idx = idx.long()
+    return ((idx[:, 0] * shape[0] + idx[:, 1]) * shape[1] + idx[:, 2]) * shape[2] + idx[:, 3]
+
+
+class SparseMixin:
+    """bitmap-rank rulebooks (sorted tensors), tile order, implicit GEMM, dense().  The bitmap / prefix arrays are opaque to
+    the host code, so the emulator keeps the coordinate set they stand for in a side table keyed by the `bits` tensor."""
+
+    def _maps(self):
+        if not hasattr(self, '_map'):
+            self._map = {}
+        return self._map
+
+    def isf_bitmap_words(self, shape, batch):
+        s = _ints(shape)
+        return (int(batch) * s[0] * s[1] * s[2] + 31) // 32
+
+    def isf_bitmap_workspace_size(self, words, out):
+        _set_size(out, 1024)
+        return 0
+
+    def isf_bitmap_build(self, indices, v, v_dev, shape, batch, bits, prefix, ws, ws_bytes, stream):
+        n = int(v_dev.item()) if v_dev is not None else v
+        self._maps()[bits.data_ptr()] = (indices[:n].clone(), _ints(shape))
+        return 0
+
+    def isf_spconv_out_shape(self, in_shape, ks, st, pd, dl, out_shape):
+        i, k, s, p, d = _ints(in_shape), _ints(ks), _ints(st), _ints(pd), _ints(dl)
+        for a in range(3):
+            out_shape[a] = (i[a] + 2 * p[a] - d[a] * (k[a] - 1) - 1) // s[a] + 1
+        return 0
+
+    def isf_bitmap_out_sites(self, in_indices, v_in, v_in_dev, in_shape, batch, ks, st, pd, dl, out_bits, out_prefix, out_indices,
+                             out_cap, num_out_dev, ws, ws_bytes, stream):
+        from oracle import spconv_ops as so
+        n = int(v_in_dev.item()) if v_in_dev is not None else v_in
+        oi, oshape, _ = so.get_indice_pairs(in_indices[:n], batch, _ints(in_shape), _ints(ks), _ints(st), _ints(pd), _ints(dl), False)
+        cnt = min(oi.shape[0], out_cap)
+        out_indices[:cnt] = oi[:cnt]
+        num_out_dev[0] = cnt
+        self._maps()[out_bits.data_ptr()] = (oi[:cnt].clone(), list(oshape))
+        return 0
+
+    def _neighbours(self, out_indices, n, in_bits, in_shape, ks, st, pd, dl, subm):
+        in_idx, shape = self._maps()[in_bits.data_ptr()]
+        assert shape == _ints(in_shape)
+        ks, st, pd, dl = _ints(ks), ([1, 1, 1] if subm else _ints(st)), None if subm else _ints(pd), _ints(dl)
+        key = _lin(in_idx, shape)
+        assert (key[1:] > key[:-1]).all(), 'bitmap-rank rulebooks need rows in ascending key order'
+        oi = out_indices[:n].long()
+        taps = ks[0] * ks[1] * ks[2]
+        nbr = torch.full((taps, n), -1, dtype=torch.int32)
+        k = 0
+        for kz in range(ks[0]):
+            for ky in range(ks[1]):
+                for kx in range(ks[2]):
+                    kk = torch.tensor([kz, ky, kx])
+                    pad = torch.tensor([(ks[d] // 2) * dl[d] for d in range(3)]) if subm else torch.tensor(pd)
+                    ip = oi[:, 1:] * torch.tensor(st) - pad + kk * torch.tensor(dl)
+                    ok = ((ip >= 0) & (ip < torch.tensor(shape))).all(1)
+                    q = _lin(torch.cat([oi[:, :1], ip.clamp(min=0)], 1), shape)
+                    pos = torch.searchsorted(key, q).clamp(max=max(len(key) - 1, 0))
+                    hit = ok & (key[pos] == q) if len(key) else torch.zeros_like(ok)
+                    nbr[k, hit] = pos[hit].int()
+                    k += 1
+        return nbr
+
+    def isf_spconv_neighbors_bitmap(self, out_indices, v_out, v_dev, in_bits, in_prefix, in_shape, ks, st, pd, dl, subm, nbr,
+                                    nbr_stride, stream):
+        n = int(v_dev.item()) if v_dev is not None else v_out
+        nbr[:, :n] = self._neighbours(out_indices, n, in_bits, in_shape, ks, st, pd, dl, bool(subm))
+        return 0
+
+    def isf_spconv_tile_order_workspace_size(self, v, out):
+        _set_size(out, 1024)
+        return 0
+
+    def _order(self, nbr_valid_rows, chunk_log2, ksize):
+        import tile_occupancy as to
+        return torch.from_numpy(to.tile_order_model((nbr_valid_rows >= 0).numpy(), int(chunk_log2), tuple(_ints(ksize)))).long()
+
+    def isf_spconv_tile_order(self, nbr, nbr_stride, taps, ksize, v, v_dev, chunk_log2, nbr_out, row_perm, ws, ws_bytes, stream):
+        n = min(int(v_dev.item()), v) if v_dev is not None else v
+        perm = self._order(nbr[:, :n], chunk_log2, ksize)
+        nbr_out.fill_(-1)
+        row_perm.fill_(-1)
+        nbr_out[:, :n] = nbr[:, perm]
+        row_perm[:n] = perm.int()
+        return 0
+
+    def isf_spconv_neighbors_bitmap_ordered(self, out_indices, v_out, v_dev, in_bits, in_prefix, in_shape, ks, st, pd, dl, subm,
+                                            chunk_log2, nbr_out, nbr_stride, row_perm, ws, ws_bytes, stream):
+        n = min(int(v_dev.item()), v_out) if v_dev is not None else v_out
+        nbr = self._neighbours(out_indices, n, in_bits, in_shape, ks, st, pd, dl, bool(subm))
+        perm = self._order(nbr, chunk_log2, ks)
+        nbr_out.fill_(-1)
+        row_perm.fill_(-1)
+        nbr_out[:, :n] = nbr[:, perm]
+        row_perm[:n] = perm.int()
+        return 0
+
+    def _implicit(self, feats, cin, w, kpad, cout, nbr, taps, v_out, v_dev, row_perm, scale, shift, residual, relu, out):
+        n = min(int(v_dev.item()), v_out) if v_dev is not None else v_out
+        assert w.shape == (cout, kpad) and kpad >= taps * cin
+        acc = torch.zeros((n, cout))
+        f = feats.float()
+        for k in range(taps):
+            r = nbr[k, :n].long()
+            hit = r >= 0
+            if hit.any():
+                acc[hit] += f[r[hit]] @ w[:, k * cin:(k + 1) * cin].float().t()
+        if scale is not None:
+            acc = acc * scale
+        if shift is not None:
+            acc = acc + shift
+        rows = row_perm[:n].long() if row_perm is not None else torch.arange(n)
+        assert (rows >= 0).all()
+        if residual is not None:
+            acc = acc + residual[rows].float()
+        if relu:
+            acc = torch.relu(acc)
+        out[rows] = acc.to(out.dtype)
+        return 0
+
+    def isf_spconv_implicit_gemm(self, feats, cin, w, kpad, cout, nbr, nbr_stride, taps, v_out, v_dev, scale, shift, residual, ldr,
+                                 relu, out, ldo, stream):
+        return self._implicit(feats, cin, w, kpad, cout, nbr, taps, v_out, v_dev, None, scale, shift, residual, relu, out)
+
+    def isf_spconv_implicit_gemm_ordered(self, feats, cin, w, kpad, cout, nbr, nbr_stride, taps, v_out, v_dev, row_perm, scale, shift,
+                                         residual, ldr, relu, out, ldo, stream):
+        return self._implicit(feats, cin, w, kpad, cout, nbr, taps, v_out, v_dev, row_perm, scale, shift, residual, relu, out)
+
+    def isf_sparse_to_dense(self, feats, indices, v, c, batch, d, h, w, out, stream):
+        out.zero_()
+        i = indices[:v].long()
+        out[i[:, 0], :, i[:, 1], i[:, 2], i[:, 3]] = feats[:v].to(out.dtype)
+        return 0
+
+
+class FakeLib(_FusionLib, SparseMixin):
+    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_version')
+
+    def __init__(self, real=None):
+        self._real = real
+
+    def __getattr__(self, name):           # host-only entry points need no GPU: the real library serves them
+        if name in FakeLib.HOST_ONLY and self.__dict__.get('_real') is not None:
+            return getattr(self._real, name)
+        raise AttributeError('abi_emulator: %s is not emulated' % name)
+
+
 def _conv_cpu(x_nhwc, packed, stride=1, relu=True):
     w, b = packed
     y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).float(), w.float(), b.float(), stride=stride, padding=1)
@@ -164,7 +322,7 @@ def install(monkeypatch):
     """patch isfusion_b200 so that its modules run on CPU tensors against FakeLib; returns the FakeLib."""
     import isfusion_b200._lib as L
     import isfusion_b200.fusion_encoder as FE
-    fake = FakeLib()
+    fake = FakeLib(L.lib())
     monkeypatch.setattr(L, 'lib', lambda: fake)
     monkeypatch.setattr(L, 'ptr', lambda t: t)
     monkeypatch.setattr(L, 'stream', lambda: None)

@@ -303,3 +303,34 @@ def test_fusion_encoder_host_logic_against_the_reference_run(monkeypatch):
     assert rel(feats[0].float().numpy(), g['feat0']) < 3e-2 and rel(feats[1].float().numpy(), g['feat1']) < 3e-2
     neck = fpn(feats)[0]
     assert rel(neck.float().numpy()[:, ::8], g['neck_c8']) < 3e-2
+
+
+def test_sparse_encoder_host_logic_and_tile_order_wiring(monkeypatch):
+    """The product SparseEncoder / SparseBasicBlock / spconv.py Python code, unmodified, on the CPU against the ABI emulator:
+    bitmap-rank rulebooks shared per stage, BN folding into the implicit-GEMM epilogue, residual wiring, dense() — against
+    the reference's run (ref_sparse.npz) — and the opt-in tile order (fused builder and two-call path, global and chunked):
+    regrouped tables + row_perm threaded through every conv must give the default path's output."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests', 'analysis'))
+    import abi_emulator
+    import isfusion_b200.spconv as sp
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    abi_emulator.install(monkeypatch)
+    g = np.load(os.path.join(HERE, 'golden', 'ref_sparse.npz'))
+    net = gc.fill_state(SparseEncoder(**gc.sparse_cfg()), 6).eval()
+    feats, coors = gc.sparse_inputs()
+
+    def run():
+        out, enc, _ = net(feats.half(), coors, 2, sorted_coors=True)
+        return out.float(), [int(e.indices.shape[0]) for e in enc], enc[1].indices.clone()
+    monkeypatch.setattr(sp, 'TILE_ORDER', None)
+    base, counts, idx1 = run()
+    assert counts == g['stage_voxels'].tolist() and np.array_equal(idx1.numpy(), g['stage1_coors'])
+    err = float(np.linalg.norm(base.numpy() - g['out']) / np.linalg.norm(g['out']))
+    assert err < 5e-3, err                                    # 21 stacked fp16 layers
+    for chunk, fused in ((31, True), (31, False), (8, True)):
+        monkeypatch.setattr(sp, 'TILE_ORDER', chunk)
+        monkeypatch.setattr(sp, 'TILE_ORDER_FUSED', fused)
+        out, counts2, _ = run()
+        assert counts2 == counts
+        assert torch.allclose(out, base, atol=1e-3, rtol=1e-3), (chunk, fused, float((out - base).abs().max()))
