@@ -6,7 +6,7 @@ tensor itself over (instead of its device address) and neutralises the CUDA-only
 `is_cuda` checks, cuDNN's fused conv).  The product's Python modules then run UNMODIFIED on the CPU: packing, layouts,
 token orders, the transposed-kernel trick, epilogue arguments, row scatters ... everything except the kernels themselves,
 which the GPU suite covers.  Emulated: the entry points of the fusion encoder / SECONDV2 / SECONDFPN path and of the sparse
-encoder with bitmap-rank rulebooks (incl. the opt-in tile order).
+encoder with bitmap-rank rulebooks (incl. the opt-in tile order), voxelization and the two-call DynamicVFE.
 """
 import ctypes
 
@@ -67,7 +67,9 @@ class _FusionLib:
     # ------------------------------------------------------------------ isf_cam2bev
     def isf_cam2bev(self, pillars, num_pillars, num_dev, ppp, nfeat, coors, cdim, b_override, feat, proj, bs, ncam, fh, fw, c,
                     img_w, img_h, gh, gw, out, ldo, ch_off, stream):
-        assert num_dev is None and out.shape[-1] == ldo and feat.shape == (bs, ncam, fh, fw, c)
+        assert out.shape[-1] == ldo and feat.shape == (bs, ncam, fh, fw, c)
+        if num_dev is not None:                                          # capacity mode: device-side pillar count
+            num_pillars = min(int(num_dev.item()), num_pillars)
         img_w, img_h = _val(img_w), _val(img_h)
         pts = pillars[:num_pillars, :, :3].float()
         co = coors[:num_pillars].long()
@@ -300,7 +302,87 @@ class SparseMixin:
         return 0
 
 
-class FakeLib(_FusionLib, SparseMixin):
+class VoxelMixin:
+    """voxelization, the two-call DynamicVFE (group / compute), the BEV view of the sparse output."""
+
+    def isf_dynamic_voxelize(self, points, n, nfeat, voxel_size, coors_range, coors, cpu_semantics, stream):
+        from oracle import voxel_ops
+        vs, cr = [float(voxel_size[i]) for i in range(3)], [float(coors_range[i]) for i in range(6)]
+        coors[:n] = voxel_ops.dynamic_voxelize(points[:n], vs, cr, mode='cpu' if cpu_semantics else 'cuda')
+        return 0
+
+    def isf_hard_voxelize_workspace_size(self, n, out):
+        _set_size(out, 1024)
+        return 0
+
+    def isf_hard_voxelize(self, points, n, nfeat, voxel_size, coors_range, max_points, max_voxels, voxels, coors, npv, cnt, ws,
+                          ws_bytes, stream):
+        from oracle import voxel_ops
+        vs, cr = [float(voxel_size[i]) for i in range(3)], [float(coors_range[i]) for i in range(6)]
+        v, c, k = voxel_ops.hard_voxelize(points[:n], vs, cr, max_points, max_voxels)
+        m = v.shape[0]
+        voxels[:m], coors[:m], npv[:m] = v, c, k
+        cnt[0] = m
+        return 0
+
+    def isf_dynamic_vfe_workspace_size(self, n, out):
+        _set_size(out, 1024)
+        return 0
+
+    isf_dynamic_vfe_tc_workspace_size = isf_dynamic_vfe_workspace_size
+
+    def isf_dynamic_vfe_group(self, coors, n, dims, vcoors, nv, ws, ws_bytes, stream):
+        c = coors[:n].long()
+        d = [int(dims[i]) for i in range(4)]
+        assert ((c >= 0) & (c < torch.tensor(d))).all(), 'DynamicVFE takes in-range points (SURVEY Appendix C #5)'
+        key = ((c[:, 0] * d[1] + c[:, 1]) * d[2] + c[:, 2]) * d[3] + c[:, 3]
+        uniq, inv = torch.unique(key, return_inverse=True)                    # ascending = sorted-unique (b,z,y,x) order
+        v = uniq.numel()
+        vc = torch.stack([uniq // (d[1] * d[2] * d[3]), (uniq // (d[2] * d[3])) % d[1], (uniq // d[3]) % d[2], uniq % d[3]], 1)
+        vcoors[:v] = vc.int()
+        nv[0] = v
+        if not hasattr(self, '_groups'):
+            self._groups = {}
+        self._groups[ws.data_ptr()] = (inv, vc, v)
+        return 0
+
+    def _vfe(self, points, n, voxel_size, offsets, w1, s1, b1, w2, s2, b2, ws):
+        inv, vc, v = self._groups[ws.data_ptr()]
+        p = points[:n].float()
+        c = p.shape[1]
+        seg_mean = torch.zeros(v, 3).index_add_(0, inv, p[:, :3]) / torch.bincount(inv, minlength=v)[:, None]
+        vs, off = torch.tensor([float(voxel_size[i]) for i in range(3)]), torch.tensor([float(offsets[i]) for i in range(3)])
+        centre = torch.stack([vc[inv, 3] * vs[0] + off[0], vc[inv, 2] * vs[1] + off[1], vc[inv, 1] * vs[2] + off[2]], 1)
+        f = torch.cat([p[:, :c], p[:, :3] - seg_mean[inv], p[:, :3] - centre], 1)                  # [N, 11]
+        h1 = torch.relu((f @ w1.float().t()) * s1 + b1)
+        idx = inv[:, None].expand(-1, h1.shape[1])
+        vmax = torch.full((v, h1.shape[1]), float('-inf')).scatter_reduce(0, idx, h1, 'amax')
+        h2 = torch.relu((torch.cat([h1, vmax[inv]], 1) @ w2.float().t()) * s2 + b2)
+        return torch.full((v, h2.shape[1]), float('-inf')).scatter_reduce(0, inv[:, None].expand(-1, h2.shape[1]), h2, 'amax'), v
+
+    def isf_dynamic_vfe_compute_tc(self, points, n, nfeat, dims, voxel_size, offsets, w1, s1, b1, w2a, w2b, s2, b2, feats, ws,
+                                   ws_bytes, stream):
+        out, v = self._vfe(points, n, voxel_size, offsets, w1, s1, b1, torch.cat([w2a.float()[:, :64], w2b.float()[:, :64]], 1),
+                           s2, b2, ws)
+        feats[:v] = out.to(feats.dtype)
+        return 0
+
+    def isf_dynamic_vfe_compute(self, points, n, nfeat, dims, voxel_size, offsets, w1, s1, b1, w2, s2, b2, in_ch, feat_ch, f32, f16,
+                                ws, ws_bytes, stream):
+        out, v = self._vfe(points, n, voxel_size, offsets, w1, s1, b1, w2, s2, b2, ws)
+        dst = f16 if f16 is not None else f32
+        dst[:v] = out.to(dst.dtype)
+        return 0
+
+    def isf_sparse_to_bev_nhwc(self, feats, indices, v, v_dev, c, d, h, w, out, ldo, ch_offset, stream):
+        n = min(int(v_dev.item()), v) if v_dev is not None else v
+        i = indices[:n].long()
+        ch = ch_offset + torch.arange(c)[None, :] * d + i[:, 1:2]                                 # channel c*D + z
+        out[i[:, 0:1].expand(-1, c), i[:, 2:3].expand(-1, c), i[:, 3:4].expand(-1, c), ch] = feats[:n].to(out.dtype)
+        return 0
+
+
+class FakeLib(_FusionLib, SparseMixin, VoxelMixin):
     HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_version')
 
     def __init__(self, real=None):

@@ -334,3 +334,33 @@ def test_sparse_encoder_host_logic_and_tile_order_wiring(monkeypatch):
         out, counts2, _ = run()
         assert counts2 == counts
         assert torch.allclose(out, base, atol=1e-3, rtol=1e-3), (chunk, fused, float((out - base).abs().max()))
+
+
+def test_whole_detector_host_logic_against_the_oracle(monkeypatch):
+    """`ISFusionDetector.extract_pts_feat` (exact mode) — voxelize, DynamicVFE group/compute, SparseEncoder with bitmap
+    rulebooks, pillarize, camera->BEV, the fused 768-channel buffer fed straight from the sparse output, fusion encoder,
+    SECONDV2 — the product's Python code unmodified on the CPU against the ABI emulator, versus the oracle neck with the
+    same weights (what __graft_entry__.smoke() checks on the GPU)."""
+    import abi_emulator
+    import synth
+    from __graft_entry__ import make_pair
+    abi_emulator.install(monkeypatch)
+    ref, net = make_pair(0)
+    net = net.eval()
+    pts = [synth.make_points(3000, 'S', 0), synth.make_points(2500, 'S', 1)]
+    l2i, aug, laug = synth.make_calib(2)
+    feats = synth.make_img_feats(2)
+    metas = [dict(input_shape=(256, 704))] * 2
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    gf, ghm = net(pts, feats, metas, **kw)
+    rf, rhm = ref(pts, feats, metas, **kw)
+    assert tuple(gf[0].shape) == tuple(rf[0].shape) == (2, 128, 180, 180) and tuple(gf[1].shape) == tuple(rf[1].shape)
+    for a, b in zip(list(gf) + [ghm], list(rf) + [rhm]):
+        r = ((a.float() - b).norm() / b.norm()).item()
+        assert r < 1e-2, r
+    # capacity mode (device-side counts, capacity-sized buffers: the path the CUDA graph captures) gives the same maps
+    import isfusion_b200.spconv as sp
+    sf, shm = net(pts, feats, metas, nosync=True, **kw)
+    assert not sp.check_overflow()
+    for a, b in zip(list(sf) + [shm], list(gf) + [ghm]):
+        assert torch.allclose(a.float(), b.float(), atol=2e-3, rtol=2e-3), float((a.float() - b.float()).abs().max())
