@@ -9,9 +9,14 @@ which the GPU suite covers.  Emulated: the entry points of the fusion encoder / 
 encoder with bitmap-rank rulebooks (incl. the opt-in tile order), voxelization and the two-call DynamicVFE.
 """
 import ctypes
+import os
+import sys
 
 import torch
 import torch.nn.functional as F
+
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'analysis'))      # tile_occupancy (order model)
 
 
 def _val(x):
@@ -268,7 +273,7 @@ class SparseMixin:
         n = min(int(v_dev.item()), v_out) if v_dev is not None else v_out
         assert w.shape == (cout, kpad) and kpad >= taps * cin
         acc = torch.zeros((n, cout))
-        f = feats.float()
+        f = feats.reshape(-1, cin).float()               # the kernel sees a flat matrix of cin-wide rows
         for k in range(taps):
             r = nbr[k, :n].long()
             hit = r >= 0
@@ -400,10 +405,15 @@ def _conv_cpu(x_nhwc, packed, stride=1, relu=True):
     return (torch.relu(y) if relu else y).permute(0, 2, 3, 1).half().contiguous()
 
 
+ORIGINAL_CONV = None      # fusion_encoder._conv as shipped (set by install; lets a test re-enable it for the own-conv path)
+
+
 def install(monkeypatch):
     """patch isfusion_b200 so that its modules run on CPU tensors against FakeLib; returns the FakeLib."""
     import isfusion_b200._lib as L
     import isfusion_b200.fusion_encoder as FE
+    global ORIGINAL_CONV
+    ORIGINAL_CONV = FE._conv
     fake = FakeLib(L.lib())
     monkeypatch.setattr(L, 'lib', lambda: fake)
     monkeypatch.setattr(L, 'ptr', lambda t: t)

@@ -364,3 +364,19 @@ def test_whole_detector_host_logic_against_the_oracle(monkeypatch):
     assert not sp.check_overflow()
     for a, b in zip(list(sf) + [shm], list(gf) + [ghm]):
         assert torch.allclose(a.float(), b.float(), atol=2e-3, rtol=2e-3), float((a.float() - b.float()).abs().max())
+    # opt-in paths wired through the whole detector: neighbour-pattern tile order (capacity mode: the order is computed
+    # under a device-side row count) and the dense 3x3 convs on the implicit-GEMM entry point
+    import isfusion_b200.fusion_encoder as FE
+    from isfusion_b200 import conv2d
+    monkeypatch.setattr(sp, 'TILE_ORDER', 31)
+    tf, thm = net(pts, feats, metas, nosync=True, **kw)
+    assert not sp.check_overflow()
+    for a, b in zip(list(tf) + [thm], list(gf) + [ghm]):
+        assert torch.allclose(a.float(), b.float(), atol=2e-3, rtol=2e-3), float((a.float() - b.float()).abs().max())
+    monkeypatch.setattr(sp, 'TILE_ORDER', None)
+    monkeypatch.setattr(FE, '_conv', abi_emulator.ORIGINAL_CONV)
+    monkeypatch.setattr(conv2d, 'ENABLED', True)
+    cf, chm = net(pts, feats, metas, **kw)
+    for a, b in zip(list(cf) + [chm], list(gf) + [ghm]):
+        r = ((a.float() - b.float()).norm() / b.float().norm()).item()
+        assert r < 3e-3, r
