@@ -216,7 +216,7 @@ class TransFusionHeadV2(_Packable):
         """inputs [B, in_channels, X, Y] (any memory format; channels-last fp16 is consumed without a copy)."""
         if self.training:
             raise L.IsfError('TransFusionHeadV2: eval-mode CUDA path only')
-        if not inputs.is_cuda:
+        if not L.is_device(inputs):
             raise L.IsfError('expected a CUDA tensor (the product path has no CPU fallback)')
         dev = inputs.device
         pk = self._pack(dev)

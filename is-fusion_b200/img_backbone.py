@@ -221,7 +221,7 @@ class SwinTransformer(_Packable):
         """x [B*views, 3, H, W] -> list of [B*views, C_i, H_i, W_i] fp16 maps (channels-last memory) for `out_indices`."""
         if self.training:
             raise L.IsfError('SwinTransformer: eval-mode CUDA path only')
-        if not x.is_cuda:
+        if not L.is_device(x):
             raise L.IsfError('expected a CUDA tensor (the product path has no CPU fallback)')
         pk = self._pack()
         pe = self.patch_embed

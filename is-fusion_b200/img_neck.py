@@ -62,7 +62,7 @@ class GeneralizedLSSFPN(_Packable):
         pk = self._pack()
         lat = []
         for t in inputs:
-            if not t.is_cuda:
+            if not L.is_device(t):
                 raise L.IsfError('expected a CUDA tensor (the product path has no CPU fallback)')
             lat.append(t.half().contiguous(memory_format=torch.channels_last))
         for i in range(len(lat) - 2, -1, -1):

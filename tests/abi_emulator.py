@@ -387,7 +387,65 @@ class VoxelMixin:
         return 0
 
 
-class FakeLib(_FusionLib, SparseMixin, VoxelMixin):
+class RowsAroundMixin:
+    """entry points of the rows around the path: head (top-K with class, query -> scene attention) and Swin window attention."""
+
+    def isf_heatmap_topk_class(self, logits, batch, classes, h, w, plain_from, k, top_idx, top_score, ws, ws_bytes, stream):
+        lg = logits.float().view(batch, classes, h, w)
+        keep = torch.zeros_like(lg, dtype=torch.bool)
+        keep[:, :, 1:-1, 1:-1] = lg[:, :, 1:-1, 1:-1] == F.max_pool2d(lg, 3, 1, 0)
+        keep[:, plain_from:] = True
+        score = torch.where(keep, lg.sigmoid(), torch.zeros_like(lg)).view(batch, -1)
+        top_idx.copy_(torch.argsort(score, dim=1, descending=True, stable=True)[:, :k].int())
+        return 0
+
+    def isf_query_scene_attention_workspace_size(self, batch, queries, nk, channels, heads, out):
+        _set_size(out, 1024)
+        return 0
+
+    def isf_query_scene_attention(self, q, kv, batch, queries, nk, channels, heads, out, ws, ws_bytes, stream):
+        assert q.shape == (batch, queries, channels) and kv.shape == (batch, nk, 2 * channels)
+        d = channels // heads
+        qq = q.float().view(batch, queries, heads, d).transpose(1, 2)
+        kk = kv[..., :channels].float().view(batch, nk, heads, d).transpose(1, 2)
+        vv = kv[..., channels:].float().view(batch, nk, heads, d).transpose(1, 2)
+        out.copy_(F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(batch, queries, channels).to(out.dtype))
+        return 0
+
+    def isf_swin_window_attention(self, qkv, qkv_bias, rel_bias, batch, h, w, c, heads, shift, out, stream):
+        """the reference's sequence (swin.py:206-283) on the token-major qkv matrix; padding positions carry the bias."""
+        ws, d = 7, c // heads
+        assert qkv.shape == (batch * h * w, 3 * c) and rel_bias.shape == (heads, 49, 49) and qkv_bias.shape == (3 * c,)
+        x = qkv.float().view(batch, h, w, 3 * c)
+        hp, wp = (h + ws - 1) // ws * ws, (w + ws - 1) // ws * ws
+        full = qkv_bias.float().view(1, 1, 1, -1).expand(batch, hp, wp, -1).clone()
+        full[:, :h, :w] = x
+        mask = None
+        if shift > 0:
+            full = torch.roll(full, shifts=(-shift, -shift), dims=(1, 2))
+            region = torch.zeros(hp, wp)
+            cnt = 0
+            for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+                for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+                    region[hs, wsl] = cnt
+                    cnt += 1
+            mw = region.view(hp // ws, ws, wp // ws, ws).permute(0, 2, 1, 3).reshape(-1, 49)
+            diff = mw.unsqueeze(1) - mw.unsqueeze(2)
+            mask = torch.where(diff != 0, torch.tensor(-100.0), torch.tensor(0.0))[None, :, None]          # [1, nW, 1, N, N]
+        win = full.view(batch, hp // ws, ws, wp // ws, ws, 3 * c).permute(0, 1, 3, 2, 4, 5).reshape(batch, -1, 49, 3, heads, d)
+        q, k, v = (win[:, :, :, i].permute(0, 1, 3, 2, 4) for i in range(3))                                 # [B, nW, heads, N, d]
+        m = rel_bias.float()[None, None]
+        if mask is not None:
+            m = m + mask
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=m.expand(batch, -1, -1, -1, -1))
+        o = o.permute(0, 1, 3, 2, 4).reshape(batch, hp // ws, wp // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(batch, hp, wp, c)
+        if shift > 0:
+            o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+        out.copy_(o[:, :h, :w].reshape(batch * h * w, c).to(out.dtype))
+        return 0
+
+
+class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):
     HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_version')
 
     def __init__(self, real=None):
