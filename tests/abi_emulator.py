@@ -19,6 +19,34 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'analysis'))      # tile_occupancy (order model)
 
 
+def _header_params():
+    """{entry point: [C type of every parameter]} parsed from include/isfusion_b200.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r'/\*.*?\*/', '', open(os.path.join(root, 'include', 'isfusion_b200.h')).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r'\b(?:int|long long|unsigned long long|const char\*)\s+(isf_\w+)\s*\(([^;]*?)\)\s*;', hdr, flags=re.S):
+        params = [p.strip() for p in m.group(2).split(',')] if m.group(2).strip() not in ('', 'void') else []
+        out[m.group(1)] = [re.sub(r'\s*\w+$', '', p) for p in params]          # drop the parameter name
+    return out
+
+
+def _check_kinds(name, ctypes_of, args):
+    """every argument must be of the KIND the header declares: a pointer gets a tensor / ctypes array / byref / None,
+    an integer an int, a float a (ctypes) float — catches swapped or shifted arguments that ctypes itself would accept."""
+    for i, (ct, a) in enumerate(zip(ctypes_of, args)):
+        is_ptr = '*' in ct
+        ok_ptr = a is None or isinstance(a, (torch.Tensor, ctypes.Array, bytes)) or type(a).__name__ == 'CArgObject' \
+            or isinstance(a, ctypes.c_void_p)
+        if is_ptr:
+            assert ok_ptr, '%s: argument %d (%s) got %r' % (name, i, ct, type(a))
+        elif ct in ('float', 'double'):
+            assert isinstance(a, (float, ctypes.c_float, ctypes.c_double)), '%s: argument %d (%s) got %r' % (name, i, ct, type(a))
+        else:
+            assert isinstance(a, (int, bool, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t)) and not isinstance(a, torch.Tensor), \
+                '%s: argument %d (%s) got %r' % (name, i, ct, type(a))
+
+
 def _val(x):
     return x.value if hasattr(x, 'value') else x
 
@@ -446,10 +474,26 @@ class RowsAroundMixin:
 
 
 class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):
+    _KINDS = None
     HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_version')
 
     def __init__(self, real=None):
         self._real = real
+
+    def __getattribute__(self, name):       # every emulated call is checked against the header's parameter kinds first
+        attr = object.__getattribute__(self, name)
+        if name.startswith('isf_') and callable(attr):
+            kinds = FakeLib._KINDS.get(name) if FakeLib._KINDS is not None else None
+            if FakeLib._KINDS is None:
+                FakeLib._KINDS = _header_params()
+                kinds = FakeLib._KINDS.get(name)
+            if kinds is not None:
+                def checked(*args, _f=attr, _k=kinds, _n=name):
+                    assert len(args) == len(_k), '%s: %d arguments, the header declares %d' % (_n, len(args), len(_k))
+                    _check_kinds(_n, _k, args)
+                    return _f(*args)
+                return checked
+        return attr
 
     def __getattr__(self, name):           # host-only entry points need no GPU: the real library serves them
         if name in FakeLib.HOST_ONLY and self.__dict__.get('_real') is not None:

@@ -84,3 +84,25 @@ def test_new_host_side_entry_points_validate_arguments():
     assert lib.isf_set_option(b'no_such_option', 1) == 1
     # the tile-order entry points refuse bad geometry before touching the device
     assert lib.isf_spconv_tile_order(None, ctypes.c_longlong(128), 27, None, 10, None, 31, None, None, None, ctypes.c_size_t(0), None) == 1
+
+
+def test_emulator_signatures_match_the_header():
+    """ctypes does not check argument counts, so a call site with a missing / extra argument would only show on the GPU.
+    The CPU host-logic tests run the product against tests/abi_emulator.py, whose Python methods DO check arity — provided
+    they have exactly the parameters the header declares.  This test ties the two together."""
+    import inspect
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import abi_emulator
+    hdr = open(os.path.join(ROOT, 'include', 'isfusion_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    decl = {}
+    for m in re.finditer(r'\b(?:int|long long|unsigned long long|const char\*)\s+(isf_\w+)\s*\(([^;]*?)\)\s*;', hdr, flags=re.S):
+        params = m.group(2).strip()
+        decl[m.group(1)] = 0 if params in ('', 'void') else params.count(',') + 1
+    emulated = [n for n in dir(abi_emulator.FakeLib) if n.startswith('isf_')]
+    assert len(emulated) >= 35
+    for name in emulated:
+        assert name in decl, name + ' is emulated but not declared in the header'
+        n_emul = len(inspect.signature(getattr(abi_emulator.FakeLib, name)).parameters) - 1      # minus self
+        assert n_emul == decl[name], (name, n_emul, decl[name])
