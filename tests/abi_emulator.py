@@ -239,12 +239,47 @@ class SparseMixin:
         self._maps()[out_bits.data_ptr()] = (oi[:cnt].clone(), list(oshape))
         return 0
 
-    def _neighbours(self, out_indices, n, in_bits, in_shape, ks, st, pd, dl, subm):
+    # hash-table rulebooks (tensors of unknown row order): the table is opaque too
+    def isf_hash_capacity(self, n):
+        c = 1024
+        while c < 2 * n:
+            c <<= 1
+        return c
+
+    def isf_hash_build(self, indices, v, v_dev, shape, batch, table, capacity, stream):
+        n = int(v_dev.item()) if v_dev is not None else v
+        self._maps()[table.data_ptr()] = (indices[:n].clone(), _ints(shape))
+        return 0
+
+    def isf_spconv_out_indices_workspace_size(self, v_in, kvol, out_cap, out):
+        _set_size(out, 1024)
+        return 0
+
+    def isf_spconv_out_indices(self, in_indices, v_in, v_in_dev, in_shape, batch, ks, st, pd, dl, out_indices, out_cap, num_out_dev,
+                               ws, ws_bytes, stream):
+        from oracle import spconv_ops as so
+        n = int(v_in_dev.item()) if v_in_dev is not None else v_in
+        oi, _, _ = so.get_indice_pairs(in_indices[:n], batch, _ints(in_shape), _ints(ks), _ints(st), _ints(pd), _ints(dl), False)
+        cnt = min(oi.shape[0], out_cap)
+        out_indices[:cnt] = oi[:cnt]
+        num_out_dev[0] = cnt
+        return 0
+
+    def isf_spconv_neighbors(self, out_indices, v_out, v_dev, table, capacity, in_shape, ks, st, pd, dl, subm, nbr, nbr_stride, stream):
+        n = int(v_dev.item()) if v_dev is not None else v_out
+        nbr[:, :n] = self._neighbours(out_indices, n, table, in_shape, ks, st, pd, dl, bool(subm), need_sorted=False)
+        return 0
+
+    def _neighbours(self, out_indices, n, in_bits, in_shape, ks, st, pd, dl, subm, need_sorted=True):
         in_idx, shape = self._maps()[in_bits.data_ptr()]
         assert shape == _ints(in_shape)
         ks, st, pd, dl = _ints(ks), ([1, 1, 1] if subm else _ints(st)), None if subm else _ints(pd), _ints(dl)
         key = _lin(in_idx, shape)
-        assert (key[1:] > key[:-1]).all(), 'bitmap-rank rulebooks need rows in ascending key order'
+        order = torch.arange(len(key))
+        if need_sorted:
+            assert (key[1:] > key[:-1]).all(), 'bitmap-rank rulebooks need rows in ascending key order'
+        else:
+            key, order = torch.sort(key)
         oi = out_indices[:n].long()
         taps = ks[0] * ks[1] * ks[2]
         nbr = torch.full((taps, n), -1, dtype=torch.int32)
@@ -259,7 +294,7 @@ class SparseMixin:
                     q = _lin(torch.cat([oi[:, :1], ip.clamp(min=0)], 1), shape)
                     pos = torch.searchsorted(key, q).clamp(max=max(len(key) - 1, 0))
                     hit = ok & (key[pos] == q) if len(key) else torch.zeros_like(ok)
-                    nbr[k, hit] = pos[hit].int()
+                    nbr[k, hit] = order[pos[hit]].int()
                     k += 1
         return nbr
 
@@ -356,6 +391,30 @@ class VoxelMixin:
         m = v.shape[0]
         voxels[:m], coors[:m], npv[:m] = v, c, k
         cnt[0] = m
+        return 0
+
+    def isf_dynamic_scatter_workspace_size(self, n, out):
+        _set_size(out, 1024)
+        return 0
+
+    def isf_dynamic_point_to_voxel_forward(self, feats, coors, n, c, ndim, dims, reduce_type, reduced, out_coors, coors_map, rcount,
+                                           nv, ws, ws_bytes, stream):
+        from oracle import voxel_ops
+        red, oc, cmap, cnt = voxel_ops.dynamic_scatter(feats[:n], coors[:n], {0: 'sum', 1: 'mean', 2: 'max'}[reduce_type])
+        v = red.shape[0]
+        reduced[:v], out_coors[:v], rcount[:v] = red, oc, cnt
+        coors_map[:n] = cmap
+        nv[0] = v
+        return 0
+
+    def isf_ingroup_indices(self, group_inds, n, key_bits, out_inds, ws, ws_bytes, stream):
+        g = group_inds[:n]
+        order = torch.argsort(g, stable=True)
+        gs = g[order]
+        start = torch.ones_like(gs, dtype=torch.bool)
+        start[1:] = gs[1:] != gs[:-1]
+        first = torch.nonzero(start).squeeze(1)
+        out_inds[order] = torch.arange(n) - first[torch.cumsum(start.long(), 0) - 1]
         return 0
 
     def isf_dynamic_vfe_workspace_size(self, n, out):

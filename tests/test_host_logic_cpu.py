@@ -427,3 +427,41 @@ def test_rows_around_the_path_on_the_emulator_with_their_own_attention_kernels(m
     for k in ('center', 'height', 'dim', 'rot', 'vel', 'heatmap'):
         a, r = p[k].float().numpy(), g[k]
         assert rel(a, r) < 5e-2, (k, rel(a, r))          # fp16 K/V with these synthetic weights; a wiring error would be O(1)
+
+
+def test_remaining_call_sites_on_the_emulator(monkeypatch):
+    """the call sites the detector run does not reach: hash-table rulebooks (tensors of unknown row order), the public
+    dynamic_scatter / DynamicScatter / ingroup_indices wrappers, the SIMT DynamicVFE entry point — argument count and kind
+    checked against the header by the emulator, results against the oracle."""
+    import abi_emulator
+    import isfusion_b200.spconv as sp
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    from isfusion_b200.voxel_encoder import DynamicVFE
+    from isfusion_b200.voxel_layer import DynamicScatter, dynamic_scatter, ingroup_indices
+    from oracle import voxel_ops
+    abi_emulator.install(monkeypatch)
+    # hash path: the same voxels in shuffled row order give the same dense output as the sorted (bitmap) path
+    net = gc.fill_state(SparseEncoder(**gc.sparse_cfg()), 6).eval()
+    feats, coors = gc.sparse_inputs()
+    base, _, _ = net(feats.half(), coors, 2, sorted_coors=True)
+    perm = torch.randperm(feats.shape[0], generator=torch.Generator().manual_seed(0))
+    out, _, _ = net(feats[perm].half(), coors[perm], 2, sorted_coors=False)
+    assert torch.allclose(out.float(), base.float(), atol=1e-3, rtol=1e-3)
+    # scatter wrappers
+    pts, c4 = gc.vfe_inputs()
+    for red in ('mean', 'max', 'sum'):
+        got = dynamic_scatter(pts, c4[:, 1:].contiguous(), red)
+        want = voxel_ops.dynamic_scatter(pts, c4[:, 1:], red)
+        assert torch.equal(got[1], want[1]) and torch.allclose(got[0], want[0], atol=1e-6)
+    f, c = DynamicScatter(gc.VFE_VOXEL, gc.VFE_RANGE, True)(pts, c4)
+    wf, wc = voxel_ops.DynamicScatter(gc.VFE_VOXEL, gc.VFE_RANGE, True)(pts, c4)
+    assert torch.equal(c, wc) and torch.allclose(f, wf, atol=1e-6)
+    g = torch.tensor([3, 1, 3, 3, 0, 1], dtype=torch.int64)
+    assert ingroup_indices(g).tolist() == [0, 0, 1, 2, 0, 1]
+    # SIMT DynamicVFE entry point (fp32 output)
+    vfe = gc.fill_state(DynamicVFE(out_dtype=torch.float32, **gc.vfe_cfg()), 5).eval()
+    vfe.tensor_core = False
+    ref = gc.fill_state(voxel_ops.DynamicVFE(**gc.vfe_cfg()), 5).eval()
+    a, ac = vfe(pts, c4)
+    b, bc = ref(pts, c4)
+    assert torch.equal(ac, bc) and torch.allclose(a, b, atol=1e-4)
