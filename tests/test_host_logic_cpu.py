@@ -465,3 +465,31 @@ def test_remaining_call_sites_on_the_emulator(monkeypatch):
     a, ac = vfe(pts, c4)
     b, bc = ref(pts, c4)
     assert torch.equal(ac, bc) and torch.allclose(a, b, atol=1e-4)
+
+
+def test_bench_network_is_well_conditioned(monkeypatch):
+    """bench.py times `make_net(0)` — the product modules with their own seeded default initialisation, no oracle weights.
+    The maps that network produces on a synthetic frame must be finite and non-degenerate (a bench over NaN / saturated
+    fp16 activations or an empty proposal set would time a different workload), and its initialisation statistics must
+    equal the oracle-initialised twin used by smoke() layer by layer."""
+    import abi_emulator
+    import synth
+    from __graft_entry__ import make_net, make_pair
+    abi_emulator.install(monkeypatch)
+    net = make_net(0).eval()
+    ref, _ = make_pair(0)
+    sd, rd = net.state_dict(), ref.state_dict()
+    assert list(sd.keys()) == list(rd.keys())
+    for k in sd:
+        a, b = sd[k].float(), rd[k].float()
+        assert a.shape == b.shape, k
+        if a.numel() >= 4096 and 'num_batches' not in k:
+            assert abs(a.std().item() - b.std().item()) <= 0.15 * b.std().item() + 1e-6, (k, a.std().item(), b.std().item())
+    pts = [synth.make_points(3000, 'S', 0)]
+    l2i, aug, laug = synth.make_calib(1)
+    feats = synth.make_img_feats(1)
+    gf, ghm = net(pts, feats, [dict(input_shape=(256, 704))], lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    for t in list(gf) + [ghm]:
+        t = t.float()
+        assert torch.isfinite(t).all()
+        assert t.abs().max().item() < 6e4 and t.std().item() > 1e-4
