@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) nbr_bitmap_rows_kernel(const int* __restr
                                                               const unsigned int* __restrict__ bits,
                                                               const int* __restrict__ prefix, int* __restrict__ nbr,
                                                               long long nbr_stride, const int* __restrict__ perm,
-                                                              int* __restrict__ row_perm, TapBits tb, int chunk_shift,
+                                                              int* __restrict__ row_perm, const __grid_constant__ TapBits tb, int chunk_shift,
                                                               int invalid_bit, unsigned long long* __restrict__ keys,
                                                               int* __restrict__ rows) {
   const int n = v_out_dev ? min(*v_out_dev, v_out) : v_out;
@@ -677,7 +677,7 @@ extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const voi
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tile_order_keys_kernel(const int* __restrict__ nbr, long long nbr_stride, int taps,
                                                               int v, const int* __restrict__ v_dev, int chunk_shift,
-                                                              int invalid_bit, TapBits tb,
+                                                              int invalid_bit, const __grid_constant__ TapBits tb,
                                                               unsigned long long* __restrict__ keys, int* __restrict__ rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v) return;
