@@ -90,6 +90,20 @@ int isf_dynamic_point_to_voxel_forward(const float* feats, const int* coors, int
                                        int* coors_map, int* reduce_count, int* num_voxels_dev,
                                        void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- K3b: dynamic scatter backward ----------------------------------------------
+ * replaces voxel_layer.dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduced_feats,
+ *   coors_map, reduce_count, reduce_type)   mmdet3d/ops/voxel/src/voxelization.h:122-140,
+ *   scatter_points_cuda.cu:105-179 (kernels), :241-320 (driver).
+ * grad_feats [n,c] fp32 is written completely (no pre-zeroing needed): sum -> grad_reduced[coors_map[x]];
+ * mean -> that / reduce_count; max -> the gradient of (voxel, channel) goes to the LOWEST-index point whose feature
+ * equals the reduced value, 0 elsewhere; rows with coors_map -1 get 0.  reduce_type as in the forward (0 sum, 1 mean,
+ * 2 max).  feats / reduced are only read for max, reduce_count only for mean.  workspace: num_reduced*c int32 (max). */
+int isf_dynamic_scatter_backward_workspace_size(int num_reduced, int c, size_t* bytes);
+int isf_dynamic_point_to_voxel_backward(float* grad_feats, const float* grad_reduced, const float* feats,
+                                        const float* reduced, const int* coors_map, const int* reduce_count, int n,
+                                        int num_reduced, int c, int reduce_type, void* workspace, size_t ws_bytes,
+                                        void* stream);
+
 /* ---- K7: rank inside a group --------------------------------------------------
  * replaces ingroup_indices.forward(group_inds, out_inds)
  *   mmdet3d/ops/TorchEx/torchex/src/ingroup_inds/ingroup_inds.cpp:28-54, kernel :17-30.
@@ -283,6 +297,22 @@ int isf_ms_deform_attn_forward(const void* value, int value_is_half, const long 
                                const long long* level_start_index, const float* sampling_loc,
                                const float* attn_weight, int B, int S, int H, int D, int L, int Q, int P, float* out,
                                void* stream);
+
+/* ---- K9b: multi-scale deformable attention backward -------------------------------
+ * replaces mmcv._ext.ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+ *   grad_output, grad_value, grad_sampling_loc, grad_attn_weight, im2col_step)
+ *   (call site multi_scale_deformable_attn_function.py:61-84; kernel spec ops/src/cuda/ms_deform_im2col_cuda.cuh:87-160).
+ * grad_output [B,Q,H*D] fp32.  grad_value [B,S,H,D] fp32 is ACCUMULATED INTO (the caller zeroes it, as the reference's
+ * autograd function does); grad_sampling_loc [B,Q,H,L,P,2] and grad_attn_weight [B,Q,H,L,P] are overwritten. */
+int isf_ms_deform_attn_backward(const void* value, int value_is_half, const long long* spatial_shapes,
+                                const long long* level_start_index, const float* sampling_loc, const float* attn_weight,
+                                const float* grad_output, int B, int S, int H, int D, int L, int Q, int P,
+                                float* grad_value, float* grad_sampling_loc, float* grad_attn_weight, void* stream);
+/* TEST HOOK: the kernel's own per-sample arithmetic (shared host/device source) on HOST memory, fp32 value. */
+int isf_debug_msda_backward_host(const float* value, const long long* spatial_shapes, const long long* level_start_index,
+                                 const float* sampling_loc, const float* attn_weight, const float* grad_output, int B,
+                                 int S, int H, int D, int L, int Q, int P, float* grad_value, float* grad_sampling_loc,
+                                 float* grad_attn_weight);
 
 /* ---- a12: instance -> scene attention -------------------------------------------
  * isf_i2s_attention: softmax(q k^T / sqrt(d)) v of fusion_encoder.py:441-462 for tokens x num_keys per frame:

@@ -625,11 +625,11 @@ extern "C" int isf_heatmap_topk_class(const float* logits, int batch, int classe
 // multi-scale deformable attention (forward)
 // ================================================================================================
 template <typename T>
-__device__ __forceinline__ float ldv(const T* p);
+__host__ __device__ __forceinline__ float ldv(const T* p);
 template <>
-__device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
+__host__ __device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
 template <>
-__device__ __forceinline__ float ldv<__half>(const __half* p) { return __half2float(*p); }
+__host__ __device__ __forceinline__ float ldv<__half>(const __half* p) { return __half2float(*p); }
 
 template <typename T>
 __global__ void __launch_bounds__(256) msda_kernel(const T* __restrict__ value, const long long* __restrict__ shapes,
@@ -692,6 +692,179 @@ extern "C" int isf_ms_deform_attn_forward(const void* value, int value_is_half, 
                                                 attn_weight, B, S, H, D, L, Q, P, out);
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ================================================================================================
+// multi-scale deformable attention (backward, K9b)
+// ================================================================================================
+// replaces mmcv._ext.ms_deform_attn_backward (call site multi_scale_deformable_attn_function.py:61-84; kernel spec
+// ops/src/cuda/ms_deform_im2col_cuda.cuh:87-160 bilinear backward, :300-400 the col2im kernels).  Same work split as the
+// forward (a thread = one channel d of one (b, q, h)); the geometry of a sampling point (corner cells, bilinear weights
+// and their derivatives) does not depend on the channel and is shared host / device code, so the CPU test runs the very
+// same arithmetic (isf_debug_msda_backward_host).  grad_value is accumulated with fp32 atomics (red.global.add.f32), the
+// per-point gradients of the sampling location and of the attention weight are summed over the D channels of a head
+// with warp shuffles (D a power of two <= 32: a head's channels are consecutive lanes) and written once, without atomics.
+struct MsdaCorners {
+  long long cell[4];      // h * width + w of the four corners (valid only where ok)
+  float w[4];             // bilinear weights  (hh*hw, hh*lw, lh*hw, lh*lw)
+  float dh[4], dw[4];     // d(sample)/d(h), d(sample)/d(w) coefficient of each corner value
+  bool ok[4];
+};
+
+// loc = (x, y) in [0, 1] (x = width first, fusion_encoder.py:589-596); false = the sample lies outside the map
+__host__ __device__ __forceinline__ bool msda_corners(float loc_w, float loc_h, int sh, int sw, MsdaCorners& c) {
+  const float him = loc_h * sh - 0.5f, wim = loc_w * sw - 0.5f;
+  if (!(him > -1.f && wim > -1.f && him < (float)sh && wim < (float)sw)) return false;
+  const int hl = (int)floorf(him), wl = (int)floorf(wim);
+  const float lh = him - hl, lw = wim - wl, hh = 1.f - lh, hw = 1.f - lw;
+  c.ok[0] = hl >= 0 && wl >= 0;
+  c.ok[1] = hl >= 0 && wl + 1 <= sw - 1;
+  c.ok[2] = hl + 1 <= sh - 1 && wl >= 0;
+  c.ok[3] = hl + 1 <= sh - 1 && wl + 1 <= sw - 1;
+  c.cell[0] = (long long)hl * sw + wl;       c.cell[1] = (long long)hl * sw + wl + 1;
+  c.cell[2] = (long long)(hl + 1) * sw + wl; c.cell[3] = (long long)(hl + 1) * sw + wl + 1;
+  c.w[0] = hh * hw;  c.w[1] = hh * lw;  c.w[2] = lh * hw;  c.w[3] = lh * lw;
+  c.dh[0] = -hw;     c.dh[1] = -lw;     c.dh[2] = hw;      c.dh[3] = lw;
+  c.dw[0] = -hh;     c.dw[1] = hh;      c.dw[2] = -lh;     c.dw[3] = lh;
+  return true;
+}
+
+// one channel of one sampling point: vb / gvb = value / grad_value at (level base, head h, channel d), `stride` = H*D
+// elements between cells.  Adds the value gradient in place and returns this channel's share of the three point gradients.
+template <typename T>
+__host__ __device__ __forceinline__ void msda_bwd_channel(const MsdaCorners& c, const T* vb, float* gvb, long long stride,
+                                                          float top_grad, float attn, int sh, int sw, float& g_attn,
+                                                          float& g_x, float& g_y) {
+  const float tgv = top_grad * attn;
+  float val = 0.f, gh = 0.f, gw = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (!c.ok[i]) continue;
+    const float v = ldv(vb + c.cell[i] * stride);
+    val += c.w[i] * v;
+    gh += c.dh[i] * v;
+    gw += c.dw[i] * v;
+#ifdef __CUDA_ARCH__
+    atomicAdd(gvb + c.cell[i] * stride, c.w[i] * tgv);
+#else
+    gvb[c.cell[i] * stride] += c.w[i] * tgv;
+#endif
+  }
+  g_attn = top_grad * val;
+  g_x = (float)sw * gw * tgv;
+  g_y = (float)sh * gh * tgv;
+}
+
+template <typename T, bool SHUFFLE>
+__global__ void __launch_bounds__(256) msda_backward_kernel(const T* __restrict__ value, const long long* __restrict__ shapes,
+                                                            const long long* __restrict__ lvl_start,
+                                                            const float* __restrict__ loc, const float* __restrict__ attn,
+                                                            const float* __restrict__ grad_out, int B, int S, int H, int D,
+                                                            int L, int Q, int P, float* __restrict__ grad_value,
+                                                            float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+  const long long n = (long long)B * Q * H * D;
+  const long long n_pad = (n + 31) / 32 * 32;            // whole warps take part in the shuffles
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_pad; t += (long long)gridDim.x * blockDim.x) {
+    const bool live = t < n;
+    const long long tt = live ? t : n - 1;
+    const int d = (int)(tt % D);
+    long long r = tt / D;
+    const int h = (int)(r % H); r /= H;
+    const int q = (int)(r % Q);
+    const int b = (int)(r / Q);
+    const long long samp = ((long long)b * Q + q) * H + h;
+    const float* lp = loc + samp * L * P * 2;
+    const float* ap = attn + samp * L * P;
+    const float top_grad = live ? grad_out[tt] : 0.f;
+    const long long stride = (long long)H * D;
+    for (int l = 0; l < L; ++l) {
+      const int sh = (int)shapes[2 * l], sw = (int)shapes[2 * l + 1];
+      const long long base = ((long long)b * S + lvl_start[l]) * stride + h * D + d;
+      for (int p = 0; p < P; ++p) {
+        float ga = 0.f, gx = 0.f, gy = 0.f;
+        MsdaCorners c;
+        if (live && msda_corners(lp[(l * P + p) * 2], lp[(l * P + p) * 2 + 1], sh, sw, c))
+          msda_bwd_channel(c, value + base, grad_value + base, stride, top_grad, ap[l * P + p], sh, sw, ga, gx, gy);
+        const long long o = samp * L * P + l * P + p;
+        if (SHUFFLE) {
+          for (int s = D >> 1; s > 0; s >>= 1) {
+            ga += __shfl_xor_sync(0xffffffffu, ga, s);
+            gx += __shfl_xor_sync(0xffffffffu, gx, s);
+            gy += __shfl_xor_sync(0xffffffffu, gy, s);
+          }
+          if (live && d == 0) { grad_attn[o] = ga; grad_loc[2 * o] = gx; grad_loc[2 * o + 1] = gy; }
+        } else if (live) {                       // any D: the outputs were zeroed by the entry point
+          atomicAdd(grad_attn + o, ga); atomicAdd(grad_loc + 2 * o, gx); atomicAdd(grad_loc + 2 * o + 1, gy);
+        }
+      }
+    }
+  }
+}
+
+// value [B,S,H,D] fp32|fp16, grad_out [B,Q,H*D] fp32 -> grad_value [B,S,H,D] fp32 ACCUMULATED INTO (the caller zeroes it,
+// as the reference's autograd function does), grad_sampling_loc [B,Q,H,L,P,2] and grad_attn_weight [B,Q,H,L,P] overwritten.
+extern "C" int isf_ms_deform_attn_backward(const void* value, int value_is_half, const long long* spatial_shapes,
+                                           const long long* level_start_index, const float* sampling_loc,
+                                           const float* attn_weight, const float* grad_output, int B, int S, int H, int D,
+                                           int L, int Q, int P, float* grad_value, float* grad_sampling_loc,
+                                           float* grad_attn_weight, void* stream) {
+  ISF_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && grad_output);
+  ISF_CHECK_ARG(grad_value && grad_sampling_loc && grad_attn_weight);
+  ISF_CHECK_ARG(B >= 1 && S >= 1 && H >= 1 && D >= 1 && L >= 1 && Q >= 1 && P >= 1);
+  const long long n = (long long)B * Q * H * D;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool shuffle = D <= 32 && (D & (D - 1)) == 0;
+  if (!shuffle) {
+    const size_t pts = (size_t)B * Q * H * L * P;
+    ISF_CUDA(cudaMemsetAsync(grad_attn_weight, 0, pts * sizeof(float), st));
+    ISF_CUDA(cudaMemsetAsync(grad_sampling_loc, 0, 2 * pts * sizeof(float), st));
+  }
+#define ISF_MSDA_BWD(T, SH)                                                                                          \
+  msda_backward_kernel<T, SH><<<blocks, 256, 0, st>>>((const T*)value, spatial_shapes, level_start_index, sampling_loc, \
+                                                      attn_weight, grad_output, B, S, H, D, L, Q, P, grad_value,      \
+                                                      grad_sampling_loc, grad_attn_weight)
+  if (value_is_half) { if (shuffle) ISF_MSDA_BWD(__half, true); else ISF_MSDA_BWD(__half, false); }
+  else               { if (shuffle) ISF_MSDA_BWD(float, true);  else ISF_MSDA_BWD(float, false); }
+#undef ISF_MSDA_BWD
+  isf_count_launch(1);
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// TEST HOOK (host memory, no GPU): the same msda_corners / msda_bwd_channel code on the CPU, fp32 value.
+extern "C" int isf_debug_msda_backward_host(const float* value, const long long* spatial_shapes,
+                                            const long long* level_start_index, const float* sampling_loc,
+                                            const float* attn_weight, const float* grad_output, int B, int S, int H, int D,
+                                            int L, int Q, int P, float* grad_value, float* grad_sampling_loc,
+                                            float* grad_attn_weight) {
+  ISF_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && grad_output);
+  ISF_CHECK_ARG(grad_value && grad_sampling_loc && grad_attn_weight);
+  const long long stride = (long long)H * D;
+  for (long long samp = 0; samp < (long long)B * Q * H; ++samp) {
+    const int h = (int)(samp % H);
+    const int b = (int)(samp / ((long long)Q * H));
+    for (int l = 0; l < L; ++l) {
+      const int sh = (int)spatial_shapes[2 * l], sw = (int)spatial_shapes[2 * l + 1];
+      for (int p = 0; p < P; ++p) {
+        const long long o = samp * L * P + l * P + p;
+        float sa = 0.f, sx = 0.f, sy = 0.f;
+        MsdaCorners c;
+        if (msda_corners(sampling_loc[2 * o], sampling_loc[2 * o + 1], sh, sw, c)) {
+          for (int d = 0; d < D; ++d) {
+            const long long base = ((long long)b * S + level_start_index[l]) * stride + h * D + d;
+            float ga, gx, gy;
+            msda_bwd_channel(c, value + base, grad_value + base, stride, grad_output[samp * D + d], attn_weight[o], sh, sw,
+                             ga, gx, gy);
+            sa += ga; sx += gx; sy += gy;
+          }
+        }
+        grad_attn_weight[o] = sa; grad_sampling_loc[2 * o] = sx; grad_sampling_loc[2 * o + 1] = sy;
+      }
+    }
+  }
   return ISF_OK;
 }
 

@@ -299,6 +299,99 @@ extern "C" int isf_dynamic_point_to_voxel_forward(const float* feats, const int*
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3b: dynamic scatter backward  (scatter_points_cuda.cu:105-179, driver :241-320)
+//   sum : grad_feats[x] = grad_reduced[map[x]]            mean: ... / reduce_count[map[x]]
+//   max : for every (voxel, channel) the LOWEST-index point whose feature equals the reduced value receives the
+//         gradient (the reference's atomicMin over point indices), every other point 0.
+// Rows with map[x] == -1 get 0.  Unlike the reference there is no fill_(0) + scattered write: both variants are one
+// coalesced point-major pass that writes every element of grad_feats exactly once.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scatter_backward_add_kernel(const float* __restrict__ grad_reduced,
+                                                                   const int* __restrict__ coors_map,
+                                                                   const int* __restrict__ reduce_count, long long total,
+                                                                   int c, int mean, float* __restrict__ grad_feats) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t / c), i = (int)(t % c);
+    const int to = coors_map[x];
+    float g = 0.f;
+    if (to >= 0) {
+      g = grad_reduced[(long long)to * c + i];
+      if (mean) g = g / (float)reduce_count[to];
+    }
+    grad_feats[t] = g;
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_backward_argmax_kernel(const float* __restrict__ feats,
+                                                                      const float* __restrict__ reduced,
+                                                                      const int* __restrict__ coors_map, long long total,
+                                                                      int c, int* __restrict__ reduce_from) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t / c), i = (int)(t % c);
+    const int to = coors_map[x];
+    if (to < 0) continue;
+    const long long r = (long long)to * c + i;
+    if (feats[t] == reduced[r]) atomicMin(&reduce_from[r], x);
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_backward_max_kernel(const float* __restrict__ grad_reduced,
+                                                                   const int* __restrict__ coors_map,
+                                                                   const int* __restrict__ reduce_from, long long total,
+                                                                   int c, float* __restrict__ grad_feats) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t / c), i = (int)(t % c);
+    const int to = coors_map[x];
+    float g = 0.f;
+    if (to >= 0) {
+      const long long r = (long long)to * c + i;
+      if (reduce_from[r] == x) g = grad_reduced[r];
+    }
+    grad_feats[t] = g;
+  }
+}
+
+extern "C" int isf_dynamic_scatter_backward_workspace_size(int num_reduced, int c, size_t* bytes) {
+  ISF_CHECK_ARG(bytes && num_reduced >= 0 && c >= 1);
+  *bytes = (size_t)num_reduced * c * sizeof(int) + 256;
+  return ISF_OK;
+}
+
+extern "C" int isf_dynamic_point_to_voxel_backward(float* grad_feats, const float* grad_reduced, const float* feats,
+                                                   const float* reduced, const int* coors_map, const int* reduce_count,
+                                                   int n, int num_reduced, int c, int reduce_type, void* workspace,
+                                                   size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(n >= 0 && num_reduced >= 0 && c >= 1 && reduce_type >= 0 && reduce_type <= 2);
+  if (n == 0) return ISF_OK;
+  ISF_CHECK_ARG(grad_feats && coors_map);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * c;
+  if (num_reduced == 0) {                   // every point was dropped: the gradient is zero
+    ISF_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * total, st));
+    return ISF_OK;
+  }
+  ISF_CHECK_ARG(grad_reduced);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+  if (reduce_type != 2) {                   // 0 = sum, 1 = mean (same codes as the forward)
+    ISF_CHECK_ARG(reduce_type == 0 || reduce_count);
+    scatter_backward_add_kernel<<<blocks, 256, 0, st>>>(grad_reduced, coors_map, reduce_count, total, c, reduce_type == 1,
+                                                        grad_feats);
+    isf_count_launch(1);
+  } else {
+    ISF_CHECK_ARG(feats && reduced && workspace);
+    if (ws_bytes < (size_t)num_reduced * c * sizeof(int)) { isf_set_error("dynamic scatter backward: workspace too small"); return ISF_ERR_WORKSPACE; }
+    int* reduce_from = (int*)workspace;
+    ISF_CUDA(cudaMemsetAsync(reduce_from, 0x7F, sizeof(int) * (size_t)num_reduced * c, st));   // 0x7F7F7F7F > any point index
+    scatter_backward_argmax_kernel<<<blocks, 256, 0, st>>>(feats, reduced, coors_map, total, c, reduce_from);
+    scatter_backward_max_kernel<<<blocks, 256, 0, st>>>(grad_reduced, coors_map, reduce_from, total, c, grad_feats);
+    isf_count_launch(3);
+  }
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7: ingroup indices  (TorchEx/.../ingroup_inds_kernel.cu:17-30: rank of each element inside its
 // group; the reference hands ranks out in atomic arrival order, here rank = stable index order)
 // ------------------------------------------------------------------------------------------------

@@ -426,18 +426,51 @@ class MSDeformAttn(nn.Module):
         nn.init.constant_(self.output_proj.bias.data, 0.)
 
 
-def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=64):
-    """ref: MultiScaleDeformableAttnFunction_fp32.forward (multi_scale_deformable_attn_function.py:90-128) ->
-    mmcv._ext.ms_deform_attn_forward.  value [B,S,H,D] fp32|fp16 -> [B,Q,H*D] fp32."""
-    L.require_cuda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+def _msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
     b, s, h, d = value.shape
     _, q, _, lv, p, _ = sampling_locations.shape
     out = torch.empty((b, q, h * d), dtype=torch.float32, device=value.device)
     L.check(L.lib().isf_ms_deform_attn_forward(
-        L.ptr(value.contiguous()), 1 if value.dtype == torch.float16 else 0, L.ptr(spatial_shapes.long().contiguous()),
-        L.ptr(level_start_index.long().contiguous()), L.ptr(sampling_locations.float().contiguous()),
-        L.ptr(attention_weights.float().contiguous()), b, s, h, d, lv, q, p, L.ptr(out), L.stream()))
+        L.ptr(value), 1 if value.dtype == torch.float16 else 0, L.ptr(spatial_shapes), L.ptr(level_start_index),
+        L.ptr(sampling_locations), L.ptr(attention_weights), b, s, h, d, lv, q, p, L.ptr(out), L.stream()))
     return out
+
+
+class MultiScaleDeformableAttnFunction(torch.autograd.Function):
+    """ref: MultiScaleDeformableAttnFunction_fp32 (multi_scale_deformable_attn_function.py:90-171): forward = K9,
+    backward = K9b (isf_ms_deform_attn_backward) — gradients of value, sampling locations and attention weights."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+        return _msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lvl_start, loc, aw = ctx.saved_tensors
+        b, s, h, d = value.shape
+        _, q, _, lv, p, _ = loc.shape
+        grad_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)     # accumulated into
+        grad_loc = torch.empty_like(loc)
+        grad_aw = torch.empty_like(aw)
+        L.check(L.lib().isf_ms_deform_attn_backward(
+            L.ptr(value), 1 if value.dtype == torch.float16 else 0, L.ptr(shapes), L.ptr(lvl_start), L.ptr(loc), L.ptr(aw),
+            L.ptr(grad_output.float().contiguous()), b, s, h, d, lv, q, p, L.ptr(grad_value), L.ptr(grad_loc), L.ptr(grad_aw),
+            L.stream()))
+        return grad_value.to(value.dtype), None, None, grad_loc, grad_aw
+
+
+def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=64):
+    """ref: MultiScaleDeformableAttnFunction_fp32 (multi_scale_deformable_attn_function.py:90-171) ->
+    mmcv._ext.ms_deform_attn_forward / _backward.  value [B,S,H,D] fp32|fp16 -> [B,Q,H*D] fp32; differentiable in value,
+    sampling_locations and attention_weights (the autograd function is only entered when a gradient is asked for)."""
+    L.require_cuda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+    args = (value.contiguous(), spatial_shapes.long().contiguous(), level_start_index.long().contiguous(),
+            sampling_locations.float().contiguous(), attention_weights.float().contiguous())
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (value, sampling_locations, attention_weights)):
+        return MultiScaleDeformableAttnFunction.apply(*args)
+    return _msda_forward(*args)
 
 
 class DeformableTransformerDecoderLayer(nn.Module):

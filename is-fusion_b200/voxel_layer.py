@@ -5,6 +5,7 @@ voxel_layer.* pybind functions voxelization.cpp:6-11, and ingroup_indices.forwar
 TorchEx/.../ingroup_inds.cpp:28-54) on top of the C-ABI library.
 """
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -74,6 +75,26 @@ def dynamic_point_to_voxel_forward(feats, coors, reduce_type='max', dims=None):
     return [reduced[:v], out_coors[:v], cmap, rcount[:v]]
 
 
+def dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_map, reduce_count,
+                                    reduce_type='max'):
+    """ref: voxel_layer.dynamic_point_to_voxel_backward (voxelization.h:122-140, scatter_points_cuda.cu:241-320): fills
+    the caller's `grad_feats` [N,C] in place (sum / mean: the voxel's gradient (/ count); max: the lowest-index arg-max
+    point of every (voxel, channel))."""
+    L.require_cuda(grad_feats, grad_reduced_feats, feats, reduced_feats, coors_map, reduce_count)
+    n, c = feats.shape
+    v = reduced_feats.size(0)
+    if n == 0:
+        return
+    if grad_feats.dtype != torch.float32 or grad_reduced_feats.dtype != torch.float32 or coors_map.dtype != torch.int32:
+        raise L.IsfError('dynamic_point_to_voxel_backward: float32 gradients and an int32 map expected')
+    ws_bytes = ctypes.c_size_t(0)
+    L.check(L.lib().isf_dynamic_scatter_backward_workspace_size(v, c, ctypes.byref(ws_bytes)))
+    ws = L.workspace(ws_bytes.value, feats.device)
+    L.check(L.lib().isf_dynamic_point_to_voxel_backward(
+        L.ptr(grad_feats), L.ptr(grad_reduced_feats), L.ptr(feats), L.ptr(reduced_feats), L.ptr(coors_map),
+        L.ptr(reduce_count), n, v, c, _REDUCE[reduce_type], L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
+
+
 def ingroup_indices(group_inds):
     """ref: IngroupIndicesFunction (mmdet3d/ops/sst/sst_ops.py:199-217): rank of each element in its group."""
     L.require_cuda(group_inds)
@@ -138,10 +159,15 @@ class Voxelization(nn.Module):
                 f'deterministic={self.deterministic})')
 
 
+# opt-in: hand-written K3b backward kernels (written at the end of round 1 without GPU time; brought up in round 2)
+OWN_SCATTER_BACKWARD = os.environ.get('ISF_SCATTER_BWD', '') == 'own'
+
+
 class _dynamic_scatter(Function):
-    """ref: mmdet3d/ops/voxel/scatter_points.py:9-46.  Backward (K3b) follows
-    scatter_points_cuda.cu:105-179: mean/sum spread grad/count, max routes the gradient to the
-    lowest-index arg-max point of every (voxel, channel)."""
+    """ref: mmdet3d/ops/voxel/scatter_points.py:9-46.  Backward follows scatter_points_cuda.cu:105-179: mean/sum spread
+    grad (/count), max routes the gradient to the lowest-index arg-max point of every (voxel, channel).  Two
+    implementations with identical results: device-side torch index ops (default until the kernels' first GPU run) and
+    the K3b kernels (csrc/voxel.cu isf_dynamic_point_to_voxel_backward; ISF_SCATTER_BWD=own)."""
 
     @staticmethod
     def forward(ctx, feats, coors, reduce_type='max'):
@@ -155,6 +181,11 @@ class _dynamic_scatter(Function):
     @staticmethod
     def backward(ctx, grad_voxel_feats, grad_voxel_coors=None):
         feats, voxel_feats, p2v, count = ctx.saved_tensors
+        if OWN_SCATTER_BACKWARD:
+            grad_feats = torch.empty_like(feats)          # the kernel writes every element
+            dynamic_point_to_voxel_backward(grad_feats, grad_voxel_feats.contiguous(), feats, voxel_feats, p2v, count,
+                                            ctx.reduce_type)
+            return grad_feats, None, None
         grad_feats = torch.zeros_like(feats)
         valid = p2v >= 0
         idx = p2v.clamp(min=0).long()

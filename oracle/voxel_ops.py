@@ -168,6 +168,41 @@ def dynamic_scatter(feats, coors, reduce_type='max'):
     return red, out_coors.to(coors.dtype), cmap.to(torch.int32), counts.to(torch.int32)
 
 
+def dynamic_scatter_backward(grad_reduced, feats, reduced, coors_map, reduce_count, reduce_type='max'):
+    """gradient of dynamic_scatter w.r.t. feats, as the reference's backward kernels define it
+    (scatter_points_cuda.cu:105-179, driver :241-320; NO CPU path in the reference, voxelization.h:139, so this is a
+    literal loop restatement — for sum / mean it equals autograd of the brute-force definition, which the test checks):
+      sum : grad_feats[x] = grad_reduced[map[x]]   (:121-124)      mean: ... / reduce_count[map[x]]   (:125-130)
+      max : per (voxel, channel) the LOWEST point index with feats == reduced gets the gradient (atomicMin, :135-161;
+            scatter :163-179); everything else, and rows with map == -1, stay 0 (grad_feats.fill_(0), :258)."""
+    import numpy as np
+    g = grad_reduced.detach().cpu().float().numpy()
+    f = feats.detach().cpu().float().numpy()
+    r = reduced.detach().cpu().float().numpy()
+    m = coors_map.detach().cpu().numpy()
+    cnt = reduce_count.detach().cpu().numpy()
+    n, c = f.shape
+    out = np.zeros((n, c), np.float32)
+    if reduce_type in ('sum', 'mean'):
+        for x in range(n):
+            if m[x] < 0:
+                continue
+            out[x] = g[m[x]] if reduce_type == 'sum' else g[m[x]] / np.float32(cnt[m[x]])
+        return torch.from_numpy(out)
+    reduce_from = np.full(r.shape, n, np.int64)
+    for x in range(n):
+        if m[x] < 0:
+            continue
+        for i in range(c):
+            if f[x, i] == r[m[x], i] and x < reduce_from[m[x], i]:
+                reduce_from[m[x], i] = x
+    for v in range(r.shape[0]):
+        for i in range(c):
+            if reduce_from[v, i] < n:
+                out[reduce_from[v, i], i] = g[v, i]
+    return torch.from_numpy(out)
+
+
 class DynamicScatter(nn.Module):
     """ref: mmdet3d/ops/voxel/scatter_points.py:54-103 (per-sample loop + batch pad)."""
 

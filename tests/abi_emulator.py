@@ -172,6 +172,18 @@ class _FusionLib:
         out.copy_(ms_deform_attn_core_pytorch(value.float(), shapes, loc.float(), attn.float()))
         return 0
 
+    def isf_ms_deform_attn_backward(self, value, is_half, shapes, lvl_start, loc, attn, grad_out, b, s, h, d, lv, q, p, grad_value,
+                                    grad_loc, grad_attn, stream):
+        from oracle.fusion_ops import ms_deform_attn_core_pytorch
+        with torch.enable_grad():
+            v64, l64, a64 = (t.detach().double().requires_grad_(True) for t in (value, loc, attn))
+            y = ms_deform_attn_core_pytorch(v64, shapes, l64, a64)
+            gv, gl, ga = torch.autograd.grad(y, (v64, l64, a64), grad_out.double())
+        grad_value.add_(gv.float())                 # accumulated into, as the kernel does
+        grad_loc.copy_(gl.float())
+        grad_attn.copy_(ga.float())
+        return 0
+
     # ------------------------------------------------------------------ isf_i2s_attention / isf_channel_attention
     def isf_i2s_attention(self, q, kv, batch, tokens, nk, channels, heads, out, stream):
         d = channels // heads
@@ -407,6 +419,16 @@ class VoxelMixin:
         nv[0] = v
         return 0
 
+    def isf_dynamic_scatter_backward_workspace_size(self, v, c, bytes_ref):
+        _set_size(bytes_ref, 256)
+        return 0
+
+    def isf_dynamic_point_to_voxel_backward(self, grad_feats, grad_reduced, feats, reduced, cmap, count, n, v, c, reduce_type, ws,
+                                            ws_bytes, stream):
+        from oracle import voxel_ops as vo
+        grad_feats.copy_(vo.dynamic_scatter_backward(grad_reduced, feats, reduced, cmap, count, {0: 'sum', 1: 'mean', 2: 'max'}[reduce_type]))
+        return 0
+
     def isf_ingroup_indices(self, group_inds, n, key_bits, out_inds, ws, ws_bytes, stream):
         g = group_inds[:n]
         order = torch.argsort(g, stable=True)
@@ -534,7 +556,8 @@ class RowsAroundMixin:
 
 class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):
     _KINDS = None
-    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_version')
+    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_debug_msda_backward_host',
+                 'isf_version')
 
     def __init__(self, real=None):
         self._real = real

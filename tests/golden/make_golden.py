@@ -104,6 +104,38 @@ def msda_ref():
     np.savez_compressed(os.path.join(HERE, 'msda_ref.npz'), **out)
 
 
+def msda_bwd_ref():
+    """msda_bwd_ref.npz: gradients of the reference's own ms_deform_attn_core_pytorch (ops/functions/ms_deform_attn_func.py:
+    41-61, executed unmodified) by autograd in float64 — what the reference's gradient test (ops/test.py:63-86,
+    check_gradient_numerical) holds its CUDA backward against."""
+    src = open(os.path.join(REF, 'ops/functions/ms_deform_attn_func.py')).read().split('\n')
+    ns = {'torch': torch, 'F': torch.nn.functional}
+    exec('\n'.join(src[40:61]), ns)
+    core = ns['ms_deform_attn_core_pytorch']
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    cases = {
+        'a': dict(N=1, M=2, D=2, Lq=2, shapes=[(6, 4), (3, 2)], P=2, spread=1.0),        # ops/test.py:20-36
+        'b': dict(N=2, M=8, D=16, Lq=50, shapes=[(12, 14)], P=16, spread=1.2),           # IGF layout, samples outside [0,1]
+        'c': dict(N=1, M=3, D=5, Lq=7, shapes=[(5, 7), (4, 3), (2, 2)], P=3, spread=1.1),   # D not a power of two
+    }
+    for k, c in cases.items():
+        shapes = torch.as_tensor(c['shapes'], dtype=torch.long)
+        S = int((shapes[:, 0] * shapes[:, 1]).sum())
+        Lv = len(c['shapes'])
+        value = torch.randn(c['N'], S, c['M'], c['D'], generator=g)
+        loc = torch.rand(c['N'], c['Lq'], c['M'], Lv, c['P'], 2, generator=g) * c['spread'] - (c['spread'] - 1) / 2
+        aw = torch.softmax(torch.randn(c['N'], c['Lq'], c['M'], Lv * c['P'], generator=g), -1).view(c['N'], c['Lq'], c['M'], Lv, c['P'])
+        go = torch.randn(c['N'], c['Lq'], c['M'] * c['D'], generator=g)
+        v64, l64, a64 = (t.double().requires_grad_(True) for t in (value, loc, aw))
+        y = core(v64, shapes, l64, a64)
+        gv, gl, ga = torch.autograd.grad(y, (v64, l64, a64), go.double())
+        out.update({k + '_value': value.numpy(), k + '_shapes': shapes.numpy(), k + '_loc': loc.numpy(), k + '_aw': aw.numpy(),
+                    k + '_grad_out': go.numpy(), k + '_out': y.detach().float().numpy(), k + '_grad_value': gv.float().numpy(),
+                    k + '_grad_loc': gl.float().numpy(), k + '_grad_aw': ga.float().numpy()})
+    np.savez_compressed(os.path.join(HERE, 'msda_bwd_ref.npz'), **out)
+
+
 SPCONV_CASES = {   # the four rulebook shapes of the SparseEncoder (config:72-82; sparse_encoder.py:76-105)
     'subm3': dict(ksize=(3, 3, 3), stride=(1, 1, 1), padding=(1, 1, 1), subm=True),
     'down_p1': dict(ksize=(3, 3, 3), stride=(2, 2, 2), padding=(1, 1, 1), subm=False),
@@ -148,7 +180,7 @@ def spconv_ref_cpp():
 
 
 if __name__ == '__main__':
-    for name in (sys.argv[1:] or ['voxel_generator_kat', 'voxel_ref_cpp', 'msda_ref', 'spconv_ref_cpp']):
+    for name in (sys.argv[1:] or ['voxel_generator_kat', 'voxel_ref_cpp', 'msda_ref', 'msda_bwd_ref', 'spconv_ref_cpp']):
         globals()[name]()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
