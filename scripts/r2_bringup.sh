@@ -38,6 +38,9 @@ ISF_TILE_ORDER=31 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-bas
 ISF_TILE_ORDER=16 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline              > gpurun_out/r2_bench_ord16.json 2>> $LOG
 ISF_TILE_ORDER=31 ISF_NBR_ROWS=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_ord31_rows.json 2>> $LOG
 ISF_OWN_CONV=1 timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline                 > gpurun_out/r2_bench_ownconv.json 2>> $LOG
+step "whole-config forward (images + points -> boxes), default and with the own attention kernels"
+timeout 300 python scripts/bench_full_forward.py                                                   > gpurun_out/r2_full_forward.json 2>> $LOG
+ISF_HEAD_ATTN=own ISF_SWIN_ATTN=own timeout 300 python scripts/bench_full_forward.py               > gpurun_out/r2_full_forward_own_attn.json 2>> $LOG
 export ISF_EXPERIMENTAL=1
 step "v2 warp-specialised GEMM schedule: bring-up tests (bounded waits trap instead of hanging)"
 timeout 300 python -m pytest tests/test_gemm_v2_gpu.py -x -q -m gpu            >> $LOG 2>&1 && {

@@ -33,6 +33,38 @@ def neck_config(voxel_size=VOXEL_SIZE, pc_range=PC_RANGE, out_size_factor=8):
                           norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), conv_cfg=dict(type='Conv2d', bias=False)))
 
 
+def full_model_config(voxel_size=VOXEL_SIZE, pc_range=PC_RANGE, out_size_factor=8):
+    """the whole `model = dict(...)` of configs/isfusion/isfusion_0075voxel.py:24-178 (inference keys): image branch
+    (SwinTransformer + GeneralizedLSSFPN), the neck (neck_config), SECONDFPN, TransFusionHeadV2 and test_cfg — for
+    `isfusion_b200.registry.build_detector`.  tests/test_config_dropin.py checks it key by key against the reference's file."""
+    c = neck_config(voxel_size, pc_range, out_size_factor)
+    voxel_shape = int((pc_range[3] - pc_range[0]) // voxel_size[0])
+    return dict(
+        type='ISFusionDetector', detach=True, pc_range=pc_range, voxel_size=voxel_size, out_size_factor=out_size_factor,
+        img_backbone=dict(type='SwinTransformer', embed_dims=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
+                          mlp_ratio=4, qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2,
+                          patch_norm=True, out_indices=[1, 2, 3], with_cp=False, convert_weights=False),
+        img_neck=dict(type='GeneralizedLSSFPN', in_channels=[192, 384, 768], out_channels=256, start_level=0, num_outs=3),
+        pts_voxel_layer=dict(point_cloud_range=pc_range, max_num_points=-1, voxel_size=voxel_size, max_voxels=(-1, -1)),
+        pts_voxel_encoder=dict(type='DynamicVFE', **c['pts_voxel_encoder']),
+        pts_middle_encoder=dict(type='SparseEncoder', **c['pts_middle_encoder']),
+        fusion_encoder=dict(type='ISFusionEncoder', **c['fusion_encoder']),
+        pts_backbone=dict(type='SECONDV2', **c['pts_backbone']),
+        pts_neck=dict(type='SECONDFPN', in_channels=[128, 256], out_channels=[256, 256], upsample_strides=[1, 2],
+                      norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), upsample_cfg=dict(type='deconv', bias=False),
+                      use_conv_for_no_stride=True),
+        pts_bbox_head=dict(
+            type='TransFusionHeadV2', num_proposals=200, auxiliary=True, in_channels=256 * 2, hidden_channel=128, num_classes=10,
+            num_decoder_layers=1, num_heads=8, nms_kernel_size=3, ffn_channel=256, dropout=0.1, bn_momentum=0.1, activation='relu',
+            common_heads=dict(center=(2, 2), height=(1, 2), dim=(3, 2), rot=(2, 2), vel=(2, 2)),
+            bbox_coder=dict(type='TransFusionBBoxCoder', pc_range=pc_range[:2], voxel_size=voxel_size[:2],
+                            out_size_factor=out_size_factor, post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
+                            score_threshold=0.0, code_size=10)),
+        test_cfg=dict(pts=dict(dataset='nuScenes', grid_size=[voxel_shape, voxel_shape, 40], out_size_factor=out_size_factor,
+                               pc_range=pc_range[0:2], voxel_size=voxel_size[:2], nms_type=None, use_rotate_nms=True, nms_thr=0.2,
+                               max_num=200)))
+
+
 def make_points(n, kind='S', seed=0, pc_range=PC_RANGE):
     g = torch.Generator().manual_seed(seed)
     lo = torch.tensor(pc_range[:3])

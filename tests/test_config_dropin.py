@@ -84,3 +84,34 @@ def test_img_neck_module_has_the_reference_state_dict_keys():
     from isfusion_b200.img_neck import GeneralizedLSSFPN
     net = GeneralizedLSSFPN(**gc.lss_cfg())
     assert sorted(net.state_dict().keys()) == list(np.load(os.path.join(here, 'golden', 'ref_lss.npz'))['keys'])
+
+
+@pytest.mark.skipif(not os.path.exists(CFG), reason='reference checkout not present')
+def test_synthetic_full_model_config_equals_the_reference_config():
+    """synth.full_model_config() — what the GPU box builds the whole detector from (no reference checkout there) — holds
+    the reference config's values for every key it carries (losses / train_cfg are the only keys left out)."""
+    import synth
+    ns = {}
+    exec(compile(open(CFG).read(), CFG, 'exec'), ns)
+    ref, mine = ns['model'], synth.full_model_config()
+
+    def norm(v):
+        if isinstance(v, dict):
+            return {k: norm(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return [norm(x) for x in v]
+        return v
+
+    def check(a, b, path):
+        assert isinstance(b, dict), path
+        for k, v in a.items():
+            assert k in b, path + '.' + k
+            if isinstance(v, dict):
+                check(v, b[k], path + '.' + k)
+            else:
+                assert norm(v) == norm(b[k]), (path + '.' + k, v, b[k])
+
+    check(mine, ref, 'model')
+    left_out = set(ref) - set(mine)
+    assert left_out == {'train_cfg'}, left_out
+    assert set(ref['pts_bbox_head']) - set(mine['pts_bbox_head']) == {'loss_cls', 'loss_bbox', 'loss_heatmap'}

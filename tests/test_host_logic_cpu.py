@@ -493,3 +493,29 @@ def test_bench_network_is_well_conditioned(monkeypatch):
         t = t.float()
         assert torch.isfinite(t).all()
         assert t.abs().max().item() < 6e4 and t.std().item() > 1e-4
+
+
+def test_full_detector_built_from_the_config_runs_end_to_end_on_the_emulator(monkeypatch):
+    """`make_full_net` — the config's whole detector (Swin + GeneralizedLSSFPN + neck + SECONDFPN + TransFusionHeadV2) built by
+    name from synth.full_model_config — through `simple_test(points, img_metas, img=...)` on the ABI emulator: raw camera
+    images and points in, decoded boxes out (the call scripts/bench_full_forward.py times on the GPU)."""
+    import abi_emulator
+    import synth
+    import isfusion_b200.head as H
+    import isfusion_b200.img_neck as N
+    from __graft_entry__ import make_full_net
+    abi_emulator.install(monkeypatch)
+    monkeypatch.setattr(H, '_conv', abi_emulator._conv_cpu)
+    monkeypatch.setattr(N, '_conv', abi_emulator._conv_cpu)
+    net = make_full_net(0).eval()
+    assert net.img_backbone is not None and net.img_neck is not None and net.pts_neck is not None and net.pts_bbox_head is not None
+    pts = [synth.make_points(3000, 'S', 0)]
+    l2i, aug, laug = synth.make_calib(1, img_hw=(64, 96))
+    img = torch.randn(1, 6, 3, 64, 96, generator=torch.Generator().manual_seed(0)).half()
+    metas = [dict()]
+    res = net.simple_test(pts, metas, img=img, lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    assert metas[0]['input_shape'] == (64, 96)
+    box = res[0]['pts_bbox']
+    assert box['boxes_3d'].shape == (200, 9) and box['scores_3d'].shape == (200,) and box['labels_3d'].shape == (200,)
+    assert torch.isfinite(box['boxes_3d'].float()).all() and torch.isfinite(box['scores_3d'].float()).all()
+    assert int(box['labels_3d'].min()) >= 0 and int(box['labels_3d'].max()) < 10
