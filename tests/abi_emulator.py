@@ -589,6 +589,27 @@ def _conv_cpu(x_nhwc, packed, stride=1, relu=True):
     return (torch.relu(y) if relu else y).permute(0, 2, 3, 1).half().contiguous()
 
 
+def _ptr_checked(t):
+    """L.ptr on the emulator hands the tensor itself over.  A raw pointer carries no strides, so what the kernel would read
+    equals what the emulated entry point reads only if the tensor is dense along its last dimension and its leading
+    dimensions are either contiguous or a plain row-strided 2-D view (the `ld*` arguments of the ABI describe exactly that)."""
+    if t is None or t.numel() <= 1:
+        return t
+    assert t.stride(-1) == 1 or t.size(-1) == 1, 'pointer to a tensor with a strided last dimension: %s / %s' % (tuple(t.shape), t.stride())
+    if not t.is_contiguous():
+        lead = t.reshape(-1, t.size(-1)) if t.dim() != 2 else t          # reshape of a non-collapsible view would copy:
+        assert lead.data_ptr() == t.data_ptr(), 'pointer to a view that is not row-strided: %s / %s' % (tuple(t.shape), t.stride())
+    return t
+
+
+def _require_contiguous(*tensors):
+    """L.require_cuda minus the device test: the contiguity contract still holds on the emulator."""
+    import isfusion_b200._lib as L
+    for t in tensors:
+        if t is not None and not t.is_contiguous():
+            raise L.IsfError('expected a contiguous tensor')
+
+
 ORIGINAL_CONV = None      # fusion_encoder._conv as shipped (set by install; lets a test re-enable it for the own-conv path)
 
 
@@ -600,10 +621,10 @@ def install(monkeypatch):
     ORIGINAL_CONV = FE._conv
     fake = FakeLib(L.lib())
     monkeypatch.setattr(L, 'lib', lambda: fake)
-    monkeypatch.setattr(L, 'ptr', lambda t: t)
+    monkeypatch.setattr(L, 'ptr', _ptr_checked)
     monkeypatch.setattr(L, 'stream', lambda: None)
     monkeypatch.setattr(L, 'check', lambda rc: None if rc == 0 else (_ for _ in ()).throw(L.IsfError('emulator rc %r' % (rc,))))
-    monkeypatch.setattr(L, 'require_cuda', lambda *a: None)
+    monkeypatch.setattr(L, 'require_cuda', _require_contiguous)
     monkeypatch.setattr(L, 'is_device', lambda t: True)
     monkeypatch.setattr(L, 'workspace', lambda nbytes, device: torch.empty(max(int(nbytes), 1), dtype=torch.uint8))
     monkeypatch.setattr(FE, '_conv', _conv_cpu)

@@ -106,3 +106,20 @@ def test_emulator_signatures_match_the_header():
         assert name in decl, name + ' is emulated but not declared in the header'
         n_emul = len(inspect.signature(getattr(abi_emulator.FakeLib, name)).parameters) - 1      # minus self
         assert n_emul == decl[name], (name, n_emul, decl[name])
+
+
+def test_emulator_pointer_contract_rejects_strided_views():
+    """the emulator hands tensors where the product passes raw pointers: views a pointer cannot describe are refused, so a
+    CPU run of the product code cannot pass with an argument the CUDA library would misread."""
+    import pytest
+    import torch
+    import abi_emulator as E
+    x = torch.zeros(6, 8)
+    assert E._ptr_checked(x) is x and E._ptr_checked(x[:, :4]) is not None and E._ptr_checked(None) is None
+    assert E._ptr_checked(x[2:5]) is not None                       # row slice: still one dense block
+    with pytest.raises(AssertionError):
+        E._ptr_checked(x.t())                                       # strided last dimension
+    with pytest.raises(AssertionError):
+        E._ptr_checked(torch.zeros(2, 3, 4, 8)[:, :, :2, :])        # 4-D view that is not row-strided
+    with pytest.raises(Exception):
+        E._require_contiguous(x[:, :4])
