@@ -31,6 +31,11 @@ def _header_params():
     return out
 
 
+_ELEM = {'float': (torch.float32,), 'int': (torch.int32,), 'unsigned int': (torch.int32, torch.uint32),
+         'long long': (torch.int64,), 'unsigned long long': (torch.int64, torch.uint64), 'unsigned char': (torch.uint8,)}
+_CELEM = {'float': (ctypes.c_float,), 'int': (ctypes.c_int,), 'long long': (ctypes.c_longlong,)}
+
+
 def _check_kinds(name, ctypes_of, args):
     """every argument must be of the KIND the header declares: a pointer gets a tensor / ctypes array / byref / None,
     an integer an int, a float a (ctypes) float — catches swapped or shifted arguments that ctypes itself would accept."""
@@ -40,6 +45,11 @@ def _check_kinds(name, ctypes_of, args):
             or isinstance(a, ctypes.c_void_p)
         if is_ptr:
             assert ok_ptr, '%s: argument %d (%s) got %r' % (name, i, ct, type(a))
+            base = ct.replace('const', '').replace('*', '').strip()
+            if isinstance(a, torch.Tensor) and base in _ELEM:            # typed pointer: the tensor's element type must be it
+                assert a.dtype in _ELEM[base], '%s: argument %d is %s but the tensor holds %s' % (name, i, ct, a.dtype)
+            elif isinstance(a, ctypes.Array) and base in _CELEM:
+                assert a._type_ in _CELEM[base], '%s: argument %d is %s but the host array holds %s' % (name, i, ct, a._type_)
         elif ct in ('float', 'double'):
             assert isinstance(a, (float, ctypes.c_float, ctypes.c_double)), '%s: argument %d (%s) got %r' % (name, i, ct, type(a))
         else:
