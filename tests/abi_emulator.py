@@ -19,6 +19,11 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'analysis'))      # tile_occupancy (order model)
 
 
+_PARAM_NAMES = {}
+# untyped (void*) data pointers are fp16 matrices unless listed here: scratch / opaque bytes, or either precision (flagged)
+_VOID_ANY = {'workspace', 'table', 'in_table', 'stream', 'value'}
+
+
 def _header_params():
     """{entry point: [C type of every parameter]} parsed from include/isfusion_b200.h."""
     import re
@@ -28,6 +33,7 @@ def _header_params():
     for m in re.finditer(r'\b(?:int|long long|unsigned long long|const char\*)\s+(isf_\w+)\s*\(([^;]*?)\)\s*;', hdr, flags=re.S):
         params = [p.strip() for p in m.group(2).split(',')] if m.group(2).strip() not in ('', 'void') else []
         out[m.group(1)] = [re.sub(r'\s*\w+$', '', p) for p in params]          # drop the parameter name
+        _PARAM_NAMES[m.group(1)] = [re.search(r'(\w+)$', p).group(1) for p in params]
     return out
 
 
@@ -48,6 +54,9 @@ def _check_kinds(name, ctypes_of, args):
             base = ct.replace('const', '').replace('*', '').strip()
             if isinstance(a, torch.Tensor) and base in _ELEM:            # typed pointer: the tensor's element type must be it
                 assert a.dtype in _ELEM[base], '%s: argument %d is %s but the tensor holds %s' % (name, i, ct, a.dtype)
+            elif isinstance(a, torch.Tensor) and base == 'void' and _PARAM_NAMES.get(name) and _PARAM_NAMES[name][i] not in _VOID_ANY:
+                assert a.dtype == torch.float16, '%s: %s is an fp16 matrix in the library but the tensor holds %s' % (
+                    name, _PARAM_NAMES[name][i], a.dtype)
             elif isinstance(a, ctypes.Array) and base in _CELEM:
                 assert a._type_ in _CELEM[base], '%s: argument %d is %s but the host array holds %s' % (name, i, ct, a._type_)
         elif ct in ('float', 'double'):
