@@ -13,7 +13,6 @@ are torch ops by default; `ISF_SWIN_ATTN=own` replaces the whole pad / roll / pa
 reference's padding, cyclic shift, region mask and crop as closed forms of (window, slot) — checked on the host against the
 reference's index sequence), which also lets the `proj` GEMM add the residual in its epilogue.
 Eval mode only (DropPath / dropout are the identity); activations are fp16 token matrices [B, L, C]."""
-import ctypes
 import os
 
 import torch

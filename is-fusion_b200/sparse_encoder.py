@@ -10,7 +10,7 @@ from torch import nn
 
 from . import _lib as L
 from .registry import MIDDLE_ENCODERS, build_conv_layer, build_norm_layer
-from .spconv import SparseConvTensor, SparseModule, SparseSequential, SubMConv3d, fold_bn
+from .spconv import SparseConvTensor, SparseModule, SparseSequential, fold_bn
 
 
 class SparseBasicBlock(SparseModule):
