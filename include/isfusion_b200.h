@@ -104,6 +104,25 @@ int isf_dynamic_point_to_voxel_backward(float* grad_feats, const float* grad_red
                                         int num_reduced, int c, int reduce_type, void* workspace, size_t ws_bytes,
                                         void* stream);
 
+/* ---- input contract: multi-sweep merge --------------------------
+ * replaces the per-sweep numpy work of LoadPointsFromMultiSweeps.__call__
+ *   (mmdet3d/datasets/pipelines/loading.py:846-906; _remove_close :824-844).
+ * raw [m, load_dim] fp32 on the DEVICE (load_dim >= 5) = key frame followed by the sweeps, copied in one piece;
+ * the segment tables are HOST arrays (num_segments <= 24): seg_start [S+1] row offsets (seg_start[0] = 0,
+ * seg_start[S] = m), rot [S,3,3] / trans [S,3] = sensor2lidar_rotation / _translation (float64, read only where
+ * seg_flags bit 0 is set), lag [S] = value of column 4 (ts - sweep_ts, 0 for the key frame), seg_flags [S]: bit 0 =
+ * rotate + translate, bit 1 = drop points with |x| < radius and |y| < radius (tested on the raw coordinates).
+ * out [m, 5] fp32 (capacity m rows, input order kept), *count_dev = rows written.  float64 arithmetic rounded to
+ * float32 after the rotation and after the translation, as numpy does on the reference's float32 arrays. */
+int isf_merge_sweeps_workspace_size(int m, size_t* bytes);
+int isf_merge_sweeps(const float* raw, int m, int load_dim, int num_segments, const int* seg_start, const double* rot,
+                     const double* trans, const double* lag, const int* seg_flags, float radius, float* out,
+                     int* count_dev, void* workspace, size_t ws_bytes, void* stream);
+/* TEST HOOK: the kernels' own per-point source (shared host/device) on HOST memory; *count = rows written. */
+int isf_debug_merge_sweeps_host(const float* raw, int m, int load_dim, int num_segments, const int* seg_start,
+                                const double* rot, const double* trans, const double* lag, const int* seg_flags,
+                                float radius, float* out, int* count);
+
 /* ---- K7: rank inside a group --------------------------------------------------
  * replaces ingroup_indices.forward(group_inds, out_inds)
  *   mmdet3d/ops/TorchEx/torchex/src/ingroup_inds/ingroup_inds.cpp:28-54, kernel :17-30.

@@ -392,6 +392,166 @@ extern "C" int isf_dynamic_point_to_voxel_backward(float* grad_feats, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Input contract: multi-sweep merge on the device
+//   replaces the per-sweep numpy work of LoadPointsFromMultiSweeps.__call__ (mmdet3d/datasets/pipelines/loading.py:
+//   846-906, _remove_close :824-844): the raw key frame + sweeps arrive as ONE [M, load_dim] fp32 block (one H2D copy from
+//   pinned memory); per segment (key frame / sweep) an optional "remove points with |x| < r and |y| < r", the rigid
+//   transform into the key frame's LiDAR frame and the time-lag column.  Arithmetic as numpy does it: float32 points,
+//   float64 calibration, x' = fl32(sum_j p_j R_ij) then fl32(x' + t_i); column 4 = fl32(lag).  Row order is preserved
+//   (hard voxelization keeps the FIRST 12 points of a pillar): stable compaction = flags -> exclusive scan -> scatter.
+// ------------------------------------------------------------------------------------------------
+constexpr int MERGE_MAX_SEGMENTS = 24;
+struct MergeTable {
+  int n;
+  int start[MERGE_MAX_SEGMENTS + 1];
+  int flags[MERGE_MAX_SEGMENTS];          // bit 0: rotate + translate, bit 1: remove close points
+  double rot[MERGE_MAX_SEGMENTS][9];      // sensor2lidar_rotation, row-major
+  double trans[MERGE_MAX_SEGMENTS][3];
+  double lag[MERGE_MAX_SEGMENTS];
+  float radius;
+};
+
+__host__ __device__ __forceinline__ int merge_segment_of(const MergeTable& T, int row) {
+  int s = 0;
+  while (s + 1 < T.n && row >= T.start[s + 1]) ++s;
+  return s;
+}
+
+__host__ __device__ __forceinline__ bool merge_keeps(const MergeTable& T, int s, const float* p) {
+  if (!(T.flags[s] & 2)) return true;
+  return !(fabsf(p[0]) < T.radius && fabsf(p[1]) < T.radius);
+}
+
+// one point of segment s: in = raw row (>= 5 columns), out = 5 columns
+__host__ __device__ __forceinline__ void merge_point(const MergeTable& T, int s, const float* in, float* out) {
+  float x = in[0], y = in[1], z = in[2];
+  if (T.flags[s] & 1) {
+    const double* R = T.rot[s];
+    const double px = (double)x, py = (double)y, pz = (double)z;
+    // the row-times-R^T product in float64, accumulated in column order like the BLAS kernel numpy calls
+    const float rx = (float)fma(pz, R[2], fma(py, R[1], px * R[0]));
+    const float ry = (float)fma(pz, R[5], fma(py, R[4], px * R[3]));
+    const float rz = (float)fma(pz, R[8], fma(py, R[7], px * R[6]));
+    x = (float)((double)rx + T.trans[s][0]);
+    y = (float)((double)ry + T.trans[s][1]);
+    z = (float)((double)rz + T.trans[s][2]);
+  }
+  out[0] = x; out[1] = y; out[2] = z; out[3] = in[3]; out[4] = (float)T.lag[s];
+}
+
+__global__ void __launch_bounds__(256) merge_flags_kernel(const float* __restrict__ raw, int m, int load_dim,
+                                                          const __grid_constant__ MergeTable T, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  flags[i] = merge_keeps(T, merge_segment_of(T, i), raw + (size_t)i * load_dim) ? 1 : 0;
+}
+
+// pos == nullptr: no segment removes points (out row = in row)
+__global__ void __launch_bounds__(256) merge_write_kernel(const float* __restrict__ raw, int m, int load_dim,
+                                                          const __grid_constant__ MergeTable T, const int* __restrict__ flags,
+                                                          const int* __restrict__ pos, float* __restrict__ out,
+                                                          int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const bool keep = pos ? flags[i] != 0 : true;
+  const int o = pos ? pos[i] : i;
+  if (i == m - 1 && count) *count = o + (keep ? 1 : 0);
+  if (!keep) return;
+  float v[5];
+  merge_point(T, merge_segment_of(T, i), raw + (size_t)i * load_dim, v);
+#pragma unroll
+  for (int c = 0; c < 5; ++c) out[(size_t)o * 5 + c] = v[c];
+}
+
+static int merge_fill_table(MergeTable* T, int m, int num_segments, const int* seg_start, const double* rot,
+                            const double* trans, const double* lag, const int* seg_flags, float radius, bool* any_remove) {
+  ISF_CHECK_ARG(num_segments >= 1 && num_segments <= MERGE_MAX_SEGMENTS && seg_start && seg_flags && lag);
+  ISF_CHECK_ARG(seg_start[0] == 0 && seg_start[num_segments] == m);
+  T->n = num_segments;
+  T->radius = radius;
+  *any_remove = false;
+  for (int s = 0; s < num_segments; ++s) {
+    ISF_CHECK_ARG(seg_start[s + 1] >= seg_start[s]);
+    T->start[s] = seg_start[s];
+    T->flags[s] = seg_flags[s] & 3;
+    T->lag[s] = lag[s];
+    if (seg_flags[s] & 2) *any_remove = true;
+    if (seg_flags[s] & 1) {
+      ISF_CHECK_ARG(rot && trans);
+      for (int e = 0; e < 9; ++e) T->rot[s][e] = rot[s * 9 + e];
+      for (int e = 0; e < 3; ++e) T->trans[s][e] = trans[s * 3 + e];
+    }
+  }
+  T->start[num_segments] = m;
+  return ISF_OK;
+}
+
+extern "C" int isf_merge_sweeps_workspace_size(int m, size_t* bytes) {
+  ISF_CHECK_ARG(bytes && m >= 0);
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, m > 0 ? m : 1);
+  *bytes = 2 * ((size_t)(m > 0 ? m : 1) * sizeof(int) + 256) + cub_bytes + 256;
+  return ISF_OK;
+}
+
+// raw [m, load_dim] fp32 (load_dim >= 5; DEVICE), segment tables on the HOST (<= 24 segments: key frame + sweeps),
+// out [m, 5] fp32 (capacity m rows), *count_dev = rows written.  seg_flags: bit 0 = transform, bit 1 = remove close.
+extern "C" int isf_merge_sweeps(const float* raw, int m, int load_dim, int num_segments, const int* seg_start,
+                                const double* rot, const double* trans, const double* lag, const int* seg_flags, float radius,
+                                float* out, int* count_dev, void* workspace, size_t ws_bytes, void* stream) {
+  ISF_CHECK_ARG(m >= 0 && load_dim >= 5 && count_dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0) { ISF_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int), st)); return ISF_OK; }
+  ISF_CHECK_ARG(raw && out);
+  MergeTable T;
+  bool any_remove = false;
+  int rc = merge_fill_table(&T, m, num_segments, seg_start, rot, trans, lag, seg_flags, radius, &any_remove);
+  if (rc) return rc;
+  const int blocks = isf_cdiv(m, 256);
+  if (!any_remove) {
+    merge_write_kernel<<<blocks, 256, 0, st>>>(raw, m, load_dim, T, nullptr, nullptr, out, count_dev);
+    isf_count_launch(1);
+  } else {
+    IsfArena A(workspace, ws_bytes);
+    int* flags = A.take<int>(m);
+    int* pos = A.take<int>(m);
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, m);
+    char* tmp = A.take<char>(cub_bytes);
+    if (!A.ok || !workspace) { isf_set_error("merge_sweeps: workspace too small"); return ISF_ERR_WORKSPACE; }
+    merge_flags_kernel<<<blocks, 256, 0, st>>>(raw, m, load_dim, T, flags);
+    ISF_CUDA(cub::DeviceScan::ExclusiveSum(tmp, cub_bytes, flags, pos, m, st));
+    merge_write_kernel<<<blocks, 256, 0, st>>>(raw, m, load_dim, T, flags, pos, out, count_dev);
+    isf_count_launch(4);
+  }
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}
+
+// TEST HOOK (host memory, no GPU): merge_segment_of / merge_keeps / merge_point — the kernels' own source — on the CPU.
+extern "C" int isf_debug_merge_sweeps_host(const float* raw, int m, int load_dim, int num_segments, const int* seg_start,
+                                           const double* rot, const double* trans, const double* lag, const int* seg_flags,
+                                           float radius, float* out, int* count) {
+  ISF_CHECK_ARG(m >= 0 && load_dim >= 5 && count && (m == 0 || (raw && out)));
+  *count = 0;
+  if (m == 0) return ISF_OK;
+  MergeTable T;
+  bool any_remove = false;
+  int rc = merge_fill_table(&T, m, num_segments, seg_start, rot, trans, lag, seg_flags, radius, &any_remove);
+  if (rc) return rc;
+  int o = 0;
+  for (int i = 0; i < m; ++i) {
+    const int s = merge_segment_of(T, i);
+    const float* p = raw + (size_t)i * load_dim;
+    if (!merge_keeps(T, s, p)) continue;
+    merge_point(T, s, p, out + (size_t)o * 5);
+    ++o;
+  }
+  *count = o;
+  return ISF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7: ingroup indices  (TorchEx/.../ingroup_inds_kernel.cu:17-30: rank of each element inside its
 // group; the reference hands ranks out in atomic arrival order, here rank = stable index order)
 // ------------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ MODELS = Registry('models')
 BACKBONES = NECKS = VOXEL_ENCODERS = MIDDLE_ENCODERS = FUSION_LAYERS = DETECTORS = MODELS
 NORM_LAYERS = Registry('norm')
 CONV_LAYERS = Registry('conv')
+PIPELINES = Registry('pipeline')        # mmdet.datasets.builder.PIPELINES (data-loading transforms of the input contract)
 
 NORM_LAYERS.register_module('BN', module=nn.BatchNorm2d)
 NORM_LAYERS.register_module('BN1d', module=nn.BatchNorm1d)

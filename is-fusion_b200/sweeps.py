@@ -1,0 +1,105 @@
+"""Input contract of the path: multi-sweep point loading with the merge on the device.
+
+Mirrors the reference's `LoadPointsFromMultiSweeps` (mmdet3d/datasets/pipelines/loading.py:735-911: same constructor
+arguments, same `results` keys, same sweep selection), but where the reference rotates / translates / filters every sweep
+with numpy on the host and concatenates, this module gathers the raw key frame + sweeps into ONE pinned host block, copies
+it once and lets `isf_merge_sweeps` (csrc/voxel.cu) do the per-sweep work on the GPU: `results['points']` is the device
+tensor [N, len(use_dim)] the detector consumes (the reference wraps the same values in a LiDARPoints object).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .registry import PIPELINES
+
+
+def merge_sweeps(raw, seg_start, seg_flags, lag, rot=None, trans=None, radius=1.0, load_dim=5):
+    """raw [M, load_dim] fp32 DEVICE tensor (key frame + sweeps, in order); seg_start [S+1] row offsets; seg_flags [S]
+    (bit 0: transform, bit 1: remove close); lag [S] seconds; rot [S,3,3] / trans [S,3] float64 (host).  Returns
+    (points [M, 5] fp32 with capacity M rows, count [1] int32 device = rows valid)."""
+    L.require_cuda(raw)
+    if raw.dtype != torch.float32 or raw.dim() != 2 or raw.size(1) != load_dim:
+        raise L.IsfError('merge_sweeps: raw must be float32 [M, load_dim]')
+    m, s = raw.size(0), len(seg_flags)
+    out = torch.empty((m, 5), dtype=torch.float32, device=raw.device)
+    count = torch.zeros(1, dtype=torch.int32, device=raw.device)
+    wsb = ctypes.c_size_t(0)
+    L.check(L.lib().isf_merge_sweeps_workspace_size(m, ctypes.byref(wsb)))
+    ws = L.workspace(wsb.value, raw.device)
+    rot = np.zeros((s, 3, 3)) if rot is None else np.ascontiguousarray(rot, dtype=np.float64).reshape(s, 3, 3)
+    trans = np.zeros((s, 3)) if trans is None else np.ascontiguousarray(trans, dtype=np.float64).reshape(s, 3)
+    dbl = lambda a: (ctypes.c_double * a.size)(*[float(v) for v in a.reshape(-1)])
+    L.check(L.lib().isf_merge_sweeps(
+        L.ptr(raw), m, load_dim, s, L.host_i32(seg_start), dbl(rot), dbl(trans), dbl(np.asarray(lag, dtype=np.float64)),
+        L.host_i32(seg_flags), ctypes.c_float(radius), L.ptr(out), L.ptr(count), L.ptr(ws), ctypes.c_size_t(ws.numel()),
+        L.stream()))
+    return out, count
+
+
+@PIPELINES.register_module()
+class LoadPointsFromMultiSweeps(object):
+    """ref: loading.py:735-911.  `results['points']` = key-frame points (numpy [N0, load_dim] / tensor / an object with
+    `.tensor`), `results['timestamp']`, `results['sweeps']` = list of dict(data_path | points, timestamp,
+    sensor2lidar_rotation, sensor2lidar_translation).  A sweep dict may carry its raw `points` array instead of a file."""
+
+    def __init__(self, sweeps_num=10, load_dim=5, use_dim=[0, 1, 2, 4], file_client_args=dict(backend='disk'),
+                 pad_empty_sweeps=False, remove_close=False, test_mode=False, painting=False, device='cuda'):
+        if painting:
+            raise NotImplementedError('LoadPointsFromMultiSweeps: painting is outside the path')
+        self.load_dim, self.sweeps_num, self.use_dim = load_dim, sweeps_num, list(use_dim)
+        self.pad_empty_sweeps, self.remove_close, self.test_mode = pad_empty_sweeps, remove_close, test_mode
+        self.device = device
+
+    def _load_points(self, sweep):
+        if 'points' in sweep:
+            return np.asarray(sweep['points'], dtype=np.float32)
+        path = sweep['data_path']
+        return np.load(path) if path.endswith('.npy') else np.fromfile(path, dtype=np.float32)      # loading.py:778-798
+
+    def plan(self, results):
+        """host side: which sweeps, as segments of one raw block -> (blocks, seg_start, seg_flags, lag, rot, trans)."""
+        key = results['points']
+        key = key.tensor if hasattr(key, 'tensor') else key
+        key = key.cpu().numpy() if isinstance(key, torch.Tensor) else np.asarray(key)
+        key = np.ascontiguousarray(key, dtype=np.float32).reshape(-1, self.load_dim)
+        ts = results['timestamp']
+        blocks, flags, lag, rot, trans = [key], [0], [0.0], [np.eye(3)], [np.zeros(3)]
+        sweeps = results['sweeps']
+        if self.pad_empty_sweeps and len(sweeps) == 0:                              # loading.py:865-870
+            for _ in range(self.sweeps_num):
+                blocks.append(key); flags.append(2 if self.remove_close else 0); lag.append(0.0)
+                rot.append(np.eye(3)); trans.append(np.zeros(3))
+        else:
+            if len(sweeps) <= self.sweeps_num:                                      # loading.py:872-878
+                choices = np.arange(len(sweeps))
+            elif self.test_mode:
+                choices = np.arange(self.sweeps_num)
+            else:
+                choices = np.random.choice(len(sweeps), self.sweeps_num, replace=False)
+            for idx in choices:
+                sweep = sweeps[idx]
+                blocks.append(self._load_points(sweep).reshape(-1, self.load_dim))
+                flags.append(1 | (2 if self.remove_close else 0))
+                lag.append(ts - sweep['timestamp'] / 1e6)
+                rot.append(np.asarray(sweep['sensor2lidar_rotation'], dtype=np.float64))
+                trans.append(np.asarray(sweep['sensor2lidar_translation'], dtype=np.float64))
+        seg_start = np.concatenate([[0], np.cumsum([b.shape[0] for b in blocks])]).astype(np.int64)
+        return blocks, seg_start, flags, lag, np.stack(rot), np.stack(trans)
+
+    def __call__(self, results):
+        blocks, seg_start, flags, lag, rot, trans = self.plan(results)
+        m = int(seg_start[-1])
+        host = torch.empty((m, self.load_dim), dtype=torch.float32)
+        if self.device != 'cpu' and torch.cuda.is_available():
+            host = host.pin_memory()
+        np.concatenate(blocks, 0, out=host.numpy())
+        raw = host.to(self.device, non_blocking=True)
+        pts, count = merge_sweeps(raw, seg_start, flags, lag, rot, trans, radius=1.0, load_dim=self.load_dim)
+        n = m if not self.remove_close else int(count.item())        # only the filter makes the size data dependent
+        results['points'] = pts[:n][:, self.use_dim]
+        return results
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}(sweeps_num={self.sweeps_num})'

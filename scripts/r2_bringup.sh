@@ -31,6 +31,8 @@ step "configs[4] geometry (0.05 m voxels, 256x256 BEV)"
 t 300 python -m pytest tests/test_config5_gpu.py -x -q -m gpu            >> $LOG 2>&1
 step "size-independent properties at the full-frame sizes (storage-order invariance, identity, scaling, output sites)"
 t 400 python -m pytest tests/test_properties.py -x -q -m gpu             >> $LOG 2>&1
+step "input contract: multi-sweep merge kernels"
+t 200 python -m pytest tests/test_input_contract.py -x -q -m gpu        >> $LOG 2>&1
 step "backward kernels (dynamic scatter K3b, deformable attention K9b)"
 t 300 python -m pytest tests/test_backward_ops.py -x -q -m gpu           >> $LOG 2>&1
 step "own dense 3x3 convs on the implicit-GEMM kernel"

@@ -39,7 +39,7 @@ def _header_params():
 
 _ELEM = {'float': (torch.float32,), 'int': (torch.int32,), 'unsigned int': (torch.int32, torch.uint32),
          'long long': (torch.int64,), 'unsigned long long': (torch.int64, torch.uint64), 'unsigned char': (torch.uint8,)}
-_CELEM = {'float': (ctypes.c_float,), 'int': (ctypes.c_int,), 'long long': (ctypes.c_longlong,)}
+_CELEM = {'float': (ctypes.c_float,), 'int': (ctypes.c_int,), 'long long': (ctypes.c_longlong,), 'double': (ctypes.c_double,)}
 
 
 def _check_kinds(name, ctypes_of, args):
@@ -448,6 +448,31 @@ class VoxelMixin:
         grad_feats.copy_(vo.dynamic_scatter_backward(grad_reduced, feats, reduced, cmap, count, {0: 'sum', 1: 'mean', 2: 'max'}[reduce_type]))
         return 0
 
+    def isf_merge_sweeps_workspace_size(self, m, bytes_ref):
+        _set_size(bytes_ref, 256)
+        return 0
+
+    def isf_merge_sweeps(self, raw, m, load_dim, nseg, seg_start, rot, trans, lag, seg_flags, radius, out, count, ws, ws_bytes, stream):
+        from oracle import input_ops
+        import numpy as np
+        r = raw.numpy()
+        R = np.array(list(rot), dtype=np.float64).reshape(nseg, 3, 3)
+        t = np.array(list(trans), dtype=np.float64).reshape(nseg, 3)
+        parts = []
+        for s in range(nseg):
+            ps = np.copy(r[seg_start[s]:seg_start[s + 1]])
+            if seg_flags[s] & 2:
+                ps = input_ops.remove_close(ps, _val(radius))
+            if seg_flags[s] & 1:                               # the three numpy statements of loading.py:886-888
+                ps[:, :3] = ps[:, :3] @ R[s].T
+                ps[:, :3] += t[s]
+            ps[:, 4] = lag[s]
+            parts.append(ps[:, :5])
+        res = np.concatenate(parts, 0)
+        out[:res.shape[0]].copy_(torch.from_numpy(res))
+        count.fill_(res.shape[0])
+        return 0
+
     def isf_ingroup_indices(self, group_inds, n, key_bits, out_inds, ws, ws_bytes, stream):
         g = group_inds[:n]
         order = torch.argsort(g, stable=True)
@@ -575,7 +600,7 @@ class RowsAroundMixin:
 
 class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):
     _KINDS = None
-    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_debug_msda_backward_host',
+    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_debug_msda_backward_host', 'isf_debug_merge_sweeps_host',
                  'isf_version')
 
     def __init__(self, real=None):

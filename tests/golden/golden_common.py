@@ -236,3 +236,29 @@ def sparse_inputs(seed=0, v=1400, bs=2):
     full = full[np.lexsort((full[:, 3], full[:, 2], full[:, 1], full[:, 0]))]
     feats = torch.relu(rand('sparse_feats', (len(full), 64), seed))
     return feats, torch.from_numpy(full).int()
+
+
+# ---------------------------------------------------------------------- input contract: multi-sweep loading
+def sweep_inputs(seed=12, n_key=2000, n_sweeps=10, n_sweep=1500):
+    """(key_points [N0,5] f32, ts seconds, sweeps): synthetic nuScenes-shaped sweeps — ego motion of a few metres, yaw of a few
+    degrees, 50 ms apart, a blob of returns on the ego vehicle itself (|x|,|y| < 1 m: what remove_close drops)."""
+    rs = np.random.RandomState(seed)
+
+    def cloud(n):
+        p = np.empty((n, 5), np.float32)
+        p[:, :2] = rs.uniform(-50, 50, (n, 2))
+        p[:, 2] = rs.uniform(-4, 2, n)
+        p[: n // 20, :2] = rs.uniform(-1.5, 1.5, (n // 20, 2))        # returns on / next to the ego vehicle
+        p[:, 3] = rs.uniform(0, 255, n)
+        p[:, 4] = rs.uniform(0, 31, n)                                # ring index in the raw file; overwritten by the time lag
+        return p
+
+    ts = 1533151603.547590
+    sweeps = []
+    for i in range(n_sweeps):
+        yaw, pitch = np.deg2rad(rs.uniform(-4, 4)), np.deg2rad(rs.uniform(-0.5, 0.5))
+        cz, sz, cy, sy = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+        rot = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        sweeps.append(dict(points=cloud(n_sweep), timestamp=(ts - 0.05 * (i + 1)) * 1e6 + rs.uniform(-2e3, 2e3),
+                           sensor2lidar_rotation=rot, sensor2lidar_translation=rs.uniform(-3, 3, 3) * np.array([1, 1, 0.05])))
+    return cloud(n_key), ts, sweeps

@@ -184,9 +184,33 @@ def head(R):
     print('head:', {k: v.shape for k, v in out.items() if k != 'keys'})
 
 
+def sweeps(R):
+    """the reference's LoadPointsFromFile + LoadPointsFromMultiSweeps on synthetic sweep files written to a temp dir."""
+    import tempfile
+    R = ref_shim.install_loading()
+    key, ts, sw = gc.sweep_inputs()
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        key.tofile(os.path.join(d, 'key.bin'))
+        infos = []
+        for i, s in enumerate(sw):
+            path = os.path.join(d, 'sweep%d.bin' % i)
+            s['points'].tofile(path)
+            infos.append(dict(data_path=path, timestamp=s['timestamp'], sensor2lidar_rotation=s['sensor2lidar_rotation'],
+                              sensor2lidar_translation=s['sensor2lidar_translation']))
+        for tag, kw, n_sw in (('plain', dict(), 10), ('close', dict(remove_close=True), 10), ('test3', dict(test_mode=True, sweeps_num=3), 10),
+                              ('pad', dict(pad_empty_sweeps=True, remove_close=True, sweeps_num=2), 0)):
+            res = dict(pts_filename=os.path.join(d, 'key.bin'), timestamp=ts, sweeps=infos[:n_sw])
+            res = R.LoadPointsFromFile(coord_type='LIDAR', load_dim=5, use_dim=5)(res)
+            res = R.LoadPointsFromMultiSweeps(use_dim=[0, 1, 2, 3, 4], **kw)(res)
+            out[tag] = res['points'].tensor.numpy()
+            print('sweeps', tag, out[tag].shape)
+    np.savez_compressed(os.path.join(HERE, 'ref_sweeps.npz'), **out)
+
+
 if __name__ == '__main__':
     R = ref_shim.install()
-    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head', 'lss', 'swin']
+    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head', 'lss', 'swin', 'sweeps']
     for w in which:
         globals()[w](R)
     for f in sorted(os.listdir(HERE)):

@@ -669,3 +669,51 @@ if __name__ == '__main__':
     ns = install_head()
     print('reference classes loaded:', [k for k in vars(ns)])
     print(inspect.getsourcefile(ns.ISFusionEncoder))
+
+
+_loading_installed = False
+
+
+def install_loading():
+    """SURVEY §8f rank 3 (input contract): load the reference's point loaders (datasets/pipelines/loading.py) with its own
+    point classes (core/points/*.py).  Stand-ins: mmcv.FileClient = plain disk reads, the mmdet PIPELINES registry, and the
+    two mmdet loader base classes the file imports but this path never builds."""
+    global _loading_installed
+    ns = install()
+    m = sys.modules
+    if not _loading_installed:
+        class _FileClient:
+            def __init__(self, backend='disk', **kw):
+                assert backend == 'disk'
+
+            def get(self, path):
+                with open(path, 'rb') as f:
+                    return f.read()
+
+        mm = m['mmcv']
+        mm.FileClient = _FileClient
+        mm.check_file_exist = lambda p: None
+        _pkg('mmdet.datasets')
+        _mod('mmdet.datasets.builder', PIPELINES=Registry('pipeline'))
+        _mod('mmdet.datasets.pipelines', LoadAnnotations=type('LoadAnnotations', (), {}),
+             LoadImageFromFile=type('LoadImageFromFile', (), {}))
+        core = m.get('mmdet3d.core') or _pkg('mmdet3d.core')
+        if not hasattr(core, '__path__'):
+            core.__path__ = []
+        pts = _pkg('mmdet3d.core.points')
+        for leaf in ('base_points', 'cam_points', 'depth_points', 'lidar_points'):
+            _load_ref('mmdet3d.core.points.' + leaf, 'mmdet3d/core/points/%s.py' % leaf)
+        # what core/points/__init__.py exports (it is 30 lines of imports + this lookup)
+        pts.BasePoints = m['mmdet3d.core.points.base_points'].BasePoints
+        pts.LiDARPoints = m['mmdet3d.core.points.lidar_points'].LiDARPoints
+        pts.CameraPoints = m['mmdet3d.core.points.cam_points'].CameraPoints
+        pts.DepthPoints = m['mmdet3d.core.points.depth_points'].DepthPoints
+        pts.get_points_type = lambda t: {'CAMERA': pts.CameraPoints, 'LIDAR': pts.LiDARPoints, 'DEPTH': pts.DepthPoints}[t.upper()]
+        _pkg('mmdet3d.datasets')
+        _pkg('mmdet3d.datasets.pipelines')
+        _load_ref('mmdet3d.datasets.pipelines.loading', 'mmdet3d/datasets/pipelines/loading.py')
+        _loading_installed = True
+    mod = m['mmdet3d.datasets.pipelines.loading']
+    ns.LoadPointsFromFile = mod.LoadPointsFromFile
+    ns.LoadPointsFromMultiSweeps = mod.LoadPointsFromMultiSweeps
+    return ns

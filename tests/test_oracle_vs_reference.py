@@ -199,3 +199,17 @@ def test_swin_backbone_matches_reference():
     outs = net(gc.swin_input())
     for i, o in enumerate(outs):
         _close(o, g['out%d' % i], 'swin stage output %d' % (i + 1), 5e-4)
+
+
+@pytest.mark.parametrize('tag,kw,n_sw', [('plain', dict(), 10), ('close', dict(remove_close_pts=True), 10),
+                                         ('test3', dict(test_mode=True, sweeps_num=3), 10),
+                                         ('pad', dict(pad_empty_sweeps=True, remove_close_pts=True, sweeps_num=2), 0)])
+def test_multi_sweep_loading_matches_reference(tag, kw, n_sw):
+    """oracle/input_ops.py against the reference's LoadPointsFromFile + LoadPointsFromMultiSweeps
+    (loading.py:735-906) run on synthetic sweep files — bit-exact (same dtypes at every step)."""
+    from oracle import input_ops
+    g = np.load(os.path.join(HERE, 'golden', 'ref_sweeps.npz'))
+    key, ts, sweeps = gc.sweep_inputs()
+    got = input_ops.load_points_from_multi_sweeps(key, ts, sweeps[:n_sw], **kw)
+    assert got.dtype == np.float32 and got.shape == g[tag].shape
+    assert np.array_equal(got, g[tag])
