@@ -123,3 +123,33 @@ def test_emulator_pointer_contract_rejects_strided_views():
         E._ptr_checked(torch.zeros(2, 3, 4, 8)[:, :, :2, :])        # 4-D view that is not row-strided
     with pytest.raises(Exception):
         E._require_contiguous(x[:, :4])
+
+
+def test_backward_and_input_entry_points_validate_arguments():
+    """argument checks of the entry points added for the backward kernels and the input contract run before any CUDA call,
+    so they can be exercised here: bad arguments give ISF_ERR_ARG (1) and a message, never a crash."""
+    import isfusion_b200._lib as L
+    lib = L.lib()
+    n = ctypes.c_size_t(0)
+    assert lib.isf_dynamic_scatter_backward_workspace_size(1000, 64, ctypes.byref(n)) == 0 and n.value >= 1000 * 64 * 4
+    assert lib.isf_dynamic_scatter_backward_workspace_size(-1, 64, ctypes.byref(n)) == 1
+    assert lib.isf_dynamic_point_to_voxel_backward(None, None, None, None, None, None, 10, 5, 4, 3, None, ctypes.c_size_t(0), None) == 1   # reduce_type 3
+    assert lib.isf_dynamic_point_to_voxel_backward(None, None, None, None, None, None, 0, 0, 4, 2, None, ctypes.c_size_t(0), None) == 0    # empty input: no-op
+    assert lib.isf_dynamic_point_to_voxel_backward(None, None, None, None, None, None, 10, 5, 4, 2, None, ctypes.c_size_t(0), None) == 1   # null pointers
+    assert lib.isf_ms_deform_attn_backward(None, 0, None, None, None, None, None, 1, 4, 2, 2, 1, 2, 2, None, None, None, None) == 1
+    assert lib.isf_merge_sweeps_workspace_size(300000, ctypes.byref(n)) == 0 and n.value >= 2 * 300000 * 4
+    cnt = ctypes.c_int(0)
+    raw = (ctypes.c_float * 50)()
+    out = (ctypes.c_float * 50)()
+    one = (ctypes.c_double * 1)(0.0)
+    # segments must tile [0, m] exactly; at most 24 segments; load_dim >= 5
+    args = lambda start, nseg=1, load_dim=5: (raw, 10, load_dim, nseg, L.host_i32(start), None, None, one, L.host_i32([0] * max(nseg, 1)),
+                                               ctypes.c_float(1.0), out, ctypes.byref(cnt))
+    assert lib.isf_debug_merge_sweeps_host(*args([0, 10])) == 0 and cnt.value == 10
+    assert lib.isf_debug_merge_sweeps_host(*args([0, 9])) == 1
+    assert lib.isf_debug_merge_sweeps_host(*args([1, 10])) == 1
+    assert lib.isf_debug_merge_sweeps_host(*args([0, 10], load_dim=4)) == 1
+    assert lib.isf_debug_merge_sweeps_host(*args([0] * 26, nseg=25)) == 1
+    # a transforming segment needs its calibration
+    assert lib.isf_debug_merge_sweeps_host(raw, 10, 5, 1, L.host_i32([0, 10]), None, None, one, L.host_i32([1]), ctypes.c_float(1.0), out,
+                                           ctypes.byref(cnt)) == 1
