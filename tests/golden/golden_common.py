@@ -262,3 +262,25 @@ def sweep_inputs(seed=12, n_key=2000, n_sweeps=10, n_sweep=1500):
         sweeps.append(dict(points=cloud(n_sweep), timestamp=(ts - 0.05 * (i + 1)) * 1e6 + rs.uniform(-2e3, 2e3),
                            sensor2lidar_rotation=rot, sensor2lidar_translation=rs.uniform(-3, 3, 3) * np.array([1, 1, 0.05])))
     return cloud(n_key), ts, sweeps
+
+
+def camera_images(seed=13, n=2, hw=(225, 400)):
+    """synthetic uint8 camera frames (quarter-size nuScenes aspect 900x1600): smooth gradients + edges + noise, so that both
+    the clipping of the bicubic overshoot (0 / 255) and the rounding between the two resampling passes are exercised."""
+    rs = np.random.RandomState(seed)
+    h, w = hw
+    yy, xx = np.mgrid[0:h, 0:w]
+    out = []
+    for i in range(n):
+        base = 127 + 120 * np.sin(xx / (7.0 + i) + rs.uniform(0, 3)) * np.cos(yy / (5.0 + 2 * i))
+        img = np.stack([base, np.roll(base, 13, 1), 255 - base], -1)
+        img[h // 3:h // 3 + 20, w // 4:w // 2] = 255                     # saturated block: overshoot clips at 255 / 0 next to it
+        img[h // 2:h // 2 + 9, w // 2:w // 2 + 40] = 0
+        img = img + rs.normal(0, 12, img.shape)
+        out.append(np.clip(img, 0, 255).astype(np.uint8))
+    return out
+
+
+IMG_NORM = dict(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])                     # config:283-285
+IMG_AUG_TEST = dict(final_dim=(96, 264), resize_lim=[0.72, 0.72], bot_pct_lim=[0.0, 0.0], rot_lim=[0.0, 0.0], rand_flip=False,
+                    is_train=False)                                                          # config:321-327 at quarter size

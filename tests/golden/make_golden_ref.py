@@ -208,9 +208,36 @@ def sweeps(R):
     np.savez_compressed(os.path.join(HERE, 'ref_sweeps.npz'), **out)
 
 
+def images(R):
+    """the reference's ImageAug3D + ImageNormalize (transforms_3d.py:25-145, those lines executed unmodified; the rest of that
+    file needs numba / cv2 / box classes) on synthetic uint8 frames: test branch, and the train branch with seeded draws
+    (rot_lim = 0: PIL's rotate is outside the device path)."""
+    from PIL import Image
+    import torchvision
+    from typing import Any, Dict
+    src = open(os.path.join(ref_shim.REF, 'mmdet3d/datasets/pipelines/transforms_3d.py')).read().split('\n')
+    ns = dict(np=np, torch=torch, torchvision=torchvision, Image=Image, Any=Any, Dict=Dict, PIPELINES=ref_shim.Registry('pipeline'))
+    exec('\n'.join(src[23:145]), ns)
+    imgs = gc.camera_images()
+    out = {}
+    h, w = imgs[0].shape[:2]
+    for tag, cfg, seed in (('test', gc.IMG_AUG_TEST, None),
+                           ('train', dict(gc.IMG_AUG_TEST, resize_lim=[0.57, 0.825], rand_flip=True, is_train=True), 4),
+                           ('train2', dict(gc.IMG_AUG_TEST, resize_lim=[0.57, 0.825], rand_flip=True, is_train=True), 9)):
+        if seed is not None:
+            np.random.seed(seed)
+        data = dict(img=[Image.fromarray(i) for i in imgs], ori_shape=(w, h))
+        data = ns['ImageAug3D'](**cfg)(data)
+        data = ns['ImageNormalize'](**gc.IMG_NORM)(data)
+        out[tag + '_img'] = np.stack([t.numpy() for t in data['img']])
+        out[tag + '_aug'] = np.stack(data['img_aug_matrix'])
+        print('images', tag, out[tag + '_img'].shape, out[tag + '_aug'][0][:2, [0, 1, 3]].tolist())
+    np.savez_compressed(os.path.join(HERE, 'ref_images.npz'), **out)
+
+
 if __name__ == '__main__':
     R = ref_shim.install()
-    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head', 'lss', 'swin', 'sweeps']
+    which = sys.argv[1:] or ['fusion', 'fusion_full', 'sst', 'vfe', 'sparse', 'head', 'lss', 'swin', 'sweeps', 'images']
     for w in which:
         globals()[w](R)
     for f in sorted(os.listdir(HERE)):

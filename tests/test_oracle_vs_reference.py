@@ -213,3 +213,34 @@ def test_multi_sweep_loading_matches_reference(tag, kw, n_sw):
     got = input_ops.load_points_from_multi_sweeps(key, ts, sweeps[:n_sw], **kw)
     assert got.dtype == np.float32 and got.shape == g[tag].shape
     assert np.array_equal(got, g[tag])
+
+
+@pytest.mark.parametrize('tag,seed', [('test', None), ('train', 4), ('train2', 9)])
+def test_image_aug_and_normalize_match_reference(tag, seed):
+    """oracle/input_ops.py (Pillow's 8-bit bicubic resampler restated in integer arithmetic, crop with
+    zero padding, flip, ToTensor + Normalize, img_aug_matrix) against the reference's own ImageAug3D + ImageNormalize run
+    on synthetic uint8 frames — bit-exact, test branch and seeded train branch (crop window partly outside the image)."""
+    from oracle import input_ops
+    g = np.load(os.path.join(HERE, 'golden', 'ref_images.npz'))
+    imgs = gc.camera_images()
+    cfg = dict(gc.IMG_AUG_TEST) if seed is None else dict(gc.IMG_AUG_TEST, resize_lim=[0.57, 0.825], rand_flip=True, is_train=True)
+    if seed is not None:
+        np.random.seed(seed)
+    h, w = imgs[0].shape[:2]
+    for i, img in enumerate(imgs):
+        resize, dims, crop, flip, rotate = input_ops.sample_augmentation((w, h), **cfg)
+        assert rotate == 0
+        got = input_ops.image_aug_normalize(img, dims, crop, flip, **gc.IMG_NORM)
+        assert got.dtype == np.float32 and np.array_equal(got, g[tag + '_img'][i]), (tag, i)
+        assert np.array_equal(input_ops.image_aug_matrix(resize, crop, flip), g[tag + '_aug'][i])
+
+
+def test_pillow_resampler_restatement_against_pillow():
+    """the restated 8-bit bicubic resampler against PIL.Image.resize itself on shapes the fixture does not cover (up-scaling,
+    mixed, tiny outputs, the config's real 1600x900 -> 1152x648)."""
+    PIL = pytest.importorskip('PIL.Image')
+    from oracle import input_ops
+    rs = np.random.RandomState(1)
+    for h, w, ow, oh in [(50, 70, 100, 80), (37, 53, 20, 11), (90, 160, 160, 51), (900, 1600, 1152, 648)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        assert np.array_equal(np.asarray(PIL.fromarray(img).resize((ow, oh))), input_ops.pil_resize_bicubic(img, ow, oh)), (h, w, ow, oh)
