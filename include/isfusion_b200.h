@@ -123,6 +123,28 @@ int isf_debug_merge_sweeps_host(const float* raw, int m, int load_dim, int num_s
                                 const double* rot, const double* trans, const double* lag, const int* seg_flags,
                                 float radius, float* out, int* count);
 
+/* ---- input contract, camera side: ImageAug3D + ImageNormalize -----------
+ * replaces the PIL / torchvision pixel work of mmdet3d/datasets/pipelines/transforms_3d.py:25-43 (ImageNormalize:
+ *   ToTensor + Normalize) and :82-90 (ImageAug3D.img_transform: img.resize(resize_dims) = Pillow's 8-bit BICUBIC
+ *   resampler, img.crop(crop), FLIP_LEFT_RIGHT; rotate = 0).
+ * isf_image_plan: Pillow's coefficient tables (Resample.c precompute_coeffs + normalize_coeffs_8bpc) for the output
+ *   columns / rows that survive the crop, written to plan_dev (isf_image_plan_size bytes); rows[2] (HOST) receives the
+ *   input rows [lo, hi) the vertical pass reads.  crop = (crop_x, crop_y, crop_x + out_w, crop_y + out_h) in the
+ *   resized image; parts outside it read zeros (PIL crop).
+ * isf_image_aug_normalize: img [n, in_h, in_w, 3] uint8 -> out [n, 3, out_h, out_w] fp32 | fp16 =
+ *   ((u8 / 255) - mean) / std of the resampled + cropped (+ flipped) frame; n frames share the plan.  mean / std HOST [3].
+ *   workspace: isf_image_aug_workspace_size (the uint8 intermediate between the two passes). */
+int isf_image_plan_size(int in_w, int in_h, int rs_w, int rs_h, int out_w, int out_h, size_t* plan_bytes);
+int isf_image_plan(int in_w, int in_h, int rs_w, int rs_h, int crop_x, int crop_y, int out_w, int out_h, int flip,
+                   void* plan_dev, size_t plan_bytes, int* rows, void* stream);
+int isf_image_aug_workspace_size(int n, int out_w, int row_lo, int row_hi, size_t* bytes);
+int isf_image_aug_normalize(const unsigned char* img, int n, int in_w, int in_h, int rs_w, int rs_h, int out_w, int out_h,
+                            int row_lo, int row_hi, const void* plan_dev, const float* mean, const float* stdv, void* out,
+                            int out_is_half, void* workspace, size_t ws_bytes, void* stream);
+/* TEST HOOK: plan + both passes with the kernels' own per-pixel source on HOST memory; out fp32 [n, 3, out_h, out_w]. */
+int isf_debug_image_aug_host(const unsigned char* img, int n, int in_w, int in_h, int rs_w, int rs_h, int crop_x, int crop_y,
+                             int out_w, int out_h, int flip, const float* mean, const float* stdv, float* out);
+
 /* ---- K7: rank inside a group --------------------------------------------------
  * replaces ingroup_indices.forward(group_inds, out_inds)
  *   mmdet3d/ops/TorchEx/torchex/src/ingroup_inds/ingroup_inds.cpp:28-54, kernel :17-30.

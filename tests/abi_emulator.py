@@ -21,7 +21,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ana
 
 _PARAM_NAMES = {}
 # untyped (void*) data pointers are fp16 matrices unless listed here: scratch / opaque bytes, or either precision (flagged)
-_VOID_ANY = {'workspace', 'table', 'in_table', 'stream', 'value'}
+_VOID_ANY = {'workspace', 'table', 'in_table', 'stream', 'value', 'plan_dev'}
+_VOID_ANY_FN = {('isf_image_aug_normalize', 'out')}          # fp32 or fp16 by flag
 
 
 def _header_params():
@@ -54,7 +55,8 @@ def _check_kinds(name, ctypes_of, args):
             base = ct.replace('const', '').replace('*', '').strip()
             if isinstance(a, torch.Tensor) and base in _ELEM:            # typed pointer: the tensor's element type must be it
                 assert a.dtype in _ELEM[base], '%s: argument %d is %s but the tensor holds %s' % (name, i, ct, a.dtype)
-            elif isinstance(a, torch.Tensor) and base == 'void' and _PARAM_NAMES.get(name) and _PARAM_NAMES[name][i] not in _VOID_ANY:
+            elif isinstance(a, torch.Tensor) and base == 'void' and _PARAM_NAMES.get(name) and _PARAM_NAMES[name][i] not in _VOID_ANY \
+                    and (name, _PARAM_NAMES[name][i]) not in _VOID_ANY_FN:
                 assert a.dtype == torch.float16, '%s: %s is an fp16 matrix in the library but the tensor holds %s' % (
                     name, _PARAM_NAMES[name][i], a.dtype)
             elif isinstance(a, ctypes.Array) and base in _CELEM:
@@ -473,6 +475,34 @@ class VoxelMixin:
         count.fill_(res.shape[0])
         return 0
 
+    def isf_image_plan_size(self, in_w, in_h, rs_w, rs_h, out_w, out_h, bytes_ref):
+        _set_size(bytes_ref, 64)
+        return 0
+
+    def isf_image_plan(self, in_w, in_h, rs_w, rs_h, crop_x, crop_y, out_w, out_h, flip, plan, plan_bytes, rows, stream):
+        from oracle import input_ops
+        plan[:3] = torch.tensor([crop_x, crop_y, flip], dtype=torch.int32)        # what the emulated kernel needs of the tables
+        ymin, ycnt, _ = input_ops.resample_coeffs(in_h, rs_h) if rs_h != in_h else (list(range(in_h)), [1] * in_h, None)
+        valid = [oy + crop_y for oy in range(out_h) if 0 <= oy + crop_y < rs_h]
+        rows[0] = min([int(ymin[r]) for r in valid], default=0)
+        rows[1] = max([int(ymin[r] + ycnt[r]) for r in valid], default=1)
+        return 0
+
+    def isf_image_aug_workspace_size(self, n, out_w, row_lo, row_hi, bytes_ref):
+        assert 0 <= row_lo < row_hi
+        _set_size(bytes_ref, 256)
+        return 0
+
+    def isf_image_aug_normalize(self, img, n, in_w, in_h, rs_w, rs_h, out_w, out_h, row_lo, row_hi, plan, mean, std, out, is_half,
+                                ws, ws_bytes, stream):
+        from oracle import input_ops
+        cx, cy, flip = (int(v) for v in plan[:3])
+        assert tuple(img.shape) == (n, in_h, in_w, 3) and 0 <= row_lo < row_hi <= in_h
+        for i in range(n):
+            r = input_ops.image_aug_normalize(img[i].numpy(), (rs_w, rs_h), (cx, cy, cx + out_w, cy + out_h), bool(flip), list(mean), list(std))
+            out[i].copy_(torch.from_numpy(r).to(out.dtype))
+        return 0
+
     def isf_ingroup_indices(self, group_inds, n, key_bits, out_inds, ws, ws_bytes, stream):
         g = group_inds[:n]
         order = torch.argsort(g, stable=True)
@@ -600,7 +630,7 @@ class RowsAroundMixin:
 
 class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):
     _KINDS = None
-    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_debug_msda_backward_host', 'isf_debug_merge_sweeps_host',
+    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_debug_msda_backward_host', 'isf_debug_merge_sweeps_host', 'isf_debug_image_aug_host',
                  'isf_version')
 
     def __init__(self, real=None):

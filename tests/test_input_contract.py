@@ -107,3 +107,115 @@ def test_merge_sweeps_full_size():
         got = LoadPointsFromMultiSweeps(use_dim=[0, 1, 2, 3, 4], remove_close=rc)(dict(res))['points'].cpu().numpy()
         host = _host_merge(LoadPointsFromMultiSweeps(use_dim=[0, 1, 2, 3, 4], device='cpu', remove_close=rc), dict(res))
         assert np.array_equal(got, host)
+
+
+# ------------------------------------------------------------------------------------------------ camera side
+GI = np.load(os.path.join(HERE, 'golden', 'ref_images.npz'))
+IMG_CASES = [('test', None), ('train', 4), ('train2', 9)]
+
+
+def _aug_cfg(seed):
+    return dict(gc.IMG_AUG_TEST) if seed is None else dict(gc.IMG_AUG_TEST, resize_lim=[0.57, 0.825], rand_flip=True, is_train=True)
+
+
+@pytest.mark.parametrize('tag,seed', IMG_CASES)
+def test_image_kernel_source_on_host_matches_the_reference_pipeline(tag, seed):
+    """plan + both passes (Pillow's integer resampler, crop, flip, ToTensor + Normalize) with the kernels' per-pixel source
+    compiled for the host, against the reference's ImageAug3D + ImageNormalize run: bit-exact float32."""
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.image_pipeline import ImageAug3D
+    imgs = gc.camera_images()
+    h, w = imgs[0].shape[:2]
+    if seed is not None:
+        np.random.seed(seed)
+    data = ImageAug3D(**_aug_cfg(seed))(dict(img=list(imgs), ori_shape=(w, h)))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for i, (img, (dims, crop, flip)) in enumerate(zip(imgs, data['img_aug_plan'])):
+        out = np.zeros((1, 3, crop[3] - crop[1], crop[2] - crop[0]), np.float32)
+        L.check(L.lib().isf_debug_image_aug_host(p(np.ascontiguousarray(img)), 1, w, h, dims[0], dims[1], crop[0], crop[1], crop[2] - crop[0],
+                                                 crop[3] - crop[1], int(flip), L.host_f32(gc.IMG_NORM['mean']), L.host_f32(gc.IMG_NORM['std']),
+                                                 p(out)))
+        assert np.array_equal(out[0], GI[tag + '_img'][i]), (tag, i)
+        assert np.array_equal(data['img_aug_matrix'][i], GI[tag + '_aug'][i])
+
+
+@pytest.mark.parametrize('tag,seed', IMG_CASES)
+def test_product_image_pipeline_on_the_emulator(tag, seed, monkeypatch):
+    """ImageAug3D -> ImageNormalize built by name from the config's dicts, PIL images in (as LoadMultiViewImageFromFilesV2
+    delivers them), device tensors out: same draws, same matrices, same pixels as the reference run."""
+    PIL = pytest.importorskip('PIL.Image')
+    import abi_emulator
+    from isfusion_b200.registry import PIPELINES
+    import isfusion_b200.image_pipeline as IP
+    abi_emulator.install(monkeypatch)
+    monkeypatch.setattr(IP, '_PLANS', {})
+    imgs = gc.camera_images()
+    h, w = imgs[0].shape[:2]
+    aug = PIPELINES.build(dict(type='ImageAug3D', **_aug_cfg(seed)))
+    norm = PIPELINES.build(dict(type='ImageNormalize', device='cpu', **gc.IMG_NORM))
+    if seed is not None:
+        np.random.seed(seed)
+    data = norm(aug(dict(img=[PIL.fromarray(i) for i in imgs], ori_shape=(w, h))))
+    assert data['img_norm_cfg'] == dict(gc.IMG_NORM) and 'img_aug_plan' not in data
+    for i, t in enumerate(data['img']):
+        assert t.dtype == torch.float32 and np.array_equal(t.numpy(), GI[tag + '_img'][i])
+        assert np.array_equal(data['img_aug_matrix'][i], GI[tag + '_aug'][i])
+    # fp16 output for the backbone = the float32 result rounded once
+    norm16 = PIPELINES.build(dict(type='ImageNormalize', device='cpu', out_dtype=torch.float16, **gc.IMG_NORM))
+    if seed is not None:
+        np.random.seed(seed)
+    d16 = norm16(aug(dict(img=list(imgs), ori_shape=(w, h))))
+    assert d16['img'][0].dtype == torch.float16 and torch.equal(d16['img'][0], torch.from_numpy(GI[tag + '_img'][0]).half())
+
+
+def test_image_plan_full_size_against_pillow():
+    """the config's real geometry (1600x900 -> resize 0.72 -> crop to 384x1056): the host-compiled kernel source against
+    PIL + the float32 normalisation, bit-exact; and the plan only asks for the input rows below the crop line."""
+    PIL = pytest.importorskip('PIL.Image')
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.image_pipeline import ImageAug3D
+    rs = np.random.RandomState(2)
+    img = rs.randint(0, 256, (900, 1600, 3)).astype(np.uint8)
+    aug = ImageAug3D(final_dim=(384, 1056), resize_lim=[0.72, 0.72], bot_pct_lim=[0.0, 0.0], rot_lim=[0.0, 0.0], rand_flip=False, is_train=False)
+    resize, dims, crop, flip, rot = aug.sample_augmentation(dict(ori_shape=(1600, 900)))
+    assert dims == (1152, 648) and crop == (48, 264, 1104, 648)
+    ref = np.asarray(PIL.fromarray(img).resize(dims).crop(crop)).transpose(2, 0, 1).astype(np.float32) / np.float32(255)
+    ref = (ref - np.float32(gc.IMG_NORM['mean'])[:, None, None]) / np.float32(gc.IMG_NORM['std'])[:, None, None]
+    out = np.zeros((1, 3, 384, 1056), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.check(L.lib().isf_debug_image_aug_host(p(img), 1, 1600, 900, 1152, 648, 48, 264, 1056, 384, 0, L.host_f32(gc.IMG_NORM['mean']),
+                                             L.host_f32(gc.IMG_NORM['std']), p(out)))
+    assert np.array_equal(out[0], ref)
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.parametrize('tag,seed', IMG_CASES)
+def test_image_kernels_against_the_reference_pipeline(tag, seed):
+    from isfusion_b200.image_pipeline import ImageAug3D, ImageNormalize
+    imgs = gc.camera_images()
+    h, w = imgs[0].shape[:2]
+    if seed is not None:
+        np.random.seed(seed)
+    data = ImageNormalize(**gc.IMG_NORM)(ImageAug3D(**_aug_cfg(seed))(dict(img=list(imgs), ori_shape=(w, h))))
+    for i, t in enumerate(data['img']):
+        assert np.array_equal(t.cpu().numpy(), GI[tag + '_img'][i]), (tag, i)
+
+
+@pytest.mark.gpu
+@experimental
+def test_image_kernels_full_size_six_cameras():
+    """6 x 1600x900 frames through the config's test-time geometry: device == the same source compiled for the host."""
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.image_pipeline import image_aug_normalize
+    rs = np.random.RandomState(3)
+    imgs = rs.randint(0, 256, (6, 900, 1600, 3)).astype(np.uint8)
+    got = image_aug_normalize(torch.from_numpy(imgs).cuda(), (1152, 648), (48, 264, 1104, 648), False, gc.IMG_NORM['mean'], gc.IMG_NORM['std'])
+    out = np.zeros((6, 3, 384, 1056), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.check(L.lib().isf_debug_image_aug_host(p(imgs), 6, 1600, 900, 1152, 648, 48, 264, 1056, 384, 0, L.host_f32(gc.IMG_NORM['mean']),
+                                             L.host_f32(gc.IMG_NORM['std']), p(out)))
+    assert np.array_equal(got.cpu().numpy(), out)
+    half = image_aug_normalize(torch.from_numpy(imgs).cuda(), (1152, 648), (48, 264, 1104, 648), False, gc.IMG_NORM['mean'], gc.IMG_NORM['std'],
+                               out_dtype=torch.float16)
+    assert torch.equal(half.cpu(), torch.from_numpy(out).half())
