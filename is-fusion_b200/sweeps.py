@@ -103,3 +103,54 @@ class LoadPointsFromMultiSweeps(object):
 
     def __repr__(self):
         return f'{self.__class__.__name__}(sweeps_num={self.sweeps_num})'
+
+
+@PIPELINES.register_module()
+class PointsRangeFilter(object):
+    """ref: transforms_3d.py:2002-2043 with BasePoints.in_range_3d (core/points/base_points.py:208-230): keeps the points
+    STRICTLY inside the range, order preserved.  Device tensor in, device tensor out (one masked select)."""
+
+    def __init__(self, point_cloud_range):
+        self.pcd_range = np.array(point_cloud_range, dtype=np.float32)
+
+    def __call__(self, input_dict):
+        pts = input_dict['points']
+        r = torch.as_tensor(self.pcd_range, device=pts.device)
+        mask = ((pts[:, 0] > r[0]) & (pts[:, 1] > r[1]) & (pts[:, 2] > r[2]) & (pts[:, 0] < r[3]) & (pts[:, 1] < r[4]) & (pts[:, 2] < r[5]))
+        input_dict['points'] = pts[mask]
+        for key in ('pts_instance_mask', 'pts_semantic_mask'):
+            if input_dict.get(key) is not None:
+                input_dict[key] = input_dict[key][mask.cpu().numpy()]
+        return input_dict
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}(point_cloud_range={self.pcd_range.tolist()})'
+
+
+@PIPELINES.register_module()
+class GlobalRotScaleTransV2:
+    """ref: transforms_3d.py:1871-1915, inference branch: `lidar_aug_matrix` = identity (the train branch augments the
+    ground-truth boxes as well, which is outside the path)."""
+
+    def __init__(self, resize_lim, rot_lim, trans_lim, is_train):
+        self.resize_lim, self.rot_lim, self.trans_lim, self.is_train = resize_lim, rot_lim, trans_lim, is_train
+
+    def __call__(self, data):
+        if self.is_train or isinstance(self.rot_lim, float):
+            raise NotImplementedError('GlobalRotScaleTransV2: only the inference branch (identity) is on the path')
+        data['lidar_aug_matrix'] = np.eye(4).astype(np.float32)
+        return data
+
+
+class Compose:
+    """minimal mmdet Compose over the PIPELINES registry: a list of config dicts / callables applied in order."""
+
+    def __init__(self, transforms):
+        self.transforms = [PIPELINES.build(t) if isinstance(t, dict) else t for t in transforms]
+
+    def __call__(self, data):
+        for t in self.transforms:
+            data = t(data)
+            if data is None:
+                return None
+        return data

@@ -205,6 +205,8 @@ def sweeps(R):
             res = R.LoadPointsFromMultiSweeps(use_dim=[0, 1, 2, 3, 4], **kw)(res)
             out[tag] = res['points'].tensor.numpy()
             print('sweeps', tag, out[tag].shape)
+            if tag == 'plain':      # PointsRangeFilter's arithmetic: the reference's own BasePoints.in_range_3d on a 40 m range
+                out['plain_in_range40'] = res['points'].in_range_3d(np.array([-40, -40, -3, 40, 40, 1], dtype=np.float32)).numpy()
     np.savez_compressed(os.path.join(HERE, 'ref_sweeps.npz'), **out)
 
 

@@ -219,3 +219,45 @@ def test_image_kernels_full_size_six_cameras():
     half = image_aug_normalize(torch.from_numpy(imgs).cuda(), (1152, 648), (48, 264, 1104, 648), False, gc.IMG_NORM['mean'], gc.IMG_NORM['std'],
                                out_dtype=torch.float16)
     assert torch.equal(half.cpu(), torch.from_numpy(out).half())
+
+
+def test_inference_pipeline_assembled_from_config_dicts(monkeypatch):
+    """the config's test-time transforms that touch the path's inputs (config:305-343), built by name and composed: sweeps merged,
+    cameras resized / cropped / normalised, identity lidar_aug_matrix, points strictly inside the range — against the oracle
+    statements of the same steps."""
+    import abi_emulator
+    from oracle import input_ops
+    import isfusion_b200.image_pipeline  # noqa: F401  (registers the transforms)
+    import isfusion_b200.image_pipeline as IP
+    from isfusion_b200.sweeps import Compose
+    abi_emulator.install(monkeypatch)
+    monkeypatch.setattr(IP, '_PLANS', {})
+    pcr = [-54, -54, -5, 54, 54, 3]
+    pipe = Compose([
+        dict(type='LoadPointsFromMultiSweeps', sweeps_num=10, use_dim=[0, 1, 2, 3, 4], device='cpu'),
+        dict(type='ImageAug3D', **gc.IMG_AUG_TEST),
+        dict(type='ImageNormalize', device='cpu', **gc.IMG_NORM),
+        dict(type='GlobalRotScaleTransV2', resize_lim=[1.0, 1.0], rot_lim=[0.0, 0.0], trans_lim=0.0, is_train=False),
+        dict(type='PointsRangeFilter', point_cloud_range=pcr),
+    ])
+    key, ts, sweeps = gc.sweep_inputs()
+    key[:5, 0] = [54.0, -54.0, 60.0, 53.999, -53.999]            # on / outside / just inside the range faces
+    imgs = gc.camera_images()
+    h, w = imgs[0].shape[:2]
+    data = pipe(dict(points=key.copy(), timestamp=ts, sweeps=sweeps, img=list(imgs), ori_shape=(w, h)))
+    want = input_ops.load_points_from_multi_sweeps(key, ts, sweeps)
+    r = np.array(pcr, np.float32)
+    keep = (want[:, 0] > r[0]) & (want[:, 1] > r[1]) & (want[:, 2] > r[2]) & (want[:, 0] < r[3]) & (want[:, 1] < r[4]) & (want[:, 2] < r[5])
+    assert 0 < keep.sum() < len(want) and not keep[0] and not keep[1] and not keep[2] and keep[3] and keep[4]
+    assert np.array_equal(data['points'].numpy(), want[keep])
+    assert np.array_equal(data['lidar_aug_matrix'], np.eye(4, dtype=np.float32))
+    assert np.array_equal(torch.stack(data['img']).numpy(), GI['test_img']) and np.array_equal(np.stack(data['img_aug_matrix']), GI['test_aug'])
+
+
+def test_points_range_filter_matches_the_reference_point_class():
+    """PointsRangeFilter (device-side mask) against the reference's own BasePoints.in_range_3d evaluated on the merged cloud."""
+    from isfusion_b200.sweeps import PointsRangeFilter
+    pts = torch.from_numpy(G['plain'])
+    got = PointsRangeFilter([-40, -40, -3, 40, 40, 1])(dict(points=pts))['points']
+    mask = G['plain_in_range40']
+    assert 0 < mask.sum() < len(mask) and np.array_equal(got.numpy(), G['plain'][mask])
