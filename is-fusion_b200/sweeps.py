@@ -154,3 +154,44 @@ class Compose:
             if data is None:
                 return None
         return data
+
+
+@PIPELINES.register_module()
+class LoadPointsFromFile(object):
+    """ref: loading.py `LoadPointsFromFile.__call__` (:1465-1520, the path's arguments: coord_type='LIDAR', load_dim,
+    use_dim): raw float32 file -> `results['points']` [N, len(use_dim)] numpy (the reference wraps it in LiDARPoints)."""
+
+    def __init__(self, coord_type='LIDAR', load_dim=6, use_dim=[0, 1, 2], shift_height=False, use_color=False,
+                 file_client_args=dict(backend='disk'), painting=False, **kwargs):
+        if shift_height or use_color or painting:
+            raise NotImplementedError('LoadPointsFromFile: shift_height / use_color / painting are outside the path')
+        assert coord_type in ('CAMERA', 'LIDAR', 'DEPTH')
+        self.load_dim = load_dim
+        self.use_dim = list(range(use_dim)) if isinstance(use_dim, int) else list(use_dim)
+        assert max(self.use_dim) < load_dim, f'Expect all used dimensions < {load_dim}, got {use_dim}'
+
+    def __call__(self, results):
+        path = results['pts_filename']
+        pts = np.load(path) if path.endswith('.npy') else np.fromfile(path, dtype=np.float32)
+        results['points'] = pts.reshape(-1, self.load_dim)[:, self.use_dim]
+        return results
+
+
+@PIPELINES.register_module()
+class LoadMultiViewImageFromFilesV2:
+    """ref: loading.py:14-72: opens the camera files with PIL; the frames stay undecoded-lazy PIL images until ImageNormalize
+    takes their uint8 pixels to the device."""
+
+    def __init__(self, to_float32=False, color_type='unchanged'):
+        self.to_float32, self.color_type = to_float32, color_type
+
+    def __call__(self, results):
+        if 'img_filename' not in results:
+            return results
+        from PIL import Image
+        images = [Image.open(name) for name in results['img_filename']]
+        results['filename'] = results['img_filename']
+        results['img'] = images
+        results['img_shape'] = results['ori_shape'] = results['pad_shape'] = images[0].size
+        results['scale_factor'] = 1.0
+        return results

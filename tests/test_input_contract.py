@@ -261,3 +261,35 @@ def test_points_range_filter_matches_the_reference_point_class():
     got = PointsRangeFilter([-40, -40, -3, 40, 40, 1])(dict(points=pts))['points']
     mask = G['plain_in_range40']
     assert 0 < mask.sum() < len(mask) and np.array_equal(got.numpy(), G['plain'][mask])
+
+
+def test_file_loaders_feed_the_pipeline(tmp_path, monkeypatch):
+    """the config's test pipeline from FILE NAMES (config:297-332): .bin sweeps + PNG cameras on disk -> the same points /
+    images as from arrays."""
+    PIL = pytest.importorskip('PIL.Image')
+    import abi_emulator
+    import isfusion_b200.image_pipeline as IP
+    from isfusion_b200.sweeps import Compose
+    abi_emulator.install(monkeypatch)
+    monkeypatch.setattr(IP, '_PLANS', {})
+    key, ts, sweeps = gc.sweep_inputs()
+    key.tofile(str(tmp_path / 'key.bin'))
+    infos = []
+    for i, s in enumerate(sweeps):
+        s['points'].tofile(str(tmp_path / ('s%d.bin' % i)))
+        infos.append(dict(data_path=str(tmp_path / ('s%d.bin' % i)), timestamp=s['timestamp'],
+                          sensor2lidar_rotation=s['sensor2lidar_rotation'], sensor2lidar_translation=s['sensor2lidar_translation']))
+    names = []
+    for i, img in enumerate(gc.camera_images()):
+        PIL.fromarray(img).save(str(tmp_path / ('cam%d.png' % i)))          # lossless, so the pixels are the fixture's
+        names.append(str(tmp_path / ('cam%d.png' % i)))
+    pipe = Compose([
+        dict(type='LoadPointsFromFile', coord_type='LIDAR', load_dim=5, use_dim=5, painting=False),
+        dict(type='LoadPointsFromMultiSweeps', sweeps_num=10, use_dim=[0, 1, 2, 3, 4], painting=False, device='cpu'),
+        dict(type='LoadMultiViewImageFromFilesV2', to_float32=True),
+        dict(type='ImageAug3D', **gc.IMG_AUG_TEST),
+        dict(type='ImageNormalize', device='cpu', **gc.IMG_NORM),
+    ])
+    data = pipe(dict(pts_filename=str(tmp_path / 'key.bin'), timestamp=ts, sweeps=infos, img_filename=names))
+    assert np.array_equal(data['points'].numpy(), G['plain'])
+    assert data['ori_shape'] == (400, 225) and np.array_equal(torch.stack(data['img']).numpy(), GI['test_img'])
