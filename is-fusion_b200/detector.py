@@ -151,7 +151,33 @@ class ISFusionDetector(nn.Module):
             feats = self.pts_neck(feats)
         return feats, ins_hm
 
-    forward = extract_pts_feat
+    def forward(self, *args, return_loss=None, **kwargs):
+        """`net(points, img_feats, img_metas, ...)` runs the path itself (extract_pts_feat).  With the reference's keyword
+        (detectors/base.py:46-62) `return_loss=False` dispatches to forward_test (double-nested points / img_metas / img);
+        `return_loss=True` is the training step, which is outside this build."""
+        if return_loss is None:
+            return self.extract_pts_feat(*args, **kwargs)
+        if return_loss:
+            raise NotImplementedError('ISFusionDetector: forward_train (losses, assigner) is outside the path')
+        return self.forward_test(*args, **kwargs)
+
+    def extract_feat(self, points, img, img_metas, **kwargs):
+        """ref: isfusion.py:178-182."""
+        img_feats = self.extract_img_feat(img, img_metas)
+        pts_feats = self.extract_pts_feat(points, img_feats, img_metas, **kwargs)
+        return (img_feats, pts_feats)
+
+    def forward_test(self, points, img_metas=None, img=None, **kwargs):
+        """ref: detectors/base.py:15-44: the outer lists are test-time augmentations; one entry -> simple_test."""
+        for var, name in [(points, 'points'), (img_metas, 'img_metas')]:
+            if not isinstance(var, list):
+                raise TypeError('{} must be a list, but got {}'.format(name, type(var)))
+        if len(points) != len(img_metas):
+            raise ValueError('num of augmentations ({}) != num of image meta ({})'.format(len(points), len(img_metas)))
+        if len(points) != 1:
+            raise NotImplementedError('ISFusionDetector: aug_test (test-time augmentation) is outside the path')
+        img = [img] if img is None else img
+        return self.simple_test(points[0], img_metas[0], img[0], **kwargs)
 
     @torch.no_grad()
     def extract_img_feat(self, img, img_metas):

@@ -519,3 +519,12 @@ def test_full_detector_built_from_the_config_runs_end_to_end_on_the_emulator(mon
     assert box['boxes_3d'].shape == (200, 9) and box['scores_3d'].shape == (200,) and box['labels_3d'].shape == (200,)
     assert torch.isfinite(box['boxes_3d'].float()).all() and torch.isfinite(box['scores_3d'].float()).all()
     assert int(box['labels_3d'].min()) >= 0 and int(box['labels_3d'].max()) < 10
+    # the reference's entry point: forward(return_loss=False, points=[...], img_metas=[[...]], img=[...]) (detectors/base.py:46-62)
+    res2 = net(return_loss=False, points=[pts], img_metas=[[dict()]], img=[img], lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    assert torch.equal(res2[0]['pts_bbox']['boxes_3d'], box['boxes_3d'])
+    img_feats, pts_feats = net.extract_feat(pts, img, [dict()], lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    assert len(img_feats) == 2 and tuple(pts_feats[0][0].shape[:2]) == (1, 512)
+    with pytest.raises(NotImplementedError):
+        net(return_loss=True)
+    with pytest.raises(TypeError):
+        net(return_loss=False, points=pts[0], img_metas=[[dict()]])
