@@ -14,6 +14,7 @@
 // The coefficient tables are Pillow's (precompute_coeffs + normalize_coeffs_8bpc, float64 on the host), computed once per
 // geometry by isf_image_plan.  The per-pixel arithmetic is shared host / device source (isf_debug_image_aug_host).
 #include <cmath>
+#include <cstdint>
 #include <vector>
 #include "common.cuh"
 
@@ -109,6 +110,27 @@ __host__ __device__ __forceinline__ unsigned char img_resample_px(const unsigned
   return (unsigned char)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
 }
 
+// the same for FOUR adjacent byte columns of the interleaved intermediate (vertical pass: every byte column is an independent
+// signal, the taps are whole rows apart): one aligned 32-bit load per tap instead of four byte loads.  src 4-byte aligned.
+__host__ __device__ __forceinline__ void img_resample_px4(const unsigned char* src, long long stride, const int* coef, int cnt,
+                                                          unsigned char (&out)[4]) {
+  if (cnt < 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+  int s0 = 1 << (32 - 8 - 2 - 1), s1 = s0, s2 = s0, s3 = s0;
+  for (int j = 0; j < cnt; ++j) {
+    const unsigned int w = *(const unsigned int*)(src + j * stride);
+    const int k = coef[j];
+    s0 += (int)(w & 0xFFu) * k;
+    s1 += (int)((w >> 8) & 0xFFu) * k;
+    s2 += (int)((w >> 16) & 0xFFu) * k;
+    s3 += (int)(w >> 24) * k;
+  }
+  s0 >>= (32 - 8 - 2); s1 >>= (32 - 8 - 2); s2 >>= (32 - 8 - 2); s3 >>= (32 - 8 - 2);
+  out[0] = (unsigned char)(s0 < 0 ? 0 : (s0 > 255 ? 255 : s0));
+  out[1] = (unsigned char)(s1 < 0 ? 0 : (s1 > 255 ? 255 : s1));
+  out[2] = (unsigned char)(s2 < 0 ? 0 : (s2 > 255 ? 255 : s2));
+  out[3] = (unsigned char)(s3 < 0 ? 0 : (s3 > 255 ? 255 : s3));
+}
+
 // ToTensor + Normalize of one value, float32 with correctly rounded divisions (torch: x.to(float32).div(255).sub_(mean).div_(std))
 __host__ __device__ __forceinline__ float img_normalize_px(unsigned char u, float mean, float stdv) {
 #ifdef __CUDA_ARCH__
@@ -159,6 +181,34 @@ __global__ void __launch_bounds__(256) image_vertical_normalize_kernel(const uns
     o[0] = (OUT)img_normalize_px(img_resample_px(src + 0, stride, k, cnt), m0, s0);
     o[plane] = (OUT)img_normalize_px(img_resample_px(src + 1, stride, k, cnt), m1, s1);
     o[2 * plane] = (OUT)img_normalize_px(img_resample_px(src + 2, stride, k, cnt), m2, s2);
+  }
+}
+
+// vertical pass, four byte columns per thread (row pitch out_w * 3 a multiple of 4): byte column b of a row = pixel b / 3,
+// channel b % 3.  7 word loads instead of 28 byte loads per four outputs.
+template <typename OUT>
+__global__ void __launch_bounds__(256) image_vertical_normalize4_kernel(const unsigned char* __restrict__ tmp, ImageDims d,
+                                                                        const int* __restrict__ ymin, const int* __restrict__ ycnt,
+                                                                        const int* __restrict__ ycoef, float m0, float m1, float m2,
+                                                                        float s0, float s1, float s2, OUT* __restrict__ out) {
+  const int quads = d.out_w * 3 / 4;
+  const long long total = (long long)d.n * d.out_h * quads;
+  const long long plane = (long long)d.out_h * d.out_w;
+  const long long stride = (long long)d.out_w * 3;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int qd = (int)(t % quads);
+    const long long r = t / quads;
+    const int oy = (int)(r % d.out_h), im = (int)(r / d.out_h);
+    const unsigned char* src = tmp + ((long long)im * d.rows + (ymin[oy] - d.row_lo)) * stride + qd * 4;
+    unsigned char u[4];
+    img_resample_px4(src, stride, ycoef + (long long)oy * d.ksy, ycnt[oy], u);
+    OUT* o = out + (long long)im * 3 * plane + (long long)oy * d.out_w;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int b = qd * 4 + e, px = b / 3, c = b - px * 3;
+      const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+      o[c * plane + px] = (OUT)img_normalize_px(u[e], mean, sd);
+    }
   }
 }
 
@@ -223,12 +273,17 @@ extern "C" int isf_image_aug_normalize(const unsigned char* img, int n, int in_w
   unsigned char* tmp = (unsigned char*)workspace;
   auto grid = [](long long total) { long long b = (total + 255) / 256; return (int)(b > ISF_NUM_SMS * 32 ? ISF_NUM_SMS * 32 : b); };
   image_horizontal_kernel<<<grid((long long)n * d.rows * out_w), 256, 0, st>>>(img, d, xmin, xcnt, xcoef, tmp);
-  if (out_is_half)
-    image_vertical_normalize_kernel<__half><<<grid((long long)n * out_h * out_w), 256, 0, st>>>(
-        tmp, d, ymin, ycnt, ycoef, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], (__half*)out);
-  else
-    image_vertical_normalize_kernel<float><<<grid((long long)n * out_h * out_w), 256, 0, st>>>(
-        tmp, d, ymin, ycnt, ycoef, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], (float*)out);
+  const bool quad = (out_w * 3) % 4 == 0 && ((uintptr_t)tmp & 3) == 0;      // word loads need a 4-byte row pitch
+#define ISF_IMG_V(KERNEL, T, TOTAL)                                                                                  \
+  KERNEL<T><<<grid(TOTAL), 256, 0, st>>>(tmp, d, ymin, ycnt, ycoef, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2], (T*)out)
+  if (quad) {
+    const long long total = (long long)n * out_h * (out_w * 3 / 4);
+    if (out_is_half) ISF_IMG_V(image_vertical_normalize4_kernel, __half, total); else ISF_IMG_V(image_vertical_normalize4_kernel, float, total);
+  } else {
+    const long long total = (long long)n * out_h * out_w;
+    if (out_is_half) ISF_IMG_V(image_vertical_normalize_kernel, __half, total); else ISF_IMG_V(image_vertical_normalize_kernel, float, total);
+  }
+#undef ISF_IMG_V
   isf_count_launch(2);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
@@ -260,13 +315,27 @@ extern "C" int isf_debug_image_aug_host(const unsigned char* img, int n, int in_
         for (int c = 0; c < 3; ++c)
           tmp[((size_t)row * out_w + ox) * 3 + c] = img_resample_px(src + c, 3, xcoef + (size_t)ox * P.ksx, xcnt[ox]);
       }
-    for (int oy = 0; oy < out_h; ++oy)
+    const bool quad = (out_w * 3) % 4 == 0 && ((uintptr_t)tmp.data() & 3) == 0;     // the path the device launch takes
+    for (int oy = 0; oy < out_h; ++oy) {
+      if (quad) {
+        for (int qd = 0; qd < out_w * 3 / 4; ++qd) {
+          unsigned char u[4];
+          img_resample_px4(tmp.data() + ((size_t)(ymin[oy] - P.row_lo)) * out_w * 3 + qd * 4, (long long)out_w * 3,
+                           ycoef + (size_t)oy * P.ksy, ycnt[oy], u);
+          for (int e = 0; e < 4; ++e) {
+            const int b = qd * 4 + e, px = b / 3, c = b - px * 3;
+            out[(long long)im * 3 * plane + c * plane + (long long)oy * out_w + px] = img_normalize_px(u[e], mean[c], stdv[c]);
+          }
+        }
+        continue;
+      }
       for (int ox = 0; ox < out_w; ++ox) {
         const unsigned char* src = tmp.data() + (((size_t)(ymin[oy] - P.row_lo)) * out_w + ox) * 3;
         for (int c = 0; c < 3; ++c)
           out[(long long)im * 3 * plane + c * plane + (long long)oy * out_w + ox] =
               img_normalize_px(img_resample_px(src + c, (long long)out_w * 3, ycoef + (size_t)oy * P.ksy, ycnt[oy]), mean[c], stdv[c]);
       }
+    }
   }
   return ISF_OK;
 }

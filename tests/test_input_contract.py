@@ -293,3 +293,21 @@ def test_file_loaders_feed_the_pipeline(tmp_path, monkeypatch):
     data = pipe(dict(pts_filename=str(tmp_path / 'key.bin'), timestamp=ts, sweeps=infos, img_filename=names))
     assert np.array_equal(data['points'].numpy(), G['plain'])
     assert data['ori_shape'] == (400, 225) and np.array_equal(torch.stack(data['img']).numpy(), GI['test_img'])
+
+
+@pytest.mark.parametrize('fw', [263, 262, 264])
+def test_image_kernel_source_scalar_and_word_paths_against_the_oracle(fw):
+    """row pitches that are / are not a multiple of 4 bytes take the word-vectorised / the scalar vertical pass: both equal
+    the oracle (itself pinned by the reference run and by Pillow)."""
+    from oracle import input_ops
+    from isfusion_b200 import _lib as L
+    img = gc.camera_images()[1]
+    h, w = img.shape[:2]
+    dims, crop = input_ops.image_aug_geometry((w, h), (90, fw), 0.72)
+    for flip in (False, True):
+        want = input_ops.image_aug_normalize(img, dims, crop, flip, **gc.IMG_NORM)
+        out = np.zeros((1, 3, 90, fw), np.float32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        L.check(L.lib().isf_debug_image_aug_host(p(np.ascontiguousarray(img)), 1, w, h, dims[0], dims[1], crop[0], crop[1], fw, 90, int(flip),
+                                                 L.host_f32(gc.IMG_NORM['mean']), L.host_f32(gc.IMG_NORM['std']), p(out)))
+        assert np.array_equal(out[0], want), (fw, flip)
