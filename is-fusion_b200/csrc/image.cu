@@ -131,6 +131,58 @@ __host__ __device__ __forceinline__ void img_resample_px4(const unsigned char* s
   out[3] = (unsigned char)(s3 < 0 ? 0 : (s3 > 255 ? 255 : s3));
 }
 
+// horizontal pass of one output pixel (3 channels, up to 8 taps = 24 contiguous source bytes at any alignment): eight aligned
+// 32-bit loads, re-aligned with funnel shifts, instead of 21-24 byte loads.  The caller guarantees that the 32 bytes from
+// (src & ~3) lie inside the image buffer and that 0 <= cnt <= 8.
+__host__ __device__ __forceinline__ unsigned int img_funnel_r(unsigned int lo, unsigned int hi, unsigned int bytes) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, bytes * 8);
+#else
+  return bytes == 0 ? lo : (lo >> (bytes * 8)) | (hi << (32 - bytes * 8));
+#endif
+}
+
+__host__ __device__ __forceinline__ void img_resample_rgb8(const unsigned char* src, const int* coef, int cnt, unsigned char* dst) {
+  const uintptr_t a = (uintptr_t)src;
+  const unsigned int* wp = (const unsigned int*)(a & ~(uintptr_t)3);
+  const unsigned int mis = (unsigned int)(a & 3);
+  unsigned int w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = wp[i];
+  unsigned int al[7];                                  // 28 bytes starting at src
+#pragma unroll
+  for (int i = 0; i < 7; ++i) al[i] = img_funnel_r(w[i], w[i + 1], mis);
+  int s0 = 1 << (32 - 8 - 2 - 1), s1 = s0, s2 = s0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < cnt) {
+      const int k = coef[j];
+      const int b0 = j * 3, b1 = j * 3 + 1, b2 = j * 3 + 2;
+      s0 += (int)((al[b0 >> 2] >> ((b0 & 3) * 8)) & 0xFFu) * k;
+      s1 += (int)((al[b1 >> 2] >> ((b1 & 3) * 8)) & 0xFFu) * k;
+      s2 += (int)((al[b2 >> 2] >> ((b2 & 3) * 8)) & 0xFFu) * k;
+    }
+  }
+  s0 >>= (32 - 8 - 2); s1 >>= (32 - 8 - 2); s2 >>= (32 - 8 - 2);
+  dst[0] = (unsigned char)(s0 < 0 ? 0 : (s0 > 255 ? 255 : s0));
+  dst[1] = (unsigned char)(s1 < 0 ? 0 : (s1 > 255 ? 255 : s1));
+  dst[2] = (unsigned char)(s2 < 0 ? 0 : (s2 > 255 ? 255 : s2));
+}
+
+// one output pixel of the horizontal pass: word path when the window allows it, byte path otherwise (same values)
+__host__ __device__ __forceinline__ void img_horizontal_px(const unsigned char* img, long long img_bytes, long long src_off,
+                                                           const int* coef, int cnt, unsigned char* dst) {
+  const unsigned char* src = img + src_off;
+  const long long base = src_off - (long long)((uintptr_t)src & 3);
+  if (cnt >= 0 && cnt <= 8 && base >= 0 && base + 32 <= img_bytes && ((uintptr_t)img & 3) == 0) {
+    img_resample_rgb8(src, coef, cnt, dst);
+  } else {
+    dst[0] = img_resample_px(src + 0, 3, coef, cnt);
+    dst[1] = img_resample_px(src + 1, 3, coef, cnt);
+    dst[2] = img_resample_px(src + 2, 3, coef, cnt);
+  }
+}
+
 // ToTensor + Normalize of one value, float32 with correctly rounded divisions (torch: x.to(float32).div(255).sub_(mean).div_(std))
 __host__ __device__ __forceinline__ float img_normalize_px(unsigned char u, float mean, float stdv) {
 #ifdef __CUDA_ARCH__
@@ -152,13 +204,8 @@ __global__ void __launch_bounds__(256) image_horizontal_kernel(const unsigned ch
     const int ox = (int)(t % d.out_w);
     const long long r = t / d.out_w;                         // image * rows + row
     const int row = (int)(r % d.rows), im = (int)(r / d.rows);
-    const int cnt = xcnt[ox];
-    const unsigned char* src = img + (((long long)im * d.in_h + d.row_lo + row) * d.in_w + xmin[ox]) * 3;
-    const int* k = xcoef + (long long)ox * d.ksx;
-    unsigned char* dst = tmp + t * 3;
-    dst[0] = img_resample_px(src + 0, 3, k, cnt);
-    dst[1] = img_resample_px(src + 1, 3, k, cnt);
-    dst[2] = img_resample_px(src + 2, 3, k, cnt);
+    const long long off = (((long long)im * d.in_h + d.row_lo + row) * d.in_w + xmin[ox]) * 3;
+    img_horizontal_px(img, (long long)d.n * d.in_h * d.in_w * 3, off, xcoef + (long long)ox * d.ksx, xcnt[ox], tmp + t * 3);
   }
 }
 
@@ -311,9 +358,8 @@ extern "C" int isf_debug_image_aug_host(const unsigned char* img, int n, int in_
   for (int im = 0; im < n; ++im) {
     for (int row = 0; row < rows; ++row)
       for (int ox = 0; ox < out_w; ++ox) {
-        const unsigned char* src = img + (((long long)im * in_h + P.row_lo + row) * in_w + xmin[ox]) * 3;
-        for (int c = 0; c < 3; ++c)
-          tmp[((size_t)row * out_w + ox) * 3 + c] = img_resample_px(src + c, 3, xcoef + (size_t)ox * P.ksx, xcnt[ox]);
+        const long long off = (((long long)im * in_h + P.row_lo + row) * in_w + xmin[ox]) * 3;
+        img_horizontal_px(img, (long long)n * in_h * in_w * 3, off, xcoef + (size_t)ox * P.ksx, xcnt[ox], &tmp[((size_t)row * out_w + ox) * 3]);
       }
     const bool quad = (out_w * 3) % 4 == 0 && ((uintptr_t)tmp.data() & 3) == 0;     // the path the device launch takes
     for (int oy = 0; oy < out_h; ++oy) {
