@@ -33,6 +33,8 @@ step "size-independent properties at the full-frame sizes (storage-order invaria
 t 400 python -m pytest tests/test_properties.py -x -q -m gpu             >> $LOG 2>&1
 step "input contract: multi-sweep merge kernels"
 t 200 python -m pytest tests/test_input_contract.py -x -q -m gpu        >> $LOG 2>&1
+step "input-contract kernels at full size: time and GB/s"
+t 200 python scripts/bench_input_pipeline.py > gpurun_out/r2_input_pipeline.json 2>> $LOG
 step "backward kernels (dynamic scatter K3b, deformable attention K9b)"
 t 300 python -m pytest tests/test_backward_ops.py -x -q -m gpu           >> $LOG 2>&1
 step "own dense 3x3 convs on the implicit-GEMM kernel"
