@@ -2,7 +2,9 @@
 """Input-contract kernels at the config's real sizes (round-2 bring-up tool, GPU only): CUDA-event time and achieved GB/s of
   * isf_merge_sweeps          key frame + 10 sweeps, ~300 k points (20 B read + 20 B write per point; + 8 B with the close filter)
   * isf_image_aug_normalize   6 cameras 1600x900 uint8 -> resize 0.72 -> crop 384x1056 -> normalised fp16 / fp32
-against the algorithmic bytes (inputs resident in HBM; L2 flushed between repetitions by rotating 8 distinct inputs), plus
+against the algorithmic bytes (inputs resident in HBM; 8 distinct inputs rotated).  NOTE: a call is a few microseconds of kernel
+time behind ~50 us of Python / ctypes argument marshalling, so `ms` is per CALL (host-paced) and `gbps` a lower bound; the kernel
+times proper come from the ncu launch list (`ncu -k regex:merge_|image_ ...`).  Plus
 the same through the host-facing pipeline classes with pinned host buffers (H2D inside the timed region).
     python scripts/bench_input_pipeline.py [--reps 50]
 """
