@@ -27,3 +27,6 @@ ncu --clock-control none --metrics $METRICS -k regex:'gemm|nbr_|bitmap_|vfe_|vox
     --launch-skip 85 --launch-count 120 --csv --log-file gpurun_out/own_kernels_$TAG.csv \
     python bench.py --eager-only --steps 1 --warmup 1 --frames 2 >> gpurun_out/profile_$TAG.log 2>&1
 ls -la gpurun_out | tail -12
+# input-contract kernels (multi-sweep merge, camera resample + normalise) at the config's sizes: time + DRAM bytes per launch
+ncu --clock-control none --metrics $METRICS -k regex:'merge_|image_' --launch-count 40 --csv --log-file gpurun_out/input_kernels_$TAG.csv \
+    python scripts/bench_input_pipeline.py --reps 2 >> gpurun_out/profile_$TAG.log 2>&1
