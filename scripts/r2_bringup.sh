@@ -37,6 +37,8 @@ step "input-contract kernels at full size: time and GB/s"
 t 200 python scripts/bench_input_pipeline.py > gpurun_out/r2_input_pipeline.json 2>> $LOG
 step "backward kernels (dynamic scatter K3b, deformable attention K9b)"
 t 300 python -m pytest tests/test_backward_ops.py -x -q -m gpu           >> $LOG 2>&1
+step "configs[4] at full size: 1 M points, eager, per-stage times"
+t 300 python scripts/bench_config5.py > gpurun_out/r2_config5.json 2>> $LOG
 step "own dense 3x3 convs on the implicit-GEMM kernel"
 t 300 python -m pytest tests/test_conv2d_own.py -x -q -m gpu             >> $LOG 2>&1
 step "per-layer A/B: tile orders on the validated kernel"
