@@ -528,3 +528,39 @@ def test_full_detector_built_from_the_config_runs_end_to_end_on_the_emulator(mon
         net(return_loss=True)
     with pytest.raises(TypeError):
         net(return_loss=False, points=pts[0], img_metas=[[dict()]])
+
+
+def test_config5_geometry_host_logic_against_the_oracle(monkeypatch):
+    """BASELINE configs[4] geometry (0.05 m voxels, 2048^2 x 41 grid, 256x256 BEV: partial 6x6 windows, the 256-grid channel
+    attention, a 172 M-cell coordinate bitmap) through the product detector on the ABI emulator versus the oracle neck with
+    the same weights — the CPU twin of the gated tests/test_config5_gpu.py."""
+    import abi_emulator
+    import synth
+    import isfusion_b200.detector as det
+    from oracle import model as omodel
+    abi_emulator.install(monkeypatch)
+    torch.manual_seed(0)
+    pc_range = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    cfg = synth.neck_config(voxel_size=[0.05, 0.05, 0.2], pc_range=pc_range, out_size_factor=8)
+    assert cfg['bev_size'] == 256 and cfg['pts_middle_encoder']['sparse_shape'] == [41, 2048, 2048]
+    ref = synth.randomize_bn(omodel.ISFusionNeck(cfg, shuffle_voxels=False)).eval()
+    net = det.ISFusionDetector(
+        pts_voxel_layer=dict(point_cloud_range=pc_range, max_num_points=-1, voxel_size=cfg['voxel_size'], max_voxels=(-1, -1)),
+        pts_voxel_encoder=dict(type='DynamicVFE', **cfg['pts_voxel_encoder']),
+        pts_middle_encoder=dict(type='SparseEncoder', **cfg['pts_middle_encoder']),
+        fusion_encoder=dict(type='ISFusionEncoder', **cfg['fusion_encoder']),
+        pts_backbone=dict(type='SECONDV2', **cfg['pts_backbone']),
+        detach=True, pc_range=pc_range, voxel_size=cfg['voxel_size'], out_size_factor=8)
+    net.load_state_dict(ref.state_dict())
+    net = net.eval()
+    pts = [synth.make_points(4000, 'S', 3, pc_range)]
+    l2i, aug, laug = synth.make_calib(1)
+    feats = synth.make_img_feats(1)
+    metas = [dict(input_shape=(256, 704))]
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    gf, ghm = net(pts, feats, metas, **kw)
+    rf, rhm = ref(pts, feats, metas, **kw)
+    assert tuple(gf[0].shape) == tuple(rf[0].shape) == (1, 128, 256, 256) and tuple(gf[1].shape) == tuple(rf[1].shape) == (1, 256, 128, 128)
+    for a, b in zip(list(gf) + [ghm], list(rf) + [rhm]):
+        r = ((a.float() - b).norm() / b.norm()).item()
+        assert r < 1e-2, r
