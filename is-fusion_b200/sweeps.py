@@ -195,3 +195,40 @@ class LoadMultiViewImageFromFilesV2:
         results['img_shape'] = results['ori_shape'] = results['pad_shape'] = images[0].size
         results['scale_factor'] = 1.0
         return results
+
+
+@PIPELINES.register_module()
+class Collect3DV2:
+    """ref: formating.py:183-254.  Same key sets; the values the reference wraps in mmcv DataContainers are plain tensors
+    here (`meta_keys`: float tensors, lists stacked) and `img_metas` is the plain dict of the `meta_lis_keys` present."""
+
+    def __init__(self, keys, meta_keys=('camera_intrinsics', 'camera2ego', 'img_aug_matrix', 'lidar_aug_matrix'),
+                 meta_lis_keys=('filename', 'timestamp', 'ori_shape', 'img_shape', 'lidar2image', 'depth2img', 'cam2img', 'pad_shape',
+                                'scale_factor', 'flip', 'pcd_horizontal_flip', 'pcd_vertical_flip', 'box_mode_3d', 'box_type_3d',
+                                'img_norm_cfg', 'pcd_trans', 'token', 'pcd_scale_factor', 'pcd_rotation', 'lidar_path',
+                                'transformation_3d_flow', 'img_mask_idx')):
+        self.keys, self.meta_keys, self.meta_lis_keys = keys, meta_keys, meta_lis_keys
+
+    def __call__(self, results):
+        data = {}
+        for key in self.keys:
+            if key not in self.meta_keys:
+                val = results[key]
+                data[key] = torch.stack(list(val)) if key == 'img' and isinstance(val, (list, tuple)) else val   # DefaultFormatBundle3D's stack
+        for key in self.meta_keys:
+            if key in results:
+                data[key] = torch.as_tensor(np.array(results[key]))
+        data['img_metas'] = {k: results[k] for k in self.meta_lis_keys if k in results}
+        return data
+
+
+def collate(samples):
+    """the batch `forward(return_loss=False, **batch)` takes (mmcv collate + scatter + MultiScaleFlipAug3D's single-entry outer
+    lists): points -> [[per-sample tensors]], img -> [[B, N, 3, H, W]], img_metas -> [[dicts]], matrices -> [B, ...]."""
+    batch = {'points': [[s['points'] for s in samples]], 'img_metas': [[s['img_metas'] for s in samples]]}
+    if 'img' in samples[0]:
+        batch['img'] = [torch.stack([s['img'] for s in samples])]
+    for key in samples[0]:
+        if key not in ('points', 'img', 'img_metas'):
+            batch[key] = torch.stack([torch.as_tensor(s[key]) for s in samples])
+    return batch

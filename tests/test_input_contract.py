@@ -311,3 +311,57 @@ def test_image_kernel_source_scalar_and_word_paths_against_the_oracle(fw):
         L.check(L.lib().isf_debug_image_aug_host(p(np.ascontiguousarray(img)), 1, w, h, dims[0], dims[1], crop[0], crop[1], fw, 90, int(flip),
                                                  L.host_f32(gc.IMG_NORM['mean']), L.host_f32(gc.IMG_NORM['std']), p(out)))
         assert np.array_equal(out[0], want), (fw, flip)
+
+
+def test_files_to_boxes_through_the_reference_entry_point(tmp_path, monkeypatch):
+    """the whole inference story on the CPU emulator: sweep / camera FILES -> the config's test-time transforms (built by name)
+    -> Collect3DV2 -> collate -> `detector(return_loss=False, **batch)` (the reference's call, detectors/base.py:46-62) ->
+    decoded boxes.  The detector is the config's whole model (synth.full_model_config)."""
+    PIL = pytest.importorskip('PIL.Image')
+    import abi_emulator
+    import synth
+    import isfusion_b200.head as H
+    import isfusion_b200.img_neck as N
+    import isfusion_b200.image_pipeline as IP
+    from isfusion_b200.sweeps import Compose, collate
+    from __graft_entry__ import make_full_net
+    abi_emulator.install(monkeypatch)
+    monkeypatch.setattr(IP, '_PLANS', {})
+    monkeypatch.setattr(H, '_conv', abi_emulator._conv_cpu)
+    monkeypatch.setattr(N, '_conv', abi_emulator._conv_cpu)
+    key, ts, sweeps = gc.sweep_inputs(n_key=1500, n_sweeps=3, n_sweep=800)
+    key.tofile(str(tmp_path / 'key.bin'))
+    infos = []
+    for i, s in enumerate(sweeps):
+        s['points'].tofile(str(tmp_path / ('s%d.bin' % i)))
+        infos.append(dict(data_path=str(tmp_path / ('s%d.bin' % i)), timestamp=s['timestamp'],
+                          sensor2lidar_rotation=s['sensor2lidar_rotation'], sensor2lidar_translation=s['sensor2lidar_translation']))
+    names = []
+    for i, img in enumerate(gc.camera_images(n=6, hw=(90, 160))):
+        PIL.fromarray(img).save(str(tmp_path / ('cam%d.png' % i)))
+        names.append(str(tmp_path / ('cam%d.png' % i)))
+    pipe = Compose([
+        dict(type='LoadPointsFromFile', coord_type='LIDAR', load_dim=5, use_dim=5, painting=False),
+        dict(type='LoadPointsFromMultiSweeps', sweeps_num=10, use_dim=[0, 1, 2, 3, 4], painting=False, device='cpu'),
+        dict(type='LoadMultiViewImageFromFilesV2', to_float32=True),
+        dict(type='ImageAug3D', final_dim=(64, 96), resize_lim=[0.72, 0.72], bot_pct_lim=[0.0, 0.0], rot_lim=[0.0, 0.0], rand_flip=False,
+             is_train=False),
+        dict(type='ImageNormalize', device='cpu', out_dtype=torch.float16, **gc.IMG_NORM),
+        dict(type='GlobalRotScaleTransV2', resize_lim=[1.0, 1.0], rot_lim=[0.0, 0.0], trans_lim=0.0, is_train=False),
+        dict(type='PointsRangeFilter', point_cloud_range=[-54, -54, -5, 54, 54, 3]),
+        dict(type='Collect3DV2', keys=['points', 'img'],
+             meta_keys=['camera_intrinsics', 'camera2ego', 'lidar2ego', 'lidar2camera', 'camera2lidar', 'lidar2img', 'img_aug_matrix',
+                        'lidar_aug_matrix']),
+    ])
+    l2i = synth.make_calib(1, img_hw=(64, 96))[0][0]                       # [6, 4, 4] of the sample
+    sample = pipe(dict(pts_filename=str(tmp_path / 'key.bin'), timestamp=ts, sweeps=infos, img_filename=names, lidar2img=list(l2i.numpy())))
+    assert tuple(sample['img'].shape) == (6, 3, 64, 96) and sample['img'].dtype == torch.float16
+    assert tuple(sample['img_aug_matrix'].shape) == (6, 4, 4) and tuple(sample['lidar_aug_matrix'].shape) == (4, 4)
+    assert sample['img_metas']['ori_shape'] == (160, 90) and 'img_norm_cfg' in sample['img_metas']
+    batch = collate([sample])
+    assert tuple(batch['img'][0].shape) == (1, 6, 3, 64, 96) and tuple(batch['lidar2img'].shape) == (1, 6, 4, 4)
+    net = make_full_net(0).eval()
+    res = net(return_loss=False, **batch)
+    box = res[0]['pts_bbox']
+    assert box['boxes_3d'].shape == (200, 9) and torch.isfinite(box['boxes_3d'].float()).all()
+    assert batch['img_metas'][0][0]['input_shape'] == (64, 96)            # recorded by extract_img_feat for the projection
