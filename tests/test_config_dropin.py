@@ -115,3 +115,25 @@ def test_synthetic_full_model_config_equals_the_reference_config():
     left_out = set(ref) - set(mine)
     assert left_out == {'train_cfg'}, left_out
     assert set(ref['pts_bbox_head']) - set(mine['pts_bbox_head']) == {'loss_cls', 'loss_bbox', 'loss_heatmap'}
+
+
+def test_load_checkpoint_helper(tmp_path, capsys):
+    """a checkpoint saved the way mmcv does (`{'meta', 'state_dict'}` with DataParallel's `module.` prefix, sparse-conv weights
+    in the spconv2 layout) loads into the B200 modules; key problems are reported, `strict` raises."""
+    import pytest as _pytest
+    import torch
+    import isfusion_b200.spconv as sp
+    from isfusion_b200.checkpoint import load_checkpoint
+    src = torch.nn.Sequential(sp.SubMConv3d(16, 32, 3, padding=1, bias=False), torch.nn.BatchNorm1d(32))
+    torch.nn.init.normal_(src[0].weight)
+    sd = {'module.' + k: v.clone() for k, v in src.state_dict().items()}
+    sd['module.0.weight'] = sd['module.0.weight'].permute(4, 0, 1, 2, 3).contiguous()          # spconv2 layout
+    sd['module.extra.bias'] = torch.zeros(3)
+    path = str(tmp_path / 'ckpt.pth')
+    torch.save({'meta': {'epoch': 10}, 'state_dict': sd}, path)
+    dst = torch.nn.Sequential(sp.SubMConv3d(16, 32, 3, padding=1, bias=False), torch.nn.BatchNorm1d(32))
+    ckpt = load_checkpoint(dst, path)
+    assert ckpt['meta']['epoch'] == 10 and torch.equal(dst[0].weight, src[0].weight) and torch.equal(dst[1].running_var, src[1].running_var)
+    assert 'unexpected key' in capsys.readouterr().out
+    with _pytest.raises(RuntimeError):
+        load_checkpoint(dst, path, strict=True)
