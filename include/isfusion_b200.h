@@ -112,16 +112,18 @@ int isf_dynamic_point_to_voxel_backward(float* grad_feats, const float* grad_red
  * seg_start[S] = m), rot [S,3,3] / trans [S,3] = sensor2lidar_rotation / _translation (float64, read only where
  * seg_flags bit 0 is set), lag [S] = value of column 4 (ts - sweep_ts, 0 for the key frame), seg_flags [S]: bit 0 =
  * rotate + translate, bit 1 = drop points with |x| < radius and |y| < radius (tested on the raw coordinates).
+ * range (HOST [6] or NULL): PointsRangeFilter fused (transforms_3d.py:2002-2037, BasePoints.in_range_3d): only points
+ * strictly inside (x0,y0,z0,x1,y1,z1) after the transform are kept.
  * out [m, 5] fp32 (capacity m rows, input order kept), *count_dev = rows written.  float64 arithmetic rounded to
  * float32 after the rotation and after the translation, as numpy does on the reference's float32 arrays. */
 int isf_merge_sweeps_workspace_size(int m, size_t* bytes);
 int isf_merge_sweeps(const float* raw, int m, int load_dim, int num_segments, const int* seg_start, const double* rot,
-                     const double* trans, const double* lag, const int* seg_flags, float radius, float* out,
-                     int* count_dev, void* workspace, size_t ws_bytes, void* stream);
+                     const double* trans, const double* lag, const int* seg_flags, float radius, const float* range,
+                     float* out, int* count_dev, void* workspace, size_t ws_bytes, void* stream);
 /* TEST HOOK: the kernels' own per-point source (shared host/device) on HOST memory; *count = rows written. */
 int isf_debug_merge_sweeps_host(const float* raw, int m, int load_dim, int num_segments, const int* seg_start,
                                 const double* rot, const double* trans, const double* lag, const int* seg_flags,
-                                float radius, float* out, int* count);
+                                float radius, const float* range, float* out, int* count);
 
 /* ---- input contract, camera side: ImageAug3D + ImageNormalize -----------
  * replaces the PIL / torchvision pixel work of mmdet3d/datasets/pipelines/transforms_3d.py:25-43 (ImageNormalize:

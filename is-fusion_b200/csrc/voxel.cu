@@ -409,6 +409,8 @@ struct MergeTable {
   double trans[MERGE_MAX_SEGMENTS][3];
   double lag[MERGE_MAX_SEGMENTS];
   float radius;
+  int use_range;                          // PointsRangeFilter fused: keep only points STRICTLY inside range (after the transform)
+  float range[6];
 };
 
 __host__ __device__ __forceinline__ int merge_segment_of(const MergeTable& T, int row) {
@@ -420,6 +422,11 @@ __host__ __device__ __forceinline__ int merge_segment_of(const MergeTable& T, in
 __host__ __device__ __forceinline__ bool merge_keeps(const MergeTable& T, int s, const float* p) {
   if (!(T.flags[s] & 2)) return true;
   return !(fabsf(p[0]) < T.radius && fabsf(p[1]) < T.radius);
+}
+
+// BasePoints.in_range_3d (core/points/base_points.py:224-229) on a merged point: strictly inside on all six faces
+__host__ __device__ __forceinline__ bool merge_in_range(const MergeTable& T, const float* v) {
+  return v[0] > T.range[0] && v[1] > T.range[1] && v[2] > T.range[2] && v[0] < T.range[3] && v[1] < T.range[4] && v[2] < T.range[5];
 }
 
 // one point of segment s: in = raw row (>= 5 columns), out = 5 columns
@@ -443,7 +450,14 @@ __global__ void __launch_bounds__(256) merge_flags_kernel(const float* __restric
                                                           const __grid_constant__ MergeTable T, int* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  flags[i] = merge_keeps(T, merge_segment_of(T, i), raw + (size_t)i * load_dim) ? 1 : 0;
+  const int s = merge_segment_of(T, i);
+  bool keep = merge_keeps(T, s, raw + (size_t)i * load_dim);
+  if (keep && T.use_range) {
+    float v[5];
+    merge_point(T, s, raw + (size_t)i * load_dim, v);
+    keep = merge_in_range(T, v);
+  }
+  flags[i] = keep ? 1 : 0;
 }
 
 // pos == nullptr: no segment removes points (out row = in row)
@@ -464,12 +478,14 @@ __global__ void __launch_bounds__(256) merge_write_kernel(const float* __restric
 }
 
 static int merge_fill_table(MergeTable* T, int m, int num_segments, const int* seg_start, const double* rot,
-                            const double* trans, const double* lag, const int* seg_flags, float radius, bool* any_remove) {
+                            const double* trans, const double* lag, const int* seg_flags, float radius, const float* range, bool* any_remove) {
   ISF_CHECK_ARG(num_segments >= 1 && num_segments <= MERGE_MAX_SEGMENTS && seg_start && seg_flags && lag);
   ISF_CHECK_ARG(seg_start[0] == 0 && seg_start[num_segments] == m);
   T->n = num_segments;
   T->radius = radius;
-  *any_remove = false;
+  T->use_range = range ? 1 : 0;
+  for (int e = 0; e < 6; ++e) T->range[e] = range ? range[e] : 0.f;
+  *any_remove = range != nullptr;
   for (int s = 0; s < num_segments; ++s) {
     ISF_CHECK_ARG(seg_start[s + 1] >= seg_start[s]);
     T->start[s] = seg_start[s];
@@ -496,16 +512,17 @@ extern "C" int isf_merge_sweeps_workspace_size(int m, size_t* bytes) {
 
 // raw [m, load_dim] fp32 (load_dim >= 5; DEVICE), segment tables on the HOST (<= 24 segments: key frame + sweeps),
 // out [m, 5] fp32 (capacity m rows), *count_dev = rows written.  seg_flags: bit 0 = transform, bit 1 = remove close.
+// range (HOST [6] or NULL) = PointsRangeFilter fused: only points strictly inside (x0,y0,z0,x1,y1,z1) after the transform.
 extern "C" int isf_merge_sweeps(const float* raw, int m, int load_dim, int num_segments, const int* seg_start,
                                 const double* rot, const double* trans, const double* lag, const int* seg_flags, float radius,
-                                float* out, int* count_dev, void* workspace, size_t ws_bytes, void* stream) {
+                                const float* range, float* out, int* count_dev, void* workspace, size_t ws_bytes, void* stream) {
   ISF_CHECK_ARG(m >= 0 && load_dim >= 5 && count_dev);
   cudaStream_t st = (cudaStream_t)stream;
   if (m == 0) { ISF_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int), st)); return ISF_OK; }
   ISF_CHECK_ARG(raw && out);
   MergeTable T;
   bool any_remove = false;
-  int rc = merge_fill_table(&T, m, num_segments, seg_start, rot, trans, lag, seg_flags, radius, &any_remove);
+  int rc = merge_fill_table(&T, m, num_segments, seg_start, rot, trans, lag, seg_flags, radius, range, &any_remove);
   if (rc) return rc;
   const int blocks = isf_cdiv(m, 256);
   if (!any_remove) {
@@ -531,20 +548,23 @@ extern "C" int isf_merge_sweeps(const float* raw, int m, int load_dim, int num_s
 // TEST HOOK (host memory, no GPU): merge_segment_of / merge_keeps / merge_point — the kernels' own source — on the CPU.
 extern "C" int isf_debug_merge_sweeps_host(const float* raw, int m, int load_dim, int num_segments, const int* seg_start,
                                            const double* rot, const double* trans, const double* lag, const int* seg_flags,
-                                           float radius, float* out, int* count) {
+                                           float radius, const float* range, float* out, int* count) {
   ISF_CHECK_ARG(m >= 0 && load_dim >= 5 && count && (m == 0 || (raw && out)));
   *count = 0;
   if (m == 0) return ISF_OK;
   MergeTable T;
   bool any_remove = false;
-  int rc = merge_fill_table(&T, m, num_segments, seg_start, rot, trans, lag, seg_flags, radius, &any_remove);
+  int rc = merge_fill_table(&T, m, num_segments, seg_start, rot, trans, lag, seg_flags, radius, range, &any_remove);
   if (rc) return rc;
   int o = 0;
   for (int i = 0; i < m; ++i) {
     const int s = merge_segment_of(T, i);
     const float* p = raw + (size_t)i * load_dim;
     if (!merge_keeps(T, s, p)) continue;
-    merge_point(T, s, p, out + (size_t)o * 5);
+    float v[5];
+    merge_point(T, s, p, v);
+    if (T.use_range && !merge_in_range(T, v)) continue;
+    for (int c = 0; c < 5; ++c) out[(size_t)o * 5 + c] = v[c];
     ++o;
   }
   *count = o;

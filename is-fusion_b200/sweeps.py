@@ -15,9 +15,10 @@ from . import _lib as L
 from .registry import PIPELINES
 
 
-def merge_sweeps(raw, seg_start, seg_flags, lag, rot=None, trans=None, radius=1.0, load_dim=5):
+def merge_sweeps(raw, seg_start, seg_flags, lag, rot=None, trans=None, radius=1.0, load_dim=5, point_cloud_range=None):
     """raw [M, load_dim] fp32 DEVICE tensor (key frame + sweeps, in order); seg_start [S+1] row offsets; seg_flags [S]
-    (bit 0: transform, bit 1: remove close); lag [S] seconds; rot [S,3,3] / trans [S,3] float64 (host).  Returns
+    (bit 0: transform, bit 1: remove close); lag [S] seconds; rot [S,3,3] / trans [S,3] float64 (host); point_cloud_range =
+    PointsRangeFilter fused into the same pass (strictly-inside test on the merged coordinates).  Returns
     (points [M, 5] fp32 with capacity M rows, count [1] int32 device = rows valid)."""
     L.require_cuda(raw)
     if raw.dtype != torch.float32 or raw.dim() != 2 or raw.size(1) != load_dim:
@@ -33,8 +34,8 @@ def merge_sweeps(raw, seg_start, seg_flags, lag, rot=None, trans=None, radius=1.
     dbl = lambda a: (ctypes.c_double * a.size)(*[float(v) for v in a.reshape(-1)])
     L.check(L.lib().isf_merge_sweeps(
         L.ptr(raw), m, load_dim, s, L.host_i32(seg_start), dbl(rot), dbl(trans), dbl(np.asarray(lag, dtype=np.float64)),
-        L.host_i32(seg_flags), ctypes.c_float(radius), L.ptr(out), L.ptr(count), L.ptr(ws), ctypes.c_size_t(ws.numel()),
-        L.stream()))
+        L.host_i32(seg_flags), ctypes.c_float(radius), L.host_f32(point_cloud_range) if point_cloud_range is not None else None,
+        L.ptr(out), L.ptr(count), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
     return out, count
 
 
@@ -45,12 +46,15 @@ class LoadPointsFromMultiSweeps(object):
     sensor2lidar_rotation, sensor2lidar_translation).  A sweep dict may carry its raw `points` array instead of a file."""
 
     def __init__(self, sweeps_num=10, load_dim=5, use_dim=[0, 1, 2, 4], file_client_args=dict(backend='disk'),
-                 pad_empty_sweeps=False, remove_close=False, test_mode=False, painting=False, device='cuda'):
+                 pad_empty_sweeps=False, remove_close=False, test_mode=False, painting=False, device='cuda',
+                 point_cloud_range=None):
         if painting:
             raise NotImplementedError('LoadPointsFromMultiSweeps: painting is outside the path')
         self.load_dim, self.sweeps_num, self.use_dim = load_dim, sweeps_num, list(use_dim)
         self.pad_empty_sweeps, self.remove_close, self.test_mode = pad_empty_sweeps, remove_close, test_mode
         self.device = device
+        # extension: the pipeline's later PointsRangeFilter folded into the merge kernel (same points, one pass, one count)
+        self.point_cloud_range = None if point_cloud_range is None else [float(v) for v in np.asarray(point_cloud_range, dtype=np.float32)]
 
     def _load_points(self, sweep):
         if 'points' in sweep:
@@ -96,8 +100,10 @@ class LoadPointsFromMultiSweeps(object):
             host = host.pin_memory()
         np.concatenate(blocks, 0, out=host.numpy())
         raw = host.to(self.device, non_blocking=True)
-        pts, count = merge_sweeps(raw, seg_start, flags, lag, rot, trans, radius=1.0, load_dim=self.load_dim)
-        n = m if not self.remove_close else int(count.item())        # only the filter makes the size data dependent
+        pts, count = merge_sweeps(raw, seg_start, flags, lag, rot, trans, radius=1.0, load_dim=self.load_dim,
+                                  point_cloud_range=self.point_cloud_range)
+        filtered = self.remove_close or self.point_cloud_range is not None
+        n = int(count.item()) if filtered else m                     # only the filters make the size data dependent
         results['points'] = pts[:n][:, self.use_dim]
         return results
 

@@ -454,7 +454,8 @@ class VoxelMixin:
         _set_size(bytes_ref, 256)
         return 0
 
-    def isf_merge_sweeps(self, raw, m, load_dim, nseg, seg_start, rot, trans, lag, seg_flags, radius, out, count, ws, ws_bytes, stream):
+    def isf_merge_sweeps(self, raw, m, load_dim, nseg, seg_start, rot, trans, lag, seg_flags, radius, rng, out, count, ws, ws_bytes,
+                         stream):
         from oracle import input_ops
         import numpy as np
         r = raw.numpy()
@@ -471,6 +472,9 @@ class VoxelMixin:
             ps[:, 4] = lag[s]
             parts.append(ps[:, :5])
         res = np.concatenate(parts, 0)
+        if rng is not None:                                    # BasePoints.in_range_3d on the merged cloud
+            r = np.array(list(rng), dtype=np.float32)
+            res = res[(res[:, 0] > r[0]) & (res[:, 1] > r[1]) & (res[:, 2] > r[2]) & (res[:, 0] < r[3]) & (res[:, 1] < r[4]) & (res[:, 2] < r[5])]
         out[:res.shape[0]].copy_(torch.from_numpy(res))
         count.fill_(res.shape[0])
         return 0

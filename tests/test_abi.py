@@ -144,12 +144,12 @@ def test_backward_and_input_entry_points_validate_arguments():
     one = (ctypes.c_double * 1)(0.0)
     # segments must tile [0, m] exactly; at most 24 segments; load_dim >= 5
     args = lambda start, nseg=1, load_dim=5: (raw, 10, load_dim, nseg, L.host_i32(start), None, None, one, L.host_i32([0] * max(nseg, 1)),
-                                               ctypes.c_float(1.0), out, ctypes.byref(cnt))
+                                               ctypes.c_float(1.0), None, out, ctypes.byref(cnt))
     assert lib.isf_debug_merge_sweeps_host(*args([0, 10])) == 0 and cnt.value == 10
     assert lib.isf_debug_merge_sweeps_host(*args([0, 9])) == 1
     assert lib.isf_debug_merge_sweeps_host(*args([1, 10])) == 1
     assert lib.isf_debug_merge_sweeps_host(*args([0, 10], load_dim=4)) == 1
     assert lib.isf_debug_merge_sweeps_host(*args([0] * 26, nseg=25)) == 1
     # a transforming segment needs its calibration
-    assert lib.isf_debug_merge_sweeps_host(raw, 10, 5, 1, L.host_i32([0, 10]), None, None, one, L.host_i32([1]), ctypes.c_float(1.0), out,
+    assert lib.isf_debug_merge_sweeps_host(raw, 10, 5, 1, L.host_i32([0, 10]), None, None, one, L.host_i32([1]), ctypes.c_float(1.0), None, out,
                                            ctypes.byref(cnt)) == 1

@@ -27,7 +27,7 @@ def _results(n_sw):
     return dict(points=key, timestamp=ts, sweeps=sweeps[:n_sw])
 
 
-def _host_merge(loader, results):
+def _host_merge(loader, results, rng=None):
     """the plan of the product loader through the host-compiled kernel source."""
     from isfusion_b200 import _lib as L
     blocks, seg_start, flags, lag, rot, trans = loader.plan(results)
@@ -38,7 +38,8 @@ def _host_merge(loader, results):
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     dbl = lambda a: (ctypes.c_double * a.size)(*[float(v) for v in np.asarray(a, dtype=np.float64).reshape(-1)])
     L.check(L.lib().isf_debug_merge_sweeps_host(p(raw), m, 5, s, L.host_i32(seg_start), dbl(rot), dbl(trans), dbl(np.array(lag)),
-                                                L.host_i32(flags), ctypes.c_float(1.0), p(out), ctypes.byref(count)))
+                                                L.host_i32(flags), ctypes.c_float(1.0), L.host_f32(rng) if rng is not None else None, p(out),
+                                                ctypes.byref(count)))
     return out[:count.value]
 
 
@@ -365,3 +366,23 @@ def test_files_to_boxes_through_the_reference_entry_point(tmp_path, monkeypatch)
     box = res[0]['pts_bbox']
     assert box['boxes_3d'].shape == (200, 9) and torch.isfinite(box['boxes_3d'].float()).all()
     assert batch['img_metas'][0][0]['input_shape'] == (64, 96)            # recorded by extract_img_feat for the projection
+
+
+@pytest.mark.parametrize('rc', [False, True])
+def test_range_filter_fused_into_the_merge(rc, monkeypatch):
+    """point_cloud_range on the loader = the pipeline's PointsRangeFilter folded into the merge kernel: the kernel source on the
+    host and the product loader on the emulator give the reference loader's cloud filtered by the reference's in_range_3d."""
+    import abi_emulator
+    from isfusion_b200.sweeps import LoadPointsFromMultiSweeps
+    rng = [-40, -40, -3, 40, 40, 1]
+    tag = 'close' if rc else 'plain'
+    r = np.array(rng, np.float32)
+    c = G[tag]
+    want = c[(c[:, 0] > r[0]) & (c[:, 1] > r[1]) & (c[:, 2] > r[2]) & (c[:, 0] < r[3]) & (c[:, 1] < r[4]) & (c[:, 2] < r[5])]
+    if not rc:
+        assert np.array_equal(want, G['plain'][G['plain_in_range40']])          # = the reference's own mask
+    got = _host_merge(LoadPointsFromMultiSweeps(use_dim=[0, 1, 2, 3, 4], device='cpu', remove_close=rc), _results(10), rng)
+    assert np.array_equal(got, want)
+    abi_emulator.install(monkeypatch)
+    res = LoadPointsFromMultiSweeps(use_dim=[0, 1, 2, 3, 4], device='cpu', remove_close=rc, point_cloud_range=rng)(_results(10))
+    assert np.array_equal(res['points'].numpy(), want)
