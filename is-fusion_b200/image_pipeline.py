@@ -79,24 +79,20 @@ class ImageAug3D:
         self.rand_flip, self.rot_lim, self.is_train = rand_flip, rot_lim, is_train
 
     def sample_augmentation(self, results):
-        W, H = results['ori_shape']
-        fH, fW = self.final_dim
-        if self.is_train:
-            resize = np.random.uniform(*self.resize_lim)
-            resize_dims = (int(W * resize), int(H * resize))
-            newW, newH = resize_dims
-            crop_h = int((1 - np.random.uniform(*self.bot_pct_lim)) * newH) - fH
-            crop_w = int(np.random.uniform(0, max(0, newW - fW)))
-            flip = bool(self.rand_flip and np.random.choice([0, 1]))
-            rotate = np.random.uniform(*self.rot_lim)
-        else:
-            resize = np.mean(self.resize_lim)
-            resize_dims = (int(W * resize), int(H * resize))
-            newW, newH = resize_dims
-            crop_h = int((1 - np.mean(self.bot_pct_lim)) * newH) - fH
-            crop_w = int(max(0, newW - fW) / 2)
-            flip, rotate = False, 0
-        return resize, resize_dims, (crop_w, crop_h, crop_w + fW, crop_h + fH), flip, rotate
+        """(resize, resize_dims, crop, flip, rotate) of one camera.  Training draws, in the reference's order (transforms_3d.py:
+        60-70): scale, bottom fraction, horizontal offset, flip coin, angle — so a seeded run reproduces the reference's
+        augmentation; inference uses the interval means and a centred crop (:71-79)."""
+        src_w, src_h = results['ori_shape']
+        out_h, out_w = self.final_dim
+        draw = (lambda lim: np.random.uniform(*lim)) if self.is_train else (lambda lim: np.mean(lim))
+        scale = draw(self.resize_lim)
+        dims = (int(src_w * scale), int(src_h * scale))
+        top = int((1 - draw(self.bot_pct_lim)) * dims[1]) - out_h
+        slack = max(0, dims[0] - out_w)
+        left = int(np.random.uniform(0, slack)) if self.is_train else int(slack / 2)
+        flip = bool(self.is_train and self.rand_flip and np.random.choice([0, 1]))
+        angle = np.random.uniform(*self.rot_lim) if self.is_train else 0
+        return scale, dims, (left, top, left + out_w, top + out_h), flip, angle
 
     @staticmethod
     def aug_matrix(resize, crop, flip):
