@@ -15,6 +15,7 @@
 // geometry by isf_image_plan.  The per-pixel arithmetic is shared host / device source (isf_debug_image_aug_host).
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 #include "common.cuh"
 
@@ -110,6 +111,17 @@ __host__ __device__ __forceinline__ unsigned char img_resample_px(const unsigned
   return (unsigned char)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
 }
 
+// aligned 32-bit load from a byte buffer (host: through memcpy, no aliasing assumptions)
+__host__ __device__ __forceinline__ unsigned int img_load_u32(const unsigned char* p) {
+#ifdef __CUDA_ARCH__
+  return *(const unsigned int*)p;
+#else
+  unsigned int w;
+  memcpy(&w, p, 4);
+  return w;
+#endif
+}
+
 // the same for FOUR adjacent byte columns of the interleaved intermediate (vertical pass: every byte column is an independent
 // signal, the taps are whole rows apart): one aligned 32-bit load per tap instead of four byte loads.  src 4-byte aligned.
 __host__ __device__ __forceinline__ void img_resample_px4(const unsigned char* src, long long stride, const int* coef, int cnt,
@@ -117,7 +129,7 @@ __host__ __device__ __forceinline__ void img_resample_px4(const unsigned char* s
   if (cnt < 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
   int s0 = 1 << (32 - 8 - 2 - 1), s1 = s0, s2 = s0, s3 = s0;
   for (int j = 0; j < cnt; ++j) {
-    const unsigned int w = *(const unsigned int*)(src + j * stride);
+    const unsigned int w = img_load_u32(src + j * stride);
     const int k = coef[j];
     s0 += (int)(w & 0xFFu) * k;
     s1 += (int)((w >> 8) & 0xFFu) * k;
@@ -144,11 +156,11 @@ __host__ __device__ __forceinline__ unsigned int img_funnel_r(unsigned int lo, u
 
 __host__ __device__ __forceinline__ void img_resample_rgb8(const unsigned char* src, const int* coef, int cnt, unsigned char* dst) {
   const uintptr_t a = (uintptr_t)src;
-  const unsigned int* wp = (const unsigned int*)(a & ~(uintptr_t)3);
+  const unsigned char* wp = (const unsigned char*)(a & ~(uintptr_t)3);
   const unsigned int mis = (unsigned int)(a & 3);
   unsigned int w[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) w[i] = wp[i];
+  for (int i = 0; i < 8; ++i) w[i] = img_load_u32(wp + 4 * i);
   unsigned int al[7];                                  // 28 bytes starting at src
 #pragma unroll
   for (int i = 0; i < 7; ++i) al[i] = img_funnel_r(w[i], w[i + 1], mis);
