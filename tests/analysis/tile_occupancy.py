@@ -177,13 +177,14 @@ def main():
     ap.add_argument('--cloud', default='S')
     ap.add_argument('--seed', type=int, default=8)
     ap.add_argument('--all-orders', action='store_true', help='also list the spatial re-blockings (they do not help)')
+    ap.add_argument('--config5', action='store_true', help='BASELINE configs[4] geometry: 0.05 m voxels, +-51.2 m, 2048^2 x 41 grid (use --points 1000000)')
     args = ap.parse_args()
-    pts = synth.make_points(args.points, args.cloud, args.seed)
-    vs, pr = [0.075, 0.075, 0.2], synth.PC_RANGE
+    vs, pr = ([0.05, 0.05, 0.2], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]) if args.config5 else ([0.075, 0.075, 0.2], synth.PC_RANGE)
+    pts = synth.make_points(args.points, args.cloud, args.seed, pr)
     c = voxel_ops.dynamic_voxelize(pts, vs, pr)
     c = c[(c >= 0).all(1)]
     idx = torch.unique(torch.cat([torch.zeros(len(c), 1, dtype=c.dtype), c], 1), dim=0).int()
-    shape = [41, 1440, 1440]
+    shape = [41, 2048, 2048] if args.config5 else [41, 1440, 1440]
     stages = [('stage1 SubM 32', None), ('stage2 SubM 64', (1, 1, 1)), ('stage3 SubM 128', (1, 1, 1)), ('stage4 SubM 256', (0, 1, 1))]
     for name, pad in stages:
         if pad is not None:
@@ -200,7 +201,7 @@ def main():
     print('\nwhole sparse encoder (21 launches): useful %.0f GFLOP, issued now %.0f GFLOP (fill %.3f), issued with the global '
           'tile order %.0f GFLOP (fill %.3f, x%.3f)' % (tot[0] / 1e9, tot[1] / 1e9, tot[0] / tot[1], tot[2] / 1e9, tot[0] / tot[2],
                                                          tot[2] / tot[1]))
-    if args.points == 300000 and args.cloud == 'S' and args.seed == 8:
+    if args.points == 300000 and args.cloud == 'S' and args.seed == 8 and not args.config5:
         predict()
 
 
