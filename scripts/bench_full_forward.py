@@ -63,7 +63,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
-    n0 = L.lib().isf_launch_count()
+    n0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -71,7 +71,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (L.lib().isf_launch_count() - n0) // args.steps
+    launches = (L.launch_count() - n0) // args.steps
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     step(0, ev)
     torch.cuda.synchronize()
