@@ -27,7 +27,7 @@ def main():
     import isfusion_b200.spconv as spmod
     from isfusion_b200 import profiling
     torch.manual_seed(0)
-    dev = torch.device('cuda', 0)
+    dev = torch.device(os.environ.get('ISF_TOOL_DEVICE', 'cuda:0'))      # 'cpu' only for the emulator dry run in tests/
     pc_range = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
     cfg = synth.neck_config(voxel_size=[0.05, 0.05, 0.2], pc_range=pc_range, out_size_factor=8)
     net = synth.randomize_bn(det.ISFusionDetector(

@@ -30,8 +30,9 @@ def main():
     from __graft_entry__ import make_full_net
     from isfusion_b200 import _lib as L
     hw = tuple(int(v) for v in args.img.split('x'))
-    dev = torch.device('cuda', 0)
-    torch.cuda.set_device(dev)
+    dev = torch.device(os.environ.get('ISF_TOOL_DEVICE', 'cuda:0'))      # 'cpu' only for the emulator dry run in tests/
+    if dev.type == 'cuda':
+        torch.cuda.set_device(dev)
     net = make_full_net(0).to(dev).eval()
     frames = []
     for i in range(args.frames):
