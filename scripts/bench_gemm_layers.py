@@ -25,11 +25,12 @@ def main():
     ap.add_argument('--tile-order', default='', help='comma-separated chunk log2 values, e.g. 12,16,31')
     ap.add_argument('--reps', type=int, default=10)
     args = ap.parse_args()
+    dev = torch.device(os.environ.get('ISF_TOOL_DEVICE', 'cuda:0'))      # 'cpu' only for the emulator dry run in tests/
     net = make_net(0)
-    net = net.cuda().eval()
-    pts = [synth.make_points(args.points, args.cloud, 8).cuda()]
+    net = net.to(dev).eval()
+    pts = [synth.make_points(args.points, args.cloud, 8).to(dev)]
     l2i, aug, laug = synth.make_calib(1)
-    feats = [f.cuda() for f in synth.make_img_feats(1)]
+    feats = [f.to(dev) for f in synth.make_img_feats(1)]
     metas = [dict(input_shape=(256, 704))]
     kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
     orders = [None] + [int(t) for t in args.tile_order.split(',') if t]

@@ -634,7 +634,7 @@ class RowsAroundMixin:
 
 class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):
     _KINDS = None
-    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_debug_msda_backward_host', 'isf_debug_merge_sweeps_host', 'isf_debug_image_aug_host',
+    HOST_ONLY = ('isf_spconv_tile_order_bits', 'isf_debug_nbr_rows_host', 'isf_debug_swin_window_map', 'isf_debug_msda_backward_host', 'isf_debug_merge_sweeps_host', 'isf_debug_image_aug_host', 'isf_set_option',
                  'isf_version')
 
     def __init__(self, real=None):
