@@ -88,12 +88,12 @@ def test_bench_gemm_layers_dry_run(monkeypatch, capsys):
     monkeypatch.setenv('ISF_TOOL_DEVICE', 'cpu')
     monkeypatch.setattr(torch.cuda, 'Event', _Event)
     monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
-    monkeypatch.setattr(sys, 'argv', ['bench_gemm_layers', '--points', '3000', '--v2', '--tile-order', '12,31', '--reps', '1'])
+    monkeypatch.setattr(sys, 'argv', ['bench_gemm_layers', '--points', '2000', '--v2', '--tile-order', '31', '--reps', '1'])
     spec = importlib.util.spec_from_file_location('tool_gemm_layers', os.path.join(ROOT, 'scripts', 'bench_gemm_layers.py'))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()
     out = capsys.readouterr().out
-    assert out.count('bit-identical to the default path') == 5 and 'DIFFERS' not in out       # v1+ord12, v1+ord31, v2, v2+ord12, v2+ord31
+    assert out.count('bit-identical to the default path') == 3 and 'DIFFERS' not in out       # v1+ord31, v2, v2+ord31
     assert 'total ms:' in out and sp.TILE_ORDER is None
     assert L.lib().isf_set_option(b'gemm_v2', 0) == 0
