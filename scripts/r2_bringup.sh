@@ -57,6 +57,7 @@ ISF_TILE_ORDER=31 ISF_NBR_ROWS=1 t 300 python bench.py --steps 40 --warmup 5 --n
 ISF_OWN_CONV=1 t 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline                 > gpurun_out/r2_bench_ownconv.json 2>> $LOG
 step "whole-config forward (images + points -> boxes), default and with the own attention kernels"
 t 300 python scripts/bench_full_forward.py                                                   > gpurun_out/r2_full_forward.json 2>> $LOG
+t 300 python scripts/bench_full_forward.py --raw                                             > gpurun_out/r2_full_forward_raw.json 2>> $LOG
 ISF_HEAD_ATTN=own ISF_SWIN_ATTN=own t 300 python scripts/bench_full_forward.py               > gpurun_out/r2_full_forward_own_attn.json 2>> $LOG
 export ISF_EXPERIMENTAL=1
 step "v2 warp-specialised GEMM schedule: bring-up tests (bounded waits trap instead of hanging)"

@@ -62,6 +62,14 @@ def test_bench_full_forward_dry_run(monkeypatch, capsys):
     assert line['h2d_bytes_per_step'] == 3000 * 5 * 4 + 6 * 3 * 64 * 96 * 2 or line['h2d_bytes_per_step'] > 0
 
 
+def test_bench_full_forward_raw_sensor_dry_run(monkeypatch, capsys):
+    """--raw: uint8 camera frames + raw sweeps in, the input-contract kernels in front of the detector."""
+    line = _run_tool('bench_full_forward', ['--steps', '1', '--warmup', '0', '--points', '3300', '--img', '64x96', '--frames', '1', '--raw',
+                                            '--raw-hw', '90x160'], monkeypatch, capsys)
+    assert line['boxes'] == [200, 9] and line['raw_sensor_input'] is True
+    assert line['h2d_bytes_per_step'] == 3300 * 5 * 4 + 6 * 90 * 160 * 3
+
+
 def test_bench_config5_dry_run(monkeypatch, capsys):
     line = _run_tool('bench_config5', ['--steps', '1', '--warmup', '0', '--points', '4000'], monkeypatch, capsys)
     assert line['feat_shapes'] == [[1, 128, 256, 256], [1, 256, 128, 128]]
