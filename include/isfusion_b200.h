@@ -38,12 +38,12 @@ const char* isf_last_error(void);
 /* number of kernels this library has launched since the last reset (bench.py gpu_launches) */
 unsigned long long isf_launch_count(int reset);
 /* runtime options: "gemm_cluster" = 1 | 2 : thread-block-cluster size of the tcgen05 GEMM (CTAs of a cluster
- * share every weight chunk through TMA multicast).  "gemm_v2" = 0 | 1 | 2 : opt-in warp-specialised GEMM schedule
- * (csrc/tc_gemm2.cuh; 1 = sparse-conv launches, 2 = every GEMM); 0 (default) = the validated kernel.
- * "gemm_v2_zskip" / "gemm_v2_io256" = 0 | 1 : zero-skip of all-missing 4-row copies / 32-byte epilogue accesses of
- * that schedule (default 1).  "tile_order_drop_bits" = 0..26 : low occupancy-mask bits left out of the sort of
- * isf_spconv_tile_order (fewer radix passes).  "nbr_rows" = 0 | 1 : row-per-thread kernel behind
- * isf_spconv_neighbors_bitmap (one bitmap word load per (kz, ky) instead of per tap; same results). */
+ * share every weight chunk through TMA multicast).  "gemm_mt" = 1 | 2 : 128-row sub-tiles per CTA tile of the
+ * sparse-conv GEMM (2 = one weight chunk feeds 256 output rows).  "gemm_debug" = bit mask of TIMING experiments
+ * (results meaningless; csrc/tc_gemm.cuh GemmParams::debug).  "tile_order_drop_bits" = 0..26 : low occupancy-mask
+ * bits left out of the sort of isf_spconv_tile_order (fewer radix passes).  "nbr_rows" = 0 | 1 : row-per-thread
+ * kernel behind isf_spconv_neighbors_bitmap (one bitmap word load per (kz, ky) instead of per tap; same results;
+ * default 1). */
 int isf_set_option(const char* name, int value);
 
 /* ---- a1: dynamic voxelization -------------------------------------------------
@@ -197,6 +197,18 @@ int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad, int n, co
                  const float* shift, const void* residual, int ldr, int act, const float* ln_gamma,
                  const float* ln_beta, float ln_eps, void* out_f16, float* out_f32, int ldo,
                  const int* out_rows, const int* m_dev, void* stream);
+
+/* ---- a7 / a10 / a13 / a14: dense 3x3 BEV convolution (tcgen05 implicit GEMM, TMA-tiled halos) ------------
+ * replaces the nn.Conv2d(3x3, padding 1) + BN (+ReLU) modules of the neck, which the reference runs on cuDNN:
+ *   ISFusionEncoder.conv_fusion mmdet3d/models/middle_encoders/fusion_encoder.py:862-869, conv_ins / conv_scene /
+ *   conv_heatmap / heatmap_head_{1,2,3} :915-960 (call sites :1093-1146), SECONDV2 blocks + ds_layer
+ *   mmdet3d/models/backbones/second.py:127-167 (forward :200-239).
+ * x [batch,h,w,ldx] fp16 channels-last (cin <= ldx, cin % 64 == 0); w_packed [cout_pad, 9*cin] fp16, column
+ * (ky*3 + kx)*cin + c (BN folded), cout_pad in {32,64,128,256}; shift [cout_pad] fp32 (folded BN / bias) or NULL;
+ * stride 1 | 2 (stride 2: h, w even); out [batch,oh,ow,ldo] fp16, channels [0, cout_store) are written
+ * (cout_store % 8 == 0; the padded channels of w_packed are zero).  No workspace. */
+int isf_conv3x3_nhwc_f16(const void* x, int batch, int h, int w, int cin, int ldx, const void* w_packed, int cout_pad,
+                         const float* shift, int stride, int relu, void* out, int ldo, int cout_store, void* stream);
 
 /* ---- a4: sparse 3-D convolution ------------------------------------------------
  * Replaces the spconv / mmcv.ops sparse-conv stack the reference delegates to
@@ -374,6 +386,11 @@ int isf_query_scene_attention(const void* q, const void* kv, int batch, int quer
 int isf_channel_attention_workspace_size(int batch, int grid, int channels, size_t* bytes);
 int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid, int channels,
                           void* out, int ldo, void* workspace, size_t ws_bytes, void* stream);
+
+/* bring-up probe (NOT on the product path): TMA tile::gather4 of 128 rows x 64 fp16 columns into shared memory, raw
+ * shared memory (32 KiB) returned in out32k, *status_dev = 1 when the transaction completed (csrc/debug_tma.cu). */
+int isf_debug_tma_gather4(const void* a, int rows, int cols, const int* idx_dev, int col0, int variant, void* out32k,
+                          int* status_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,18 +1,19 @@
-"""Dense 3x3 BEV convolutions on the library's own tcgen05 implicit-GEMM kernel (opt-in: ISF_OWN_CONV=1).
+"""Dense 3x3 BEV convolutions on the library's own tcgen05 kernels (no cuDNN on the product path).
 
-The neck's dense convolutions (conv_fusion 768->128, the heat-map / scene / instance convs, SECONDV2: 251 GFLOP per
-frame, fusion_encoder.py:862-958, backbones/second.py:98-239) run on cuDNN by default.  A dense 3x3 convolution over a
-channels-last BEV map [B,H,W,C] is the sparse convolution kernel's special case "every site active, 9 kernel offsets":
-the token matrix [B*H*W, C] is the feature matrix, the neighbour table is a closed form of (b, y, x) built once per
-(B, H, W, stride) and cached, and `isf_spconv_implicit_gemm` (csrc/tc_gemm.cuh: gathered rows -> swizzled smem ->
-tcgen05.mma accumulating all offsets in TMEM -> fused bias/ReLU epilogue) does the rest.  Input widths that are not a
-power of two (768 = 3 x 256) are split into channel groups: the feature matrix is viewed as [rows * groups, C / groups]
-and every (offset, group) pair becomes one virtual offset (9 x 3 = 27 <= the kernel's 27).  Output widths below 32 are
-zero-padded to 32 columns.
+The neck's dense convolutions (conv_fusion 768->128, the heat-map / scene / instance convs, SECONDV2: 203 GFLOP per
+frame, reference fusion_encoder.py:862-958, backbones/second.py:98-239) are nn.Conv2d modules in the reference.  Here:
 
-Same folded fp16 weights and fp32 accumulation as the cuDNN path; the host-side index / packing logic here is pure
-torch and is checked on the CPU against F.conv2d (tests/test_conv2d_own.py); the GPU bring-up test is gated until its
-first run (ISF_EXPERIMENTAL=1)."""
+* `BACKEND = 'tma'` (default): `isf_conv3x3_nhwc_f16` (csrc/conv2d.cu) — implicit GEMM with TMA-tiled halos: the input
+  tile (+ halo) of a CTA comes in as 4-D / 5-D tensor boxes straight into the swizzled UMMA layout, zero padding is the
+  TMA's out-of-bounds fill, the three dy taps re-use one box, folded-BN shift + ReLU in the epilogue, TMA store.
+* `BACKEND = 'gather'` (ISF_CONV=gather; also the fallback for input widths that are not a multiple of 64): the sparse
+  convolution kernel's special case "every site active, 9 kernel offsets" — the token matrix [B*H*W, C] is the feature
+  matrix, the neighbour table is a closed form of (b, y, x) cached per (B, H, W, stride) (`isf_spconv_implicit_gemm`).
+  Widths that are not a power of two (768 = 3 x 256) are split into channel groups = virtual offsets (9 x 3 = 27).
+* `BACKEND = 'cudnn'` (ISF_CONV=cudnn): the library baseline kept for A/B measurements only (scripts/bench_conv.py).
+
+Same folded fp16 weights and fp32 accumulation everywhere; the host-side index / packing logic is pure torch and is
+checked on the CPU against F.conv2d (tests/test_conv2d_own.py)."""
 import ctypes
 import os
 
@@ -20,7 +21,7 @@ import torch
 
 from . import _lib as L
 
-ENABLED = os.environ.get('ISF_OWN_CONV') == '1'
+BACKEND = os.environ.get('ISF_CONV', 'tma')          # 'tma' | 'gather' | 'cudnn' (A/B baseline only)
 _plans = {}
 _weights = {}
 
@@ -92,10 +93,10 @@ def emulate(x_nhwc, nbr, wp, shift, groups, cout, relu):
     return acc[:, :cout]
 
 
-def conv3x3(x_nhwc, packed, stride=1, relu=True):
-    """3x3 / padding 1 conv (+ folded-BN bias) (+ReLU) of a channels-last fp16 map [B,H,W,Cin] -> [B,OH,OW,Cout], or None
-    when the shape is outside what the kernel takes (the caller then uses cuDNN)."""
-    w, bias = packed
+def conv3x3_gather(x_nhwc, packed, stride=1, relu=True):
+    """3x3 / padding 1 conv (+ folded-BN bias) (+ReLU) of a channels-last fp16 map [B,H,W,Cin] -> [B,OH,OW,Cout] on the
+    sparse-conv implicit-GEMM kernel, or None when the shape is outside what the kernel takes."""
+    w, bias = packed[0], packed[1]
     cout, cin = w.shape[0], w.shape[1]
     if tuple(w.shape[2:]) != (3, 3) or stride not in (1, 2):
         return None
@@ -125,3 +126,42 @@ def conv3x3(x_nhwc, packed, stride=1, relu=True):
         L.ptr(x), cin // groups, L.ptr(wp), wp.shape[1], cpad, L.ptr(nbr), ctypes.c_longlong(nbr.shape[1]), 9 * groups, n_out,
         L.ptr(None), L.ptr(None), L.ptr(shift), L.ptr(None), 0, 1 if relu else 0, L.ptr(out), cpad, L.stream()))
     return out.view(bs, oh, ow, cpad)[..., :cout]
+
+
+def conv3x3_tma(x_nhwc, packed, stride=1, relu=True):
+    """the same conv on `isf_conv3x3_nhwc_f16` (TMA-tiled halos), or None when the shape is outside what that kernel takes
+    (input width not a multiple of 64, more than 256 output channels, odd map with stride 2)."""
+    w, bias = packed[0], packed[1]
+    cout, cin = w.shape[0], w.shape[1]
+    bs, h, wd, cx = x_nhwc.shape
+    if tuple(w.shape[2:]) != (3, 3) or stride not in (1, 2) or cin % 64 or cx != cin or cout > 256:
+        return None
+    if stride == 2 and (h % 2 or wd % 2):
+        return None
+    key = (w.data_ptr(), w._version, bias.data_ptr() if bias is not None else 0)
+    ent = _weights.get(key)
+    if ent is None:
+        b32 = packed[2] if len(packed) > 2 else bias          # fp32 folded shift when the caller kept it
+        ent = pack_dense_weight(w, b32)
+        _weights[key] = ent
+    wp, shift, cpad = ent
+    x = x_nhwc if (x_nhwc.is_contiguous() and x_nhwc.dtype == torch.float16) else x_nhwc.half().contiguous()
+    L.require_cuda(x, wp, shift)
+    oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    ldo = (cout + 7) // 8 * 8
+    out = torch.empty((bs, oh, ow, ldo), dtype=torch.float16, device=x.device)
+    L.check(L.lib().isf_conv3x3_nhwc_f16(L.ptr(x), bs, h, wd, cin, cin, L.ptr(wp), cpad, L.ptr(shift), stride, 1 if relu else 0,
+                                         L.ptr(out), ldo, ldo, L.stream()))
+    return out if ldo == cout else out[..., :cout]
+
+
+def conv3x3(x_nhwc, packed, stride=1, relu=True):
+    """3x3 / padding 1 conv (+ folded-BN shift) (+ReLU) of a channels-last fp16 map on the library's own kernels."""
+    y = None
+    if BACKEND != 'gather':
+        y = conv3x3_tma(x_nhwc, packed, stride, relu)
+    if y is None:
+        y = conv3x3_gather(x_nhwc, packed, stride, relu)
+    if y is None:
+        raise L.IsfError('conv3x3: no kernel for input %s / weight %s / stride %d' % (tuple(x_nhwc.shape), tuple(packed[0].shape), stride))
+    return y

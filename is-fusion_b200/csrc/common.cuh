@@ -61,11 +61,22 @@ struct IsfArena {
 
 __host__ __device__ inline int isf_cdiv(int a, int b) { return (a + b - 1) / b; }
 
-constexpr int ISF_NUM_SMS = 148;  // B200
+// SM count of the current device (148 on B200), cached per device ordinal
+static inline int isf_num_sms() {
+  static int cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+#define ISF_NUM_SMS isf_num_sms()
 
 extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2), defined in error.cu
-extern int g_isf_gemm_v2_zskip;   // isf_set_option("gemm_v2_zskip", 0|1): zero-skip of the v2 producers (default 1)
-extern int g_isf_gemm_v2_io256;   // isf_set_option("gemm_v2_io256", 0|1): 32-byte epilogue loads / stores of the v2 kernel (default 1)
 extern int g_isf_tile_order_drop_bits;   // isf_set_option("tile_order_drop_bits", 0..26): low mask bits left out of the tile-order sort
+extern int g_isf_gemm_mt;         // isf_set_option("gemm_mt", 1|2): 128-row sub-tiles per CTA tile of the sparse-conv GEMM
+extern int g_isf_gemm_debug;      // isf_set_option("gemm_debug", bits): timing experiments (tc_gemm.cuh GemmParams::debug)
 extern int g_isf_nbr_rows;        // isf_set_option("nbr_rows", 0|1): row-per-thread neighbour-table kernel (opt-in)
-extern int g_isf_gemm_v2;         // isf_set_option("gemm_v2", 0|1|2): opt-in warp-specialised GEMM (tc_gemm2.cuh)

@@ -26,34 +26,29 @@ extern "C" unsigned long long isf_launch_count(int reset) {
 
 // ---- runtime options
 int g_isf_gemm_cluster = 1;
-int g_isf_gemm_v2 = 0;
-int g_isf_gemm_v2_zskip = 1;
-int g_isf_gemm_v2_io256 = 1;
 int g_isf_tile_order_drop_bits = 0;
-int g_isf_nbr_rows = 0;
+int g_isf_nbr_rows = 1;
+int g_isf_gemm_mt = 1;
+int g_isf_gemm_debug = 0;
 extern "C" int isf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_cluster") == 0 && (value == 1 || value == 2)) {
     g_isf_gemm_cluster = value;
-    return ISF_OK;
-  }
-  if (name && strcmp(name, "gemm_v2") == 0 && value >= 0 && value <= 2) {
-    g_isf_gemm_v2 = value;
-    return ISF_OK;
-  }
-  if (name && strcmp(name, "gemm_v2_zskip") == 0 && (value == 0 || value == 1)) {
-    g_isf_gemm_v2_zskip = value;
     return ISF_OK;
   }
   if (name && strcmp(name, "tile_order_drop_bits") == 0 && value >= 0 && value <= 26) {
     g_isf_tile_order_drop_bits = value;
     return ISF_OK;
   }
-  if (name && strcmp(name, "nbr_rows") == 0 && (value == 0 || value == 1)) {
-    g_isf_nbr_rows = value;
+  if (name && strcmp(name, "gemm_mt") == 0 && (value == 1 || value == 2)) {
+    g_isf_gemm_mt = value;
     return ISF_OK;
   }
-  if (name && strcmp(name, "gemm_v2_io256") == 0 && (value == 0 || value == 1)) {
-    g_isf_gemm_v2_io256 = value;
+  if (name && strcmp(name, "gemm_debug") == 0 && value >= 0 && value <= 7) {
+    g_isf_gemm_debug = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "nbr_rows") == 0 && (value == 0 || value == 1)) {
+    g_isf_nbr_rows = value;
     return ISF_OK;
   }
   isf_set_error("isf_set_option: unknown option or bad value: %s=%d", name ? name : "(null)", value);

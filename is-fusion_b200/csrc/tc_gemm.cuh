@@ -37,6 +37,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait (~2 s): a protocol error traps instead of hanging the box (used by kernels under bring-up)
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 256; ++i)
+      if (mbar_try(bar, parity)) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -178,8 +200,8 @@ struct GemmParams {
   float* out_f32;         // [m, ldo] fp32 (may be nullptr)
   int ldo;
   const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
-  int v2_flags;           // tc_gemm2.cuh only (set by dispatch_gemm2): bit 0 = skip zero-fill copies of rows already zero,
-                          // bit 1 = 32-byte residual loads, bit 2 = 32-byte fp16 output stores (alignment checked by the host)
+  int debug;              // timing experiments only (isf_set_option("gemm_debug")): 1 = weight chunk loaded for the first chunk of a
+                          // tile only, 2 = every gathered row reads row 0, 4 = no A copies at all.  Results are then meaningless.
 };
 
 constexpr int BM = 128;
@@ -190,13 +212,13 @@ constexpr int MAX_CHUNKS = 512;
 constexpr int THREADS = PRODUCERS + 32;
 constexpr int PWARPS = PRODUCERS / 32;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT = 1>
 struct SmemLayout {
-  static constexpr int A_BYTES = BM * 128;
+  static constexpr int A_BYTES = MT * BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NBR_OFF = STAGES * STAGE_BYTES;            // [MAX_TAPS][128] int32 neighbour tile
-  static constexpr int LIST_OFF = NBR_OFF + MAX_TAPS * BM * 4;     // active chunk list (uint16) + flags
+  static constexpr int NBR_OFF = STAGES * STAGE_BYTES;            // [MAX_TAPS][MT*128] int32 neighbour tile
+  static constexpr int LIST_OFF = NBR_OFF + MAX_TAPS * MT * BM * 4;     // active chunk list (uint16) + flags
   static constexpr int BAR_OFF = LIST_OFF + MAX_CHUNKS * 2 + 64 * 4;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + tmem slot, + alignment slack
 };
@@ -264,12 +286,21 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
 // CS = thread-block-cluster size.  CS > 1: the CTAs of a cluster walk the same K-chunk sequence on CS consecutive
 // row tiles; each CTA TMA-loads 1/CS of the weight chunk and multicasts it to the whole cluster, so weight
 // traffic from L2 drops by CS; smem stages are recycled cluster-wide (tcgen05.commit multicast on the empty barrier).
-template <int BN, int STAGES, int CS>
+// MT = 128-row sub-tiles per CTA tile (one TMEM accumulator each): with MT = 2 one weight chunk feeds 256 output rows, which
+// halves the weight bytes an SM pulls from L2 per FLOP (the 128/256-column layers are paced by the SM's L2 read port).
+template <int BN, int STAGES, int CS, int MT>
 __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
-  using SL = SmemLayout<BN, STAGES>;
+  using SL = SmemLayout<BN, STAGES, MT>;
+  static_assert(CS == 1 || MT == 1, "clusters only with single sub-tile CTAs");
+  constexpr int TILE_M = BM * MT;
+  constexpr int TSPLIT = PRODUCERS / TILE_M;        // thread groups that split the kernel offsets in the tile prologue
+  constexpr int NVR = (MAX_TAPS + TSPLIT - 1) / TSPLIT;
+  constexpr int RPT = TILE_M * 8 / PRODUCERS;       // A rows per producer thread and chunk
   constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1);
   constexpr int SLICE_ROWS = BN / CS;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr int ACC_COLS = BN * MT;
+  static_assert(ACC_COLS <= 512, "TMEM holds 512 columns");
+  constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by offsetting the __shared__ array itself (keeps the shared address space visible to the
   // compiler: LDS/STS instead of generic LD/ST on every smem access)
@@ -281,7 +312,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_total = p.m_dev ? *p.m_dev : p.m;
-  const int num_tiles = (m_total + BM - 1) / BM;
+  const int num_tiles = (m_total + TILE_M - 1) / TILE_M;
   const int n0 = blockIdx.y * BN;
   const int num_chunks = p.kpad / BK;
 
@@ -312,32 +343,32 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
 
   for (int grp = cluster_id; grp < num_groups; grp += num_clusters, ++tile_ctr) {
     const int tile = grp * CS + crank;     // may lie beyond the last tile: the CTA then only feeds the multicast
-    const int row0 = tile * BM;
+    const int row0 = tile * TILE_M;
     // ---------------------------------------------------------------- tile prologue: neighbour tile -> smem,
     // list of K-chunks that have at least one neighbour in this tile (empty kernel offsets are skipped)
     if (warp < PWARPS) {
       if (gather) {
-        const int r = tid & (BM - 1);          // row of the tile; the two thread halves split the kernel offsets
-        const int thalf = tid >> 7;
+        const int r = tid % TILE_M;            // row of the tile; the thread groups split the kernel offsets
+        const int thalf = tid / TILE_M;
         if (tid < 33) tap_flag[tid] = 0;
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
         for (int cs = 0; cs < CS; ++cs) {       // flags = union over the cluster's tiles (same chunk list everywhere)
-          const long long prow = (long long)(grp * CS + cs) * BM + r;
+          const long long prow = (long long)(grp * CS + cs) * TILE_M + r;
           const bool pok = prow < m_total;
           // all neighbour loads of this row are issued before any is consumed (one exposed latency, not 14)
-          int nv[(MAX_TAPS + 1) / 2];
+          int nv[NVR];
 #pragma unroll
-          for (int u = 0; u < (MAX_TAPS + 1) / 2; ++u) {
-            const int t = thalf + 2 * u;
+          for (int u = 0; u < NVR; ++u) {
+            const int t = thalf + TSPLIT * u;
             nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
           }
 #pragma unroll
-          for (int u = 0; u < (MAX_TAPS + 1) / 2; ++u) {
-            const int t = thalf + 2 * u;
+          for (int u = 0; u < NVR; ++u) {
+            const int t = thalf + TSPLIT * u;
             if (t < p.taps) {
               // staged as the BYTE offset of the neighbour's feature row (0xFFFFFFFF = none): one add per piece later
-              if (cs == crank) nbr_s[t * BM + r] = nv[u] >= 0 ? (int)((unsigned)nv[u] * (unsigned)(p.cin * 2)) : -1;
+              if (cs == crank) nbr_s[t * TILE_M + r] = nv[u] >= 0 ? (int)((unsigned)nv[u] * (unsigned)(p.cin * 2)) : -1;
               if (nv[u] >= 0) tap_flag[t] = 1;
             }
           }
@@ -367,9 +398,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
     const int n_act = tap_flag[32];
     if (warp < PWARPS) {
       // ------------------------------------------------ producers
-      const int r = tid & (BM - 1);            // epilogue row of this thread (TMEM lane = 32*(warp%4) + lane)
-      const int grow = row0 + r;
-      const bool row_ok = grow < m_total;
+      const int r = tid & (BM - 1);            // epilogue row of this thread inside a sub-tile (TMEM lane = 32*(warp%4) + lane)
       // A tile = 4 warp-coalesced sweeps: thread -> 16-byte piece c = tid%8 of rows rr_j = tid/8 + 32 j, so one warp
       // instruction fetches 4 whole 128 B rows; (rr_j & 7) is the same for every j -> the swizzled offset is a constant
       const int pc = tid & 7;
@@ -381,18 +410,21 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       uint32_t use = c0 / STAGES;
       // byte offsets of this thread's 4 rows for the kernel offset it is currently gathering: re-read from the smem
       // neighbour tile only when the offset changes (Cin = 128 / 256 spend 2 / 4 chunks on one offset)
-      unsigned offs[BM * 8 / PRODUCERS];
+      unsigned offs[RPT];
       int offs_tap = -1;
       for (int i = 0; i < n_act; ++i) {
         const int q = chunk_list[i];
-        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+        if (use > 0) mbar_wait_b(&empty_bar[s], (use - 1) & 1);
         const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
         const uint32_t b_base = sa + SL::A_BYTES;
         // weights: one TMA box (128B swizzle = the UMMA layout); with clusters each CTA loads 1/CS and multicasts
         if (tid == 0) {
+          if ((p.debug & 1) && i > 0) mbar_arrive(&full_bar[s]);
+          else {
           mbar_expect_tx(&full_bar[s], BN * 128);
           if constexpr (CS == 1) tma_load_2d(b_base, &tmap_w, q * BK, n0, &full_bar[s]);
           else tma_load_2d_mcast(b_base + crank * SLICE_ROWS * 128, &tmap_w, q * BK, n0 + crank * SLICE_ROWS, &full_bar[s], CMASK);
+          }
         }
         {
           const int k = q * BK + pc * 8;
@@ -402,19 +434,21 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
           const char* src_ch = a_bytes + ch * 2;
           if (tap != offs_tap) {
             offs_tap = tap;
-            const int* nrow = nbr_s + tap * BM + rbase;
+            const int* nrow = nbr_s + tap * TILE_M + rbase;
 #pragma unroll
-            for (int j = 0; j < BM * 8 / PRODUCERS; ++j) {
+            for (int j = 0; j < RPT; ++j) {
               unsigned off = 0xFFFFFFFFu;
               if (tap_ok) {
                 if (gather) off = (unsigned)nrow[(PRODUCERS / 8) * j];
                 else { const int gr = row0 + rbase + (PRODUCERS / 8) * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
               }
+              if ((p.debug & 2) && off != 0xFFFFFFFFu) off = 0;
               offs[j] = off;
             }
           }
+          if (!(p.debug & 4))
 #pragma unroll
-          for (int j = 0; j < BM * 8 / PRODUCERS; ++j) {
+          for (int j = 0; j < RPT; ++j) {
             const bool ok = offs[j] != 0xFFFFFFFFu;
             cp_async16(sa + a_thr_off + j * (PRODUCERS / 8) * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
           }
@@ -425,14 +459,18 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
         if (++s == STAGES) { s = 0; ++use; }
       }
       // ------------------------------------------------ epilogue
-      mbar_wait(accum_bar, tile_ctr & 1);
+      mbar_wait_b(accum_bar, tile_ctr & 1);
       tc_fence_after();
-      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       // warps 0-3 own columns [0, BN/2), warps 4-7 [BN/2, BN) of the same rows; the row-local LayerNorm needs the
       // whole row in one thread and stays on warps 0-3
       const bool ln = p.ln_gamma != nullptr;
       const int cb_lo = (ln || BN < 64) ? 0 : (warp >> 2) * (BN / 2);
       const int cb_hi = (ln || BN < 64) ? ((warp >> 2) ? 0 : BN) : cb_lo + BN / 2;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * BN);
+      const int grow = row0 + mt * BM + r;
+      const bool row_ok = grow < m_total;
       long long orow = grow;
       if (p.out_rows && row_ok) orow = p.out_rows[grow];
       const bool store_ok = row_ok && orow >= 0;
@@ -485,6 +523,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
           }
         }
       }
+      }
       // all TMEM reads of this tile are ordered before the __syncthreads below, after which the MMA
       // warp may overwrite the accumulator with the next tile
       tc_fence_before();
@@ -495,18 +534,21 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       for (int q = 0; q < n_act; ++q) {
         const uint32_t cc = c0 + q;
         const int s = cc % STAGES;
-        mbar_wait(&full_bar[s], (cc / STAGES) & 1);
+        mbar_wait_b(&full_bar[s], (cc / STAGES) & 1);
         fence_proxy_async();     // cp.async (generic proxy) writes of the producers -> visible to the tensor core
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
           const uint32_t b_addr = a_addr + SL::A_BYTES;
-          const uint64_t a_desc = make_desc_sw128(a_addr);
           const uint64_t b_desc = make_desc_sw128(b_addr);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
-            umma_f16(tmem_base, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t a_desc = make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128));
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
+              umma_f16(tmem_base + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+            }
           }
           if constexpr (CS == 1) umma_commit(&empty_bar[s]); else umma_commit_mcast(&empty_bar[s], CMASK);
           if (q == n_act - 1) umma_commit(accum_bar);
@@ -558,14 +600,20 @@ static int make_weight_tmap(CUtensorMap* tm, const void* w, int n_total, int kpa
 }
 
 
-template <int BN, int STAGES, int CS>
+template <int BN, int STAGES, int CS, int MT = 1>
 static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
-  using SL = SmemLayout<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+  using SL = SmemLayout<BN, STAGES, MT>;
+  static_assert(SL::TOTAL <= 227 * 1024, "gemm: shared memory budget exceeded");
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { isf_set_error("gemm: bad device"); return ISF_ERR_CUDA; }
+  static bool configured[64] = {};          // cudaFuncSetAttribute is per-device state
+  static int sm_count[64] = {};
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES, CS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
     if (e != cudaSuccess) { isf_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
-    configured = true;
+    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || sm_count[dev] < 1) { isf_set_error("gemm: cannot query the SM count"); return ISF_ERR_CUDA; }
+    configured[dev] = true;
   }
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
@@ -573,14 +621,15 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
     int rc = make_weight_tmap(&tm, p.W, p.n_total, p.kpad, BN / CS);
     if (rc) return rc;
   }
-  int tiles = (m_upper + BM - 1) / BM;
+  int tiles = (m_upper + BM * MT - 1) / (BM * MT);
   if (tiles < 1) tiles = 1;
   int ctas_per_sm = (227 * 1024) / (SL::TOTAL + 1024);
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 4) ctas_per_sm = 4;
+  if (ctas_per_sm * BN * MT > 512) ctas_per_sm = 512 / (BN * MT);      // TMEM columns
   int n_tiles = p.n_total / BN;
   int groups = (tiles + CS - 1) / CS;
-  int gx = ISF_NUM_SMS * ctas_per_sm / n_tiles / CS;     // clusters
+  int gx = sm_count[dev] * ctas_per_sm / n_tiles / CS;     // clusters
   if (gx < 1) gx = 1;
   if (gx > groups) gx = groups;
   cudaLaunchConfig_t cfg;
@@ -596,7 +645,7 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, CS>, p, tm);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, CS, MT>, p, tm);
   if (e != cudaSuccess) { isf_set_error("gemm launch: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
   return ISF_OK;
 }
@@ -612,15 +661,24 @@ static inline int dispatch_gemm_cs(const GemmParams& p, int bn, int m_upper, cud
   }
 }
 
-static inline int dispatch_gemm2(const GemmParams& p, int bn, int m_upper, cudaStream_t st);   // tc_gemm2.cuh
+// 256-row CTA tiles (two accumulators, one weight chunk per 256 rows): isf_set_option("gemm_mt", 2), sparse-conv launches
+static inline int dispatch_gemm_mt2(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_gemm<64, 3, 1, 2>(p, m_upper, st);      // 3 x 40 KB + 27 KB: 1 CTA/SM
+    case 128: return launch_gemm<128, 3, 1, 2>(p, m_upper, st);    // 3 x 48 KB + 27 KB
+    case 256: return launch_gemm<256, 3, 1, 2>(p, m_upper, st);    // 3 x 64 KB + 27 KB = 221 KB, all 512 TMEM columns
+    default: return dispatch_gemm_cs<1>(p, bn, m_upper, st);
+  }
+}
 
-static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
-  if (p.taps > MAX_TAPS || p.kpad / BK > MAX_CHUNKS) {
-    isf_set_error("gemm: taps=%d (max %d) / K chunks=%d (max %d) out of range", p.taps, MAX_TAPS, p.kpad / BK, MAX_CHUNKS);
+static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaStream_t st) {
+  if (p0.taps > MAX_TAPS || p0.kpad / BK > MAX_CHUNKS) {
+    isf_set_error("gemm: taps=%d (max %d) / K chunks=%d (max %d) out of range", p0.taps, MAX_TAPS, p0.kpad / BK, MAX_CHUNKS);
     return ISF_ERR_UNSUPPORTED;
   }
-  // opt-in warp-specialised variant (isf_set_option("gemm_v2", 1 = sparse-conv launches, 2 = every GEMM))
-  if (::g_isf_gemm_v2 == 2 || (::g_isf_gemm_v2 == 1 && p.nbr != nullptr)) return dispatch_gemm2(p, bn, m_upper, st);
+  GemmParams p = p0;
+  p.debug = ::g_isf_gemm_debug;
+  if (::g_isf_gemm_mt == 2 && p.nbr != nullptr && m_upper >= 148 * 256) return dispatch_gemm_mt2(p, bn, m_upper, st);
   switch (::g_isf_gemm_cluster) {
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
     default: break;
@@ -631,5 +689,3 @@ static inline int dispatch_gemm(const GemmParams& p, int bn, int m_upper, cudaSt
 }
 
 }  // namespace tc
-
-#include "tc_gemm2.cuh"

@@ -37,16 +37,16 @@ def _fold_conv_bn(conv, bn, transpose_kernel=False):
         b = conv.bias if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
     if transpose_kernel:
         w = w.transpose(2, 3)
-    return (w.half().contiguous(memory_format=torch.channels_last), b.detach().half().contiguous())
+    b = b.detach()
+    return (w.half().contiguous(memory_format=torch.channels_last), b.half().contiguous(), b.float().contiguous())   # + fp32 shift
 
 
 def _conv(x_nhwc, packed, stride=1, relu=True):
-    """3x3 conv + folded BN (+ReLU) on a channels-last fp16 map [B,Y,X,C] (cuDNN implicit GEMM)."""
-    if conv2d.ENABLED:       # opt-in: the library's own tcgen05 implicit GEMM instead of cuDNN (conv2d.py)
-        y = conv2d.conv3x3(x_nhwc, packed, stride, relu)
-        if y is not None:
-            return y
-    w, b = packed
+    """3x3 conv + folded BN (+ReLU) on a channels-last fp16 map [B,Y,X,C]: the library's own tcgen05 kernels (conv2d.py).
+    cuDNN is reachable only as the A/B baseline (ISF_CONV=cudnn)."""
+    if conv2d.BACKEND != 'cudnn':
+        return conv2d.conv3x3(x_nhwc, packed, stride, relu)
+    w, b = packed[0], packed[1]
     x = x_nhwc.permute(0, 3, 1, 2)
     if relu:     # cuDNN runtime-fused conv + bias + ReLU (one kernel)
         y = torch.cudnn_convolution_relu(x, w, b, [stride, stride], [1, 1], [1, 1], 1)

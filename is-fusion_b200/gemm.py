@@ -8,8 +8,6 @@ from . import _lib as L
 
 ACT = {None: 0, 'none': 0, 'relu': 1, 'gelu': 2}
 
-if os.environ.get('ISF_GEMM_V2'):       # opt-in warp-specialised schedule (csrc/tc_gemm2.cuh): 1 = sparse convs, 2 = every GEMM
-    L.set_option('gemm_v2', int(os.environ['ISF_GEMM_V2']))
 
 
 def pack_weight(w, dtype=torch.float16):

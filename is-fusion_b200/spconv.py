@@ -89,9 +89,11 @@ class Rulebook:
 
 
 # Opt-in tile order of the implicit GEMM (csrc/spconv.cu "Tile order", tests/analysis/tile_occupancy.py): None = rows in
-# storage order (default); an int = rows regrouped by neighbour pattern inside chunks of 2**TILE_ORDER consecutive rows
-# (31 = one global sort).  Results are bit-identical either way.  Environment: ISF_TILE_ORDER=<int>.
-TILE_ORDER = int(os.environ['ISF_TILE_ORDER']) if os.environ.get('ISF_TILE_ORDER') else None
+# None = storage order; an int = rows regrouped by neighbour pattern inside chunks of 2**TILE_ORDER consecutive rows
+# (31 = one global sort, the default: measured -12.5 % on the 21 implicit-GEMM launches of the bench frame, round 2).
+# Results are bit-identical either way.  Environment: ISF_TILE_ORDER=<int> | none.
+_to = os.environ.get('ISF_TILE_ORDER', '31')
+TILE_ORDER = None if _to in ('none', 'off', '') else int(_to)
 if os.environ.get('ISF_NBR_ROWS'):      # opt-in row-per-thread neighbour-table kernel (csrc/spconv.cu nbr_bitmap_rows_kernel)
     L.set_option('nbr_rows', int(os.environ['ISF_NBR_ROWS']))
 

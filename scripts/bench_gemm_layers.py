@@ -1,9 +1,10 @@
 """Per-layer timing of the sparse-conv implicit GEMMs of one frame (round-2 iteration aid, GPU only):
-   python scripts/bench_gemm_layers.py [--points 300000] [--v2] [--tile-order 12,16,31]
+   python scripts/bench_gemm_layers.py [--points 300000] [--opt gemm_mt=2,gemm_debug=1] [--tile-order none,16,31]
 prints, for each of the 21 launches, rows / Cin / Cout / ms and useful TFLOP/s for the default kernel and, side by
-side, the opt-in variants: the warp-specialised schedule (--v2, csrc/tc_gemm2.cuh) and the neighbour-pattern tile
-order (--tile-order, csrc/spconv.cu isf_spconv_tile_order; chunk log2 per variant, 31 = one global sort), alone and
-combined.  Also checks that every variant's encoder output is bit-identical to the default one."""
+side, variants: library options (--opt name=value, isf_set_option; each listed option is one variant) and the
+neighbour-pattern tile order (--tile-order, csrc/spconv.cu isf_spconv_tile_order; chunk log2 per variant, 31 = one
+global sort = the default, none = storage order).  Also checks whether every variant's neck output is bit-identical
+to the first one (gemm_debug variants are timing experiments and are expected to differ)."""
 import argparse
 import os
 import sys
@@ -21,7 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--points', type=int, default=300000)
     ap.add_argument('--cloud', default='S')
-    ap.add_argument('--v2', action='store_true')
+    ap.add_argument('--opt', default='', help='comma-separated library options, each one a variant, e.g. gemm_mt=2,gemm_debug=1')
     ap.add_argument('--tile-order', default='', help='comma-separated chunk log2 values, e.g. 12,16,31')
     ap.add_argument('--reps', type=int, default=10)
     args = ap.parse_args()
@@ -33,13 +34,16 @@ def main():
     feats = [f.to(dev) for f in synth.make_img_feats(1)]
     metas = [dict(input_shape=(256, 704))]
     kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
-    orders = [None] + [int(t) for t in args.tile_order.split(',') if t]
-    variants = [('v1' + ('' if o is None else '+ord%d' % o), 0, o) for o in orders]
-    if args.v2:
-        variants += [('v2' + ('' if o is None else '+ord%d' % o), 1, o) for o in orders]
+    default_order = spmod.TILE_ORDER
+    orders = [default_order] + [None if t == 'none' else int(t) for t in args.tile_order.split(',') if t]
+    oname = lambda o: 'storage' if o is None else 'ord%d' % o
+    variants = [(oname(o), None, o) for o in orders]
+    variants += [(t, t.split('='), default_order) for t in args.opt.split(',') if t]
+    defaults = {'gemm_mt': 1, 'gemm_debug': 0, 'gemm_cluster': 1, 'nbr_rows': 1}
     cols, ref_out = {}, None
-    for name, v2, order in variants:
-        L.set_option('gemm_v2', v2)
+    for name, opt, order in variants:
+        if opt:
+            L.set_option(opt[0], int(opt[1]))
         spmod.TILE_ORDER = order
         try:
             net(pts, feats, metas, **kw)
@@ -52,12 +56,13 @@ def main():
                 ref_out = [o.clone() for o in out]
             else:
                 same = all(torch.equal(a, b) for a, b in zip(ref_out, out))
-                print('%s: neck output %s the default path' % (name, 'bit-identical to' if same else 'DIFFERS from'))
+                print('%s: neck output %s the first variant' % (name, 'bit-identical to' if same else 'DIFFERS from'))
             cols[name] = spmod.time_launches(prof, reps=args.reps)
         finally:
             spmod.PROFILE = None
-            spmod.TILE_ORDER = None
-            L.set_option('gemm_v2', 0)
+            spmod.TILE_ORDER = default_order
+            if opt:
+                L.set_option(opt[0], defaults[opt[0]])
     names = list(cols)
     print('%3s %8s %4s %4s | %s' % ('#', 'rows', 'cin', 'cout', ' | '.join('%-16s' % (n + ' ms/TF') for n in names)))
     tot = {n: 0.0 for n in names}

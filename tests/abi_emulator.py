@@ -92,6 +92,18 @@ class _FusionLib:
         _set_size(out, 1024)
         return 0
 
+    # ------------------------------------------------------------------ isf_conv3x3_nhwc_f16
+    def isf_conv3x3_nhwc_f16(self, x, batch, h, w, cin, ldx, wpk, cout_pad, shift, stride, relu, out, ldo, cout_store, stream):
+        assert cin % 64 == 0 and ldx >= cin and cout_pad in (32, 64, 128, 256) and wpk.shape == (cout_pad, 9 * cin)
+        assert stride in (1, 2) and cout_store % 8 == 0 and cout_store <= min(cout_pad, ldo)
+        xx = x.reshape(batch, h, w, ldx)[..., :cin].float().permute(0, 3, 1, 2)
+        wt = wpk.float().view(cout_pad, 3, 3, cin).permute(0, 3, 1, 2)
+        y = F.conv2d(xx, wt, shift, stride=stride, padding=1)
+        y = (torch.relu(y) if _val(relu) else y).permute(0, 2, 3, 1)
+        o = out.view(batch, y.shape[1], y.shape[2], ldo)
+        o[..., :cout_store] = y[..., :cout_store].half()
+        return 0
+
     # ------------------------------------------------------------------ isf_gemm_f16
     def isf_gemm_f16(self, a, w, m, k, kpad, n, scale, shift, residual, ldr, act, ln_g, ln_b, ln_eps, out_f16, out_f32, ldo,
                      out_rows, m_dev, stream):
@@ -662,7 +674,7 @@ class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):
 
 
 def _conv_cpu(x_nhwc, packed, stride=1, relu=True):
-    w, b = packed
+    w, b = packed[0], packed[1]
     y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).float(), w.float(), b.float(), stride=stride, padding=1)
     return (torch.relu(y) if relu else y).permute(0, 2, 3, 1).half().contiguous()
 
@@ -705,5 +717,4 @@ def install(monkeypatch):
     monkeypatch.setattr(L, 'require_cuda', _require_contiguous)
     monkeypatch.setattr(L, 'is_device', lambda t: True)
     monkeypatch.setattr(L, 'workspace', lambda nbytes, device: torch.empty(max(int(nbytes), 1), dtype=torch.uint8))
-    monkeypatch.setattr(FE, '_conv', _conv_cpu)
     return fake

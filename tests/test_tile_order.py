@@ -1,8 +1,8 @@
-"""Tile order of the sparse-conv implicit GEMM (csrc/spconv.cu, isf_spconv_tile_order; opt-in via
+"""Tile order of the sparse-conv implicit GEMM (csrc/spconv.cu, isf_spconv_tile_order; the default since round 2,
 isfusion_b200.spconv.TILE_ORDER / ISF_TILE_ORDER).
 
 CPU part: the host-side key layout and a numpy model of the order (tests/analysis/tile_occupancy.py) on an oracle rulebook.
-GPU part (bring-up, ISF_EXPERIMENTAL=1: written at the end of round 1 without GPU time left to run it): the device
+GPU part: the device
 order equals the model and every convolution over the regrouped table is BIT-IDENTICAL to the default launch."""
 import ctypes
 import os
@@ -13,8 +13,8 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEFAULT_ORDER = 31        # isfusion_b200.spconv.TILE_ORDER as shipped (restored after every test that switches it)
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'analysis'))
-experimental = pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='opt-in path: set ISF_EXPERIMENTAL=1')
 
 
 def test_key_bits_rank_z_moving_and_far_offsets_first():
@@ -79,7 +79,6 @@ def _device_order(nbr, v, chunk, num_dev=None, ksize=(3, 3, 3)):
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('chunk', [7, 12, 31])
 def test_device_order_equals_model(chunk):
     import tile_occupancy as to
@@ -111,7 +110,6 @@ def test_device_order_equals_model(chunk):
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('chunk', [12, 31])
 def test_fused_ordered_rulebook_equals_two_call_path(chunk):
     """isf_spconv_neighbors_bitmap_ordered == isf_spconv_neighbors_bitmap + isf_spconv_tile_order, every geometry."""
@@ -136,11 +134,10 @@ def test_fused_ordered_rulebook_equals_two_call_path(chunk):
             assert torch.equal(res[0][1], res[1][1]), (ks, st, pd, subm)
             assert torch.equal(res[0][0], res[1][0]), (ks, st, pd, subm)
     finally:
-        sp.TILE_ORDER, sp.TILE_ORDER_FUSED = None, True
+        sp.TILE_ORDER, sp.TILE_ORDER_FUSED = DEFAULT_ORDER, True
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('chunk', [12, 31])
 def test_sparse_encoder_bit_identical_with_tile_order(chunk):
     import isfusion_b200.spconv as sp
@@ -161,11 +158,10 @@ def test_sparse_encoder_bit_identical_with_tile_order(chunk):
         torch.cuda.synchronize()
         assert torch.equal(out, ref)
     finally:
-        sp.TILE_ORDER = None
+        sp.TILE_ORDER = DEFAULT_ORDER
 
 
 @pytest.mark.gpu
-@experimental
 def test_graphed_neck_bit_identical_with_tile_order():
     """capacity mode + CUDA graph: device-side row counts, rulebooks (and their orders) built on the side stream."""
     import isfusion_b200.spconv as sp
@@ -194,7 +190,7 @@ def test_graphed_neck_bit_identical_with_tile_order():
         for a, b in zip(outs[None], outs[31]):
             assert torch.equal(a, b)
     finally:
-        sp.TILE_ORDER = None
+        sp.TILE_ORDER = DEFAULT_ORDER
 
 
 def test_issued_flops_counts_exactly_the_chunks_the_kernel_walks():
@@ -220,7 +216,6 @@ def test_issued_flops_counts_exactly_the_chunks_the_kernel_walks():
 
 
 @pytest.mark.gpu
-@experimental
 def test_row_per_thread_neighbour_kernel_bit_identical():
     """isf_set_option("nbr_rows", 1): same neighbour tables as the tap-per-thread kernel for every conv geometry of the
     encoder, exact and capacity mode."""

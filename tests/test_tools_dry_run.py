@@ -87,7 +87,7 @@ def test_bench_input_pipeline_dry_run(monkeypatch, capsys):
 
 
 def test_bench_gemm_layers_dry_run(monkeypatch, capsys):
-    """the per-layer A/B tool of the bring-up (default kernel, v2 schedule, tile orders): variants switch on and off, the
+    """the per-layer A/B tool (default kernel, library options, tile orders): variants switch on and off, the
     bit-identity check and the table print.  (On the emulator every variant is the same arithmetic.)"""
     import abi_emulator
     import isfusion_b200._lib as L
@@ -96,12 +96,12 @@ def test_bench_gemm_layers_dry_run(monkeypatch, capsys):
     monkeypatch.setenv('ISF_TOOL_DEVICE', 'cpu')
     monkeypatch.setattr(torch.cuda, 'Event', _Event)
     monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
-    monkeypatch.setattr(sys, 'argv', ['bench_gemm_layers', '--points', '2000', '--v2', '--tile-order', '31', '--reps', '1'])
+    monkeypatch.setattr(sys, 'argv', ['bench_gemm_layers', '--points', '2000', '--opt', 'gemm_mt=2', '--tile-order', 'none,16', '--reps', '1'])
     spec = importlib.util.spec_from_file_location('tool_gemm_layers', os.path.join(ROOT, 'scripts', 'bench_gemm_layers.py'))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()
     out = capsys.readouterr().out
-    assert out.count('bit-identical to the default path') == 3 and 'DIFFERS' not in out       # v1+ord31, v2, v2+ord31
-    assert 'total ms:' in out and sp.TILE_ORDER is None
-    assert L.lib().isf_set_option(b'gemm_v2', 0) == 0
+    assert out.count('bit-identical to the first variant') == 3 and 'DIFFERS' not in out       # storage, ord16, gemm_mt=2
+    assert 'total ms:' in out and sp.TILE_ORDER == 31
+    assert L.lib().isf_set_option(b'gemm_mt', 1) == 0
