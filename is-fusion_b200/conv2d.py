@@ -75,6 +75,22 @@ def pack_dense_weight(w, bias):
     return wp.contiguous(), shift.contiguous(), cpad
 
 
+def _packed_weight(w, bias, shift_src):
+    """packed weight + fp32 shift of a folded conv, cached per weight tensor.  The entry keeps the source tensors alive: a
+    key built from data_ptr() alone would alias a NEW tensor the allocator places at a freed weight's address."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), bias.data_ptr() if bias is not None else 0, bias._version if bias is not None else 0)
+    hit = _weights.get(key)
+    if hit is None:
+        ent = pack_dense_weight(w, shift_src)
+        if ent is None:
+            return None
+        if len(_weights) > 256:
+            _weights.clear()
+        hit = (ent, w, bias, shift_src)
+        _weights[key] = hit
+    return hit[0]
+
+
 def emulate(x_nhwc, nbr, wp, shift, groups, cout, relu):
     """pure-torch statement of what the kernel computes from (nbr, wp, shift) — used by the CPU test of this module."""
     bs, h, w, cin = x_nhwc.shape
@@ -103,13 +119,9 @@ def conv3x3_gather(x_nhwc, packed, stride=1, relu=True):
     groups = channel_groups(cin)
     if groups is None or 9 * groups > 27:
         return None
-    key = (w.data_ptr(), w._version, bias.data_ptr() if bias is not None else 0)
-    ent = _weights.get(key)
+    ent = _packed_weight(w, bias, bias)
     if ent is None:
-        ent = pack_dense_weight(w, bias)
-        if ent is None:
-            return None
-        _weights[key] = ent
+        return None
     wp, shift, cpad = ent
     bs, h, wd, _ = x_nhwc.shape
     pkey = (x_nhwc.device, bs, h, wd, stride, groups)
@@ -138,12 +150,9 @@ def conv3x3_tma(x_nhwc, packed, stride=1, relu=True):
         return None
     if stride == 2 and (h % 2 or wd % 2):
         return None
-    key = (w.data_ptr(), w._version, bias.data_ptr() if bias is not None else 0)
-    ent = _weights.get(key)
+    ent = _packed_weight(w, bias, packed[2] if len(packed) > 2 else bias)      # fp32 folded shift when the caller kept it
     if ent is None:
-        b32 = packed[2] if len(packed) > 2 else bias          # fp32 folded shift when the caller kept it
-        ent = pack_dense_weight(w, b32)
-        _weights[key] = ent
+        return None
     wp, shift, cpad = ent
     x = x_nhwc if (x_nhwc.is_contiguous() and x_nhwc.dtype == torch.float16) else x_nhwc.half().contiguous()
     L.require_cuda(x, wp, shift)

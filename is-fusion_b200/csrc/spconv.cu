@@ -350,11 +350,14 @@ __global__ void __launch_bounds__(256) bitmap_candidates_kernel(const int* __res
       }
 }
 
-__global__ void __launch_bounds__(256) bitmap_enumerate_kernel(const unsigned int* __restrict__ bits,
+// Sites beyond the output capacity are dropped from the BITMAP too (their bits are cleared): the bitmap is the next layer's
+// coordinate -> row map, and a set bit whose rank is >= cap would send that layer's gather past the [cap, C] feature buffer.
+__global__ void __launch_bounds__(256) bitmap_enumerate_kernel(unsigned int* __restrict__ bits,
                                                                const int* __restrict__ prefix, long long words, ConvGeom g,
                                                                int cap, int* __restrict__ out_indices, int* __restrict__ num_out) {
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
-    unsigned int word = bits[w];
+    const unsigned int orig = bits[w];
+    unsigned int word = orig, keep = orig;
     int row = prefix[w];
     if (w == words - 1) { int tot = row + __popc(word); *num_out = tot < cap ? tot : cap; }
     while (word) {
@@ -367,9 +370,12 @@ __global__ void __launch_bounds__(256) bitmap_enumerate_kernel(const unsigned in
         int z = k % g.out_shape[0]; k /= g.out_shape[0];
         int* o = out_indices + (size_t)row * 4;
         o[0] = (int)k; o[1] = z; o[2] = y; o[3] = x;
+      } else {
+        keep &= ~(1u << b);
       }
       ++row;
     }
+    if (keep != orig) bits[w] = keep;
   }
 }
 

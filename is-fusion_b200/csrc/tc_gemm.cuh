@@ -288,7 +288,10 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
 // traffic from L2 drops by CS; smem stages are recycled cluster-wide (tcgen05.commit multicast on the empty barrier).
 // MT = 128-row sub-tiles per CTA tile (one TMEM accumulator each): with MT = 2 one weight chunk feeds 256 output rows, which
 // halves the weight bytes an SM pulls from L2 per FLOP (the 128/256-column layers are paced by the SM's L2 read port).
-template <int BN, int STAGES, int CS, int MT>
+// LN = LayerNorm-epilogue instantiation (dense GEMMs only: the neighbour-tile region of shared memory holds the per-column
+// vectors and the row-statistics exchange): both warp halves take half of the row's columns, ONE pass over TMEM with the
+// half row kept in registers, partial (sum, sum of squares) exchanged through shared memory.
+template <int BN, int STAGES, int CS, int MT, bool LN>
 __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
   using SL = SmemLayout<BN, STAGES, MT>;
   static_assert(CS == 1 || MT == 1, "clusters only with single sub-tile CTAs");
@@ -325,6 +328,15 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
     fence_barrier_init();
   }
   if (warp == PWARPS) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if constexpr (LN) {       // per-column vectors of this CTA's columns -> shared memory (read there by every tile's epilogue)
+    float* vec = (float*)(smem + SL::NBR_OFF);
+    for (int c = tid; c < BN; c += THREADS) {
+      vec[c] = p.scale ? p.scale[n0 + c] : 1.f;
+      vec[BN + c] = p.shift ? p.shift[n0 + c] : 0.f;
+      vec[2 * BN + c] = p.ln_gamma[n0 + c];
+      vec[3 * BN + c] = p.ln_beta[n0 + c];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();       // peers' barriers are initialised before anyone signals them
@@ -463,6 +475,87 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       tc_fence_after();
       // warps 0-3 own columns [0, BN/2), warps 4-7 [BN/2, BN) of the same rows; the row-local LayerNorm needs the
       // whole row in one thread and stays on warps 0-3
+      if constexpr (LN) {
+        static_assert(!LN || (BN >= 64 && MT == 1), "LayerNorm epilogue: 64..256 columns, single sub-tile");
+        constexpr int HC = BN / 2;                       // columns per thread
+        const int half = warp >> 2;
+        const float* vec = (const float*)(smem + SL::NBR_OFF);
+        float2* part = (float2*)(smem + SL::NBR_OFF + 4 * BN * 4);     // [2][128] partial (sum, sum of squares)
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * HC);
+        const int grow = row0 + r;
+        const bool row_ok = grow < m_total;
+        long long orow = grow;
+        if (p.out_rows && row_ok) orow = p.out_rows[grow];
+        const bool store_ok = row_ok && orow >= 0;
+        long long rrow = row_ok ? (long long)grow : -1;
+        if (p.res_rows && row_ok) rrow = p.res_rows[grow];
+        float x[HC];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int cb = 0; cb < HC; cb += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + cb, v);
+          tmem_ld_wait();
+          const float* vs = vec + half * HC + cb;
+          const float* vh = vec + BN + half * HC + cb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[cb + j] = __uint_as_float(v[j]) * vs[j] + vh[j];
+          if (p.residual && rrow >= 0) {
+            const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n0 + half * HC + cb);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 u = rp[j4];
+              const __half2* h = (const __half2*)&u;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                x[cb + j4 * 8 + e * 2] += f.x; x[cb + j4 * 8 + e * 2 + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1 += x[cb + j]; s2 += x[cb + j] * x[cb + j]; }
+        }
+        part[half * BM + r] = make_float2(s1, s2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float2 o = part[(half ^ 1) * BM + r];
+        // both halves add the two partials in the same order (low half first): identical statistics on both sides
+        const float t1 = half ? o.x + s1 : s1 + o.x, t2 = half ? o.y + s2 : s2 + o.y;
+        const float mean = t1 / BN;
+        const float var = t2 / BN - mean * mean;
+        const float rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+        const float* ga = vec + 2 * BN + half * HC;
+        const float* be = vec + 3 * BN + half * HC;
+#pragma unroll
+        for (int cb = 0; cb < HC; cb += 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float y = (x[cb + j] - mean) * rstd * ga[cb + j] + be[cb + j];
+            if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
+            else if (p.act == ACT_GELU) y = gelu_erf(y);
+            x[cb + j] = y;
+          }
+          if (store_ok) {
+            if (p.out) {
+              uint4* op = (uint4*)(p.out + orow * p.ldo + n0 + half * HC + cb);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint4 u;
+                __half2* h = (__half2*)&u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[cb + j4 * 8 + e * 2], x[cb + j4 * 8 + e * 2 + 1]);
+                op[j4] = u;
+              }
+            }
+            if (p.out_f32) {
+              float4* op = (float4*)(p.out_f32 + orow * p.ldo + n0 + half * HC + cb);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(x[cb + j4 * 4], x[cb + j4 * 4 + 1], x[cb + j4 * 4 + 2], x[cb + j4 * 4 + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+      } else {
       const bool ln = p.ln_gamma != nullptr;
       const int cb_lo = (ln || BN < 64) ? 0 : (warp >> 2) * (BN / 2);
       const int cb_hi = (ln || BN < 64) ? ((warp >> 2) ? 0 : BN) : cb_lo + BN / 2;
@@ -527,6 +620,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       // all TMEM reads of this tile are ordered before the __syncthreads below, after which the MMA
       // warp may overwrite the accumulator with the next tile
       tc_fence_before();
+      }
     } else {
       // ------------------------------------------------ MMA issuer (warp PWARPS)
       constexpr uint32_t idesc = make_idesc_f16(BM, BN);
@@ -600,7 +694,7 @@ static int make_weight_tmap(CUtensorMap* tm, const void* w, int n_total, int kpa
 }
 
 
-template <int BN, int STAGES, int CS, int MT = 1>
+template <int BN, int STAGES, int CS, int MT = 1, bool LN = false>
 static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
   using SL = SmemLayout<BN, STAGES, MT>;
   static_assert(SL::TOTAL <= 227 * 1024, "gemm: shared memory budget exceeded");
@@ -609,7 +703,7 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
   static bool configured[64] = {};          // cudaFuncSetAttribute is per-device state
   static int sm_count[64] = {};
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES, CS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, STAGES, CS, MT, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
     if (e != cudaSuccess) { isf_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
     e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess || sm_count[dev] < 1) { isf_set_error("gemm: cannot query the SM count"); return ISF_ERR_CUDA; }
@@ -645,7 +739,7 @@ static int launch_gemm(const GemmParams& p, int m_upper, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, CS, MT>, p, tm);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, CS, MT, LN>, p, tm);
   if (e != cudaSuccess) { isf_set_error("gemm launch: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
   return ISF_OK;
 }
@@ -678,6 +772,14 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
   }
   GemmParams p = p0;
   p.debug = ::g_isf_gemm_debug;
+  if (p.ln_gamma != nullptr && p.nbr == nullptr && ::g_isf_gemm_ln_fast) {      // LayerNorm epilogue: dense GEMMs, one column block
+    switch (bn) {
+      case 64: return launch_gemm<64, 2, 1, 1, true>(p, m_upper, st);
+      case 128: return launch_gemm<128, 3, 1, 1, true>(p, m_upper, st);
+      case 256: return launch_gemm<256, 2, 1, 1, true>(p, m_upper, st);
+      default: break;
+    }
+  }
   if (::g_isf_gemm_mt == 2 && p.nbr != nullptr && m_upper >= 148 * 256) return dispatch_gemm_mt2(p, bn, m_upper, st);
   switch (::g_isf_gemm_cluster) {
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);

@@ -86,7 +86,7 @@ class FFN(nn.Module):
         return {head: getattr(self, head)(x) for head in self.heads}
 
 
-OWN_ATTENTION = os.environ.get('ISF_HEAD_ATTN') == 'own'    # opt-in: the library's split-K kernel instead of SDPA
+OWN_ATTENTION = os.environ.get('ISF_HEAD_ATTN', 'own') == 'own'    # default: the library's split-K kernel (GPU-verified round 2); 'sdpa' = torch baseline
 
 
 def query_scene_attention(qc, kv, heads):

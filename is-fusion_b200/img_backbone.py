@@ -27,7 +27,7 @@ from .registry import BACKBONES
 
 # opt-in: the library's shifted-window attention kernel (csrc/fusion.cu swin_window_attention_kernel) instead of the torch
 # pad / roll / partition / SDPA / reverse sequence; with it a block is LN -> GEMM -> kernel -> GEMM(+residual) -> LN -> 2 GEMMs
-OWN_WINDOW_ATTENTION = os.environ.get('ISF_SWIN_ATTN') == 'own'
+OWN_WINDOW_ATTENTION = os.environ.get('ISF_SWIN_ATTN', 'own') == 'own'     # default since round 2 (GPU-verified, image branch 12.1 -> 5.7 ms); 'torch' = SDPA baseline
 
 
 class _Lin:

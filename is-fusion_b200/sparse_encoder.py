@@ -121,7 +121,7 @@ class SparseEncoder(nn.Module):
         out = []
         for stage in self.encoder_layers:
             for blk in stage:
-                if isinstance(blk, SparseSequential):
+                if isinstance(blk, SparseSequential) and not getattr(blk[0], 'subm', False):      # conv_module layouts wrap SubM convs too
                     out.append(blk[0])
         out.append(self.conv_out[0])
         return out

@@ -136,6 +136,13 @@ def _hash_table(x):
 OVERFLOW_WATCH = []     # (count tensor, capacity) of every capacity-mode strided conv since the last check
 
 
+def _watch(cnt, cap):
+    """bounded: eager nosync loops that never call check_overflow() must not pin device tensors without limit."""
+    OVERFLOW_WATCH.append((cnt, cap))
+    if len(OVERFLOW_WATCH) > 512:
+        del OVERFLOW_WATCH[:-128]
+
+
 def check_overflow():
     """capacity mode: did any strided conv produce more output sites than its buffer holds? (one host sync)"""
     bad = [(int(c.item()), cap) for c, cap in OVERFLOW_WATCH if int(c.item()) >= cap]
@@ -201,7 +208,7 @@ def build_rulebook_bitmap(x, ksize, stride, padding, dilation, subm, out_capacit
                                          ctypes.c_size_t(ws.numel()), L.stream()))
         if capacity_mode:
             v_out, out_indices, num_dev = cap_out, out_buf, cnt
-            OVERFLOW_WATCH.append((cnt, cap_out))
+            _watch(cnt, cap_out)
         else:
             v_out = int(cnt.item())
             out_indices = out_buf[:v_out]
@@ -264,7 +271,7 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm, out_capacity=None)
                                            ctypes.c_size_t(ws.numel()), L.stream()))
         if capacity_mode:
             v_out, out_indices, num_dev = cap_out, out_buf, cnt
-            OVERFLOW_WATCH.append((cnt, cap_out))
+            _watch(cnt, cap_out)
         else:
             v_out = int(cnt.item())      # exact mode: one host read per strided layer
             out_indices = out_buf[:v_out]

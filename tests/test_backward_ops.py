@@ -10,7 +10,7 @@ CPU (default suite):
     definition (sum / mean) and the lowest-index tie rule (max);
   * the product's autograd wiring (voxel_layer._dynamic_scatter, fusion_encoder.MultiScaleDeformableAttnFunction) on the
     ABI emulator.
-GPU (bring-up, ISF_EXPERIMENTAL=1: written at the end of round 1 without GPU time left): the kernels against the same."""
+GPU: the kernels against the same."""
 import ctypes
 import os
 import sys
@@ -24,7 +24,6 @@ sys.path.insert(0, HERE)
 from oracle import fusion_ops as fo     # noqa: E402
 from oracle import voxel_ops as vo      # noqa: E402
 
-experimental = pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='bring-up test: set ISF_EXPERIMENTAL=1')
 G = np.load(os.path.join(HERE, 'golden', 'msda_bwd_ref.npz'))
 CASES = ['a', 'b', 'c']
 
@@ -152,7 +151,6 @@ def test_product_msda_autograd_wiring_on_the_emulator(monkeypatch):
 
 # ---------------------------------------------------------------------------------------------- GPU (bring-up)
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('k', CASES)
 @pytest.mark.parametrize('half', [False, True])
 def test_msda_backward_kernel(k, half):
@@ -171,7 +169,6 @@ def test_msda_backward_kernel(k, half):
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('red', ['sum', 'mean', 'max'])
 @pytest.mark.parametrize('n,c', [(400, 3), (200000, 5), (50000, 64)])
 def test_scatter_backward_kernels(red, n, c, monkeypatch):

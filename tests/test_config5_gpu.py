@@ -1,7 +1,7 @@
 """BASELINE configs[4] geometry (dense-scene stress: 0.05 m voxels, +-51.2 m range -> 2048 x 2048 x 40 voxel grid,
 256 x 256 BEV) through the whole neck against the CPU oracle, at a point count the oracle finishes in seconds.
 
-Bring-up (ISF_EXPERIMENTAL=1): the kernels were validated on the 0.075 m / 180 x 180 configuration; this geometry
+The kernels were validated on the 0.075 m / 180 x 180 configuration; this geometry
 exercises the 256-grid instance of the channel attention, partial 6x6 windows on a grid that is not a multiple of 6 and
 a 2048^2 x 41 coordinate bitmap."""
 import os
@@ -10,8 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='bring-up test: set ISF_EXPERIMENTAL=1')]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_neck_on_the_005_voxel_256_bev_geometry():

@@ -2,7 +2,7 @@
 
 CPU: the kernels' per-point source compiled for the host (isf_debug_merge_sweeps_host) and the product's
 LoadPointsFromMultiSweeps (on the ABI emulator) against the reference's own loader run (tests/golden/ref_sweeps.npz).
-GPU (bring-up, ISF_EXPERIMENTAL=1): the kernels against the same fixture and at 300 k points against the host-compiled code."""
+GPU: the kernels against the same fixture and at 300 k points against the host-compiled code."""
 import ctypes
 import os
 import sys
@@ -16,7 +16,6 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(HERE, 'golden'))
 import golden_common as gc      # noqa: E402
 
-experimental = pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='bring-up test: set ISF_EXPERIMENTAL=1')
 G = np.load(os.path.join(HERE, 'golden', 'ref_sweeps.npz'))
 CASES = [('plain', dict(), 10), ('close', dict(remove_close=True), 10), ('test3', dict(test_mode=True, sweeps_num=3), 10),
          ('pad', dict(pad_empty_sweeps=True, remove_close=True, sweeps_num=2), 0)]
@@ -86,7 +85,6 @@ def test_train_mode_draws_sweeps_like_the_reference(monkeypatch):
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('tag,kw,n_sw', CASES)
 def test_merge_sweeps_kernels_against_the_reference_loader(tag, kw, n_sw):
     from isfusion_b200.sweeps import LoadPointsFromMultiSweeps
@@ -98,7 +96,6 @@ def test_merge_sweeps_kernels_against_the_reference_loader(tag, kw, n_sw):
 
 
 @pytest.mark.gpu
-@experimental
 def test_merge_sweeps_full_size():
     """a nuScenes-sized frame: key frame + 10 sweeps of ~27 k points (300 k points), with and without the close filter."""
     from isfusion_b200.sweeps import LoadPointsFromMultiSweeps
@@ -190,7 +187,6 @@ def test_image_plan_full_size_against_pillow():
 
 
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('tag,seed', IMG_CASES)
 def test_image_kernels_against_the_reference_pipeline(tag, seed):
     from isfusion_b200.image_pipeline import ImageAug3D, ImageNormalize
@@ -204,7 +200,6 @@ def test_image_kernels_against_the_reference_pipeline(tag, seed):
 
 
 @pytest.mark.gpu
-@experimental
 def test_image_kernels_full_size_six_cameras():
     """6 x 1600x900 frames through the config's test-time geometry: device == the same source compiled for the host."""
     from isfusion_b200 import _lib as L

@@ -10,8 +10,7 @@ can be checked at BASELINE's full sizes where the CPU oracle would take minutes.
   * deformable attention: a constant value map sampled strictly inside it with weights summing to one returns the constant.
 
 The same property functions run (a) on the CPU at small sizes against the ABI emulator — which proves the TEST code, and the
-product's host code, before any GPU time is spent — and (b) on the GPU at the full-frame sizes (bring-up: ISF_EXPERIMENTAL=1,
-written at the end of round 1 without GPU time left)."""
+product's host code, before any GPU time is spent — and (b) on the GPU at the full-frame sizes."""
 import ctypes
 import os
 import sys
@@ -21,7 +20,6 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-experimental = pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='bring-up test: set ISF_EXPERIMENTAL=1')
 
 
 def _voxels(n_points, shape, voxel, lo, seed, dev):
@@ -161,7 +159,6 @@ def test_properties_on_the_emulator(monkeypatch):
 
 # ------------------------------------------------------------------------------------------------ GPU: full-frame sizes
 @pytest.mark.gpu
-@experimental
 @pytest.mark.parametrize('cin,cout', [(32, 32), (64, 64), (128, 128), (32, 64)])
 def test_sparse_conv_properties_on_the_full_frame(cin, cout):
     shape = [41, 1440, 1440]
@@ -171,7 +168,6 @@ def test_sparse_conv_properties_on_the_full_frame(cin, cout):
 
 
 @pytest.mark.gpu
-@experimental
 def test_scatter_topk_msda_properties_at_full_size():
     prop_dynamic_scatter('cuda', 1000000, 5)
     prop_dynamic_scatter('cuda', 300000, 64, seed=1)

@@ -2,7 +2,7 @@
 tests/golden/make_golden_ref.py), not through the oracle.  The default GPU suite proves CUDA == oracle and the CPU
 suite proves oracle == reference; this closes the triangle on the small reference-run cases (24x24 BEV, B = 2).
 
-Bring-up (ISF_EXPERIMENTAL=1): written at the end of round 1 without GPU time left to run it; the product kernels
+First run green on a B200 in round 2; the product kernels
 were validated at the config's sizes (180 / 90 grids), these cases use 24 / 12 grids and 41x48x48 sparse shapes.
 Tolerances: fp16 storage through 2-40 stacked layers against an fp32 CPU reference (the bars of DESIGN.md §4)."""
 import os
@@ -16,8 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, 'golden'))
 import golden_common as gc  # noqa: E402
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('ISF_EXPERIMENTAL') != '1', reason='bring-up test: set ISF_EXPERIMENTAL=1')]
+pytestmark = [pytest.mark.gpu]
 
 
 def _g(name):
@@ -224,6 +223,7 @@ def test_query_scene_attention_kernel_against_sdpa(nq, nk):
     b, c, h = 2, 128, 8
     q = (torch.randn(b, nq, c, device='cuda') * 0.7).half()
     kv = (torch.randn(b, nk, 2, h, c // h, device='cuda') * 0.7).half()
+    H_DEFAULT = H.OWN_ATTENTION
     try:
         H.OWN_ATTENTION = False
         want = H.query_scene_attention(q, kv, h).float()
@@ -231,7 +231,7 @@ def test_query_scene_attention_kernel_against_sdpa(nq, nk):
         got = H.query_scene_attention(q, kv, h).float()
         torch.cuda.synchronize()
     finally:
-        H.OWN_ATTENTION = False
+        H.OWN_ATTENTION = H_DEFAULT
     assert got.shape == want.shape == (b, nq, c)
     assert ((got - want).norm() / want.norm()).item() < 3e-3
 
@@ -243,6 +243,7 @@ def test_swin_own_window_attention_against_torch_path_and_reference():
     g = _g('ref_swin.npz')
     net = gc.fill_state(B.SwinTransformer(**gc.swin_cfg()), 9).cuda().eval()
     x = gc.swin_input().cuda()
+    B_DEFAULT = B.OWN_WINDOW_ATTENTION
     try:
         B.OWN_WINDOW_ATTENTION = False
         ref = [o.float() for o in net(x)]
@@ -250,7 +251,7 @@ def test_swin_own_window_attention_against_torch_path_and_reference():
         out = [o.float() for o in net(x)]
         torch.cuda.synchronize()
     finally:
-        B.OWN_WINDOW_ATTENTION = False
+        B.OWN_WINDOW_ATTENTION = B_DEFAULT
     for i, (a, r) in enumerate(zip(out, ref)):
         assert ((a - r).norm() / r.norm()).item() < 5e-3, i
         assert _rel(a, g['out%d' % i]) < 2e-2, i

@@ -165,3 +165,38 @@ def test_bitmap_rulebook_matches_hash_rulebook():
     rb = sp.build_rulebook(xs, [3, 3, 3], [2, 2, 2], [1, 1, 1], [1, 1, 1], False)
     oi, osz, nbr = so.get_indice_pairs(c.cpu(), 2, [41, 128, 128], 3, 2, 1, 1, False)
     assert torch.equal(rb.out_indices.cpu(), oi) and torch.equal(rb.nbr[:, :rb.num_out].cpu().long(), nbr)
+
+
+def test_capacity_overflow_drops_sites_from_the_coordinate_map_too():
+    """capacity (sync-free) mode with an output buffer SMALLER than the true site count: the surplus sites are dropped from
+    the index list AND from the bitmap the next layer uses as its coordinate map, so no neighbour entry of the next layer
+    points past the [cap, C] feature buffer (it used to: rank = prefix + popc >= cap -> out-of-bounds gather), the kept
+    rows equal the first `cap` rows of the exact result, and check_overflow() reports the layer."""
+    import isfusion_b200.spconv as sp
+    x = _rand_tensor([41, 96, 96], 30000, 16, 2, 3, clustered=True)
+    order = torch.argsort(so._lin(x.indices, x.spatial_shape))
+    idx = x.indices[order].contiguous().cuda()
+    n = idx.shape[0]
+    exact = sp.SparseConvTensor(None, idx, x.spatial_shape, 2)
+    exact.sorted = True
+    rb_exact = sp.build_rulebook(exact, [3, 3, 3], [2, 2, 2], [1, 1, 1], [1, 1, 1], False)
+    true_out = rb_exact.num_out
+    cap = true_out // 2
+    sp.check_overflow()
+    num_dev = torch.tensor([n], dtype=torch.int32, device='cuda')
+    xt = sp.SparseConvTensor(None, idx, x.spatial_shape, 2, num_dev=num_dev)
+    xt.sorted = True
+    rb = sp.build_rulebook(xt, [3, 3, 3], [2, 2, 2], [1, 1, 1], [1, 1, 1], False, out_capacity=cap)
+    torch.cuda.synchronize()
+    assert int(rb.num_dev.item()) == cap
+    assert torch.equal(rb.out_indices[:cap], rb_exact.out_indices[:cap])
+    # the next layer (a SubM conv over the strided conv's output) looks its neighbours up in the output bitmap
+    yt = sp.SparseConvTensor(None, rb.out_indices, rb.out_shape, 2, num_dev=rb.num_dev)
+    yt.sorted = True
+    yt.indice_dict = xt.indice_dict
+    rb2 = sp.build_rulebook(yt, [3, 3, 3], [1, 1, 1], [1, 1, 1], [1, 1, 1], True)
+    torch.cuda.synchronize()
+    tab = rb2.nbr_ordered if rb2.nbr_ordered is not None else rb2.nbr
+    assert int(tab.max().item()) < cap, 'a neighbour entry points past the capacity-sized feature buffer'
+    bad = sp.check_overflow()
+    assert bad and bad[0][1] == cap
