@@ -158,6 +158,12 @@ def oracle_fps(points, cloud, steps, warmup, threads=None, img_hw=(384, 1056)):
     return steps / sum(times), threads, {k: round(v, 3) for k, v in stages.items()}
 
 
+def workload_config(args, points):
+    """`config` of the JSON line, identical for the B200 arm and the reference arm (how each arm runs it goes under `run`)."""
+    return {'workload': 'BASELINE configs[1]: isfusion_0075voxel.py fusion-neck forward, synthetic nuScenes-shaped frame',
+            'points_per_frame': points, 'cloud': args.cloud, 'cams': 6, 'img': list(img_hw_of(args)), 'bev': 180, 'batch_per_gpu': args.batch}
+
+
 def cpu_baseline_subprocess(args, deadline=200):
     """the CPU arm in a child process with a hard deadline (a mis-sized OpenMP pool must not stall the bench)."""
     for pts_n in [args.cpu_points or args.points, 20000]:
@@ -189,9 +195,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': 1000.0 / fps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE configs[1]: isfusion_0075voxel.py fusion-neck forward, synthetic nuScenes-shaped frame',
-                       'points_per_frame': cpu_points, 'cloud': args.cloud, 'cams': 6, 'img': list(img_hw_of(args)), 'bev': 180,
-                       'batch_per_gpu': 1, 'parallelism': 'host cores of the box (CPU oracle = restated reference, fp32)'},
+            'config': workload_config(args, cpu_points),
+            'run': {'parallelism': 'host cores of the box (CPU oracle = restated reference, fp32)'},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                              'stage_seconds': stages},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -372,23 +377,24 @@ def main():
                 peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
             except Exception:
                 pass
-            peak = peaks.get('bf16_tflops_sustained', 1400.0)
+            # the launches are re-issued in isolation (not inside a long step): the recipe's denominator is the BURST peak
+            peak = peaks.get('bf16_tflops', 1600.0)
             top = max(recs, key=lambda r: r[0])
-            # DRAM traffic of the largest launch from the committed `ncu --set full` capture (profiles/), if present
-            traffic = None
+            # DRAM traffic of the largest launch: not measurable inside this run (needs ncu); the figure of the committed
+            # `ncu --set full` capture of the same launch is quoted with its provenance, null when there is none
+            traffic, traffic_src = None, None
             try:
-                txt = open(os.path.join(ROOT, 'profiles', 'prof_gemm_r01_final.txt')).read().split('== tc::gemm_kernel<256')[0]
-                rd = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_read.sum')][0]
-                wr = [float(l.split()[-1]) for l in txt.splitlines() if l.startswith('dram__bytes_write.sum')][0]
-                traffic = (rd + wr) * 1e6      # ncu prints MB
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+                traffic, traffic_src = float(tj['dram_bytes_per_launch']), tj['source']
             except Exception:
                 pass
             roof = {'kernel': 'tc::gemm_kernel (tcgen05 sparse-conv implicit GEMM; %d launches per frame)' % len(recs),
                     'bound': 'tensor', 'achieved': useful / (t_ms * 1e-3) / 1e12, 'achieved_issued': issued / (t_ms * 1e-3) / 1e12,
-                    'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF/s sustained',
+                    'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; launches timed in isolation)' if peaks else 'fallback 1.6 PF/s burst',
+                    'frac_of_sustained': useful / (t_ms * 1e-3) / 1e12 / peaks.get('bf16_tflops_sustained', 1400.0),
                     'unit': 'TFLOP/s', 'frac': useful / (t_ms * 1e-3) / 1e12 / peak, 'traffic': traffic,
-                    'traffic_note': 'dram read+write bytes of the largest launch (stage-3 SubM 128->128; algorithmic 170 MB incl. the '
-                                    'neighbour table) from profiles/prof_gemm_r01_final.txt', 'launches_per_frame': len(recs),
+                    'traffic_note': ('dram read+write bytes of the largest launch, quoted from %s (ncu capture, not measured in this run)'
+                                     % traffic_src) if traffic_src else 'no ncu capture of this build committed', 'launches_per_frame': len(recs),
                     'kernel_ms_per_step': t_ms, 'share_of_step': t_ms / ms_frame,
                     'share_note': 'kernel time of one frame / latency of one frame alone (%.3f ms); with %d frames in flight the '
                                   'steps overlap, so ms_per_step is below that latency' % (ms_frame, LANES),
@@ -404,16 +410,17 @@ def main():
         line = {'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'frame_latency_ms': ms_frame, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
                 'data': 'synthetic',
-                'config': {'workload': 'BASELINE configs[1]: isfusion_0075voxel.py fusion-neck forward, synthetic nuScenes-shaped frame',
-                           'points_per_frame': args.points, 'cloud': args.cloud, 'cams': 6, 'img': list(IMG), 'bev': 180,
-                           'batch_per_gpu': B, 'frames_in_flight': LANES, 'parallelism': 'dp%d (independent replicas, no data-path collective)' % world,
-                           'l2': 'rotating %d distinct resident frames (%.0f MB of inputs) > 126 MB L2' % (F_, F_ * in_bytes / 1e6)},
+                'config': workload_config(args, args.points),
+                'run': {'frames_in_flight': LANES, 'parallelism': 'dp%d (independent replicas, no data-path collective)' % world,
+                        'l2': 'rotating %d distinct resident frames (%.0f MB of inputs) > 126 MB L2' % (F_, F_ * in_bytes / 1e6),
+                        'value_note': '`value` = throughput with %d frames in flight (graph lanes); one frame alone takes '
+                                      'frame_latency_ms' % LANES},
                 'clocks': sampler.summary(),
                 'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
                         'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': int(round(own_per_step * args.steps)), 'eager_ms_per_step': ms_eager,
                 'gpu_launches_note': 'kernels of libisfusion_b200.so (incl. its CUB passes) in the timed region; the dense 3x3 '
-                                     'convs additionally run on cuDNN through torch',
+                                     'convs are among them (isf_conv3x3_nhwc_f16)',
                 'roofline': roof, 'cpu_baseline': cpu}
         if stage_ms:
             line['stage_ms'] = stage_ms

@@ -392,6 +392,11 @@ int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, 
 int isf_debug_tma_gather4(const void* a, int rows, int cols, const int* idx_dev, int col0, int variant, void* out32k,
                           int* status_dev, void* stream);
 
+/* micro-benchmark (NOT on the product path): sustained rate of 128-row x 128-B gathers into shared memory per SM, by TMA
+ * tile::gather4 (modes 0-2), a plain TMA tile load (3) or LDGSTS (4); out_cycles[block] = cycles per 16 KB chunk. */
+int isf_debug_gather_bench(const void* a, int rows, int cols, const int* idx_dev, int n_idx, int mode, int stages, int iters,
+                           int blocks, float* out_cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

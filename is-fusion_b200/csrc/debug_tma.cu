@@ -67,3 +67,126 @@ extern "C" int isf_debug_tma_gather4(const void* a, int rows, int cols, const in
   ISF_LAUNCH_CHECK();
   return ISF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark (NOT on the product path): how fast can one SM pull 128 gathered rows x 128 B into shared memory?
+//   mode 0: tile::gather4, one warp, every lane issues its own instruction (32 per chunk)
+//   mode 1: tile::gather4, one elected lane issues all 32
+//   mode 2: tile::gather4, four warps, every lane of the first 8 lanes of each... (8 instructions per warp)
+//   mode 3: plain 2-D TMA tile load of 128 CONSECUTIVE rows (one instruction per chunk) — the no-gather reference
+//   mode 4: LDGSTS (16-byte cp.async, 256 threads, 4 pieces each — the implicit-GEMM producer's pattern)
+// A ring of STAGES 16 KB stages; a stage is re-issued as soon as its previous load has landed (no consumer): the result is
+// the sustained load rate with STAGES chunks in flight.  out[blockIdx.x] = cycles per chunk.
+// ------------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(256) gather_bench_kernel(const __grid_constant__ CUtensorMap tm_row,
+                                                           const __grid_constant__ CUtensorMap tm_tile, const __half* __restrict__ a,
+                                                           int cols, const int* __restrict__ idx, int n_idx, int mode, int iters,
+                                                           float* __restrict__ out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
+  uint64_t* bar = (uint64_t*)(smem + STAGES * 16384);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) tc::mbar_init(&bar[s], mode == 4 ? 256 : 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const int s = it % STAGES;
+    const uint32_t u = it / STAGES;
+    const uint32_t dst = tc::smem_u32(smem + s * 16384);
+    const int* ix = idx + ((size_t)(blockIdx.x * 977 + it) * 128) % (size_t)(n_idx - 128);
+    if (mode == 4) {
+      if (u > 0) tc::mbar_wait_b(&bar[s], (u - 1) & 1);
+      const int pc = tid & 7, rbase = tid >> 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = ix[rbase + 32 * j];
+        tc::cp_async16(dst + (rbase + 32 * j) * 128 + ((pc ^ (rbase & 7)) << 4), (const char*)a + ((size_t)(r < 0 ? 0 : r) * cols + pc * 8) * 2,
+                       r < 0 ? 0u : 16u);
+      }
+      tc::cp_async_mbar_arrive(&bar[s]);
+    } else if (mode == 0) {
+      if (warp == 0) {
+        if (u > 0) tc::mbar_wait_b(&bar[s], (u - 1) & 1);
+        if (lane == 0) tc::mbar_expect_tx(&bar[s], 16384);
+        __syncwarp();
+        const int4 r = *(const int4*)(ix + 4 * lane);
+        gather4<0>(dst + lane * 512, &tm_row, 0, r.x, r.y, r.z, r.w, &bar[s]);
+      }
+    } else if (mode == 1) {
+      if (tid == 0) {
+        if (u > 0) tc::mbar_wait_b(&bar[s], (u - 1) & 1);
+        tc::mbar_expect_tx(&bar[s], 16384);
+        for (int g = 0; g < 32; ++g) {
+          const int4 r = *(const int4*)(ix + 4 * g);
+          gather4<0>(dst + g * 512, &tm_row, 0, r.x, r.y, r.z, r.w, &bar[s]);
+        }
+      }
+    } else if (mode == 2) {
+      if (warp < 4) {
+        if (u > 0) tc::mbar_wait_b(&bar[s], (u - 1) & 1);
+        if (tid == 0) tc::mbar_expect_tx(&bar[s], 16384);
+        __syncwarp();
+        if (lane < 8) {
+          const int g = warp * 8 + lane;
+          const int4 r = *(const int4*)(ix + 4 * g);
+          gather4<0>(dst + g * 512, &tm_row, 0, r.x, r.y, r.z, r.w, &bar[s]);
+        }
+      }
+    } else {
+      if (tid == 0) {
+        if (u > 0) tc::mbar_wait_b(&bar[s], (u - 1) & 1);
+        tc::mbar_expect_tx(&bar[s], 16384);
+        int r0 = ix[0];
+        if (r0 < 0) r0 = 0;
+        tc::tma_load_2d(dst, &tm_tile, 0, r0, &bar[s]);
+      }
+    }
+  }
+  // drain: wait for the last use of every stage
+  if (mode == 4 || tid == 0 || (mode == 0 && warp == 0) || (mode == 2 && warp < 4)) {
+    for (int s = 0; s < STAGES; ++s) {
+      const int uses = (iters - s + STAGES - 1) / STAGES;
+      if (uses > 0) tc::mbar_wait_b(&bar[s], (uint32_t)(uses - 1) & 1);
+    }
+  }
+  if (mode == 4) asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)iters;
+}
+
+extern "C" int isf_debug_gather_bench(const void* a, int rows, int cols, const int* idx_dev, int n_idx, int mode, int stages,
+                                      int iters, int blocks, float* out_cycles, void* stream) {
+  ISF_CHECK_ARG(a && idx_dev && out_cycles && rows >= 128 && cols >= 64 && n_idx > 256 && mode >= 0 && mode <= 4 && iters >= 1);
+  tc::EncodeTiledFn fn = tc::get_encode_fn();
+  if (!fn) { isf_set_error("no cuTensorMapEncodeTiled"); return ISF_ERR_CUDA; }
+  CUtensorMap tr, tt;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t estr[2] = {1, 1};
+  cuuint32_t box1[2] = {64, 1}, box128[2] = {64, 128};
+  CUresult r = fn(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a), dims, strides, box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { isf_set_error("encode failed %d", (int)r); return ISF_ERR_CUDA; }
+  r = fn(&tt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a), dims, strides, box128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { isf_set_error("encode failed %d", (int)r); return ISF_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+#define ISF_GB(S)                                                                                                         \
+  {                                                                                                                       \
+    ISF_CUDA(cudaFuncSetAttribute(gather_bench_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S * 16384 + 2048)); \
+    gather_bench_kernel<S><<<blocks, 256, S * 16384 + 2048, st>>>(tr, tt, (const __half*)a, cols, idx_dev, n_idx, mode, iters,  \
+                                                                  out_cycles);                                           \
+  }
+  if (stages == 4) ISF_GB(4) else if (stages == 8) ISF_GB(8) else if (stages == 12) ISF_GB(12) else {
+    isf_set_error("gather bench: stages in {4, 8, 12}");
+    return ISF_ERR_INVALID;
+  }
+#undef ISF_GB
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}

@@ -765,6 +765,9 @@ static inline int dispatch_gemm_mt2(const GemmParams& p, int bn, int m_upper, cu
   }
 }
 
+static inline bool spconv3_supported(const GemmParams& p, int bn);                               // tc_spconv.cuh
+static inline int dispatch_spconv3(const GemmParams& p, int bn, int m_upper, cudaStream_t st);
+
 static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaStream_t st) {
   if (p0.taps > MAX_TAPS || p0.kpad / BK > MAX_CHUNKS) {
     isf_set_error("gemm: taps=%d (max %d) / K chunks=%d (max %d) out of range", p0.taps, MAX_TAPS, p0.kpad / BK, MAX_CHUNKS);
@@ -780,6 +783,7 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
       default: break;
     }
   }
+  if (::g_isf_gemm_v3 && spconv3_supported(p, bn) && m_upper >= 4 * BM) return dispatch_spconv3(p, bn, m_upper, st);
   if (::g_isf_gemm_mt == 2 && p.nbr != nullptr && m_upper >= 148 * 256) return dispatch_gemm_mt2(p, bn, m_upper, st);
   switch (::g_isf_gemm_cluster) {
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
@@ -791,3 +795,5 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
 }
 
 }  // namespace tc
+
+#include "tc_spconv.cuh"

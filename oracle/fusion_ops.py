@@ -410,7 +410,11 @@ class ISFusionEncoder(nn.Module):
         heatmap = heatmap * (heatmap == local_max)
         heatmap = heatmap.view(bs, heatmap.shape[1], -1)
         top = heatmap.view(bs, -1).argsort(dim=-1, descending=True)[..., :self.instance_num]
-        top_idx = top % heatmap.shape[-1]
+        top_idx = natural_idx = top % heatmap.shape[-1]
+        # test hook: downstream arithmetic on a GIVEN selection (the discrete top-K flips on near-ties between fp16 and fp32
+        # heat-maps; a parity test that wants to isolate the arithmetic passes the selection of the path under test)
+        if getattr(self, 'force_top_idx', None) is not None:
+            top_idx = self.force_top_idx.to(top_idx.device).long()
         query_pos = bev_pos.gather(index=top_idx[:, None, :].permute(0, 2, 1).expand(-1, -1, 2), dim=1)
         qpn = torch.zeros_like(query_pos)
         qpn[..., 0] = query_pos[..., 1]
@@ -420,7 +424,7 @@ class ISFusionEncoder(nn.Module):
         x_ins = self.instance_att(x_ins, qpn, bev_pos, scene_feats=x_scene)
         bf = self.conv_ins(bev_feats).flatten(2, 3)
         ret = self.instance_to_scene_att(bf, x_ins, scene_feats, bs, self.bev_size)
-        self._dbg = dict(heatmap=hm, top_idx=top_idx, x_ins=x_ins, x_scene=x_scene)
+        self._dbg = dict(heatmap=hm, top_idx=natural_idx, top_idx_used=top_idx, x_ins=x_ins, x_scene=x_scene)
         return ret, hm
 
     @torch.no_grad()

@@ -39,7 +39,7 @@ def main():
     oname = lambda o: 'storage' if o is None else 'ord%d' % o
     variants = [(oname(o), None, o) for o in orders]
     variants += [(t, t.split('='), default_order) for t in args.opt.split(',') if t]
-    defaults = {'gemm_mt': 1, 'gemm_debug': 0, 'gemm_cluster': 1, 'nbr_rows': 1}
+    defaults = {'gemm_mt': 1, 'gemm_debug': 0, 'gemm_cluster': 1, 'nbr_rows': 1, 'gemm_ln_fast': 1, 'gemm_v3': 0}
     cols, ref_out = {}, None
     for name, opt, order in variants:
         if opt:
@@ -62,7 +62,7 @@ def main():
             spmod.PROFILE = None
             spmod.TILE_ORDER = default_order
             if opt:
-                L.set_option(opt[0], defaults[opt[0]])
+                L.set_option(opt[0], defaults.get(opt[0], 0))
     names = list(cols)
     print('%3s %8s %4s %4s | %s' % ('#', 'rows', 'cin', 'cout', ' | '.join('%-16s' % (n + ' ms/TF') for n in names)))
     tot = {n: 0.0 for n in names}

@@ -162,7 +162,12 @@ def test_bitmap_rulebook_matches_hash_rulebook():
     # oracle cross-check of one strided rulebook built by the bitmap path
     xs = sp.SparseConvTensor(f, c, [41, 128, 128], 2)
     xs.sorted = True
-    rb = sp.build_rulebook(xs, [3, 3, 3], [2, 2, 2], [1, 1, 1], [1, 1, 1], False)
+    old = sp.TILE_ORDER
+    try:
+        sp.TILE_ORDER = None        # the plain table (the fused ordered builder never materialises it)
+        rb = sp.build_rulebook(xs, [3, 3, 3], [2, 2, 2], [1, 1, 1], [1, 1, 1], False)
+    finally:
+        sp.TILE_ORDER = old
     oi, osz, nbr = so.get_indice_pairs(c.cpu(), 2, [41, 128, 128], 3, 2, 1, 1, False)
     assert torch.equal(rb.out_indices.cpu(), oi) and torch.equal(rb.nbr[:, :rb.num_out].cpu().long(), nbr)
 
@@ -200,3 +205,32 @@ def test_capacity_overflow_drops_sites_from_the_coordinate_map_too():
     assert int(tab.max().item()) < cap, 'a neighbour entry points past the capacity-sized feature buffer'
     bad = sp.check_overflow()
     assert bad and bad[0][1] == cap
+
+
+@pytest.mark.parametrize('order', [None, 31])
+def test_sparse_encoder_tma_gather_schedule_bit_identical(order):
+    """isf_set_option("gemm_v3", 1): the TMA tile::gather4 schedule of the implicit GEMM (csrc/tc_spconv.cuh; 256-row CTA
+    tiles, double-buffered TMEM) accumulates every output row over the same chunks in the same order -> same bits."""
+    from isfusion_b200 import _lib as L
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    import isfusion_b200.spconv as sp
+    torch.manual_seed(0)
+    cfg = dict(in_channels=64, sparse_shape=[41, 128, 128], base_channels=32, output_channels=256,
+               encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    mod = SparseEncoder(**cfg).cuda().eval()
+    _randomize_bn(mod)
+    x = _rand_tensor([41, 128, 128], 40000, 64, 2, 11, clustered=True)
+    f, c = torch.relu(x.features).half().cuda(), x.indices.cuda()
+    old = sp.TILE_ORDER
+    try:
+        sp.TILE_ORDER = order
+        L.set_option('gemm_v3', 0)
+        ref, _, _ = mod(f, c, 2)
+        L.set_option('gemm_v3', 1)
+        out, _, _ = mod(f, c, 2)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    finally:
+        L.set_option('gemm_v3', 0)
+        sp.TILE_ORDER = old
