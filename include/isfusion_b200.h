@@ -353,6 +353,21 @@ int isf_ms_deform_attn_forward(const void* value, int value_is_half, const long 
                                const float* attn_weight, int B, int S, int H, int D, int L, int Q, int P, float* out,
                                void* stream);
 
+/* ---- a11: the whole instance-context decoder in one launch (csrc/decoder.cu) ---------------------------
+ * replaces InsContextAtt.forward (mmdet3d/models/middle_encoders/fusion_encoder.py:768-830) = query position embedding
+ * (PositionEmbeddingLearned :176-190) + `layers` x DeformableTransformerDecoderLayer.forward (:600-674: self-attention,
+ * MSDeformAttn :523-598 with ms_deform_attn_core ops/functions/ms_deform_attn_func.py:41-61, FFN, three LayerNorms), and
+ * the key / value in-projection of Instane2SceneAtt's MultiheadAttention (:441-462) applied to its output.
+ * scene_tokens [B, G*G, C] fp16 (conv_scene output, [Y,X] frame); top_idx [B, K] int32 cell n = y*G + x; value [B*G*G, ldv]
+ * fp16 = value_proj(tokens + key_pos) of layer l at columns [l*C, (l+1)*C); out [B, K, C] fp32; kv_out [B, K, 2C] fp16 or
+ * NULL.  C = 128, 8 heads, 16 points, K <= 224.  packed_weights (fp16) / params (fp32): layouts of
+ * isfusion_b200.fusion_encoder.pack_decoder (sizes from isf_ins_context_decoder_sizes); every weight matrix [N,128] is
+ * stored per 8 output rows in mma.sync B-fragment order. */
+int isf_ins_context_decoder_sizes(int layers, size_t* packed_weight_bytes, size_t* param_floats);
+int isf_ins_context_decoder(const void* scene_tokens, const int* top_idx, const void* value, int ldv,
+                            const void* packed_weights, const float* params, int batch, int grid, int num_queries,
+                            int channels, int heads, int points, int layers, float* out, void* kv_out, void* stream);
+
 /* ---- K9b: multi-scale deformable attention backward -------------------------------
  * replaces mmcv._ext.ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
  *   grad_output, grad_value, grad_sampling_loc, grad_attn_weight, im2col_step)

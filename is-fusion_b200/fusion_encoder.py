@@ -12,6 +12,7 @@ transposing the 3x3 kernels (conv(x^T, W)^T == conv(x, W^T)) instead of the acti
 """
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -507,6 +508,53 @@ class DeformableTransformerDecoderLayer(nn.Module):
         return self.norm3(tgt + tgt2)
 
 
+# a11: one fused launch (csrc/decoder.cu) instead of ~60 small torch launches; ISF_DECODER=torch keeps the module-by-module
+# path (the second statement of the same arithmetic, used by the parity test)
+FUSED_DECODER = os.environ.get('ISF_DECODER', 'fused') == 'fused'
+
+
+def _frag_pack(w):
+    """[N, 128] weight (nn.Linear layout) -> fp16 in the B-fragment order of mma.sync.m16n8k16 per 8 output rows: lane
+    (n % 8) * 4 + l4 holds, contiguously, the halves k = ks*16 + j*8 + l4*2 + {0,1} for ks = 0..7, j = 0..1 (csrc/decoder.cu gemm32)."""
+    n, k = w.shape
+    assert k == 128 and n % 8 == 0
+    v = w.detach().half().view(n // 8, 8, 8, 2, 4, 2)          # (ntile, n_in, ks, j, l4, pair)
+    return v.permute(0, 1, 4, 2, 3, 5).reshape(n, 128).contiguous()
+
+
+def pack_decoder(ia, mha):
+    """packed fp16 weights + fp32 parameters of isf_ins_context_decoder for InsContextAtt `ia` (+ the k / v rows of the
+    instance->scene MultiheadAttention `mha`); row / offset plan = the constants of csrc/decoder.cu (namespace dec)."""
+    c = ia.layers[0].norm1.normalized_shape[0]
+    pe = ia.query_pos_embed.position_embedding_head
+    conv1, bn, conv2 = pe[0], pe[1], pe[3]
+    s1 = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    t1 = bn.bias - bn.running_mean * s1 + conv1.bias * s1
+    rows = [_frag_pack(conv2.weight.detach()[:, :, 0])]
+    fpar = [conv1.weight.detach()[:, :, 0].reshape(-1), s1.detach(), t1.detach(), conv2.bias.detach()]
+    for l in ia.layers:
+        sa, ca = l.self_attn, l.cross_attn
+        rows += [_frag_pack(sa.in_proj_weight.detach()[:2 * c]), _frag_pack(sa.in_proj_weight.detach()[2 * c:]),
+                 _frag_pack(sa.out_proj.weight.detach()),
+                 _frag_pack(torch.cat([ca.sampling_offsets.weight.detach(), ca.attention_weights.weight.detach()], 0)),
+                 _frag_pack(ca.output_proj.weight.detach()), _frag_pack(l.linear1.weight.detach()), _frag_pack(l.linear2.weight.detach())]
+        fpar += [sa.in_proj_bias.detach()[:2 * c], sa.in_proj_bias.detach()[2 * c:], sa.out_proj.bias.detach(),
+                 l.norm2.weight.detach(), l.norm2.bias.detach(),
+                 torch.cat([ca.sampling_offsets.bias.detach(), ca.attention_weights.bias.detach()], 0), ca.output_proj.bias.detach(),
+                 l.norm1.weight.detach(), l.norm1.bias.detach(), l.linear1.bias.detach(), l.linear2.bias.detach(),
+                 l.norm3.weight.detach(), l.norm3.bias.detach()]
+    rows.append(_frag_pack(mha.in_proj_weight.detach()[c:]))
+    fpar.append(mha.in_proj_bias.detach()[c:])
+    wp = torch.cat(rows, 0).contiguous()
+    fp = torch.cat([t.float().reshape(-1) for t in fpar]).contiguous()
+    nb, nf = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    L.check(L.lib().isf_ins_context_decoder_sizes(len(ia.layers), ctypes.byref(nb), ctypes.byref(nf)))
+    if wp.numel() * 2 != nb.value or fp.numel() != nf.value:
+        raise L.IsfError('pack_decoder: layout mismatch with the library (%d / %d bytes, %d / %d floats)'
+                         % (wp.numel() * 2, nb.value, fp.numel(), nf.value))
+    return wp, fp
+
+
 class InsContextAtt(nn.Module):
     def __init__(self, num_layers=1, embed_dims=128, bev_size=180, n_points=16):
         super().__init__()
@@ -603,6 +651,7 @@ class ISFusionEncoder(_Packable):
             pk['i2s_bo'] = mha.out_proj.bias.detach().float().contiguous()
             n = self.instance_to_scene_att.norm
             pk['i2s_ln'] = (n.weight.detach().float().contiguous(), n.bias.detach().float().contiguous(), n.eps)
+            pk['dec_w'], pk['dec_f'] = pack_decoder(ia, mha)
             pk['shapes'] = torch.tensor([[g, g]], dtype=torch.long, device=device)
             pk['lvl0'] = torch.zeros(1, dtype=torch.long, device=device)
             self.__dict__['_pk'] = pk
@@ -673,26 +722,35 @@ class ISFusionEncoder(_Packable):
         plain_from = 8 if self.num_views == 6 else self.num_classes      # classes 8,9: 1x1 NMS (:1107-1115)
         L.check(lib.isf_heatmap_topk(L.ptr(logits), bs, self.num_classes, g, g, plain_from, k, L.ptr(top_yx),
                                      L.ptr(None), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
-        top_yx = top_yx.long()                                  # n = y*G + x  (reference index t = x*G + y)
-        ty, tx = top_yx // g, top_yx % g
-        # reference: query_pos = bev_pos[t] = (x+.5, y+.5); query_pos_new swaps -> (y+.5, x+.5); /bev_size
-        ref_pts = torch.stack([ty.float() + 0.5, tx.float() + 0.5], -1) / g
+        ty, tx = top_yx // g, top_yx % g                        # n = y*G + x  (reference index t = x*G + y)
         # conv_scene in the [Y,X] frame == the reference's x_scene transposed back (InsContextAtt :797)
         x_scene = _conv(bev, pk['scene'])                                                     # [B,Y,X,C]
         toks = x_scene.reshape(bs, g * g, c)
-        x_ins = torch.gather(toks, 1, top_yx[..., None].expand(-1, -1, c)).float()            # [B,K,C]
         ia = self.instance_att
         src = (toks + pk['key_pos'][None]).reshape(bs * g * g, c)
         value = gemm(src, pk['value_w'], shift=pk['value_b'])                                 # both layers: [T, 2C]
-        qpe = ia.query_pos_embed(ref_pts).permute(0, 2, 1)                                    # [B,K,C]
-        out = x_ins
-        for li, layer in enumerate(ia.layers):
-            v = value[:, li * c:(li + 1) * c].reshape(bs, g * g, 8, c // 8)
-            out = layer(out, qpe, ref_pts[:, :, None], v.contiguous(), pk['shapes'], pk['lvl0'])
+        if FUSED_DECODER:
+            # a11 in one launch: query position embedding + both decoder layers + the k | v projection of the i2s attention
+            # (reference: query_pos = bev_pos[t] = (x+.5, y+.5); query_pos_new swaps -> (y+.5, x+.5); / bev_size — in-kernel)
+            out = torch.empty((bs, k, c), dtype=torch.float32, device=dev)
+            kv = torch.empty((bs, k, 2 * c), dtype=torch.float16, device=dev)
+            toks_c = toks if toks.is_contiguous() else toks.contiguous()
+            L.check(lib.isf_ins_context_decoder(L.ptr(toks_c), L.ptr(top_yx), L.ptr(value), value.stride(0), L.ptr(pk['dec_w']),
+                                                L.ptr(pk['dec_f']), bs, g, k, c, 8, ia.layers[0].cross_attn.n_points, len(ia.layers),
+                                                L.ptr(out), L.ptr(kv), L.stream()))
+        else:
+            tl = top_yx.long()
+            ref_pts = torch.stack([ty.float() + 0.5, tx.float() + 0.5], -1) / g
+            x_ins = torch.gather(toks, 1, tl[..., None].expand(-1, -1, c)).float()            # [B,K,C]
+            qpe = ia.query_pos_embed(ref_pts).permute(0, 2, 1)                                # [B,K,C]
+            out = x_ins
+            for li, layer in enumerate(ia.layers):
+                v = value[:, li * c:(li + 1) * c].reshape(bs, g * g, 8, c // 8)
+                out = layer(out, qpe, ref_pts[:, :, None], v.contiguous(), pk['shapes'], pk['lvl0'])
+            kv = F.linear(out, pk['i2s_wkv'], pk['i2s_bkv']).half().contiguous()              # [B,K,2C]
         # instance -> scene attention (a12)
         ins_tok = _conv(bev, pk['ins']).reshape(bs * g * g, c)                                # query tokens
         q = gemm(ins_tok, pk['i2s_wq'], shift=pk['i2s_bq'])
-        kv = F.linear(out, pk['i2s_wkv'], pk['i2s_bkv']).half().contiguous()                  # [B,K,2C]
         att = torch.empty_like(q)
         L.check(lib.isf_i2s_attention(L.ptr(q), L.ptr(kv), bs, g * g, k, c, 8, L.ptr(att), L.stream()))
         query_ins = gemm(att, pk['i2s_wo'], shift=pk['i2s_bo'], residual=ins_tok, ln=pk['i2s_ln'])
@@ -704,7 +762,7 @@ class ISFusionEncoder(_Packable):
         L.check(lib.isf_channel_attention(L.ptr(scene), c, L.ptr(query_ins), c, bs, g, c, L.ptr(fused), c, L.ptr(caws),
                                           ctypes.c_size_t(caws.numel()), L.stream()))
         ins_heatmap = logits.transpose(2, 3)                  # back to the reference's [X,Y] frame
-        self._dbg = dict(top_idx=tx * g + ty, x_ins=out)
+        self._dbg = dict(top_idx=(tx * g + ty).long(), x_ins=out)
         return fused, ins_heatmap
 
     # ------------------------------------------------------------------ forward

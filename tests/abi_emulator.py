@@ -92,6 +92,54 @@ class _FusionLib:
         _set_size(out, 1024)
         return 0
 
+    # ------------------------------------------------------------------ isf_ins_context_decoder (a11, one launch)
+    def isf_ins_context_decoder_sizes(self, layers, nbytes, nfloats):
+        _set_size(nbytes, (128 + layers * 1280 + 256) * 128 * 2)
+        _set_size(nfloats, 640 + layers * 2048 + 256)
+        return 0
+
+    def isf_ins_context_decoder(self, toks, top_idx, value, ldv, wp, fpar, batch, grid, k, c, heads, points, layers, out, kv_out,
+                                stream):
+        """torch statement of csrc/decoder.cu from the PACKED buffers (fragment order undone), fp32 throughout."""
+        assert c == 128 and heads == 8 and points == 16 and k <= 224 and wp.dtype == torch.float16 and fpar.dtype == torch.float32
+        n_rows = wp.numel() // 128
+        w = wp.view(n_rows // 8, 8, 4, 8, 2, 2).permute(0, 1, 3, 4, 2, 5).reshape(n_rows, 128).float()
+        f = fpar
+        g, s = grid, grid * grid
+        toks = toks.reshape(batch, s, c).float()
+        value = value.reshape(batch, s, ldv).float()
+        ln = lambda x, gm, bt: F.layer_norm(x, (c,), gm, bt, 1e-5)
+        for b in range(batch):
+            n = top_idx[b].long()
+            ref = torch.stack([((n // g).float() + 0.5) / g, ((n % g).float() + 0.5) / g], -1)
+            x = toks[b][n]
+            h1 = torch.relu((ref @ f[0:256].view(c, 2).t()) * f[256:384] + f[384:512])
+            qpe = h1 @ w[0:128].t() + f[512:640]
+            for li in range(layers):
+                wl, fl = w[128 + li * 1280:], f[640 + li * 2048:]
+                qk = (x + qpe) @ wl[0:256].t() + fl[0:256]
+                q, kk = qk[:, :c].view(k, 8, 16), qk[:, c:].view(k, 8, 16)
+                v = (x @ wl[256:384].t() + fl[256:384]).view(k, 8, 16)
+                att = torch.softmax(torch.einsum('qhd,khd->hqk', q, kk) * 0.25, -1)
+                o = torch.einsum('hqk,khd->qhd', att, v).reshape(k, c)
+                x = ln(x + o @ wl[384:512].t() + fl[384:512], fl[512:640], fl[640:768])
+                soaw = (x + qpe) @ wl[512:896].t() + fl[768:1152]
+                so = soaw[:, :256].view(k, 8, 16, 2)
+                aw = torch.softmax(soaw[:, 256:].view(k, 8, 16), -1)
+                loc = ref[:, None, None, :] + so / g                                        # component 0 = width coordinate
+                vmap = value[b, :, li * c:(li + 1) * c].reshape(g, g, 8, 16).permute(2, 3, 0, 1)     # [8,16,Y,X]
+                grids = (2 * loc - 1).permute(1, 0, 2, 3)                                   # [8,K,16,2]
+                smp = F.grid_sample(vmap, grids, mode='bilinear', padding_mode='zeros', align_corners=False)   # [8,16,K,16]
+                ms = (smp * aw.permute(1, 0, 2)[:, None]).sum(-1).permute(2, 0, 1).reshape(k, c)
+                x = ln(x + ms @ wl[896:1024].t() + fl[1152:1280], fl[1280:1408], fl[1408:1536])
+                hdn = torch.relu(x @ wl[1024:1152].t() + fl[1536:1664])
+                x = ln(x + hdn @ wl[1152:1280].t() + fl[1664:1792], fl[1792:1920], fl[1920:2048])
+            out[b] = x
+            if kv_out is not None:
+                wkv, bkv = w[128 + layers * 1280:], f[640 + layers * 2048:]
+                kv_out[b] = (x @ wkv[:256].t() + bkv[:256]).half()
+        return 0
+
     # ------------------------------------------------------------------ isf_conv3x3_nhwc_f16
     def isf_conv3x3_nhwc_f16(self, x, batch, h, w, cin, ldx, wpk, cout_pad, shift, stride, relu, out, ldo, cout_store, stream):
         assert cin % 64 == 0 and ldx >= cin and cout_pad in (32, 64, 128, 256) and wpk.shape == (cout_pad, 9 * cin)

@@ -380,3 +380,48 @@ def test_bench_workload_parity_through_frame_pipeline():
           % (r_hm, overlap, r0, m0, r1, m1))
     assert r_hm < 1e-3 and overlap >= 0.98
     assert r0 < 2e-3 and r1 < 2.5e-3
+
+
+@pytest.mark.parametrize('batch', [1, 2])
+def test_fused_instance_decoder_matches_module_path_and_oracle(batch):
+    """a11 in one launch (isf_ins_context_decoder: position embedding + 2 x (self-attention, deformable cross-attention, FFN,
+    3 LayerNorms) + the k | v projection of the i2s attention; fp16 operands on mma.sync, fp32 accumulation / residual stream)
+    against (a) the module-by-module fp32 torch path over the SAME selection and value maps and (b) the CPU oracle."""
+    import isfusion_b200.fusion_encoder as FE
+    ref, net = build_pair(0)
+    pts = [synth.make_points(15000, 'S', 30 + s) for s in range(batch)]
+    l2i, aug, laug = synth.make_calib(batch)
+    feats = synth.make_img_feats(batch)
+    metas = [dict(input_shape=(256, 704))] * batch
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug)
+    dpts, dfeats = [p.cuda() for p in pts], [f.cuda() for f in feats]
+    old = FE.FUSED_DECODER
+    try:
+        FE.FUSED_DECODER = False
+        mf, mhm = net(dpts, dfeats, metas, **kw)
+        x_mod = net.fusion_encoder._dbg['x_ins'].clone()
+        FE.FUSED_DECODER = True
+        ff, fhm = net(dpts, dfeats, metas, **kw)
+        x_fus = net.fusion_encoder._dbg['x_ins'].clone()
+        top = net.fusion_encoder._dbg['top_idx'].clone()
+        torch.cuda.synchronize()
+    finally:
+        FE.FUSED_DECODER = old
+    assert torch.equal(mhm, fhm)                                  # same heat-map -> same selection on both paths
+    r_mod, m_mod = rel(x_fus, x_mod)
+    ref.fusion_encoder.force_top_idx = top.cpu()
+    try:
+        rf, _ = ref(pts, feats, metas, **kw)
+    finally:
+        ref.fusion_encoder.force_top_idx = None
+    x_ref = ref.fusion_encoder._dbg['x_ins'].transpose(1, 2)      # [B,C,K] -> [B,K,C]
+    r_ref, m_ref = rel(x_fus, x_ref)
+    r0, _ = rel(ff[0], rf[0])
+    r1, _ = rel(ff[1], rf[1])
+    print('fused decoder: vs module path rel %.2e max %.2e | vs oracle rel %.2e max %.2e | feat0 %.2e feat1 %.2e' % (r_mod, m_mod, r_ref, m_ref, r0, r1))
+    assert x_fus.shape == x_mod.shape == x_ref.shape
+    assert torch.isfinite(x_fus).all()
+    assert r_mod < 2e-3 and r_ref < 2e-3
+    assert r0 < 2e-3 and r1 < 2.5e-3
+    for a, b in zip(ff, mf):
+        assert rel(a, b)[0] < 1e-3
