@@ -38,7 +38,7 @@ const char* isf_last_error(void);
 /* number of kernels this library has launched since the last reset (bench.py gpu_launches) */
 unsigned long long isf_launch_count(int reset);
 /* runtime options: "gemm_cluster" = 1 | 2 : thread-block-cluster size of the tcgen05 GEMM (CTAs of a cluster
- * share every weight chunk through TMA multicast).  "gemm_mt" = 1 | 2 : 128-row sub-tiles per CTA tile of the
+ * share every weight chunk through TMA multicast).  "gemm_mt" = 1 | 2 | 3 : 128-row sub-tiles per CTA tile of the
  * sparse-conv GEMM (2 = one weight chunk feeds 256 output rows).  "gemm_debug" = bit mask of TIMING experiments
  * (results meaningless; csrc/tc_gemm.cuh GemmParams::debug).  "tile_order_drop_bits" = 0..26 : low occupancy-mask
  * bits left out of the sort of isf_spconv_tile_order (fewer radix passes).  "nbr_rows" = 0 | 1 : row-per-thread

@@ -41,7 +41,7 @@ extern "C" int isf_set_option(const char* name, int value) {
     g_isf_tile_order_drop_bits = value;
     return ISF_OK;
   }
-  if (name && strcmp(name, "gemm_mt") == 0 && (value == 1 || value == 2)) {
+  if (name && strcmp(name, "gemm_mt") == 0 && value >= 1 && value <= 3) {
     g_isf_gemm_mt = value;
     return ISF_OK;
   }

@@ -672,6 +672,87 @@ __global__ void __launch_bounds__(256) msda_kernel(const T* __restrict__ value, 
   }
 }
 
+// Fused bilinear-gather formulation for head_dim 16 (what the config instantiates): a WARP per (frame, query, head), a lane
+// per (sampling point, 16-byte slice of the head's channels).  A lane derives the corner geometry of its point once, fetches
+// 4 x 16 bytes (8 fp16 / 4 fp32 channels per corner) and the partial sums of the points are combined by shuffles.  The
+// thread-per-output-channel mapping above (the reference's ms_deformable_im2col_gpu_kernel mapping) re-derives the same
+// corners once per channel and fetches 2 bytes per load; it stays as the generic fallback for other head widths.
+template <typename T>
+__global__ void __launch_bounds__(256) msda_warp_kernel(const T* __restrict__ value, const long long* __restrict__ shapes,
+                                                        const long long* __restrict__ lvl_start, const float* __restrict__ loc,
+                                                        const float* __restrict__ attn, int B, int S, int H, int L, int Q, int P,
+                                                        float* __restrict__ out) {
+  constexpr int D = 16;
+  constexpr int OCT = D * (int)sizeof(T) / 16;          // lanes per sampling point: 2 (fp16) or 4 (fp32)
+  constexpr int CH = D / OCT;                           // channels per lane: 8 or 4
+  constexpr int SPP = 32 / OCT;                         // sampling points per pass
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % OCT, sidx = lane / OCT;
+  const long long nwarp = (long long)B * Q * H;
+  for (long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wid < nwarp;
+       wid += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int h = (int)(wid % H);
+    const int b = (int)(wid / ((long long)H * Q));
+    const float* lp = loc + wid * L * P * 2;
+    const float* ap = attn + wid * L * P;
+    float acc[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+    for (int s = sidx; s < L * P; s += SPP) {
+      const int l = s / P;
+      const int sh = (int)shapes[2 * l], sw = (int)shapes[2 * l + 1];
+      const float lw = lp[s * 2], lh = lp[s * 2 + 1];
+      const float wgt = ap[s];
+      const float him = lh * sh - 0.5f, wim = lw * sw - 0.5f;
+      if (him > -1.f && wim > -1.f && him < (float)sh && wim < (float)sw) {
+        const int hl = (int)floorf(him), wl = (int)floorf(wim);
+        const float lhh = him - hl, lww = wim - wl, hh = 1.f - lhh, hw = 1.f - lww;
+        const T* vb = value + ((long long)b * S + lvl_start[l]) * H * D + h * D + sub * CH;
+        const long long stride = (long long)H * D;
+        const float cw[4] = {hh * hw, hh * lww, lhh * hw, lhh * lww};
+        const bool ok[4] = {hl >= 0 && wl >= 0, hl >= 0 && wl + 1 <= sw - 1, hl + 1 <= sh - 1 && wl >= 0,
+                            hl + 1 <= sh - 1 && wl + 1 <= sw - 1};
+        const long long off[4] = {(long long)hl * sw + wl, (long long)hl * sw + wl + 1, (long long)(hl + 1) * sw + wl,
+                                  (long long)(hl + 1) * sw + wl + 1};
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = ok[k] ? __ldg((const uint4*)(vb + off[k] * stride)) : make_uint4(0, 0, 0, 0);
+        // same association as the reference kernel: (w1 v1 + w2 v2 + w3 v3 + w4 v4) * attention weight
+        float smp[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) smp[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if constexpr (sizeof(T) == 2) {
+            const __half2* hp = (const __half2*)&v[k];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(hp[e]);
+              smp[2 * e] += cw[k] * f.x; smp[2 * e + 1] += cw[k] * f.y;
+            }
+          } else {
+            const float* fp_ = (const float*)&v[k];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) smp[e] += cw[k] * fp_[e];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) acc[j] += smp[j] * wgt;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+#pragma unroll
+      for (int o = OCT; o < 32; o <<= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (sidx == 0) {
+      float* op = out + wid * D + sub * CH;
+#pragma unroll
+      for (int j = 0; j < CH; j += 4) *(float4*)(op + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+  }
+}
+
 // value [B,S,H,D] (fp32 or fp16), spatial_shapes int64 [L,2] (h,w), level_start_index int64 [L] (both DEVICE),
 // sampling_loc [B,Q,H,L,P,2] fp32 in [0,1] (x = width first), attn_weight [B,Q,H,L,P] fp32 -> out [B,Q,H*D] fp32
 extern "C" int isf_ms_deform_attn_forward(const void* value, int value_is_half, const long long* spatial_shapes,
@@ -680,16 +761,29 @@ extern "C" int isf_ms_deform_attn_forward(const void* value, int value_is_half, 
                                           float* out, void* stream) {
   ISF_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out);
   ISF_CHECK_ARG(B >= 1 && S >= 1 && H >= 1 && D >= 1 && L >= 1 && Q >= 1 && P >= 1);
-  long long n = (long long)B * Q * H * D;
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
   cudaStream_t st = (cudaStream_t)stream;
-  if (value_is_half)
-    msda_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)value, spatial_shapes, level_start_index, sampling_loc,
-                                                 attn_weight, B, S, H, D, L, Q, P, out);
-  else
-    msda_kernel<float><<<blocks, 256, 0, st>>>((const float*)value, spatial_shapes, level_start_index, sampling_loc,
-                                                attn_weight, B, S, H, D, L, Q, P, out);
+  const bool aligned = ((uintptr_t)value & 15) == 0;
+  if (D == 16 && aligned) {      // the fused bilinear-gather mapping: a warp per (frame, query, head)
+    const long long nw = (long long)B * Q * H;
+    int blocks = (int)((nw + 7) / 8);
+    if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+    if (value_is_half)
+      msda_warp_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)value, spatial_shapes, level_start_index, sampling_loc,
+                                                        attn_weight, B, S, H, L, Q, P, out);
+    else
+      msda_warp_kernel<float><<<blocks, 256, 0, st>>>((const float*)value, spatial_shapes, level_start_index, sampling_loc,
+                                                       attn_weight, B, S, H, L, Q, P, out);
+  } else {
+    long long n = (long long)B * Q * H * D;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ISF_NUM_SMS * 16) blocks = ISF_NUM_SMS * 16;
+    if (value_is_half)
+      msda_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)value, spatial_shapes, level_start_index, sampling_loc,
+                                                   attn_weight, B, S, H, D, L, Q, P, out);
+    else
+      msda_kernel<float><<<blocks, 256, 0, st>>>((const float*)value, spatial_shapes, level_start_index, sampling_loc,
+                                                  attn_weight, B, S, H, D, L, Q, P, out);
+  }
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();
   return ISF_OK;

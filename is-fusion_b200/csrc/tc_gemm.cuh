@@ -150,6 +150,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 columns of fp32
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B smem matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
@@ -208,7 +218,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;          // 64 fp16 = 128 B = one swizzle row
 constexpr int PRODUCERS = 256;  // 8 warps gather A; all of them also run the epilogue (two column halves)
 constexpr int MAX_TAPS = 27;
-constexpr int MAX_CHUNKS = 512;
+constexpr int MAX_CHUNKS = 256;     // K <= 16384
 constexpr int THREADS = PRODUCERS + 32;
 constexpr int PWARPS = PRODUCERS / 32;
 
@@ -219,7 +229,9 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NBR_OFF = STAGES * STAGE_BYTES;            // [MAX_TAPS][MT*128] int32 neighbour tile
   static constexpr int LIST_OFF = NBR_OFF + MAX_TAPS * MT * BM * 4;     // active chunk list (uint16) + flags
-  static constexpr int BAR_OFF = LIST_OFF + MAX_CHUNKS * 2 + 64 * 4;
+  static constexpr int VEC_OFF = LIST_OFF + MAX_CHUNKS * 2 + 64 * 4;     // epilogue scale[BN] | shift[BN] fp32 (column tiles <= 128: the
+  static constexpr int VEC_BYTES = BN <= 128 ? 2 * BN * 4 : 0;           // 256-column tile has no room left at 2 CTAs / SM)
+  static constexpr int BAR_OFF = VEC_OFF + VEC_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + tmem slot, + alignment slack
 };
 
@@ -292,7 +304,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
 // vectors and the row-statistics exchange): both warp halves take half of the row's columns, ONE pass over TMEM with the
 // half row kept in registers, partial (sum, sum of squares) exchanged through shared memory.
 template <int BN, int STAGES, int CS, int MT, bool LN>
-__global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
+__global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 2)) gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
   using SL = SmemLayout<BN, STAGES, MT>;
   static_assert(CS == 1 || MT == 1, "clusters only with single sub-tile CTAs");
   constexpr int TILE_M = BM * MT;
@@ -328,6 +340,13 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
     fence_barrier_init();
   }
   if (warp == PWARPS) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if constexpr (!LN && SL::VEC_BYTES > 0) {      // BN scale / shift of this CTA's columns -> shared memory, once per CTA
+    float* vec = (float*)(smem + SL::VEC_OFF);
+    for (int c = tid; c < BN; c += THREADS) {
+      vec[c] = p.scale ? p.scale[n0 + c] : 1.f;
+      vec[BN + c] = p.shift ? p.shift[n0 + c] : 0.f;
+    }
+  }
   if constexpr (LN) {       // per-column vectors of this CTA's columns -> shared memory (read there by every tile's epilogue)
     float* vec = (float*)(smem + SL::NBR_OFF);
     for (int c = tid; c < BN; c += THREADS) {
@@ -471,12 +490,12 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
         if (++s == STAGES) { s = 0; ++use; }
       }
       // ------------------------------------------------ epilogue
-      mbar_wait_b(accum_bar, tile_ctr & 1);
-      tc_fence_after();
       // warps 0-3 own columns [0, BN/2), warps 4-7 [BN/2, BN) of the same rows; the row-local LayerNorm needs the
       // whole row in one thread and stays on warps 0-3
       if constexpr (LN) {
         static_assert(!LN || (BN >= 64 && MT == 1), "LayerNorm epilogue: 64..256 columns, single sub-tile");
+        mbar_wait_b(accum_bar, tile_ctr & 1);
+        tc_fence_after();
         constexpr int HC = BN / 2;                       // columns per thread
         const int half = warp >> 2;
         const float* vec = (const float*)(smem + SL::NBR_OFF);
@@ -559,6 +578,98 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
       const bool ln = p.ln_gamma != nullptr;
       const int cb_lo = (ln || BN < 64) ? 0 : (warp >> 2) * (BN / 2);
       const int cb_hi = (ln || BN < 64) ? ((warp >> 2) ? 0 : BN) : cb_lo + BN / 2;
+      if (!ln) {
+        // pipelined epilogue (no LayerNorm): the row maps and the first residual block are fetched BEFORE the wait for the
+        // accumulator, the residual of block i+1 while block i is processed, scale / shift come from shared memory (<= 128
+        // columns) — the round-2 source-level profile had 20 % of the kernel's stall samples on these dependent global loads
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * BN);
+        const int grow = row0 + mt * BM + r;
+        const bool row_ok = grow < m_total;
+        long long orow = grow;
+        if (p.out_rows && row_ok) orow = p.out_rows[grow];
+        long long rrow = row_ok ? (long long)grow : -1;
+        if (p.res_rows && row_ok) rrow = p.res_rows[grow];
+        const bool store_ok = row_ok && orow >= 0;
+        const bool has_res = p.residual != nullptr && rrow >= 0 && cb_lo < cb_hi;
+        const uint4* rp = has_res ? (const uint4*)(p.residual + rrow * p.ldr + n0 + cb_lo) : nullptr;
+        uint4 rnext[2];                                   // 16-column blocks keep the live set small (2-3 CTAs / SM)
+        if (has_res) { rnext[0] = rp[0]; rnext[1] = rp[1]; }
+        if (mt == 0) {
+          mbar_wait_b(accum_bar, tile_ctr & 1);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int cb = cb_lo; cb < cb_hi; cb += 16) {
+          uint4 rcur[2];
+          if (has_res) {
+            rcur[0] = rnext[0]; rcur[1] = rnext[1];
+            if (cb + 16 < cb_hi) { rnext[0] = rp[(cb + 16 - cb_lo) / 8]; rnext[1] = rp[(cb + 16 - cb_lo) / 8 + 1]; }
+          }
+          uint32_t v[16];
+          tmem_ld16(t_lane + cb, v);
+          tmem_ld_wait();
+          float x[16];
+          if constexpr (SL::VEC_BYTES > 0) {
+            const float* vs = (const float*)(smem + SL::VEC_OFF) + cb;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float y = __uint_as_float(v[j]);
+              if (p.scale) y *= vs[j];
+              if (p.shift) y += vs[BN + j];
+              x[j] = y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float y = __uint_as_float(v[j]);
+              if (p.scale) y *= p.scale[n0 + cb + j];
+              if (p.shift) y += p.shift[n0 + cb + j];
+              x[j] = y;
+            }
+          }
+          if (has_res) {
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              const __half2* h = (const __half2*)&rcur[j4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
+              }
+            }
+          }
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+          } else if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = gelu_erf(x[j]);
+          }
+          if (store_ok) {
+            if (p.out) {
+              uint4* op = (uint4*)(p.out + orow * p.ldo + n0 + cb);
+#pragma unroll
+              for (int j4 = 0; j4 < 2; ++j4) {
+                uint4 u;
+                __half2* h = (__half2*)&u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+                op[j4] = u;
+              }
+            }
+            if (p.out_f32) {
+              float4* op = (float4*)(p.out_f32 + orow * p.ldo + n0 + cb);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+            }
+          }
+        }
+        }
+      } else {
+      mbar_wait_b(accum_bar, tile_ctr & 1);
+      tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
       const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * BN);
@@ -615,6 +726,7 @@ __global__ void __launch_bounds__(THREADS) gemm_kernel(const GemmParams p, const
             for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
           }
         }
+      }
       }
       }
       // all TMEM reads of this tile are ordered before the __syncthreads below, after which the MMA
@@ -758,6 +870,7 @@ static inline int dispatch_gemm_cs(const GemmParams& p, int bn, int m_upper, cud
 // 256-row CTA tiles (two accumulators, one weight chunk per 256 rows): isf_set_option("gemm_mt", 2), sparse-conv launches
 static inline int dispatch_gemm_mt2(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
   switch (bn) {
+    case 32: return launch_gemm<32, 4, 1, 2>(p, m_upper, st);      // 4 x 36 KB + 27 KB
     case 64: return launch_gemm<64, 3, 1, 2>(p, m_upper, st);      // 3 x 40 KB + 27 KB: 1 CTA/SM
     case 128: return launch_gemm<128, 3, 1, 2>(p, m_upper, st);    // 3 x 48 KB + 27 KB
     case 256: return launch_gemm<256, 3, 1, 2>(p, m_upper, st);    // 3 x 64 KB + 27 KB = 221 KB, all 512 TMEM columns
@@ -784,7 +897,9 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
     }
   }
   if (::g_isf_gemm_v3 && spconv3_supported(p, bn) && m_upper >= 4 * BM) return dispatch_spconv3(p, bn, m_upper, st);
-  if (::g_isf_gemm_mt == 2 && p.nbr != nullptr && m_upper >= 148 * 256) return dispatch_gemm_mt2(p, bn, m_upper, st);
+  // 256-row CTA tiles: measured faster for the 32-column (-22 %) and 256-column (-7 %) layers, slower for 64 / 128 (round 2)
+  if (p.nbr != nullptr && m_upper >= 148 * 256 &&
+      (::g_isf_gemm_mt == 2 || (::g_isf_gemm_mt == 3 && (bn == 32 || bn == 256)))) return dispatch_gemm_mt2(p, bn, m_upper, st);
   switch (::g_isf_gemm_cluster) {
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
     default: break;

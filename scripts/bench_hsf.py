@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""BASELINE configs[2] — HSF-only ablation on one GPU: Hierarchical Scene Fusion of the IS-Fusion neck in isolation,
+Point-to-Grid (camera -> BEV projection of the pillars, a6) + Grid-to-Region (conv_fusion 768 -> 128, a7, and the shifted-window
+transformer over the 180 x 180 BEV, a8/a9; optionally the second region level on the 90 x 90 map), on a synthetic frame.
+The sequence is captured into ONE CUDA graph and replayed; per-stage times come from a second, eager pass with CUDA events.
+    python scripts/bench_hsf.py [--steps 200 --warmup 20 --points 300000 --levels 1]
+Tensor-core path: fp16 operands, fp32 accumulation (tcgen05 kind::f16 runs fp16 and bf16 at the same rate; the library has no
+bf16 instantiation — DESIGN.md section 7)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--points', type=int, default=300000)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--levels', type=int, default=1, help='region levels: 1 = 180x180 only, 2 = + the 90x90 level')
+    args = ap.parse_args()
+    import synth
+    from __graft_entry__ import make_net
+    from isfusion_b200 import _lib as L
+    dev = torch.device(os.environ.get('ISF_TOOL_DEVICE', 'cuda:0'))
+    img = (384, 1056)
+    net = make_net(0).to(dev).eval()
+    enc = net.fusion_encoder
+    g = enc.bev_size
+    pts = [synth.make_points(args.points, 'S', 0).to(dev)]
+    l2i, aug, laug = synth.make_calib(1, img)
+    feats = [f.to(dev) for f in synth.make_img_feats(1, img)]
+    metas = [dict(input_shape=img)]
+    kw = dict(lidar2img=l2i, img_aug_matrix=aug, lidar_aug_matrix=laug, img_metas=metas)
+    kw['cam_proj'] = net.fusion_encoder.camera_projection(l2i, aug, laug, 1, dev)      # input-independent of the graph
+    pm = dict(pillars_list=net.voxelize_nosync(pts), pts=pts, pillar_size=net.pillar_size)
+    torch.manual_seed(1)
+    lidar_bev = (torch.randn(1, g, g, 512, device=dev) * 0.5).half()          # stands for the sparse encoder's BEV output
+    lvl1_in = (torch.randn(1 * (g // 2) * (g // 2), 256, device=dev) * 0.5).half()
+    pk = enc._pack(dev)
+    from isfusion_b200.fusion_encoder import _conv
+    cat = enc.new_fusion_buffer(1, dev)
+
+    def hsf():
+        cat[..., :enc.embed_dims].zero_()
+        enc.img_fv_to_bev([feats[1]], 1, out=cat, pts_metas=pm, **kw)                       # a6: Point-to-Grid
+        cat[..., enc.embed_dims:] = lidar_bev
+        bev = _conv(cat, pk['fusion'])                                                       # a7
+        x = enc.grid2region_att[0](enc.get_regions[0](bev.reshape(g * g, -1), None, 1))      # a8 / a9: Grid-to-Region
+        outs = [x[0]]
+        if args.levels > 1:
+            outs.append(enc.grid2region_att[1](enc.get_regions[1](lvl1_in, None, 1))[0])
+        return outs
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    L.launch_count(reset=True)
+    hsf()
+    launches = L.launch_count(reset=True)
+    ms_eager = timed(hsf, max(5, args.steps // 10), 3)
+    if dev.type == 'cuda':
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                hsf()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = hsf()
+        ms = timed(graph.replay, args.steps, args.warmup)
+    else:                                   # emulator dry run (tests/test_tools_dry_run.py)
+        outs, ms = hsf(), ms_eager
+    # stage split (eager, CUDA events around each stage)
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    marks = [ev() for _ in range(5)]
+    marks[0].record()
+    cat[..., :enc.embed_dims].zero_()
+    enc.img_fv_to_bev([feats[1]], 1, out=cat, pts_metas=pm, **kw)
+    marks[1].record()
+    cat[..., enc.embed_dims:] = lidar_bev
+    bev = _conv(cat, pk['fusion'])
+    marks[2].record()
+    x = enc.grid2region_att[0](enc.get_regions[0](bev.reshape(g * g, -1), None, 1))
+    marks[3].record()
+    if args.levels > 1:
+        enc.grid2region_att[1](enc.get_regions[1](lvl1_in, None, 1))
+    marks[4].record()
+    torch.cuda.synchronize()
+    st = {'a6 point-to-grid (cam2bev)': marks[0].elapsed_time(marks[1]), 'a7 conv_fusion': marks[1].elapsed_time(marks[2]),
+          'a8+a9 grid-to-region level 0': marks[2].elapsed_time(marks[3])}
+    if args.levels > 1:
+        st['a8+a9 grid-to-region level 1'] = marks[3].elapsed_time(marks[4])
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        peaks = {}
+    flops = 2.0 * g * g * 9 * 768 * 128 + 15.3e9 + (14.0e9 if args.levels > 1 else 0.0)       # conv_fusion + SST levels
+    cam_bytes = g * g * 12 * 12.0 + 6 * 256 * (img[0] // 16) * (img[1] // 16) * 2.0 + 256.0 * g * g * 2
+    line = {'metric': 'frames/sec HSF-only (Point-to-Grid + Grid-to-Region over 180x180 BEV)', 'value': 1000.0 / ms, 'unit': 'frames/s',
+            'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'eager_ms_per_step': ms_eager, 'higher_is_better': True,
+            'dtype': 'f16', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[2]: HSF-only ablation', 'points_per_frame': args.points, 'cams': 6, 'img': list(img),
+                       'bev': g, 'region_levels': args.levels, 'mode': 'one CUDA graph replayed back to back (inputs resident)'},
+            'gpu_launches_per_step': int(launches), 'stage_ms_eager': {k: round(v, 4) for k, v in st.items()},
+            'roofline': {'bound': 'tensor', 'achieved': flops / (ms * 1e-3) / 1e12, 'peak': peaks.get('bf16_tflops', 1590.0), 'unit': 'TFLOP/s',
+                         'frac': flops / (ms * 1e-3) / 1e12 / peaks.get('bf16_tflops', 1590.0),
+                         'note': 'whole HSF step: %.1f GFLOP of conv_fusion + window-transformer work over the replay time; the step is '
+                                 'launch / latency bound at batch 1 (see stage split)' % (flops / 1e9),
+                         'point_to_grid': {'algorithmic_MB': round(cam_bytes / 1e6, 2), 'GBps': cam_bytes / st['a6 point-to-grid (cam2bev)'] / 1e6,
+                                           'hbm_peak_GBps': peaks.get('hbm_gbs', 6650.0)}},
+            'out_shapes': [list(o.shape) for o in outs]}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

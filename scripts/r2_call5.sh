@@ -4,6 +4,8 @@ LOG=gpurun_out/r2_call5.log
 . "$(dirname "$0")/r2_common.sh"
 step "fused decoder"
 t 300 python -m pytest tests/test_fusion_gpu.py -x -q -s -m gpu -k "fused_instance_decoder" >> $LOG 2>&1
+step "GEMM per layer (pipelined epilogue)"
+t 300 python scripts/bench_gemm_layers.py >> $LOG 2>&1
 step "default GPU suite"
 t 900 python -m pytest tests -q -m gpu >> $LOG 2>&1
 step "bench: default (fused decoder), module-path decoder"

@@ -75,7 +75,7 @@ def test_new_host_side_entry_points_validate_arguments():
     n = ctypes.c_size_t(0)
     assert lib.isf_spconv_tile_order_workspace_size(300000, ctypes.byref(n)) == 0 and n.value > 300000 * 24
     assert lib.isf_spconv_tile_order_workspace_size(-1, ctypes.byref(n)) == 1
-    for name, good, bad in (('tile_order_drop_bits', 11, 27), ('nbr_rows', 1, 2), ('gemm_mt', 2, 3), ('gemm_debug', 0, 8)):
+    for name, good, bad in (('tile_order_drop_bits', 11, 27), ('nbr_rows', 1, 2), ('gemm_mt', 3, 4), ('gemm_debug', 0, 8)):
         assert lib.isf_set_option(name.encode(), good) == 0, name
         assert lib.isf_set_option(name.encode(), bad) == 1 and b'unknown option or bad value' in lib.isf_last_error(), name
     for name, default in (('tile_order_drop_bits', 0), ('nbr_rows', 1), ('gemm_mt', 1), ('gemm_debug', 0)):

@@ -211,8 +211,8 @@ def test_neck_end_to_end(npts, batch):
     print('neck e2e: heatmap rel %.2e | top-200 overlap %.3f | feat0 rel %.2e max %.2e | feat1 rel %.2e max %.2e'
           % (r_hm, overlap, r0, m0, r1, m1))
     assert gf[0].shape == rf[0].shape and gf[1].shape == rf[1].shape and ghm.shape == rhm.shape
-    assert r_hm < 5e-3 and overlap > 0.9
-    assert r0 < 1e-2 and r1 < 1e-2
+    assert r_hm < 1e-3 and overlap > 0.95
+    assert r0 < 2e-3 and r1 < 2.5e-3       # measured 9.0e-4 / 1.4e-3 (fp16 storage through ~20 / ~35 layers)
 
 
 def test_sync_free_and_graph_paths_match_exact_path():
@@ -424,4 +424,4 @@ def test_fused_instance_decoder_matches_module_path_and_oracle(batch):
     assert r_mod < 2e-3 and r_ref < 2e-3
     assert r0 < 2e-3 and r1 < 2.5e-3
     for a, b in zip(ff, mf):
-        assert rel(a, b)[0] < 1e-3
+        assert rel(a, b)[0] < 2e-3

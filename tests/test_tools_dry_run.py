@@ -105,3 +105,11 @@ def test_bench_gemm_layers_dry_run(monkeypatch, capsys):
     assert out.count('bit-identical to the first variant') == 3 and 'DIFFERS' not in out       # storage, ord16, gemm_mt=2
     assert 'total ms:' in out and sp.TILE_ORDER == 31
     assert L.lib().isf_set_option(b'gemm_mt', 1) == 0
+
+
+def test_bench_hsf_dry_run(monkeypatch, capsys):
+    line = _run_tool('bench_hsf', ['--steps', '1', '--warmup', '0', '--points', '3000', '--levels', '2'], monkeypatch, capsys)
+    assert line['config']['region_levels'] == 2 and len(line['out_shapes']) == 2
+    for key in ('a6 point-to-grid (cam2bev)', 'a7 conv_fusion', 'a8+a9 grid-to-region level 0', 'a8+a9 grid-to-region level 1'):
+        assert key in line['stage_ms_eager'], key
+    assert line['roofline']['bound'] == 'tensor' and 'point_to_grid' in line['roofline']
