@@ -39,7 +39,9 @@ const char* isf_last_error(void);
 unsigned long long isf_launch_count(int reset);
 /* runtime options: "gemm_cluster" = 1 | 2 : thread-block-cluster size of the tcgen05 GEMM (CTAs of a cluster
  * share every weight chunk through TMA multicast).  "gemm_mt" = 1 | 2 | 3 : 128-row sub-tiles per CTA tile of the
- * sparse-conv GEMM (2 = one weight chunk feeds 256 output rows).  "gemm_debug" = bit mask of TIMING experiments
+ * sparse-conv GEMM (2 = one weight chunk feeds 256 output rows, 3 = only for the 32- and 256-column layers).  "gemm_v4" =
+ * 0 | 1 | 2 : schedule with dedicated epilogue warps and a double-buffered TMEM accumulator (csrc/tc_gemm4.cuh; 1 = sparse-
+ * conv launches, 2 = dense GEMMs too).  "gemm_ln_fast" = 0 | 1 : split-row LayerNorm epilogue (default 1).  "gemm_debug" = bit mask of TIMING experiments
  * (results meaningless; csrc/tc_gemm.cuh GemmParams::debug).  "tile_order_drop_bits" = 0..26 : low occupancy-mask
  * bits left out of the sort of isf_spconv_tile_order (fewer radix passes).  "nbr_rows" = 0 | 1 : row-per-thread
  * kernel behind isf_spconv_neighbors_bitmap (one bitmap word load per (kz, ky) instead of per tap; same results;

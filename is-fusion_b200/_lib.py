@@ -26,7 +26,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.isf_last_error.restype = ctypes.c_char_p
         _lib.isf_launch_count.restype = ctypes.c_ulonglong
-        for item in os.environ.get('ISF_OPTS', '').split(','):        # e.g. ISF_OPTS=gemm_v3=1,gemm_ln_fast=0 (isf_set_option)
+        for item in os.environ.get('ISF_OPTS', '').split(','):        # e.g. ISF_OPTS=gemm_v4=1,gemm_ln_fast=0 (isf_set_option)
             if '=' in item:
                 name, value = item.split('=')
                 if _lib.isf_set_option(name.strip().encode(), int(value)) != 0:

@@ -28,8 +28,8 @@ extern "C" unsigned long long isf_launch_count(int reset) {
 int g_isf_gemm_cluster = 1;
 int g_isf_tile_order_drop_bits = 0;
 int g_isf_nbr_rows = 1;
-int g_isf_gemm_mt = 1;
-int g_isf_gemm_v3 = 0;
+int g_isf_gemm_mt = 3;
+int g_isf_gemm_v4 = 0;
 int g_isf_gemm_ln_fast = 1;
 int g_isf_gemm_debug = 0;
 extern "C" int isf_set_option(const char* name, int value) {
@@ -49,8 +49,8 @@ extern "C" int isf_set_option(const char* name, int value) {
     g_isf_gemm_ln_fast = value;
     return ISF_OK;
   }
-  if (name && strcmp(name, "gemm_v3") == 0 && (value == 0 || value == 1)) {
-    g_isf_gemm_v3 = value;
+  if (name && strcmp(name, "gemm_v4") == 0 && value >= 0 && value <= 2) {
+    g_isf_gemm_v4 = value;
     return ISF_OK;
   }
   if (name && strcmp(name, "gemm_debug") == 0 && value >= 0 && value <= 7) {

@@ -263,8 +263,8 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float y = __uint_as_float(v[j]);
-    if (p.scale) y *= p.scale[n_base + j];
-    if (p.shift) y += p.shift[n_base + j];
+    if (p.scale) y = __fmul_rn(y, p.scale[n_base + j]);      // explicit roundings: every epilogue variant of the library
+    if (p.shift) y = __fadd_rn(y, p.shift[n_base + j]);      // (fast / LayerNorm / v3) produces the same bits
     x[j] = y;
   }
   if (p.residual && rrow >= 0) {
@@ -518,7 +518,12 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
           const float* vs = vec + half * HC + cb;
           const float* vh = vec + BN + half * HC + cb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[cb + j] = __uint_as_float(v[j]) * vs[j] + vh[j];
+          for (int j = 0; j < 32; ++j) {
+            float y = __uint_as_float(v[j]);
+            if (p.scale) y = __fmul_rn(y, vs[j]);
+            if (p.shift) y = __fadd_rn(y, vh[j]);
+            x[cb + j] = y;
+          }
           if (p.residual && rrow >= 0) {
             const uint4* rp = (const uint4*)(p.residual + rrow * p.ldr + n0 + half * HC + cb);
 #pragma unroll
@@ -616,16 +621,16 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float y = __uint_as_float(v[j]);
-              if (p.scale) y *= vs[j];
-              if (p.shift) y += vs[BN + j];
+              if (p.scale) y = __fmul_rn(y, vs[j]);
+              if (p.shift) y = __fadd_rn(y, vs[BN + j]);
               x[j] = y;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float y = __uint_as_float(v[j]);
-              if (p.scale) y *= p.scale[n0 + cb + j];
-              if (p.shift) y += p.shift[n0 + cb + j];
+              if (p.scale) y = __fmul_rn(y, p.scale[n0 + cb + j]);
+              if (p.shift) y = __fadd_rn(y, p.shift[n0 + cb + j]);
               x[j] = y;
             }
           }
@@ -878,8 +883,8 @@ static inline int dispatch_gemm_mt2(const GemmParams& p, int bn, int m_upper, cu
   }
 }
 
-static inline bool spconv3_supported(const GemmParams& p, int bn);                               // tc_spconv.cuh
-static inline int dispatch_spconv3(const GemmParams& p, int bn, int m_upper, cudaStream_t st);
+static inline bool gemm4_supported(const GemmParams& p, int bn);                               // tc_gemm4.cuh
+static inline int dispatch_gemm4(const GemmParams& p, int bn, int m_upper, cudaStream_t st);
 
 static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaStream_t st) {
   if (p0.taps > MAX_TAPS || p0.kpad / BK > MAX_CHUNKS) {
@@ -896,10 +901,14 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
       default: break;
     }
   }
-  if (::g_isf_gemm_v3 && spconv3_supported(p, bn) && m_upper >= 4 * BM) return dispatch_spconv3(p, bn, m_upper, st);
-  // 256-row CTA tiles: measured faster for the 32-column (-22 %) and 256-column (-7 %) layers, slower for 64 / 128 (round 2)
+  // dedicated epilogue warps + double-buffered accumulator (tc_gemm4.cuh): 1 = sparse-conv launches, 2 = dense GEMMs too
+  if (::g_isf_gemm_v4 && gemm4_supported(p, bn) && m_upper >= 8 * BM && (p.nbr != nullptr || ::g_isf_gemm_v4 == 2))
+    return dispatch_gemm4(p, bn, m_upper, st);
+  // 256-row CTA tiles (one weight chunk per 256 rows): measured -5..-7 % on the 256-column layers of stage 4 (round 2, with the
+  // pipelined epilogue), neutral or slower elsewhere and slower below two waves of tiles -> the default (3) takes them only there
   if (p.nbr != nullptr && m_upper >= 148 * 256 &&
-      (::g_isf_gemm_mt == 2 || (::g_isf_gemm_mt == 3 && (bn == 32 || bn == 256)))) return dispatch_gemm_mt2(p, bn, m_upper, st);
+      (::g_isf_gemm_mt == 2 || (::g_isf_gemm_mt == 3 && bn == 256 && m_upper >= 2 * 148 * 256)))
+    return dispatch_gemm_mt2(p, bn, m_upper, st);
   switch (::g_isf_gemm_cluster) {
     case 2: return dispatch_gemm_cs<2>(p, bn, m_upper, st);
     default: break;
@@ -911,4 +920,4 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
 
 }  // namespace tc
 
-#include "tc_spconv.cuh"
+#include "tc_gemm4.cuh"

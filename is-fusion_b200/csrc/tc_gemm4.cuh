@@ -1,0 +1,345 @@
+// tcgen05 implicit GEMM, schedule "v4": the producers of tc::gemm_kernel (tc_gemm.cuh) with the epilogue on its own warps and a
+// DOUBLE-BUFFERED TMEM accumulator.  Same contract, same arithmetic order, same bits as tc::gemm_kernel (no LayerNorm).
+//
+// Why (round-2 source-level ncu of the stage-3 launch, profiles/ncu_gemm_r02.md): ~21 % of the warp-stall samples sat in the
+// epilogue (its global loads), ~11 % at the __syncthreads that separates the epilogue of tile t from the main loop of tile
+// t+1, and the tensor pipe idles while the eight producer warps — which are also the epilogue warps — drain a tile.  Here
+//   warps 0-7    producers: tile prologue (neighbour tile -> shared memory, active-chunk list) and the A gathers (16-byte
+//                cp.async into the 128B-swizzled UMMA layout, hardware-signalled full barrier), weight chunk by TMA;
+//                they start tile t+1 as soon as their last chunk of tile t is issued;
+//   warp  8      MMA issuer: tcgen05.mma into accumulator (t & 1), tcgen05.commit frees smem stages / publishes the accumulator;
+//   warps 9-12   epilogue: accumulator (t & 1) -> BN fold, residual, activation -> global, row maps and the first residual
+//                block fetched before the accumulator is complete.
+// The CTA-wide barrier per tile is gone; the only CTA-wide synchronisation is at start-up and tear-down.  Two CTAs per SM for
+// column tiles <= 128 (2 x 2 x 128 TMEM columns), one for 256.  A failed TMA-gather variant of this skeleton ("v3",
+// tile::gather4 for the A rows) is documented in DESIGN.md 3.1: the TMA serves ~1 gather4 per 40-85 cycles per SM.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace tc {
+
+constexpr int V4_MMA_WARP = 8;
+constexpr int V4_EPI_WARP0 = 9;
+constexpr int V4_THREADS = 13 * 32;
+
+template <int BN, int STAGES>
+struct Smem4 {
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NBR_OFF = STAGES * STAGE_BYTES;                  // [MAX_TAPS][128] byte offsets of the neighbour rows
+  static constexpr int LIST_OFF = NBR_OFF + MAX_TAPS * BM * 4;          // active chunk list (uint16)
+  static constexpr int FLAG_OFF = LIST_OFF + MAX_CHUNKS * 2;            // 32 tap flags + count, + n_act slots of the two buffers
+  static constexpr int VEC_OFF = FLAG_OFF + 64 * 4;                     // scale[BN] | shift[BN] fp32
+  static constexpr int BAR_OFF = VEC_OFF + 2 * BN * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 8;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES, int CTAS>
+__global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
+  using SL = Smem4<BN, STAGES>;
+  constexpr int ACC_COLS = 2 * BN;
+  static_assert(ACC_COLS * CTAS <= 512, "TMEM holds 512 columns per SM");
+  constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+  constexpr int NVR = (MAX_TAPS + 1) / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = (uint64_t*)(smem + SL::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint64_t* list_full = acc_empty + 2;         // [2]  n_act slot of the buffer is valid
+  uint64_t* list_empty = list_full + 2;        // [2]  the MMA warp has read it
+  uint32_t* tmem_slot = (uint32_t*)(list_empty + 2);
+  int* nbr_s = (int*)(smem + SL::NBR_OFF);
+  uint16_t* chunk_list = (uint16_t*)(smem + SL::LIST_OFF);
+  int* tap_flag = (int*)(smem + SL::FLAG_OFF);             // [0,32) flags, [32] count (producers), [40 + buf] n_act slot (MMA warp)
+  float* vec = (float*)(smem + SL::VEC_OFF);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_total = p.m_dev ? *p.m_dev : p.m;
+  const int num_tiles = (m_total + BM - 1) / BM;
+  const int n0 = blockIdx.y * BN;
+  const int num_chunks = p.kpad / BK;
+  const bool gather = p.nbr != nullptr;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 128);
+      mbar_init(&list_full[b], 1);
+      mbar_init(&list_empty[b], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == V4_MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int c = tid; c < BN; c += V4_THREADS) {
+    vec[c] = p.scale ? p.scale[n0 + c] : 1.f;
+    vec[BN + c] = p.shift ? p.shift[n0 + c] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < PWARPS) {
+    // ================================================================ producers
+    const int r = tid & (BM - 1);
+    const int thalf = tid >> 7;
+    const int pc = tid & 7;
+    const int rbase = tid >> 3;
+    const uint32_t a_thr_off = (uint32_t)(rbase * 128 + ((pc ^ (rbase & 7)) << 4));
+    const char* a_bytes = (const char*)p.A;
+    uint32_t ca = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ubuf = (uint32_t)(it >> 1);
+      const int row0 = tile * BM;
+      // every producer warp has issued its last chunk of the previous tile: the neighbour tile / chunk list can be replaced
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (gather) {
+        const long long prow = (long long)row0 + r;
+        const bool pok = prow < m_total;
+        int nv[NVR];
+#pragma unroll
+        for (int u = 0; u < NVR; ++u) {
+          const int t = thalf + 2 * u;
+          nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
+        }
+        if (tid < 33) tap_flag[tid] = 0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < NVR; ++u) {
+          const int t = thalf + 2 * u;
+          if (t < p.taps) {
+            nbr_s[t * BM + r] = nv[u] >= 0 ? (int)((unsigned)nv[u] * (unsigned)(p.cin * 2)) : -1;
+            if (nv[u] >= 0) tap_flag[t] = 1;
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (warp == 0) {
+        int count = 0;
+        for (int base = 0; base < num_chunks; base += 32) {
+          const int q = base + lane;
+          bool act = q < num_chunks;
+          if (act && gather) {
+            const int t0 = (q * BK) / p.cin, t1 = (q * BK + BK - 1) / p.cin;
+            bool any = false;
+            for (int t = t0; t <= t1 && t < p.taps; ++t) any |= tap_flag[t] != 0;
+            act = any;
+          }
+          const unsigned mask = __ballot_sync(0xffffffffu, act);
+          if (act) chunk_list[count + __popc(mask & ((1u << lane) - 1))] = (uint16_t)q;
+          count += __popc(mask);
+        }
+        if (count == 0) { if (lane == 0) chunk_list[0] = 0; count = 1; }   // keeps the accumulator defined
+        if (ubuf > 0) mbar_wait_b(&list_empty[buf], (ubuf - 1) & 1);       // the MMA warp has read this slot's previous value
+        if (lane == 0) { tap_flag[32] = count; tap_flag[40 + buf] = count; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&list_full[buf]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int n_act = tap_flag[32];
+      unsigned offs[4];
+      int offs_tap = -1;
+      for (int i = 0; i < n_act; ++i, ++ca) {
+        const int q = chunk_list[i];
+        const int s = (int)(ca % STAGES);
+        const uint32_t use = ca / STAGES;
+        if (use > 0) mbar_wait_b(&empty_bar[s], (use - 1) & 1);
+        const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
+        if (tid == 0) {
+          mbar_expect_tx(&full_bar[s], BN * 128);
+          tma_load_2d(sa + SL::A_BYTES, &tmap_w, q * BK, n0, &full_bar[s]);
+        }
+        const int k = q * BK + pc * 8;
+        int tap, ch;
+        if (p.taps == 1) { tap = k >= p.cin ? 1 : 0; ch = k; } else { tap = k >> p.cin_shift; ch = k & (p.cin - 1); }
+        const bool tap_ok = tap < p.taps;
+        const char* src_ch = a_bytes + ch * 2;
+        if (tap != offs_tap) {
+          offs_tap = tap;
+          const int* nrow = nbr_s + tap * BM + rbase;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            unsigned off = 0xFFFFFFFFu;
+            if (tap_ok) {
+              if (gather) off = (unsigned)nrow[32 * j];
+              else { const int gr = row0 + rbase + 32 * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
+            }
+            offs[j] = off;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = offs[j] != 0xFFFFFFFFu;
+          cp_async16(sa + a_thr_off + j * 32 * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive(&full_bar[s]);
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == V4_MMA_WARP) {
+    // ================================================================ MMA issuer
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    uint32_t ca = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ubuf = (uint32_t)(it >> 1);
+      mbar_wait_b(&list_full[buf], ubuf & 1);
+      const int n_act = ((const volatile int*)tap_flag)[40 + buf];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&list_empty[buf]);
+      if (ubuf > 0) mbar_wait_b(&acc_empty[buf], (ubuf - 1) & 1);      // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      for (int q = 0; q < n_act; ++q, ++ca) {
+        const int s = (int)(ca % STAGES);
+        mbar_wait_b(&full_bar[s], (ca / STAGES) & 1);
+        fence_proxy_async();     // cp.async (generic proxy) writes of the producers -> visible to the tensor core
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
+          const uint64_t a_desc = make_desc_sw128(a_addr);
+          const uint64_t b_desc = make_desc_sw128(a_addr + SL::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_f16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (q == n_act - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 9-12; TMEM lane quarter = warp % 4)
+    const int r = (warp & 3) * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ubuf = (uint32_t)(it >> 1);
+      const int grow = tile * BM + r;
+      const bool row_ok = grow < m_total;
+      long long orow = grow;
+      if (p.out_rows && row_ok) orow = p.out_rows[grow];
+      long long rrow = row_ok ? (long long)grow : -1;
+      if (p.res_rows && row_ok) rrow = p.res_rows[grow];
+      const bool store_ok = row_ok && orow >= 0;
+      const bool has_res = p.residual != nullptr && rrow >= 0;
+      const uint4* rp = has_res ? (const uint4*)(p.residual + rrow * p.ldr + n0) : nullptr;
+      uint4 rnext[2];
+      if (has_res) { rnext[0] = rp[0]; rnext[1] = rp[1]; }
+      mbar_wait_b(&acc_full[buf], ubuf & 1);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 16) {
+        uint4 rcur[2];
+        if (has_res) {
+          rcur[0] = rnext[0]; rcur[1] = rnext[1];
+          if (cb + 16 < BN) { rnext[0] = rp[(cb + 16) / 8]; rnext[1] = rp[(cb + 16) / 8 + 1]; }
+        }
+        uint32_t v[16];
+        tmem_ld16(t_lane + cb, v);
+        tmem_ld_wait();
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float y = __uint_as_float(v[j]);
+          if (p.scale) y = __fmul_rn(y, vec[cb + j]);
+          if (p.shift) y = __fadd_rn(y, vec[BN + cb + j]);
+          x[j] = y;
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            const __half2* h = (const __half2*)&rcur[j4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h[e]);
+              x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+        } else if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = gelu_erf(x[j]);
+        }
+        if (store_ok) {
+          if (p.out) {
+            uint4* op = (uint4*)(p.out + orow * p.ldo + n0 + cb);
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              uint4 u;
+              __half2* h = (__half2*)&u;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+              op[j4] = u;
+            }
+          }
+          if (p.out_f32) {
+            float4* op = (float4*)(p.out_f32 + orow * p.ldo + n0 + cb);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) op[j4] = make_float4(x[j4 * 4], x[j4 * 4 + 1], x[j4 * 4 + 2], x[j4 * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == V4_MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int STAGES, int CTAS>
+static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
+  using SL = Smem4<BN, STAGES>;
+  static_assert((SL::TOTAL + 1024) * CTAS <= 227 * 1024, "v4 GEMM: shared memory budget exceeded");
+  auto kern = gemm4_kernel<BN, STAGES, CTAS>;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { isf_set_error("gemm v4: bad device"); return ISF_ERR_CUDA; }
+  static bool configured[64] = {};
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL);
+    if (e != cudaSuccess) { isf_set_error("cudaFuncSetAttribute (v4): %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
+    configured[dev] = true;
+  }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  int rc = make_weight_tmap(&tm, p.W, p.n_total, p.kpad, BN);
+  if (rc) return rc;
+  int tiles = (m_upper + BM - 1) / BM;
+  if (tiles < 1) tiles = 1;
+  const int n_tiles = p.n_total / BN;
+  int gx = isf_num_sms() * CTAS / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > tiles) gx = tiles;
+  kern<<<dim3(gx, n_tiles), V4_THREADS, SL::TOTAL, st>>>(p, tm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { isf_set_error("gemm v4 launch: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }
+  return ISF_OK;
+}
+
+static inline bool gemm4_supported(const GemmParams& p, int bn) { return p.ln_gamma == nullptr && bn >= 64; }
+
+static inline int dispatch_gemm4(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_gemm4<64, 4, 2>(p, m_upper, st);        // 4 x 24 KB, 2 x 128 TMEM columns per CTA
+    case 128: return launch_gemm4<128, 3, 2>(p, m_upper, st);      // 3 x 32 KB
+    case 256: return launch_gemm4<256, 4, 1>(p, m_upper, st);      // 4 x 48 KB, all 512 TMEM columns
+    default: isf_set_error("gemm v4: unsupported column tile %d", bn); return ISF_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace tc

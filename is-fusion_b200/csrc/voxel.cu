@@ -896,10 +896,17 @@ extern "C" int isf_dynamic_vfe_forward(const float* points, const int* coors, in
   if (rc) return rc;
   VfeParams P{voxel_size[0], voxel_size[1], voxel_size[2], offsets[0], offsets[1], offsets[2]};
   // persistent warps: exactly one resident wave (a partial second wave would double the kernel time)
-  static int occ = 0;
-  if (!occ) {
-    ISF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfe_fused_kernel, VFE_WARPS * 32, 0));
-    if (occ < 1) occ = 1;
+  int occ = 0;
+  {   // occupancy is per-device state
+    static int occ_dev[64] = {};
+    int dev = 0;
+    ISF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!occ_dev[dev]) {
+      ISF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[dev], vfe_fused_kernel, VFE_WARPS * 32, 0));
+      if (occ_dev[dev] < 1) occ_dev[dev] = 1;
+    }
+    occ = occ_dev[dev];
   }
   int blocks = isf_cdiv(n, VFE_WARPS);
   if (blocks > ISF_NUM_SMS * occ) blocks = ISF_NUM_SMS * occ;
@@ -965,10 +972,17 @@ extern "C" int isf_dynamic_vfe_compute(const float* points, int n, int nfeat, co
   if (!A.ok) { isf_set_error("dynamic_vfe_compute: workspace too small"); return ISF_ERR_WORKSPACE; }
   KeyLayout L = make_layout(4, dims);
   VfeParams P{voxel_size[0], voxel_size[1], voxel_size[2], offsets[0], offsets[1], offsets[2]};
-  static int occ = 0;
-  if (!occ) {
-    ISF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vfe_fused_kernel, VFE_WARPS * 32, 0));
-    if (occ < 1) occ = 1;
+  int occ = 0;
+  {   // occupancy is per-device state
+    static int occ_dev[64] = {};
+    int dev = 0;
+    ISF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!occ_dev[dev]) {
+      ISF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[dev], vfe_fused_kernel, VFE_WARPS * 32, 0));
+      if (occ_dev[dev] < 1) occ_dev[dev] = 1;
+    }
+    occ = occ_dev[dev];
   }
   int blocks = isf_cdiv(n, VFE_WARPS);
   if (blocks > ISF_NUM_SMS * occ) blocks = ISF_NUM_SMS * occ;

@@ -281,6 +281,10 @@ class GraphedNeck:
             self.net.__dict__['_side_streams'] = saved
         self.watch = list(self._spmod.OVERFLOW_WATCH)
         self._spmod.OVERFLOW_WATCH.clear()
+        # the graph bakes the device pointers of every packed / folded weight tensor (and TMA descriptors built from them):
+        # keep those cache objects alive for the life of the graph, so that a later net.eval() / load_state_dict(), which drops
+        # the module-side caches, cannot hand their memory back to the allocator under a replay
+        self._keepalive = [m.__dict__[k] for m in self.net.modules() for k in ('_pk', '_packed') if m.__dict__.get(k) is not None]
         return self
 
     def __call__(self, points=None, img_feat1=None):

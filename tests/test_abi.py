@@ -78,7 +78,7 @@ def test_new_host_side_entry_points_validate_arguments():
     for name, good, bad in (('tile_order_drop_bits', 11, 27), ('nbr_rows', 1, 2), ('gemm_mt', 3, 4), ('gemm_debug', 0, 8)):
         assert lib.isf_set_option(name.encode(), good) == 0, name
         assert lib.isf_set_option(name.encode(), bad) == 1 and b'unknown option or bad value' in lib.isf_last_error(), name
-    for name, default in (('tile_order_drop_bits', 0), ('nbr_rows', 1), ('gemm_mt', 1), ('gemm_debug', 0)):
+    for name, default in (('tile_order_drop_bits', 0), ('nbr_rows', 1), ('gemm_mt', 3), ('gemm_debug', 0)):
         assert lib.isf_set_option(name.encode(), default) == 0
     assert lib.isf_set_option(b'no_such_option', 1) == 1
     # the tile-order entry points refuse bad geometry before touching the device

@@ -208,9 +208,9 @@ def test_capacity_overflow_drops_sites_from_the_coordinate_map_too():
 
 
 @pytest.mark.parametrize('order', [None, 31])
-def test_sparse_encoder_tma_gather_schedule_bit_identical(order):
-    """isf_set_option("gemm_v3", 1): the TMA tile::gather4 schedule of the implicit GEMM (csrc/tc_spconv.cuh; 256-row CTA
-    tiles, double-buffered TMEM) accumulates every output row over the same chunks in the same order -> same bits."""
+def test_sparse_encoder_v4_schedule_bit_identical(order):
+    """isf_set_option("gemm_v4", 1): dedicated epilogue warps + double-buffered TMEM accumulator (csrc/tc_gemm4.cuh): every
+    output row is accumulated over the same chunks in the same order and goes through the same epilogue arithmetic -> same bits."""
     from isfusion_b200 import _lib as L
     from isfusion_b200.sparse_encoder import SparseEncoder
     import isfusion_b200.spconv as sp
@@ -225,12 +225,12 @@ def test_sparse_encoder_tma_gather_schedule_bit_identical(order):
     old = sp.TILE_ORDER
     try:
         sp.TILE_ORDER = order
-        L.set_option('gemm_v3', 0)
+        L.set_option('gemm_v4', 0)
         ref, _, _ = mod(f, c, 2)
-        L.set_option('gemm_v3', 1)
+        L.set_option('gemm_v4', 1)
         out, _, _ = mod(f, c, 2)
         torch.cuda.synchronize()
         assert torch.equal(out, ref)
     finally:
-        L.set_option('gemm_v3', 0)
+        L.set_option('gemm_v4', 0)
         sp.TILE_ORDER = old

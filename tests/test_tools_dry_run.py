@@ -104,7 +104,7 @@ def test_bench_gemm_layers_dry_run(monkeypatch, capsys):
     out = capsys.readouterr().out
     assert out.count('bit-identical to the first variant') == 3 and 'DIFFERS' not in out       # storage, ord16, gemm_mt=2
     assert 'total ms:' in out and sp.TILE_ORDER == 31
-    assert L.lib().isf_set_option(b'gemm_mt', 1) == 0
+    assert L.lib().isf_set_option(b'gemm_mt', 3) == 0
 
 
 def test_bench_hsf_dry_run(monkeypatch, capsys):
