@@ -29,7 +29,7 @@ int g_isf_gemm_cluster = 1;
 int g_isf_tile_order_drop_bits = 0;
 int g_isf_nbr_rows = 1;
 int g_isf_gemm_mt = 3;
-int g_isf_gemm_v4 = 0;
+int g_isf_gemm_v4 = 2;
 int g_isf_gemm_ln_fast = 1;
 int g_isf_gemm_debug = 0;
 extern "C" int isf_set_option(const char* name, int value) {

@@ -22,13 +22,14 @@ constexpr int V4_MMA_WARP = 8;
 constexpr int V4_EPI_WARP0 = 9;
 constexpr int V4_THREADS = 13 * 32;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT = 1>
 struct Smem4 {
-  static constexpr int A_BYTES = BM * 128;
+  static constexpr int TILE_M = MT * BM;
+  static constexpr int A_BYTES = TILE_M * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NBR_OFF = STAGES * STAGE_BYTES;                  // [MAX_TAPS][128] byte offsets of the neighbour rows
-  static constexpr int LIST_OFF = NBR_OFF + MAX_TAPS * BM * 4;          // active chunk list (uint16)
+  static constexpr int LIST_OFF = NBR_OFF + MAX_TAPS * TILE_M * 4;      // active chunk list (uint16)
   static constexpr int FLAG_OFF = LIST_OFF + MAX_CHUNKS * 2;            // 32 tap flags + count, + n_act slots of the two buffers
   static constexpr int VEC_OFF = FLAG_OFF + 64 * 4;                     // scale[BN] | shift[BN] fp32
   static constexpr int BAR_OFF = VEC_OFF + 2 * BN * 4;
@@ -36,13 +37,17 @@ struct Smem4 {
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int BN, int STAGES, int CTAS>
+// MT = 128-row sub-tiles per CTA tile: with MT = 2 one weight chunk feeds 256 output rows (half the weight bytes per FLOP from L2)
+template <int BN, int STAGES, int CTAS, int MT>
 __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
-  using SL = Smem4<BN, STAGES>;
-  constexpr int ACC_COLS = 2 * BN;
+  using SL = Smem4<BN, STAGES, MT>;
+  constexpr int TILE_M = SL::TILE_M;
+  constexpr int TSPLIT = PRODUCERS / TILE_M;          // thread groups that split the kernel offsets in the tile prologue
+  constexpr int RPT = TILE_M * 8 / PRODUCERS;         // A rows per producer thread and chunk
+  constexpr int ACC_COLS = 2 * MT * BN;
   static_assert(ACC_COLS * CTAS <= 512, "TMEM holds 512 columns per SM");
   constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
-  constexpr int NVR = (MAX_TAPS + 1) / 2;
+  constexpr int NVR = (MAX_TAPS + TSPLIT - 1) / TSPLIT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = (uint64_t*)(smem + SL::BAR_OFF);
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_total = p.m_dev ? *p.m_dev : p.m;
-  const int num_tiles = (m_total + BM - 1) / BM;
+  const int num_tiles = (m_total + TILE_M - 1) / TILE_M;
   const int n0 = blockIdx.y * BN;
   const int num_chunks = p.kpad / BK;
   const bool gather = p.nbr != nullptr;
@@ -86,8 +91,8 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
 
   if (warp < PWARPS) {
     // ================================================================ producers
-    const int r = tid & (BM - 1);
-    const int thalf = tid >> 7;
+    const int r = tid % TILE_M;
+    const int thalf = tid / TILE_M;
     const int pc = tid & 7;
     const int rbase = tid >> 3;
     const uint32_t a_thr_off = (uint32_t)(rbase * 128 + ((pc ^ (rbase & 7)) << 4));
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
-      const int row0 = tile * BM;
+      const int row0 = tile * TILE_M;
       // every producer warp has issued its last chunk of the previous tile: the neighbour tile / chunk list can be replaced
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (gather) {
@@ -106,16 +111,16 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
         int nv[NVR];
 #pragma unroll
         for (int u = 0; u < NVR; ++u) {
-          const int t = thalf + 2 * u;
+          const int t = thalf + TSPLIT * u;
           nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
         }
         if (tid < 33) tap_flag[tid] = 0;
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
         for (int u = 0; u < NVR; ++u) {
-          const int t = thalf + 2 * u;
+          const int t = thalf + TSPLIT * u;
           if (t < p.taps) {
-            nbr_s[t * BM + r] = nv[u] >= 0 ? (int)((unsigned)nv[u] * (unsigned)(p.cin * 2)) : -1;
+            nbr_s[t * TILE_M + r] = nv[u] >= 0 ? (int)((unsigned)nv[u] * (unsigned)(p.cin * 2)) : -1;
             if (nv[u] >= 0) tap_flag[t] = 1;
           }
         }
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int n_act = tap_flag[32];
-      unsigned offs[4];
+      unsigned offs[RPT];
       int offs_tap = -1;
       for (int i = 0; i < n_act; ++i, ++ca) {
         const int q = chunk_list[i];
@@ -153,8 +158,11 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
         if (use > 0) mbar_wait_b(&empty_bar[s], (use - 1) & 1);
         const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
         if (tid == 0) {
-          mbar_expect_tx(&full_bar[s], BN * 128);
-          tma_load_2d(sa + SL::A_BYTES, &tmap_w, q * BK, n0, &full_bar[s]);
+          if ((p.debug & 1) && i > 0) mbar_arrive(&full_bar[s]);      // timing experiment: weight chunk only once per tile
+          else {
+            mbar_expect_tx(&full_bar[s], BN * 128);
+            tma_load_2d(sa + SL::A_BYTES, &tmap_w, q * BK, n0, &full_bar[s]);
+          }
         }
         const int k = q * BK + pc * 8;
         int tap, ch;
@@ -163,9 +171,9 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
         const char* src_ch = a_bytes + ch * 2;
         if (tap != offs_tap) {
           offs_tap = tap;
-          const int* nrow = nbr_s + tap * BM + rbase;
+          const int* nrow = nbr_s + tap * TILE_M + rbase;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RPT; ++j) {
             unsigned off = 0xFFFFFFFFu;
             if (tap_ok) {
               if (gather) off = (unsigned)nrow[32 * j];
@@ -174,8 +182,9 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
             offs[j] = off;
           }
         }
+        if (!(p.debug & 4))
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < RPT; ++j) {
           const bool ok = offs[j] != 0xFFFFFFFFu;
           cp_async16(sa + a_thr_off + j * 32 * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
         }
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       if (lane == 0) mbar_arrive(&list_empty[buf]);
       if (ubuf > 0) mbar_wait_b(&acc_empty[buf], (ubuf - 1) & 1);      // the epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * MT * BN);
       for (int q = 0; q < n_act; ++q, ++ca) {
         const int s = (int)(ca % STAGES);
         mbar_wait_b(&full_bar[s], (ca / STAGES) & 1);
@@ -205,11 +214,14 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
-          const uint64_t a_desc = make_desc_sw128(a_addr);
           const uint64_t b_desc = make_desc_sw128(a_addr + SL::A_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)
-            umma_f16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t a_desc = make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128));
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_f16(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[s]);
           if (q == n_act - 1) umma_commit(&acc_full[buf]);
         }
@@ -223,7 +235,9 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
-      const int grow = tile * BM + r;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int grow = tile * TILE_M + mt * BM + r;
       const bool row_ok = grow < m_total;
       long long orow = grow;
       if (p.out_rows && row_ok) orow = p.out_rows[grow];
@@ -234,9 +248,11 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       const uint4* rp = has_res ? (const uint4*)(p.residual + rrow * p.ldr + n0) : nullptr;
       uint4 rnext[2];
       if (has_res) { rnext[0] = rp[0]; rnext[1] = rp[1]; }
-      mbar_wait_b(&acc_full[buf], ubuf & 1);
-      tc_fence_after();
-      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(buf * BN);
+      if (mt == 0) {
+        mbar_wait_b(&acc_full[buf], ubuf & 1);
+        tc_fence_after();
+      }
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((buf * MT + mt) * BN);
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 16) {
         uint4 rcur[2];
@@ -292,6 +308,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
           }
         }
       }
+      }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
     }
@@ -302,11 +319,11 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
   if (warp == V4_MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int BN, int STAGES, int CTAS>
+template <int BN, int STAGES, int CTAS, int MT = 1>
 static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
-  using SL = Smem4<BN, STAGES>;
+  using SL = Smem4<BN, STAGES, MT>;
   static_assert((SL::TOTAL + 1024) * CTAS <= 227 * 1024, "v4 GEMM: shared memory budget exceeded");
-  auto kern = gemm4_kernel<BN, STAGES, CTAS>;
+  auto kern = gemm4_kernel<BN, STAGES, CTAS, MT>;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { isf_set_error("gemm v4: bad device"); return ISF_ERR_CUDA; }
   static bool configured[64] = {};
@@ -319,7 +336,7 @@ static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
   memset(&tm, 0, sizeof(tm));
   int rc = make_weight_tmap(&tm, p.W, p.n_total, p.kpad, BN);
   if (rc) return rc;
-  int tiles = (m_upper + BM - 1) / BM;
+  int tiles = (m_upper + SL::TILE_M - 1) / SL::TILE_M;
   if (tiles < 1) tiles = 1;
   const int n_tiles = p.n_total / BN;
   int gx = isf_num_sms() * CTAS / n_tiles;
@@ -334,6 +351,13 @@ static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
 static inline bool gemm4_supported(const GemmParams& p, int bn) { return p.ln_gamma == nullptr && bn >= 64; }
 
 static inline int dispatch_gemm4(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  if (::g_isf_gemm_mt == 2 && p.nbr != nullptr && m_upper >= 2 * 148 * 256) {      // 256-row tiles (experiment: isf_set_option("gemm_mt", 2))
+    switch (bn) {
+      case 64: return launch_gemm4<64, 2, 2, 2>(p, m_upper, st);      // 2 x 40 KB + 27 KB, 2 CTAs / SM
+      case 128: return launch_gemm4<128, 4, 1, 2>(p, m_upper, st);    // 4 x 48 KB + 27 KB, all 512 TMEM columns
+      default: break;
+    }
+  }
   switch (bn) {
     case 64: return launch_gemm4<64, 4, 2>(p, m_upper, st);        // 4 x 24 KB, 2 x 128 TMEM columns per CTA
     case 128: return launch_gemm4<128, 3, 2>(p, m_upper, st);      // 3 x 32 KB

@@ -227,10 +227,13 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
         sp.TILE_ORDER = order
         L.set_option('gemm_v4', 0)
         ref, _, _ = mod(f, c, 2)
-        L.set_option('gemm_v4', 1)
+        L.set_option('gemm_v4', 2)
         out, _, _ = mod(f, c, 2)
+        L.set_option('gemm_mt', 2)               # 256-row CTA tiles of the same schedule
+        out2, _, _ = mod(f, c, 2)
         torch.cuda.synchronize()
-        assert torch.equal(out, ref)
+        assert torch.equal(out, ref) and torch.equal(out2, ref)
     finally:
-        L.set_option('gemm_v4', 0)
+        L.set_option('gemm_v4', 2)
+        L.set_option('gemm_mt', 3)
         sp.TILE_ORDER = old
