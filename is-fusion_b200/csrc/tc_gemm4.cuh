@@ -351,12 +351,11 @@ static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
 static inline bool gemm4_supported(const GemmParams& p, int bn) { return p.ln_gamma == nullptr && bn >= 64; }
 
 static inline int dispatch_gemm4(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
-  if (::g_isf_gemm_mt == 2 && p.nbr != nullptr && m_upper >= 2 * 148 * 256) {      // 256-row tiles (experiment: isf_set_option("gemm_mt", 2))
-    switch (bn) {
-      case 64: return launch_gemm4<64, 2, 2, 2>(p, m_upper, st);      // 2 x 40 KB + 27 KB, 2 CTAs / SM
-      case 128: return launch_gemm4<128, 4, 1, 2>(p, m_upper, st);    // 4 x 48 KB + 27 KB, all 512 TMEM columns
-      default: break;
-    }
+  // 256-row tiles (one weight chunk per 256 rows): measured on v4 (round 2, call 8) -8 % on the 64-column layers, +7 % on the
+  // 128-column ones -> default (gemm_mt = 3) only for 64 columns; gemm_mt = 2 forces them for 128 as well, 1 disables them
+  if (p.nbr != nullptr && m_upper >= 2 * 148 * 256 && ::g_isf_gemm_mt >= 2) {
+    if (bn == 64) return launch_gemm4<64, 2, 2, 2>(p, m_upper, st);                              // 2 x 40 KB + 27 KB, 2 CTAs / SM
+    if (bn == 128 && ::g_isf_gemm_mt == 2) return launch_gemm4<128, 4, 1, 2>(p, m_upper, st);    // 4 x 48 KB + 27 KB, 512 TMEM columns
   }
   switch (bn) {
     case 64: return launch_gemm4<64, 4, 2>(p, m_upper, st);        // 4 x 24 KB, 2 x 128 TMEM columns per CTA

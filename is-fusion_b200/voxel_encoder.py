@@ -125,21 +125,49 @@ class DynamicVFE(nn.Module):
             L.ptr(None if f16 else feats), L.ptr(feats if f16 else None), L.ptr(ws), ctypes.c_size_t(ws.numel()), L.stream()))
         return feats
 
-    @torch.no_grad()
+    def forward_train(self, features, coors):
+        """TRAIN mode (batch-statistics BN, differentiable): the reference's layer-by-layer algorithm
+        (voxel_encoder.py:470-547) on the library's scatter operator — `dynamic_scatter` (forward K1-K3, backward K3b) for
+        the voxel mean and the two voxel max poolings, the point -> voxel map of that operator instead of the 663 MB
+        `map_voxel_center_to_point` canvas, `naiveSyncBN1d` (norm.py: rank-averaged moments over NCCL when world size > 1)
+        between the Linear and the ReLU.  fp32 throughout, as the reference trains it.  Gradients reach both Linear
+        weights and both BN affine pairs; the fused inference kernels are not involved."""
+        from .voxel_layer import dynamic_point_to_voxel_forward, dynamic_scatter
+        L.require_cuda(features, coors)
+        features = features.float()
+        coors = coors.contiguous()
+        with torch.no_grad():       # the points carry no gradient: voxel mean + point -> voxel map in one call
+            voxel_mean, _, p2v, _ = dynamic_point_to_voxel_forward(features[:, :3].contiguous(), coors, 'mean')
+        if bool((p2v < 0).any()):
+            raise L.IsfError('DynamicVFE.forward_train: out-of-range points must be filtered before the path (SURVEY App. C #5)')
+        idx = p2v.long()
+        f_cluster = features[:, :3] - voxel_mean[idx]
+        cf = coors.to(features.dtype)
+        f_center = torch.stack([features[:, 0] - (cf[:, 3] * self.vx + self.x_offset),
+                                features[:, 1] - (cf[:, 2] * self.vy + self.y_offset),
+                                features[:, 2] - (cf[:, 1] * self.vz + self.z_offset)], 1)
+        x = torch.cat([features, f_cluster, f_center], 1)
+        voxel_feats = voxel_coors = None
+        for i, layer in enumerate(self.vfe_layers):
+            point_feats = torch.relu(layer.norm(layer.linear(x)))
+            voxel_feats, voxel_coors = dynamic_scatter(point_feats.contiguous(), coors, 'max')
+            if i != len(self.vfe_layers) - 1:
+                x = torch.cat([point_feats, voxel_feats[idx]], 1)
+        return voxel_feats, voxel_coors
+
     def forward(self, features, coors, points=None, img_feats=None, img_metas=None, batch_size=None, nosync=False,
                 **kwargs):
         """features [N,5] fp32 points, coors [N,4] int32 (b,z,y,x), all in range ->
-        (voxel_feats [V,64], voxel_coors [V,4] int32)."""
+        (voxel_feats [V,64], voxel_coors [V,4] int32).  eval: the fused kernels (BN folded); train: `forward_train`."""
         if self.training:
-            raise L.IsfError('DynamicVFE: the fused CUDA path implements eval-mode BN only')
-        L.require_cuda(features, coors)
-        n = features.size(0)
-        dev = features.device
-        if batch_size is None:
-            batch_size = int(coors[-1, 0].item()) + 1        # same host read as isfusion.py:110
-        vcoors, nv, ws = self.group(features, coors, batch_size)
-        feats = self.compute(features, batch_size, ws)
-        if nosync:       # capacity mode: (feats [N,64], coors [N,4], device-side voxel count)
-            return feats, vcoors, nv
-        v = int(nv.item())
-        return feats[:v], vcoors[:v]
+            return self.forward_train(features, coors)
+        with torch.no_grad():
+            L.require_cuda(features, coors)
+            if batch_size is None:
+                batch_size = int(coors[-1, 0].item()) + 1        # same host read as isfusion.py:110
+            vcoors, nv, ws = self.group(features, coors, batch_size)
+            feats = self.compute(features, batch_size, ws)
+            if nosync:       # capacity mode: (feats [N,64], coors [N,4], device-side voxel count)
+                return feats, vcoors, nv
+            v = int(nv.item())
+            return feats[:v], vcoors[:v]

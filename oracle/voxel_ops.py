@@ -311,6 +311,31 @@ class DynamicVFE(nn.Module):
         return voxel_feats, voxel_coors
 
 
+def dynamic_vfe_train_forward(vfe, features, coors):
+    """DIFFERENTIABLE restatement of DynamicVFE.forward for training-parity tests (the forward above runs under no_grad
+    because the reference's scatter has no CPU autograd): same algorithm (voxel_encoder.py:470-547) with the scatters written
+    as torch index_add / scatter_reduce on the lexicographically sorted unique coordinates (= the order of `dynamic_scatter`).
+    The max-pool gradient of torch (split among ties) and of the reference (lowest-index arg-max, scatter_points_cuda.cu:105-179)
+    differ only on ties, which after the ReLU occur at 0 where the ReLU gradient is 0 anyway."""
+    features = features.float()
+    uniq, inv = torch.unique(coors, dim=0, sorted=True, return_inverse=True)
+    v = uniq.shape[0]
+    cnt = torch.zeros(v).index_add_(0, inv, torch.ones(features.shape[0]))
+    mean = torch.zeros(v, 3).index_add_(0, inv, features[:, :3]) / cnt[:, None]
+    cf = coors.float()
+    f_center = torch.stack([features[:, 0] - (cf[:, 3] * vfe.vx + vfe.x_offset), features[:, 1] - (cf[:, 2] * vfe.vy + vfe.y_offset),
+                            features[:, 2] - (cf[:, 1] * vfe.vz + vfe.z_offset)], 1)
+    x = torch.cat([features, features[:, :3] - mean[inv], f_center], 1)
+    vf = None
+    for i, layer in enumerate(vfe.vfe_layers):
+        pf = layer(x)
+        vf = torch.full((v, pf.shape[1]), float('-inf')).scatter_reduce(0, inv[:, None].expand(-1, pf.shape[1]), pf, reduce='amax',
+                                                                         include_self=True)
+        if i != len(vfe.vfe_layers) - 1:
+            x = torch.cat([pf, vf[inv]], 1)
+    return vf, uniq.to(coors.dtype)
+
+
 class Voxelization(nn.Module):
     """ref: mmdet3d/ops/voxel/voxelize.py:77-148."""
 

@@ -141,3 +141,50 @@ def test_dynamic_vfe_parity(n, batch, tensor_core):
     print('vfe tensor_core=%s: max abs err %.3e (max ref %.2f), rel l2 %.2e' % (tensor_core, err, rf.abs().max().item(), rel_l2))
     assert rel_l2 <= 1e-3, rel_l2
     assert err <= 2e-3 * max(1.0, rf.abs().max().item()), err   # 1e-3 rel (fp16 output of an fp32 pipeline)
+
+
+@pytest.mark.parametrize('own_bwd', [False, True])
+def test_dynamic_vfe_train_mode_forward_backward(own_bwd):
+    """TRAIN mode of the product DynamicVFE (batch-statistics naiveSyncBN1d, differentiable: scatter forward K1-K3 and backward
+    K3b from the library, Linear / BN / ReLU through autograd) against the oracle module trained the same way on the CPU:
+    outputs, voxel order, gradients of every parameter and the updated running statistics."""
+    import isfusion_b200.voxel_layer as VL
+    from isfusion_b200.voxel_encoder import DynamicVFE
+    ref = _make_vfe().train()
+    n = 6000
+    pts = _cloud(n, 9, margin=-0.01)
+    c3 = vo.dynamic_voxelize(pts, *MAIN)
+    coors = torch.nn.functional.pad(c3, (1, 0), value=0)
+    coors[n // 2:, 0] = 1
+    mod = DynamicVFE(5, [64, 64], False, True, True, MAIN[0], MAIN[1], dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01))
+    mod.load_state_dict(ref.state_dict())
+    mod = mod.cuda().train()
+    rf, rc = vo.dynamic_vfe_train_forward(ref, pts, coors)
+    with torch.no_grad():
+        ef, ec = ref.eval()(pts, coors)        # the differentiable restatement == the oracle's forward (eval statistics)
+    ref.train()
+    assert torch.equal(ec, rc)
+    torch.manual_seed(3)
+    wgt = torch.randn(rf.shape)
+    (rf * wgt).sum().backward()
+    old = VL.OWN_SCATTER_BACKWARD
+    try:
+        VL.OWN_SCATTER_BACKWARD = own_bwd
+        f, c = mod(pts.cuda(), coors.cuda())
+        assert f.requires_grad and f.dtype == torch.float32
+        (f * wgt.cuda()).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        VL.OWN_SCATTER_BACKWARD = old
+    assert torch.equal(c.cpu(), rc)
+    assert torch.allclose(f.detach().cpu(), rf.detach(), rtol=1e-4, atol=1e-4)
+    for (name, p), (_, q) in zip(mod.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, name
+        r = ((p.grad.cpu() - q.grad).norm() / q.grad.norm().clamp(min=1e-12)).item()
+        assert r < 1e-3, (name, r)
+    for (name, b), (_, q) in zip(mod.named_buffers(), ref.named_buffers()):
+        assert torch.allclose(b.cpu().float(), q.float(), rtol=1e-4, atol=1e-5), name
+    # eval after train still takes the fused kernels (packed weights were invalidated by train())
+    mod.eval()
+    fe, ce = mod(pts.cuda(), coors.cuda())
+    assert fe.dtype == torch.float16 and torch.equal(ce.cpu(), rc)
