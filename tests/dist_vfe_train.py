@@ -15,15 +15,30 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+class RefAllReduce(torch.autograd.Function):
+    """the reference's `AllReduce` autograd function (mmdet3d/ops/norm.py:8-24): forward = all_gather + sum, backward = all_reduce."""
+
+    @staticmethod
+    def forward(ctx, x):
+        parts = [torch.zeros_like(x) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, x.contiguous())
+        return torch.stack(parts).sum(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g)
+        return g
+
+
 class RefSyncBN1d(torch.nn.BatchNorm1d):
     """restatement of the reference's naiveSyncBN1d.forward (mmdet3d/ops/norm.py:160-202) for the checker side: per-rank
-    [mean, mean of squares], averaged over ranks with EQUAL weight through a differentiable all_gather, biased variance."""
+    [mean, mean of squares], averaged over ranks with EQUAL weight (the reference's AllReduce function), biased variance."""
 
     def forward(self, x):
-        import torch.distributed.nn.functional as dfn
         c = x.shape[1]
         vec = torch.cat([x.mean(0), (x * x).mean(0)])
-        vec = torch.stack(dfn.all_gather(vec)).sum(0) / dist.get_world_size()
+        vec = RefAllReduce.apply(vec) * (1.0 / dist.get_world_size())
         mean, meansqr = vec.split(c)
         var = meansqr - mean * mean
         with torch.no_grad():
