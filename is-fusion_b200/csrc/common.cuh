@@ -79,6 +79,7 @@ extern int g_isf_gemm_cluster;    // isf_set_option("gemm_cluster", 1|2), define
 extern int g_isf_tile_order_drop_bits;   // isf_set_option("tile_order_drop_bits", 0..26): low mask bits left out of the tile-order sort
 extern int g_isf_gemm_ln_fast;    // isf_set_option("gemm_ln_fast", 0|1): split-row LayerNorm epilogue (default 1; 0 = the round-1 two-pass epilogue)
 extern int g_isf_gemm_v4;         // isf_set_option("gemm_v4", 0|1|2): dedicated-epilogue / double-buffered schedule (tc_gemm4.cuh)
+extern int g_isf_gemm_zskip;      // isf_set_option("gemm_zskip", 0|1): zero-skip of the v4 producers
 extern int g_isf_gemm_mt;         // isf_set_option("gemm_mt", 1|2): 128-row sub-tiles per CTA tile of the sparse-conv GEMM
 extern int g_isf_gemm_debug;      // isf_set_option("gemm_debug", bits): timing experiments (tc_gemm.cuh GemmParams::debug)
 extern int g_isf_nbr_rows;        // isf_set_option("nbr_rows", 0|1): row-per-thread neighbour-table kernel (opt-in)

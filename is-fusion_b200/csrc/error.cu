@@ -29,6 +29,7 @@ int g_isf_gemm_cluster = 1;
 int g_isf_tile_order_drop_bits = 0;
 int g_isf_nbr_rows = 1;
 int g_isf_gemm_mt = 3;
+int g_isf_gemm_zskip = 0;
 int g_isf_gemm_v4 = 2;
 int g_isf_gemm_ln_fast = 1;
 int g_isf_gemm_debug = 0;
@@ -51,6 +52,10 @@ extern "C" int isf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_v4") == 0 && value >= 0 && value <= 2) {
     g_isf_gemm_v4 = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "gemm_zskip") == 0 && (value == 0 || value == 1)) {
+    g_isf_gemm_zskip = value;
     return ISF_OK;
   }
   if (name && strcmp(name, "gemm_debug") == 0 && value >= 0 && value <= 7) {

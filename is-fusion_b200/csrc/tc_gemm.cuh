@@ -210,6 +210,7 @@ struct GemmParams {
   float* out_f32;         // [m, ldo] fp32 (may be nullptr)
   int ldo;
   const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
+  int zskip;              // tc_gemm4.cuh: skip all-missing 4-row copies onto rows that already hold zeros (isf_set_option("gemm_zskip"))
   int debug;              // timing experiments only (isf_set_option("gemm_debug")): 1 = weight chunk loaded for the first chunk of a
                           // tile only, 2 = every gathered row reads row 0, 4 = no A copies at all.  Results are then meaningless.
 };
@@ -893,6 +894,7 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
   }
   GemmParams p = p0;
   p.debug = ::g_isf_gemm_debug;
+  p.zskip = ::g_isf_gemm_zskip;
   if (p.ln_gamma != nullptr && p.nbr == nullptr && ::g_isf_gemm_ln_fast) {      // LayerNorm epilogue: dense GEMMs, one column block
     switch (bn) {
       case 64: return launch_gemm<64, 2, 1, 1, true>(p, m_upper, st);

@@ -98,6 +98,24 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     const uint32_t a_thr_off = (uint32_t)(rbase * 128 + ((pc ^ (rbase & 7)) << 4));
     const char* a_bytes = (const char*)p.A;
     uint32_t ca = 0;
+    // zero-skip: one warp-level LDGSTS covers 4 rows x 128 B of a stage; when none of the 4 rows has a neighbour at the current
+    // kernel offset AND the previous use of the stage left zeros in those rows, the copy is not issued (the 64 / 128-column
+    // stages fill 40-60 % of their slots, and the LSU queue is what throttles their producers).  Bit (s * RPT + j) of zst.
+    static_assert(STAGES * RPT <= 32, "zero-skip state");
+    unsigned zst = 0;
+    const bool zskip = p.zskip != 0;
+    // neighbour ids of the tile AFTER the one being gathered live in registers: their global-load latency hides behind the
+    // gather loop instead of sitting between two tiles (where only STAGES chunks of work are queued for the tensor core)
+    int nv[NVR];
+    if (gather) {
+      const long long prow = (long long)blockIdx.x * TILE_M + r;
+      const bool pok = (int)blockIdx.x < num_tiles && prow < m_total;
+#pragma unroll
+      for (int u = 0; u < NVR; ++u) {
+        const int t = thalf + TSPLIT * u;
+        nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
+      }
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -106,14 +124,6 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       // every producer warp has issued its last chunk of the previous tile: the neighbour tile / chunk list can be replaced
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (gather) {
-        const long long prow = (long long)row0 + r;
-        const bool pok = prow < m_total;
-        int nv[NVR];
-#pragma unroll
-        for (int u = 0; u < NVR; ++u) {
-          const int t = thalf + TSPLIT * u;
-          nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
-        }
         if (tid < 33) tap_flag[tid] = 0;
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
@@ -149,6 +159,16 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int n_act = tap_flag[32];
+      if (gather) {      // prefetch the next tile's neighbour ids (consumed after this tile's gather loop)
+        const int ntile = tile + (int)gridDim.x;
+        const long long prow = (long long)ntile * TILE_M + r;
+        const bool pok = ntile < num_tiles && prow < m_total;
+#pragma unroll
+        for (int u = 0; u < NVR; ++u) {
+          const int t = thalf + TSPLIT * u;
+          nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
+        }
+      }
       unsigned offs[RPT];
       int offs_tap = -1;
       for (int i = 0; i < n_act; ++i, ++ca) {
@@ -182,9 +202,19 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
             offs[j] = off;
           }
         }
+        unsigned skip = 0;
+        if (zskip) {
+          unsigned miss = 0;
+#pragma unroll
+          for (int j = 0; j < RPT; ++j)
+            if (__all_sync(0xffffffffu, offs[j] == 0xFFFFFFFFu)) miss |= 1u << j;
+          skip = miss & (zst >> (s * RPT));
+          zst = (zst & ~(((1u << RPT) - 1u) << (s * RPT))) | (miss << (s * RPT));
+        }
         if (!(p.debug & 4))
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
+          if (skip & (1u << j)) continue;
           const bool ok = offs[j] != 0xFFFFFFFFu;
           cp_async16(sa + a_thr_off + j * 32 * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
         }

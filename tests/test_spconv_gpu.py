@@ -231,9 +231,14 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
         out, _, _ = mod(f, c, 2)
         L.set_option('gemm_mt', 2)               # 256-row CTA tiles of the same schedule
         out2, _, _ = mod(f, c, 2)
+        L.set_option('gemm_zskip', 1)            # + zero-skip of all-missing 4-row copies
+        out3, _, _ = mod(f, c, 2)
+        L.set_option('gemm_mt', 3)
+        out4, _, _ = mod(f, c, 2)
         torch.cuda.synchronize()
-        assert torch.equal(out, ref) and torch.equal(out2, ref)
+        assert torch.equal(out, ref) and torch.equal(out2, ref) and torch.equal(out3, ref) and torch.equal(out4, ref)
     finally:
         L.set_option('gemm_v4', 2)
         L.set_option('gemm_mt', 3)
+        L.set_option('gemm_zskip', 0)
         sp.TILE_ORDER = old
