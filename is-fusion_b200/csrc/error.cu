@@ -30,6 +30,10 @@ int g_isf_tile_order_drop_bits = 0;
 int g_isf_nbr_rows = 1;
 int g_isf_gemm_mt = 3;
 int g_isf_gemm_zskip = 0;
+int g_isf_gemm_wpc = 0;
+int g_isf_gemm_rev = 0;
+int g_isf_gemm_pair = 1;
+int g_isf_gemm_v4_32 = 1;
 int g_isf_gemm_v4 = 2;
 int g_isf_gemm_ln_fast = 1;
 int g_isf_gemm_debug = 0;
@@ -56,6 +60,22 @@ extern "C" int isf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_zskip") == 0 && (value == 0 || value == 1)) {
     g_isf_gemm_zskip = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "gemm_pair") == 0 && (value == 0 || value == 1 || value == 64 || value == 128 || value == 256)) {
+    g_isf_gemm_pair = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "gemm_wpc") == 0 && value >= 0 && value <= 2) {
+    g_isf_gemm_wpc = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "gemm_rev") == 0 && (value == 0 || value == 1)) {
+    g_isf_gemm_rev = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "gemm_v4_32") == 0 && value >= 0 && value <= 2) {
+    g_isf_gemm_v4_32 = value;
     return ISF_OK;
   }
   if (name && strcmp(name, "gemm_debug") == 0 && value >= 0 && value <= 7) {

@@ -210,6 +210,8 @@ struct GemmParams {
   float* out_f32;         // [m, ldo] fp32 (may be nullptr)
   int ldo;
   const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
+  int wpc;                // tc_gemm4.cuh: producer warps per K chunk (1 or 2) of the warp-per-chunk mapping
+  int rev;                // tc_gemm4.cuh: tiles walked from the last one down (isf_set_option("gemm_rev"))
   int zskip;              // tc_gemm4.cuh: skip all-missing 4-row copies onto rows that already hold zeros (isf_set_option("gemm_zskip"))
   int debug;              // timing experiments only (isf_set_option("gemm_debug")): 1 = weight chunk loaded for the first chunk of a
                           // tile only, 2 = every gathered row reads row 0, 4 = no A copies at all.  Results are then meaningless.
@@ -886,6 +888,8 @@ static inline int dispatch_gemm_mt2(const GemmParams& p, int bn, int m_upper, cu
 
 static inline bool gemm4_supported(const GemmParams& p, int bn);                               // tc_gemm4.cuh
 static inline int dispatch_gemm4(const GemmParams& p, int bn, int m_upper, cudaStream_t st);
+static inline bool gemm5_supported(const GemmParams& p, int bn, int m_upper);                  // tc_gemm5.cuh
+static inline int dispatch_gemm5(const GemmParams& p, int bn, int m_upper, cudaStream_t st);
 
 static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaStream_t st) {
   if (p0.taps > MAX_TAPS || p0.kpad / BK > MAX_CHUNKS) {
@@ -895,6 +899,8 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
   GemmParams p = p0;
   p.debug = ::g_isf_gemm_debug;
   p.zskip = ::g_isf_gemm_zskip;
+  p.rev = ::g_isf_gemm_rev;
+  p.wpc = 1;
   if (p.ln_gamma != nullptr && p.nbr == nullptr && ::g_isf_gemm_ln_fast) {      // LayerNorm epilogue: dense GEMMs, one column block
     switch (bn) {
       case 64: return launch_gemm<64, 2, 1, 1, true>(p, m_upper, st);
@@ -903,6 +909,9 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
       default: break;
     }
   }
+  // CTA pairs on tcgen05.mma.cta_group::2 (tc_gemm5.cuh): sparse-conv launches with >= 64 columns
+  if (::g_isf_gemm_pair && gemm5_supported(p, bn, m_upper) && (::g_isf_gemm_pair == 1 || bn >= ::g_isf_gemm_pair))
+    return dispatch_gemm5(p, bn, m_upper, st);
   // dedicated epilogue warps + double-buffered accumulator (tc_gemm4.cuh): 1 = sparse-conv launches, 2 = dense GEMMs too
   if (::g_isf_gemm_v4 && gemm4_supported(p, bn) && m_upper >= 8 * BM && (p.nbr != nullptr || ::g_isf_gemm_v4 == 2))
     return dispatch_gemm4(p, bn, m_upper, st);
@@ -923,3 +932,4 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
 }  // namespace tc
 
 #include "tc_gemm4.cuh"
+#include "tc_gemm5.cuh"

@@ -38,7 +38,13 @@ struct Smem4 {
 };
 
 // MT = 128-row sub-tiles per CTA tile: with MT = 2 one weight chunk feeds 256 output rows (half the weight bytes per FLOP from L2)
-template <int BN, int STAGES, int CTAS, int MT>
+// WPC ("warp per chunk", round 2 call 14): a K chunk is gathered by ONE producer warp (32 LDGSTS per lane and 128 rows) instead of
+// by all eight (4 per thread), the warps taking the chunks of a tile round-robin.  Why: the timing experiments of call 13 (no A
+// copies, weights once per tile: results meaningless, time 2.18 of 2.87 ms) left a floor of ~550 SM-cycles per 128 x 64 block that
+// does not depend on the column tile - 257 mbarrier arrivals (cp.async.mbarrier.arrive.noinc, one per producer thread) and 256
+// try_wait pollers per chunk go through the same MIO / LSU queue as the 32 LDGSTS (8 cycles each): ~2.2 cycles per arrival + 256
+// = the ~800 cycles per block measured on stages 2 / 3 against 188 / 375 of MMA time.  One (two) warp(s) per chunk = 33 (65) arrivals.
+template <int BN, int STAGES, int CTAS, int MT, bool WPC>
 __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
   using SL = Smem4<BN, STAGES, MT>;
   constexpr int TILE_M = SL::TILE_M;
@@ -68,9 +74,13 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
   const int n0 = blockIdx.y * BN;
   const int num_chunks = p.kpad / BK;
   const bool gather = p.nbr != nullptr;
+  // tile walk: CTA b takes positions b, b + grid, ... of the tile sequence; rev = from the last tile down (under the neighbour-
+  // pattern order the densest tiles sit at the end: walking them first leaves the cheap ones for the partial last round)
+  const bool rev = p.rev != 0;
+#define V4_TILE(idx) (rev ? num_tiles - 1 - (idx) : (idx))
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], (WPC ? 32 * p.wpc : PRODUCERS) + 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 128);
@@ -108,7 +118,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     // gather loop instead of sitting between two tiles (where only STAGES chunks of work are queued for the tensor core)
     int nv[NVR];
     if (gather) {
-      const long long prow = (long long)blockIdx.x * TILE_M + r;
+      const long long prow = (long long)V4_TILE((int)blockIdx.x) * TILE_M + r;
       const bool pok = (int)blockIdx.x < num_tiles && prow < m_total;
 #pragma unroll
       for (int u = 0; u < NVR; ++u) {
@@ -117,7 +127,8 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       }
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tidx = blockIdx.x; tidx < num_tiles; tidx += gridDim.x, ++it) {
+      const int tile = V4_TILE(tidx);
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
       const int row0 = tile * TILE_M;
@@ -160,65 +171,113 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int n_act = tap_flag[32];
       if (gather) {      // prefetch the next tile's neighbour ids (consumed after this tile's gather loop)
-        const int ntile = tile + (int)gridDim.x;
-        const long long prow = (long long)ntile * TILE_M + r;
-        const bool pok = ntile < num_tiles && prow < m_total;
+        const int nidx = tidx + (int)gridDim.x;
+        const long long prow = (long long)V4_TILE(nidx) * TILE_M + r;
+        const bool pok = nidx < num_tiles && prow < m_total;
 #pragma unroll
         for (int u = 0; u < NVR; ++u) {
           const int t = thalf + TSPLIT * u;
           nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
         }
       }
-      unsigned offs[RPT];
-      int offs_tap = -1;
-      for (int i = 0; i < n_act; ++i, ++ca) {
-        const int q = chunk_list[i];
-        const int s = (int)(ca % STAGES);
-        const uint32_t use = ca / STAGES;
-        if (use > 0) mbar_wait_b(&empty_bar[s], (use - 1) & 1);
-        const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
-        if (tid == 0) {
-          if ((p.debug & 1) && i > 0) mbar_arrive(&full_bar[s]);      // timing experiment: weight chunk only once per tile
-          else {
-            mbar_expect_tx(&full_bar[s], BN * 128);
-            tma_load_2d(sa + SL::A_BYTES, &tmap_w, q * BK, n0, &full_bar[s]);
+      if constexpr (WPC) {
+        // a chunk is gathered by G = p.wpc (1 or 2) producer warps that OWN its smem stage: warps [G s, G s + G) serve stage s and
+        // nothing else, so each of them sees every phase of that stage's empty barrier in order (a warp that skipped phases would
+        // alias the parity test: call 14's fault); warps >= G * STAGES only take part in the tile prologue.
+        // lane = (row & 3, 16-byte piece): 4 rows x 128 B per instruction, TILE_M / (4 G) instructions per lane and chunk
+        const int G = p.wpc;
+        const int s = warp / G, part = warp - s * G;
+        if (s < STAGES) {
+          const int lrow = lane >> 3, lpc = lane & 7;
+          const uint32_t sw0 = (uint32_t)(lrow * 128 + ((lpc ^ lrow) << 4));           // rows 8m + lrow
+          const uint32_t sw1 = (uint32_t)(lrow * 128 + ((lpc ^ (lrow | 4)) << 4));     // rows 8m + 4 + lrow
+          const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
+          const int jn = TILE_M / 4 / G, jb = part * jn;
+          for (int i = (s + STAGES - (int)(ca % STAGES)) % STAGES; i < n_act; i += STAGES) {
+            const uint32_t use = (ca + (uint32_t)i) / STAGES;
+            const int q = chunk_list[i];
+            if (use > 0) mbar_wait_b(&empty_bar[s], (use - 1) & 1);
+            if (part == 0 && lane == 0) {
+              if ((p.debug & 1) && i > 0) mbar_arrive(&full_bar[s]);      // timing experiment: weight chunk only once per tile
+              else {
+                mbar_expect_tx(&full_bar[s], BN * 128);
+                tma_load_2d(sa + SL::A_BYTES, &tmap_w, q * BK, n0, &full_bar[s]);
+              }
+            }
+            const int k = q * BK + lpc * 8;
+            int tap, ch;
+            if (p.taps == 1) { tap = k >= p.cin ? 1 : 0; ch = k; } else { tap = k >> p.cin_shift; ch = k & (p.cin - 1); }
+            const bool tap_ok = tap < p.taps;
+            const char* src_ch = a_bytes + ch * 2;
+            const int* nrow = nbr_s + (tap_ok ? tap : 0) * TILE_M + lrow;
+            if (!(p.debug & 4)) {
+#pragma unroll 8
+              for (int j = jb; j < jb + jn; ++j) {
+                unsigned off = 0xFFFFFFFFu;
+                if (tap_ok) {
+                  if (gather) off = (unsigned)nrow[4 * j];
+                  else { const int gr = row0 + 4 * j + lrow; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
+                }
+                const bool ok = off != 0xFFFFFFFFu;
+                cp_async16(sa + (uint32_t)(j * 512) + ((j & 1) ? sw1 : sw0), ok ? src_ch + off : a_bytes, ok ? 16u : 0u);
+              }
+            }
+            cp_async_mbar_arrive(&full_bar[s]);
           }
         }
-        const int k = q * BK + pc * 8;
-        int tap, ch;
-        if (p.taps == 1) { tap = k >= p.cin ? 1 : 0; ch = k; } else { tap = k >> p.cin_shift; ch = k & (p.cin - 1); }
-        const bool tap_ok = tap < p.taps;
-        const char* src_ch = a_bytes + ch * 2;
-        if (tap != offs_tap) {
-          offs_tap = tap;
-          const int* nrow = nbr_s + tap * TILE_M + rbase;
+        ca += (uint32_t)n_act;
+      } else {
+        unsigned offs[RPT];
+        int offs_tap = -1;
+        for (int i = 0; i < n_act; ++i, ++ca) {
+          const int q = chunk_list[i];
+          const int s = (int)(ca % STAGES);
+          const uint32_t use = ca / STAGES;
+          if (use > 0) mbar_wait_b(&empty_bar[s], (use - 1) & 1);
+          const uint32_t sa = smem_u32(smem + s * SL::STAGE_BYTES);
+          if (tid == 0) {
+            if ((p.debug & 1) && i > 0) mbar_arrive(&full_bar[s]);      // timing experiment: weight chunk only once per tile
+            else {
+              mbar_expect_tx(&full_bar[s], BN * 128);
+              tma_load_2d(sa + SL::A_BYTES, &tmap_w, q * BK, n0, &full_bar[s]);
+            }
+          }
+          const int k = q * BK + pc * 8;
+          int tap, ch;
+          if (p.taps == 1) { tap = k >= p.cin ? 1 : 0; ch = k; } else { tap = k >> p.cin_shift; ch = k & (p.cin - 1); }
+          const bool tap_ok = tap < p.taps;
+          const char* src_ch = a_bytes + ch * 2;
+          if (tap != offs_tap) {
+            offs_tap = tap;
+            const int* nrow = nbr_s + tap * TILE_M + rbase;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+              unsigned off = 0xFFFFFFFFu;
+              if (tap_ok) {
+                if (gather) off = (unsigned)nrow[32 * j];
+                else { const int gr = row0 + rbase + 32 * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
+              }
+              offs[j] = off;
+            }
+          }
+          unsigned skip = 0;
+          if (zskip) {
+            unsigned miss = 0;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+              if (__all_sync(0xffffffffu, offs[j] == 0xFFFFFFFFu)) miss |= 1u << j;
+            skip = miss & (zst >> (s * RPT));
+            zst = (zst & ~(((1u << RPT) - 1u) << (s * RPT))) | (miss << (s * RPT));
+          }
+          if (!(p.debug & 4))
 #pragma unroll
           for (int j = 0; j < RPT; ++j) {
-            unsigned off = 0xFFFFFFFFu;
-            if (tap_ok) {
-              if (gather) off = (unsigned)nrow[32 * j];
-              else { const int gr = row0 + rbase + 32 * j; if (gr < m_total) off = (unsigned)gr * (unsigned)(p.cin * 2); }
-            }
-            offs[j] = off;
+            if (skip & (1u << j)) continue;
+            const bool ok = offs[j] != 0xFFFFFFFFu;
+            cp_async16(sa + a_thr_off + j * 32 * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
           }
+          cp_async_mbar_arrive(&full_bar[s]);
         }
-        unsigned skip = 0;
-        if (zskip) {
-          unsigned miss = 0;
-#pragma unroll
-          for (int j = 0; j < RPT; ++j)
-            if (__all_sync(0xffffffffu, offs[j] == 0xFFFFFFFFu)) miss |= 1u << j;
-          skip = miss & (zst >> (s * RPT));
-          zst = (zst & ~(((1u << RPT) - 1u) << (s * RPT))) | (miss << (s * RPT));
-        }
-        if (!(p.debug & 4))
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-          if (skip & (1u << j)) continue;
-          const bool ok = offs[j] != 0xFFFFFFFFu;
-          cp_async16(sa + a_thr_off + j * 32 * 128, ok ? src_ch + offs[j] : a_bytes, ok ? 16u : 0u);
-        }
-        cp_async_mbar_arrive(&full_bar[s]);
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -227,7 +286,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     constexpr uint32_t idesc = make_idesc_f16(BM, BN);
     uint32_t ca = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tidx = blockIdx.x; tidx < num_tiles; tidx += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
       mbar_wait_b(&list_full[buf], ubuf & 1);
@@ -262,7 +321,8 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     // ================================================================ epilogue (warps 9-12; TMEM lane quarter = warp % 4)
     const int r = (warp & 3) * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tidx = blockIdx.x; tidx < num_tiles; tidx += gridDim.x, ++it) {
+      const int tile = V4_TILE(tidx);
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
 #pragma unroll 1
@@ -347,13 +407,14 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
   tc_fence_before();
   __syncthreads();
   if (warp == V4_MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
+#undef V4_TILE
 }
 
-template <int BN, int STAGES, int CTAS, int MT = 1>
-static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
+template <int BN, int STAGES, int CTAS, int MT, bool WPC>
+static int launch_gemm4_impl(const GemmParams& p, int m_upper, cudaStream_t st) {
   using SL = Smem4<BN, STAGES, MT>;
   static_assert((SL::TOTAL + 1024) * CTAS <= 227 * 1024, "v4 GEMM: shared memory budget exceeded");
-  auto kern = gemm4_kernel<BN, STAGES, CTAS, MT>;
+  auto kern = gemm4_kernel<BN, STAGES, CTAS, MT, WPC>;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { isf_set_error("gemm v4: bad device"); return ISF_ERR_CUDA; }
   static bool configured[64] = {};
@@ -378,7 +439,17 @@ static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
   return ISF_OK;
 }
 
-static inline bool gemm4_supported(const GemmParams& p, int bn) { return p.ln_gamma == nullptr && bn >= 64; }
+template <int BN, int STAGES, int CTAS, int MT = 1>
+static int launch_gemm4(const GemmParams& p, int m_upper, cudaStream_t st) {
+  if (::g_isf_gemm_wpc) {
+    GemmParams q = p;
+    q.wpc = (::g_isf_gemm_wpc == 2 && STAGES * 2 <= PWARPS) ? 2 : 1;
+    return launch_gemm4_impl<BN, STAGES, CTAS, MT, true>(q, m_upper, st);
+  }
+  return launch_gemm4_impl<BN, STAGES, CTAS, MT, false>(p, m_upper, st);
+}
+
+static inline bool gemm4_supported(const GemmParams& p, int bn) { return p.ln_gamma == nullptr && (bn >= 64 || (bn == 32 && ::g_isf_gemm_v4_32)); }
 
 static inline int dispatch_gemm4(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
   // 256-row tiles (one weight chunk per 256 rows): measured on v4 (round 2, call 8) -8 % on the 64-column layers, +7 % on the
@@ -388,6 +459,9 @@ static inline int dispatch_gemm4(const GemmParams& p, int bn, int m_upper, cudaS
     if (bn == 128 && ::g_isf_gemm_mt == 2) return launch_gemm4<128, 4, 1, 2>(p, m_upper, st);    // 4 x 48 KB + 27 KB, 512 TMEM columns
   }
   switch (bn) {
+    case 32:                                                       // stage 1: 3-5 chunks per tile, latency-bound
+      if (::g_isf_gemm_v4_32 == 2) return launch_gemm4<32, 2, 3>(p, m_upper, st);      // 2 x 20 KB + 14 KB, 3 CTAs / SM (48 registers)
+      return launch_gemm4<32, 4, 2>(p, m_upper, st);                                   // 4 x 20 KB + 14 KB, 2 CTAs / SM
     case 64: return launch_gemm4<64, 4, 2>(p, m_upper, st);        // 4 x 24 KB, 2 x 128 TMEM columns per CTA
     case 128: return launch_gemm4<128, 3, 2>(p, m_upper, st);      // 3 x 32 KB
     case 256: return launch_gemm4<256, 4, 1>(p, m_upper, st);      // 4 x 48 KB, all 512 TMEM columns

@@ -225,6 +225,7 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
     old = sp.TILE_ORDER
     try:
         sp.TILE_ORDER = order
+        L.set_option('gemm_pair', 0)
         L.set_option('gemm_v4', 0)
         ref, _, _ = mod(f, c, 2)
         L.set_option('gemm_v4', 2)
@@ -237,8 +238,30 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
         out4, _, _ = mod(f, c, 2)
         torch.cuda.synchronize()
         assert torch.equal(out, ref) and torch.equal(out2, ref) and torch.equal(out3, ref) and torch.equal(out4, ref)
+        L.set_option('gemm_zskip', 0)
+        # producer mapping (all eight warps per chunk / one warp per chunk), tile walk direction, 32-column layers on v4
+        for wpc, rev, v32, mt in ((0, 0, 0, 3), (1, 0, 0, 3), (0, 1, 1, 3), (1, 1, 1, 3), (2, 1, 2, 3), (1, 1, 1, 2), (2, 0, 2, 1), (2, 1, 1, 2)):
+            L.set_option('gemm_wpc', wpc)
+            L.set_option('gemm_rev', rev)
+            L.set_option('gemm_v4_32', v32)
+            L.set_option('gemm_mt', mt)
+            o, _, _ = mod(f, c, 2)
+            torch.cuda.synchronize()
+            assert torch.equal(o, ref), (wpc, rev, v32, mt)
+        # CTA pairs (tcgen05.mma.cta_group::2, csrc/tc_gemm5.cuh): every column tile >= 64 / only 256 / 128-and-up, both walks
+        for pair, rev, mt in ((1, 0, 3), (1, 1, 3), (256, 0, 3), (128, 0, 1), (1, 0, 1)):
+            L.set_option('gemm_pair', pair)
+            L.set_option('gemm_rev', rev)
+            L.set_option('gemm_mt', mt)
+            o, _, _ = mod(f, c, 2)
+            torch.cuda.synchronize()
+            assert torch.equal(o, ref), ('pair', pair, rev, mt)
     finally:
+        L.set_option('gemm_pair', 1)
         L.set_option('gemm_v4', 2)
         L.set_option('gemm_mt', 3)
         L.set_option('gemm_zskip', 0)
+        L.set_option('gemm_wpc', 0)
+        L.set_option('gemm_rev', 0)
+        L.set_option('gemm_v4_32', 1)
         sp.TILE_ORDER = old
