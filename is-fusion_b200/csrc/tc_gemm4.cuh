@@ -38,12 +38,11 @@ struct Smem4 {
 };
 
 // MT = 128-row sub-tiles per CTA tile: with MT = 2 one weight chunk feeds 256 output rows (half the weight bytes per FLOP from L2)
-// WPC ("warp per chunk", round 2 call 14): a K chunk is gathered by ONE producer warp (32 LDGSTS per lane and 128 rows) instead of
-// by all eight (4 per thread), the warps taking the chunks of a tile round-robin.  Why: the timing experiments of call 13 (no A
-// copies, weights once per tile: results meaningless, time 2.18 of 2.87 ms) left a floor of ~550 SM-cycles per 128 x 64 block that
-// does not depend on the column tile - 257 mbarrier arrivals (cp.async.mbarrier.arrive.noinc, one per producer thread) and 256
-// try_wait pollers per chunk go through the same MIO / LSU queue as the 32 LDGSTS (8 cycles each): ~2.2 cycles per arrival + 256
-// = the ~800 cycles per block measured on stages 2 / 3 against 188 / 375 of MMA time.  One (two) warp(s) per chunk = 33 (65) arrivals.
+// WPC ("warp per chunk", round 2 calls 14-16; opt-in, isf_set_option("gemm_wpc", 1|2)): a K chunk is gathered by one or two
+// producer warps that own its smem stage instead of by all eight.  Hypothesis: the 257 mbarrier arrivals + 256 try_wait pollers
+// per chunk pace the MIO queue.  Measured: bit-identical and SLOWER (21 launches 2.83 -> 3.55 ms with two warps per chunk, 4.80 ms
+// with one): a single warp cannot keep 32 dependent LDS -> LDGSTS pairs per chunk in flight; with every load removed the floor
+// only moved from 2.18 to 1.98 ms, i.e. the arrivals were never the cost.  Kept as the second producer mapping of the kernel.
 template <int BN, int STAGES, int CTAS, int MT, bool WPC>
 __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
   using SL = Smem4<BN, STAGES, MT>;

@@ -13,7 +13,7 @@
 //   * cluster of 2 CTAs; super-tile = 2 x TILE_M rows, CTA r gathers rows [r TILE_M, (r + 1) TILE_M) and TMA-loads weight rows
 //     [r BN / 2, (r + 1) BN / 2) of the chunk into its own stage;
 //   * both CTAs walk the SAME chunk list: the per-tile kernel-offset masks are exchanged through distributed shared memory
-//     (st.shared::cluster + a remote mbarrier arrive) and OR-ed;
+//     (st.async with complete_tx on the peer's barrier) and OR-ed;
 //   * the leader's MMA thread waits for its own full barrier and for `peer_full` (one remote arrival per chunk from the peer's
 //     otherwise idle MMA warp, which relays the peer's full barrier: cp.async cannot signal a remote barrier), issues
 //     tcgen05.mma.cta_group::2 and commits with multicast to the empty / accumulator barriers of both CTAs;
@@ -29,33 +29,17 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Plain (cta-scope release) remote arrive, as cutlass::arch::ClusterBarrier::arrive(cta_id): the .release.cluster form costs a
+// MEMBAR.ALL.GPU per arrival and the .acquire.cluster try_wait a CCTL.IVALL per success (call 17: the relay thread of the peer CTA
+// then serves one chunk per ~900 cycles and paces the whole pair).  What the barriers order here is consumed by the tensor core
+// (behind fence.proxy.async) or carried by st.async, not by generic loads.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void st_remote_u32(uint32_t cluster_addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait with cluster-scope acquire (barriers that receive remote arrivals)
-__device__ __forceinline__ void mbar_wait_cluster_b(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  for (;;) {
-#pragma unroll 1
-    for (int i = 0; i < 256; ++i)
-      if (mbar_try_cluster(bar, parity)) return;
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
+// remote 4-byte store that completes 4 transaction bytes on a barrier of the destination CTA when the data has landed
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v), "r"(cluster_bar)
+               : "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem) {
@@ -198,10 +182,10 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
         // kernel offsets present in this CTA's rows -> peer; union of both = the chunk list both CTAs walk
         const unsigned own = __ballot_sync(0xffffffffu, lane < p.taps && tap_flag[lane] != 0);
         if (lane == 0) {
-          st_remote_u32(mapa_u32(smem_u32(&tap_flag[48 + buf]), rank ^ 1u), own);
-          mbar_arrive_remote(mapa_u32(smem_u32(&xbar[buf]), rank ^ 1u));
+          mbar_expect_tx(&xbar[buf], 4);      // this CTA's arrival of the phase + the 4 bytes the peer will send
+          st_async_u32(mapa_u32(smem_u32(&tap_flag[48 + buf]), rank ^ 1u), own, mapa_u32(smem_u32(&xbar[buf]), rank ^ 1u));
         }
-        mbar_wait_cluster_b(&xbar[buf], ubuf & 1);
+        mbar_wait_b(&xbar[buf], ubuf & 1);
         const unsigned both = own | (unsigned)((const volatile int*)tap_flag)[48 + buf];
         int count = 0;
         for (int base = 0; base < num_chunks; base += 32) {
@@ -283,14 +267,14 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
         const int n_act = ((const volatile int*)tap_flag)[40 + buf];
         __syncwarp();
         if (lane == 0) mbar_arrive(&list_empty[buf]);
-        if (ubuf > 0) mbar_wait_cluster_b(&acc_empty[buf], (ubuf - 1) & 1);      // both epilogues have drained this accumulator
+        if (ubuf > 0) mbar_wait_b(&acc_empty[buf], (ubuf - 1) & 1);      // both epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * MT * BN);
         for (int q = 0; q < n_act; ++q, ++ca) {
           const int s = (int)(ca % STAGES);
           const uint32_t par = (ca / STAGES) & 1;
           mbar_wait_b(&full_bar[s], par);
-          mbar_wait_cluster_b(&peer_full[s], par);
+          mbar_wait_b(&peer_full[s], par);
           fence_proxy_async();
           tc_fence_after();
           if (lane == 0) {
