@@ -190,3 +190,123 @@ extern "C" int isf_debug_gather_bench(const void* a, int rows, int cols, const i
   ISF_LAUNCH_CHECK();
   return ISF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark (NOT on the product path): issue rate of tcgen05.mma kind::f16 by instruction shape and operand source.
+// One thread per CTA (per CTA pair for cta_group::2) issues `iters` groups of four K = 16 instructions of shape m x n on constant
+// (zero) shared-memory operands, four groups in flight (tcgen05.commit ring); nothing else runs.  out[block] = cycles per
+// instruction as seen by that CTA.  a_tmem = 1: the A operand comes from tensor memory (TS mode) instead of shared memory.
+// With probe != 0 (one CTA, m x 32 x 16, cta_group::1) it runs ONE instruction on A[i][0] = i + 1, B[j][0] = 1 and dumps TMEM
+// column 0 of all 128 lanes: the accumulator layout of the shape (out_probe[lane] = D value held by that lane).
+// ------------------------------------------------------------------------------------------------
+#include "tc_gemm5.cuh"
+
+template <int CG>
+__global__ void __launch_bounds__(128) mma_rate_kernel(int m, int n, int a_tmem, int iters, float* __restrict__ out,
+                                                       float* __restrict__ out_probe) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
+  uint8_t* sa = smem;                  // 256 rows x 128 B
+  uint8_t* sb = smem + 32768;          // 256 rows x 128 B
+  uint64_t* bar = (uint64_t*)(smem + 65536);      // [4]
+  uint32_t* slot = (uint32_t*)(bar + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool probe = out_probe != nullptr;
+  for (int e = tid; e < 65536 / 16; e += 128) ((uint4*)smem)[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (probe) {
+    // row r, k = 0 of the 128B-swizzled K-major layout sits at r * 128 + ((r & 7) << 4)
+    for (int r = tid; r < 256; r += 128) {
+      *(__half*)(sa + r * 128 + ((r & 7) << 4)) = __float2half((float)(r + 1));
+      *(__half*)(sb + r * 128 + ((r & 7) << 4)) = __float2half(1.f);
+    }
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) tc::mbar_init(&bar[s], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) {
+    if constexpr (CG == 2) tc::tmem_alloc2<256>(slot); else tc::tmem_alloc<256>(slot);
+  }
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  if constexpr (CG == 2) tc::cluster_sync_all(); else __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *slot;
+  const bool leader = CG == 1 || tc::cluster_ctarank() == 0;
+  if (tid == 0 && leader) {
+    const uint32_t idesc = tc::make_idesc_f16(CG * m, n);
+    const uint64_t a_desc = tc::make_desc_sw128(tc::smem_u32(sa)), b_desc = tc::make_desc_sw128(tc::smem_u32(sb));
+    const uint32_t a_t = tmem + 128;      // TS mode: A at columns [128, 160) (n <= 128 then)
+    const int groups = probe ? 1 : iters;
+    const long long t0 = clock64();
+    for (int i = 0; i < groups; ++i) {
+      const int s = i & 3;
+      if (i >= 4) tc::mbar_wait_b(&bar[s], (uint32_t)((i - 4) >> 2) & 1);
+      for (int kk = 0; kk < (probe ? 1 : 4); ++kk) {
+        const uint32_t acc = (probe && kk == 0) ? 0u : 1u;
+        if (a_tmem) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem),
+              "r"(a_t + (uint32_t)(kk * 8)), "l"(b_desc + (uint64_t)(kk * 2)), "r"(idesc), "r"(acc)
+              : "memory");
+        } else if constexpr (CG == 2) {
+          tc::umma_f16_2cta(tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, acc);
+        } else {
+          tc::umma_f16(tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, acc);
+        }
+      }
+      if constexpr (CG == 2) tc::umma_commit2_mcast(&bar[s], 1); else tc::umma_commit(&bar[s]);
+    }
+    for (int i = (groups > 4 ? groups - 4 : 0); i < groups; ++i) tc::mbar_wait_b(&bar[i & 3], (uint32_t)(i >> 2) & 1);
+    const long long t1 = clock64();
+    out[blockIdx.x] = (float)(t1 - t0) / (float)(groups * 4);
+  }
+  tc::tc_fence_before();
+  if constexpr (CG == 2) tc::cluster_sync_all(); else __syncthreads();
+  tc::tc_fence_after();
+  if (probe) {
+    uint32_t v[16];
+    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+    tc::tmem_ld_wait();
+    out_probe[tid] = __uint_as_float(v[0]);
+    out_probe[128 + tid] = __uint_as_float(v[1]);
+  }
+  tc::tc_fence_before();
+  if constexpr (CG == 2) tc::cluster_sync_all(); else __syncthreads();
+  if (warp == 0) {
+    if constexpr (CG == 2) tc::tmem_dealloc2<256>(tmem); else tc::tmem_dealloc<256>(tmem);
+  }
+}
+
+extern "C" int isf_debug_mma_rate(int m, int n, int cta_group, int a_tmem, int blocks, int iters, float* out_cycles,
+                                  float* out_probe, void* stream) {
+  ISF_CHECK_ARG(out_cycles && (m == 64 || m == 128) && n >= 16 && n <= 256 && n % 16 == 0 && (cta_group == 1 || cta_group == 2) &&
+                blocks >= 1 && iters >= 1 && (!a_tmem || (cta_group == 1 && n <= 128)) && (!out_probe || (cta_group == 1 && blocks == 1)));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = 65536 + 1024 + 256;
+  if (cta_group == 2) {
+    ISF_CHECK_ARG(blocks % 2 == 0);
+    ISF_CUDA(cudaFuncSetAttribute(mma_rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ISF_CUDA(cudaLaunchKernelEx(&cfg, mma_rate_kernel<2>, m, n, a_tmem, iters, out_cycles, out_probe));
+  } else {
+    ISF_CUDA(cudaFuncSetAttribute(mma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate_kernel<1><<<blocks, 128, smem, st>>>(m, n, a_tmem, iters, out_cycles, out_probe);
+  }
+  ISF_LAUNCH_CHECK();
+  return ISF_OK;
+}

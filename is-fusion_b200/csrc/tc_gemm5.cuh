@@ -281,13 +281,11 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
             const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
             const uint64_t b_desc = make_desc_sw128(a_addr + SL::A_BYTES);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t a_desc = make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128));
+            for (int kk = 0; kk < BK / 16; ++kk)       // K step outermost: consecutive instructions alternate accumulators (tc_gemm4.cuh)
 #pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk)
-                umma_f16_2cta(d_tmem + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                              (q | kk) ? 1u : 0u);
-            }
+              for (int mt = 0; mt < MT; ++mt)
+                umma_f16_2cta(d_tmem + (uint32_t)(mt * BN), make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128)) + (uint64_t)(kk * 2),
+                              b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
             umma_commit2_mcast(&empty_bar[s], 3);
             if (q == n_act - 1) umma_commit2_mcast(&acc_full[buf], 3);
           }

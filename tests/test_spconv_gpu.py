@@ -257,7 +257,7 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
             torch.cuda.synchronize()
             assert torch.equal(o, ref), ('pair', pair, rev, mt)
     finally:
-        L.set_option('gemm_pair', 1)
+        L.set_option('gemm_pair', 0)
         L.set_option('gemm_v4', 2)
         L.set_option('gemm_mt', 3)
         L.set_option('gemm_zskip', 0)
