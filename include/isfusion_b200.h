@@ -415,11 +415,12 @@ int isf_debug_gather_bench(const void* a, int rows, int cols, const int* idx_dev
                            int blocks, float* out_cycles, void* stream);
 
 /* micro-benchmark (NOT on the product path): cycles per tcgen05.mma kind::f16 instruction of shape m x n x 16 (cta_group 1 | 2;
- * a_tmem = 1: A operand from tensor memory) issued back to back by one thread per CTA (pair) on constant operands,
+ * a_tmem = 1: A operand from tensor memory; chains = independent accumulators the instructions alternate between; issuers =
+ * warps of the CTA issuing their own streams) issued back to back on constant operands,
  * out_cycles[block]; with out_probe (256 floats, one block) it runs one m x 32 instruction on A[i][0] = i + 1, B[j][0] = 1 and
  * returns TMEM columns 0 and 1 of the 128 lanes (the accumulator layout of the shape) (csrc/debug_tma.cu). */
-int isf_debug_mma_rate(int m, int n, int cta_group, int a_tmem, int blocks, int iters, float* out_cycles, float* out_probe,
-                       void* stream);
+int isf_debug_mma_rate(int m, int n, int cta_group, int a_tmem, int chains, int issuers, int blocks, int iters,
+                       float* out_cycles, float* out_probe, void* stream);
 
 #ifdef __cplusplus
 }

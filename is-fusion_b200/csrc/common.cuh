@@ -83,7 +83,7 @@ extern int g_isf_gemm_wpc;        // isf_set_option("gemm_wpc", 0|1|2): one / tw
 extern int g_isf_gemm_rev;        // isf_set_option("gemm_rev", 0|1): v4 walks the tiles from the last one down (default 1)
 extern int g_isf_gemm_v4_32;      // isf_set_option("gemm_v4_32", 0|1|2): 32-column layers on the v4 schedule (1 = 2 CTAs / SM, default; 2 = 3 CTAs / SM)
 extern int g_isf_gemm_pair;       // isf_set_option("gemm_pair", 0|1|64|128|256): sparse convs on CTA pairs (tcgen05.mma.cta_group::2, tc_gemm5.cuh);
-                                  // 1 = every column tile >= 64, N = only column tiles >= N
+                                  // 1 = every column tile >= 64, N = only column tiles >= N (default 128)
 extern int g_isf_gemm_zskip;      // isf_set_option("gemm_zskip", 0|1): zero-skip of the v4 producers
 extern int g_isf_gemm_mt;         // isf_set_option("gemm_mt", 1|2): 128-row sub-tiles per CTA tile of the sparse-conv GEMM
 extern int g_isf_gemm_debug;      // isf_set_option("gemm_debug", bits): timing experiments (tc_gemm.cuh GemmParams::debug)

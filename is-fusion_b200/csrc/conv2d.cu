@@ -182,27 +182,16 @@ conv3x3_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_x, c
             const int sb = (int)(cb % SB);
             mbar_wait_b(&b_full[sb], (cb / SB) & 1);
             tc_fence_after();
-            if (lane == 0) {
-              const uint64_t b_desc = make_desc_sw128(smem_u32(smem + SL::B_OFF + sb * SL::B_BYTES));
-              // K step outermost, sub-tiles innermost: consecutive instructions alternate between the accumulators (an accumulator
-              // chain retires one instruction per ~179 cycles whatever its shape: scripts/bench_mma_rate.py)
-#pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk)
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  // sub-tile mt, tap row shift t (stride 1: dy rows of the halo box): a multiple of 4096 B
-                  const uint64_t a_desc = make_desc_sw128(a_addr + (uint32_t)((mt * SUB_ROWS + (STRIDE == 1 ? t : 0)) * ROW_BYTES));
-                  umma_f16(tmem_base + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                           (c | l | t | kk) ? 1u : 0u);
-                }
-              umma_commit(&b_empty[sb]);
+            {      // whole warp, converged: one election per (tap, chunk) (umma_chunk, tc_gemm.cuh); sub-tiles alternate per K step
+              // sub-tile mt, tap row shift t (stride 1: dy rows of the halo box): a multiple of 4096 B
+              const uint32_t a0 = a_addr + (uint32_t)((STRIDE == 1 ? t : 0) * ROW_BYTES);
+              umma_chunk<1, MT>(tmem_base, tmem_base + (uint32_t)BN, make_desc_sw128(a0), make_desc_sw128(a0 + (uint32_t)(SUB_ROWS * ROW_BYTES)),
+                                make_desc_sw128(smem_u32(smem + SL::B_OFF + sb * SL::B_BYTES)), idesc, (c | l | t) ? 1u : 0u, &b_empty[sb]);
             }
             __syncwarp();
           }
-          if (lane == 0) {
-            umma_commit(&a_empty[sa]);
-            if (c == chunks - 1 && l == NL - 1) umma_commit(acc_full);
-          }
+          umma_commit(&a_empty[sa]);
+          if (c == chunks - 1 && l == NL - 1) umma_commit(acc_full);
           __syncwarp();
         }
       }

@@ -195,22 +195,24 @@ extern "C" int isf_debug_gather_bench(const void* a, int rows, int cols, const i
 // Micro-benchmark (NOT on the product path): issue rate of tcgen05.mma kind::f16 by instruction shape and operand source.
 // One thread per CTA (per CTA pair for cta_group::2) issues `iters` groups of four K = 16 instructions of shape m x n on constant
 // (zero) shared-memory operands, four groups in flight (tcgen05.commit ring); nothing else runs.  out[block] = cycles per
-// instruction as seen by that CTA.  a_tmem = 1: the A operand comes from tensor memory (TS mode) instead of shared memory.
+// instruction as seen by that CTA.  a_tmem = 1: the A operand comes from tensor memory (TS mode) instead of shared memory;
+// chains = independent accumulators the instructions of one issuing thread alternate between; issuers = warps of the CTA that
+// each issue their own stream (own accumulators, own commit ring).  TMEM columns allocated = what that needs (128 / 256 / 512).
 // With probe != 0 (one CTA, m x 32 x 16, cta_group::1) it runs ONE instruction on A[i][0] = i + 1, B[j][0] = 1 and dumps TMEM
 // column 0 of all 128 lanes: the accumulator layout of the shape (out_probe[lane] = D value held by that lane).
 // ------------------------------------------------------------------------------------------------
 #include "tc_gemm5.cuh"
 
-template <int CG>
-__global__ void __launch_bounds__(128) mma_rate_kernel(int m, int n, int a_tmem, int iters, float* __restrict__ out,
-                                                       float* __restrict__ out_probe) {
+template <int CG, int COLS>
+__global__ void __launch_bounds__(128) mma_rate_kernel(int m, int n, int a_tmem, int chains, int issuers, int iters,
+                                                       float* __restrict__ out, float* __restrict__ out_probe) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
   uint8_t* sa = smem;                  // 256 rows x 128 B
   uint8_t* sb = smem + 32768;          // 256 rows x 128 B
-  uint64_t* bar = (uint64_t*)(smem + 65536);      // [4]
-  uint32_t* slot = (uint32_t*)(bar + 4);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  uint64_t* bar = (uint64_t*)(smem + 65536);      // [4 issuers][4]
+  uint32_t* slot = (uint32_t*)(bar + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool probe = out_probe != nullptr;
   for (int e = tid; e < 65536 / 16; e += 128) ((uint4*)smem)[e] = make_uint4(0, 0, 0, 0);
   __syncthreads();
@@ -222,11 +224,11 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int m, int n, int a_tmem,
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) tc::mbar_init(&bar[s], 1);
+    for (int s = 0; s < 16; ++s) tc::mbar_init(&bar[s], 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) {
-    if constexpr (CG == 2) tc::tmem_alloc2<256>(slot); else tc::tmem_alloc<256>(slot);
+    if constexpr (CG == 2) tc::tmem_alloc2<COLS>(slot); else tc::tmem_alloc<COLS>(slot);
   }
   tc::fence_proxy_async();
   tc::tc_fence_before();
@@ -234,34 +236,101 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int m, int n, int a_tmem,
   tc::tc_fence_after();
   const uint32_t tmem = *slot;
   const bool leader = CG == 1 || tc::cluster_ctarank() == 0;
-  if (tid == 0 && leader) {
+  // warp w < issuers issues its own instruction stream into its own accumulators (columns [(w chains + c) n, + n)): lane 0 inside
+  // `if (lane == 0)` (the library's MMA warps), or - a_tmem bit 1 - the whole warp converged with the instruction predicated by
+  // elect.sync (no per-instruction ELECT / BRA.U.ANY loop in the SASS)
+  const bool elect_mode = (a_tmem & 6) != 0, group_mode = (a_tmem & 4) != 0;
+  a_tmem &= 1;
+  if (elect_mode && warp < issuers && leader) {
+    uint64_t* mybar = bar + 4 * warp;
     const uint32_t idesc = tc::make_idesc_f16(CG * m, n);
     const uint64_t a_desc = tc::make_desc_sw128(tc::smem_u32(sa)), b_desc = tc::make_desc_sw128(tc::smem_u32(sb));
-    const uint32_t a_t = tmem + 128;      // TS mode: A at columns [128, 160) (n <= 128 then)
+    const uint32_t d_t = tmem + (uint32_t)(warp * n);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int s = i & 3;
+      if (i >= 4) tc::mbar_wait_b(&mybar[s], (uint32_t)((i - 4) >> 2) & 1);
+      if (group_mode) {      // one election per group of four instructions + commit (tc::umma_chunk: what the library issues)
+        tc::umma_chunk<CG, 1>(d_t, d_t, a_desc, a_desc, b_desc, idesc, 1u, &mybar[s], 1);
+        continue;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if constexpr (CG == 2)
+          asm volatile(
+              "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+              "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, 1;\n\t}" ::"r"(d_t),
+              "l"(a_desc + (uint64_t)(kk * 2)), "l"(b_desc + (uint64_t)(kk * 2)), "r"(idesc)
+              : "memory");
+        else
+          asm volatile(
+              "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+              "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;\n\t}" ::"r"(d_t),
+              "l"(a_desc + (uint64_t)(kk * 2)), "l"(b_desc + (uint64_t)(kk * 2)), "r"(idesc)
+              : "memory");
+      }
+      if constexpr (CG == 2)
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+                tc::smem_u32(&mybar[s])),
+            "h"((uint16_t)1)
+            : "memory");
+      else
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(tc::smem_u32(&mybar[s]))
+            : "memory");
+    }
+    for (int i = (iters > 4 ? iters - 4 : 0); i < iters; ++i) tc::mbar_wait_b(&mybar[i & 3], (uint32_t)(i >> 2) & 1);
+    const long long t1 = clock64();
+    if (warp == 0 && lane == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)(iters * 4);
+  } else if (lane == 0 && warp < issuers && leader) {
+    uint64_t* mybar = bar + 4 * warp;
+    const uint32_t idesc = tc::make_idesc_f16(CG * m, n);
+    const uint64_t a_desc = tc::make_desc_sw128(tc::smem_u32(sa)), b_desc = tc::make_desc_sw128(tc::smem_u32(sb));
+    const uint32_t a_t = tmem + (uint32_t)(COLS - 32);      // TS mode: A in the last 32 columns
     const int groups = probe ? 1 : iters;
     const long long t0 = clock64();
     for (int i = 0; i < groups; ++i) {
       const int s = i & 3;
-      if (i >= 4) tc::mbar_wait_b(&bar[s], (uint32_t)((i - 4) >> 2) & 1);
-      for (int kk = 0; kk < (probe ? 1 : 4); ++kk) {
-        const uint32_t acc = (probe && kk == 0) ? 0u : 1u;
-        if (a_tmem) {
-          asm volatile(
-              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-              "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem),
-              "r"(a_t + (uint32_t)(kk * 8)), "l"(b_desc + (uint64_t)(kk * 2)), "r"(idesc), "r"(acc)
-              : "memory");
-        } else if constexpr (CG == 2) {
-          tc::umma_f16_2cta(tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, acc);
-        } else {
-          tc::umma_f16(tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, acc);
+      if (i >= 4) tc::mbar_wait_b(&mybar[s], (uint32_t)((i - 4) >> 2) & 1);
+      for (int kk = 0; kk < (probe ? 1 : 4); ++kk)
+        for (int c = 0; c < chains; ++c) {
+          const uint32_t d_t = tmem + (uint32_t)((warp * chains + c) * n);
+          const uint32_t acc = (probe && kk == 0) ? 0u : 1u;
+          if (a_tmem) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_t),
+                "r"(a_t + (uint32_t)(kk * 8)), "l"(b_desc + (uint64_t)(kk * 2)), "r"(idesc), "r"(acc)
+                : "memory");
+          } else if constexpr (CG == 2) {      // the un-elected issue form the library used before call 20 (single active lane)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_t),
+                "l"(a_desc + (uint64_t)(kk * 2)), "l"(b_desc + (uint64_t)(kk * 2)), "r"(idesc), "r"(acc)
+                : "memory");
+          } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_t),
+                "l"(a_desc + (uint64_t)(kk * 2)), "l"(b_desc + (uint64_t)(kk * 2)), "r"(idesc), "r"(acc)
+                : "memory");
+          }
         }
-      }
-      if constexpr (CG == 2) tc::umma_commit2_mcast(&bar[s], 1); else tc::umma_commit(&bar[s]);
+      if constexpr (CG == 2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         tc::smem_u32(&mybar[s])),
+                     "h"((uint16_t)1)
+                     : "memory");
+      else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(&mybar[s]))
+                     : "memory");
     }
-    for (int i = (groups > 4 ? groups - 4 : 0); i < groups; ++i) tc::mbar_wait_b(&bar[i & 3], (uint32_t)(i >> 2) & 1);
+    for (int i = (groups > 4 ? groups - 4 : 0); i < groups; ++i) tc::mbar_wait_b(&mybar[i & 3], (uint32_t)(i >> 2) & 1);
     const long long t1 = clock64();
-    out[blockIdx.x] = (float)(t1 - t0) / (float)(groups * 4);
+    if (warp == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)(groups * 4 * (probe ? 1 : chains));
   }
   tc::tc_fence_before();
   if constexpr (CG == 2) tc::cluster_sync_all(); else __syncthreads();
@@ -276,19 +345,24 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int m, int n, int a_tmem,
   tc::tc_fence_before();
   if constexpr (CG == 2) tc::cluster_sync_all(); else __syncthreads();
   if (warp == 0) {
-    if constexpr (CG == 2) tc::tmem_dealloc2<256>(tmem); else tc::tmem_dealloc<256>(tmem);
+    if constexpr (CG == 2) tc::tmem_dealloc2<COLS>(tmem); else tc::tmem_dealloc<COLS>(tmem);
   }
 }
 
-extern "C" int isf_debug_mma_rate(int m, int n, int cta_group, int a_tmem, int blocks, int iters, float* out_cycles,
-                                  float* out_probe, void* stream) {
+extern "C" int isf_debug_mma_rate(int m, int n, int cta_group, int a_tmem, int chains, int issuers, int blocks, int iters,
+                                  float* out_cycles, float* out_probe, void* stream) {
+  const int need = chains * issuers * n + ((a_tmem & 1) ? 32 : 0);
   ISF_CHECK_ARG(out_cycles && (m == 64 || m == 128) && n >= 16 && n <= 256 && n % 16 == 0 && (cta_group == 1 || cta_group == 2) &&
-                blocks >= 1 && iters >= 1 && (!a_tmem || (cta_group == 1 && n <= 128)) && (!out_probe || (cta_group == 1 && blocks == 1)));
+                chains >= 1 && issuers >= 1 && issuers <= 4 && need <= 512 && blocks >= 1 && iters >= 1 && (!(a_tmem & 1) || cta_group == 1) &&
+                (!(a_tmem & 6) || (chains == 1 && !(a_tmem & 1) && !out_probe)) &&
+                (!out_probe || (cta_group == 1 && blocks == 1)));
   cudaStream_t st = (cudaStream_t)stream;
   const int smem = 65536 + 1024 + 256;
+  const int cols = need <= 128 ? 128 : (need <= 256 ? 256 : 512);      // TMEM columns per CTA: bounds the CTAs per SM
   if (cta_group == 2) {
     ISF_CHECK_ARG(blocks % 2 == 0);
-    ISF_CUDA(cudaFuncSetAttribute(mma_rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto kern = cols == 128 ? mma_rate_kernel<2, 128> : (cols == 256 ? mma_rate_kernel<2, 256> : mma_rate_kernel<2, 512>);
+    ISF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(blocks);
@@ -302,10 +376,11 @@ extern "C" int isf_debug_mma_rate(int m, int n, int cta_group, int a_tmem, int b
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    ISF_CUDA(cudaLaunchKernelEx(&cfg, mma_rate_kernel<2>, m, n, a_tmem, iters, out_cycles, out_probe));
+    ISF_CUDA(cudaLaunchKernelEx(&cfg, kern, m, n, a_tmem, chains, issuers, iters, out_cycles, out_probe));
   } else {
-    ISF_CUDA(cudaFuncSetAttribute(mma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mma_rate_kernel<1><<<blocks, 128, smem, st>>>(m, n, a_tmem, iters, out_cycles, out_probe);
+    auto kern = cols == 128 ? mma_rate_kernel<1, 128> : (cols == 256 ? mma_rate_kernel<1, 256> : mma_rate_kernel<1, 512>);
+    ISF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<blocks, 128, smem, st>>>(m, n, a_tmem, chains, issuers, iters, out_cycles, out_probe);
   }
   ISF_LAUNCH_CHECK();
   return ISF_OK;

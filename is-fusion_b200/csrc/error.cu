@@ -32,7 +32,7 @@ int g_isf_gemm_mt = 3;
 int g_isf_gemm_zskip = 0;
 int g_isf_gemm_wpc = 0;
 int g_isf_gemm_rev = 0;
-int g_isf_gemm_pair = 0;
+int g_isf_gemm_pair = 128;
 int g_isf_gemm_v4_32 = 1;
 int g_isf_gemm_v4 = 2;
 int g_isf_gemm_ln_fast = 1;

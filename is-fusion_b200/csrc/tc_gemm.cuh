@@ -87,19 +87,80 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::f16, fp32 accumulate)
+// D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::f16, fp32 accumulate).
+// ISSUE FORM (round 2, scripts/bench_mma_rate.py, profiles/call20_r02.log): these wrappers are called by ALL 32 lanes of a
+// converged warp and predicate the instruction with elect.sync.  Inside `if (lane == 0) { ... }` the compiler wraps every UTCHMMA
+// in an ELECT / BRA.U.ANY loop and a thread then issues ONE instruction per ~179 cycles whatever its shape (128 x 32 ... 256 x 256);
+// in the elected form the same thread issues one per 86 cycles and the tensor pipe runs at its nominal 128 N / 256 cycles per
+// instruction (N = 256: 128.0 cycles measured).  elect.sync with a full mask always elects the same lane, so tcgen05.commit (which
+// tracks the MMAs of the executing thread) sees the instructions it must wait for.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+// One K chunk (BK = 64 = four K = 16 steps) of MT (1 | 2) sub-tiles behind ONE elect.sync: the 4 MT instructions (K step outermost,
+// sub-tiles alternating) and the tcgen05.commit that releases the shared-memory stage.  Per-instruction election costs ~86 cycles
+// of issue per instruction (bench_mma_rate.py), more than the 64 cycles a 128 x 128 instruction occupies the tensor pipe.
+// CG = cta_group (2: the commit is multicast to the CTAs of `mask`).  Whole warp, converged.
+template <int CG, int MT>
+__device__ __forceinline__ void umma_chunk(uint32_t d0, uint32_t d1, uint64_t a0, uint64_t a1, uint64_t b, uint32_t idesc,
+                                           uint32_t acc_first, uint64_t* commit_bar, uint16_t mask = 3) {
+  static_assert((CG == 1 || CG == 2) && (MT == 1 || MT == 2), "umma_chunk");
+#define ISF_MMA1 "@pe tcgen05.mma.cta_group::1.kind::f16 "
+#define ISF_MMA2 "@pe tcgen05.mma.cta_group::2.kind::f16 "
+#define ISF_CHUNK_HEAD                                                                              \
+  "{\n\t.reg .pred pe, p0;\n\t.reg .b64 x1, x2, x3, y1, y2, y3, b1, b2, b3;\n\t"                  \
+  "elect.sync _|pe, 0xffffffff;\n\t"                                                                \
+  "setp.ne.b32 p0, %6, 0;\n\t"                                                                      \
+  "add.u64 x1, %2, 2;\n\tadd.u64 x2, %2, 4;\n\tadd.u64 x3, %2, 6;\n\t"                             \
+  "add.u64 y1, %3, 2;\n\tadd.u64 y2, %3, 4;\n\tadd.u64 y3, %3, 6;\n\t"                             \
+  "add.u64 b1, %4, 2;\n\tadd.u64 b2, %4, 4;\n\tadd.u64 b3, %4, 6;\n\t"
+#define ISF_CHUNK_ARGS                                                                              \
+  ::"r"(d0), "r"(d1), "l"(a0), "l"(a1), "l"(b), "r"(idesc), "r"(acc_first), "r"(smem_u32(commit_bar)), "h"(mask) : "memory"
+  if constexpr (CG == 1 && MT == 1)
+    asm volatile(ISF_CHUNK_HEAD
+                 ISF_MMA1 "[%0], %2, %4, %5, p0;\n\t" ISF_MMA1 "[%0], x1, b1, %5, 1;\n\t"
+                 ISF_MMA1 "[%0], x2, b2, %5, 1;\n\t" ISF_MMA1 "[%0], x3, b3, %5, 1;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}" ISF_CHUNK_ARGS);
+  else if constexpr (CG == 1 && MT == 2)
+    asm volatile(ISF_CHUNK_HEAD
+                 ISF_MMA1 "[%0], %2, %4, %5, p0;\n\t" ISF_MMA1 "[%1], %3, %4, %5, p0;\n\t"
+                 ISF_MMA1 "[%0], x1, b1, %5, 1;\n\t" ISF_MMA1 "[%1], y1, b1, %5, 1;\n\t"
+                 ISF_MMA1 "[%0], x2, b2, %5, 1;\n\t" ISF_MMA1 "[%1], y2, b2, %5, 1;\n\t"
+                 ISF_MMA1 "[%0], x3, b3, %5, 1;\n\t" ISF_MMA1 "[%1], y3, b3, %5, 1;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}" ISF_CHUNK_ARGS);
+  else if constexpr (CG == 2 && MT == 1)
+    asm volatile(ISF_CHUNK_HEAD
+                 ISF_MMA2 "[%0], %2, %4, %5, p0;\n\t" ISF_MMA2 "[%0], x1, b1, %5, 1;\n\t"
+                 ISF_MMA2 "[%0], x2, b2, %5, 1;\n\t" ISF_MMA2 "[%0], x3, b3, %5, 1;\n\t"
+                 "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %8;\n\t}"
+                 ISF_CHUNK_ARGS);
+  else
+    asm volatile(ISF_CHUNK_HEAD
+                 ISF_MMA2 "[%0], %2, %4, %5, p0;\n\t" ISF_MMA2 "[%1], %3, %4, %5, p0;\n\t"
+                 ISF_MMA2 "[%0], x1, b1, %5, 1;\n\t" ISF_MMA2 "[%1], y1, b1, %5, 1;\n\t"
+                 ISF_MMA2 "[%0], x2, b2, %5, 1;\n\t" ISF_MMA2 "[%1], y2, b2, %5, 1;\n\t"
+                 ISF_MMA2 "[%0], x3, b3, %5, 1;\n\t" ISF_MMA2 "[%1], y3, b3, %5, 1;\n\t"
+                 "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %8;\n\t}"
+                 ISF_CHUNK_ARGS);
+#undef ISF_MMA1
+#undef ISF_MMA2
+#undef ISF_CHUNK_HEAD
+#undef ISF_CHUNK_ARGS
 }
 
 // ---- thread-block-cluster helpers (weight-chunk multicast)
@@ -130,11 +191,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
       "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {      // whole warp, elected lane (see umma_f16)
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
 }
 
 // 32 lanes x 32 columns of fp32: thread i of the warp receives lane (base_lane + i), columns col..col+31
@@ -751,20 +815,25 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
         mbar_wait_b(&full_bar[s], (cc / STAGES) & 1);
         fence_proxy_async();     // cp.async (generic proxy) writes of the producers -> visible to the tensor core
         tc_fence_after();
-        if (lane == 0) {
+        {      // whole warp, converged: the wrappers elect the issuing lane
           const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
           const uint32_t b_addr = a_addr + SL::A_BYTES;
           const uint64_t b_desc = make_desc_sw128(b_addr);
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t a_desc = make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128));
+          if constexpr (CS == 1) {
+            umma_chunk<1, MT>(tmem_base, tmem_base + (uint32_t)BN, make_desc_sw128(a_addr), make_desc_sw128(a_addr + (uint32_t)(BM * 128)),
+                              b_desc, idesc, q ? 1u : 0u, &empty_bar[s]);
+          } else {
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
-              // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
-              umma_f16(tmem_base + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the >>4 address field
+                umma_f16(tmem_base + (uint32_t)(mt * BN), make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128)) + (uint64_t)(kk * 2),
+                         b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
+              }
             }
+            umma_commit_mcast(&empty_bar[s], CMASK);
           }
-          if constexpr (CS == 1) umma_commit(&empty_bar[s]); else umma_commit_mcast(&empty_bar[s], CMASK);
           if (q == n_act - 1) umma_commit(accum_bar);
         }
         __syncwarp();

@@ -300,19 +300,10 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
         mbar_wait_b(&full_bar[s], (ca / STAGES) & 1);
         fence_proxy_async();     // cp.async (generic proxy) writes of the producers -> visible to the tensor core
         tc_fence_after();
-        if (lane == 0) {
+        {      // whole warp, converged: one election per chunk (umma_chunk, tc_gemm.cuh); sub-tiles alternate per K step
           const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
-          const uint64_t b_desc = make_desc_sw128(a_addr + SL::A_BYTES);
-          // K step outermost, sub-tiles innermost: consecutive instructions go to DIFFERENT accumulators.  An accumulator chain
-          // retires one instruction per ~179 cycles whatever its shape (scripts/bench_mma_rate.py, call 20), so the issue rate
-          // is (independent chains) x (columns per instruction) / 179: interleaving doubles it for MT = 2.
-#pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              umma_f16(d_tmem + (uint32_t)(mt * BN), make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128)) + (uint64_t)(kk * 2),
-                       b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          umma_chunk<1, MT>(d_tmem, d_tmem + (uint32_t)BN, make_desc_sw128(a_addr), make_desc_sw128(a_addr + (uint32_t)(BM * 128)),
+                            make_desc_sw128(a_addr + SL::A_BYTES), idesc, q ? 1u : 0u, &empty_bar[s]);
           if (q == n_act - 1) umma_commit(&acc_full[buf]);
         }
         __syncwarp();

@@ -51,20 +51,25 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
+// whole warp, converged; the elected lane issues (see umma_f16 in tc_gemm.cuh)
 __device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit2_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
 }
 
 template <int BN, int STAGES, int MT = 1>
@@ -277,16 +282,10 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
           mbar_wait_b(&peer_full[s], par);
           fence_proxy_async();
           tc_fence_after();
-          if (lane == 0) {
+          {      // whole warp, converged: one election per chunk (umma_chunk, tc_gemm.cuh)
             const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
-            const uint64_t b_desc = make_desc_sw128(a_addr + SL::A_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)       // K step outermost: consecutive instructions alternate accumulators (tc_gemm4.cuh)
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt)
-                umma_f16_2cta(d_tmem + (uint32_t)(mt * BN), make_desc_sw128(a_addr + (uint32_t)(mt * BM * 128)) + (uint64_t)(kk * 2),
-                              b_desc + (uint64_t)(kk * 2), idesc, (q | kk) ? 1u : 0u);
-            umma_commit2_mcast(&empty_bar[s], 3);
+            umma_chunk<2, MT>(d_tmem, d_tmem + (uint32_t)BN, make_desc_sw128(a_addr), make_desc_sw128(a_addr + (uint32_t)(BM * 128)),
+                              make_desc_sw128(a_addr + SL::A_BYTES), idesc, q ? 1u : 0u, &empty_bar[s], 3);
             if (q == n_act - 1) umma_commit2_mcast(&acc_full[buf], 3);
           }
           __syncwarp();
@@ -451,12 +450,14 @@ static inline bool gemm5_supported(const GemmParams& p, int bn, int m_upper) {
 }
 
 static inline int dispatch_gemm5(const GemmParams& p, int bn, int m_upper, cudaStream_t st) {
+  // ONE CTA per SM in every configuration (256-row CTA tiles for the 64- / 128-column layers): two pairs per TPC each allocating
+  // tensor memory with cta_group::2 is a situation no vendor kernel creates, and the one hung bench run of call 21 had it
+  // (gemm_mt = 1 selects those two-CTAs-per-SM configurations for A/B runs).
+  const bool two = ::g_isf_gemm_mt == 1;
   switch (bn) {
-    case 64:
-      if (::g_isf_gemm_mt >= 2 && m_upper >= 2 * 148 * 512) return launch_gemm5<64, 2, 2, 2>(p, m_upper, st);   // 2 x 36 KB + 27 KB
-      return launch_gemm5<64, 4, 2>(p, m_upper, st);         // 4 x 20 KB + 14 KB, 2 CTAs / SM
-    case 128: return launch_gemm5<128, 4, 2>(p, m_upper, st);   // 4 x 24 KB + 14 KB, 2 CTAs / SM
-    case 256: return launch_gemm5<256, 6, 1>(p, m_upper, st);   // 6 x 32 KB + 14 KB, all 512 TMEM columns
+    case 64: return two ? launch_gemm5<64, 4, 2, 1>(p, m_upper, st) : launch_gemm5<64, 4, 1, 2>(p, m_upper, st);      // 4 x 36 KB + 27 KB
+    case 128: return two ? launch_gemm5<128, 4, 2, 1>(p, m_upper, st) : launch_gemm5<128, 4, 1, 2>(p, m_upper, st);   // 4 x 40 KB + 27 KB
+    case 256: return launch_gemm5<256, 6, 1, 1>(p, m_upper, st);   // 6 x 32 KB + 14 KB, all 512 TMEM columns
     default: isf_set_error("gemm v5: unsupported column tile %d", bn); return ISF_ERR_UNSUPPORTED;
   }
 }

@@ -11,9 +11,9 @@ import torch  # noqa: E402
 from isfusion_b200 import _lib as L  # noqa: E402
 
 
-def rate(m, n, cg, a_tmem, blocks, iters=4000):
+def rate(m, n, cg, a_tmem, blocks, chains=1, issuers=1, iters=4000):
     out = torch.zeros(blocks, device='cuda')
-    L.check(L.lib().isf_debug_mma_rate(m, n, cg, a_tmem, blocks, iters, L.ptr(out), None, L.stream()))
+    L.check(L.lib().isf_debug_mma_rate(m, n, cg, a_tmem, chains, issuers, blocks, iters, L.ptr(out), None, L.stream()))
     torch.cuda.synchronize()
     v = out[out > 0]
     return v.mean().item(), v.min().item(), v.max().item()
@@ -22,31 +22,46 @@ def rate(m, n, cg, a_tmem, blocks, iters=4000):
 def main():
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     mhz = 1965.0
-    print('%-42s %9s %9s %9s %12s' % ('variant', 'cyc/instr', 'min', 'max', 'chip TFLOP/s'))
-    cases = []
+    print('%-64s %9s %9s %9s %12s' % ('variant', 'cyc/instr', 'min', 'max', 'chip TFLOP/s'))
+    cases = []      # (m, n, cta_group, a_tmem, chains, issuers, CTAs per SM)
     for n in (32, 64, 128, 256):
-        cases.append(('M=128 N=%d SS cta_group::1, 1 CTA/SM' % n, 128, n, 1, 0, sms))
-    for n in (64, 128):
-        cases.append(('M=128 N=%d SS cta_group::1, 2 CTAs/SM' % n, 128, n, 1, 0, 2 * sms))
-    for n in (64, 128, 256):
-        cases.append(('M=64  N=%d SS cta_group::1, 1 CTA/SM' % n, 64, n, 1, 0, sms))
-    for n in (64, 128, 256):
-        cases.append(('M=256 N=%d SS cta_group::2, 1 pair / 2 SMs' % n, 128, n, 2, 0, sms - sms % 2))
-    for n in (32, 64, 128):
-        cases.append(('M=128 N=%d TS (A in TMEM), 1 CTA/SM' % n, 128, n, 1, 1, sms))
-    for name, m, n, cg, at, blocks in cases:
+        cases.append((128, n, 1, 0, 1, 1, 1))
+    for n, ch in ((256, 2), (128, 2), (128, 4), (64, 4), (64, 8)):
+        cases.append((128, n, 1, 0, ch, 1, 1))
+    for n, iss in ((256, 2), (128, 2), (128, 4), (64, 2), (64, 4), (32, 4)):
+        cases.append((128, n, 1, 0, 1, iss, 1))
+    for n, ctas in ((256, 2), (128, 2), (128, 3), (128, 4), (64, 4)):
+        cases.append((128, n, 1, 0, 1, 1, ctas))
+    cases += [(128, 128, 1, 0, 1, 2, 2), (128, 64, 1, 0, 1, 4, 2)]
+    cases += [(64, 256, 1, 0, 1, 1, 1), (64, 256, 1, 0, 1, 2, 1)]
+    cases += [(128, 256, 2, 0, 1, 1, 1), (128, 256, 2, 0, 1, 2, 1), (128, 128, 2, 0, 1, 2, 1), (128, 128, 2, 0, 1, 1, 2)]
+    cases += [(128, 128, 1, 1, 1, 1, 1), (128, 128, 1, 1, 1, 2, 1), (128, 64, 1, 1, 1, 4, 1)]
+    # a_tmem = 2: whole warp converged, instruction predicated by elect.sync
+    for n in (32, 64, 128, 256):
+        cases.append((128, n, 1, 2, 1, 1, 1))
+    cases += [(128, 128, 1, 2, 1, 2, 1), (128, 64, 1, 2, 1, 4, 1), (128, 128, 1, 2, 1, 1, 2), (128, 256, 1, 2, 1, 2, 1),
+              (128, 256, 2, 2, 1, 1, 1), (128, 128, 2, 2, 1, 1, 2), (64, 256, 1, 2, 1, 1, 1)]
+    # a_tmem = 4: one elect.sync per group of four instructions + commit (tc::umma_chunk)
+    for n in (32, 64, 128, 256):
+        cases.append((128, n, 1, 4, 1, 1, 1))
+    cases += [(128, 128, 1, 4, 1, 2, 1), (128, 64, 1, 4, 1, 4, 1), (128, 64, 1, 4, 1, 2, 2), (128, 128, 1, 4, 1, 1, 2), (128, 256, 2, 4, 1, 1, 1),
+              (128, 128, 2, 4, 1, 1, 2), (128, 64, 2, 4, 1, 1, 2)]
+    for m, n, cg, at, ch, iss, ctas in cases:
+        name = 'M=%d N=%d %s cta_group::%d, %d chain(s) x %d issuer(s), %d CTA(s)/SM' % (cg * m, n, {0: 'SS', 1: 'TS', 2: 'SS elect', 4: 'SS elect/4'}[at], cg, ch, iss, ctas)
+        blocks = sms * ctas
+        blocks -= blocks % cg
         try:
-            mean, lo, hi = rate(m, n, cg, at, blocks)
+            mean, lo, hi = rate(m, n, cg, at, blocks, ch, iss)
         except Exception as e:      # noqa: BLE001
-            print('%-42s failed: %s' % (name, str(e)[:80]))
+            print('%-64s failed: %s' % (name, str(e)[:80]))
             continue
-        issuers = blocks / cg
+        streams = blocks / cg * iss
         flops = 2.0 * (cg * m) * n * 16
-        print('%-42s %9.1f %9.1f %9.1f %12.0f' % (name, mean, lo, hi, flops * issuers / mean * mhz * 1e6 / 1e12))
+        print('%-64s %9.1f %9.1f %9.1f %12.0f' % (name, mean, lo, hi, flops * streams / mean * mhz * 1e6 / 1e12))
     for m in (64, 128):
         out = torch.zeros(1, device='cuda')
         probe = torch.full((256,), -1.0, device='cuda')
-        L.check(L.lib().isf_debug_mma_rate(m, 32, 1, 0, 1, 1, L.ptr(out), L.ptr(probe), L.stream()))
+        L.check(L.lib().isf_debug_mma_rate(m, 32, 1, 0, 1, 1, 1, 1, L.ptr(out), L.ptr(probe), L.stream()))
         torch.cuda.synchronize()
         p = probe.cpu().tolist()
         print('accumulator layout M=%d: TMEM lane -> row + 1 (column 0): %s' % (m, ' '.join('%d' % int(x) for x in p[:128])))
