@@ -404,6 +404,21 @@ int isf_channel_attention_workspace_size(int batch, int grid, int channels, size
 int isf_channel_attention(const void* scene, int lds, const void* ins, int ldi, int batch, int grid, int channels,
                           void* out, int ldo, void* workspace, size_t ws_bytes, void* stream);
 
+/* bf16 twins of the dense tensor-core entry points of the Hierarchical-Scene-Fusion path (BASELINE configs[2] names a bf16
+ * tensor-core path; reference: the same modules as their f16 siblings, run under torch autocast(bfloat16) semantics): identical
+ * arguments, every 16-bit tensor (operands, residual, output) is bf16 instead of fp16, accumulation / epilogue / softmax are fp32. */
+int isf_gemm_bf16(const void* A, const void* W, int m, int k, int kpad, int n, const float* scale, const float* shift,
+                  const void* residual, int ldr, int act, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                  void* out_bf16, float* out_f32, int ldo, const int* out_rows, const int* m_dev, void* stream);
+int isf_conv3x3_nhwc_bf16(const void* x, int batch, int h, int w, int cin, int ldx, const void* w_packed, int cout_pad,
+                          const float* shift, int stride, int relu, void* out, int ldo, int cout_store, void* stream);
+int isf_window_attention_bf16(const void* qkv, const float* pos_q, const float* pos_k, int batch, int grid, int channels,
+                              int heads, int shifted, void* out, void* stream);
+int isf_cam2bev_bf16(const float* pillars, int num_pillars, const int* num_pillars_dev, int points_per_pillar, int nfeat,
+                     const int* pillar_coors, int coors_dim, int batch_index, const void* img_feat_nhwc, const float* proj_dev,
+                     int batch, int ncam, int fh, int fw, int channels, float img_w, float img_h, int bev_h, int bev_w,
+                     void* out_nhwc, int ldo, int ch_off, void* stream);
+
 /* bring-up probe (NOT on the product path): TMA tile::gather4 of 128 rows x 64 fp16 columns into shared memory, raw
  * shared memory (32 KiB) returned in out32k, *status_dev = 1 when the transaction completed (csrc/debug_tma.cu). */
 int isf_debug_tma_gather4(const void* a, int rows, int cols, const int* idx_dev, int col0, int variant, void* out32k,

@@ -91,6 +91,28 @@ def launch_count(reset=False):
     return int(lib().isf_launch_count(1 if reset else 0))
 
 
+# 16-bit element type of the Hierarchical-Scene-Fusion path (camera -> BEV, conv_fusion, the SST levels): fp16 (default; what meets
+# north_star's 1e-3) or bf16 (BASELINE configs[2]; the `_bf16` entry points: same kernels, bf16 encodings).  Set it BEFORE the first
+# forward: the modules cache their packed weights in this type.
+DTYPE = torch.float16
+
+
+def set_dtype(dtype):
+    global DTYPE
+    if dtype not in (torch.float16, torch.bfloat16):
+        raise IsfError('set_dtype: torch.float16 or torch.bfloat16')
+    DTYPE = dtype
+
+
+def fn16(name, dtype):
+    """entry point `name` (an `..._f16` / untyped symbol) for 16-bit tensors of `dtype`."""
+    if dtype == torch.float16:
+        return getattr(lib(), name)
+    if dtype != torch.bfloat16:
+        raise IsfError('%s: fp16 or bf16 tensors expected, got %s' % (name, dtype))
+    return getattr(lib(), name[:-4] + '_bf16' if name.endswith('_f16') else name + '_bf16')
+
+
 def set_option(name, value):
     """runtime options of the library (isf_set_option), e.g. set_option('gemm_cluster', 4)."""
     check(lib().isf_set_option(name.encode(), int(value)))

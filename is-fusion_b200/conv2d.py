@@ -67,8 +67,8 @@ def pack_dense_weight(w, bias):
         return None
     k = 9 * cin
     kpad = (k + 63) // 64 * 64
-    wp = torch.zeros((cpad, kpad), dtype=torch.float16, device=w.device)
-    wp[:cout, :k] = w.permute(0, 2, 3, 1).reshape(cout, k).half()
+    wp = torch.zeros((cpad, kpad), dtype=w.dtype if w.dtype == torch.bfloat16 else torch.float16, device=w.device)
+    wp[:cout, :k] = w.permute(0, 2, 3, 1).reshape(cout, k).to(wp.dtype)
     shift = torch.zeros(cpad, dtype=torch.float32, device=w.device)
     if bias is not None:
         shift[:cout] = bias.float()
@@ -154,12 +154,12 @@ def conv3x3_tma(x_nhwc, packed, stride=1, relu=True):
     if ent is None:
         return None
     wp, shift, cpad = ent
-    x = x_nhwc if (x_nhwc.is_contiguous() and x_nhwc.dtype == torch.float16) else x_nhwc.half().contiguous()
+    x = x_nhwc if (x_nhwc.is_contiguous() and x_nhwc.dtype == wp.dtype) else x_nhwc.to(wp.dtype).contiguous()
     L.require_cuda(x, wp, shift)
     oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
     ldo = (cout + 7) // 8 * 8
-    out = torch.empty((bs, oh, ow, ldo), dtype=torch.float16, device=x.device)
-    L.check(L.lib().isf_conv3x3_nhwc_f16(L.ptr(x), bs, h, wd, cin, cin, L.ptr(wp), cpad, L.ptr(shift), stride, 1 if relu else 0,
+    out = torch.empty((bs, oh, ow, ldo), dtype=wp.dtype, device=x.device)
+    L.check(L.fn16('isf_conv3x3_nhwc_f16', wp.dtype)(L.ptr(x), bs, h, wd, cin, cin, L.ptr(wp), cpad, L.ptr(shift), stride, 1 if relu else 0,
                                          L.ptr(out), ldo, ldo, L.stream()))
     return out if ldo == cout else out[..., :cout]
 

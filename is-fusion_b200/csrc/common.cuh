@@ -88,3 +88,20 @@ extern int g_isf_gemm_zskip;      // isf_set_option("gemm_zskip", 0|1): zero-ski
 extern int g_isf_gemm_mt;         // isf_set_option("gemm_mt", 1|2): 128-row sub-tiles per CTA tile of the sparse-conv GEMM
 extern int g_isf_gemm_debug;      // isf_set_option("gemm_debug", bits): timing experiments (tc_gemm.cuh GemmParams::debug)
 extern int g_isf_nbr_rows;        // isf_set_option("nbr_rows", 0|1): row-per-thread neighbour-table kernel (opt-in)
+
+// ---- 16-bit element type of the dense tensor-core entry points (BASELINE configs[2] names a bf16 path): the `_bf16` entry points
+// (isf_gemm_bf16, isf_conv3x3_nhwc_bf16, isf_window_attention_bf16, isf_cam2bev_bf16) run the SAME kernels with bf16 operand /
+// output encoding (tcgen05 kind::f16 takes either format at the same rate; accumulation, epilogue and softmax stay fp32).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+int isf_bf16_mode();                       // error.cu: 1 inside a `_bf16` entry point of this thread
+struct IsfBf16Scope { IsfBf16Scope(); ~IsfBf16Scope(); };
+__device__ __forceinline__ float2 isf_unpack2(unsigned int w, bool bf16) {
+  if (bf16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  return __half22float2(*(const __half2*)&w);
+}
+__device__ __forceinline__ unsigned int isf_pack2(float x, float y, bool bf16) {
+  if (bf16) { const __nv_bfloat162 b = __floats2bfloat162_rn(x, y); return *(const unsigned int*)&b; }
+  const __half2 h = __floats2half2_rn(x, y);
+  return *(const unsigned int*)&h;
+}

@@ -82,6 +82,7 @@ struct ConvParams {
   int relu;
   __half* out;                // [batch, oh, ow, ldo]
   int ldo;
+  int bf16;                   // operands / output are bf16 (isf_conv3x3_nhwc_bf16), else fp16
 };
 
 // STRIDE 1: 3 A loads per channel chunk (dx), 3 taps (dy) per load.  STRIDE 2: 9 loads, 1 tap each.
@@ -165,7 +166,7 @@ conv3x3_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_x, c
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    const uint32_t idesc = make_idesc_f16(BM, BN) | (p.bf16 ? tc::IDESC_AB_BF16 : 0u);
     uint32_t ca = 0, cb = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -227,13 +228,13 @@ conv3x3_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_x, c
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 uint4 u;
-                __half2* hp = (__half2*)&u;
+                uint32_t* hp = (uint32_t*)&u;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   float a0 = __uint_as_float(v[j4 * 8 + e * 2]) + sh[j4 * 8 + e * 2];
                   float a1 = __uint_as_float(v[j4 * 8 + e * 2 + 1]) + sh[j4 * 8 + e * 2 + 1];
                   if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                  hp[e] = __floats2half2_rn(a0, a1);
+                  hp[e] = isf_pack2(a0, a1, p.bf16 != 0);
                 }
                 // 16-byte piece (h*4 + j4) of row r in the 128B-swizzled tile the store's tensor map describes
                 *(uint4*)(stage + r * 128 + (((h * 4 + j4) ^ (r & 7)) << 4)) = u;
@@ -258,13 +259,13 @@ conv3x3_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_x, c
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               uint4 u;
-              __half2* hp = (__half2*)&u;
+              uint32_t* hp = (uint32_t*)&u;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float a0 = __uint_as_float(v[j4 * 8 + e * 2]) + vec[cb + j4 * 8 + e * 2];
                 float a1 = __uint_as_float(v[j4 * 8 + e * 2 + 1]) + vec[cb + j4 * 8 + e * 2 + 1];
                 if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                hp[e] = __floats2half2_rn(a0, a1);
+                hp[e] = isf_pack2(a0, a1, p.bf16 != 0);
               }
               if (ok && n0 + cb + j4 * 8 < p.cout_store) *(uint4*)(orow + cb + j4 * 8) = u;
             }
@@ -388,5 +389,14 @@ extern "C" int isf_conv3x3_nhwc_f16(const void* x, int batch, int h, int w, int 
   a.x = x; a.batch = batch; a.h = h; a.w = w; a.cin = cin; a.ldx = ldx; a.wpk = w_packed; a.n_total = cout_pad; a.stride = stride;
   a.p.batch = batch; a.p.oh = (h + 2 - 3) / stride + 1; a.p.ow = (w + 2 - 3) / stride + 1; a.p.cin = cin; a.p.ldx = ldx; a.p.n_total = cout_pad;
   a.p.cout_store = cout_store; a.p.shift = shift; a.p.relu = relu; a.p.out = (__half*)out; a.p.ldo = ldo;
+  a.p.bf16 = isf_bf16_mode() ? 1 : 0;
   return stride == 1 ? dc::dispatch<1>(a, (cudaStream_t)stream) : dc::dispatch<2>(a, (cudaStream_t)stream);
+}
+
+// bf16 twin of isf_conv3x3_nhwc_f16 (x, w_packed and out are bf16; the TMA boxes move 2-byte elements either way)
+extern "C" int isf_conv3x3_nhwc_bf16(const void* x, int batch, int h, int w, int cin, int ldx, const void* w_packed, int cout_pad,
+                                     const float* shift, int stride, int relu, void* out, int ldo, int cout_store,
+                                     void* stream) {
+  IsfBf16Scope scope;
+  return isf_conv3x3_nhwc_f16(x, batch, h, w, cin, ldx, w_packed, cout_pad, shift, stride, relu, out, ldo, cout_store, stream);
 }

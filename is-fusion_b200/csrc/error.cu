@@ -29,6 +29,10 @@ int g_isf_gemm_cluster = 1;
 int g_isf_tile_order_drop_bits = 0;
 int g_isf_nbr_rows = 1;
 int g_isf_gemm_mt = 3;
+static thread_local int t_isf_bf16 = 0;
+int isf_bf16_mode() { return t_isf_bf16; }
+IsfBf16Scope::IsfBf16Scope() { ++t_isf_bf16; }
+IsfBf16Scope::~IsfBf16Scope() { --t_isf_bf16; }
 int g_isf_gemm_zskip = 0;
 int g_isf_gemm_wpc = 0;
 int g_isf_gemm_rev = 0;

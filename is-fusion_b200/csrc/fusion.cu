@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) cam2bev_kernel(const float* __restrict__ 
                                                       const __half* __restrict__ feat,  // [B, ncam, h, w, C]
                                                       const CamProj* __restrict__ proj,  // [B, ncam]
                                                       int ncam, int fh, int fw, float img_w, float img_h, int bev_h,
-                                                      int bev_w, __half* __restrict__ out, int ldo, int ch_off) {
+                                                      int bev_w, __half* __restrict__ out, int ldo, int ch_off, int bf16) {
   constexpr int CPL = C / 32;  // channels per lane (8 for C=256 -> one 16-byte load)
   static_assert(CPL == 8, "cam2bev is built for 256 feature channels");
   const int lane = threadIdx.x & 31;
@@ -82,10 +82,10 @@ __global__ void __launch_bounds__(256) cam2bev_kernel(const float* __restrict__ 
         if (xx < 0 || xx >= fw || yy < 0 || yy >= fh) continue;
         const float w = ((t & 1) ? wx1 : wx0) * ((t >> 1) ? wy1 : wy0);
         const uint4 u4 = *(const uint4*)(fb + ((size_t)yy * fw + xx) * C);
-        const __half2* h2 = (const __half2*)&u4;
+        const uint32_t* h2 = (const uint32_t*)&u4;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h2[e]);
+          const float2 f = isf_unpack2(h2[e], bf16 != 0);
           acc[e * 2] = fmaf(w, f.x, acc[e * 2]);
           acc[e * 2 + 1] = fmaf(w, f.y, acc[e * 2 + 1]);
         }
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(256) cam2bev_kernel(const float* __restrict__ 
     }
   }
   uint4 o;
-  __half2* oh = (__half2*)&o;
+  uint32_t* oh = (uint32_t*)&o;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[e * 2], acc[e * 2 + 1]);
+  for (int e = 0; e < 4; ++e) oh[e] = isf_pack2(acc[e * 2], acc[e * 2 + 1], bf16 != 0);
   *(uint4*)(out + ((size_t)(b * bev_h + cy) * bev_w + cx) * ldo + ch_off + lane * CPL) = o;
 }
 
@@ -115,10 +115,21 @@ extern "C" int isf_cam2bev(const float* pillars, int num_pillars, const int* num
   cam2bev_kernel<256><<<blocks, 256, 0, (cudaStream_t)stream>>>(
       pillars, points_per_pillar, nfeat, pillar_coors, coors_dim, batch_index, num_pillars, num_pillars_dev,
       (const __half*)img_feat_nhwc,
-      (const CamProj*)proj_dev, ncam, fh, fw, img_w, img_h, bev_h, bev_w, (__half*)out_nhwc, ldo, ch_off);
+      (const CamProj*)proj_dev, ncam, fh, fw, img_w, img_h, bev_h, bev_w, (__half*)out_nhwc, ldo, ch_off, isf_bf16_mode());
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
+}
+
+// bf16 twin: the camera feature map and the BEV output are bf16 (projection and bilinear accumulation stay fp32)
+extern "C" int isf_cam2bev_bf16(const float* pillars, int num_pillars, const int* num_pillars_dev, int points_per_pillar,
+                                int nfeat, const int* pillar_coors, int coors_dim, int batch_index,
+                                const void* img_feat_nhwc, const float* proj_dev, int batch,
+                                int ncam, int fh, int fw, int channels, float img_w, float img_h, int bev_h, int bev_w,
+                                void* out_nhwc, int ldo, int ch_off, void* stream) {
+  IsfBf16Scope scope;
+  return isf_cam2bev(pillars, num_pillars, num_pillars_dev, points_per_pillar, nfeat, pillar_coors, coors_dim, batch_index,
+                     img_feat_nhwc, proj_dev, batch, ncam, fh, fw, channels, img_w, img_h, bev_h, bev_w, out_nhwc, ldo, ch_off, stream);
 }
 
 // ================================================================================================
@@ -135,6 +146,12 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
   __half2 h = __floats2half2_rn(x, y);
   return *(uint32_t*)&h;
 }
+__device__ __forceinline__ void mma16816_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ uint32_t pack_2h(__half lo, __half hi) {
   return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16);
 }
@@ -148,7 +165,8 @@ __device__ __forceinline__ uint32_t pack_2h(__half lo, __half hi) {
 // per head: S = QK^T (48x40 padded) and PV on mma.sync.m16n8k16, fp32 softmax in the accumulator registers
 // (quad shuffles), K(+pos) and V of the window in smem with a conflict-free pitch.  Keys outside the grid are masked
 // (the key_padding_mask of the reference); query rows outside the grid are never stored.
-template <int C, int HEADS>
+// BF: qkv / out (and the probabilities fed to the P.V product) are bf16 instead of fp16; scores and softmax are fp32 either way
+template <int C, int HEADS, bool BF>
 __global__ void __launch_bounds__(HEADS * 32) window_attention_kernel(const __half* __restrict__ qkv,
                                                                       const float* __restrict__ pos_q,
                                                                       const float* __restrict__ pos_k, int S, int shift,
@@ -183,13 +201,13 @@ __global__ void __launch_bounds__(HEADS * 32) window_attention_kernel(const __ha
       const __half* row = qkv + (size_t)t * 3 * C;
       kk = *(const uint4*)(row + C + c8);
       vv = *(const uint4*)(row + 2 * C + c8);
-      __half2* k2 = (__half2*)&kk;
+      uint32_t* k2 = (uint32_t*)&kk;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 f = __half22float2(k2[i]);
+        float2 f = isf_unpack2(k2[i], BF);
         f.x += pos_k[slot * C + c8 + 2 * i];
         f.y += pos_k[slot * C + c8 + 2 * i + 1];
-        k2[i] = __floats2half2_rn(f.x, f.y);
+        k2[i] = isf_pack2(f.x, f.y, BF);
       }
     }
     if (slot < 40) *(uint4*)&ks[slot][c8] = kk;
@@ -213,11 +231,11 @@ __global__ void __launch_bounds__(HEADS * 32) window_attention_kernel(const __ha
         const int col = h * D + kt * 16 + gc + (part >> 1) * 8;
         float2 f = make_float2(0.f, 0.f);
         if (tk >= 0) {
-          f = __half22float2(*(const __half2*)(qkv + (size_t)tk * 3 * C + col));
+          f = isf_unpack2(*(const uint32_t*)(qkv + (size_t)tk * 3 * C + col), BF);
           f.x += pos_q[slot * C + col];
           f.y += pos_q[slot * C + col + 1];
         }
-        qa[kt][part] = pack_h2(f.x, f.y);
+        qa[kt][part] = isf_pack2(f.x, f.y, BF);
       }
     }
     float sc[5][4];
@@ -227,7 +245,8 @@ __global__ void __launch_bounds__(HEADS * 32) window_attention_kernel(const __ha
 #pragma unroll
       for (int kt = 0; kt < KS; ++kt) {
         const __half* kr = &ks[nt * 8 + gr][h * D + kt * 16 + gc];
-        mma16816(sc[nt], qa[kt], *(const uint32_t*)kr, *(const uint32_t*)(kr + 8));
+        if constexpr (BF) mma16816_bf16(sc[nt], qa[kt], *(const uint32_t*)kr, *(const uint32_t*)(kr + 8));
+        else mma16816(sc[nt], qa[kt], *(const uint32_t*)kr, *(const uint32_t*)(kr + 8));
       }
     }
     float m0 = -INFINITY, m1 = -INFINITY;
@@ -265,23 +284,24 @@ __global__ void __launch_bounds__(HEADS * 32) window_attention_kernel(const __ha
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt) {
       uint32_t pa[4];
-      pa[0] = pack_h2(pe[2 * kt][0], pe[2 * kt][1]);
-      pa[1] = pack_h2(pe[2 * kt][2], pe[2 * kt][3]);
-      pa[2] = pack_h2(pe[2 * kt + 1][0], pe[2 * kt + 1][1]);
-      pa[3] = pack_h2(pe[2 * kt + 1][2], pe[2 * kt + 1][3]);
+      pa[0] = isf_pack2(pe[2 * kt][0], pe[2 * kt][1], BF);
+      pa[1] = isf_pack2(pe[2 * kt][2], pe[2 * kt][3], BF);
+      pa[2] = isf_pack2(pe[2 * kt + 1][0], pe[2 * kt + 1][1], BF);
+      pa[3] = isf_pack2(pe[2 * kt + 1][2], pe[2 * kt + 1][3], BF);
       const __half* vr = &vs[kt * 16 + gc][h * D + gr];       // B[k = key][n = dv] = V[key][dv]
 #pragma unroll
       for (int n = 0; n < NV; ++n) {
         const uint32_t b0 = pack_2h(vr[n * 8], vr[PITCH + n * 8]);
         const uint32_t b1 = pack_2h(vr[8 * PITCH + n * 8], vr[9 * PITCH + n * 8]);
-        mma16816(o[n], pa, b0, b1);
+        if constexpr (BF) mma16816_bf16(o[n], pa, b0, b1);
+        else mma16816(o[n], pa, b0, b1);
       }
     }
     const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
     for (int n = 0; n < NV; ++n) {
-      if (t0 >= 0) *(__half2*)(out + (size_t)t0 * C + h * D + n * 8 + gc) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
-      if (t1 >= 0) *(__half2*)(out + (size_t)t1 * C + h * D + n * 8 + gc) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+      if (t0 >= 0) *(uint32_t*)(out + (size_t)t0 * C + h * D + n * 8 + gc) = isf_pack2(o[n][0] * i0, o[n][1] * i0, BF);
+      if (t1 >= 0) *(uint32_t*)(out + (size_t)t1 * C + h * D + n * 8 + gc) = isf_pack2(o[n][2] * i1, o[n][3] * i1, BF);
     }
   }
 }
@@ -293,12 +313,17 @@ extern "C" int isf_window_attention(const void* qkv, const float* pos_q, const f
   const int shift = shifted ? 3 : 6;
   const int blocks = batch * nwin * nwin;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool bf = isf_bf16_mode() != 0;
   if (channels == 128) {
-    window_attention_kernel<128, 8><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
-                                                             1.0f / sqrtf(16.f), (__half*)out);
+    if (bf) window_attention_kernel<128, 8, true><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+                                                                          1.0f / sqrtf(16.f), (__half*)out);
+    else window_attention_kernel<128, 8, false><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+                                                                        1.0f / sqrtf(16.f), (__half*)out);
   } else if (channels == 256) {
-    window_attention_kernel<256, 8><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
-                                                             1.0f / sqrtf(32.f), (__half*)out);
+    if (bf) window_attention_kernel<256, 8, true><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+                                                                          1.0f / sqrtf(32.f), (__half*)out);
+    else window_attention_kernel<256, 8, false><<<blocks, 256, 0, st>>>((const __half*)qkv, pos_q, pos_k, grid, shift, nwin,
+                                                                        1.0f / sqrtf(32.f), (__half*)out);
   } else {
     isf_set_error("window_attention: channels must be 128 or 256");
     return ISF_ERR_UNSUPPORTED;
@@ -306,6 +331,13 @@ extern "C" int isf_window_attention(const void* qkv, const float* pos_q, const f
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();
   return ISF_OK;
+}
+
+// bf16 twin of isf_window_attention (qkv and out are bf16)
+extern "C" int isf_window_attention_bf16(const void* qkv, const float* pos_q, const float* pos_k, int batch, int grid,
+                                         int channels, int heads, int shifted, void* out, void* stream) {
+  IsfBf16Scope scope;
+  return isf_window_attention(qkv, pos_q, pos_k, batch, grid, channels, heads, shifted, out, stream);
 }
 
 // ================================================================================================

@@ -34,3 +34,14 @@ extern "C" int isf_gemm_f16(const void* A, const void* W, int m, int k, int kpad
   isf_count_launch(1);
   return rc;
 }
+
+// bf16 twin (BASELINE configs[2]: "bf16 tensor-core path"): A, W, residual and the 16-bit output are bf16; same kernels, same fp32
+// accumulation and epilogue arithmetic (tcgen05 kind::f16 with the BF16 operand formats).
+extern "C" int isf_gemm_bf16(const void* A, const void* W, int m, int k, int kpad, int n, const float* scale,
+                             const float* shift, const void* residual, int ldr, int act, const float* ln_gamma,
+                             const float* ln_beta, float ln_eps, void* out_bf16, float* out_f32, int ldo,
+                             const int* out_rows, const int* m_dev, void* stream) {
+  IsfBf16Scope scope;
+  return isf_gemm_f16(A, W, m, k, kpad, n, scale, shift, residual, ldr, act, ln_gamma, ln_beta, ln_eps, out_bf16, out_f32, ldo,
+                      out_rows, m_dev, stream);
+}

@@ -244,6 +244,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+constexpr uint32_t IDESC_AB_BF16 = (1u << 7) | (1u << 10);      // a_format / b_format = BF16 (1) instead of F16 (0)
 
 // ---------------------------------------------------------------- kernel
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
@@ -274,6 +275,7 @@ struct GemmParams {
   float* out_f32;         // [m, ldo] fp32 (may be nullptr)
   int ldo;
   const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
+  int bf16;               // 16-bit operands / residual / output are bf16 (else fp16); dense GEMMs only (isf_gemm_bf16)
   int wpc;                // tc_gemm4.cuh: producer warps per K chunk (1 or 2) of the warp-per-chunk mapping
   int rev;                // tc_gemm4.cuh: tiles walked from the last one down (isf_set_option("gemm_rev"))
   int zskip;              // tc_gemm4.cuh: skip all-missing 4-row copies onto rows that already hold zeros (isf_set_option("gemm_zskip"))
@@ -342,7 +344,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
         ld_global_256(p.residual + rrow * p.ldr + n_base + j8 * 16, w);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float2 f = __half22float2(*(const __half2*)&w[e]);
+          const float2 f = isf_unpack2(w[e], p.bf16 != 0);
           x[j8 * 16 + e * 2] += f.x; x[j8 * 16 + e * 2 + 1] += f.y;
         }
       }
@@ -351,10 +353,10 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const uint4 u = rp[j4];
-        const __half2* h = (const __half2*)&u;
+        const uint32_t* h = (const uint32_t*)&u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(h[e]);
+          const float2 f = isf_unpack2(h[e], p.bf16 != 0);
           x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
         }
       }
@@ -596,10 +598,10 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const uint4 u = rp[j4];
-              const __half2* h = (const __half2*)&u;
+              const uint32_t* h = (const uint32_t*)&u;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h[e]);
+                const float2 f = isf_unpack2(h[e], p.bf16 != 0);
                 x[cb + j4 * 8 + e * 2] += f.x; x[cb + j4 * 8 + e * 2 + 1] += f.y;
               }
             }
@@ -632,9 +634,9 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 uint4 u;
-                __half2* h = (__half2*)&u;
+                uint32_t* h = (uint32_t*)&u;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[cb + j4 * 8 + e * 2], x[cb + j4 * 8 + e * 2 + 1]);
+                for (int e = 0; e < 4; ++e) h[e] = isf_pack2(x[cb + j4 * 8 + e * 2], x[cb + j4 * 8 + e * 2 + 1], p.bf16 != 0);
                 op[j4] = u;
               }
             }
@@ -704,10 +706,10 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
           if (has_res) {
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
-              const __half2* h = (const __half2*)&rcur[j4];
+              const uint32_t* h = (const uint32_t*)&rcur[j4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h[e]);
+                const float2 f = isf_unpack2(h[e], p.bf16 != 0);
                 x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
               }
             }
@@ -725,9 +727,9 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
 #pragma unroll
               for (int j4 = 0; j4 < 2; ++j4) {
                 uint4 u;
-                __half2* h = (__half2*)&u;
+                uint32_t* h = (uint32_t*)&u;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+                for (int e = 0; e < 4; ++e) h[e] = isf_pack2(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1], p.bf16 != 0);
                 op[j4] = u;
               }
             }
@@ -786,9 +788,9 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               uint4 u;
-              __half2* h = (__half2*)&u;
+              uint32_t* h = (uint32_t*)&u;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+              for (int e = 0; e < 4; ++e) h[e] = isf_pack2(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1], p.bf16 != 0);
               op[j4] = u;
             }
           }
@@ -807,7 +809,7 @@ __global__ void __launch_bounds__(THREADS, (LN || MT > 1) ? 1 : (BN <= 64 ? 3 : 
       }
     } else {
       // ------------------------------------------------ MMA issuer (warp PWARPS)
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      const uint32_t idesc = make_idesc_f16(BM, BN) | (p.bf16 ? IDESC_AB_BF16 : 0u);
       uint32_t c0 = chunk_ctr;
       for (int q = 0; q < n_act; ++q) {
         const uint32_t cc = c0 + q;
@@ -970,6 +972,7 @@ static inline int dispatch_gemm(const GemmParams& p0, int bn, int m_upper, cudaS
   p.zskip = ::g_isf_gemm_zskip;
   p.rev = ::g_isf_gemm_rev;
   p.wpc = 1;
+  p.bf16 = (::isf_bf16_mode() && p.nbr == nullptr) ? 1 : 0;
   if (p.ln_gamma != nullptr && p.nbr == nullptr && ::g_isf_gemm_ln_fast) {      // LayerNorm epilogue: dense GEMMs, one column block
     switch (bn) {
       case 64: return launch_gemm<64, 2, 1, 1, true>(p, m_upper, st);

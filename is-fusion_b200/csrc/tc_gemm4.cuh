@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == V4_MMA_WARP) {
     // ================================================================ MMA issuer
-    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    const uint32_t idesc = make_idesc_f16(BM, BN) | (p.bf16 ? IDESC_AB_BF16 : 0u);
     uint32_t ca = 0;
     int it = 0;
     for (int tidx = blockIdx.x; tidx < num_tiles; tidx += gridDim.x, ++it) {
@@ -356,10 +356,10 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
         if (has_res) {
 #pragma unroll
           for (int j4 = 0; j4 < 2; ++j4) {
-            const __half2* h = (const __half2*)&rcur[j4];
+            const uint32_t* h = (const uint32_t*)&rcur[j4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(h[e]);
+              const float2 f = isf_unpack2(h[e], p.bf16 != 0);
               x[j4 * 8 + e * 2] += f.x; x[j4 * 8 + e * 2 + 1] += f.y;
             }
           }
@@ -377,9 +377,9 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
               uint4 u;
-              __half2* h = (__half2*)&u;
+              uint32_t* h = (uint32_t*)&u;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+              for (int e = 0; e < 4; ++e) h[e] = isf_pack2(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1], p.bf16 != 0);
               op[j4] = u;
             }
           }

@@ -39,7 +39,7 @@ def _fold_conv_bn(conv, bn, transpose_kernel=False):
     if transpose_kernel:
         w = w.transpose(2, 3)
     b = b.detach()
-    return (w.half().contiguous(memory_format=torch.channels_last), b.half().contiguous(), b.float().contiguous())   # + fp32 shift
+    return (w.to(L.DTYPE).contiguous(memory_format=torch.channels_last), b.to(L.DTYPE).contiguous(), b.float().contiguous())   # + fp32 shift
 
 
 def _conv(x_nhwc, packed, stride=1, relu=True):
@@ -200,8 +200,9 @@ class SSTv2(_Packable):
         x = voxel_info['voxel_feats']
         bs, g = voxel_info['batch_size'], voxel_info['grid']
         pk = self._pack(voxel_info['pos'])
-        if x.dtype != torch.float16:
-            x = x.half()
+        dt = pk['layers'][0]['win'].dtype          # fp16, or bf16 when packed under _lib.set_dtype(torch.bfloat16)
+        if x.dtype != dt:
+            x = x.to(dt)
         x = x.contiguous()
         if 'l0' in pk:
             x = gemm(x, pk['l0'][0], shift=pk['l0'][1])
@@ -211,8 +212,8 @@ class SSTv2(_Packable):
             shifted = li % 2                              # BasicShiftBlockV2: layer 0 aligned, layer 1 shifted
             qkv = gemm(x, ly['win'], shift=ly['bin'])
             att = torch.empty_like(x)
-            L.check(lib.isf_window_attention(L.ptr(qkv), L.ptr(ly['posq']), L.ptr(ly['posk']), bs, g, c, 8, shifted,
-                                             L.ptr(att), L.stream()))
+            L.check(L.fn16('isf_window_attention', dt)(L.ptr(qkv), L.ptr(ly['posq']), L.ptr(ly['posk']), bs, g, c, 8, shifted,
+                                                       L.ptr(att), L.stream()))
             x = gemm(att, ly['wo'], shift=ly['bo'], residual=x, ln=ly['ln1'])
             h = gemm(x, ly['w1'], shift=ly['b1'], act='gelu')
             x = gemm(h, ly['w2'], shift=ly['b2'], residual=x, ln=ly['ln2'])
@@ -660,7 +661,7 @@ class ISFusionEncoder(_Packable):
     def new_fusion_buffer(self, bs, device):
         """zeroed channels-last [B,G,G,768] buffer: image BEV in channels 0..255, LiDAR BEV in 256..767."""
         g = self.bev_size
-        return torch.zeros((bs, g, g, self.embed_dims * 3), dtype=torch.float16, device=device)
+        return torch.zeros((bs, g, g, self.embed_dims * 3), dtype=L.DTYPE, device=device)
 
     # ------------------------------------------------------------------ a6: camera -> BEV
     def camera_projection(self, lidar2img, img_aug_matrix, lidar_aug_matrix, bs, device):
@@ -685,24 +686,25 @@ class ISFusionEncoder(_Packable):
         feat = mlvl_feats[0]
         dev = feat.device
         c, fh, fw = feat.shape[1], feat.shape[2], feat.shape[3]
-        feat_nhwc = feat.view(bs, self.num_views, c, fh, fw).permute(0, 1, 3, 4, 2).contiguous().half()
+        dt = out.dtype if out is not None else L.DTYPE
+        feat_nhwc = feat.view(bs, self.num_views, c, fh, fw).permute(0, 1, 3, 4, 2).contiguous().to(dt)
         image_size = kwargs['img_metas'][0]['input_shape']
         proj = kwargs.get('cam_proj')
         if proj is None:
             proj = self.camera_projection(kwargs['lidar2img'], kwargs['img_aug_matrix'], kwargs['lidar_aug_matrix'], bs, dev)
         g = self.bev_size
         if out is None:
-            out = torch.zeros((bs, g, g, self.embed_dims), dtype=torch.float16, device=dev)
+            out = torch.zeros((bs, g, g, self.embed_dims), dtype=dt, device=dev)
         if 'pillars_list' in pm:
             jobs = [(p, co, cnt, 3, b) for b, (p, co, cnt) in enumerate(pm['pillars_list'])]
         else:
             jobs = [(pm['pillars'].contiguous(), pm['pillar_coors'].contiguous(), None, 4, 0)]
         for pillars, pcoors, cnt, cdim, b in jobs:
             L.require_cuda(pillars, pcoors)
-            L.check(L.lib().isf_cam2bev(L.ptr(pillars), pillars.shape[0], L.ptr(cnt), pillars.shape[1], pillars.shape[2],
-                                        L.ptr(pcoors), cdim, b, L.ptr(feat_nhwc), L.ptr(proj), bs, self.num_views, fh, fw,
-                                        c, ctypes.c_float(image_size[1]), ctypes.c_float(image_size[0]), g, g, L.ptr(out),
-                                        out.shape[-1], 0, L.stream()))
+            L.check(L.fn16('isf_cam2bev', dt)(L.ptr(pillars), pillars.shape[0], L.ptr(cnt), pillars.shape[1], pillars.shape[2],
+                                              L.ptr(pcoors), cdim, b, L.ptr(feat_nhwc), L.ptr(proj), bs, self.num_views, fh, fw,
+                                              c, ctypes.c_float(image_size[1]), ctypes.c_float(image_size[0]), g, g, L.ptr(out),
+                                              out.shape[-1], 0, L.stream()))
         return out
 
     # ------------------------------------------------------------------ a10-a12: instance-guided fusion

@@ -4,8 +4,8 @@ Point-to-Grid (camera -> BEV projection of the pillars, a6) + Grid-to-Region (co
 transformer over the 180 x 180 BEV, a8/a9; optionally the second region level on the 90 x 90 map), on a synthetic frame.
 The sequence is captured into ONE CUDA graph and replayed; per-stage times come from a second, eager pass with CUDA events.
     python scripts/bench_hsf.py [--steps 200 --warmup 20 --points 300000 --levels 1]
-Tensor-core path: fp16 operands, fp32 accumulation (tcgen05 kind::f16 runs fp16 and bf16 at the same rate; the library has no
-bf16 instantiation — DESIGN.md section 7)."""
+    python scripts/bench_hsf.py --dtype bf16      (the `_bf16` entry points: what BASELINE configs[2] names)
+Tensor-core path: fp16 (default) or bf16 operands, fp32 accumulation (tcgen05 kind::f16 runs both formats at the same rate)."""
 import argparse
 import json
 import os
@@ -23,10 +23,13 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--levels', type=int, default=1, help='region levels: 1 = 180x180 only, 2 = + the 90x90 level')
+    ap.add_argument('--dtype', default='f16', choices=['f16', 'bf16'])
     args = ap.parse_args()
     import synth
     from __graft_entry__ import make_net
     from isfusion_b200 import _lib as L
+    if args.dtype == 'bf16':
+        L.set_dtype(torch.bfloat16)           # before the first forward: weights are packed in this type
     dev = torch.device(os.environ.get('ISF_TOOL_DEVICE', 'cuda:0'))
     img = (384, 1056)
     net = make_net(0).to(dev).eval()
@@ -40,8 +43,8 @@ def main():
     kw['cam_proj'] = net.fusion_encoder.camera_projection(l2i, aug, laug, 1, dev)      # input-independent of the graph
     pm = dict(pillars_list=net.voxelize_nosync(pts), pts=pts, pillar_size=net.pillar_size)
     torch.manual_seed(1)
-    lidar_bev = (torch.randn(1, g, g, 512, device=dev) * 0.5).half()          # stands for the sparse encoder's BEV output
-    lvl1_in = (torch.randn(1 * (g // 2) * (g // 2), 256, device=dev) * 0.5).half()
+    lidar_bev = (torch.randn(1, g, g, 512, device=dev) * 0.5).to(L.DTYPE)          # stands for the sparse encoder's BEV output
+    lvl1_in = (torch.randn(1 * (g // 2) * (g // 2), 256, device=dev) * 0.5).to(L.DTYPE)
     pk = enc._pack(dev)
     from isfusion_b200.fusion_encoder import _conv
     cat = enc.new_fusion_buffer(1, dev)
@@ -115,7 +118,7 @@ def main():
     cam_bytes = g * g * 12 * 12.0 + 6 * 256 * (img[0] // 16) * (img[1] // 16) * 2.0 + 256.0 * g * g * 2
     line = {'metric': 'frames/sec HSF-only (Point-to-Grid + Grid-to-Region over 180x180 BEV)', 'value': 1000.0 / ms, 'unit': 'frames/s',
             'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'eager_ms_per_step': ms_eager, 'higher_is_better': True,
-            'dtype': 'f16', 'data': 'synthetic',
+            'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': 'BASELINE configs[2]: HSF-only ablation', 'points_per_frame': args.points, 'cams': 6, 'img': list(img),
                        'bev': g, 'region_levels': args.levels, 'mode': 'one CUDA graph replayed back to back (inputs resident)'},
             'gpu_launches_per_step': int(launches), 'stage_ms_eager': {k: round(v, 4) for k, v in st.items()},
