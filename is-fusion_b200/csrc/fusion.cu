@@ -1089,8 +1089,9 @@ __global__ void __launch_bounds__(256) i2s_attention_kernel(const __half* __rest
   }
 }
 
-extern "C" int isf_i2s_attention(const void* q, const void* kv, int batch, int tokens, int num_keys, int channels,
-                                 int heads, void* out, void* stream) {
+// mma.sync implementation; the C entry point isf_i2s_attention (i2s_tc.cu) runs the tcgen05 kernel unless isf_set_option("i2s_tc", 0)
+int isf_i2s_attention_mma(const void* q, const void* kv, int batch, int tokens, int num_keys, int channels,
+                          int heads, void* out, void* stream) {
   ISF_CHECK_ARG(q && kv && out && batch >= 1 && tokens >= 1 && num_keys >= 1);
   if (channels != 128 || heads != 8 || num_keys > 208) {
     isf_set_error("i2s_attention: built for d_model 128, 8 heads, <= 208 keys");

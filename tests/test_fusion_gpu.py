@@ -173,6 +173,45 @@ def test_instance_to_scene_parity():
     assert r < 3e-3, (r, m)
 
 
+@pytest.mark.parametrize('B,T,K', [(1, 32400, 200), (2, 32400, 200), (1, 8100, 200), (3, 1000, 150), (1, 127, 8), (1, 129, 208)])
+def test_i2s_attention_tcgen05_kernel(B, T, K):
+    """isf_i2s_attention on tcgen05 tiles (csrc/i2s_tc.cu: TMA-staged Q / K, S and O in TMEM, P through shared memory) against the
+    fp32 attention of the same fp16 operands and against the mma.sync kernel (the default; the tcgen05 kernel is opt-in,
+    isf_set_option("i2s_tc", 1): measured 3x slower at head dimension 16); ragged last tile, fewer than 208 keys, several frames.
+    Prints both kernels' times."""
+    from isfusion_b200 import _lib as L
+    torch.manual_seed(T + K)
+    C, H = 128, 8
+    q = (torch.randn(B * T, C) * 0.8).half().cuda()
+    kv = (torch.randn(B, K, 2 * C) * 0.8).half().cuda()
+    qf = q.float().view(B, T, H, 16).permute(0, 2, 1, 3)
+    kf = kv[..., :C].float().view(B, K, H, 16).permute(0, 2, 1, 3)
+    vf = kv[..., C:].float().view(B, K, H, 16).permute(0, 2, 1, 3)
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) / 4.0, -1) @ vf          # [B, H, T, 16]
+    ref = ref.permute(0, 2, 1, 3).reshape(B * T, C)
+    outs, times = {}, {}
+    try:
+        for mode in (1, 0):
+            L.set_option('i2s_tc', mode)
+            o = torch.full((B * T, C), 7.0, dtype=torch.float16, device='cuda')
+            L.check(L.lib().isf_i2s_attention(L.ptr(q), L.ptr(kv), B, T, K, C, H, L.ptr(o), L.stream()))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                L.check(L.lib().isf_i2s_attention(L.ptr(q), L.ptr(kv), B, T, K, C, H, L.ptr(o), L.stream()))
+            e1.record()
+            torch.cuda.synchronize()
+            outs[mode], times[mode] = o, e0.elapsed_time(e1) / 10
+    finally:
+        L.set_option('i2s_tc', 0)
+    print('i2s B=%d T=%d K=%d: tcgen05 %.1f us, mma.sync %.1f us' % (B, T, K, times[1] * 1e3, times[0] * 1e3))
+    for mode in (1, 0):
+        r, m = rel(outs[mode], ref)
+        assert r < 1e-3 and m < 2e-3 * max(1.0, ref.abs().max().item()), (mode, r, m)
+    assert rel(outs[1], outs[0])[0] < 1e-3
+
+
 def test_secondv2_parity():
     from isfusion_b200.fusion_encoder import SECONDV2
     torch.manual_seed(0)
