@@ -88,8 +88,15 @@ struct Smem5 {
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte alignment of the 128B swizzle");
 };
 
-template <int BN, int STAGES, int CTAS, int MT>
-__global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
+// MMAW = MMA-issuing warps of the leader (1, or 2 with MT = 2: warp 8 issues sub-tile 0, warp 13 sub-tile 1).  One thread issues a
+// tcgen05.mma per ~90-100 cycles (bench_mma_rate.py); a 256 x 128 x 16 pair instruction occupies the two tensor pipes for 64, so a
+// single issuer leaves a third of the pipe idle on the 128-column layers.  Each warp commits its own instructions: the stage /
+// accumulator barriers then expect MMAW arrivals.
+template <int BN, int STAGES, int CTAS, int MT, int MMAW = 1>
+__global__ void __launch_bounds__(V4_THREADS + (MMAW - 1) * 32, CTAS) gemm5_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
+  static_assert(MMAW == 1 || (MMAW == 2 && MT == 2), "two MMA warps split the two sub-tiles");
+  constexpr int NTHREADS = V4_THREADS + (MMAW - 1) * 32;
+  constexpr int MMA_WARP1 = V4_THREADS / 32;          // the second MMA warp sits behind the epilogue warps
   using SL = Smem5<BN, STAGES, MT>;
   constexpr int TILE_M = SL::TILE_M;
   constexpr int TSPLIT = PRODUCERS / TILE_M;
@@ -126,20 +133,20 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], PRODUCERS + 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MMAW);
       mbar_init(&peer_full[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_full[b], MMAW);
       mbar_init(&acc_empty[b], 256);
       mbar_init(&list_full[b], 1);
-      mbar_init(&list_empty[b], 1);
+      mbar_init(&list_empty[b], cluster_ctarank() == 0 ? MMAW : 1);      // leader: its MMA warps; peer: the relay warp
       mbar_init(&xbar[b], 1);
     }
     fence_barrier_init();
   }
   if (warp == V4_MMA_WARP) tmem_alloc2<TMEM_COLS>(tmem_slot);
-  for (int c = tid; c < BN; c += V4_THREADS) {
+  for (int c = tid; c < BN; c += NTHREADS) {
     vec[c] = p.scale ? p.scale[c] : 1.f;
     vec[BN + c] = p.shift ? p.shift[c] : 0.f;
   }
@@ -259,10 +266,13 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == V4_MMA_WARP) {
+  } else if (warp == V4_MMA_WARP || (MMAW == 2 && warp == MMA_WARP1)) {
     uint32_t ca = 0;
     int it = 0;
-    if (rank == 0) {
+    const int sub = warp == V4_MMA_WARP ? 0 : 1;      // MMAW == 2: the sub-tile this warp issues
+    if (rank != 0 && sub == 1) {
+      // the peer's second MMA warp has nothing to do
+    } else if (rank == 0) {
       // ================================================================ leader: MMA issuer for the pair
       constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
       for (int sidx = pair0; sidx < num_super; sidx += npairs, ++it) {
@@ -284,8 +294,14 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
           tc_fence_after();
           {      // whole warp, converged: one election per chunk (umma_chunk, tc_gemm.cuh)
             const uint32_t a_addr = smem_u32(smem + s * SL::STAGE_BYTES);
-            umma_chunk<2, MT>(d_tmem, d_tmem + (uint32_t)BN, make_desc_sw128(a_addr), make_desc_sw128(a_addr + (uint32_t)(BM * 128)),
-                              make_desc_sw128(a_addr + SL::A_BYTES), idesc, q ? 1u : 0u, &empty_bar[s], 3);
+            if constexpr (MMAW == 2) {
+              const uint32_t d_sub = d_tmem + (uint32_t)(sub * BN);
+              const uint64_t a_sub = make_desc_sw128(a_addr + (uint32_t)(sub * BM * 128));
+              umma_chunk<2, 1>(d_sub, d_sub, a_sub, a_sub, make_desc_sw128(a_addr + SL::A_BYTES), idesc, q ? 1u : 0u, &empty_bar[s], 3);
+            } else {
+              umma_chunk<2, MT>(d_tmem, d_tmem + (uint32_t)BN, make_desc_sw128(a_addr), make_desc_sw128(a_addr + (uint32_t)(BM * 128)),
+                                make_desc_sw128(a_addr + SL::A_BYTES), idesc, q ? 1u : 0u, &empty_bar[s], 3);
+            }
             if (q == n_act - 1) umma_commit2_mcast(&acc_full[buf], 3);
           }
           __syncwarp();
@@ -404,11 +420,11 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm5_kernel(const GemmParam
 #undef V5_SUPER
 }
 
-template <int BN, int STAGES, int CTAS, int MT = 1>
+template <int BN, int STAGES, int CTAS, int MT = 1, int MMAW = 1>
 static int launch_gemm5(const GemmParams& p, int m_upper, cudaStream_t st) {
   using SL = Smem5<BN, STAGES, MT>;
   static_assert((SL::TOTAL + 1024) * CTAS <= 227 * 1024, "v5 GEMM: shared memory budget exceeded");
-  auto kern = gemm5_kernel<BN, STAGES, CTAS, MT>;
+  auto kern = gemm5_kernel<BN, STAGES, CTAS, MT, MMAW>;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { isf_set_error("gemm v5: bad device"); return ISF_ERR_CUDA; }
   static bool configured[64] = {};
@@ -429,7 +445,7 @@ static int launch_gemm5(const GemmParams& p, int m_upper, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs, 1);
-  cfg.blockDim = dim3(V4_THREADS);
+  cfg.blockDim = dim3(V4_THREADS + (MMAW - 1) * 32);
   cfg.dynamicSmemBytes = SL::TOTAL;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -455,8 +471,12 @@ static inline int dispatch_gemm5(const GemmParams& p, int bn, int m_upper, cudaS
   // (gemm_mt = 1 selects those two-CTAs-per-SM configurations for A/B runs).
   const bool two = ::g_isf_gemm_mt == 1;
   switch (bn) {
-    case 64: return two ? launch_gemm5<64, 4, 2, 1>(p, m_upper, st) : launch_gemm5<64, 4, 1, 2>(p, m_upper, st);      // 4 x 36 KB + 27 KB
-    case 128: return two ? launch_gemm5<128, 4, 2, 1>(p, m_upper, st) : launch_gemm5<128, 4, 1, 2>(p, m_upper, st);   // 4 x 40 KB + 27 KB
+    case 64:
+      if (two) return launch_gemm5<64, 4, 2, 1>(p, m_upper, st);
+      return ::g_isf_gemm_mma2 ? launch_gemm5<64, 4, 1, 2, 2>(p, m_upper, st) : launch_gemm5<64, 4, 1, 2>(p, m_upper, st);      // 4 x 36 KB + 27 KB
+    case 128:
+      if (two) return launch_gemm5<128, 4, 2, 1>(p, m_upper, st);
+      return ::g_isf_gemm_mma2 ? launch_gemm5<128, 4, 1, 2, 2>(p, m_upper, st) : launch_gemm5<128, 4, 1, 2>(p, m_upper, st);   // 4 x 40 KB + 27 KB
     case 256: return launch_gemm5<256, 6, 1, 1>(p, m_upper, st);   // 6 x 32 KB + 14 KB, all 512 TMEM columns
     default: isf_set_error("gemm v5: unsupported column tile %d", bn); return ISF_ERR_UNSUPPORTED;
   }

@@ -249,14 +249,16 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
             torch.cuda.synchronize()
             assert torch.equal(o, ref), (wpc, rev, v32, mt)
         # CTA pairs (tcgen05.mma.cta_group::2, csrc/tc_gemm5.cuh): every column tile >= 64 / only 256 / 128-and-up, both walks
-        for pair, rev, mt in ((1, 0, 3), (1, 1, 3), (256, 0, 3), (128, 0, 3), (128, 0, 1), (1, 0, 1)):
+        for pair, rev, mt, mma2 in ((1, 0, 3, 1), (1, 1, 3, 0), (256, 0, 3, 1), (128, 0, 3, 1), (128, 0, 3, 0), (128, 0, 1, 1), (1, 0, 1, 0)):
             L.set_option('gemm_pair', pair)
             L.set_option('gemm_rev', rev)
             L.set_option('gemm_mt', mt)
+            L.set_option('gemm_mma2', mma2)
             o, _, _ = mod(f, c, 2)
             torch.cuda.synchronize()
             assert torch.equal(o, ref), ('pair', pair, rev, mt)
     finally:
+        L.set_option('gemm_mma2', 1)
         L.set_option('gemm_pair', 128)
         L.set_option('gemm_v4', 2)
         L.set_option('gemm_mt', 3)
