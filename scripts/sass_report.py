@@ -12,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'is-fusion_b200', 'libisfusion_b200.so')
-MNEMONICS = ['UTCHMMA', 'LDTM', 'UTCBAR', 'UTMALDG', 'UTCATOMSWS', 'LDGSTS', 'SYNCS', 'HMMA', 'ENL2.256', 'STL', 'LDL', 'BAR.SYNC']
+MNEMONICS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTCBAR', 'UTCBAR.2CTA.MULTICAST', 'UTMALDG', 'UTMASTG', 'STAS', 'UTCATOMSWS', 'LDGSTS', 'SYNCS', 'HMMA', 'ENL2.256', 'STL', 'LDL',
+             'BAR.SYNC']
 
 
 def demangle(names):
