@@ -388,7 +388,7 @@ def main():
                 traffic, traffic_src = float(tj['dram_bytes_per_launch']), tj['source']
             except Exception:
                 pass
-            roof = {'kernel': 'tc::gemm_kernel (tcgen05 sparse-conv implicit GEMM; %d launches per frame)' % len(recs),
+            roof = {'kernel': 'tc::gemm5_kernel (CTA pairs, >= 128 columns) / tc::gemm4_kernel (tcgen05 sparse-conv implicit GEMM; %d launches per frame)' % len(recs),
                     'bound': 'tensor', 'achieved': useful / (t_ms * 1e-3) / 1e12, 'achieved_issued': issued / (t_ms * 1e-3) / 1e12,
                     'peak': peak, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; launches timed in isolation)' if peaks else 'fallback 1.6 PF/s burst',
                     'frac_of_sustained': useful / (t_ms * 1e-3) / 1e12 / peaks.get('bf16_tflops_sustained', 1400.0),
