@@ -57,8 +57,9 @@ def _check_kinds(name, ctypes_of, args):
                 assert a.dtype in _ELEM[base], '%s: argument %d is %s but the tensor holds %s' % (name, i, ct, a.dtype)
             elif isinstance(a, torch.Tensor) and base == 'void' and _PARAM_NAMES.get(name) and _PARAM_NAMES[name][i] not in _VOID_ANY \
                     and (name, _PARAM_NAMES[name][i]) not in _VOID_ANY_FN:
-                assert a.dtype == torch.float16, '%s: %s is an fp16 matrix in the library but the tensor holds %s' % (
-                    name, _PARAM_NAMES[name][i], a.dtype)
+                want = torch.bfloat16 if name.endswith('_bf16') else torch.float16       # the `_bf16` twins take bf16 matrices
+                assert a.dtype == want, '%s: %s is a %s matrix in the library but the tensor holds %s' % (
+                    name, _PARAM_NAMES[name][i], want, a.dtype)
             elif isinstance(a, ctypes.Array) and base in _CELEM:
                 assert a._type_ in _CELEM[base], '%s: argument %d is %s but the host array holds %s' % (name, i, ct, a._type_)
         elif ct in ('float', 'double'):
@@ -149,7 +150,7 @@ class _FusionLib:
         y = F.conv2d(xx, wt, shift, stride=stride, padding=1)
         y = (torch.relu(y) if _val(relu) else y).permute(0, 2, 3, 1)
         o = out.view(batch, y.shape[1], y.shape[2], ldo)
-        o[..., :cout_store] = y[..., :cout_store].half()
+        o[..., :cout_store] = y[..., :cout_store].to(o.dtype)
         return 0
 
     # ------------------------------------------------------------------ isf_gemm_f16
@@ -690,6 +691,28 @@ class RowsAroundMixin:
             o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
         out.copy_(o[:, :h, :w].reshape(batch * h * w, c).to(out.dtype))
         return 0
+
+
+def _bf16_twin(f16_name, tensor_args):
+    """`_bf16` entry point = the statement of its f16 sibling (written on .float() copies, storing in the output's own 16-bit
+    type) with the SAME parameter list, after checking that the 16-bit tensors really are bf16."""
+    import inspect
+    f = getattr(_FusionLib, f16_name)
+    names = list(inspect.signature(f).parameters)[1:]
+
+    def twin(self, *args):
+        for n in tensor_args:
+            t = args[names.index(n)]
+            assert t is None or t.dtype in (torch.bfloat16, torch.float32), '%s_bf16: %s holds %s' % (f16_name, n, t.dtype)
+        return f(self, *args)
+    twin.__signature__ = inspect.signature(f)
+    return twin
+
+
+_FusionLib.isf_gemm_bf16 = _bf16_twin('isf_gemm_f16', ('a', 'w', 'residual', 'out_f16'))
+_FusionLib.isf_conv3x3_nhwc_bf16 = _bf16_twin('isf_conv3x3_nhwc_f16', ('x', 'wpk', 'out'))
+_FusionLib.isf_window_attention_bf16 = _bf16_twin('isf_window_attention', ('qkv', 'out'))
+_FusionLib.isf_cam2bev_bf16 = _bf16_twin('isf_cam2bev', ('feat', 'out'))
 
 
 class FakeLib(_FusionLib, SparseMixin, VoxelMixin, RowsAroundMixin):

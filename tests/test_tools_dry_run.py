@@ -107,6 +107,17 @@ def test_bench_gemm_layers_dry_run(monkeypatch, capsys):
     assert L.lib().isf_set_option(b'gemm_mt', 3) == 0
 
 
+def test_bench_hsf_bf16_dry_run(monkeypatch, capsys):
+    """configs[2] on the bf16 entry points (isf_*_bf16): host plumbing of _lib.set_dtype through the HSF modules on the emulator."""
+    import torch
+    from isfusion_b200 import _lib as L
+    try:
+        line = _run_tool('bench_hsf', ['--steps', '1', '--warmup', '0', '--points', '3000', '--dtype', 'bf16'], monkeypatch, capsys)
+    finally:
+        L.set_dtype(torch.float16)
+    assert line['dtype'] == 'bf16' and line['config']['region_levels'] == 1
+
+
 def test_bench_hsf_dry_run(monkeypatch, capsys):
     line = _run_tool('bench_hsf', ['--steps', '1', '--warmup', '0', '--points', '3000', '--levels', '2'], monkeypatch, capsys)
     assert line['config']['region_levels'] == 2 and len(line['out_shapes']) == 2
