@@ -152,3 +152,39 @@ def test_backward_and_input_entry_points_validate_arguments():
     # a transforming segment needs its calibration
     assert lib.isf_debug_merge_sweeps_host(raw, 10, 5, 1, L.host_i32([0, 10]), None, None, one, L.host_i32([1]), ctypes.c_float(1.0), None, out,
                                            ctypes.byref(cnt)) == 1
+
+
+def test_bf16_entry_points_and_dtype_switch():
+    """the `_bf16` twins are exported, resolve through _lib.fn16 by tensor type, validate their arguments without a GPU, and the
+    library's options for the round-2 schedules accept / reject values as documented."""
+    import pytest
+    import torch
+    from isfusion_b200 import _lib as L
+    lib = L.lib()
+    for name in ('isf_gemm_bf16', 'isf_conv3x3_nhwc_bf16', 'isf_window_attention_bf16', 'isf_cam2bev_bf16'):
+        assert hasattr(lib, name), name
+    assert L.fn16('isf_gemm_f16', torch.float16).__name__ == 'isf_gemm_f16'
+    assert L.fn16('isf_gemm_f16', torch.bfloat16).__name__ == 'isf_gemm_bf16'
+    assert L.fn16('isf_cam2bev', torch.bfloat16).__name__ == 'isf_cam2bev_bf16'
+    with pytest.raises(L.IsfError):
+        L.fn16('isf_gemm_f16', torch.float32)
+    with pytest.raises(L.IsfError):
+        L.set_dtype(torch.float32)
+    assert L.DTYPE == torch.float16
+    L.set_dtype(torch.bfloat16)
+    try:
+        assert L.DTYPE == torch.bfloat16
+    finally:
+        L.set_dtype(torch.float16)
+    # argument validation happens before any CUDA call (k not a multiple of 8; misaligned leading dimension)
+    assert lib.isf_gemm_bf16(None, None, 4, 12, 64, 64, None, None, None, 0, 0, None, None, ctypes.c_float(0), None, None, 64, None, None,
+                             None) != 0
+    for name, good, bad in (('gemm_pair', (0, 1, 64, 128, 256), (2, 512)), ('gemm_mma2', (0, 1), (2,)), ('gemm_wpc', (0, 1, 2), (3,)),
+                            ('gemm_v4_32', (0, 1, 2), (3,)), ('i2s_tc', (0, 1), (2,)), ('gemm_rev', (0, 1), (2,))):
+        for v in bad:
+            assert lib.isf_set_option(name.encode(), v) != 0, (name, v)
+        for v in good:
+            assert lib.isf_set_option(name.encode(), v) == 0, (name, v)
+    # back to the shipped defaults
+    for name, v in (('gemm_pair', 128), ('gemm_mma2', 1), ('gemm_wpc', 0), ('gemm_v4_32', 1), ('i2s_tc', 0), ('gemm_rev', 0)):
+        assert lib.isf_set_option(name.encode(), v) == 0
