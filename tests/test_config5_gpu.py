@@ -41,5 +41,8 @@ def test_neck_on_the_005_voxel_256_bev_geometry():
     rel = lambda a, b: ((a.float().cpu() - b).norm() / b.norm()).item()
     assert gf[0].shape == rf[0].shape == (1, 128, 256, 256) and gf[1].shape == rf[1].shape == (1, 256, 128, 128)
     overlap = len(set(ref.fusion_encoder._dbg['top_idx'][0].tolist()) & set(net.fusion_encoder._dbg['top_idx'][0].cpu().tolist())) / 200.0
+    print('config-5 geometry parity: heat-map %.2e, top-200 overlap %.3f, feat0 %.2e, feat1 %.2e' % (
+        rel(ghm, rhm), overlap, rel(gf[0], rf[0]), rel(gf[1], rf[1])))
     assert rel(ghm, rhm) < 5e-3 and overlap > 0.9
+    # the selection is not forced here: a swapped near-tie instance moves the maps by ~1e-2 around it
     assert rel(gf[0], rf[0]) < 1e-2 and rel(gf[1], rf[1]) < 1e-2

@@ -11,11 +11,20 @@ from oracle import model as omodel
 from oracle import sst_ops as ss
 
 pytestmark = pytest.mark.gpu
+# north_star's bar is 1e-3 relative: measured on B200 (profiles/call34_r02.log) SST level 5.2-6.1e-4, instance->scene block 4.5e-4,
+# SECONDV2 stage 1 (6 convs + the stride-2 conv) 7.7e-4 / 8.4e-4; stage 2 stacks 5 more fp16 conv outputs on stage 1's (9.6e-4)
+SST_BOUND, I2S_BOUND, SECOND_BOUND = 1e-3, 1e-3, (1e-3, 1.5e-3)
 
 
 def rel(a, b):
     a, b = a.float().cpu(), b.float().cpu()
     return ((a - b).norm() / b.norm().clamp(min=1e-12)).item(), (a - b).abs().max().item()
+
+
+def chk(name, value, bound):
+    """asserted bound next to the measured value (pytest -s shows the line; profiles/call*_r02.log keep them)."""
+    print('parity %-46s %.2e  (bound %.1e)' % (name, value, bound))
+    assert value < bound, (name, value, bound)
 
 
 def build_pair(seed=0, shuffle=False):
@@ -84,7 +93,7 @@ def test_sst_level_parity(g, c, b):
     out = gn(gl(feats.half().cuda(), None, b))[0]
     assert out.shape == ref.shape
     r, m = rel(out, ref)
-    assert r < 3e-3, (r, m)       # two post-norm layers in fp16 storage / fp32 accumulate
+    chk('SST level g=%d c=%d rel-L2' % (g, c), r, SST_BOUND)       # 2 encoder layers: 10 GEMMs, 2 attention cores, 4 LayerNorms
 
 
 def test_cam2bev_parity():
@@ -169,8 +178,7 @@ def test_instance_to_scene_parity():
     L.check(L.lib().isf_channel_attention(L.ptr(sc), C, L.ptr(qi), C, B, G, C, L.ptr(out), C, L.ptr(ws),
                                           ctypes.c_size_t(ws.numel()), L.stream()))
     r, m = rel(out.permute(0, 3, 1, 2), want)
-    print('i2s rel %.2e max %.2e' % (r, m))
-    assert r < 3e-3, (r, m)
+    chk('instance->scene attention block rel-L2', r, I2S_BOUND)
 
 
 @pytest.mark.parametrize('B,T,K', [(1, 32400, 200), (2, 32400, 200), (1, 8100, 200), (3, 1000, 150), (1, 127, 8), (1, 129, 208)])
@@ -224,10 +232,11 @@ def test_secondv2_parity():
     rt, rc, rf = ref([x], 'stage1')
     xt = x.half().cuda().contiguous(memory_format=torch.channels_last)
     gt, _, gf = net([xt], 'stage1')
-    assert rel(gf, rf)[0] < 3e-3 and rel(gt, rt)[0] < 3e-3
+    chk('SECONDV2 stage1 block0 (6 convs) rel-L2', rel(gf, rf)[0], SECOND_BOUND[0])
+    chk('SECONDV2 stage1 downsample rel-L2', rel(gt, rt)[0], SECOND_BOUND[0])
     r2 = ref([rt.view(1, 30, 30, 256).permute(0, 3, 1, 2)], 'stage2')[2]
     g2 = net([gt.view(1, 30, 30, 256).permute(0, 3, 1, 2)], 'stage2')[2]
-    assert rel(g2, r2)[0] < 5e-3
+    chk('SECONDV2 stage2 (5 convs more) rel-L2', rel(g2, r2)[0], SECOND_BOUND[1])
 
 
 @pytest.mark.parametrize('npts,batch', [(20000, 1), (12000, 2)])

@@ -23,6 +23,12 @@ def _g(name):
     return np.load(os.path.join(HERE, 'golden', name))
 
 
+def chk(name, value, bound):
+    """asserted bound next to the measured value (pytest -s shows the line; profiles/call*_r02.log keep them)."""
+    print('parity %-52s %.2e  (bound %.1e)' % (name, value, bound))
+    assert value < bound, (name, value, bound)
+
+
 def _rel(a, b):
     a = a.float().cpu().numpy() if isinstance(a, torch.Tensor) else a
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
@@ -49,7 +55,7 @@ def test_sparse_encoder_against_reference_run():
     assert [int(e.indices.shape[0]) for e in enc] == g['stage_voxels'].tolist()
     assert np.array_equal(enc[1].indices.cpu().numpy(), g['stage1_coors'])   # output sites: bit-exact, same order
     assert out.shape == g['out'].shape
-    assert _rel(out, g['out']) < 3e-3                                   # 21 stacked fp16 layers
+    chk('SparseEncoder vs reference run (21 fp16 layers)', _rel(out, g['out']), 1e-3)       # measured 7.9e-4
 
 
 def test_fusion_encoder_against_reference_run():
@@ -70,7 +76,7 @@ def test_fusion_encoder_against_reference_run():
                     pts_backbone=bb, lidar2img=inp['lidar2img'], img_aug_matrix=inp['img_aug_matrix'],
                     lidar_aug_matrix=inp['lidar_aug_matrix'])
     assert tuple(feats[0].shape) == g['feat0'].shape and tuple(feats[1].shape) == g['feat1'].shape
-    assert _rel(hm, g['heatmap']) < 5e-3
+    chk('fusion encoder heat-map vs reference run', _rel(hm, g['heatmap']), 1e-3)       # measured 5.8e-4
     # the CPU emulation of the product's fp16 storage alone gives 1.0e-2 / 1.5e-2 on this fixture (test_host_logic_cpu.py)
     assert _rel(feats[0], g['feat0']) < 3e-2 and _rel(feats[1], g['feat1']) < 3e-2
     neck = fpn(feats)[0]
@@ -87,7 +93,7 @@ def test_transfusion_head_against_reference_run():
     x = gc.head_input().half().cuda().contiguous(memory_format=torch.channels_last)
     res = net([x])
     p = res[0][0]
-    assert _rel(p['dense_heatmap'], g['dense_heatmap']) < 5e-3
+    chk('head dense heat-map vs reference run', _rel(p['dense_heatmap'], g['dense_heatmap']), 1e-3)       # measured 4.4e-4
     hw = gc.BEV * gc.BEV
     for b in range(2):
         # proposal identity = (class, cell): class from query_labels, cell from the integer part of the query position
@@ -121,7 +127,9 @@ def test_fusion_encoder_at_config_size_against_reference_samples():
     for name, t, bar in (('heatmap', hm, 5e-3), ('feat0', feats[0], 1e-2), ('feat1', feats[1], 1e-2)):
         assert list(t.shape) == g[name + '_shape'].tolist()
         got = t.float().cpu().numpy().reshape(-1)[gc.sample_positions(t.shape)]
-        assert _rel(got, g[name + '_samples']) < bar, name
+        # feature maps: a near-tie among the top-200 picks (fp16 vs fp32 heat-map) swaps an instance and moves the maps around it
+        # ("the discrete selection"), hence the wider bar on a run whose selection is not forced
+        chk('fusion encoder @180x180 %s vs reference samples' % name, _rel(got, g[name + '_samples']), bar)
 
 
 def test_generalized_lss_fpn_against_reference_run():
@@ -130,7 +138,8 @@ def test_generalized_lss_fpn_against_reference_run():
     net = gc.fill_state(GeneralizedLSSFPN(**gc.lss_cfg()), 8).cuda().eval()
     outs = net([t.cuda() for t in gc.lss_inputs()])
     assert len(outs) == 2
-    assert _rel(outs[0][:, ::8], g['out0_c8']) < 3e-3 and _rel(outs[1][:, ::4], g['out1_c4']) < 3e-3
+    chk('LSS-FPN level 0 vs reference run', _rel(outs[0][:, ::8], g['out0_c8']), 1e-3)       # measured 6.0e-4
+    chk('LSS-FPN level 1 vs reference run', _rel(outs[1][:, ::4], g['out1_c4']), 1e-3)       # measured 4.4e-4
 
 
 @pytest.mark.parametrize('g', [200, 256])
@@ -152,7 +161,7 @@ def test_channel_attention_on_grids_up_to_256(g):
     sp, ip = s.float().permute(0, 3, 1, 2), i.float().permute(0, 3, 1, 2)
     want = sp + torch.softmax(sp @ ip.transpose(2, 3), dim=-1) @ ip
     got = out.float().permute(0, 3, 1, 2)
-    assert ((got - want).norm() / want.norm()).item() < 3e-3
+    chk('channel attention g=%d vs fp32' % g, ((got - want).norm() / want.norm()).item(), 1e-3)       # measured 2.1e-4
 
 
 def test_detector_simple_test_end_to_end_against_the_oracle_pipeline():
@@ -212,7 +221,7 @@ def test_swin_backbone_against_reference_run():
     assert len(outs) == 3
     for i, o in enumerate(outs):
         assert tuple(o.shape) == g['out%d' % i].shape
-        assert _rel(o, g['out%d' % i]) < 2e-2, i
+        chk('Swin stage %d (torch attention) vs reference run' % i, _rel(o, g['out%d' % i]), 5e-3)
 
 
 @pytest.mark.parametrize('nq,nk', [(200, 32400), (37, 576), (16, 208), (1, 209)])
@@ -233,7 +242,7 @@ def test_query_scene_attention_kernel_against_sdpa(nq, nk):
     finally:
         H.OWN_ATTENTION = H_DEFAULT
     assert got.shape == want.shape == (b, nq, c)
-    assert ((got - want).norm() / want.norm()).item() < 3e-3
+    chk('query->scene attention vs SDPA', ((got - want).norm() / want.norm()).item(), 1e-3)       # measured 1.5-4.0e-4
 
 
 def test_swin_own_window_attention_against_torch_path_and_reference():
@@ -253,5 +262,5 @@ def test_swin_own_window_attention_against_torch_path_and_reference():
     finally:
         B.OWN_WINDOW_ATTENTION = B_DEFAULT
     for i, (a, r) in enumerate(zip(out, ref)):
-        assert ((a - r).norm() / r.norm()).item() < 5e-3, i
-        assert _rel(a, g['out%d' % i]) < 2e-2, i
+        chk('Swin stage %d own vs torch attention' % i, ((a - r).norm() / r.norm()).item(), 3.5e-3)       # measured 1.5 / 2.1 / 2.6e-3 (12 fp16 blocks deep)
+        chk('Swin stage %d vs reference run' % i, _rel(a, g['out%d' % i]), 5e-3)       # measured 2.0 / 2.6 / 3.2e-3
