@@ -123,7 +123,7 @@ def test_cam2bev_parity():
     r, m = rel(out, ref)
     print('cam2bev rel %.2e max %.2e (ref max %.2f, nonzero cells %d)' % (r, m, ref.abs().max(), (ref.abs().sum(1) > 0).sum()))
     assert (ref.abs().sum(1) > 0).sum() > 1000
-    assert r < 2e-3 and m < 2e-3 * max(1.0, ref.abs().max().item())
+    assert r < 1e-3 and m < 2e-3 * max(1.0, ref.abs().max().item())       # measured rel-L2 2.1e-4
 
 
 def test_heatmap_topk():

@@ -115,7 +115,7 @@ def test_sparse_encoder_parity():
     den = rs.norm().item()
     mx = (gs.float().cpu() - rs).abs().max().item()
     print('sparse encoder rel l2 err %.3e  max abs %.3e (max ref %.3f)' % (num / den, mx, rs.abs().max().item()))
-    assert num / den <= 3e-3, (num / den)
+    assert num / den <= 1e-3, (num / den)       # measured 2.1e-4
 
 
 def test_sparse_encoder_parity_on_the_config_grid():
