@@ -87,6 +87,7 @@ extern int g_isf_gemm_pair;       // isf_set_option("gemm_pair", 0|1|64|128|256)
 extern int g_isf_gemm_zskip;      // isf_set_option("gemm_zskip", 0|1): zero-skip of the v4 producers
 extern int g_isf_gemm_mt;         // isf_set_option("gemm_mt", 1|2): 128-row sub-tiles per CTA tile of the sparse-conv GEMM
 extern int g_isf_gemm_debug;      // isf_set_option("gemm_debug", bits): timing experiments (tc_gemm.cuh GemmParams::debug)
+extern int g_isf_gemm_trim;       // isf_set_option("gemm_trim", 0|1): fewest CTAs that keep the number of tile rounds (default 0: +1 % throughput with 3 frames in flight, -3.5 % per launch)
 extern int g_isf_gemm_mma2;       // isf_set_option("gemm_mma2", 0|1): two MMA-issuing warps in the 256-row CTA-pair kernels (tc_gemm5.cuh)
 extern int g_isf_i2s_tc;          // isf_set_option("i2s_tc", 0|1): instance -> scene attention on the tcgen05 kernel (i2s_tc.cu; default 0: measured 3x slower than the mma.sync kernel)
 extern int g_isf_nbr_rows;        // isf_set_option("nbr_rows", 0|1): row-per-thread neighbour-table kernel (opt-in)

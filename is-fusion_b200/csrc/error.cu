@@ -39,6 +39,7 @@ int g_isf_gemm_rev = 0;
 int g_isf_gemm_pair = 128;
 int g_isf_i2s_tc = 0;
 int g_isf_gemm_mma2 = 1;
+int g_isf_gemm_trim = 0;
 int g_isf_gemm_v4_32 = 1;
 int g_isf_gemm_v4 = 2;
 int g_isf_gemm_ln_fast = 1;
@@ -70,6 +71,10 @@ extern "C" int isf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_pair") == 0 && (value == 0 || value == 1 || value == 64 || value == 128 || value == 256)) {
     g_isf_gemm_pair = value;
+    return ISF_OK;
+  }
+  if (name && strcmp(name, "gemm_trim") == 0 && (value == 0 || value == 1)) {
+    g_isf_gemm_trim = value;
     return ISF_OK;
   }
   if (name && strcmp(name, "gemm_mma2") == 0 && (value == 0 || value == 1)) {

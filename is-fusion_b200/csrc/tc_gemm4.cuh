@@ -425,6 +425,12 @@ static int launch_gemm4_impl(const GemmParams& p, int m_upper, cudaStream_t st) 
   int gx = isf_num_sms() * CTAS / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
+  // the fewest CTAs that finish in the same number of tile rounds: 780 tiles on 148 CTAs are 6 rounds, 130 CTAs do them in 6 as
+  // well - the SMs left over run the small kernels of the other frames in flight (isf_set_option("gemm_trim", 0) = all CTAs)
+  if (::g_isf_gemm_trim && p.nbr != nullptr) {
+    const int rounds = (tiles + gx - 1) / gx;
+    gx = (tiles + rounds - 1) / rounds;
+  }
   kern<<<dim3(gx, n_tiles), V4_THREADS, SL::TOTAL, st>>>(p, tm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { isf_set_error("gemm v4 launch: %s", cudaGetErrorString(e)); return ISF_ERR_CUDA; }

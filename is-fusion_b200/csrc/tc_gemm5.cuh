@@ -442,6 +442,10 @@ static int launch_gemm5(const GemmParams& p, int m_upper, cudaStream_t st) {
   int pairs = isf_num_sms() * CTAS / 2;
   if (pairs < 1) pairs = 1;
   if (pairs > supers) pairs = supers;
+  if (::g_isf_gemm_trim) {      // the fewest pairs that finish in the same number of tile rounds (tc_gemm4.cuh)
+    const int rounds = (supers + pairs - 1) / pairs;
+    pairs = (supers + rounds - 1) / rounds;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs, 1);

@@ -39,7 +39,7 @@ def main():
     oname = lambda o: 'storage' if o is None else 'ord%d' % o
     variants = [(oname(o), None, o) for o in orders]
     variants += [(t, t.split('='), default_order) for t in args.opt.split(',') if t]
-    defaults = {'gemm_mt': 3, 'gemm_debug': 0, 'gemm_cluster': 1, 'nbr_rows': 1, 'gemm_ln_fast': 1, 'gemm_v4': 2, 'gemm_zskip': 0, 'gemm_wpc': 0, 'gemm_rev': 0, 'gemm_v4_32': 1, 'gemm_pair': 128, 'gemm_mma2': 1}
+    defaults = {'gemm_mt': 3, 'gemm_debug': 0, 'gemm_cluster': 1, 'nbr_rows': 1, 'gemm_ln_fast': 1, 'gemm_v4': 2, 'gemm_zskip': 0, 'gemm_wpc': 0, 'gemm_rev': 0, 'gemm_v4_32': 1, 'gemm_pair': 128, 'gemm_mma2': 1, 'gemm_trim': 0}
     cols, ref_out = {}, None
     for name, opt, order in variants:
         if opt:
