@@ -298,6 +298,11 @@ int isf_spconv_implicit_gemm_ordered(const void* feats_in, int cin, const void* 
                                      const int* nbr_ordered, long long nbr_stride, int taps, int v_out,
                                      const int* v_out_dev, const int* row_perm, const float* scale, const float* shift,
                                      const void* residual, int ldr, int relu, void* out_f16, int ldo, void* stream);
+/* Dynamic tile scheduling (no reference counterpart): hands the NEXT isf_spconv_implicit_gemm[_ordered] call of this host thread
+ * a device buffer of two ints that is zero on entry; the kernel's CTAs then draw their row tiles from it (densest tiles first)
+ * instead of walking them round-robin, and leave it zeroed.  One buffer per rulebook: launches that share it must be
+ * stream-ordered.  Without the call (or with NULL) the tiles are walked round-robin; results are bit-identical either way. */
+int isf_spconv_tile_counter(int* counter2);
 int isf_sparse_to_dense(const void* feats, const int* indices, int v, int c, int batch, int D, int H, int W,
                         void* out, void* stream);
 int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, const int* v_dev, int c, int D, int H, int W,

@@ -97,6 +97,7 @@ extern int g_isf_nbr_rows;        // isf_set_option("nbr_rows", 0|1): row-per-th
 // output encoding (tcgen05 kind::f16 takes either format at the same rate; accumulation, epilogue and softmax stay fp32).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+int* isf_take_tile_counter();               // error.cu: the counter handed over by isf_spconv_tile_counter (consumed), or nullptr
 int isf_bf16_mode();                       // error.cu: 1 inside a `_bf16` entry point of this thread
 struct IsfBf16Scope { IsfBf16Scope(); ~IsfBf16Scope(); };
 __device__ __forceinline__ float2 isf_unpack2(unsigned int w, bool bf16) {

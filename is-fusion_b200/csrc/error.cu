@@ -29,6 +29,10 @@ int g_isf_gemm_cluster = 1;
 int g_isf_tile_order_drop_bits = 0;
 int g_isf_nbr_rows = 1;
 int g_isf_gemm_mt = 3;
+static thread_local int* t_isf_tile_ctr = nullptr;
+int* isf_take_tile_counter() { int* c = t_isf_tile_ctr; t_isf_tile_ctr = nullptr; return c; }
+// see include/isfusion_b200.h
+extern "C" int isf_spconv_tile_counter(int* counter2) { t_isf_tile_ctr = counter2; return ISF_OK; }
 static thread_local int t_isf_bf16 = 0;
 int isf_bf16_mode() { return t_isf_bf16; }
 IsfBf16Scope::IsfBf16Scope() { ++t_isf_bf16; }

@@ -663,6 +663,7 @@ extern "C" int isf_spconv_implicit_gemm(const void* feats_in, int cin, const voi
   p.scale = scale; p.shift = shift; p.residual = (const __half*)residual; p.ldr = ldr;
   p.act = relu ? tc::ACT_RELU : tc::ACT_NONE;
   p.out = (__half*)out_f16; p.ldo = ldo;
+  p.tile_ctr = isf_take_tile_counter();
   int rc = tc::dispatch_gemm(p, cout, v_out, (cudaStream_t)stream);
   isf_count_launch(1);
   return rc;
@@ -864,6 +865,7 @@ extern "C" int isf_spconv_implicit_gemm_ordered(const void* feats_in, int cin, c
   p.out_rows = row_perm;
   p.act = relu ? tc::ACT_RELU : tc::ACT_NONE;
   p.out = (__half*)out_f16; p.ldo = ldo;
+  p.tile_ctr = isf_take_tile_counter();
   int rc = tc::dispatch_gemm(p, cout, v_out, (cudaStream_t)stream);
   isf_count_launch(1);
   return rc;

@@ -275,6 +275,7 @@ struct GemmParams {
   float* out_f32;         // [m, ldo] fp32 (may be nullptr)
   int ldo;
   const int* out_rows;    // optional scatter: output row index per m (e.g. window -> flat), -1 = skip
+  int* tile_ctr;          // tc_gemm4 / tc_gemm5: int[2] zeroed device buffer for dynamic tile scheduling (isf_spconv_tile_counter), or nullptr
   int bf16;               // 16-bit operands / residual / output are bf16 (else fp16); dense GEMMs only (isf_gemm_bf16)
   int wpc;                // tc_gemm4.cuh: producer warps per K chunk (1 or 2) of the warp-per-chunk mapping
   int rev;                // tc_gemm4.cuh: tiles walked from the last one down (isf_set_option("gemm_rev"))

@@ -77,6 +77,16 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
   // pattern order the densest tiles sit at the end: walking them first leaves the cheap ones for the partial last round)
   const bool rev = p.rev != 0;
 #define V4_TILE(idx) (rev ? num_tiles - 1 - (idx) : (idx))
+  // Dynamic tile scheduling (p.tile_ctr, isf_spconv_tile_counter): the CTAs draw positions of the tile sequence from a global counter
+  // instead of taking every gridDim.x-th one, and walk it from the LAST tile down (under the neighbour-pattern order the densest
+  // tiles sit at the end: the cheap ones then fill the tail).  Static round-robin leaves the longest CTA 1.42x / 1.16x / 1.19x
+  // above the mean on stages 2 / 3 / 4 of the bench frame (tile cost = 1 ... 27 kernel offsets), drawing 1.11x / 1.05x / 1.13x
+  // (tests/analysis model).  Producer thread 0 draws two tiles ahead (the atomic's latency hides behind a tile's
+  // gather loop) into a ring of 8 positions in shared memory that the three roles read; position >= num_tiles = stop.
+  const bool dyn = p.tile_ctr != nullptr && gridDim.y == 1;
+  volatile int* ids = (volatile int*)(tap_flag + 48);        // [8] drawn positions, indexed by (iteration & 7)
+#define V4_POS(it) (dyn ? ids[(it) & 7] : (int)blockIdx.x + (it) * (int)gridDim.x)
+#define V4_TILE_OF(pos) (dyn ? num_tiles - 1 - (pos) : V4_TILE(pos))
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], (WPC ? 32 * p.wpc : PRODUCERS) + 1); mbar_init(&empty_bar[s], 1); }
@@ -89,6 +99,11 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     fence_barrier_init();
   }
   if (warp == V4_MMA_WARP) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (dyn && tid == 32) {
+    const int base = atomicAdd(p.tile_ctr, 2);
+    ids[0] = base;
+    ids[1] = base + 1;
+  }
   for (int c = tid; c < BN; c += V4_THREADS) {
     vec[c] = p.scale ? p.scale[n0 + c] : 1.f;
     vec[BN + c] = p.shift ? p.shift[n0 + c] : 0.f;
@@ -117,8 +132,9 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     // gather loop instead of sitting between two tiles (where only STAGES chunks of work are queued for the tensor core)
     int nv[NVR];
     if (gather) {
-      const long long prow = (long long)V4_TILE((int)blockIdx.x) * TILE_M + r;
-      const bool pok = (int)blockIdx.x < num_tiles && prow < m_total;
+      const int pos0 = V4_POS(0);
+      const long long prow = (long long)V4_TILE_OF(pos0) * TILE_M + r;
+      const bool pok = pos0 < num_tiles && prow < m_total;
 #pragma unroll
       for (int u = 0; u < NVR; ++u) {
         const int t = thalf + TSPLIT * u;
@@ -126,8 +142,10 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       }
     }
     int it = 0;
-    for (int tidx = blockIdx.x; tidx < num_tiles; tidx += gridDim.x, ++it) {
-      const int tile = V4_TILE(tidx);
+    for (;; ++it) {
+      const int tidx = V4_POS(it);
+      if (tidx >= num_tiles) break;
+      const int tile = V4_TILE_OF(tidx);
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
       const int row0 = tile * TILE_M;
@@ -170,8 +188,8 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int n_act = tap_flag[32];
       if (gather) {      // prefetch the next tile's neighbour ids (consumed after this tile's gather loop)
-        const int nidx = tidx + (int)gridDim.x;
-        const long long prow = (long long)V4_TILE(nidx) * TILE_M + r;
+        const int nidx = V4_POS(it + 1);
+        const long long prow = (long long)V4_TILE_OF(nidx) * TILE_M + r;
         const bool pok = nidx < num_tiles && prow < m_total;
 #pragma unroll
         for (int u = 0; u < NVR; ++u) {
@@ -179,6 +197,8 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
           nv[u] = (pok && t < p.taps) ? p.nbr[(long long)t * p.nbr_stride + prow] : -1;
         }
       }
+      int drawn = 0;
+      if (dyn && tid == 0) drawn = atomicAdd(p.tile_ctr, 1);       // position of iteration it + 2 (consumed after the gather loop)
       if constexpr (WPC) {
         // a chunk is gathered by G = p.wpc (1 or 2) producer warps that OWN its smem stage: warps [G s, G s + G) serve stage s and
         // nothing else, so each of them sees every phase of that stage's empty barrier in order (a warp that skipped phases would
@@ -278,14 +298,20 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
           cp_async_mbar_arrive(&full_bar[s]);
         }
       }
+      if (dyn && tid == 0) ids[(it + 2) & 7] = drawn;      // read by the roles after the next tile's first producer barrier at the earliest
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    if (dyn && tid == 0) {      // every CTA has stopped drawing when it gets here: the last one re-arms the counter for the next launch
+      __threadfence();
+      if (atomicAdd(p.tile_ctr + 1, 1) == (int)gridDim.x - 1) { p.tile_ctr[0] = 0; p.tile_ctr[1] = 0; }
+    }
   } else if (warp == V4_MMA_WARP) {
     // ================================================================ MMA issuer
     const uint32_t idesc = make_idesc_f16(BM, BN) | (p.bf16 ? IDESC_AB_BF16 : 0u);
     uint32_t ca = 0;
     int it = 0;
-    for (int tidx = blockIdx.x; tidx < num_tiles; tidx += gridDim.x, ++it) {
+    for (;; ++it) {
+      if (V4_POS(it) >= num_tiles) break;
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
       mbar_wait_b(&list_full[buf], ubuf & 1);
@@ -313,8 +339,10 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
     // ================================================================ epilogue (warps 9-12; TMEM lane quarter = warp % 4)
     const int r = (warp & 3) * 32 + lane;
     int it = 0;
-    for (int tidx = blockIdx.x; tidx < num_tiles; tidx += gridDim.x, ++it) {
-      const int tile = V4_TILE(tidx);
+    for (;; ++it) {
+      const int tidx = V4_POS(it);
+      if (tidx >= num_tiles) break;
+      const int tile = V4_TILE_OF(tidx);
       const int buf = it & 1;
       const uint32_t ubuf = (uint32_t)(it >> 1);
 #pragma unroll 1
@@ -400,6 +428,8 @@ __global__ void __launch_bounds__(V4_THREADS, CTAS) gemm4_kernel(const GemmParam
   __syncthreads();
   if (warp == V4_MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
 #undef V4_TILE
+#undef V4_POS
+#undef V4_TILE_OF
 }
 
 template <int BN, int STAGES, int CTAS, int MT, bool WPC>

@@ -78,7 +78,7 @@ class SparseConvTensor:
 class Rulebook:
     """output indices + neighbour table of one (coordinate set, kernel geometry)."""
     __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'num_dev', 'pairs', 'nbr_ordered',
-                 'row_perm')
+                 'row_perm', 'tile_ctr')
 
     def __init__(self, out_indices, out_shape, nbr, nbr_stride, taps, num_out, num_dev=None):
         self.out_indices, self.out_shape, self.nbr = out_indices, out_shape, nbr
@@ -86,12 +86,14 @@ class Rulebook:
         self.num_dev = num_dev                                                    # device-side valid-row count
         self.pairs = None
         self.nbr_ordered = self.row_perm = None     # tile order (TILE_ORDER): regrouped table + tile slot -> storage row
+        self.tile_ctr = None                        # int32[2], zero between launches: dynamic tile scheduling (DYNAMIC_TILES)
 
 
 # Opt-in tile order of the implicit GEMM (csrc/spconv.cu "Tile order", tests/analysis/tile_occupancy.py): None = rows in
 # None = storage order; an int = rows regrouped by neighbour pattern inside chunks of 2**TILE_ORDER consecutive rows
 # (31 = one global sort, the default: measured -12.5 % on the 21 implicit-GEMM launches of the bench frame, round 2).
 # Results are bit-identical either way.  Environment: ISF_TILE_ORDER=<int> | none.
+XX
 _to = os.environ.get('ISF_TILE_ORDER', '31')
 TILE_ORDER = None if _to in ('none', 'off', '') else int(_to)
 if os.environ.get('ISF_NBR_ROWS'):      # opt-in row-per-thread neighbour-table kernel (csrc/spconv.cu nbr_bitmap_rows_kernel)
@@ -355,6 +357,10 @@ def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, resid
     if out is None:
         out = torch.empty((rb.num_out, cout), dtype=torch.float16, device=feats.device)
     ldr = residual.stride(0) if residual is not None else 0
+    if DYNAMIC_TILES:
+        if rb.tile_ctr is None:
+            rb.tile_ctr = torch.zeros(2, dtype=torch.int32, device=feats.device)
+        L.check(L.lib().isf_spconv_tile_counter(L.ptr(rb.tile_ctr)))       # consumed by the GEMM call below
     if rb.row_perm is not None:
         L.check(L.lib().isf_spconv_implicit_gemm_ordered(
             L.ptr(feats), cin, L.ptr(w_packed), w_packed.shape[1], cout, L.ptr(rb.nbr_ordered),

@@ -449,6 +449,10 @@ class SparseMixin:
         out[rows] = acc.to(out.dtype)
         return 0
 
+    def isf_spconv_tile_counter(self, counter2):
+        assert counter2 is None or (counter2.dtype == torch.int32 and counter2.numel() == 2 and int(counter2.abs().sum()) == 0)
+        return 0
+
     def isf_spconv_implicit_gemm(self, feats, cin, w, kpad, cout, nbr, nbr_stride, taps, v_out, v_dev, scale, shift, residual, ldr,
                                  relu, out, ldo, stream):
         return self._implicit(feats, cin, w, kpad, cout, nbr, taps, v_out, v_dev, None, scale, shift, residual, relu, out)

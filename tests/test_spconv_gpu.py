@@ -262,9 +262,10 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
     _randomize_bn(mod)
     x = _rand_tensor([41, 128, 128], 40000, 64, 2, 11, clustered=True)
     f, c = torch.relu(x.features).half().cuda(), x.indices.cuda()
-    old = sp.TILE_ORDER
+    old, old_dyn = sp.TILE_ORDER, sp.DYNAMIC_TILES
     try:
         sp.TILE_ORDER = order
+        sp.DYNAMIC_TILES = False
         L.set_option('gemm_pair', 0)
         L.set_option('gemm_v4', 0)
         ref, _, _ = mod(f, c, 2)
@@ -288,6 +289,16 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
             o, _, _ = mod(f, c, 2)
             torch.cuda.synchronize()
             assert torch.equal(o, ref), (wpc, rev, v32, mt)
+        # dynamic tile scheduling (isf_spconv_tile_counter): twice per setting, the second run finds the counters re-armed
+        sp.DYNAMIC_TILES = True
+        for pair, v32 in ((0, 1), (0, 1), (128, 1), (128, 1), (1, 2), (1, 2)):
+            L.set_option('gemm_pair', pair)
+            L.set_option('gemm_v4_32', v32)
+            L.set_option('gemm_mt', 3)
+            o, _, _ = mod(f, c, 2)
+            torch.cuda.synchronize()
+            assert torch.equal(o, ref), ('dynamic tiles', pair, v32)
+        sp.DYNAMIC_TILES = False
         # CTA pairs (tcgen05.mma.cta_group::2, csrc/tc_gemm5.cuh): every column tile >= 64 / only 256 / 128-and-up, both walks
         for pair, rev, mt, mma2 in ((1, 0, 3, 1), (1, 1, 3, 0), (256, 0, 3, 1), (128, 0, 3, 1), (128, 0, 3, 0), (128, 0, 1, 1), (1, 0, 1, 0)):
             L.set_option('gemm_pair', pair)
@@ -306,4 +317,4 @@ def test_sparse_encoder_v4_schedule_bit_identical(order):
         L.set_option('gemm_wpc', 0)
         L.set_option('gemm_rev', 0)
         L.set_option('gemm_v4_32', 1)
-        sp.TILE_ORDER = old
+        sp.TILE_ORDER, sp.DYNAMIC_TILES = old, old_dyn
