@@ -93,13 +93,17 @@ class Rulebook:
 # None = storage order; an int = rows regrouped by neighbour pattern inside chunks of 2**TILE_ORDER consecutive rows
 # (31 = one global sort, the default: measured -12.5 % on the 21 implicit-GEMM launches of the bench frame, round 2).
 # Results are bit-identical either way.  Environment: ISF_TILE_ORDER=<int> | none.
-XX
 _to = os.environ.get('ISF_TILE_ORDER', '31')
 TILE_ORDER = None if _to in ('none', 'off', '') else int(_to)
 if os.environ.get('ISF_NBR_ROWS'):      # opt-in row-per-thread neighbour-table kernel (csrc/spconv.cu nbr_bitmap_rows_kernel)
     L.set_option('nbr_rows', int(os.environ['ISF_NBR_ROWS']))
 
 
+# Dynamic tile scheduling of the implicit GEMM (isf_spconv_tile_counter): the kernel's CTAs draw their row tiles from a counter
+# owned by the rulebook instead of walking them round-robin (32- / 64-column layers, tc::gemm4_kernel); bit-identical results.
+# Opt-in (ISF_DYNAMIC_TILES=1): measured -4 % on the stage-2 launches, -0.8 % on the 21 launches (call 36) against a CPU model that
+# promised -22 %: a tile's cost is dominated by its fixed part, not by its 1 ... 27 kernel offsets.
+DYNAMIC_TILES = os.environ.get('ISF_DYNAMIC_TILES', '0') == '1'
 TILE_ORDER_FUSED = os.environ.get('ISF_TILE_ORDER_FUSED', '1') != '0'   # sorted tensors: build the table in tile order directly
 
 
