@@ -36,8 +36,12 @@ class SparseBasicBlock(SparseModule):
         return self.bn2
 
     def forward(self, x):
-        if self.training:
-            raise L.IsfError('SparseBasicBlock: the fused CUDA path implements eval-mode BN only')
+        if self.training:      # ref sparse_block.py:117-134: conv1 -> bn1 -> relu -> conv2 -> bn2 -> (+ identity) -> relu, batch statistics
+            identity = x.features
+            out = self.conv1(x)
+            out = out.replace_feature(torch.relu(self.bn1(out.features)))
+            out = self.conv2(out)
+            return out.replace_feature(torch.relu(self.bn2(out.features) + identity))
         s1, b1 = fold_bn(self.bn1)
         s2, b2 = fold_bn(self.bn2)
         identity = x.features
@@ -179,9 +183,29 @@ class SparseEncoder(nn.Module):
         build(self.conv_out[0], cur)
         return events
 
+    def forward(self, voxel_features, coors, batch_size, *args, **kwargs):
+        """eval: the fused no-grad CUDA path; train: the same kernels under autograd (spconv.ImplicitGemmFunction), BatchNorm with
+        batch statistics over the active voxels, exact-size tensors (ref sparse_encoder.py:107-138)."""
+        if self.training and torch.is_grad_enabled():
+            return self.forward_train(voxel_features, coors, batch_size)
+        return self.forward_eval(voxel_features, coors, batch_size, *args, **kwargs)
+
+    def forward_train(self, voxel_features, coors, batch_size, sorted_coors=False):
+        x = SparseConvTensor(voxel_features.contiguous(), coors.int().contiguous(), self.sparse_shape, batch_size)
+        x.sorted = bool(sorted_coors)
+        x = self.conv_input(x)
+        encode_features = [x]
+        for encoder_layer in self.encoder_layers:
+            x = encoder_layer(x)
+            encode_features.append(x)
+        out = self.conv_out(encode_features[-1])
+        spatial_features = out.dense()
+        n, c, d, h, w = spatial_features.shape
+        return spatial_features.reshape(n, c * d, h, w), encode_features, {}
+
     @torch.no_grad()
-    def forward(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True,
-                num_voxels_dev=None, sorted_coors=False, rulebook_stream=None, prebuilt=None, **kwargs):
+    def forward_eval(self, voxel_features, coors, batch_size, swin_format=False, img_feats=None, dense=True,
+                     num_voxels_dev=None, sorted_coors=False, rulebook_stream=None, prebuilt=None, **kwargs):
         """voxel_features [V,C], coors [V,4] int32 (b,z,y,x) -> (spatial_features [B, C*D, H, W], encode_features, kwargs)"""
         coors = coors.int()
         feats = voxel_features if voxel_features.dtype == torch.float16 else voxel_features.half()

@@ -63,6 +63,12 @@ class SparseConvTensor:
         if self.num_dev is not None:
             return self.exact().dense(channels_first)
         f = self.features
+        if f.requires_grad and torch.is_grad_enabled():      # training: device-side index glue that autograd understands
+            d, h, w = self.spatial_shape
+            idx = self.indices.long()
+            out = torch.zeros((self.batch_size, d, h, w, f.shape[1]), dtype=f.dtype, device=f.device)
+            out = out.index_put((idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]), f)
+            return out.permute(0, 4, 1, 2, 3) if channels_first else out
         if f.dtype != torch.float16:
             f = f.half()
         L.require_cuda(f, self.indices)
@@ -78,7 +84,7 @@ class SparseConvTensor:
 class Rulebook:
     """output indices + neighbour table of one (coordinate set, kernel geometry)."""
     __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'num_dev', 'pairs', 'nbr_ordered',
-                 'row_perm', 'tile_ctr')
+                 'row_perm', 'tile_ctr', 'inverse')
 
     def __init__(self, out_indices, out_shape, nbr, nbr_stride, taps, num_out, num_dev=None):
         self.out_indices, self.out_shape, self.nbr = out_indices, out_shape, nbr
@@ -87,6 +93,7 @@ class Rulebook:
         self.pairs = None
         self.nbr_ordered = self.row_perm = None     # tile order (TILE_ORDER): regrouped table + tile slot -> storage row
         self.tile_ctr = None                        # int32[2], zero between launches: dynamic tile scheduling (DYNAMIC_TILES)
+        self.inverse = None                         # training: rulebook of the data gradient of a strided conv (inverse_rulebook)
 
 
 # Opt-in tile order of the implicit GEMM (csrc/spconv.cu "Tile order", tests/analysis/tile_occupancy.py): None = rows in
@@ -378,6 +385,105 @@ def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, resid
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Training: backward of the implicit GEMM.
+#   data gradient   din[i] = sum_k dout[o(k, i)] . W[k]^T  is the SAME kernel over the transposed rulebook: for a submanifold conv
+#                   the transposed table is the table itself with the kernel offsets mirrored (o at offset k of i  <=>  i at offset
+#                   K-1-k of o), i.e. the forward launch with weights W'[k] = W[K-1-k]^T; for a strided conv the inverse table
+#                   inv[k][i] = o is scattered from the forward table once per rulebook (device-side index glue);
+#   weight gradient dW[k] = X[nbr[k]]^T . dout  (a gathered A^T B per kernel offset) runs on torch ops (index_select + matmul in
+#                   fp32): a library GEMM, not a kernel of this repository.
+# Mixed precision like the inference path: fp16 operands, fp32 accumulation, fp32 master weights and gradients.
+# ------------------------------------------------------------------------------------------------------------------
+def _slot_rows(rb):
+    """storage row of every tile slot of the rulebook's table (identity without tile order)."""
+    if rb.row_perm is not None:
+        return rb.row_perm[:rb.nbr_stride].long()
+    return None
+
+
+def inverse_rulebook(rb, v_in):
+    """rulebook of the data gradient of a strided conv: inv[k][i] = output row that reads input row i at kernel offset k."""
+    if rb.inverse is None:
+        tab = rb.nbr_ordered if rb.nbr_ordered is not None else rb.nbr
+        taps = rb.taps
+        n = rb.num_out
+        tab = tab[:, :n] if rb.row_perm is None else tab
+        rows = _slot_rows(rb)
+        stride = (v_in + 127) // 128 * 128
+        inv = torch.full((taps, stride), -1, dtype=torch.int32, device=tab.device)
+        k_idx = torch.arange(taps, device=tab.device).view(taps, 1).expand_as(tab)
+        o_idx = (rows.view(1, -1).expand_as(tab) if rows is not None else
+                 torch.arange(tab.shape[1], device=tab.device).view(1, -1).expand_as(tab))
+        ok = (tab >= 0) & (o_idx >= 0)
+        inv[k_idx[ok], tab[ok].long()] = o_idx[ok].int()
+        rb.inverse = Rulebook(None, None, inv.contiguous(), stride, taps, v_in)
+    return rb.inverse
+
+
+def pack_conv_weight_transposed(weight, mirror):
+    """weights of the data-gradient launch: [Cin, Kpad] with column k*Cout + c = W[k' ][cin][c], k' = K-1-k when the table is the
+    forward table of a submanifold conv (mirror), k' = k over an inverse table."""
+    kd, kh, kw, cin, cout = weight.shape
+    taps = kd * kh * kw
+    w = weight.detach().reshape(taps, cin, cout)
+    if mirror:
+        w = w.flip(0)
+    w = w.permute(1, 0, 2).reshape(cin, taps * cout)            # [Cin, taps * Cout]
+    kpad = (taps * cout + 63) // 64 * 64
+    out = torch.zeros((cin, kpad), dtype=torch.float16, device=weight.device)
+    out[:, :taps * cout] = w.half()
+    return out.contiguous()
+
+
+class ImplicitGemmFunction(torch.autograd.Function):
+    """y = conv(x; W) over a rulebook, differentiable in x and W (train mode of SparseConvolution)."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, rb, subm):
+        cin, cout = weight.shape[3], weight.shape[4]
+        xh = feats.detach().half().contiguous()
+        y = _implicit_gemm(xh, rb, pack_conv_weight(weight), cin, cout)
+        ctx.save_for_backward(xh, weight)
+        ctx.rb, ctx.subm, ctx.in_dtype = rb, subm, feats.dtype
+        return y.to(feats.dtype if feats.dtype != torch.float16 else torch.float16)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xh, weight = ctx.saved_tensors
+        rb, subm = ctx.rb, ctx.subm
+        cin, cout = weight.shape[3], weight.shape[4]
+        taps = rb.taps
+        g32 = grad_out.detach().float()
+        grad_x = grad_w = None
+        if ctx.needs_input_grad[0]:
+            # per-tensor scaling into fp16's range (gradients deep in the encoder are ~1e-6: they would flush to zero in fp16);
+            # the scale is a device-side power of two, so the un-scaling is exact and nothing synchronises with the host
+            amax = g32.abs().amax().clamp(min=1e-30)
+            scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
+            gh = (g32 * scale).half().contiguous()
+            if subm:
+                gx = _implicit_gemm(gh, rb, pack_conv_weight_transposed(weight, True), cout, cin)
+            else:
+                gx = _implicit_gemm(gh, inverse_rulebook(rb, xh.shape[0]), pack_conv_weight_transposed(weight, False), cout, cin)
+            grad_x = (gx.float() / scale).to(ctx.in_dtype)
+        if ctx.needs_input_grad[1]:
+            tab = rb.nbr_ordered if rb.nbr_ordered is not None else rb.nbr[:, :rb.num_out]
+            rows = _slot_rows(rb)
+            gw = torch.zeros((taps, cin, cout), dtype=torch.float32, device=xh.device)
+            for k in range(taps):
+                ok = tab[k] >= 0
+                if rows is not None:
+                    ok = ok & (rows >= 0)
+                if not bool(ok.any()):
+                    continue
+                xi = xh.index_select(0, tab[k][ok].long()).float()
+                go = g32.index_select(0, (rows[ok] if rows is not None else ok.nonzero().squeeze(1)))
+                gw[k] = xi.t() @ go
+            grad_w = gw.view_as(weight).to(weight.dtype)
+        return grad_x, grad_w, None, None
+
+
 def pack_conv_weight(weight):
     """(kD,kH,kW,Cin,Cout) -> K-major fp16 [Cout, Kpad] with column k*Cin + c (zero padded to 64)."""
     kd, kh, kw, cin, cout = weight.shape
@@ -452,6 +558,18 @@ class SparseConvolution(SparseModule):
         ev = x.indice_dict.get(('event', id(rb)))
         if ev is not None:      # rulebook built on a side stream (SparseEncoder.prebuild_rulebooks)
             torch.cuda.current_stream().wait_event(ev)
+        if self.training and torch.is_grad_enabled() and (x.features.requires_grad or self.weight.requires_grad):
+            if scale is not None or shift is not None or residual is not None or relu:
+                raise L.IsfError('sparse conv: the fused epilogue is an eval-mode feature')
+            if rb.num_dev is not None:
+                raise L.IsfError('sparse conv: training runs in exact mode (no capacity buffers)')
+            f = ImplicitGemmFunction.apply(x.features, self.weight, rb, self.subm)
+            if self.bias is not None:
+                f = f + self.bias.to(f.dtype)
+            out = SparseConvTensor(f, rb.out_indices, rb.out_shape, x.batch_size)
+            out.indice_dict = x.indice_dict
+            out.sorted = x.sorted if self.subm else True
+            return out
         feats = x.features if x.features.dtype == torch.float16 else x.features.half()
         if self.bias is not None:
             shift = self.bias.float() if shift is None else shift + self.bias.float() * (scale if scale is not None else 1)

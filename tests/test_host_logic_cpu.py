@@ -563,3 +563,66 @@ def test_config5_geometry_host_logic_against_the_oracle(monkeypatch):
     for a, b in zip(list(gf) + [ghm], list(rf) + [rhm]):
         r = ((a.float() - b).norm() / b.norm()).item()
         assert r < 1e-2, r
+
+
+def test_sparse_encoder_train_mode_on_the_emulator(monkeypatch):
+    """spconv.ImplicitGemmFunction on the CPU against the ABI emulator: the data gradient as the forward product over the mirrored
+    (submanifold) / inverse (strided) rulebook, the per-offset weight gradient, batch-statistics BatchNorm, the differentiable
+    dense() — single convolutions (with and without the tile order) and the whole encoder against autograd of the oracle."""
+    import abi_emulator
+    import isfusion_b200.spconv as sp
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    from oracle import spconv_ops as so
+    sys.path.insert(0, HERE)
+    import test_sparse_train_gpu as T
+    abi_emulator.install(monkeypatch)
+
+    def rel(a, b):
+        a, b = a.detach().float(), b.detach().float()
+        return float((a - b).norm() / b.norm().clamp(min=1e-12))
+    for subm, cin, cout, ksize, stride, padding in ((True, 32, 32, 3, 1, 1), (False, 32, 64, 3, 2, 1), (False, 32, 32, (3, 1, 1), (2, 1, 1), 0)):
+        for order in (None, 31):
+            monkeypatch.setattr(sp, 'TILE_ORDER', order)
+            feats, idx = T._inputs(1500, cin, [9, 24, 20], 2, cin + cout)
+            ref = (so.SubMConv3d if subm else so.SparseConv3d)(cin, cout, ksize, stride=stride, padding=padding, bias=False)
+            ref.weight.data = ref.weight.data.half().float()
+            mod = (sp.SubMConv3d if subm else sp.SparseConv3d)(cin, cout, ksize, stride=stride, padding=padding, bias=False)
+            mod.load_state_dict(ref.state_dict())
+            mod.train()
+            xr = feats.clone().requires_grad_(True)
+            yr = ref(so.SparseConvTensor(xr, idx, [9, 24, 20], 2)).features
+            gout = torch.randn(yr.shape, generator=torch.Generator().manual_seed(3)).half().float()
+            (yr * gout).sum().backward()
+            xg = feats.clone().requires_grad_(True)
+            yg = mod(sp.SparseConvTensor(xg, idx, [9, 24, 20], 2)).features
+            (yg * gout).sum().backward()
+            r = (rel(yg, yr), rel(xg.grad, xr.grad), rel(mod.weight.grad, ref.weight.grad))
+            assert max(r) < 2e-3, (subm, stride, order, r)
+    monkeypatch.setattr(sp, 'TILE_ORDER', 31)
+    cfg = dict(in_channels=64, sparse_shape=[41, 64, 64], base_channels=32, output_channels=256,
+               encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    torch.manual_seed(0)
+    ref = so.SparseEncoder(**cfg).train()
+    feats, idx = T._inputs(3000, 64, [41, 64, 64], 2, 11)
+    mod = SparseEncoder(**cfg)
+    mod.load_state_dict(ref.state_dict(), strict=True)
+    mod.train()
+    xr = feats.clone().requires_grad_(True)
+    rs, _, _ = so.SparseEncoder.forward.__wrapped__(ref, xr, idx, 2)
+    gout = torch.randn(rs.shape, generator=torch.Generator().manual_seed(5))
+    (rs * gout).sum().backward()
+    xg = feats.clone().requires_grad_(True)
+    gs, _, _ = mod(xg, idx, 2)
+    (gs * gout).sum().backward()
+    # the single convolutions above pin the gradient ARITHMETIC to 2e-3; through 21 ReLU layers the fp16 forward flips the sign of
+    # a fraction of near-zero pre-activations, each flip a 100 % change of that element's gradient: the whole-encoder gradients are
+    # compared by direction (cosine) and loosely by norm
+    def cos(a, b):
+        a, b = a.detach().float().flatten(), b.detach().float().flatten()
+        return float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+    r_out, c_x = rel(gs, rs), cos(xg.grad, xr.grad)
+    pr = dict(ref.named_parameters())
+    worst = min(cos(p.grad, pr[n].grad) for n, p in mod.named_parameters())
+    print('emulated train mode: out rel %.2e, grad_x cosine %.4f, worst parameter-gradient cosine %.4f' % (r_out, c_x, worst))
+    assert r_out < 1e-2 and c_x > 0.99 and worst > 0.98, (r_out, c_x, worst)

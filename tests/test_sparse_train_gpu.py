@@ -1,0 +1,103 @@
+"""GPU: train mode of the sparse encoder: the implicit-GEMM kernels under autograd (spconv.ImplicitGemmFunction:
+data gradient = the forward kernel over the mirrored / inverse rulebook, weight gradient = gathered A^T B on torch ops), BatchNorm
+with batch statistics, against autograd of the oracle's SparseEncoder (fp32) on the same inputs and weights."""
+import pytest
+import torch
+
+from oracle import spconv_ops as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+
+
+def _inputs(nvox, c, shape, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    cells = batch * shape[0] * shape[1] * shape[2]
+    base = torch.randint(0, cells, (nvox // 8,), generator=g)
+    lin = (base[:, None] + torch.randint(-2, 3, (nvox // 8, 8), generator=g) * torch.tensor([1, shape[2], shape[1] * shape[2], 1, shape[2], 1, 1, shape[2]])).flatten() % cells
+    lin = torch.unique(lin)
+    idx = torch.stack([lin // (shape[0] * shape[1] * shape[2]), (lin // (shape[1] * shape[2])) % shape[0],
+                       (lin // shape[2]) % shape[1], lin % shape[2]], 1).int()
+    return torch.relu(torch.randn(idx.shape[0], c, generator=g)).half().float(), idx
+
+
+@pytest.mark.parametrize('subm,cin,cout,ksize,stride,padding', [(True, 64, 64, 3, 1, 1), (False, 32, 64, 3, 2, 1), (True, 128, 128, 3, 1, 1),
+                                                                 (False, 256, 256, (3, 1, 1), (2, 1, 1), 0)])
+@pytest.mark.parametrize('order', [None, 31])
+def test_single_conv_gradients(subm, cin, cout, ksize, stride, padding, order):
+    """data and weight gradients of one sparse convolution against autograd of the oracle's gather -> matmul -> scatter-add."""
+    import isfusion_b200.spconv as sp
+    feats, idx = _inputs(6000, cin, [11, 40, 36], 2, cin + cout)
+    cls_o = so.SubMConv3d if subm else so.SparseConv3d
+    cls_g = sp.SubMConv3d if subm else sp.SparseConv3d
+    ref = cls_o(cin, cout, ksize, stride=stride, padding=padding, bias=False)
+    ref.weight.data = (torch.randn_like(ref.weight) / (27 * cin) ** 0.5 * 3).half().float()
+    mod = cls_g(cin, cout, ksize, stride=stride, padding=padding, bias=False)
+    mod.load_state_dict(ref.state_dict())
+    mod = mod.cuda().train()
+    xr = feats.clone().requires_grad_(True)
+    yr = ref(so.SparseConvTensor(xr, idx, [11, 40, 36], 2)).features
+    gout = torch.randn(yr.shape, generator=torch.Generator().manual_seed(3)).half().float()
+    (yr * gout).sum().backward()
+    old = sp.TILE_ORDER
+    try:
+        sp.TILE_ORDER = order
+        xg = feats.cuda().requires_grad_(True)
+        t = sp.SparseConvTensor(xg, idx.cuda(), [11, 40, 36], 2)
+        yg = mod(t).features
+        (yg * gout.cuda()).sum().backward()
+    finally:
+        sp.TILE_ORDER = old
+    r = (_rel(yg, yr), _rel(xg.grad, xr.grad), _rel(mod.weight.grad, ref.weight.grad))
+    print('conv %s %d->%d order=%s: out %.2e  grad_x %.2e  grad_w %.2e' % ('subm' if subm else 'strided', cin, cout, order, *r))
+    assert r[0] < 1e-3 and r[1] < 1e-3 and r[2] < 1e-3, r
+
+
+def test_sparse_encoder_train_mode_forward_backward():
+    """the whole SparseEncoder (21 convolutions, batch-statistics BatchNorm, residual blocks, dense BEV output) in train mode:
+    output, gradient of the input features and of every parameter against autograd of the oracle."""
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    torch.manual_seed(0)
+    cfg = dict(in_channels=64, sparse_shape=[41, 128, 128], base_channels=32, output_channels=256,
+               encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    ref = so.SparseEncoder(**cfg).train()
+    for p in ref.parameters():
+        if p.dim() == 5:
+            p.data = p.data.half().float()
+    feats, idx = _inputs(20000, 64, [41, 128, 128], 2, 11)
+    mod = SparseEncoder(**cfg)
+    mod.load_state_dict(ref.state_dict(), strict=True)
+    mod = mod.cuda().train()
+    xr = feats.clone().requires_grad_(True)
+    rs, _, _ = so.SparseEncoder.forward.__wrapped__(ref, xr, idx, 2)          # the oracle's forward without its no_grad decorator
+    gout = torch.randn(rs.shape, generator=torch.Generator().manual_seed(5))
+    (rs * gout).sum().backward()
+    xg = feats.cuda().requires_grad_(True)
+    gs, _, _ = mod(xg, idx.cuda(), 2)
+    assert gs.shape == rs.shape and gs.requires_grad
+    (gs * gout.cuda()).sum().backward()
+    # the single-convolution test pins the gradient ARITHMETIC to 1e-3; through 21 ReLU layers the fp16 forward flips the sign of a
+    # fraction of near-zero pre-activations (each flip a 100 % change of that element's gradient), so the whole-encoder gradients
+    # are compared by direction
+    def cos(a, b):
+        a, b = a.detach().float().cpu().flatten(), b.detach().float().cpu().flatten()
+        return float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-30))
+    r_out, c_x = _rel(gs.detach(), rs.detach()), cos(xg.grad, xr.grad)
+    pr = dict(ref.named_parameters())
+    worst = 1.0
+    for n, p in mod.named_parameters():
+        assert p.grad is not None, n
+        worst = min(worst, cos(p.grad, pr[n].grad))
+    print('sparse encoder train mode: out rel %.2e, grad_x cosine %.4f, worst parameter-gradient cosine %.4f over %d parameters' % (
+        r_out, c_x, worst, len(pr)))
+    # running statistics moved the same way
+    br = dict(ref.named_buffers())
+    for n, b in mod.named_buffers():
+        if 'running' in n:
+            assert _rel(b, br[n]) < 5e-3, n
+    assert r_out < 5e-3 and c_x > 0.99 and worst > 0.98, (r_out, c_x, worst)
