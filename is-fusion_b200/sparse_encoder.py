@@ -187,7 +187,7 @@ class SparseEncoder(nn.Module):
         """eval: the fused no-grad CUDA path; train: the same kernels under autograd (spconv.ImplicitGemmFunction), BatchNorm with
         batch statistics over the active voxels, exact-size tensors (ref sparse_encoder.py:107-138)."""
         if self.training and torch.is_grad_enabled():
-            return self.forward_train(voxel_features, coors, batch_size)
+            return self.forward_train(voxel_features, coors, batch_size, sorted_coors=kwargs.get('sorted_coors', False))
         return self.forward_eval(voxel_features, coors, batch_size, *args, **kwargs)
 
     def forward_train(self, voxel_features, coors, batch_size, sorted_coors=False):
