@@ -84,7 +84,7 @@ class SparseConvTensor:
 class Rulebook:
     """output indices + neighbour table of one (coordinate set, kernel geometry)."""
     __slots__ = ('out_indices', 'out_shape', 'nbr', 'nbr_stride', 'taps', 'num_out', 'num_dev', 'pairs', 'nbr_ordered',
-                 'row_perm', 'tile_ctr', 'inverse')
+                 'row_perm', 'tile_ctr', 'inverse', 'pair_lists')
 
     def __init__(self, out_indices, out_shape, nbr, nbr_stride, taps, num_out, num_dev=None):
         self.out_indices, self.out_shape, self.nbr = out_indices, out_shape, nbr
@@ -94,6 +94,7 @@ class Rulebook:
         self.nbr_ordered = self.row_perm = None     # tile order (TILE_ORDER): regrouped table + tile slot -> storage row
         self.tile_ctr = None                        # int32[2], zero between launches: dynamic tile scheduling (DYNAMIC_TILES)
         self.inverse = None                         # training: rulebook of the data gradient of a strided conv (inverse_rulebook)
+        self.pair_lists = None                      # training: (input rows, output rows, per-offset counts) of the weight gradient
 
 
 # Opt-in tile order of the implicit GEMM (csrc/spconv.cu "Tile order", tests/analysis/tile_occupancy.py): None = rows in
@@ -421,6 +422,23 @@ def inverse_rulebook(rb, v_in):
     return rb.inverse
 
 
+def pair_lists(rb):
+    """(input rows, output rows) of every (kernel offset, output site) pair of the rulebook, grouped by kernel offset, and the
+    per-offset pair counts as a host list: built once per rulebook (one host read), shared by the convolutions that share it."""
+    if rb.pair_lists is None:
+        tab = rb.nbr_ordered if rb.nbr_ordered is not None else rb.nbr[:, :rb.num_out]
+        rows = _slot_rows(rb)
+        ok = tab >= 0
+        if rows is not None:
+            ok = ok & (rows >= 0).view(1, -1)
+        counts = ok.sum(1).tolist()                                 # the one host read
+        kk, ss = ok.nonzero(as_tuple=True)                          # row-major: grouped by kernel offset, slots ascending
+        in_rows = tab[kk, ss].long()
+        out_rows = rows[ss] if rows is not None else ss
+        rb.pair_lists = (in_rows.contiguous(), out_rows.contiguous(), counts)
+    return rb.pair_lists
+
+
 def pack_conv_weight_transposed(weight, mirror):
     """weights of the data-gradient launch: [Cin, Kpad] with column k*Cout + c = W[k' ][cin][c], k' = K-1-k when the table is the
     forward table of a submanifold conv (mirror), k' = k over an inverse table."""
@@ -434,6 +452,16 @@ def pack_conv_weight_transposed(weight, mirror):
     out = torch.zeros((cin, kpad), dtype=torch.float16, device=weight.device)
     out[:, :taps * cout] = w.half()
     return out.contiguous()
+
+
+def _mm_f32(a, b):
+    """a @ b for fp16 operands with an fp32 result (library GEMM of the weight gradient)."""
+    if a.is_cuda:
+        try:
+            return torch.mm(a, b, out_dtype=torch.float32)
+        except (TypeError, RuntimeError):
+            pass
+    return a.float() @ b.float()
 
 
 class ImplicitGemmFunction(torch.autograd.Function):
@@ -456,31 +484,29 @@ class ImplicitGemmFunction(torch.autograd.Function):
         taps = rb.taps
         g32 = grad_out.detach().float()
         grad_x = grad_w = None
+        # per-tensor scaling into fp16's range (gradients deep in the encoder are ~1e-6: they would flush to zero in fp16);
+        # the scale is a device-side power of two, so the un-scaling is exact and nothing synchronises with the host
+        amax = g32.abs().amax().clamp(min=1e-30)
+        scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
+        gh = (g32 * scale).half().contiguous()
         if ctx.needs_input_grad[0]:
-            # per-tensor scaling into fp16's range (gradients deep in the encoder are ~1e-6: they would flush to zero in fp16);
-            # the scale is a device-side power of two, so the un-scaling is exact and nothing synchronises with the host
-            amax = g32.abs().amax().clamp(min=1e-30)
-            scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
-            gh = (g32 * scale).half().contiguous()
             if subm:
                 gx = _implicit_gemm(gh, rb, pack_conv_weight_transposed(weight, True), cout, cin)
             else:
                 gx = _implicit_gemm(gh, inverse_rulebook(rb, xh.shape[0]), pack_conv_weight_transposed(weight, False), cout, cin)
             grad_x = (gx.float() / scale).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
-            tab = rb.nbr_ordered if rb.nbr_ordered is not None else rb.nbr[:, :rb.num_out]
-            rows = _slot_rows(rb)
+            in_rows, out_rows, counts = pair_lists(rb)
+            xg = xh.index_select(0, in_rows)                       # [pairs, Cin]  fp16, grouped by kernel offset
+            gg = gh.index_select(0, out_rows)                      # [pairs, Cout] fp16 (scaled)
             gw = torch.zeros((taps, cin, cout), dtype=torch.float32, device=xh.device)
-            for k in range(taps):
-                ok = tab[k] >= 0
-                if rows is not None:
-                    ok = ok & (rows >= 0)
-                if not bool(ok.any()):
-                    continue
-                xi = xh.index_select(0, tab[k][ok].long()).float()
-                go = g32.index_select(0, (rows[ok] if rows is not None else ok.nonzero().squeeze(1)))
-                gw[k] = xi.t() @ go
-            grad_w = gw.view_as(weight).to(weight.dtype)
+            off = 0
+            for k in range(taps):                                  # counts live on the host: no synchronisation in this loop
+                n = counts[k]
+                if n:
+                    gw[k] = _mm_f32(xg[off:off + n].t(), gg[off:off + n])      # fp16 operands on the tensor cores, fp32 result
+                    off += n
+            grad_w = (gw / scale).view_as(weight).to(weight.dtype)
         return grad_x, grad_w, None, None
 
 
