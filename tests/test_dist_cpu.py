@@ -107,3 +107,55 @@ def test_naive_sync_bn_two_ranks():
             # eval = plain BatchNorm on the running statistics
             ref = torch.nn.functional.batch_norm(o['x'], o['rm'], o['rv'], o['w'], o['b'], False, 0.0, 1e-3)
             assert torch.allclose(o['y_eval'], ref, atol=1e-5)
+
+
+def _sparse_train_worker(rank, world, port, q):
+    """one data-parallel training step of the product SparseEncoder (train mode, naiveSyncBN1d over gloo) on the ABI emulator."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import pytest
+    import abi_emulator
+    import test_sparse_train_gpu as T
+    from isfusion_b200.sparse_encoder import SparseEncoder
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    mp_ = pytest.MonkeyPatch()
+    abi_emulator.install(mp_)
+    try:
+        torch.manual_seed(0)                                         # same initial weights on every rank
+        cfg = dict(in_channels=64, sparse_shape=[41, 64, 64], base_channels=32, output_channels=256,
+                   norm_cfg=dict(type='naiveSyncBN1d', eps=1e-3, momentum=0.01),
+                   encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
+                   encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+        net = SparseEncoder(**cfg).train()
+        feats, idx = T._inputs(2500 + 700 * rank, 64, [41, 64, 64], 2, 11 + rank)      # ranks see different clouds
+        x = feats.clone().requires_grad_(True)
+        out, _, _ = net(x, idx, 2)
+        out.square().mean().backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        own = flat.clone()
+        dist.all_reduce(flat)                                        # the data-parallel gradient exchange
+        flat /= world
+        stats = torch.cat([b.float().reshape(-1) for n, b in net.named_buffers() if 'running' in n])
+        # plain Python objects through the queue (a tensor would need this process alive until the parent has read it)
+        q.put((rank, own.norm().item(), flat.double().sum().item(), flat[::997].tolist(), stats.tolist(), bool(torch.isfinite(flat).all())))
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+def test_sparse_encoder_train_step_two_ranks():
+    """N > 1 path of the training step on the CPU: the sparse encoder in train mode on both ranks (ABI emulator), its
+    naiveSyncBN1d layers exchanging moments over gloo, one flat gradient all-reduce: the ranks end up with the same running
+    statistics and the same averaged gradient although their inputs (and own gradients) differ."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 777) % 2000
+    procs = [ctx.Process(target=_sparse_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    (r0, n0, t0, g0, s0, ok0), (r1, n1, t1, g1, s1, ok1) = res
+    assert ok0 and ok1 and n0 > 0 and n1 > 0 and abs(n0 - n1) > 1e-9          # different data, different own gradients
+    assert t0 == t1 and g0 == g1 and len(g0) > 1000                           # one averaged gradient, bit for bit
+    assert s0 == s1 and len(s0) > 100                                         # synchronised BN: identical running statistics
