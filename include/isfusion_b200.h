@@ -303,6 +303,14 @@ int isf_spconv_implicit_gemm_ordered(const void* feats_in, int cin, const void* 
  * instead of walking them round-robin, and leave it zeroed.  One buffer per rulebook: launches that share it must be
  * stream-ordered.  Without the call (or with NULL) the tiles are walked round-robin; results are bit-identical either way. */
 int isf_spconv_tile_counter(int* counter2);
+/* Training: weight gradient of a sparse convolution (replaces the filter-gradient half of spconv's indice_conv_backward,
+ * bevfusion-ops/spconv/include/spconv/spconv_ops.h:364-470, one gather + GEMM per kernel offset there).
+ *   dw[k][ci][co] += sum over p in [tap_offsets[k], tap_offsets[k+1]) of  x[in_rows[p]][ci] * g[out_rows[p]][co]
+ * x [*, cin] and g [*, cout] fp16 row-major (16-byte aligned rows: cin, cout multiples of 8), in_rows / out_rows device int32 pair
+ * lists grouped by kernel offset, tap_offsets device int32 [taps + 1], max_pairs_per_tap the host's bound on a group's size,
+ * dw fp32 [taps, cin, cout], accumulated into (zero it first).  fp32 accumulation; the order of the additions is not fixed. */
+int isf_spconv_wgrad(const void* x_f16, int cin, const void* g_f16, int cout, const int* in_rows, const int* out_rows,
+                     const int* tap_offsets, int taps, int max_pairs_per_tap, float* dw, void* stream);
 int isf_sparse_to_dense(const void* feats, const int* indices, int v, int c, int batch, int D, int H, int W,
                         void* out, void* stream);
 int isf_sparse_to_bev_nhwc(const void* feats, const int* indices, int v, const int* v_dev, int c, int D, int H, int W,

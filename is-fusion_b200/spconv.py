@@ -7,6 +7,7 @@ mmdet3d/ops/sparse_block.py:8-20) with weights in the spconv1/mmcv layout (kD,kH
 checkpoints (Cout,kD,kH,kW,Cin) are accepted on load (write_spconv2.py:62-94).
 """
 import ctypes
+import itertools
 import os
 
 import torch
@@ -435,8 +436,36 @@ def pair_lists(rb):
         kk, ss = ok.nonzero(as_tuple=True)                          # row-major: grouped by kernel offset, slots ascending
         in_rows = tab[kk, ss].long()
         out_rows = rows[ss] if rows is not None else ss
-        rb.pair_lists = (in_rows.contiguous(), out_rows.contiguous(), counts)
+        offs = torch.tensor([0] + list(itertools.accumulate(counts)), dtype=torch.int32).to(tab.device)
+        rb.pair_lists = (in_rows.contiguous(), out_rows.contiguous(), counts, in_rows.int().contiguous(),
+                         out_rows.int().contiguous(), offs)
     return rb.pair_lists
+
+
+# weight gradient: 'own' = the fused gather + mma.sync kernel of csrc/wgrad.cu, 'torch' = gathered copies + one library GEMM per
+# kernel offset (the first training path; kept as the in-product cross-check of the own kernel, tests/test_sparse_train_gpu.py)
+WGRAD = os.environ.get('ISF_WGRAD', 'own')
+
+
+def _weight_grad(xh, gh, rb, taps, cin, cout):
+    """sum over the pairs of each kernel offset of x[in]^T g[out]: [taps, Cin, Cout] fp32 (reference: indice_conv_backward's
+    filter gradient, bevfusion-ops/spconv/include/spconv/spconv_ops.h:364-470)."""
+    in_rows, out_rows, counts, in32, out32, offs = pair_lists(rb)
+    gw = torch.zeros((taps, cin, cout), dtype=torch.float32, device=xh.device)
+    if WGRAD == 'own' and cin % 8 == 0 and cout % 8 == 0:
+        L.require_cuda(xh, gh)
+        L.check(L.lib().isf_spconv_wgrad(L.ptr(xh), cin, L.ptr(gh), cout, L.ptr(in32), L.ptr(out32), L.ptr(offs), taps,
+                                         max(counts) if counts else 0, L.ptr(gw), L.stream()))
+        return gw
+    xg = xh.index_select(0, in_rows)                       # [pairs, Cin]  fp16, grouped by kernel offset
+    gg = gh.index_select(0, out_rows)                      # [pairs, Cout] fp16 (scaled)
+    off = 0
+    for k in range(taps):                                  # counts live on the host: no synchronisation in this loop
+        n = counts[k]
+        if n:
+            gw[k] = _mm_f32(xg[off:off + n].t(), gg[off:off + n])      # fp16 operands on the tensor cores, fp32 result
+            off += n
+    return gw
 
 
 def pack_conv_weight_transposed(weight, mirror):
@@ -496,16 +525,7 @@ class ImplicitGemmFunction(torch.autograd.Function):
                 gx = _implicit_gemm(gh, inverse_rulebook(rb, xh.shape[0]), pack_conv_weight_transposed(weight, False), cout, cin)
             grad_x = (gx.float() / scale).to(ctx.in_dtype)
         if ctx.needs_input_grad[1]:
-            in_rows, out_rows, counts = pair_lists(rb)
-            xg = xh.index_select(0, in_rows)                       # [pairs, Cin]  fp16, grouped by kernel offset
-            gg = gh.index_select(0, out_rows)                      # [pairs, Cout] fp16 (scaled)
-            gw = torch.zeros((taps, cin, cout), dtype=torch.float32, device=xh.device)
-            off = 0
-            for k in range(taps):                                  # counts live on the host: no synchronisation in this loop
-                n = counts[k]
-                if n:
-                    gw[k] = _mm_f32(xg[off:off + n].t(), gg[off:off + n])      # fp16 operands on the tensor cores, fp32 result
-                    off += n
+            gw = _weight_grad(xh, gh, rb, taps, cin, cout)
             grad_w = (gw / scale).view_as(weight).to(weight.dtype)
         return grad_x, grad_w, None, None
 

@@ -36,6 +36,7 @@ def main():
         dist.init_process_group('nccl')
     import synth
     from __graft_entry__ import make_net
+    import isfusion_b200.spconv as spconv_mod
     net = make_net(0).cuda()
     vfe, enc = net.pts_voxel_encoder.train(), net.pts_middle_encoder.train()
     params = [p for m in (vfe, enc) for p in m.parameters()]
@@ -88,7 +89,8 @@ def main():
                           'voxels_rank0': int(vc.shape[0]), 'ms_per_step_max_over_ranks': float(ms[0]), 'frames_per_s': args.frames * world / float(ms[0]) * 1e3,
                           'grad_allreduce_ms': float(ms[1]), 'grad_allreduce_share': float(ms[1] / ms[0]), 'gradient_bytes': nbytes,
                           'loss': float(loss.detach()), 'steps': args.steps, 'warmup': args.warmup,
-                          'not_in_the_step': 'camera branch, fusion encoder, head + loss (no backward of those modules); sparse-conv weight gradient on torch ops'}))
+                          'not_in_the_step': 'camera branch, fusion encoder, head + loss (no backward of those modules)',
+                          'weight_gradient': spconv_mod.WGRAD + ' (ISF_WGRAD: own = csrc/wgrad.cu, torch = gathered copies + library GEMMs)'}))
     if world > 1:
         dist.destroy_process_group()
 

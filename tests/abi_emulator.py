@@ -453,6 +453,18 @@ class SparseMixin:
         assert counter2 is None or (counter2.dtype == torch.int32 and counter2.numel() == 2 and int(counter2.abs().sum()) == 0)
         return 0
 
+    def isf_spconv_wgrad(self, x, cin, g, cout, in_rows, out_rows, tap_offsets, taps, max_pairs, dw, stream):
+        assert x.dtype == torch.float16 and g.dtype == torch.float16 and dw.dtype == torch.float32
+        assert in_rows.dtype == torch.int32 and out_rows.dtype == torch.int32 and tap_offsets.numel() == taps + 1
+        assert tuple(dw.shape) == (taps, cin, cout) and cin % 8 == 0 and cout % 8 == 0
+        offs = tap_offsets.tolist()
+        assert max(b - a for a, b in zip(offs[:-1], offs[1:])) <= max_pairs
+        for k in range(taps):
+            a, b = offs[k], offs[k + 1]
+            if b > a:
+                dw[k] += x[in_rows[a:b].long()].float().t() @ g[out_rows[a:b].long()].float()
+        return 0
+
     def isf_spconv_implicit_gemm(self, feats, cin, w, kpad, cout, nbr, nbr_stride, taps, v_out, v_dev, scale, shift, residual, ldr,
                                  relu, out, ldo, stream):
         return self._implicit(feats, cin, w, kpad, cout, nbr, taps, v_out, v_dev, None, scale, shift, residual, relu, out)

@@ -60,6 +60,7 @@ def test_merge_kernel_source_on_host_matches_the_reference_loader(tag, kw, n_sw)
 @pytest.mark.parametrize('tag,kw,n_sw', CASES)
 def test_product_loader_on_the_emulator(tag, kw, n_sw, monkeypatch):
     import abi_emulator
+    import isfusion_b200.sweeps  # noqa: F401  (registers the loader: the test must not depend on an earlier import)
     from isfusion_b200.registry import PIPELINES
     abi_emulator.install(monkeypatch)
     loader = PIPELINES.build(dict(type='LoadPointsFromMultiSweeps', use_dim=[0, 1, 2, 3, 4], device='cpu', **kw))
