@@ -3,7 +3,7 @@
 // (reference: spconv's indice_conv_backward: per-offset gather of the input and output-gradient rows followed by a GEMM,
 // bevfusion-ops/spconv/include/spconv/spconv_ops.h:364-470) as ONE kernel: no gathered copies of X / G in global memory.
 //
-// Grid = (pair chunks of a kernel offset, kernel offsets, B x B blocks of the Cin x Cout matrix), B = 32 / 64 / 128 by the layer's
+// Grid = (kernel offsets x B x B blocks of the Cin x Cout matrix, pair chunks of a kernel offset), B = 32 / 64 / 128 by the layer's
 // width.  A CTA walks its chunk of pairs in stages: the X rows and G rows of a stage are gathered by 16-byte cp.async into shared
 // memory (4 stages, prefetch distance 3: a gather is two dependent global loads, index then row), and 8 warps run
 // mma.sync.m16n8k16 with the PAIR index as K.  A = X^T and B = G are both stored pair-major, so their fragments come from
@@ -54,17 +54,20 @@ struct Cfg {
 template <int B, int WM, int WN, int KG, int KPG, int STAGES>
 __global__ void __launch_bounds__(THREADS) wgrad_kernel(const __half* __restrict__ X, int cin, const __half* __restrict__ G, int cout,
                                                         const int* __restrict__ in_rows, const int* __restrict__ out_rows,
-                                                        const int* __restrict__ tap_off, int chunk, float* __restrict__ dW) {
+                                                        const int* __restrict__ tap_off, int taps, int chunk, float* __restrict__ dW) {
   using C = Cfg<B, WM, WN, KG, KPG, STAGES>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __half* xs = reinterpret_cast<__half*>(smem_raw);                       // [STAGES][KST][PITCH]
   __half* gs = xs + STAGES * C::KST * C::PITCH;
-  const int tap = blockIdx.y;
-  const int p_begin = tap_off[tap] + blockIdx.x * chunk;
+  // blockIdx.x = kernel offset + taps * channel block (fastest), blockIdx.y = pair chunk: the CTAs in flight together work on the
+  // same stretch of output sites under every kernel offset, i.e. on the same G rows and on neighbouring X rows -> they meet in L2
+  // (the first version walked chunk-fastest and read 4.2 GB from DRAM for 250 MB of operands, profiles/ncu_raw_wgrad_1_r02.csv)
+  const int tap = blockIdx.x % taps, blk = blockIdx.x / taps;
+  const int p_begin = tap_off[tap] + blockIdx.y * chunk;
   const int p_end = min(tap_off[tap + 1], p_begin + chunk);
   if (p_begin >= p_end) return;
   const int nb = (cout + B - 1) / B;
-  const int m0 = (blockIdx.z / nb) * B, n0 = (blockIdx.z % nb) * B;       // channel block of this CTA
+  const int m0 = (blk / nb) * B, n0 = (blk % nb) * B;                     // channel block of this CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int WMN = (B / WM) * (B / WN);
   const int kg = warp / WMN, wmn = warp % WMN;
@@ -76,33 +79,48 @@ __global__ void __launch_bounds__(THREADS) wgrad_kernel(const __half* __restrict
 #pragma unroll
     for (int j = 0; j < WN / 8; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
 
-  auto load_stage = [&](int buf, int p0) {
+  // a gather is two dependent global loads (pair index, then the row): the indices of a stage are loaded one iteration before its
+  // rows are requested, so only the prologue waits for them
+  constexpr int NL = C::KST * C::PIECES / THREADS;
+  static_assert(NL * THREADS == C::KST * C::PIECES, "whole passes of the block over a stage");
+  int ri[NL], ro[NL];
+  auto load_idx = [&](int p0) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int p = p0 + (tid + l * THREADS) / C::PIECES;
+      const bool okp = p < p_end;
+      ri[l] = okp ? __ldg(in_rows + p) : -1;
+      ro[l] = okp ? __ldg(out_rows + p) : -1;
+    }
+  };
+  auto issue = [&](int buf) {
     __half* xb = xs + buf * C::KST * C::PITCH;
     __half* gb = gs + buf * C::KST * C::PITCH;
 #pragma unroll
-    for (int i = tid; i < C::KST * C::PIECES; i += THREADS) {
+    for (int l = 0; l < NL; ++l) {
+      const int i = tid + l * THREADS;
       const int pr = i / C::PIECES, lc = (i % C::PIECES) * 8;
-      const int p = p0 + pr;
-      const bool okp = p < p_end;
-      const int ri = okp ? __ldg(in_rows + p) : 0, ro = okp ? __ldg(out_rows + p) : 0;
-      cp16(xb + pr * C::PITCH + lc, X + (size_t)ri * cin + m0 + lc, okp && m0 + lc < cin);
-      cp16(gb + pr * C::PITCH + lc, G + (size_t)ro * cout + n0 + lc, okp && n0 + lc < cout);
+      const bool okp = ri[l] >= 0;
+      cp16(xb + pr * C::PITCH + lc, X + (size_t)(okp ? ri[l] : 0) * cin + m0 + lc, okp && m0 + lc < cin);
+      cp16(gb + pr * C::PITCH + lc, G + (size_t)(okp ? ro[l] : 0) * cout + n0 + lc, okp && n0 + lc < cout);
     }
   };
 
   const int stages = (p_end - p_begin + C::KST - 1) / C::KST;
 #pragma unroll
   for (int d = 0; d < STAGES - 1; ++d) {
-    if (d < stages) load_stage(d, p_begin + d * C::KST);
+    if (d < stages) { load_idx(p_begin + d * C::KST); issue(d); }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  load_idx(p_begin + (STAGES - 1) * C::KST);       // past the chunk: -1s
   // ldmatrix row of this lane: matrix q = lane / 8, row r = lane % 8
   const int q = lane >> 3, r = lane & 7;
   for (int s = 0; s < stages; ++s) {
     asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
     __syncthreads();                       // stage s has landed for every thread; the buffer of stage s - 1 is free
-    if (s + STAGES - 1 < stages) load_stage((s + STAGES - 1) % STAGES, p_begin + (s + STAGES - 1) * C::KST);
+    if (s + STAGES - 1 < stages) issue((s + STAGES - 1) % STAGES);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    load_idx(p_begin + (s + STAGES) * C::KST);     // consumed by the next iteration's issue: the latency hides behind the MMAs below
     if (!active) continue;
     const __half* xb = xs + (s % STAGES) * C::KST * C::PITCH + kg * KPG * C::PITCH;
     const __half* gb = gs + (s % STAGES) * C::KST * C::PITCH + kg * KPG * C::PITCH;
@@ -155,8 +173,8 @@ static int launch(const void* x, int cin, const void* g, int cout, const int* in
   if (chunk < 512) chunk = 512;
   chunk = (chunk + C::KST - 1) / C::KST * C::KST;
   chunks = (max_pairs + chunk - 1) / chunk;
-  kern<<<dim3(chunks, taps, blocks), THREADS, C::SMEM, stream>>>((const __half*)x, cin, (const __half*)g, cout, in_rows, out_rows,
-                                                                 tap_offsets, chunk, dw);
+  kern<<<dim3(taps * blocks, chunks), THREADS, C::SMEM, stream>>>((const __half*)x, cin, (const __half*)g, cout, in_rows, out_rows,
+                                                                  tap_offsets, taps, chunk, dw);
   isf_count_launch(1);
   ISF_LAUNCH_CHECK();
   return ISF_OK;

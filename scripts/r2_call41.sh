@@ -1,6 +1,6 @@
 #!/bin/bash
-# GPU call 41: ldmatrix / 4-stage / three-width weight-gradient kernel: tests, training step, profile
-LOG=gpurun_out/r2_call41.log
+# GPU call 41 (and 43: the same with index prefetch + tap-fastest grid): weight-gradient kernel: tests, training step, profile
+LOG=gpurun_out/r2_call${CALL:-41}.log
 . "$(dirname "$0")/r2_common.sh"
 step "sparse training tests"
 t 300 python -m pytest tests/test_sparse_train_gpu.py -q -s -m gpu 2>&1 | grep -v "^$" >> $LOG
