@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Static report of every kernel in the built library (no GPU needed): registers, shared / local memory, spills as
 `cuobjdump -res-usage` gives them, and the count of the SASS mnemonics that identify the Blackwell paths
-(tcgen05 = UTCHMMA / LDTM / UTCBAR, TMA = UTMALDG, async gathers = LDGSTS, 256-bit global IO = .ENL2.256, mma.sync = HMMA).
+(tcgen05 = UTCHMMA / LDTM / UTCBAR, TMA = UTMALDG, async gathers = LDGSTS, 256-bit global IO = .ENL2.256, mma.sync = HMMA, ldmatrix = LDSM, red.global = REDG).
     python scripts/sass_report.py > profiles/sass_rNN.txt
 """
 import collections
@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'is-fusion_b200', 'libisfusion_b200.so')
-MNEMONICS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTCBAR', 'UTCBAR.2CTA.MULTICAST', 'UTMALDG', 'UTMASTG', 'STAS', 'UTCATOMSWS', 'LDGSTS', 'SYNCS', 'HMMA', 'ENL2.256', 'STL', 'LDL',
+MNEMONICS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTCBAR', 'UTCBAR.2CTA.MULTICAST', 'UTMALDG', 'UTMASTG', 'STAS', 'UTCATOMSWS', 'LDGSTS', 'SYNCS', 'HMMA', 'LDSM', 'REDG', 'ENL2.256', 'STL', 'LDL',
              'BAR.SYNC']
 
 

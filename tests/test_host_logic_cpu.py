@@ -598,6 +598,17 @@ def test_sparse_encoder_train_mode_on_the_emulator(monkeypatch):
             (yg * gout).sum().backward()
             r = (rel(yg, yr), rel(xg.grad, xr.grad), rel(mod.weight.grad, ref.weight.grad))
             assert max(r) < 2e-3, (subm, stride, order, r)
+            # the two weight-gradient paths (isf_spconv_wgrad's contract / gathered copies + one GEMM per kernel offset) agree
+            rb = mod.rulebook(sp.SparseConvTensor(feats, idx, [9, 24, 20], 2))
+            gh = gout.half()
+            both = []
+            for path in ('own', 'torch'):
+                monkeypatch.setattr(sp, 'WGRAD', path)
+                both.append(sp._weight_grad(feats.half(), gh, rb, rb.taps, cin, cout))
+            monkeypatch.setattr(sp, 'WGRAD', 'own')
+            assert rel(both[0], both[1]) < 1e-6 and float(both[1].abs().max()) > 0
+            offs = sp.pair_lists(rb)[5].tolist()
+            assert offs[0] == 0 and offs[-1] == sp.pair_lists(rb)[0].numel() and len(offs) == rb.taps + 1
     monkeypatch.setattr(sp, 'TILE_ORDER', 31)
     cfg = dict(in_channels=64, sparse_shape=[41, 64, 64], base_channels=32, output_channels=256,
                encoder_channels=((32, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256)),
