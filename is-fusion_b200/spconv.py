@@ -393,8 +393,8 @@ def _implicit_gemm(feats, rb, w_packed, cin, cout, scale=None, shift=None, resid
 #                   the transposed table is the table itself with the kernel offsets mirrored (o at offset k of i  <=>  i at offset
 #                   K-1-k of o), i.e. the forward launch with weights W'[k] = W[K-1-k]^T; for a strided conv the inverse table
 #                   inv[k][i] = o is scattered from the forward table once per rulebook (device-side index glue);
-#   weight gradient dW[k] = X[nbr[k]]^T . dout  (a gathered A^T B per kernel offset) runs on torch ops (index_select + matmul in
-#                   fp32): a library GEMM, not a kernel of this repository.
+#   weight gradient dW[k] = X[nbr[k]]^T . dout  (a gathered A^T B per kernel offset): isf_spconv_wgrad (csrc/wgrad.cu) over the
+#                   rulebook's pair lists; ISF_WGRAD=torch = index_select copies + one library GEMM per offset (the cross-check).
 # Mixed precision like the inference path: fp16 operands, fp32 accumulation, fp32 master weights and gradients.
 # ------------------------------------------------------------------------------------------------------------------
 def _slot_rows(rb):

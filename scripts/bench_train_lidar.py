@@ -9,7 +9,7 @@
 
 Prints one JSON line: step time (CUDA events, max over ranks), the share of the gradient all-reduce, gradient bytes.  What is NOT in
 the step: the camera branch, the fusion encoder, the head and its loss (no backward of those modules exists, DESIGN.md section 7);
-the weight gradient of the sparse convolutions runs on torch ops.
+the weight gradient of the sparse convolutions is isf_spconv_wgrad (ISF_WGRAD=torch: gathered copies + library GEMMs).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_train_lidar.py --frames 4"""
 import argparse
 import json

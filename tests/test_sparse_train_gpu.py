@@ -1,5 +1,5 @@
 """GPU: train mode of the sparse encoder: the implicit-GEMM kernels under autograd (spconv.ImplicitGemmFunction:
-data gradient = the forward kernel over the mirrored / inverse rulebook, weight gradient = gathered A^T B on torch ops), BatchNorm
+data gradient = the forward kernel over the mirrored / inverse rulebook, weight gradient = isf_spconv_wgrad, the fused gather + mma.sync kernel of csrc/wgrad.cu), BatchNorm
 with batch statistics, against autograd of the oracle's SparseEncoder (fp32) on the same inputs and weights."""
 import pytest
 import torch
