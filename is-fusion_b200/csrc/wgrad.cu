@@ -61,10 +61,15 @@ __global__ void __launch_bounds__(THREADS) wgrad_kernel(const __half* __restrict
   __half* gs = xs + STAGES * C::KST * C::PITCH;
   // blockIdx.x = kernel offset + taps * channel block (fastest), blockIdx.y = pair chunk: the CTAs in flight together work on the
   // same stretch of output sites under every kernel offset, i.e. on the same G rows and on neighbouring X rows -> they meet in L2
-  // (the first version walked chunk-fastest and read 4.2 GB from DRAM for 250 MB of operands, profiles/ncu_raw_wgrad_1_r02.csv)
+  // (the first version walked chunk-fastest and read 4.2 GB from DRAM for 275 MB of operands, profiles/ncu_raw_wgrad_1_r02.csv)
   const int tap = blockIdx.x % taps, blk = blockIdx.x / taps;
-  const int p_begin = tap_off[tap] + blockIdx.y * chunk;
-  const int p_end = min(tap_off[tap + 1], p_begin + chunk);
+  // every kernel offset is cut into gridDim.y chunks of ITS OWN pair count (chunk = the host's bound for the longest list): chunk c
+  // of every offset then covers about the same stretch of output sites, and no CTA of a short list is empty
+  const int t0 = tap_off[tap], n_k = tap_off[tap + 1] - t0;
+  int ck = min(chunk, (n_k + (int)gridDim.y - 1) / (int)gridDim.y);
+  ck = (ck + Cfg<B, WM, WN, KG, KPG, STAGES>::KST - 1) / Cfg<B, WM, WN, KG, KPG, STAGES>::KST * Cfg<B, WM, WN, KG, KPG, STAGES>::KST;
+  const int p_begin = t0 + blockIdx.y * ck;
+  const int p_end = min(t0 + n_k, p_begin + ck);
   if (p_begin >= p_end) return;
   const int nb = (cout + B - 1) / B;
   const int m0 = (blk / nb) * B, n0 = (blk % nb) * B;                     // channel block of this CTA
